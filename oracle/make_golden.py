@@ -1,0 +1,226 @@
+"""Generates tests/golden/*.pt by running the UNMODIFIED reference (imported from /root/reference).
+
+TEST INFRASTRUCTURE ONLY; runs in the build container only (the GPU box has no /root/reference).
+    python -m oracle.make_golden [case ...]
+
+For every case of tests/cases.py it builds the reference's own objects (ScoreCtrl/ClippedCtrl over
+FourierMLP/TimeEmbed, VP/PinnedBM/ScaledBM/ControlledLangevinSDE, GMM/PhiFour/LogisticRegression,
+the loss classes of sde_sampler/losses/oc.py), loads the case weights with ``load_state_dict``,
+replays the case's Brownian increments through ``torch.randn_like`` (the reference has no noise
+hook in ``simulate``: losses/oc.py:277,722,1372, eq/sdes.py:537,553,662) and stores x_T, rnd and
+the estimator values.  Fixtures hold OUTPUTS only (a few KB each); inputs are regenerated from the
+case seed by tests/cases.py.  Import recipe: SURVEY.md 8c (torchquad / torchsde are imported by the
+reference at module top but unused on this path, so they are stubbed; nothing else is patched).
+"""
+from __future__ import annotations
+
+import math
+import os
+import sys
+import types
+
+import torch
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, REPO)
+REFERENCE = "/root/reference"
+
+
+def import_reference():
+    for name, attrs in (("torchquad", ["Boole"]), ("torchsde", ["BaseBrownian", "BrownianInterval"])):
+        if name not in sys.modules:
+            m = types.ModuleType(name)
+            for a in attrs:
+                setattr(m, a, type(a, (), {}))
+            sys.modules[name] = m
+    if REFERENCE not in sys.path:
+        sys.path.insert(0, REFERENCE)
+    import sde_sampler.distr.delta  # noqa: F401
+    import sde_sampler.distr.gauss  # noqa: F401
+    import sde_sampler.distr.logistic_regression  # noqa: F401
+    import sde_sampler.distr.phi_four  # noqa: F401
+    import sde_sampler.eq.sdes  # noqa: F401
+    import sde_sampler.losses.oc  # noqa: F401
+    import sde_sampler.models.mlp  # noqa: F401
+    import sde_sampler.models.reparam  # noqa: F401
+    import sde_sampler
+    return sde_sampler
+
+
+class ReplayNoise:
+    """Temporarily makes torch.randn_like return the recorded increments, one per call."""
+
+    def __init__(self, noise):
+        self.noise, self.i = noise, 0
+
+    def __enter__(self):
+        self._orig = torch.randn_like
+
+        def fake(x, *a, **k):
+            z = self.noise[self.i]
+            assert z.shape == x.shape
+            self.i += 1
+            return z.clone()
+        torch.randn_like = fake
+        return self
+
+    def __exit__(self, *exc):
+        torch.randn_like = self._orig
+
+
+def build_reference_target(ss, tgt):
+    from sde_sampler.distr.gauss import GMM
+    from sde_sampler.distr.logistic_regression import LogisticRegression
+    from sde_sampler.distr.phi_four import PhiFour
+    if tgt["kind"] == "gmm":
+        return GMM(dim=tgt["loc"].shape[1], loc=tgt["loc"].clone(), scale=tgt["scale"].clone(),
+                   mixture_weights=tgt["weights"].clone(), n_reference_samples=10)
+    if tgt["kind"] == "phi4":
+        return PhiFour(a=tgt["a"], b=tgt["b"], dim=tgt["dim"], beta=tgt["beta"])
+    if tgt["kind"] == "logreg":
+        t = LogisticRegression(dim=61, data_type="sonar", intercept_mean=tgt["intercept_mean"],
+                               intercept_scale=tgt["intercept_scale"], weight_scale=tgt["weight_scale"])
+        # synthetic-shape data instead of the pickled dataset; priors rebuilt for the new width
+        p = tgt["X"].shape[1]
+        t.X_train, t.y_train = tgt["X"].clone(), tgt["y"].clone()
+        t.dim = p + 1
+        t.weights_prior = torch.distributions.Independent(
+            torch.distributions.Normal(torch.zeros(p), t.weight_scale * torch.ones(p)), 1)
+        return t
+    raise ValueError(tgt["kind"])
+
+
+def build_reference_ctrl(c, d, target_score):
+    from sde_sampler.models.mlp import FourierMLP, TimeEmbed
+    from sde_sampler.models.reparam import ClippedCtrl, ScoreCtrl
+    num_hidden = sum(1 for k in c["sd"] if k.startswith("base_model.hidden_layer.") and k.endswith(".weight"))
+    base = FourierMLP(dim=d, activation=torch.nn.GELU(), num_layers=num_hidden + 2, channels=64)
+    if c["kind"] == "score":
+        m = ScoreCtrl(base_model=base, score_model=TimeEmbed(dim_out=1, activation=torch.nn.GELU(), num_layers=4,
+                                                             channels=64),
+                      target_score=target_score, detach_score=False, clip_score=c["clip_score"],
+                      clip_model=c["clip_model"], scale_score=c["scale_score"])
+    else:
+        m = ClippedCtrl(base_model=base, clip_model=c["clip_model"])
+    missing, unexpected = m.load_state_dict({k: v.clone() for k, v in c["sd"].items()}, strict=True)
+    assert not missing and not unexpected
+    return m.eval()
+
+
+def build_reference_sde(s):
+    from sde_sampler.eq.sdes import VP, PinnedBM, ScaledBM
+    if s["kind"] == "vp":
+        return VP(diff_coeff_sq_min=s["beta_min"], diff_coeff_sq_max=s["beta_max"], scale_diff_coeff=s["scale"],
+                  terminal_t=s["T"])
+    if s["kind"] == "pbm":
+        return PinnedBM(diff_coeff=s["diff"], terminal_t=s["T"])
+    return ScaledBM(diff_coeff=s["diff"], terminal_t=s["T"])
+
+
+def run_reference(case):
+    """Returns dict(x_T, rnd[, xs_last]) from the reference for the case."""
+    from sde_sampler.distr.gauss import Gauss, IsotropicGauss
+    from sde_sampler.eq.sdes import ControlledLangevinSDE
+    from sde_sampler.losses import oc
+    from tests.cases import initial_state, noise_for
+    p = case["problem"]
+    target = build_reference_target(None, p["target"])
+    d = target.dim
+    ctrl = build_reference_ctrl(p["ctrl"], d, target.score)
+    x0 = initial_state(case)
+    noise = noise_for(case)
+    ts = p["ts"].clone()
+    method = p["method"]
+    clip_t = p.get("clip_target")
+
+    def target_logp(x):  # TrainableDiff.clipped_target_unnorm_log_prob, solver/oc.py:80-87
+        out = target.unnorm_log_prob(x)
+        return out if clip_t is None else out.clip(-clip_t, clip_t)
+
+    kw = dict(generative_ctrl=ctrl, generative_ctrl_ema=ctrl, method="lv", max_rnd=1e8)
+    with torch.no_grad(), ReplayNoise(noise) as rp:
+        if method in ("em", "ei", "ddpm"):
+            sde = build_reference_sde(p["sde"])
+            ref = p["ref"]
+            if ref["kind"] == "gauss":  # RDS.change_reference_type('gaussian'), solver/oc.py:552-563
+                utils = {"x_init": ref["mean"].clone(), "var_init": ref["var"].clone()}
+                ref_ctrl = lambda t, x: sde.marginal_score(t=t, x=x, **utils)  # noqa: E731
+                ref_distr = sde.marginal_distr(t=torch.tensor(0.0), **utils)
+            elif ref["kind"] == "gmm":  # solver/oc.py:564-576
+                utils = {"means_init": ref["means"].clone(), "variances_init": ref["variances"].clone(),
+                         "weights_init": ref["weights"].clone()}
+                ref_ctrl = lambda t, x: sde.marginal_gmm_score(t=t, x=x, **utils)  # noqa: E731
+                ref_distr = sde.marginal_gmm_distr(t=torch.tensor(0.0), **utils)
+            else:  # PIS.setup_models, solver/oc.py:363-365
+                ref_ctrl = None
+                ref_distr = sde.marginal_distr(t=sde.terminal_t, x_init=ref["loc"].clone())
+            cls = {"em": oc.EMReferenceSDELoss, "ei": oc.EIReferenceSDELoss, "ddpm": oc.DDPMLikeReferenceSDELoss}[method]
+            loss = cls(sde=sde, reference_ctrl=ref_ctrl, **kw)
+            if case.get("eubo"):
+                rnd = loss.compute_eubo(ts, x0.clone(), target_logp, ref_distr.log_prob)
+                out = {"rnd": rnd}
+            else:
+                x, rnd, xs = loss.simulate(ts, x0, target_logp, ref_distr.log_prob, return_traj=True)
+                out = {"x_T": x, "rnd": rnd, "xs_mid": xs[len(xs) // 2]}
+        elif method == "dds":
+            prior = IsotropicGauss(dim=d, loc=p["ref"]["loc"], scale=p["ref"]["scale"])
+            loss = oc.ExponentialIntegratorSDELoss(alpha=p["alpha"], sigma=p["sigma"], sde=None, **kw)
+            x, rnd, xs = loss.simulate(ts, x0, target_logp, prior.log_prob,
+                                       compute_ito_int=case.get("compute_ito_int", True), return_traj=True)
+            out = {"x_T": x, "rnd": rnd, "xs_mid": xs[len(xs) // 2]}
+        elif method == "cmcd":
+            pr = p["prior"]
+            if pr.get("isotropic"):
+                prior = IsotropicGauss(dim=d, loc=float(pr["loc"][0]), scale=float(pr["scale"][0]))
+            else:
+                prior = Gauss(dim=d, loc=pr["loc"].clone(), scale=pr["scale"].clone())
+            sde = ControlledLangevinSDE(target_score=target.score, prior_score=prior.score, diff_coeff=p["diff"],
+                                        terminal_t=p["T"], clip_score=p["clip_score"])
+            kw2 = dict(kw)
+            kw2["max_rnd"] = None
+            loss = oc.ControlledLangevinSDELoss(sde=sde, **kw2)
+            if case.get("eubo"):
+                rnd = loss.compute_eubo(ts, x0.clone(), target_logp, prior.log_prob)
+                out = {"rnd": rnd}
+            else:
+                x, rnd, xs = loss.simulate(ts, x0, target_logp, prior.log_prob, train=False, return_traj=True)
+                out = {"x_T": x, "rnd": rnd, "xs_mid": xs[len(xs) // 2]}
+        else:
+            raise ValueError(method)
+        assert rp.i == len(noise), (rp.i, len(noise))
+    rnd = out["rnd"]
+    if case.get("eubo"):
+        from sde_sampler.additions.hacking import evaluate_eubo  # noqa: F401  (formulas restated below)
+        neg = -rnd
+        w = torch.softmax(neg, dim=0)
+        out["metrics"] = {"eval/log_norm_const_is_f": -rnd.logsumexp(dim=0).item() + math.log(len(w)),
+                          "eval/eubo": neg.mean().item(),
+                          "eval/effective_sample_size_f": (1.0 / (w ** 2).sum()).item()}
+    else:
+        res = oc.BaseOCLoss.compute_results(rnd, compute_weights=True)
+        m = dict(res.metrics)
+        m.update(res.log_norm_const_preds)
+        w = res.weights
+        m["eval/effective_sample_size"] = (w.sum() ** 2 / (w ** 2).sum()).item()  # eval/metrics.py:134-140
+        out["metrics"] = m
+    return {k: (v.detach().clone() if isinstance(v, torch.Tensor) else v) for k, v in out.items()}
+
+
+def main(argv):
+    from tests.cases import CASES
+    import_reference()
+    names = argv or list(CASES)
+    os.makedirs(os.path.join(REPO, "tests", "golden"), exist_ok=True)
+    for name in names:
+        case = CASES[name]()
+        out = run_reference(case)
+        out["torch_version"] = str(torch.__version__)
+        path = os.path.join(REPO, "tests", "golden", name + ".pt")
+        torch.save(out, path)
+        r = out["rnd"]
+        print(f"{name:24s} rnd mean {r.mean():+.4e} std {r.std():.3e} finite {bool(torch.isfinite(r).all())} "
+              f"| {', '.join(f'{k}={v:.5g}' for k, v in out['metrics'].items())} | {os.path.getsize(path)} B")
+
+
+if __name__ == "__main__":
+    main(sys.argv[1:])

@@ -1,0 +1,288 @@
+"""Neutral, seed-driven descriptions of the rollout problems used by the parity tests.
+
+A *problem* is a plain dict of python scalars and float32 torch tensors (no classes) that three
+independent builders consume: the reference (``oracle/make_golden.py``, build container only),
+the oracle (``oracle.rollout_oracle.rollout``) and the product (``tests/product_builders.py``).
+Shapes follow BASELINE.json's configs; batches are small so the CPU oracle finishes
+in seconds, and B is deliberately not a multiple of the 128-particle tile.
+
+Weights: every Linear is drawn U(+-1/sqrt(fan_in)) like nn.Linear's default, INCLUDING the last
+layers (the reference zero-inits those at scale 1e-6, models/utils.py:7-22, which would make the
+control ~0 and the test vacuous); ``out_gain``/``gamma`` scale the control so that trajectories
+stay in a numerically sane range.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+
+C = 64  # FourierMLP / TimeEmbed channels (conf/model/base/fouriermlp.yaml, time_embed.yaml)
+
+
+def _lin(g, out_f, in_f, gain=1.0):
+    b = gain / math.sqrt(in_f)
+    w = (torch.rand(out_f, in_f, generator=g) * 2 - 1) * b
+    bias = (torch.rand(out_f, generator=g) * 2 - 1) * b
+    return w, bias
+
+
+def ctrl_state_dict(d: int, kind: str, seed: int, out_gain: float = 1.0, gamma: float = 0.3,
+                    num_hidden: int = 2) -> dict:
+    """state_dict with the key names of ScoreCtrl/ClippedCtrl(FourierMLP[, TimeEmbed]) in the reference."""
+    g = torch.Generator().manual_seed(seed)
+    sd = {}
+
+    def put(name, w, b):
+        sd[name + ".weight"], sd[name + ".bias"] = w, b
+    put("base_model.input_embed", *_lin(g, C, d))
+    sd["base_model.timestep_embed.timestep_phase"] = torch.randn(1, C, generator=g)
+    put("base_model.timestep_embed.hidden_layer.0", *_lin(g, C, 2 * C))
+    put("base_model.timestep_embed.out_layer", *_lin(g, C, C))
+    for i in range(num_hidden):
+        put(f"base_model.hidden_layer.{i}", *_lin(g, C, C))
+    put("base_model.out_layer", *_lin(g, d, C, gain=out_gain))
+    if kind == "score":
+        sd["score_model.timestep_phase"] = torch.randn(1, C, generator=g)
+        put("score_model.hidden_layer.0", *_lin(g, C, 2 * C))
+        put("score_model.hidden_layer.1", *_lin(g, C, C))
+        put("score_model.hidden_layer.2", *_lin(g, C, C))
+        w, b = _lin(g, 1, C, gain=gamma)
+        put("score_model.out_layer", w, b + gamma)
+    return sd
+
+
+def ctrl(d, kind, seed, **kw):
+    return {"kind": kind, "sd": ctrl_state_dict(d, kind, seed, **kw), "clip_model": 1e4,
+            "clip_score": 1e4 if kind == "score" else None, "scale_score": 1.0}
+
+
+# ---- targets (parameters restated from the reference constructors) --------------------------
+
+
+def two_modes(dim=2, a=1.0, ill="medium"):
+    """TwoModes, distr/gauss.py:422-453."""
+    w = torch.tensor([2.0, 1.0])
+    loc = torch.stack([-a * torch.ones(dim), a * torch.ones(dim)])
+    if ill == "medium":
+        scale = torch.sqrt(0.05 * torch.logspace(-1, 0.0, dim)).unsqueeze(0).expand(2, -1).contiguous()
+    elif ill == "hard":
+        scale = torch.sqrt(0.05 * torch.logspace(-2.0, 0.0, dim)).unsqueeze(0).expand(2, -1).contiguous()
+    else:
+        scale = torch.sqrt(0.05 * torch.ones_like(loc))
+    return {"kind": "gmm", "loc": loc, "scale": scale, "weights": w}
+
+
+def many_modes(n_modes=16, dim=50, seed_loc=42, factor=3.0, var=0.5):
+    """ManyModes, distr/gauss.py:569-594."""
+    g = torch.Generator().manual_seed(seed_loc)
+    w = torch.logspace(0.0, 1.0, n_modes, base=factor)
+    loc = 2 * n_modes * torch.rand((n_modes, dim), generator=g) - n_modes
+    scale = torch.sqrt(var * torch.ones_like(loc))
+    return {"kind": "gmm", "loc": loc, "scale": scale, "weights": w}
+
+
+def phi4(dim=100, a=0.1, b=0.0, beta=20.0):
+    return {"kind": "phi4", "a": a, "b": b, "beta": beta, "dim": dim}
+
+
+def logreg_synthetic(n=166, p=60, seed=7, weight_scale=4.5, intercept_mean=-2.5, intercept_scale=0.5):
+    """Synthetic-shape twin of data/sonar.pkl (166x60) / ionosphere.pkl (280x33): X~U(0,1), y~Bern(1/2)
+    (BASELINE.json config 4); prior scales from conf/target/{sonar,ionosphere}.yaml."""
+    g = torch.Generator().manual_seed(seed)
+    X = torch.rand(n, p, generator=g)
+    y = (torch.rand(n, generator=g) < 0.5).float()
+    return {"kind": "logreg", "X": X, "y": y, "weight_scale": weight_scale,
+            "intercept_mean": intercept_mean, "intercept_scale": intercept_scale, "dim": p + 1}
+
+
+VP10 = {"kind": "vp", "beta_min": 0.1, "beta_max": 10.0, "scale": 1.0, "T": 1.0}
+VP20 = {"kind": "vp", "beta_min": 0.1, "beta_max": 20.0, "scale": 1.0, "T": 1.0}
+PBM = {"kind": "pbm", "diff": 0.4472135954999579, "T": 5.0}
+BM = {"kind": "bm", "diff": 0.4472135954999579, "T": 5.0}
+
+
+def uniform_ts(T, K, start=0.0):
+    return torch.linspace(start, T, K + 1)
+
+
+def cosine_ts(end=6.4, dt=0.05):
+    """get_timesteps(rescale_t='cosine'), utils/common.py:63-81, as DDS uses it (conf/solver/dds.yaml)."""
+    steps = int(math.ceil(end / dt))
+    s = 0.008
+    pre = torch.linspace(0.0, end, steps + 1) / end
+    dts = torch.cos(((pre + s) / (1 + s)) * torch.pi * 0.5) ** 4
+    dts = dts / dts.sum() * end
+    return torch.concat((torch.tensor([0.0]), torch.cumsum(dts, -1)))
+
+
+def snr_ts_vp(sde: dict, K: int):
+    """snr-uniform grid for VP (utils/common.py:44-56): start 1e-4, end T-1e-4 (benchmark_utils.py:188-189).
+    Computed by 1024-step bisection in float32 exactly like the reference formulas."""
+    bmin, bmax, T, c = (torch.tensor(sde[k]) for k in ("beta_min", "beta_max", "T", "scale"))
+
+    def log_snr(t):
+        a = torch.exp(-0.5 * (bmin * t + (0.5 * t ** 2 / T) * (bmax - bmin)))
+        return torch.log(torch.square(a) / (torch.square(a) * (-c ** 2 * (1.0 - (1.0 / a ** 2)))))
+    start, end = 1e-4, float(T) - 1e-4
+    rng = torch.linspace(log_snr(torch.tensor(start)), log_snr(torch.tensor(end)), steps=K + 1)[1:-1]
+    low, high = start, end
+    for _ in range(1024):
+        mid = (low + high) / 2.0
+        ret = log_snr(mid if isinstance(mid, torch.Tensor) else torch.tensor(mid))
+        low = torch.where(ret > rng, mid, low)
+        high = torch.where(ret <= rng, mid, high)
+    mid = (low + high) / 2.0
+    return torch.concat([torch.FloatTensor([start]), mid, torch.FloatTensor([end])]).sort().values
+
+
+# ---- cases ---------------------------------------------------------------------------------
+
+
+def case_em_two_modes(ctrl_kind="score"):
+    """BASELINE config 1: TwoModes 2-D, RDS vp-ref (VP 0.1..10), gaussian ref, EM, K=100."""
+    d = 2
+    return {
+        "problem": {"method": "em", "sde": VP10, "ts": uniform_ts(1.0, 100), "target": two_modes(d),
+                    "ctrl": ctrl(d, ctrl_kind, seed=11, out_gain=1.0, gamma=0.2),
+                    "ref": {"kind": "gauss", "mean": torch.zeros(d), "var": 1.5 * torch.ones(d)}},
+        "B": 200, "seed": 101, "prior": ("iso", 0.0, 1.0)}
+
+
+def case_ei_many_modes(K=200, B=200, d=50, M=16):
+    """BASELINE config 2: ManyModes d=50 (16 modes), RDS vp-ref beta_max=20, GMM ref, EI, K=200, ScoreCtrl."""
+    tgt = many_modes(M, d)
+    ref = {"kind": "gmm", "means": tgt["loc"] + 0.1, "variances": 1.2 * tgt["scale"] ** 2,
+           "weights": tgt["weights"].clone()}
+    return {
+        "problem": {"method": "ei", "sde": VP20, "ts": uniform_ts(1.0, K), "target": tgt,
+                    "ctrl": ctrl(d, "score", seed=12, out_gain=1.0, gamma=0.05), "ref": ref},
+        "B": B, "seed": 102, "prior": ("iso", 0.0, 1.0)}
+
+
+def case_ddpm_snr():
+    """DDPM-like integrator on an snr grid (API parity), TwoModes d=5, GMM ref."""
+    d = 5
+    tgt = two_modes(d)
+    ref = {"kind": "gmm", "means": tgt["loc"] * 0.9, "variances": 2.0 * tgt["scale"] ** 2,
+           "weights": torch.tensor([1.0, 1.0])}
+    return {
+        "problem": {"method": "ddpm", "sde": VP10, "ts": snr_ts_vp(VP10, 50), "target": tgt,
+                    "ctrl": ctrl(d, "score", seed=13, out_gain=0.5, gamma=0.002), "ref": ref},
+        "B": 130, "seed": 103, "prior": ("iso", 0.0, 1.0)}
+
+
+def case_ei_pbm():
+    """pbm-ref: PinnedBM, Delta prior, start 1e-4 (conf/solver/pbm_rds.yaml), default reference
+    (solver/oc.py:539-545: x_init = prior.loc, var_init = T sigma^2), EI, ManyModes d=8 M=4, ClippedCtrl."""
+    d = 8
+    return {
+        "problem": {"method": "ei", "sde": PBM, "ts": uniform_ts(5.0 - 1e-4, 64, start=1e-4),
+                    "target": many_modes(4, d, var=0.5), "ctrl": ctrl(d, "clipped", seed=14, out_gain=0.5),
+                    "ref": {"kind": "gauss", "mean": torch.zeros(d), "var": 5.0 * 0.4472135954999579 ** 2 * torch.ones(d)}},
+        "B": 150, "seed": 104, "prior": ("delta", 0.0)}
+
+
+def case_pis_phi4(K=256, B=64):
+    """BASELINE config 3 (PIS): PhiFour d=100, ScaledBM sigma=sqrt(.2) T=5, Delta prior, EM, K=256."""
+    d = 100
+    return {
+        "problem": {"method": "em", "sde": BM, "ts": uniform_ts(5.0, K), "target": phi4(d),
+                    "ctrl": ctrl(d, "score", seed=15, out_gain=0.3, gamma=0.004),
+                    "ref": {"kind": "pis", "loc": torch.zeros(d)}},
+        "B": B, "seed": 105, "prior": ("delta", 0.0)}
+
+
+def case_dds_phi4(compute_ito_int=True, B=64):
+    """BASELINE config 3 (DDS): PhiFour d=100, alpha=sigma=1, cosine grid dt=.05 end 6.4 (K=128)."""
+    d = 100
+    return {
+        "problem": {"method": "dds", "sde": None, "alpha": 1.0, "sigma": 1.0, "ts": cosine_ts(6.4, 0.05),
+                    "target": phi4(d), "ctrl": ctrl(d, "score", seed=16, out_gain=0.3, gamma=0.004),
+                    "ref": {"kind": "iso", "loc": 0.0, "scale": 1.0}},
+        "B": B, "seed": 106, "prior": ("iso", 0.0, 1.0), "compute_ito_int": compute_ito_int}
+
+
+def case_cmcd_logreg(n=166, p=60, K=32, B=96, ctrl_kind="score"):
+    """BASELINE config 4: CMCD, sigma=1 T=1 clip 1e5, prior N(0, 5^2 I), logistic regression (sonar shape)."""
+    tgt = logreg_synthetic(n, p)
+    d = p + 1
+    return {
+        "problem": {"method": "cmcd", "sde": None, "diff": 1.0, "T": 1.0, "clip_score": 1e5,
+                    "ts": uniform_ts(1.0, K), "target": tgt,
+                    "ctrl": ctrl(d, ctrl_kind, seed=17, out_gain=0.5, gamma=0.02),
+                    "prior": {"loc": torch.zeros(d), "scale": 5.0 * torch.ones(d), "isotropic": True}},
+        "B": B, "seed": 107, "prior": ("iso", 0.0, 5.0)}
+
+
+def case_cmcd_gmm():
+    """CMCD on a GMM target with a fitted diagonal Gaussian prior (CMCD.update_prior, solver/oc.py:291-303)."""
+    d = 8
+    tgt = many_modes(4, d, var=0.5)
+    g = torch.Generator().manual_seed(5)
+    return {
+        "problem": {"method": "cmcd", "sde": None, "diff": 1.0, "T": 1.0, "clip_score": 1e5,
+                    "ts": uniform_ts(1.0, 48), "target": tgt, "ctrl": ctrl(d, "clipped", seed=18, out_gain=0.5),
+                    "prior": {"loc": 0.3 * torch.randn(d, generator=g), "scale": 2.0 + torch.rand(d, generator=g),
+                              "isotropic": False}},
+        "B": 140, "seed": 108, "prior": ("gauss",)}
+
+
+def _eubo(case, seed):
+    case = dict(case)
+    case["eubo"] = True
+    case["seed"] = seed
+    return case
+
+
+CASES = {
+    "em_two_modes_score": lambda: case_em_two_modes("score"),
+    "em_two_modes_clipped": lambda: case_em_two_modes("clipped"),
+    "ei_many_modes": lambda: case_ei_many_modes(),
+    "ddpm_snr": case_ddpm_snr,
+    "ei_pbm": case_ei_pbm,
+    "pis_phi4": lambda: case_pis_phi4(),
+    "dds_phi4_ito": lambda: case_dds_phi4(True),
+    "dds_phi4_noito": lambda: case_dds_phi4(False),
+    "cmcd_logreg_sonar": lambda: case_cmcd_logreg(166, 60),
+    "cmcd_logreg_iono": lambda: case_cmcd_logreg(280, 33, ctrl_kind="clipped"),
+    "cmcd_gmm": case_cmcd_gmm,
+    "eubo_em_two_modes": lambda: _eubo(case_em_two_modes("score"), 201),
+    "eubo_ei_many_modes": lambda: _eubo(case_ei_many_modes(K=100, B=100), 202),
+    "eubo_cmcd_gmm": lambda: _eubo(case_cmcd_gmm(), 203),
+}
+
+
+def initial_state(case: dict, dtype=torch.float32):
+    """x0 for the case: prior samples for a generative rollout (drawn with the Philox stream 1 of
+    oracle.philox_ref so that no torch-generator state is involved), target-shaped samples for EUBO."""
+    from oracle import philox_ref
+    p = case["problem"]
+    d = p["target"]["loc"].shape[1] if p["target"]["kind"] == "gmm" else p["target"]["dim"]
+    B = case["B"]
+    z = torch.from_numpy(philox_ref.normals(case["seed"], B, 1, d, stream=philox_ref.STREAM_PRIOR)[0]).to(dtype)
+    if case.get("eubo"):
+        tgt = p["target"]
+        if tgt["kind"] == "gmm":  # exact GMM samples: component by inverse-cdf on a Philox uniform-ish draw
+            w = tgt["weights"] / tgt["weights"].sum()
+            u = torch.from_numpy(philox_ref.normals(case["seed"] + 1, B, 1, 1, stream=philox_ref.STREAM_PRIOR)[0, :, 0])
+            u = 0.5 * (1 + torch.erf(u.double() / math.sqrt(2))).float()
+            comp = torch.searchsorted(torch.cumsum(w, 0), u.clamp(max=1 - 1e-6))
+            return (tgt["loc"][comp] + tgt["scale"][comp] * z).to(dtype)
+        return z
+    kind = case["prior"][0]
+    if kind == "delta":
+        return torch.full((B, d), float(case["prior"][1]), dtype=dtype)
+    if kind == "iso":
+        return (case["prior"][1] + case["prior"][2] * z).to(dtype)
+    if kind == "gauss":
+        return (p["prior"]["loc"] + p["prior"]["scale"] * z).to(dtype)
+    raise ValueError(kind)
+
+
+def noise_for(case: dict, dtype=torch.float32):
+    from oracle import philox_ref
+    p = case["problem"]
+    d = p["target"]["loc"].shape[1] if p["target"]["kind"] == "gmm" else p["target"]["dim"]
+    K = len(p["ts"]) - 1
+    return torch.from_numpy(philox_ref.normals(case["seed"], case["B"], K, d)).to(dtype)
