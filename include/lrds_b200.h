@@ -1,0 +1,210 @@
+/*
+ * lrds_b200.h - C ABI of the B200-native batched trajectory rollout of sde_sampler_lrds.
+ *
+ * The reference has no FFI: its seam is the Python method contract of the loss objects in
+ * sde_sampler/losses/oc.py.  Every entry point below names the reference
+ * interface it replaces.  All pointers are DEVICE pointers unless stated otherwise, all
+ * matrices row-major float32, `stream` is a cudaStream_t.  Calls are asynchronous on `stream`,
+ * never allocate, never throw; they return LRDS_OK or a negative lrds_status (message via
+ * lrds_last_error()).  One call per GPU; re-entrant across streams and devices.
+ */
+#ifndef LRDS_B200_H
+#define LRDS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LRDS_ABI_VERSION 1
+#define LRDS_CHANNELS 64 /* FourierMLP / TimeEmbed width, conf/model/base/fouriermlp.yaml:4 */
+
+typedef enum {
+  LRDS_OK = 0,
+  LRDS_ERR_INVALID = -1,     /* bad argument / inconsistent spec */
+  LRDS_ERR_UNSUPPORTED = -2, /* valid in the reference but not built here (no silent fallback) */
+  LRDS_ERR_CUDA = -3,        /* CUDA runtime error, see lrds_last_error() */
+  LRDS_ERR_RESOURCES = -4    /* per-particle state does not fit in shared memory */
+} lrds_status;
+
+/* Which loop of losses/oc.py runs. */
+typedef enum {
+  LRDS_ROLLOUT_LINEAR = 0,     /* EM/EI/DDPM-like/DDS simulate: oc.py:218-296, 444-510, 584-651, 1319-1397 */
+  LRDS_ROLLOUT_CMCD = 1,       /* ControlledLangevinSDELoss.simulate, oc.py:666-755 */
+  LRDS_ROLLOUT_EUBO_LINEAR = 2,/* EM/EI compute_eubo, oc.py:298-362, 512-568 */
+  LRDS_ROLLOUT_EUBO_CMCD = 3   /* ControlledLangevinSDELoss.compute_eubo, oc.py:757-828 */
+} lrds_rollout_kind;
+
+/* State update of one LINEAR step (u = control, r = reference score, z ~ N(0,I)). */
+typedef enum {
+  LRDS_UPDATE_AXPY = 0, /* x' = (a x + b (r + u)) + c z       EI/DDPM: eq/sdes.py:532-555, 658-678; DDS: oc.py:1373-1377 */
+  LRDS_UPDATE_EM = 1    /* x' = x + ((-(f x) + s2 r) + sig u) dt + sig (z sqrt_dt)   oc.py:277-281 */
+} lrds_update_form;
+
+/* Ito (martingale) term of one LINEAR step. */
+typedef enum {
+  LRDS_ITO_NONE = 0,   /* DDS with compute_ito_int=False, oc.py:1380 */
+  LRDS_ITO_SCALED = 1, /* rnd += w_ito * sum(u z)                 oc.py:499, 639 */
+  LRDS_ITO_EM = 2,     /* rnd += sum(u * (z * sqrt_dt))           oc.py:277, 284 */
+  LRDS_ITO_DDS = 3     /* rnd += sum(((sig u) z) * beta_k)        oc.py:1381-1383 (sig in A, beta_k in W_ITO) */
+} lrds_ito_form;
+
+typedef enum {
+  LRDS_CTRL_CLIPPED = 0, /* ClippedCtrl.forward, models/reparam.py:33-43 (base_zero_init) */
+  LRDS_CTRL_SCORE = 1    /* ScoreCtrl.forward, models/reparam.py:112-117 (target_informed_zero_init) */
+} lrds_ctrl_kind;
+
+typedef enum {
+  LRDS_DISTR_NONE = 0,
+  LRDS_DISTR_GMM = 1,   /* diagonal Gaussian / mixture: distr/gauss.py:67-73, 97-107, 124-126, 202-221 */
+  LRDS_DISTR_PHI4 = 2,  /* PhiFour U / grad_U, distr/phi_four.py:45-96 (dim_phys=1, Dirichlet-0) */
+  LRDS_DISTR_LOGREG = 3 /* LogisticRegression.posterior_log_prob + its autograd score, distr/logistic_regression.py:41-61 */
+} lrds_distr_kind;
+
+typedef enum {
+  LRDS_PRECISION_FP32_SIMT = 0, /* FFMA everywhere (parity anchor) */
+  LRDS_PRECISION_TF32X3 = 1,    /* tcgen05 kind::tf32, 3-pass split: fp32-equivalent drift MLP */
+  LRDS_PRECISION_BF16 = 2       /* tcgen05 kind::f16 single pass: reduced-precision fast mode, reported separately */
+} lrds_precision;
+
+/* Per-step table: one row of `step_stride` floats per grid time (K rows; K+1 for the CMCD kinds, whose
+ * row k describes time ts[k]).  The host fills it with the reference's own float32 scalar formulas
+ * (eq/sdes.py) so that schedules agree bit for bit.  Offsets into a row: */
+enum {
+  LRDS_STEP_A = 0,       /* AXPY: a          | EM: drift coefficient f(tau)      | DDS ito: see LRDS_ITO_DDS */
+  LRDS_STEP_B = 1,       /* AXPY: b          | EM: sigma(tau)                                              */
+  LRDS_STEP_C = 2,       /* AXPY: c          | EM: sigma(tau)^2                                            */
+  LRDS_STEP_DT = 3,      /* t - s                                                                         */
+  LRDS_STEP_SQRT_DT = 4, /* sqrt(t - s)                                                                   */
+  LRDS_STEP_W_COST = 5,  /* rnd += W_COST * sum(u^2): 0.5*omega (EI), 0.5*dt (EM), 0.5*beta_k^2 sigma^2 (DDS) */
+  LRDS_STEP_W_ITO = 6,   /* sqrt(omega) (EI/DDPM), beta_k (DDS)                                            */
+  LRDS_STEP_GAMMA = 7,   /* clip(score_model(tau)) of ScoreCtrl, models/reparam.py:101-110                 */
+  LRDS_STEP_FRAC = 8,    /* CMCD: t / terminal_t, eq/sdes.py:103                                           */
+  LRDS_STEP_SIGU = 9,    /* DDS ito: sigma                                                                 */
+  LRDS_STEP_EU_A = 10,   /* EUBO: mean factor                                                              */
+  LRDS_STEP_EU_B = 11,   /* EUBO: std factor                                                               */
+  LRDS_STEP_EU_C = 12,   /* EUBO-EM: 1/mean - 1 + f(tau) dt ; EUBO ito weight in W_ITO                      */
+  LRDS_STEP_BIAS1 = 16,  /* 64 floats: input_embed.bias + TimeEmbed_2(tau), models/mlp.py:136-139           */
+  LRDS_STEP_STRIDE = 80
+};
+
+/* Drift backbone FourierMLP (models/mlp.py:99-143), weights pre-transposed so that the 64 outputs of one
+ * input feature are contiguous. */
+typedef struct {
+  int32_t d;            /* particle dimension */
+  int32_t d_pad;        /* d rounded up to a multiple of 8 */
+  int32_t num_hidden;   /* hidden 64x64 layers (num_layers - 2) */
+  int32_t reserved;
+  const float* w_in_t;  /* [d][64]            input_embed.weight^T */
+  const float* w_hid_t; /* [num_hidden][64][64] hidden_layer[i].weight^T */
+  const float* b_hid;   /* [num_hidden][64] */
+  const float* w_out_t; /* [64][d_pad]        out_layer.weight^T, zero padded */
+  const float* b_out;   /* [d_pad] */
+  const void* tc_image; /* optional packed tensor-core image from lrds_pack_mlp_tc (LRDS_PRECISION_TF32X3/BF16) */
+} lrds_mlp;
+
+/* Diagonal Gaussian mixture with M >= 1 components.  `step_stride_*` = 0 for a static distribution; for the
+ * time-marginal reference p_t^ref (eq/sdes.py:208-248, 281-345) the arrays hold one block per step and the
+ * strides are the element distance between consecutive steps. */
+typedef struct {
+  int32_t M;
+  int32_t reserved;
+  const float* logc; /* [M]    log w_m - d/2 log(2 pi) - 1/2 sum_j log var_mj   (w normalised) */
+  const float* mu;   /* [M][d] */
+  const float* ivar; /* [M][d] 1 / var */
+  int64_t step_stride_logc;
+  int64_t step_stride_param;
+} lrds_gmm;
+
+typedef struct {
+  float a, b, beta; /* conf/target/phi_four.yaml; coef = a * d */
+  float reserved;
+} lrds_phi4;
+
+typedef struct {
+  int32_t N, p;       /* data rows, features; d = p + 1 (intercept last) */
+  int32_t n_pad;      /* N rounded up to a multiple of 4 */
+  int32_t reserved;
+  const float* X;     /* [N][d_pad]   rows zero padded beyond p (for the gradient pass) */
+  const float* Xt;    /* [p][n_pad]   transposed, zero padded (for the logit pass) */
+  const float* y;     /* [n_pad] */
+  float weight_scale, intercept_mean, intercept_scale;
+  float threshold;    /* 1e-8, logistic_regression.py:27,56 */
+  float eps;          /* float32 machine eps used by probs_to_logits (2^-23) */
+  float reserved2;
+} lrds_logreg;
+
+typedef struct {
+  int32_t kind; /* lrds_distr_kind */
+  int32_t reserved;
+  lrds_gmm gmm;
+  lrds_phi4 phi4;
+  lrds_logreg logreg;
+} lrds_distr;
+
+typedef struct {
+  int32_t abi_version; /* LRDS_ABI_VERSION */
+  int32_t kind;        /* lrds_rollout_kind */
+  int32_t update_form; /* lrds_update_form (LINEAR kinds) */
+  int32_t ito_form;    /* lrds_ito_form    (LINEAR kinds) */
+  int32_t ctrl_kind;   /* lrds_ctrl_kind */
+  int32_t precision;   /* lrds_precision */
+  int32_t B, d, K;     /* particles on this GPU, dimension, steps */
+  int32_t has_ref_ctrl;/* LINEAR: reference_ctrl is not None (RDS yes, PIS/DDS no) */
+  float clip_model;    /* <= 0: no clip (models/reparam.py:25) */
+  float clip_score;    /* <= 0: no clip (models/reparam.py:79) */
+  float scale_score;   /* ScoreCtrl.scale_score */
+  float clip_target;   /* <= 0: none (TrainableDiff.clip_target, solver/oc.py:33,80-87) */
+  float cmcd_diff;     /* ControlledLangevinSDE.diff_coeff, eq/sdes.py:93 */
+  float cmcd_clip;     /* ControlledLangevinSDE.clip_score, <= 0: none */
+  const float* steps;  /* per-step table, LRDS_STEP_STRIDE floats per row */
+  lrds_mlp mlp;
+  lrds_distr target;   /* terminal_unnorm_log_prob + ScoreCtrl.target_score */
+  lrds_gmm ref_t;      /* time-marginal reference score (has_ref_ctrl), one block per step */
+  lrds_gmm ref_0;      /* reference_log_prob at the end of the rollout (LINEAR) / prior = initial_log_prob (CMCD) */
+} lrds_spec;
+
+/* ---- the rollout: replaces loss.simulate / loss.compute_eubo (losses/oc.py, callers solver/oc.py:305-632,
+ * additions/hacking.py:14-33).
+ *   x0       [B][d]   prior samples (EUBO kinds: target samples)
+ *   noise    [K][B][d] standard normals to consume (validation mode: the reference's own increments), or NULL
+ *            for production mode = in-kernel Philox4x32-10 keyed by (seed, particle_offset + b, step, j/4)
+ *   x_out    [B][d]   final states (may alias x0)          rnd_out [B] log-weights
+ *   traj_out [K+1][B][d] or NULL (return_traj)
+ */
+int lrds_rollout(const lrds_spec* spec, const float* x0, const float* noise, uint64_t seed,
+                 uint64_t particle_offset, float* x_out, float* rnd_out, float* traj_out, void* stream);
+
+/* ---- estimator partials: replaces BaseOCLoss.compute_results (oc.py:134-173), ESS (eval/metrics.py:134-140)
+ * and evaluate_eubo (additions/hacking.py:24-32).  Writes 8 doubles to `partials` (device):
+ *   [0] m = max(-rnd)  [1] sum exp(-rnd - m)  [2] sum exp(2(-rnd - m))  [3] sum rnd  [4] sum rnd^2
+ *   [5] count          [6] m' = max(rnd)      [7] sum exp(rnd - m')
+ * Partials of several GPUs merge associatively (the only cross-GPU exchange of the path).
+ * `scratch` must hold at least 8 * (blocks + 1) doubles where blocks = lrds_estimator_blocks(B). */
+int lrds_estimator_blocks(int32_t B);
+int lrds_estimator_partials(const float* rnd, int32_t B, double* partials, double* scratch, void* stream);
+
+/* ---- drop-in pieces of the same arithmetic, for the reference's smaller public interfaces.
+ * control u = generative_ctrl(t, x) for the time of table row `row` (models/reparam.py:33-43, 112-117). */
+int lrds_ctrl_forward(const lrds_spec* spec, int32_t row, const float* x, int32_t B, float* u_out, void* stream);
+/* Distribution.unnorm_log_prob / score (distr/base.py:128-157); either output may be NULL. */
+int lrds_distr_eval(const lrds_distr* distr, int32_t d, const float* x, int32_t B, float* logp_out,
+                    float* score_out, void* stream);
+/* out = (a x + b s) + c z : VP/PinnedBM.ei_integration_step / ddpm_integration_step (eq/sdes.py:532-555, 658-678)
+ * and EulerIntegrator.integrate's update (eq/integrator.py:116-120) with a=1. */
+int lrds_axpy_step(const float* x, const float* s, const float* z, float a, float b, float c, float* out,
+                   int64_t n, void* stream);
+/* z[K][B][d] of the production-mode generator (stream_id 0 = Brownian increments, 1 = prior draws). */
+int lrds_normals(uint64_t seed, uint64_t particle_offset, int32_t stream_id, int32_t K, int32_t B, int32_t d,
+                 float* out, void* stream);
+
+const char* lrds_last_error(void);
+int lrds_abi_version(void);
+/* number of kernels this library has launched in the calling process (bench.py's gpu_launches claim) */
+int64_t lrds_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LRDS_B200_H */

@@ -1,0 +1,425 @@
+// C ABI of liblrds_b200.so (declared in include/lrds_b200.h): argument validation, launch configuration and
+// the small auxiliary kernels (estimator partials, control / distribution evaluation, axpy step, RNG dump).
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+
+#include "lrds_rollout_simt.cuh"
+#include "lrds_rollout_tc.cuh"
+
+namespace {
+
+thread_local char g_err[512] = "";
+std::atomic<int64_t> g_launches{0};
+
+int fail(int code, const char* fmt, const char* a = "", long v = 0) {
+  snprintf(g_err, sizeof(g_err), fmt, a, v);
+  return code;
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+  snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(e));
+  return LRDS_ERR_CUDA;
+}
+
+int max_optin_smem() {
+  int dev = 0, v = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  return v;
+}
+
+// threads per CTA for the column layout: as many as fit, preferring >= 2 CTAs per SM
+int pick_threads(int floats_per_particle, int smem_cap) {
+  const int per = floats_per_particle * (int)sizeof(float);
+  if (128 * per <= smem_cap / 2) return 128;
+  if (64 * per <= smem_cap / 3) return 64;
+  for (int nt = 128; nt >= 32; nt -= 32)
+    if (nt * per <= smem_cap) return nt;
+  return 0;
+}
+
+int validate_gmm(const lrds_gmm& g, const char* name) {
+  if (g.M < 1 || !g.logc || !g.mu || !g.ivar) return fail(LRDS_ERR_INVALID, "%s: incomplete mixture block", name);
+  return LRDS_OK;
+}
+
+int validate_spec(const lrds_spec* s, bool need_steps) {
+  if (!s) return fail(LRDS_ERR_INVALID, "spec is NULL");
+  if (s->abi_version != LRDS_ABI_VERSION) return fail(LRDS_ERR_INVALID, "abi_version mismatch (got %s%ld)", "", s->abi_version);
+  if (s->B < 1 || s->d < 1 || s->K < 0) return fail(LRDS_ERR_INVALID, "B, d must be positive and K non-negative");
+  if (s->mlp.d != s->d || s->mlp.d_pad != ((s->d + 7) / 8) * 8) return fail(LRDS_ERR_INVALID, "mlp.d / d_pad inconsistent with d");
+  if (!s->mlp.w_in_t || !s->mlp.w_out_t || !s->mlp.b_out || s->mlp.num_hidden < 0 ||
+      (s->mlp.num_hidden > 0 && (!s->mlp.w_hid_t || !s->mlp.b_hid)))
+    return fail(LRDS_ERR_INVALID, "mlp weight pointers missing");
+  if (need_steps && !s->steps) return fail(LRDS_ERR_INVALID, "per-step table missing");
+  if (s->ctrl_kind != LRDS_CTRL_CLIPPED && s->ctrl_kind != LRDS_CTRL_SCORE) return fail(LRDS_ERR_INVALID, "unknown ctrl_kind");
+  switch (s->target.kind) {
+    case LRDS_DISTR_GMM:
+      if (int r = validate_gmm(s->target.gmm, "target")) return r;
+      break;
+    case LRDS_DISTR_PHI4:
+      break;
+    case LRDS_DISTR_LOGREG:
+      if (s->target.logreg.p + 1 != s->d || !s->target.logreg.X || !s->target.logreg.Xt || !s->target.logreg.y ||
+          s->target.logreg.n_pad % 4 != 0 || s->target.logreg.n_pad < s->target.logreg.N)
+        return fail(LRDS_ERR_INVALID, "logistic-regression block inconsistent");
+      break;
+    case LRDS_DISTR_NONE:
+      if (s->ctrl_kind == LRDS_CTRL_SCORE) return fail(LRDS_ERR_INVALID, "ScoreCtrl needs a target");
+      break;
+    default:
+      return fail(LRDS_ERR_UNSUPPORTED, "unknown target kind");
+  }
+  return LRDS_OK;
+}
+
+// ---- estimator partials -----------------------------------------------------------------------------
+constexpr int EST_THREADS = 256;
+constexpr int EST_PER_BLOCK = 8192;
+
+__device__ __forceinline__ double warp_sum(double v) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+template <bool IS_MAX>
+__device__ double block_reduce(double v, double* sh) {
+  v = IS_MAX ? warp_max(v) : warp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double r = IS_MAX ? -INFINITY : 0.0;
+  for (int w = 0; w < EST_THREADS / 32; ++w) r = IS_MAX ? fmax(r, sh[w]) : r + sh[w];
+  return r;
+}
+
+// merge of two partial records (max-shifted sums), associative and commutative
+__device__ void merge8(double* acc, const double* p) {
+  if (p[5] == 0.0) return;
+  if (acc[5] == 0.0) {
+    for (int i = 0; i < 8; ++i) acc[i] = p[i];
+    return;
+  }
+  const double m = fmax(acc[0], p[0]);
+  const double ea = exp(acc[0] - m), eb = exp(p[0] - m);
+  acc[1] = acc[1] * ea + p[1] * eb;
+  acc[2] = acc[2] * ea * ea + p[2] * eb * eb;
+  acc[0] = m;
+  acc[3] += p[3]; acc[4] += p[4]; acc[5] += p[5];
+  const double m2 = fmax(acc[6], p[6]);
+  acc[7] = acc[7] * exp(acc[6] - m2) + p[7] * exp(p[6] - m2);
+  acc[6] = m2;
+}
+
+__global__ void __launch_bounds__(EST_THREADS) estimator_kernel(const float* __restrict__ rnd, int B,
+                                                                double* __restrict__ out, double* scratch,
+                                                                unsigned int* counter) {
+  __shared__ double sh[EST_THREADS / 32];
+  __shared__ bool is_last;
+  const int lo = blockIdx.x * EST_PER_BLOCK, hi = min(B, lo + EST_PER_BLOCK);
+  double mx = -INFINITY, mn = -INFINITY;
+  for (int i = lo + threadIdx.x; i < hi; i += EST_THREADS) {
+    const double v = (double)rnd[i];
+    mx = fmax(mx, -v);
+    mn = fmax(mn, v);
+  }
+  mx = block_reduce<true>(mx, sh);
+  mn = block_reduce<true>(mn, sh);
+  double s1 = 0, s2 = 0, sr = 0, sr2 = 0, sf = 0;
+  for (int i = lo + threadIdx.x; i < hi; i += EST_THREADS) {
+    const double v = (double)rnd[i];
+    const double e = exp(-v - mx);
+    s1 += e; s2 += e * e; sr += v; sr2 += v * v; sf += exp(v - mn);
+  }
+  s1 = block_reduce<false>(s1, sh);
+  s2 = block_reduce<false>(s2, sh);
+  sr = block_reduce<false>(sr, sh);
+  sr2 = block_reduce<false>(sr2, sh);
+  sf = block_reduce<false>(sf, sh);
+  if (threadIdx.x == 0) {
+    double* p = scratch + 8 * blockIdx.x;
+    p[0] = mx; p[1] = s1; p[2] = s2; p[3] = sr; p[4] = sr2; p[5] = (double)(hi - lo); p[6] = mn; p[7] = sf;
+    __threadfence();
+    const unsigned int t = atomicAdd(counter, 1u);
+    is_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (is_last && threadIdx.x == 0) {
+    __threadfence();
+    double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (unsigned int k = 0; k < gridDim.x; ++k) merge8(acc, scratch + 8 * k);
+    for (int i = 0; i < 8; ++i) out[i] = acc[i];
+    *counter = 0u;
+  }
+}
+
+// ---- evaluation kernels for the small public interfaces -------------------------------------------------
+__global__ void __launch_bounds__(128) ctrl_forward_kernel(const lrds_spec s, int rowi, const float* __restrict__ x,
+                                                           float* __restrict__ out) {
+  using namespace lrds;
+  extern __shared__ float smem[];
+  const int NT = blockDim.x, tid = threadIdx.x;
+  const int b_raw = blockIdx.x * NT + tid;
+  const bool live = b_raw < s.B;
+  const int b = live ? b_raw : s.B - 1;
+  const ColLayout L = col_layout(s);
+  Particle P;
+  P.x = Col{smem + L.x * NT + tid, NT};
+  P.act = Col{smem + L.act * NT + tid, NT};
+  P.rt = Col{smem + L.rt * NT + tid, NT};
+  P.rr = Col{smem + L.rr * NT + tid, NT};
+  P.g = Col{smem + L.g * NT + tid, NT};
+  P.us = P.tsd = P.db = P.x;
+  const int d = s.d, dp = s.mlp.d_pad;
+  for (int j = 0; j < dp; ++j) P.x(j) = (j < d) ? __ldg(x + (int64_t)b * d + j) : 0.f;
+  const float* row = s.steps + (int64_t)rowi * LRDS_STEP_STRIDE;
+  const bool score_ctrl = s.ctrl_kind == LRDS_CTRL_SCORE;
+  if (score_ctrl) target_pass1(s, P, false);
+  mlp_hidden(s.mlp, row + LRDS_STEP_BIAS1, P.x, P.act);
+  float xm = 0.f;
+  for (int j0 = 0; j0 < dp; j0 += JC) {
+    float xr[JC], ts[JC], u[JC];
+    load_chunk(P.x, j0, xr);
+    const float xp = (j0 + JC < dp) ? P.x(j0 + JC) : 0.f;
+    if (score_ctrl) target_score_chunk(s, P, xr, xm, xp, j0, ts);
+    ctrl_chunk(s, P, j0, ts, __ldg(row + LRDS_STEP_GAMMA), u);
+    xm = xr[JC - 1];
+    if (live)
+#pragma unroll
+      for (int c = 0; c < JC; ++c)
+        if (j0 + c < d) out[(int64_t)b * d + j0 + c] = u[c];
+  }
+}
+
+__global__ void __launch_bounds__(128) distr_eval_kernel(const lrds_spec s, const float* __restrict__ x,
+                                                         float* __restrict__ logp_out, float* __restrict__ score_out) {
+  using namespace lrds;
+  extern __shared__ float smem[];
+  const int NT = blockDim.x, tid = threadIdx.x;
+  const int b_raw = blockIdx.x * NT + tid;
+  const bool live = b_raw < s.B;
+  const int b = live ? b_raw : s.B - 1;
+  const ColLayout L = col_layout(s);
+  Particle P;
+  P.x = Col{smem + L.x * NT + tid, NT};
+  P.act = Col{smem + L.act * NT + tid, NT};
+  P.rt = Col{smem + L.rt * NT + tid, NT};
+  P.rr = Col{smem + L.rr * NT + tid, NT};
+  P.g = Col{smem + L.g * NT + tid, NT};
+  P.us = P.tsd = P.db = P.x;
+  const int d = s.d, dp = s.mlp.d_pad;
+  for (int j = 0; j < dp; ++j) P.x(j) = (j < d) ? __ldg(x + (int64_t)b * d + j) : 0.f;
+  const float lp = target_pass1(s, P, logp_out != nullptr);
+  if (live && logp_out) logp_out[b] = lp;
+  if (!score_out) return;
+  float xm = 0.f;
+  for (int j0 = 0; j0 < dp; j0 += JC) {
+    float xr[JC], ts[JC];
+    load_chunk(P.x, j0, xr);
+    const float xp = (j0 + JC < dp) ? P.x(j0 + JC) : 0.f;
+    target_score_chunk(s, P, xr, xm, xp, j0, ts);
+    xm = xr[JC - 1];
+    if (live)
+#pragma unroll
+      for (int c = 0; c < JC; ++c)
+        if (j0 + c < d) score_out[(int64_t)b * d + j0 + c] = ts[c];
+  }
+}
+
+__global__ void axpy_step_kernel(const float* __restrict__ x, const float* __restrict__ s, const float* __restrict__ z,
+                                 float a, float b, float c, float* __restrict__ out, int64_t n) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    float v = a * x[i];
+    if (s) v += b * s[i];
+    if (z) v += c * z[i];
+    out[i] = v;
+  }
+}
+
+__global__ void normals_kernel(uint64_t seed, uint64_t offset, int stream_id, int K, int B, int d, float* __restrict__ out) {
+  const int nblk = (d + 3) / 4;
+  const int64_t total = (int64_t)K * B * nblk;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int blk = (int)(i % nblk);
+    const int b = (int)((i / nblk) % B);
+    const int k = (int)(i / ((int64_t)nblk * B));
+    float z[4];
+    lrds::normals4(seed, (uint32_t)(offset + (uint64_t)b), (uint32_t)k, (uint32_t)blk, (uint32_t)stream_id, z);
+    float* p = out + ((int64_t)k * B + b) * d + 4 * blk;
+    for (int c = 0; c < 4; ++c)
+      if (4 * blk + c < d) p[c] = z[c];
+  }
+}
+
+template <typename KernelT>
+int launch_cols(KernelT kernel, const lrds_spec& s, int floats, cudaStream_t st, int* nt_out, size_t* smem_out) {
+  const int cap = max_optin_smem();
+  const int nt = pick_threads(floats, cap);
+  if (nt == 0) return fail(LRDS_ERR_RESOURCES, "per-particle state of %s%ld floats does not fit in shared memory", "", floats);
+  const size_t smem = (size_t)floats * nt * sizeof(float);
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute");
+  *nt_out = nt;
+  *smem_out = smem;
+  (void)st;
+  (void)s;
+  return LRDS_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* lrds_last_error(void) { return g_err; }
+int lrds_abi_version(void) { return LRDS_ABI_VERSION; }
+int64_t lrds_launch_count(void) { return g_launches.load(); }
+
+int lrds_rollout(const lrds_spec* spec, const float* x0, const float* noise, uint64_t seed, uint64_t particle_offset,
+                 float* x_out, float* rnd_out, float* traj_out, void* stream) {
+  if (int r = validate_spec(spec, true)) return r;
+  if (!x0 || !rnd_out) return fail(LRDS_ERR_INVALID, "x0 and rnd_out are required");
+  const lrds_spec& s = *spec;
+  if (s.K < 1) return fail(LRDS_ERR_INVALID, "K must be >= 1");
+  if (int r = validate_gmm(s.ref_0, "ref_0")) return r;
+  const bool linear = s.kind == LRDS_ROLLOUT_LINEAR || s.kind == LRDS_ROLLOUT_EUBO_LINEAR;
+  if (s.kind == LRDS_ROLLOUT_EUBO_LINEAR && !s.has_ref_ctrl) return fail(LRDS_ERR_INVALID, "compute_eubo needs a reference control");
+  if (linear && s.has_ref_ctrl)
+    if (int r = validate_gmm(s.ref_t, "ref_t")) return r;
+  if (!linear && s.ref_0.M != 1) return fail(LRDS_ERR_UNSUPPORTED, "CMCD needs a diagonal Gaussian prior");
+  if (!linear && s.target.kind == LRDS_DISTR_NONE) return fail(LRDS_ERR_INVALID, "CMCD needs a target");
+  cudaStream_t st = (cudaStream_t)stream;
+  lrds::RolloutArgs a{s, x0, noise, seed, particle_offset, x_out, rnd_out, traj_out};
+
+  if (s.precision != LRDS_PRECISION_FP32_SIMT) {
+    int r = lrds::launch_rollout_tc(a, st);
+    if (r == LRDS_OK) g_launches.fetch_add(1);
+    else if (r == LRDS_ERR_UNSUPPORTED) return fail(r, "tensor-core rollout does not cover this spec: %s", lrds::tc_unsupported_reason());
+    else if (r == LRDS_ERR_CUDA) return cuda_fail(cudaGetLastError(), "tensor-core rollout launch");
+    return r;
+  }
+
+  const lrds::ColLayout L = lrds::col_layout(s);
+  int nt = 0;
+  size_t smem = 0;
+  auto go = [&](auto kernel) -> int {
+    if (int r = launch_cols(kernel, s, L.total, st, &nt, &smem)) return r;
+    const int grid = (s.B + nt - 1) / nt;
+    kernel<<<grid, nt, smem, st>>>(a);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "rollout launch");
+    g_launches.fetch_add(1);
+    return LRDS_OK;
+  };
+  switch (s.kind) {
+    case LRDS_ROLLOUT_LINEAR: return go(lrds::rollout_simt_kernel<LRDS_ROLLOUT_LINEAR>);
+    case LRDS_ROLLOUT_CMCD: return go(lrds::rollout_simt_kernel<LRDS_ROLLOUT_CMCD>);
+    case LRDS_ROLLOUT_EUBO_LINEAR: return go(lrds::rollout_simt_kernel<LRDS_ROLLOUT_EUBO_LINEAR>);
+    case LRDS_ROLLOUT_EUBO_CMCD: return go(lrds::rollout_simt_kernel<LRDS_ROLLOUT_EUBO_CMCD>);
+    default: return fail(LRDS_ERR_INVALID, "unknown rollout kind");
+  }
+}
+
+int lrds_estimator_blocks(int32_t B) { return B < 1 ? 0 : (B + EST_PER_BLOCK - 1) / EST_PER_BLOCK; }
+
+int lrds_estimator_partials(const float* rnd, int32_t B, double* partials, double* scratch, void* stream) {
+  if (!rnd || !partials || !scratch || B < 1) return fail(LRDS_ERR_INVALID, "estimator: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int blocks = lrds_estimator_blocks(B);
+  unsigned int* counter = reinterpret_cast<unsigned int*>(scratch + 8 * (size_t)blocks);
+  cudaError_t e = cudaMemsetAsync(counter, 0, sizeof(double), st);
+  if (e != cudaSuccess) return cuda_fail(e, "estimator memset");
+  estimator_kernel<<<blocks, EST_THREADS, 0, st>>>(rnd, B, partials, scratch, counter);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "estimator launch");
+  g_launches.fetch_add(1);
+  return LRDS_OK;
+}
+
+int lrds_ctrl_forward(const lrds_spec* spec, int32_t row, const float* x, int32_t B, float* u_out, void* stream) {
+  if (int r = validate_spec(spec, true)) return r;
+  if (!x || !u_out || B < 1 || row < 0) return fail(LRDS_ERR_INVALID, "ctrl_forward: bad arguments");
+  lrds_spec s = *spec;
+  s.B = B;
+  s.kind = LRDS_ROLLOUT_LINEAR;
+  s.has_ref_ctrl = 0;
+  s.ref_0.M = 0;
+  const lrds::ColLayout L = lrds::col_layout(s);
+  int nt = 0;
+  size_t smem = 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (int r = launch_cols(ctrl_forward_kernel, s, L.total, st, &nt, &smem)) return r;
+  ctrl_forward_kernel<<<(B + nt - 1) / nt, nt, smem, st>>>(s, row, x, u_out);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "ctrl_forward launch");
+  g_launches.fetch_add(1);
+  return LRDS_OK;
+}
+
+int lrds_distr_eval(const lrds_distr* distr, int32_t d, const float* x, int32_t B, float* logp_out, float* score_out,
+                    void* stream) {
+  if (!distr || !x || B < 1 || d < 1 || (!logp_out && !score_out)) return fail(LRDS_ERR_INVALID, "distr_eval: bad arguments");
+  lrds_spec s;
+  memset(&s, 0, sizeof(s));
+  s.abi_version = LRDS_ABI_VERSION;
+  s.B = B;
+  s.d = d;
+  s.mlp.d = d;
+  s.mlp.d_pad = ((d + 7) / 8) * 8;
+  s.target = *distr;
+  s.ctrl_kind = LRDS_CTRL_CLIPPED;
+  if (distr->kind == LRDS_DISTR_GMM) {
+    if (int r = validate_gmm(distr->gmm, "distr")) return r;
+  } else if (distr->kind == LRDS_DISTR_LOGREG) {
+    if (distr->logreg.p + 1 != d) return fail(LRDS_ERR_INVALID, "logreg: d must be p + 1");
+  } else if (distr->kind != LRDS_DISTR_PHI4) {
+    return fail(LRDS_ERR_UNSUPPORTED, "distr_eval: unknown distribution kind");
+  }
+  const lrds::ColLayout L = lrds::col_layout(s);
+  int nt = 0;
+  size_t smem = 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (int r = launch_cols(distr_eval_kernel, s, L.total, st, &nt, &smem)) return r;
+  distr_eval_kernel<<<(B + nt - 1) / nt, nt, smem, st>>>(s, x, logp_out, score_out);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "distr_eval launch");
+  g_launches.fetch_add(1);
+  return LRDS_OK;
+}
+
+int lrds_axpy_step(const float* x, const float* s, const float* z, float a, float b, float c, float* out, int64_t n,
+                   void* stream) {
+  if (!x || !out || n < 1) return fail(LRDS_ERR_INVALID, "axpy_step: bad arguments");
+  const int threads = 256;
+  const int64_t want = (n + threads - 1) / threads;
+  const int grid = (int)(want < 148 * 8 ? want : 148 * 8);
+  axpy_step_kernel<<<grid, threads, 0, (cudaStream_t)stream>>>(x, s, z, a, b, c, out, n);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "axpy_step launch");
+  g_launches.fetch_add(1);
+  return LRDS_OK;
+}
+
+int lrds_normals(uint64_t seed, uint64_t particle_offset, int32_t stream_id, int32_t K, int32_t B, int32_t d, float* out,
+                 void* stream) {
+  if (!out || K < 1 || B < 1 || d < 1) return fail(LRDS_ERR_INVALID, "normals: bad arguments");
+  const int64_t total = (int64_t)K * B * ((d + 3) / 4);
+  const int threads = 256;
+  const int64_t want = (total + threads - 1) / threads;
+  const int grid = (int)(want < 148 * 16 ? want : 148 * 16);
+  normals_kernel<<<grid, threads, 0, (cudaStream_t)stream>>>(seed, particle_offset, stream_id, K, B, d, out);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "normals launch");
+  g_launches.fetch_add(1);
+  return LRDS_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,150 @@
+"""Distribution base class: the reference's interface (sde_sampler/distr/base.py:24-157) evaluated by the
+CUDA library.  ``unnorm_log_prob`` / ``score`` run lrds_distr_eval on CUDA tensors; there is no CPU path."""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from pathlib import Path
+
+import torch
+
+from .. import _native as N
+
+EXPECTATION_FNS = {
+    "square": lambda x: (x ** 2).sum(dim=-1, keepdims=True),
+    "abs": lambda x: x.abs().sum(dim=-1, keepdims=True),
+    "sum": lambda x: x.sum(dim=-1, keepdims=True),
+    "square_minus_sum": lambda x: (x ** 2 - x).sum(dim=-1, keepdims=True),
+}
+DATA_DIR = Path(__file__).parents[2] / "data"
+
+
+def gmm_block(loc: torch.Tensor, var: torch.Tensor, weights: torch.Tensor | None, device):
+    """Packs a diagonal mixture into the (logc[M], mu[M][d], ivar[M][d]) block of lrds_gmm.
+
+    loc/var may carry a leading step axis ([S][M][d]) for the time-marginal reference.  logc follows
+    log_prob_gaussian (distr/gauss.py:67-73) + log of the normalised weights (gauss.py:100-104)."""
+    loc = loc.detach().to("cpu", torch.float32)
+    var = var.detach().to("cpu", torch.float32).expand_as(loc)
+    d = loc.shape[-1]
+    logc = -0.5 * d * math.log(2.0 * math.pi) - 0.5 * torch.log(var).sum(dim=-1)
+    if weights is not None:
+        w = weights.detach().to("cpu", torch.float32)
+        logc = logc + torch.log(w / w.sum())
+    ivar = (1.0 / var.double()).float()
+    return (logc.contiguous().to(device), loc.contiguous().to(device), ivar.contiguous().to(device))
+
+
+def fill_gmm(g: N.Gmm, block, stepped: bool = False):
+    logc, mu, ivar = block
+    g.M = mu.shape[-2]
+    g.logc, g.mu, g.ivar = logc.data_ptr(), mu.data_ptr(), ivar.data_ptr()
+    g.step_stride_logc = g.M if stepped else 0
+    g.step_stride_param = g.M * mu.shape[-1] if stepped else 0
+    return g
+
+
+class Distribution(torch.nn.Module):
+    """Base class for probability distributions (same constructor and public methods as the reference)."""
+
+    def __init__(self, dim: int, log_norm_const: float = None, domain=None, n_reference_samples=None,
+                 grid_points=None):
+        super().__init__()
+        self.dim = dim
+        self.n_reference_samples = n_reference_samples
+        self.grid_points = grid_points
+        self.set_domain(domain)
+        self.log_norm_const = log_norm_const
+        self.register_buffer("stddevs", None, persistent=False)
+        self.expectations = {}
+        self._lrds_cache = {}
+
+    # ---- packing hook: subclasses return (N.Distr, keepalive) for a device ------------------------------
+    def _lrds_pack(self, device):
+        raise NotImplementedError(f"{type(self).__name__} has no B200 kernel (no fallback is provided).")
+
+    def lrds_distr(self, device):
+        key = str(device)
+        if key not in self._lrds_cache:
+            self._lrds_cache[key] = self._lrds_pack(torch.device(device))
+        return self._lrds_cache[key]
+
+    def _apply(self, fn):
+        out = super()._apply(fn)
+        self._lrds_cache = {}
+        self._initialize_distr()
+        return out
+
+    def _initialize_distr(self):
+        pass
+
+    def _eval(self, x: torch.Tensor, want_logp: bool, want_score: bool):
+        if not x.is_cuda:
+            raise N.LrdsError(f"{type(self).__name__}: CUDA tensor required (no CPU fallback); got device {x.device}")
+        lead = x.shape[:-1]
+        xf = x.detach().reshape(-1, self.dim).to(torch.float32).contiguous()
+        B = xf.shape[0]
+        logp = torch.empty(B, device=x.device, dtype=torch.float32) if want_logp else None
+        score = torch.empty_like(xf) if want_score else None
+        distr, _keep = self.lrds_distr(x.device)
+        with torch.cuda.device(x.device):
+            N.check(N.lib().lrds_distr_eval(C.byref(distr), self.dim, N.ptr(xf), B, N.ptr(logp), N.ptr(score),
+                                            N.stream_ptr(x.device)))
+        if logp is not None:
+            logp = logp.reshape(*lead, 1)
+        if score is not None:
+            score = score.reshape(*lead, self.dim)
+        return logp, score
+
+    # ---- reference interface ------------------------------------------------------------------------------
+    def has_entropy(self):
+        return False
+
+    def set_domain(self, d=None):
+        if d is not None:
+            if not isinstance(d, torch.Tensor):
+                d = torch.tensor(d, dtype=torch.float)
+            if d.ndim == 0:
+                d = torch.stack([-d, d], dim=-1)
+            if d.ndim == 1:
+                d = d.unsqueeze(0)
+            if d.shape == (1, 2):
+                d = d.repeat(self.dim, 1)
+            assert d.shape == (self.dim, 2)
+        self.register_buffer("domain", d, persistent=False)
+
+    def unnorm_log_prob(self, x: torch.Tensor, *args, **kwargs) -> torch.Tensor:
+        return self._eval(x, True, False)[0]
+
+    def log_prob(self, x: torch.Tensor) -> torch.Tensor:
+        if self.log_norm_const is None:
+            raise NotImplementedError
+        return self.unnorm_log_prob(x) - self.log_norm_const
+
+    def pdf(self, x):
+        return self.log_prob(x).exp()
+
+    def unnorm_pdf(self, x):
+        return self.unnorm_log_prob(x).exp()
+
+    def score(self, x: torch.Tensor, *args, **kwargs) -> torch.Tensor:
+        return self._eval(x, False, True)[1]
+
+    def forward(self, x):
+        return self.unnorm_log_prob(x)
+
+    @torch.no_grad()
+    def compute_stats(self):
+        """Monte-Carlo reference expectations from true samples (reference: base.py:61-70, 96-118)."""
+        if hasattr(self, "sample") and self.n_reference_samples is not None:
+            samples = self.sample((self.n_reference_samples,))
+            for name, fn in EXPECTATION_FNS.items():
+                if name not in self.expectations:
+                    self.expectations[name] = fn(samples).mean().item()
+            if self.stddevs is None:
+                self.stddevs = samples.std(dim=0)
+
+
+def sample_uniform(domain: torch.Tensor, batchsize: int = 1) -> torch.Tensor:
+    diam = domain[:, 1] - domain[:, 0]
+    return domain[:, 0] + torch.rand(batchsize, domain.shape[0], device=domain.device) * diam

@@ -1,0 +1,422 @@
+"""The integrate-and-weight loop behind RDS / PIS / DDS / CMCD with the reference's loss classes and method
+signatures (sde_sampler/losses/oc.py): ``simulate`` / ``eval`` / ``compute_eubo`` pack the rollout into an
+``lrds_spec`` and run ONE fused CUDA kernel for all K steps (csrc/), instead of ~40-150 eager ops per step.
+
+    EMReferenceSDELoss            oc.py:203-428   (RDS-EM; PIS with reference_ctrl=None)
+    EIReferenceSDELoss            oc.py:431-568
+    DDPMLikeReferenceSDELoss      oc.py:571-651
+    ControlledLangevinSDELoss     oc.py:654-894   (CMCD)
+    ExponentialIntegratorSDELoss  oc.py:1310-1467 (DDS)
+
+Extra keyword arguments (not in the reference, all optional): ``noise`` = recorded standard normals [K, B, d]
+to consume instead of in-kernel Philox draws (validation mode), ``seed`` / ``particle_offset`` for the
+counter-based generator (global particle index => results independent of the GPU count).
+Training (``__call__`` with autograd through the control) is the next row of SURVEY.md 8f and raises.
+"""
+from __future__ import annotations
+
+import itertools
+import math
+from typing import Callable
+
+import torch
+
+from .. import _native as N
+from .. import pack
+from ..distr.base import fill_gmm
+from ..eq.sdes import OU, ControlledLangevinSDE, MarginalReference
+from ..estimators import estimator_partials, metrics_from_partials
+from ..utils.common import Results
+
+
+def _resolve_reference(ref_ctrl):
+    if ref_ctrl is None:
+        return None
+    if isinstance(ref_ctrl, MarginalReference):
+        return ref_ctrl
+    owner = getattr(ref_ctrl, "__self__", None)
+    cand = getattr(owner, "reference_score_t", None)
+    if isinstance(cand, MarginalReference):
+        return cand
+    raise NotImplementedError("reference_ctrl must be a MarginalReference (gaussian / gmm reference); "
+                              "neural references are a later row (SURVEY.md 8f item 3)")
+
+
+class BaseOCLoss:
+    """Base class: estimators and bookkeeping shared by every rollout loss."""
+
+    def __init__(self, generative_ctrl: Callable, generative_ctrl_ema: Callable, sde: OU | None = None,
+                 method: str = "kl", traj_per_sample: int = 1, filter_samples: Callable | None = None,
+                 max_rnd: float | None = None, sde_ctrl_dropout: float | None = None,
+                 sde_ctrl_noise: float | None = None, precision: str | None = None, **kwargs):
+        self.generative_ctrl = generative_ctrl
+        self.generative_ctrl_ema = generative_ctrl_ema
+        self.sde = sde
+        if method not in ["kl", "kl_ito", "lv", "lv_traj"]:
+            raise ValueError("Unknown loss method.")
+        self.method = method
+        if traj_per_sample == 1 and self.method == "lv_traj":
+            raise ValueError("Cannot compute variance over a single trajectory.")
+        self.traj_per_sample = traj_per_sample
+        self.filter_samples = filter_samples
+        self.max_rnd = max_rnd
+        self.sde_ctrl_noise = sde_ctrl_noise
+        self.sde_ctrl_dropout = sde_ctrl_dropout
+        self.n_filtered = 0
+        self.precision = precision
+        self._plans: dict = {}
+        self._calls = itertools.count()
+
+    # ---- estimators (oc.py:134-173) ---------------------------------------------------------------------------
+    @staticmethod
+    def compute_results(rnd: torch.Tensor, compute_weights: bool = False, ts=None, samples=None, xs=None,
+                        group=None) -> Results:
+        """ELBO, importance weights, log Z and LV from the log-weights; the reductions run in the estimator
+        kernel (fp64 partials), merged across ranks when ``group`` is a torch.distributed group."""
+        part = estimator_partials(rnd, group=group)
+        m = metrics_from_partials(part)
+        metrics = {"eval/elbo": m["elbo"]}
+        if compute_weights:
+            weights = torch.exp(-rnd.double() - part[0]).div(part[1]).to(rnd.dtype)  # softmax(-rnd, dim=0)
+            log_norm_const_preds = {"log_norm_const_is": m["log_norm_const_is"]}
+            metrics["eval/lv_loss"] = m["lv_loss"]
+        else:
+            weights, log_norm_const_preds = None, {}
+        return Results(samples=samples, weights=weights, log_norm_const_preds=log_norm_const_preds, ts=ts, xs=xs,
+                       metrics=metrics)
+
+    def filter(self, rnd, samples=None):
+        mask = True
+        if samples is not None and self.filter_samples is not None:
+            mask = self.filter_samples(samples)
+        if self.max_rnd is None:
+            return mask & rnd.isfinite()
+        return mask & (rnd < self.max_rnd)
+
+    def __call__(self, ts, x, *args, **kwargs):
+        raise NotImplementedError("training through the fused rollout (LV/KL gradient) is the next row of the "
+                                  "scope table (SURVEY.md 8f item 1); only simulate / eval / compute_eubo are built")
+
+    def load_state_dict(self, state_dict: dict):
+        self.n_filtered = state_dict["n_filtered"]
+
+    def state_dict(self) -> dict:
+        return {"n_filtered": self.n_filtered}
+
+    # ---- shared plumbing ------------------------------------------------------------------------------------------
+    def _ctrl(self, use_ema):
+        return pack.resolve_ctrl(self.generative_ctrl_ema if use_ema else self.generative_ctrl)
+
+    def _check_plain(self, change_sde_ctrl):
+        if change_sde_ctrl and (self.sde_ctrl_noise is not None or self.sde_ctrl_dropout is not None
+                                or torch.is_grad_enabled()):
+            raise NotImplementedError("change_sde_ctrl with autograd / control noise is training-only (SURVEY.md 8f item 1)")
+
+    def _seed(self, seed):
+        if seed is not None:
+            return int(seed)
+        return (int(torch.initial_seed()) * 0x9E3779B97F4A7C15 + next(self._calls) * 0xD1B54A32D192ED03) & (2 ** 64 - 1)
+
+    def _cached(self, key, build):
+        if key not in self._plans:
+            if len(self._plans) >= 16:
+                self._plans.pop(next(iter(self._plans)))
+            self._plans[key] = build()
+        return self._plans[key]
+
+    def _key(self, tag, ts, device, info, extra=()):
+        tsc = ts.detach().to("cpu", torch.float32)
+        vers = tuple((p.data_ptr(), p._version) for p in info.base.parameters())
+        if info.score_model is not None:
+            vers += tuple((p.data_ptr(), p._version) for p in info.score_model.parameters())
+        return (tag, tsc.numpy().tobytes(), str(device), vers, id(info.target), self.precision or pack.default_precision(),
+                extra)
+
+
+def _terminal(spec, keep, device, terminal_unnorm_log_prob, info):
+    """Fills spec.target / clip_target from the terminal log-density callable."""
+    target, clip_t = pack.resolve_log_prob(terminal_unnorm_log_prob)
+    if info.target is not None and target is not info.target:
+        raise NotImplementedError("ScoreCtrl.target_score and terminal_unnorm_log_prob must belong to the same target")
+    if target.dim != spec.d:
+        raise ValueError("target dimension differs from the drift network's")
+    distr, k = target.lrds_distr(device)
+    spec.target = distr
+    keep.append(k)
+    spec.clip_target = float(clip_t) if clip_t is not None else 0.0
+
+
+class EMReferenceSDELoss(BaseOCLoss):
+    """RDS loss with the Euler-Maruyama integrator (also PIS when ``reference_ctrl`` is None)."""
+
+    _variant = "em"
+
+    def __init__(self, *args, reference_ctrl: Callable | None = None, use_rescaling: bool = True, **kwargs):
+        super().__init__(*args, **kwargs)
+        self.reference_ctrl = reference_ctrl
+        self.use_rescaling = use_rescaling
+
+    # per-step coefficients with the reference's own float32 scalar formulas ------------------------------------
+    def _rows(self, sde, s, t, T, row):
+        tau = T - s
+        dt = t - s
+        if self._variant == "em":  # oc.py:261-284
+            sig = sde.diff(tau)
+            row[N.STEP_A], row[N.STEP_B], row[N.STEP_C] = sde.drift_coeff_t(tau), sig, torch.square(sig)
+            row[N.STEP_W_COST] = 0.5 * dt
+        else:
+            ei = self._variant == "ei"
+            a, b, c = sde.ei_coeffs(s, t) if ei else sde.ddpm_coeffs(s, t)
+            om = sde.omega(s, t) if ei else sde.omega_ddpm(s, t)
+            row[N.STEP_A], row[N.STEP_B], row[N.STEP_C] = a, b, c
+            row[N.STEP_W_COST], row[N.STEP_W_ITO] = 0.5 * om, torch.sqrt(om)
+        row[N.STEP_DT], row[N.STEP_SQRT_DT] = dt, dt.sqrt()
+
+    def _plan(self, ts, device, use_ema, terminal_unnorm_log_prob, reference_log_prob, eubo):
+        if self._variant == "em" and not self.use_rescaling:
+            raise NotImplementedError("use_rescaling=False is unreachable from the shipped configs (SURVEY.md App. B.4)")
+        info = self._ctrl(use_ema)
+        ref = _resolve_reference(self.reference_ctrl)
+        ref0, _ = pack.resolve_log_prob(reference_log_prob)
+        key = self._key((self._variant, eubo), ts, device, info, (id(ref), id(ref0), id(terminal_unnorm_log_prob)))
+
+        def build():
+            if eubo and ref is None:
+                raise NotImplementedError("compute_eubo needs a reference control (the reference calls it unconditionally)")
+            if eubo and self._variant == "ddpm":
+                raise NotImplementedError("the reference has no DDPM-like compute_eubo of its own (it inherits the EM one)")
+            sde = self.sde.host()
+            tsc, pairs = pack._scalar_rows(ts)
+            T = tsc[-1]
+            K = len(pairs)
+            spec = pack.new_spec(self.precision)
+            keep: list = []
+            pack.fill_ctrl(spec, info, device, keep)
+            _terminal(spec, keep, device, terminal_unnorm_log_prob, info)
+            spec.K = K
+            spec.kind = N.ROLLOUT_EUBO_LINEAR if eubo else N.ROLLOUT_LINEAR
+            spec.update_form = N.UPDATE_EM if self._variant == "em" else N.UPDATE_AXPY
+            spec.ito_form = N.ITO_EM if self._variant == "em" else N.ITO_SCALED
+            spec.has_ref_ctrl = int(ref is not None)
+            table = torch.zeros(K, N.STEP_STRIDE)
+            if not eubo:
+                taus = T - tsc[:-1]
+                for k, (s, t) in enumerate(pairs):
+                    self._rows(sde, s, t, T, table[k])
+            else:  # rows in loop order: reversed time (oc.py:326-329, 541-544)
+                times_s, times_t = tsc[:-1].flip((0,)), tsc[1:].flip((0,))
+                mean, var = sde.transition_params(T - times_t, T - times_s)
+                std = var.sqrt()
+                taus = T - times_s
+                for i, (s, t) in enumerate(zip(times_s, times_t)):
+                    row = table[i]
+                    dt = t - s
+                    row[N.STEP_EU_A], row[N.STEP_EU_B] = mean[i], std[i]
+                    if self._variant == "em":  # oc.py:343-359
+                        sig = sde.diff(T - s)
+                        row[N.STEP_B] = sig
+                        row[N.STEP_W_COST] = dt * sig ** 2
+                        row[N.STEP_EU_C] = 1.0 / mean[i] - 1.0 + sde.drift_coeff_t(T - s) * dt
+                        row[N.STEP_W_ITO] = std[i] / mean[i]
+                    else:  # oc.py:560-564
+                        om = sde.omega(s, t)
+                        row[N.STEP_W_COST], row[N.STEP_W_ITO] = om, torch.sqrt(om)
+            spec_table = pack.finish_table(table, info, taus, device)
+            spec.steps = spec_table.data_ptr()
+            keep.append(spec_table)
+            if ref is not None:
+                if ref.dim != spec.d:
+                    raise ValueError("reference dimension differs from the model's")
+                blk = ref.block_at(taus, device)
+                fill_gmm(spec.ref_t, blk, stepped=True)
+                keep.append(blk)
+            blk0 = pack.gauss_block_from(ref0, device)
+            fill_gmm(spec.ref_0, blk0)
+            keep.append(blk0)
+            return pack.Plan(spec, keep, rows=K, noise_steps=K)
+        return self._cached(key, build)
+
+    def simulate(self, ts, x, terminal_unnorm_log_prob, reference_log_prob, change_sde_ctrl: bool = False,
+                 return_traj: bool = False, use_ema: bool = False, noise=None, seed=None, particle_offset: int = 0):
+        """Denoising rollout from prior samples x: returns (x_T (B,d), rnd (B,1), xs (K+1,B,d) | None)."""
+        self._check_plain(change_sde_ctrl)
+        plan = self._plan(ts, x.device, use_ema, terminal_unnorm_log_prob, reference_log_prob, eubo=False)
+        return pack.run_rollout(plan, x, noise, self._seed(seed), particle_offset, return_traj)
+
+    def compute_eubo(self, ts, x, terminal_unnorm_log_prob, reference_log_prob, use_ema: bool = False, noise=None,
+                     seed=None, particle_offset: int = 0):
+        """Noising rollout from target samples x -> rnd (B,1).  Like the reference (oc.py:336-337) the input
+        tensor is overwritten with the noised samples."""
+        plan = self._plan(ts, x.device, use_ema, terminal_unnorm_log_prob, reference_log_prob, eubo=True)
+        x_end, rnd, _ = pack.run_rollout(plan, x, noise, self._seed(seed), particle_offset, False)
+        if x.dtype == torch.float32 and x.is_contiguous():
+            x.copy_(x_end)
+        return rnd
+
+    def eval(self, ts, x, terminal_unnorm_log_prob, reference_log_prob=None, compute_weights: bool = True,
+             return_traj: bool = True, use_ema: bool = True, **kw) -> Results:
+        samples, rnd, xs = self.simulate(ts, x, terminal_unnorm_log_prob=terminal_unnorm_log_prob,
+                                         reference_log_prob=reference_log_prob, change_sde_ctrl=False,
+                                         return_traj=return_traj, use_ema=use_ema, **kw)
+        return BaseOCLoss.compute_results(rnd, compute_weights=compute_weights, ts=ts, samples=samples, xs=xs)
+
+
+class EIReferenceSDELoss(EMReferenceSDELoss):
+    """RDS loss with the exponential integrator."""
+
+    _variant = "ei"
+
+    def __init__(self, *args, reference_ctrl: Callable | None = None, **kwargs):
+        kwargs.pop("use_rescaling", None)
+        super().__init__(*args, reference_ctrl=reference_ctrl, use_rescaling=False, **kwargs)
+
+
+class DDPMLikeReferenceSDELoss(EMReferenceSDELoss):
+    """RDS loss with the DDPM-like transition kernel."""
+
+    _variant = "ddpm"
+
+    def __init__(self, *args, reference_ctrl: Callable | None = None, **kwargs):
+        kwargs.pop("use_rescaling", None)
+        super().__init__(*args, reference_ctrl=reference_ctrl, use_rescaling=False, **kwargs)
+
+    def compute_eubo(self, *a, **k):
+        raise NotImplementedError("DDPM-like compute_eubo: the reference inherits the EM formula with use_rescaling=False; "
+                                  "not built")
+
+
+class ExponentialIntegratorSDELoss(BaseOCLoss):
+    """Original DDS loss (forward-time control, exponential integrator of Vargas et al.)."""
+
+    def __init__(self, *args, alpha: float, sigma: float, **kwargs):
+        super().__init__(*args, **kwargs)
+        self.alpha = alpha
+        self.sigma = sigma
+
+    def _plan(self, ts, device, use_ema, terminal_unnorm_log_prob, reference_log_prob, compute_ito_int):
+        info = self._ctrl(use_ema)
+        ref0, _ = pack.resolve_log_prob(reference_log_prob)
+        key = self._key(("dds", bool(compute_ito_int), self.alpha, self.sigma), ts, device, info,
+                        (id(ref0), id(terminal_unnorm_log_prob)))
+
+        def build():
+            tsc, pairs = pack._scalar_rows(ts)
+            K = len(pairs)
+            spec = pack.new_spec(self.precision)
+            keep: list = []
+            pack.fill_ctrl(spec, info, device, keep)
+            _terminal(spec, keep, device, terminal_unnorm_log_prob, info)
+            spec.K, spec.kind = K, N.ROLLOUT_LINEAR
+            spec.update_form = N.UPDATE_AXPY
+            spec.ito_form = N.ITO_DDS if compute_ito_int else N.ITO_NONE
+            spec.has_ref_ctrl = 0
+            table = torch.zeros(K, N.STEP_STRIDE)
+            for k, (s, t) in enumerate(pairs):  # oc.py:1366-1383
+                row = table[k]
+                dt = t - s
+                beta_k = torch.clip(self.alpha * dt.sqrt(), 0, 1)
+                alpha_k = torch.sqrt(1.0 - beta_k ** 2)
+                row[N.STEP_A] = alpha_k
+                row[N.STEP_B] = (beta_k ** 2) * (self.sigma ** 2)
+                row[N.STEP_C] = self.sigma * beta_k
+                row[N.STEP_W_COST] = 0.5 * (beta_k ** 2 * self.sigma ** 2)
+                row[N.STEP_W_ITO] = beta_k
+                row[N.STEP_SIGU] = self.sigma
+                row[N.STEP_DT], row[N.STEP_SQRT_DT] = dt, dt.sqrt()
+            spec_table = pack.finish_table(table, info, tsc[:-1], device)
+            spec.steps = spec_table.data_ptr()
+            keep.append(spec_table)
+            blk0 = pack.gauss_block_from(ref0, device)
+            fill_gmm(spec.ref_0, blk0)
+            keep.append(blk0)
+            return pack.Plan(spec, keep, rows=K, noise_steps=K)
+        return self._cached(key, build)
+
+    def simulate(self, ts, x, terminal_unnorm_log_prob, reference_log_prob, compute_ito_int: bool = False,
+                 change_sde_ctrl: bool = False, return_traj: bool = False, use_ema: bool = False, noise=None,
+                 seed=None, particle_offset: int = 0):
+        self._check_plain(change_sde_ctrl)
+        plan = self._plan(ts, x.device, use_ema, terminal_unnorm_log_prob, reference_log_prob, compute_ito_int)
+        return pack.run_rollout(plan, x, noise, self._seed(seed), particle_offset, return_traj)
+
+    def eval(self, ts, x, terminal_unnorm_log_prob, reference_log_prob=None, compute_weights: bool = True,
+             return_traj: bool = True, use_ema: bool = True, **kw) -> Results:
+        samples, rnd, xs = self.simulate(ts, x, terminal_unnorm_log_prob=terminal_unnorm_log_prob,
+                                         reference_log_prob=reference_log_prob, compute_ito_int=compute_weights,
+                                         change_sde_ctrl=False, return_traj=return_traj, use_ema=use_ema, **kw)
+        return BaseOCLoss.compute_results(rnd, compute_weights=compute_weights, ts=ts, samples=samples, xs=xs)
+
+
+class ControlledLangevinSDELoss(BaseOCLoss):
+    """Discrete-time CMCD loss.  The (control, drift) pair evaluated at the end point of step k is reused as the
+    start point of step k+1 (the reference recomputes it: 2 network + 2 score evaluations per step)."""
+
+    def __init__(self, *args, use_rescaling: bool = True, **kwargs):
+        super().__init__(*args, **kwargs)
+        self.use_rescaling = use_rescaling
+
+    def _plan(self, ts, device, use_ema, terminal_unnorm_log_prob, initial_log_prob, eubo):
+        if not self.use_rescaling:
+            raise NotImplementedError("use_rescaling=False is unreachable from the shipped configs (SURVEY.md App. B.4)")
+        if not isinstance(self.sde, ControlledLangevinSDE):
+            raise NotImplementedError("CMCD needs a ControlledLangevinSDE")
+        info = self._ctrl(use_ema)
+        prior, _ = pack.resolve_log_prob(initial_log_prob)
+        key = self._key(("cmcd", eubo), ts, device, info, (id(prior), id(terminal_unnorm_log_prob)))
+
+        def build():
+            sde = self.sde
+            tsc, pairs = pack._scalar_rows(ts)
+            K = len(pairs)
+            spec = pack.new_spec(self.precision)
+            keep: list = []
+            pack.fill_ctrl(spec, info, device, keep)
+            _terminal(spec, keep, device, terminal_unnorm_log_prob, info)
+            tgt = getattr(sde.target_score, "__self__", None)
+            pri = getattr(sde.prior_score, "__self__", None)
+            target, _ = pack.resolve_log_prob(terminal_unnorm_log_prob)
+            if tgt is not target or pri is not prior:
+                raise NotImplementedError("ControlledLangevinSDE scores must be the bound .score of the rollout's "
+                                          "target and prior distributions")
+            spec.K = K
+            spec.kind = N.ROLLOUT_EUBO_CMCD if eubo else N.ROLLOUT_CMCD
+            spec.cmcd_diff = float(sde.diff_coeff)
+            spec.cmcd_clip = float(sde.clip_score) if sde.clip_score is not None else 0.0
+            table = torch.zeros(K + 1, N.STEP_STRIDE)
+            T = sde.terminal_t.detach().to("cpu")
+            for k in range(K + 1):
+                table[k, N.STEP_FRAC] = tsc[k] / T
+                if k < K:
+                    dt = tsc[k + 1] - tsc[k]
+                    table[k, N.STEP_DT], table[k, N.STEP_SQRT_DT] = dt, dt.sqrt()
+            spec_table = pack.finish_table(table, info, tsc, device)
+            spec.steps = spec_table.data_ptr()
+            keep.append(spec_table)
+            blk0 = pack.gauss_block_from(prior, device)
+            if blk0[1].shape[0] != 1:
+                raise NotImplementedError("CMCD needs a (diagonal) Gaussian prior (solver/oc.py:276-277)")
+            fill_gmm(spec.ref_0, blk0)
+            keep.append(blk0)
+            return pack.Plan(spec, keep, rows=K + 1, noise_steps=K)
+        return self._cached(key, build)
+
+    def simulate(self, ts, x, terminal_unnorm_log_prob, initial_log_prob=None, train: bool = True,
+                 change_sde_ctrl: bool = False, return_traj: bool = False, use_ema: bool = False, noise=None,
+                 seed=None, particle_offset: int = 0):
+        self._check_plain(change_sde_ctrl)
+        if train and self.method in ["kl", "kl_ito"]:
+            raise NotImplementedError("the training variant (rnd starts at 0, oc.py:695-696) is part of SURVEY.md 8f item 1")
+        plan = self._plan(ts, x.device, use_ema, terminal_unnorm_log_prob, initial_log_prob, eubo=False)
+        return pack.run_rollout(plan, x, noise, self._seed(seed), particle_offset, return_traj)
+
+    def compute_eubo(self, ts, x, terminal_unnorm_log_prob, initial_log_prob=None, use_ema: bool = False, noise=None,
+                     seed=None, particle_offset: int = 0):
+        plan = self._plan(ts, x.device, use_ema, terminal_unnorm_log_prob, initial_log_prob, eubo=True)
+        return pack.run_rollout(plan, x, noise, self._seed(seed), particle_offset, False)[1]
+
+    def eval(self, ts, x, terminal_unnorm_log_prob, initial_log_prob=None, compute_weights: bool = True,
+             return_traj: bool = True, use_ema: bool = True, **kw) -> Results:
+        samples, rnd, xs = self.simulate(ts, x, terminal_unnorm_log_prob=terminal_unnorm_log_prob,
+                                         initial_log_prob=initial_log_prob, train=False, return_traj=return_traj,
+                                         use_ema=use_ema, **kw)
+        return BaseOCLoss.compute_results(rnd, compute_weights=compute_weights, ts=ts, samples=samples, xs=xs)
