@@ -64,8 +64,9 @@ typedef enum {
 
 typedef enum {
   LRDS_PRECISION_FP32_SIMT = 0, /* FFMA everywhere (parity anchor) */
-  LRDS_PRECISION_TF32X3 = 1,    /* tcgen05 kind::tf32, 3-pass split: fp32-equivalent drift MLP */
-  LRDS_PRECISION_BF16 = 2       /* tcgen05 kind::f16 single pass: reduced-precision fast mode, reported separately */
+  LRDS_PRECISION_TF32X3 = 1,    /* tcgen05 kind::tf32, 3-pass (hi, lo) split: fp32-grade drift MLP on tensor cores */
+  LRDS_PRECISION_BF16 = 2,      /* tcgen05 kind::f16 single pass: reduced-precision fast mode, reported separately */
+  LRDS_PRECISION_TF32 = 3       /* tcgen05 kind::tf32 single pass: reduced-precision fast mode, reported separately */
 } lrds_precision;
 
 /* Per-step table: one row of `step_stride` floats per grid time (K rows; K+1 for the CMCD kinds, whose
@@ -101,7 +102,7 @@ typedef struct {
   const float* b_hid;   /* [num_hidden][64] */
   const float* w_out_t; /* [64][d_pad]        out_layer.weight^T, zero padded */
   const float* b_out;   /* [d_pad] */
-  const void* tc_image; /* optional packed tensor-core image from lrds_pack_mlp_tc (LRDS_PRECISION_TF32X3/BF16) */
+  const void* tc_image; /* weight image written by lrds_pack_mlp_tc for spec.precision (tensor-core precisions only) */
 } lrds_mlp;
 
 /* Diagonal Gaussian mixture with M >= 1 components.  `step_stride_*` = 0 for a static distribution; for the
@@ -175,6 +176,13 @@ typedef struct {
  */
 int lrds_rollout(const lrds_spec* spec, const float* x0, const float* noise, uint64_t seed,
                  uint64_t particle_offset, float* x_out, float* rnd_out, float* traj_out, void* stream);
+
+/* ---- tensor-core weight image: the FourierMLP weights in the shared-memory operand layout of tcgen05.mma (plus
+ * the fp32 biases), staged once per CTA by a bulk TMA copy.  `image_out` (device, 16-byte aligned) must hold
+ * lrds_tc_image_bytes(d, num_hidden, precision) bytes; set mlp.tc_image to it before lrds_rollout.  Repack after
+ * every weight update. */
+int64_t lrds_tc_image_bytes(int32_t d, int32_t num_hidden, int32_t precision);
+int lrds_pack_mlp_tc(const lrds_mlp* mlp, int32_t precision, void* image_out, void* stream);
 
 /* ---- estimator partials: replaces BaseOCLoss.compute_results (oc.py:134-173), ESS (eval/metrics.py:134-140)
  * and evaluate_eubo (additions/hacking.py:24-32).  Writes 8 doubles to `partials` (device):

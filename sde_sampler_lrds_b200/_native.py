@@ -30,8 +30,8 @@ UPDATE_AXPY, UPDATE_EM = range(2)
 ITO_NONE, ITO_SCALED, ITO_EM, ITO_DDS = range(4)
 CTRL_CLIPPED, CTRL_SCORE = range(2)
 DISTR_NONE, DISTR_GMM, DISTR_PHI4, DISTR_LOGREG = range(4)
-PRECISION_FP32_SIMT, PRECISION_TF32X3, PRECISION_BF16 = range(3)
-PRECISIONS = {"fp32": PRECISION_FP32_SIMT, "tf32x3": PRECISION_TF32X3, "bf16": PRECISION_BF16}
+PRECISION_FP32_SIMT, PRECISION_TF32X3, PRECISION_BF16, PRECISION_TF32 = range(4)
+PRECISIONS = {"fp32": PRECISION_FP32_SIMT, "tf32x3": PRECISION_TF32X3, "bf16": PRECISION_BF16, "tf32": PRECISION_TF32}
 
 FP = C.c_void_p  # device pointers travel as integers
 
@@ -70,28 +70,41 @@ class Spec(C.Structure):
                 ("steps", FP), ("mlp", Mlp), ("target", Distr), ("ref_t", Gmm), ("ref_0", Gmm)]
 
 
-EXPORTS = ["lrds_rollout", "lrds_estimator_blocks", "lrds_estimator_partials", "lrds_ctrl_forward",
+EXPORTS = ["lrds_rollout", "lrds_tc_image_bytes", "lrds_pack_mlp_tc", "lrds_estimator_blocks", "lrds_estimator_partials", "lrds_ctrl_forward",
            "lrds_distr_eval", "lrds_axpy_step", "lrds_normals", "lrds_last_error", "lrds_abi_version",
            "lrds_launch_count"]
 
-NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-              "-shared", "-Xcompiler", "-fPIC"]
+COMPILE_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+                 "-Xcompiler", "-fPIC"]
+LINK_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-Xcompiler", "-fPIC"]
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
     """Compiles csrc/*.cu into csrc/liblrds_b200.so for sm_100a (cross-compiles without a GPU)."""
-    srcs = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cu", ".cuh"))]
+    srcs = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cu", ".cuh", ".h"))]
     srcs.append(os.path.join(INCLUDE, "lrds_b200.h"))
     if not force and os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(s) for s in srcs):
         return LIB_PATH
-    cmd = ["nvcc", *NVCC_FLAGS, "-I", INCLUDE, "-o", LIB_PATH, os.path.join(CSRC, "lrds_capi.cu")]
-    if verbose:
-        cmd.insert(1, "-Xptxas=-v")
-    res = subprocess.run(cmd, capture_output=True, text=True)
+    units = [f for f in sorted(os.listdir(CSRC)) if f.endswith(".cu")]
+    objs, procs = [], []
+    for u in units:  # one nvcc per translation unit, in parallel
+        obj = os.path.join(CSRC, u[:-3] + ".o")
+        cmd = ["nvcc", *COMPILE_FLAGS, "-I", INCLUDE, "-c", "-o", obj, os.path.join(CSRC, u)]
+        if verbose:
+            cmd.insert(1, "-Xptxas=-v")
+        procs.append((u, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+        objs.append(obj)
+    log = ""
+    for u, p in procs:
+        out, _ = p.communicate()
+        log += out
+        if p.returncode != 0:
+            raise RuntimeError(f"nvcc failed on {u}:\n" + out)
+    res = subprocess.run(["nvcc", *LINK_FLAGS, "-o", LIB_PATH, *objs], capture_output=True, text=True)
     if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+        raise RuntimeError("link failed:\n" + res.stdout + res.stderr)
     if verbose:
-        print(res.stderr)
+        print(log)
     return LIB_PATH
 
 
@@ -113,6 +126,9 @@ def lib():
                 L.lrds_last_error.restype = C.c_char_p
                 L.lrds_launch_count.restype = C.c_int64
                 L.lrds_rollout.argtypes = [C.POINTER(Spec), FP, FP, C.c_uint64, C.c_uint64, FP, FP, FP, FP]
+                L.lrds_tc_image_bytes.restype = C.c_int64
+                L.lrds_tc_image_bytes.argtypes = [C.c_int32, C.c_int32, C.c_int32]
+                L.lrds_pack_mlp_tc.argtypes = [C.POINTER(Mlp), C.c_int32, FP, FP]
                 L.lrds_estimator_blocks.argtypes = [C.c_int32]
                 L.lrds_estimator_partials.argtypes = [FP, C.c_int32, FP, FP, FP]
                 L.lrds_ctrl_forward.argtypes = [C.POINTER(Spec), C.c_int32, FP, C.c_int32, FP, FP]

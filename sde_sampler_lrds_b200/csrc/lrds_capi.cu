@@ -6,8 +6,8 @@
 #include <cstdio>
 #include <cstring>
 
+#include "lrds_internal.h"
 #include "lrds_rollout_simt.cuh"
-#include "lrds_rollout_tc.cuh"
 
 namespace {
 
@@ -172,24 +172,24 @@ __global__ void __launch_bounds__(128) ctrl_forward_kernel(const lrds_spec s, in
   const ColLayout L = col_layout(s);
   Particle P;
   P.x = Col{smem + L.x * NT + tid, NT};
-  P.act = Col{smem + L.act * NT + tid, NT};
   P.rt = Col{smem + L.rt * NT + tid, NT};
   P.rr = Col{smem + L.rr * NT + tid, NT};
   P.g = Col{smem + L.g * NT + tid, NT};
   P.us = P.tsd = P.db = P.x;
+  SimtMlp mlp{s.mlp, Col{smem + L.act * NT + tid, NT}};
   const int d = s.d, dp = s.mlp.d_pad;
   for (int j = 0; j < dp; ++j) P.x(j) = (j < d) ? __ldg(x + (int64_t)b * d + j) : 0.f;
   const float* row = s.steps + (int64_t)rowi * LRDS_STEP_STRIDE;
   const bool score_ctrl = s.ctrl_kind == LRDS_CTRL_SCORE;
   if (score_ctrl) target_pass1(s, P, false);
-  mlp_hidden(s.mlp, row + LRDS_STEP_BIAS1, P.x, P.act);
+  mlp.hidden(row + LRDS_STEP_BIAS1, P.x);
   float xm = 0.f;
   for (int j0 = 0; j0 < dp; j0 += JC) {
     float xr[JC], ts[JC], u[JC];
     load_chunk(P.x, j0, xr);
     const float xp = (j0 + JC < dp) ? P.x(j0 + JC) : 0.f;
     if (score_ctrl) target_score_chunk(s, P, xr, xm, xp, j0, ts);
-    ctrl_chunk(s, P, j0, ts, __ldg(row + LRDS_STEP_GAMMA), u);
+    ctrl_chunk(s, mlp, j0, ts, __ldg(row + LRDS_STEP_GAMMA), u);
     xm = xr[JC - 1];
     if (live)
 #pragma unroll
@@ -209,7 +209,6 @@ __global__ void __launch_bounds__(128) distr_eval_kernel(const lrds_spec s, cons
   const ColLayout L = col_layout(s);
   Particle P;
   P.x = Col{smem + L.x * NT + tid, NT};
-  P.act = Col{smem + L.act * NT + tid, NT};
   P.rt = Col{smem + L.rt * NT + tid, NT};
   P.rr = Col{smem + L.rr * NT + tid, NT};
   P.g = Col{smem + L.g * NT + tid, NT};
@@ -300,10 +299,8 @@ int lrds_rollout(const lrds_spec* spec, const float* x0, const float* noise, uin
   lrds::RolloutArgs a{s, x0, noise, seed, particle_offset, x_out, rnd_out, traj_out};
 
   if (s.precision != LRDS_PRECISION_FP32_SIMT) {
-    int r = lrds::launch_rollout_tc(a, st);
+    const int r = lrds::launch_rollout_tc(a, st, g_err, sizeof(g_err));
     if (r == LRDS_OK) g_launches.fetch_add(1);
-    else if (r == LRDS_ERR_UNSUPPORTED) return fail(r, "tensor-core rollout does not cover this spec: %s", lrds::tc_unsupported_reason());
-    else if (r == LRDS_ERR_CUDA) return cuda_fail(cudaGetLastError(), "tensor-core rollout launch");
     return r;
   }
 
@@ -328,6 +325,23 @@ int lrds_rollout(const lrds_spec* spec, const float* x0, const float* noise, uin
   }
 }
 
+int64_t lrds_tc_image_bytes(int32_t d, int32_t num_hidden, int32_t precision) {
+  if (d < 1 || num_hidden < 0 || precision == LRDS_PRECISION_FP32_SIMT || precision < 0 || precision > LRDS_PRECISION_TF32)
+    return fail(LRDS_ERR_INVALID, "tc_image_bytes: bad arguments");
+  return (int64_t)lrds::tc_image_bytes(d, num_hidden, precision);
+}
+
+int lrds_pack_mlp_tc(const lrds_mlp* mlp, int32_t precision, void* image_out, void* stream) {
+  if (!mlp || !image_out || !mlp->w_in_t || !mlp->w_out_t || !mlp->b_out || mlp->d < 1 ||
+      mlp->d_pad != ((mlp->d + 7) / 8) * 8 || (mlp->num_hidden > 0 && (!mlp->w_hid_t || !mlp->b_hid)))
+    return fail(LRDS_ERR_INVALID, "pack_mlp_tc: incomplete mlp block");
+  if (precision != LRDS_PRECISION_TF32X3 && precision != LRDS_PRECISION_BF16 && precision != LRDS_PRECISION_TF32)
+    return fail(LRDS_ERR_INVALID, "pack_mlp_tc: not a tensor-core precision");
+  const int r = lrds::pack_tc_image(*mlp, precision, image_out, (cudaStream_t)stream, g_err, sizeof(g_err));
+  if (r == LRDS_OK) g_launches.fetch_add(1);
+  return r;
+}
+
 int lrds_estimator_blocks(int32_t B) { return B < 1 ? 0 : (B + EST_PER_BLOCK - 1) / EST_PER_BLOCK; }
 
 int lrds_estimator_partials(const float* rnd, int32_t B, double* partials, double* scratch, void* stream) {
@@ -350,6 +364,7 @@ int lrds_ctrl_forward(const lrds_spec* spec, int32_t row, const float* x, int32_
   lrds_spec s = *spec;
   s.B = B;
   s.kind = LRDS_ROLLOUT_LINEAR;
+  s.precision = LRDS_PRECISION_FP32_SIMT;  // this entry point evaluates the network with fp32 FFMA
   s.has_ref_ctrl = 0;
   s.ref_0.M = 0;
   const lrds::ColLayout L = lrds::col_layout(s);

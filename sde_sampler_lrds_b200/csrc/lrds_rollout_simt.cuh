@@ -1,10 +1,13 @@
-// fp32 SIMT rollout kernel: one thread integrates one particle through all K steps.  Particle state
-// (x, hidden activations, mixture responsibilities, CMCD carry-over) lives in shared-memory columns for the
-// whole rollout; HBM is touched only for x0, the optional recorded noise / trajectory, and the results.
-// Weights, per-step tables and distribution parameters are warp-uniform broadcast loads served by L1/L2.
+// The rollout body: one thread integrates one particle through all K steps.  Particle state (x, mixture
+// responsibilities, CMCD carry-over) lives in shared-memory columns for the whole rollout; HBM is touched only
+// for x0, the optional recorded noise / trajectory, and the results.  Per-step tables and distribution
+// parameters are warp-uniform broadcast loads served by L1/L2.
 //
-// This is the parity anchor (LRDS_PRECISION_FP32_SIMT): the tensor-core path shares every device function
-// below except the three MLP GEMMs.
+// The drift network is a policy (template parameter MLP) with two hooks:
+//   mlp.hidden(bias1, x)      run the network up to (and, on tensor cores, including) the output GEMM
+//   mlp.out_chunk(j0, out)    out_layer(x)[j0 .. j0+8) including its bias
+// SimtMlp (below) is the fp32 FFMA parity anchor (LRDS_PRECISION_FP32_SIMT); TcMlp (lrds_rollout_tc.cuh) runs the
+// four GEMMs on tcgen05 with TMEM-resident operands.  Everything else is shared between the two.
 #pragma once
 #include "lrds_device.cuh"
 
@@ -31,7 +34,8 @@ __host__ __device__ inline ColLayout col_layout(const lrds_spec& s) {
   int off = 0;
   const int dp = s.mlp.d_pad;
   L.x = off; off += dp;
-  L.act = off; off += C;
+  L.act = off;
+  if (s.precision == LRDS_PRECISION_FP32_SIMT) off += C;  // hidden activations: tensor-core backends keep them in TMEM
   L.rt = off;
   if (s.target.kind == LRDS_DISTR_GMM && s.target.gmm.M > 1) off += s.target.gmm.M;
   L.rr = off;
@@ -56,7 +60,15 @@ __host__ __device__ inline ColLayout col_layout(const lrds_spec& s) {
 }
 
 struct Particle {
-  Col x, act, rt, rr, g, us, tsd, db;
+  Col x, rt, rr, g, us, tsd, db;
+};
+
+// fp32 FFMA drift network: hidden activations in 64 shared-memory columns per particle
+struct SimtMlp {
+  const lrds_mlp& w;
+  Col act;
+  __device__ __forceinline__ void hidden(const float* __restrict__ bias1, const Col& x) { mlp_hidden(w, bias1, x, act); }
+  __device__ __forceinline__ void out_chunk(int j0, float (&out)[JC]) { mlp_out_chunk(w, act, j0, out); }
 };
 
 // ---- target helpers ---------------------------------------------------------------------------------
@@ -99,9 +111,10 @@ __device__ __forceinline__ void load_chunk(const Col& v, int j0, float (&out)[JC
 
 // control u = generative_ctrl(tau, x) for dims [j0, j0+JC), given act = hidden activations at (tau, x),
 // the raw target score chunk `ts` (ScoreCtrl) and gamma = clip(score_model(tau)).
-__device__ __forceinline__ void ctrl_chunk(const lrds_spec& s, const Particle& P, int j0, const float (&ts)[JC],
-                                           float gamma, float (&u)[JC]) {
-  mlp_out_chunk(s.mlp, P.act, j0, u);
+template <class MLP>
+__device__ __forceinline__ void ctrl_chunk(const lrds_spec& s, MLP& mlp, int j0, const float (&ts)[JC], float gamma,
+                                           float (&u)[JC]) {
+  mlp.out_chunk(j0, u);
 #pragma unroll
   for (int c = 0; c < JC; ++c) {
     float v = clipf(u[c], s.clip_model);
@@ -142,9 +155,10 @@ __device__ __forceinline__ float langevin_drift(const lrds_spec& s, float ts, fl
   return clipf(dr, s.cmcd_clip);
 }
 
-template <int KIND>
-__global__ void __launch_bounds__(128) rollout_simt_kernel(const RolloutArgs a) {
-  extern __shared__ float smem[];
+// `smem` = this CTA's column area (col_layout(s).total * blockDim.x floats); every thread of the CTA runs the body
+// with uniform control flow (idle lanes shadow the last particle), which the tensor-core policy relies on.
+template <int KIND, class MLP>
+__device__ __forceinline__ void rollout_body(const RolloutArgs& a, float* smem, MLP& mlp) {
   const lrds_spec& s = a.s;
   const int NT = blockDim.x;
   const int tid = threadIdx.x;
@@ -155,7 +169,6 @@ __global__ void __launch_bounds__(128) rollout_simt_kernel(const RolloutArgs a) 
   const ColLayout L = col_layout(s);
   Particle P;
   P.x = Col{smem + L.x * NT + tid, NT};
-  P.act = Col{smem + L.act * NT + tid, NT};
   P.rt = Col{smem + L.rt * NT + tid, NT};
   P.rr = Col{smem + L.rr * NT + tid, NT};
   P.g = Col{smem + L.g * NT + tid, NT};
@@ -183,14 +196,14 @@ __global__ void __launch_bounds__(128) rollout_simt_kernel(const RolloutArgs a) 
         rv = gmm_at(s.ref_t, k);
         if (rv.M > 1) gmm_pass1(rv, d, P.x, P.rr);
       }
-      mlp_hidden(s.mlp, row + LRDS_STEP_BIAS1, P.x, P.act);
+      mlp.hidden(row + LRDS_STEP_BIAS1, P.x);
       float su2 = 0.f, sito = 0.f, xm = 0.f;
       for (int j0 = 0; j0 < dp; j0 += JC) {
         float xr[JC], ts[JC], u[JC], rs[JC], z[JC], xn[JC];
         load_chunk(P.x, j0, xr);
         const float xp = (j0 + JC < dp) ? P.x(j0 + JC) : 0.f;
         if (score_ctrl) target_score_chunk(s, P, xr, xm, xp, j0, ts);
-        ctrl_chunk(s, P, j0, ts, gamma, u);
+        ctrl_chunk(s, mlp, j0, ts, gamma, u);
         if (s.has_ref_ctrl) gmm_score_chunk(rv, d, xr, P.rr, j0, rs);
         noise_chunk(a, k, b, j0, z);
 #pragma unroll
@@ -248,14 +261,14 @@ __global__ void __launch_bounds__(128) rollout_simt_kernel(const RolloutArgs a) 
       if (score_ctrl) target_pass1(s, P, false);
       const GmmView rv = gmm_at(s.ref_t, k);
       if (rv.M > 1) gmm_pass1(rv, d, P.x, P.rr);
-      mlp_hidden(s.mlp, row + LRDS_STEP_BIAS1, P.x, P.act);
+      mlp.hidden(row + LRDS_STEP_BIAS1, P.x);
       float cost = 0.f, gx = 0.f, gz = 0.f, xm = 0.f;
       for (int j0 = 0; j0 < dp; j0 += JC) {
         float xr[JC], ts[JC], u[JC], rs[JC];
         load_chunk(P.x, j0, xr);
         const float xp = (j0 + JC < dp) ? P.x(j0 + JC) : 0.f;
         if (score_ctrl) target_score_chunk(s, P, xr, xm, xp, j0, ts);
-        ctrl_chunk(s, P, j0, ts, gamma, u);
+        ctrl_chunk(s, mlp, j0, ts, gamma, u);
         gmm_score_chunk(rv, d, xr, P.rr, j0, rs);
 #pragma unroll
         for (int c = 0; c < JC; ++c) {
@@ -281,14 +294,14 @@ __global__ void __launch_bounds__(128) rollout_simt_kernel(const RolloutArgs a) 
       const float* row = s.steps + (int64_t)rowi * LRDS_STEP_STRIDE;
       const float gamma = __ldg(row + LRDS_STEP_GAMMA);
       target_pass1(s, P, false);
-      mlp_hidden(s.mlp, row + LRDS_STEP_BIAS1, P.x, P.act);
+      mlp.hidden(row + LRDS_STEP_BIAS1, P.x);
       float xm = 0.f;
       for (int j0 = 0; j0 < dp; j0 += JC) {
         float xr[JC], ts[JC], u[JC];
         load_chunk(P.x, j0, xr);
         const float xp = (j0 + JC < dp) ? P.x(j0 + JC) : 0.f;
         target_score_chunk(s, P, xr, xm, xp, j0, ts);
-        ctrl_chunk(s, P, j0, ts, gamma, u);
+        ctrl_chunk(s, mlp, j0, ts, gamma, u);
 #pragma unroll
         for (int c = 0; c < JC; ++c) {
           const int j = j0 + c;
@@ -385,6 +398,14 @@ __global__ void __launch_bounds__(128) rollout_simt_kernel(const RolloutArgs a) 
     if (a.x_out != nullptr)
       for (int j = 0; j < d; ++j) a.x_out[(int64_t)b * d + j] = P.x(j);
   }
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(128) rollout_simt_kernel(const RolloutArgs a) {
+  extern __shared__ float smem[];
+  const ColLayout L = col_layout(a.s);
+  SimtMlp mlp{a.s.mlp, Col{smem + L.act * blockDim.x + threadIdx.x, (int)blockDim.x}};
+  rollout_body<KIND>(a, smem, mlp);
 }
 
 }  // namespace lrds

@@ -1,9 +1,328 @@
-// tcgen05 tensor-core rollout (LRDS_PRECISION_TF32X3 / BF16).  Placeholder until the kernel lands:
-// every spec is reported as unsupported so that callers fail loudly instead of silently using SIMT.
+// tcgen05 tensor-core drift network (LRDS_PRECISION_TF32 / TF32X3 / BF16) and the kernel wrapper that runs the
+// shared rollout body (lrds_rollout_simt.cuh) with it.
+//
+// Mapping.  A CTA holds W <= 16 warps = up to four 128-particle tiles; warp w integrates particles
+// [32 w, 32 w + 32) of the CTA and owns TMEM lanes 32 (w % 4) .. +31 of tile w / 4, i.e. thread <-> particle <->
+// TMEM lane <-> row of every GEMM.  Per grid step and tile the FourierMLP (models/mlp.py:135-143) is four GEMMs
+//     [128 x Kin] . W_in^T -> GELU -> [128 x 64] . W_h^T -> GELU -> ... -> [128 x 64] . W_out^T
+// issued by the tile's first thread as tcgen05.mma with the A operand in TMEM (written by the particles' own
+// threads with tcgen05.st), B = the weight image in shared memory (K-major, no swizzle; staged ONCE per CTA by a
+// bulk TMA copy) and the fp32 accumulator in TMEM (read back with tcgen05.ld for bias + GELU).  Activations never
+// touch shared or global memory.  Tiles of one CTA run out of phase, so one tile's MMA latency is covered by the
+// other tiles' SIMT work (scores, noise, integrator).
+//
+// Precisions: TF32X3 splits both operands into tf32 (hi, lo) and accumulates lo*hi + hi*lo + hi*hi (fp32-grade
+// products, the parity mode); TF32 and BF16 are single-pass reduced-precision modes reported separately.
 #pragma once
 #include "lrds_rollout_simt.cuh"
+#include "lrds_tc_ptx.cuh"
 
 namespace lrds {
-inline const char* tc_unsupported_reason() { return "tensor-core path not built yet"; }
-inline int launch_rollout_tc(const RolloutArgs&, cudaStream_t) { return LRDS_ERR_UNSUPPORTED; }
+
+constexpr int TC_MAX_WARPS = 16;
+constexpr int TC_TAIL_BYTES = 64;  // mbarriers + TMEM slot after the image
+
+struct TcLayout {
+  int prec, parts, es, kstep;
+  int Kin, Nout, nh;
+  uint32_t part_bytes, off_in, off_hid, off_out;  // one part = all layers of one (hi | lo) image
+  uint32_t off_bhid, off_bout, bytes;             // fp32 biases behind the parts; total bytes (multiple of 16)
+  int a_cols, d_cols, tile_cols;                  // TMEM columns: one A part, the accumulator, one tile
+};
+
+__host__ __device__ inline TcLayout tc_layout(int d, int nh, int prec) {
+  TcLayout L{};
+  L.prec = prec;
+  L.parts = prec == LRDS_PRECISION_TF32X3 ? 2 : 1;
+  L.es = prec == LRDS_PRECISION_BF16 ? 2 : 4;
+  L.kstep = prec == LRDS_PRECISION_BF16 ? 16 : 8;
+  L.Kin = (d + L.kstep - 1) / L.kstep * L.kstep;
+  L.Nout = (d + 15) / 16 * 16;
+  L.nh = nh;
+  L.off_in = 0;
+  L.off_hid = (uint32_t)(C * L.Kin * L.es);
+  L.off_out = L.off_hid + (uint32_t)(nh * C * C * L.es);
+  L.part_bytes = L.off_out + (uint32_t)(L.Nout * C * L.es);
+  L.off_bhid = L.parts * L.part_bytes;
+  L.off_bout = L.off_bhid + (uint32_t)((nh > 0 ? nh : 1) * C * 4);
+  L.bytes = L.off_bout + (uint32_t)(L.Nout * 4);
+  L.a_cols = (L.Kin > C ? L.Kin : C) * L.es / 4;
+  L.d_cols = L.Nout > C ? L.Nout : C;
+  L.tile_cols = L.parts * L.a_cols + L.d_cols;
+  return L;
+}
+
+// ---- weight image ------------------------------------------------------------------------------------------------
+// B operand of layer (N x K, K-major, no swizzle): 16-byte K chunk kc of row n at  kc * N * 16 + n * 16.
+__global__ void pack_tc_image_kernel(const lrds_mlp w, const TcLayout L, uint8_t* __restrict__ img) {
+  const int E = 16 / L.es;
+  const int n_in = C * L.Kin, n_hid = L.nh * C * C, n_out = L.Nout * C;
+  const int total = n_in + n_hid + n_out;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    float v;
+    uint32_t off;
+    int n, k, N;
+    if (idx < n_in) {
+      n = idx / L.Kin; k = idx % L.Kin; N = C; off = L.off_in;
+      v = k < w.d ? w.w_in_t[(int64_t)k * C + n] : 0.f;
+    } else if (idx < n_in + n_hid) {
+      const int r = idx - n_in, l = r / (C * C);
+      n = (r / C) % C; k = r % C; N = C; off = L.off_hid + (uint32_t)(l * C * C * L.es);
+      v = w.w_hid_t[(int64_t)l * C * C + (int64_t)k * C + n];
+    } else {
+      const int r = idx - n_in - n_hid;
+      n = r / C; k = r % C; N = L.Nout; off = L.off_out;
+      v = n < w.d_pad ? w.w_out_t[(int64_t)k * w.d_pad + n] : 0.f;
+    }
+    const uint32_t byte = off + (uint32_t)(k / E) * N * 16u + (uint32_t)n * 16u + (uint32_t)(k % E) * L.es;
+    if (L.prec == LRDS_PRECISION_BF16) {
+      *reinterpret_cast<uint16_t*>(img + byte) = (uint16_t)(ptx::pack_bf16x2(v, 0.f) & 0xFFFFu);
+    } else {
+      const float hi = ptx::to_tf32(v);
+      *reinterpret_cast<float*>(img + byte) = hi;
+      if (L.parts == 2) *reinterpret_cast<float*>(img + L.part_bytes + byte) = ptx::to_tf32(v - hi);
+    }
+  }
+  float* bh = reinterpret_cast<float*>(img + L.off_bhid);
+  float* bo = reinterpret_cast<float*>(img + L.off_bout);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < (L.nh > 0 ? L.nh : 1) * C; i += gridDim.x * blockDim.x)
+    bh[i] = i < L.nh * C ? w.b_hid[i] : 0.f;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < L.Nout; i += gridDim.x * blockDim.x)
+    bo[i] = i < w.d_pad ? w.b_out[i] : 0.f;
+}
+
+// ---- the policy --------------------------------------------------------------------------------------------------
+template <int PREC>
+struct TcMlp {
+  TcLayout L;
+  const uint8_t* img;  // weight image in shared memory
+  uint32_t img_s;      // its shared-window address
+  uint32_t tm_tile;    // TMEM address of the tile's column 0 at lane 0 (MMA operands)
+  uint32_t tm_lane;    // the same at this warp's first lane (tcgen05.ld / st)
+  uint64_t* bar;       // the tile's MMA-completion mbarrier
+  uint32_t phase;
+  int bar_id, bar_threads;
+  bool issuer;
+  int dp;              // columns of x held by the body (d rounded up to 8, zero padded)
+
+  __device__ __forceinline__ uint32_t a_col(int part) const { return (uint32_t)(part * L.a_cols); }
+  __device__ __forceinline__ uint32_t d_col() const { return (uint32_t)(L.parts * L.a_cols); }
+
+  // every particle thread has stored its A row: make it visible to the tensor core, then one thread issues the
+  // layer's MMAs and commits them to the tile's mbarrier.
+  __device__ __forceinline__ void issue(uint32_t b_off, int K, int N) {
+    ptx::tmem_wait_st();
+    ptx::tc_fence_before();
+    ptx::bar_sync(bar_id, bar_threads);
+    if (issuer) {
+      ptx::tc_fence_after();
+      const uint32_t idesc = PREC == LRDS_PRECISION_BF16 ? ptx::make_idesc_bf16(128, N) : ptx::make_idesc_tf32(128, N);
+      const uint32_t dcol = tm_tile + d_col();
+      const int ksteps = K / L.kstep;
+      const uint32_t kbytes = 2u * (uint32_t)N * 16u;  // one MMA consumes two 16-byte K chunks
+      uint32_t acc = 0;
+      auto pass = [&](int a_part, int b_part) {
+        const uint32_t abase = tm_tile + a_col(a_part);
+        const uint32_t bbase = img_s + (uint32_t)b_part * L.part_bytes + b_off;
+        for (int ks = 0; ks < ksteps; ++ks) {
+          const uint64_t bdesc = ptx::make_smem_desc(bbase + (uint32_t)ks * kbytes, (uint32_t)N * 16u, 128u);
+          if (PREC == LRDS_PRECISION_BF16) ptx::mma_bf16_ts(dcol, abase + ks * 8, bdesc, idesc, acc);
+          else ptx::mma_tf32_ts(dcol, abase + ks * 8, bdesc, idesc, acc);
+          acc = 1;
+        }
+      };
+      if (PREC == LRDS_PRECISION_TF32X3) {  // small terms first
+        pass(1, 0);
+        pass(0, 1);
+      }
+      pass(0, 0);
+      ptx::mma_commit(bar);
+    }
+  }
+  __device__ __forceinline__ void wait() {
+    ptx::mbar_wait(bar, phase);
+    phase ^= 1u;
+    ptx::tc_fence_after();
+  }
+
+  // A operand <- 8 consecutive fp32 values (columns c0 .. c0+7 of the K axis)
+  __device__ __forceinline__ void store8(int c0, const float (&v)[8]) {
+    if (PREC == LRDS_PRECISION_BF16) {
+      // handled by store16_bf16
+    } else {
+      uint32_t hi[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) hi[i] = __float_as_uint(ptx::to_tf32(v[i]));
+      ptx::tmem_st8(tm_lane + a_col(0) + c0, hi);
+      if (PREC == LRDS_PRECISION_TF32X3) {
+        uint32_t lo[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) lo[i] = __float_as_uint(ptx::to_tf32(v[i] - __uint_as_float(hi[i])));
+        ptx::tmem_st8(tm_lane + a_col(1) + c0, lo);
+      }
+    }
+  }
+
+  __device__ __forceinline__ void store_x(const Col& x) {
+    if (PREC == LRDS_PRECISION_BF16) {
+      for (int c0 = 0; c0 < L.Kin / 2; c0 += 8) {
+        uint32_t r[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int j = 2 * (c0 + i);
+          r[i] = ptx::pack_bf16x2(j < dp ? x(j) : 0.f, j + 1 < dp ? x(j + 1) : 0.f);
+        }
+        ptx::tmem_st8(tm_lane + a_col(0) + c0, r);
+      }
+    } else {
+      for (int c0 = 0; c0 < L.Kin; c0 += 8) {  // Kin == dp for the tf32 kinds
+        float v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = x(c0 + i);
+        store8(c0, v);
+      }
+    }
+  }
+
+  // accumulator (64 columns) + bias -> GELU -> A operand of the next layer
+  template <bool GLOBAL_BIAS>
+  __device__ __forceinline__ void epilogue(const float* __restrict__ bias) {
+#pragma unroll 1
+    for (int c0 = 0; c0 < C; c0 += 32) {
+      uint32_t r[32];
+      ptx::tmem_ld32(tm_lane + d_col() + c0, r);
+      ptx::tmem_wait_ld();
+      float g[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const float b = GLOBAL_BIAS ? __ldg(bias + c0 + i) : bias[c0 + i];
+        g[i] = gelu_exact(__uint_as_float(r[i]) + b);
+      }
+      if (PREC == LRDS_PRECISION_BF16) {
+        uint32_t p[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) p[i] = ptx::pack_bf16x2(g[2 * i], g[2 * i + 1]);
+        ptx::tmem_st16(tm_lane + a_col(0) + c0 / 2, p);
+      } else {
+        uint32_t hi[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) hi[i] = __float_as_uint(ptx::to_tf32(g[i]));
+        ptx::tmem_st32(tm_lane + a_col(0) + c0, hi);
+        if (PREC == LRDS_PRECISION_TF32X3) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) hi[i] = __float_as_uint(ptx::to_tf32(g[i] - __uint_as_float(hi[i])));
+          ptx::tmem_st32(tm_lane + a_col(1) + c0, hi);
+        }
+      }
+    }
+  }
+
+  __device__ __forceinline__ void hidden(const float* __restrict__ bias1, const Col& x) {
+    store_x(x);
+    issue(L.off_in, L.Kin, C);
+    const float* bh = reinterpret_cast<const float*>(img + L.off_bhid);
+    for (int l = 0; l < L.nh; ++l) {
+      wait();
+      if (l == 0) epilogue<true>(bias1);
+      else epilogue<false>(bh + (l - 1) * C);
+      issue(L.off_hid + (uint32_t)(l * C * C * L.es), C, C);
+    }
+    wait();
+    if (L.nh == 0) epilogue<true>(bias1);
+    else epilogue<false>(bh + (L.nh - 1) * C);
+    issue(L.off_out, C, L.Nout);
+    wait();
+  }
+
+  __device__ __forceinline__ void out_chunk(int j0, float (&out)[JC]) {
+    uint32_t r[8];
+    ptx::tmem_ld8(tm_lane + d_col() + j0, r);
+    ptx::tmem_wait_ld();
+    const float4* b4 = reinterpret_cast<const float4*>(img + L.off_bout + j0 * 4);
+    const float4 a = b4[0], b = b4[1];
+    out[0] = __uint_as_float(r[0]) + a.x; out[1] = __uint_as_float(r[1]) + a.y;
+    out[2] = __uint_as_float(r[2]) + a.z; out[3] = __uint_as_float(r[3]) + a.w;
+    out[4] = __uint_as_float(r[4]) + b.x; out[5] = __uint_as_float(r[5]) + b.y;
+    out[6] = __uint_as_float(r[6]) + b.z; out[7] = __uint_as_float(r[7]) + b.w;
+  }
+};
+
+// ---- kernel --------------------------------------------------------------------------------------------------------
+template <int KIND, int PREC>
+__global__ void __launch_bounds__(TC_MAX_WARPS * 32, 1)
+rollout_tc_kernel(const RolloutArgs a, const uint8_t* __restrict__ image, const uint32_t tmem_cols) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  const TcLayout TL = tc_layout(a.s.d, a.s.mlp.num_hidden, PREC);
+  const int tid = threadIdx.x, warp = tid >> 5, nwarps = blockDim.x >> 5;
+  uint8_t* img = smem_raw;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + TL.bytes);  // [0] image, [1 + t] tile t
+  uint32_t* slot = reinterpret_cast<uint32_t*>(smem_raw + TL.bytes + 48);
+  float* cols = reinterpret_cast<float*>(smem_raw + TL.bytes + TC_TAIL_BYTES);
+  if (warp == 0) ptx::tmem_alloc(slot, tmem_cols);
+  if (tid == 0) {
+    for (int i = 0; i < 5; ++i) ptx::mbar_init(bars + i, 1);
+    ptx::fence_mbar_init();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  if (tid == 0) {  // drift weights staged once per CTA by the TMA engine
+    ptx::mbar_expect_tx(bars, TL.bytes);
+    ptx::bulk_g2s(img, image, TL.bytes, bars);
+  }
+  ptx::mbar_wait(bars, 0);
+  const uint32_t tmem = *slot;
+  const int tile = warp >> 2;
+  const int tile_warps = min(4, nwarps - 4 * tile);
+  TcMlp<PREC> mlp;
+  mlp.L = TL;
+  mlp.img = img;
+  mlp.img_s = ptx::smem_u32(img);
+  mlp.tm_tile = tmem + (uint32_t)(tile * TL.tile_cols);
+  mlp.tm_lane = mlp.tm_tile + ((uint32_t)((warp & 3) * 32) << 16);
+  mlp.bar = bars + 1 + tile;
+  mlp.phase = 0;
+  mlp.bar_id = 1 + tile;
+  mlp.bar_threads = tile_warps * 32;
+  mlp.issuer = (tid & 127) == 0;
+  mlp.dp = a.s.mlp.d_pad;
+  rollout_body<KIND>(a, cols, mlp);
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) ptx::tmem_dealloc(tmem, tmem_cols);
+}
+
+// ---- host side -------------------------------------------------------------------------------------------------------
+struct TcPlan {
+  int warps, grid;
+  uint32_t tmem_cols;
+  size_t smem;
+};
+
+// Warps per CTA: as few waves as possible over the SMs (one CTA per SM), then as few idle lanes as possible.
+inline int plan_rollout_tc(const lrds_spec& s, int smem_cap, int sms, TcPlan* out, const char** why) {
+  const TcLayout TL = tc_layout(s.d, s.mlp.num_hidden, s.precision);
+  const ColLayout CL = col_layout(s);
+  const size_t fixed = (size_t)TL.bytes + TC_TAIL_BYTES;
+  const size_t per_warp = (size_t)CL.total * 32 * sizeof(float);
+  if (TL.tile_cols > 512) { *why = "TMEM columns of one tile exceed 512"; return LRDS_ERR_RESOURCES; }
+  if (fixed + per_warp > (size_t)smem_cap) { *why = "weight image + one warp of particle state exceed shared memory"; return LRDS_ERR_RESOURCES; }
+  int wmax = (int)(((size_t)smem_cap - fixed) / per_warp);
+  wmax = wmax < TC_MAX_WARPS ? wmax : TC_MAX_WARPS;
+  const int tmax = 512 / TL.tile_cols;
+  wmax = wmax < 4 * tmax ? wmax : 4 * tmax;
+  const int need = (s.B + 31) / 32;
+  const int waves = (need + sms * wmax - 1) / (sms * wmax);
+  int w = (need + sms * waves - 1) / (sms * waves);
+  w = w < 1 ? 1 : (w > wmax ? wmax : w);
+  const int tiles = (w + 3) / 4;
+  uint32_t cols = 32;
+  while ((int)cols < tiles * TL.tile_cols) cols <<= 1;
+  out->warps = w;
+  out->grid = (need + w - 1) / w;
+  out->tmem_cols = cols;
+  out->smem = fixed + per_warp * w;
+  return LRDS_OK;
+}
+
 }  // namespace lrds

@@ -1,0 +1,82 @@
+// Tensor-core rollout: kernel instantiations, launch planning and the weight-image packer (its own translation
+// unit so that it compiles in parallel with lrds_capi.cu).
+#include <cuda_runtime.h>
+
+#include <cstdio>
+
+#include "lrds_internal.h"
+#include "lrds_rollout_tc.cuh"
+
+namespace lrds {
+
+namespace {
+
+template <int KIND, int PREC>
+int launch_one(const RolloutArgs& a, const TcPlan& p, cudaStream_t st, char* err, size_t n) {
+  auto kernel = rollout_tc_kernel<KIND, PREC>;
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
+  if (e == cudaSuccess) {
+    kernel<<<p.grid, p.warps * 32, p.smem, st>>>(a, static_cast<const uint8_t*>(a.s.mlp.tc_image), p.tmem_cols);
+    e = cudaGetLastError();
+  }
+  if (e != cudaSuccess) {
+    snprintf(err, n, "tensor-core rollout launch (grid %d x %d threads, %zu B smem, %u TMEM cols): %s", p.grid,
+             p.warps * 32, p.smem, p.tmem_cols, cudaGetErrorString(e));
+    return LRDS_ERR_CUDA;
+  }
+  return LRDS_OK;
+}
+
+template <int PREC>
+int launch_kind(const RolloutArgs& a, const TcPlan& p, cudaStream_t st, char* err, size_t n) {
+  switch (a.s.kind) {
+    case LRDS_ROLLOUT_LINEAR: return launch_one<LRDS_ROLLOUT_LINEAR, PREC>(a, p, st, err, n);
+    case LRDS_ROLLOUT_CMCD: return launch_one<LRDS_ROLLOUT_CMCD, PREC>(a, p, st, err, n);
+    case LRDS_ROLLOUT_EUBO_LINEAR: return launch_one<LRDS_ROLLOUT_EUBO_LINEAR, PREC>(a, p, st, err, n);
+    case LRDS_ROLLOUT_EUBO_CMCD: return launch_one<LRDS_ROLLOUT_EUBO_CMCD, PREC>(a, p, st, err, n);
+  }
+  snprintf(err, n, "unknown rollout kind");
+  return LRDS_ERR_INVALID;
+}
+
+}  // namespace
+
+int launch_rollout_tc(const RolloutArgs& a, cudaStream_t st, char* err, size_t n) {
+  const lrds_spec& s = a.s;
+  if (!s.mlp.tc_image) {
+    snprintf(err, n, "mlp.tc_image is NULL: pack the weights with lrds_pack_mlp_tc for this precision first");
+    return LRDS_ERR_INVALID;
+  }
+  int dev = 0, cap = 0, sms = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&cap, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  TcPlan p{};
+  const char* why = "";
+  if (int r = plan_rollout_tc(s, cap, sms, &p, &why)) {
+    snprintf(err, n, "tensor-core rollout does not fit (d=%d, precision %d): %s", s.d, s.precision, why);
+    return r;
+  }
+  switch (s.precision) {
+    case LRDS_PRECISION_TF32X3: return launch_kind<LRDS_PRECISION_TF32X3>(a, p, st, err, n);
+    case LRDS_PRECISION_BF16: return launch_kind<LRDS_PRECISION_BF16>(a, p, st, err, n);
+    case LRDS_PRECISION_TF32: return launch_kind<LRDS_PRECISION_TF32>(a, p, st, err, n);
+  }
+  snprintf(err, n, "unknown precision %d", s.precision);
+  return LRDS_ERR_INVALID;
+}
+
+size_t tc_image_bytes(int d, int num_hidden, int precision) { return tc_layout(d, num_hidden, precision).bytes; }
+
+int pack_tc_image(const lrds_mlp& w, int precision, void* image, cudaStream_t st, char* err, size_t n) {
+  const TcLayout L = tc_layout(w.d, w.num_hidden, precision);
+  pack_tc_image_kernel<<<32, 256, 0, st>>>(w, L, static_cast<uint8_t*>(image));
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    snprintf(err, n, "pack_tc_image launch: %s", cudaGetErrorString(e));
+    return LRDS_ERR_CUDA;
+  }
+  return LRDS_OK;
+}
+
+}  // namespace lrds

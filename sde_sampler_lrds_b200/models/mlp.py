@@ -102,9 +102,12 @@ class FourierMLP(Model):
     def _version(self):
         return tuple((p.data_ptr(), p._version) for p in self.parameters())
 
-    def lrds_mlp(self, device):
-        """(N.Mlp, keepalive) with pre-transposed weights on ``device`` (cached until a parameter changes)."""
+    def lrds_mlp(self, device, precision: int = N.PRECISION_FP32_SIMT):
+        """(N.Mlp, keepalive) with pre-transposed weights on ``device`` (cached until a parameter changes).
+        For a tensor-core ``precision`` the block also carries the tcgen05 weight image (lrds_pack_mlp_tc)."""
         _check_gelu(self.activation)
+        if precision != N.PRECISION_FP32_SIMT:
+            return self._lrds_mlp_tc(torch.device(device), precision)
         key = (str(device), self._version())
         if self._packed.get("key") != key:
             d, Cc = self.dim, self.channels
@@ -128,6 +131,25 @@ class FourierMLP(Model):
             m.w_in_t, m.w_hid_t, m.b_hid, m.w_out_t, m.b_out = (t.data_ptr() for t in keep)
             self._packed = {"key": key, "mlp": m, "keep": keep}
         return self._packed["mlp"], self._packed["keep"]
+
+    def _lrds_mlp_tc(self, device, precision: int):
+        base, keep = self.lrds_mlp(device)
+        key = ("tc", precision, str(device), self._version())
+        hit = self._packed.get(key)
+        if hit is None:
+            for k in [k for k in self._packed if isinstance(k, tuple) and k[0] == "tc" and k != key and k[1] == precision]:
+                del self._packed[k]  # stale images of this precision
+            nbytes = N.lib().lrds_tc_image_bytes(self.dim, len(self.hidden_layer), precision)
+            if nbytes < 0:
+                N.check(int(nbytes))
+            image = torch.empty(int(nbytes), dtype=torch.uint8, device=device)
+            with torch.cuda.device(device):
+                N.check(N.lib().lrds_pack_mlp_tc(C.byref(base), precision, N.ptr(image), N.stream_ptr(device)))
+            m = N.Mlp()
+            C.memmove(C.byref(m), C.byref(base), C.sizeof(N.Mlp))
+            m.tc_image = image.data_ptr()
+            hit = self._packed[key] = (m, (keep, image))
+        return hit
 
     def bias_rows(self, taus: torch.Tensor) -> torch.Tensor:
         """[S][64] host rows input_embed.bias + TimeEmbed(tau) (the reference adds embed_x + embed_t, mlp.py:139)."""

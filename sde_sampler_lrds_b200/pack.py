@@ -100,7 +100,7 @@ def fill_ctrl(spec: N.Spec, info: CtrlInfo, device, keep: list):
     spec.clip_model = float(info.clip_model) if info.clip_model is not None else 0.0
     spec.clip_score = float(info.clip_score) if info.clip_score is not None else 0.0
     spec.scale_score = float(info.scale_score)
-    mlp, k = info.base.lrds_mlp(device)
+    mlp, k = info.base.lrds_mlp(device, spec.precision)
     spec.mlp = mlp
     keep.append(k)
     spec.d = info.base.dim

@@ -1,0 +1,159 @@
+// Probe of the tcgen05 conventions the tensor-core rollout relies on, checked against a host reference:
+//   D[128 x N] (TMEM, fp32) = A[128 x K] (TMEM, written with tcgen05.st, row r <-> lane r) * B[N x K]^T (smem,
+//   K-major, no swizzle, core matrix = 8 rows x 16 B, LBO = N*16 B between K chunks, SBO = 128 B between row groups)
+// for kind::tf32 (K step 8) and kind::f16/bf16 (K step 16).  Exits non-zero on mismatch.
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/bin/tc_probe tools/tc_probe.cu
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "../sde_sampler_lrds_b200/csrc/lrds_tc_ptx.cuh"
+
+using namespace lrds::ptx;
+
+constexpr int A_COL = 0, D_COL = 128, TMEM_COLS = 256;
+
+template <bool BF16>
+__global__ void __launch_bounds__(128) probe_kernel(const float* __restrict__ A, const float* __restrict__ Bw,
+                                                    float* __restrict__ D, int K, int N) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  if (warp == 0) tmem_alloc(&tmem_base_s, TMEM_COLS);
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    fence_mbar_init();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+  constexpr int E = BF16 ? 8 : 4;  // elements per 16-byte K chunk
+  for (int idx = tid; idx < N * K; idx += 128) {
+    const int n = idx / K, k = idx % K, kc = k / E, e = k % E;
+    uint8_t* dst = smem + (size_t)kc * N * 16 + n * 16;
+    if (BF16) reinterpret_cast<__nv_bfloat16*>(dst)[e] = __float2bfloat16(Bw[idx]);
+    else reinterpret_cast<float*>(dst)[e] = Bw[idx];
+  }
+  fence_proxy_async();
+  const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+  const float* arow = A + (size_t)tid * K;
+  if (BF16) {
+    for (int c0 = 0; c0 < K / 2; c0 += 8) {
+      uint32_t r[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const __nv_bfloat162 v = __floats2bfloat162_rn(arow[2 * (c0 + i)], arow[2 * (c0 + i) + 1]);
+        r[i] = *reinterpret_cast<const uint32_t*>(&v);
+      }
+      tmem_st8(tmem + lane_base + A_COL + c0, r);
+    }
+  } else {
+    for (int c0 = 0; c0 < K; c0 += 8) {
+      uint32_t r[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) r[i] = __float_as_uint(arow[c0 + i]);
+      tmem_st8(tmem + lane_base + A_COL + c0, r);
+    }
+  }
+  tmem_wait_st();
+  tc_fence_before();
+  __syncthreads();
+  if (tid == 0) {
+    tc_fence_after();
+    const uint32_t sbase = smem_u32(smem);
+    const int ksteps = K / (BF16 ? 16 : 8);
+    const uint32_t idesc = BF16 ? make_idesc_bf16(128, N) : make_idesc_tf32(128, N);
+    for (int ks = 0; ks < ksteps; ++ks) {
+      const uint64_t bdesc = make_smem_desc(sbase + (uint32_t)ks * 2u * N * 16u, (uint32_t)N * 16u, 128u);
+      const uint32_t a_addr = tmem + A_COL + ks * 8;
+      if (BF16) mma_bf16_ts(tmem + D_COL, a_addr, bdesc, idesc, ks > 0);
+      else mma_tf32_ts(tmem + D_COL, a_addr, bdesc, idesc, ks > 0);
+    }
+    mma_commit(&bar);
+  }
+  mbar_wait(&bar, 0);
+  tc_fence_after();
+  for (int c0 = 0; c0 < N; c0 += 8) {
+    uint32_t r[8];
+    tmem_ld8(tmem + lane_base + D_COL + c0, r);
+    tmem_wait_ld();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) D[(size_t)tid * N + c0 + i] = __uint_as_float(r[i]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, TMEM_COLS);
+}
+
+static float round_tf32(float v) {
+  uint32_t u;
+  memcpy(&u, &v, 4);
+  u = (u + 0x1000u) & 0xFFFFE000u;
+  memcpy(&v, &u, 4);
+  return v;
+}
+static float round_bf16(float v) {
+  uint32_t u;
+  memcpy(&u, &v, 4);
+  u = (u + 0x7FFFu + ((u >> 16) & 1u)) & 0xFFFF0000u;
+  memcpy(&v, &u, 4);
+  return v;
+}
+
+template <bool BF16>
+int run_case(int K, int N) {
+  std::vector<float> A(128 * K), B(N * K), D(128 * N, -1.f);
+  srand(K * 131 + N);
+  for (auto& v : A) v = BF16 ? round_bf16((rand() % 2001 - 1000) / 500.f) : round_tf32((rand() % 2001 - 1000) / 500.f);
+  for (auto& v : B) v = BF16 ? round_bf16((rand() % 2001 - 1000) / 700.f) : round_tf32((rand() % 2001 - 1000) / 700.f);
+  float *dA, *dB, *dD;
+  cudaMalloc(&dA, A.size() * 4);
+  cudaMalloc(&dB, B.size() * 4);
+  cudaMalloc(&dD, D.size() * 4);
+  cudaMemcpy(dA, A.data(), A.size() * 4, cudaMemcpyHostToDevice);
+  cudaMemcpy(dB, B.data(), B.size() * 4, cudaMemcpyHostToDevice);
+  cudaMemcpy(dD, D.data(), D.size() * 4, cudaMemcpyHostToDevice);
+  const size_t smem = (size_t)N * K * (BF16 ? 2 : 4);
+  cudaFuncSetAttribute(probe_kernel<BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  probe_kernel<BF16><<<1, 128, smem>>>(dA, dB, dD, K, N);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) {
+    printf("%s K=%d N=%d: CUDA error %s\n", BF16 ? "bf16" : "tf32", K, N, cudaGetErrorString(e));
+    return 1;
+  }
+  cudaMemcpy(D.data(), dD, D.size() * 4, cudaMemcpyDeviceToHost);
+  double worst = 0;
+  for (int m = 0; m < 128; ++m)
+    for (int n = 0; n < N; ++n) {
+      double ref = 0;
+      for (int k = 0; k < K; ++k) ref += (double)A[m * K + k] * (double)B[n * K + k];
+      worst = fmax(worst, fabs(ref - D[m * N + n]));
+    }
+  printf("%s K=%3d N=%3d: max abs err %.3e  %s\n", BF16 ? "bf16" : "tf32", K, N, worst, worst < 1e-4 ? "OK" : "MISMATCH");
+  cudaFree(dA);
+  cudaFree(dB);
+  cudaFree(dD);
+  return worst < 1e-4 ? 0 : 1;
+}
+
+int main() {
+  int bad = 0;
+  bad += run_case<false>(8, 16);
+  bad += run_case<false>(56, 64);
+  bad += run_case<false>(64, 64);
+  bad += run_case<false>(64, 112);
+  bad += run_case<false>(104, 64);
+  bad += run_case<true>(16, 16);
+  bad += run_case<true>(64, 64);
+  bad += run_case<true>(64, 112);
+  bad += run_case<true>(112, 64);
+  printf(bad ? "tc_probe: FAILED (%d cases)\n" : "tc_probe: all cases OK\n", bad);
+  return bad ? 1 : 0;
+}
