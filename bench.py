@@ -46,6 +46,7 @@ class ClockSampler(threading.Thread):
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.samples, self.reasons, self.max_mhz, self._stop_evt = index, [], set(), None, threading.Event()
+        self.ready, self.recording = threading.Event(), False  # NVML init happens BEFORE the timed region
 
     def run(self):
         try:
@@ -57,15 +58,19 @@ class ClockSampler(threading.Thread):
                      nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
                      nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
                      nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap"}
+            nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+            self.ready.set()
             while not self._stop_evt.is_set():
-                self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
-                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
-                for bit, name in names.items():
-                    if r & bit:
-                        self.reasons.add(name)
+                if self.recording:
+                    self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                    for bit, name in names.items():
+                        if r & bit:
+                            self.reasons.add(name)
                 time.sleep(0.02)
         except Exception as e:  # pragma: no cover
             self.reasons.add(f"nvml_unavailable:{type(e).__name__}")
+            self.ready.set()
 
     def stop(self):
         self._stop_evt.set()
@@ -164,13 +169,15 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    sampler = ClockSampler(local)
+    sampler.start()
+    sampler.ready.wait(timeout=10)
     for w in range(args.warmup):
         step(x0, 1000 + w)
     barrier()
 
     # ---- device-resident timing (value) + the dominant kernel alone (roofline) -----------------------------------
-    sampler = ClockSampler(local)
-    sampler.start()
+    sampler.recording = True
     launches0 = N.launch_count()
     ev = [(torch.cuda.Event(True), torch.cuda.Event(True), torch.cuda.Event(True)) for _ in range(args.steps)]
     last = None
@@ -189,9 +196,10 @@ def run_ours(args):
         c.record()
     barrier()
     launches = N.launch_count() - launches0
-    clocks = sampler.stop()
+    sampler.recording = False
     step_ms = sum(a.elapsed_time(c) for a, _, c in ev)
     kern_ms = sum(a.elapsed_time(b) for a, b, _ in ev) / args.steps
+    kern_ms_each = [round(a.elapsed_time(b), 3) for a, b, _ in ev]
     t = torch.tensor([step_ms], device=dev, dtype=torch.float64)
     if group is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -218,6 +226,7 @@ def run_ours(args):
     e2e_value = world * B * K_STEPS * args.steps / float(t.item())
     h2d = x0_host.numel() * 4
     d2h = (x_host_out.numel() + rnd_host_out.numel()) * 4
+    clocks = sampler.stop()
 
     if rank != 0:
         if group is not None:
@@ -243,7 +252,7 @@ def run_ours(args):
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": int(launches),
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                     "traffic": None, "kernel_ms": kern_ms, "peak_source": how + ", dense bf16 burst",
+                     "traffic": None, "kernel_ms": kern_ms, "kernel_ms_each": kern_ms_each, "peak_source": how + ", dense bf16 burst",
                      "flops_per_particle_step": FLOPS_PER_PARTICLE_STEP},
         "check": {"log_norm_const_is": m["log_norm_const_is"], "elbo": m["elbo"], "ess": m["effective_sample_size"]},
     }
@@ -261,7 +270,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default="fp32", choices=["fp32", "tf32x3", "bf16"])
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "tf32x3", "tf32", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

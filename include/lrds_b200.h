@@ -17,7 +17,7 @@
 extern "C" {
 #endif
 
-#define LRDS_ABI_VERSION 1
+#define LRDS_ABI_VERSION 2
 #define LRDS_CHANNELS 64 /* FourierMLP / TimeEmbed width, conf/model/base/fouriermlp.yaml:4 */
 
 typedef enum {
@@ -111,11 +111,12 @@ typedef struct {
 typedef struct {
   int32_t M;
   int32_t reserved;
-  const float* logc; /* [M]    log w_m - d/2 log(2 pi) - 1/2 sum_j log var_mj   (w normalised) */
-  const float* mu;   /* [M][d] */
-  const float* ivar; /* [M][d] 1 / var */
-  int64_t step_stride_logc;
-  int64_t step_stride_param;
+  const float* logc; /* [4 ceil(M/4)]  log w_m - d/2 log(2 pi) - 1/2 sum_j log var_mj (w normalised), 16-byte aligned */
+  const float* mu;   /* [M][d_pad]  rows padded with 0 to d_pad = 8 ceil(d / 8) floats, 16-byte aligned */
+  const float* ivar; /* [M][d_pad]  1 / var, padded with 0 */
+  const float* muiv; /* [M][d_pad]  mu / var, padded with 0 (score contraction) */
+  int64_t step_stride_logc;  /* floats between consecutive steps of logc (4 ceil(M/4)) */
+  int64_t step_stride_param; /* floats between consecutive steps of mu / ivar / muiv (M * d_pad) */
 } lrds_gmm;
 
 typedef struct {

@@ -27,10 +27,40 @@ struct Col {
   __device__ __forceinline__ float& operator()(int j) const { return p[j * stride]; }
 };
 
+// The same for vectors that the hot loops read four dims at a time (x, mixture responsibilities): dims
+// [4c, 4c+4) of thread t are the float4 at base[(c * blockDim.x + t) * 4], so one conflict-free LDS.128 feeds
+// four lanes of arithmetic.  Scalar access stays available (4-way bank conflict: keep it off the hot paths).
+struct Col4 {
+  float* p;    // base + 4 * threadIdx.x
+  int stride;  // 4 * blockDim.x floats between consecutive groups
+  __device__ __forceinline__ float& operator()(int j) const { return p[(j >> 2) * stride + (j & 3)]; }
+  __device__ __forceinline__ float4 ld4(int c) const { return *reinterpret_cast<const float4*>(p + c * stride); }
+  __device__ __forceinline__ void st4(int c, const float4& v) const { *reinterpret_cast<float4*>(p + c * stride) = v; }
+};
+
+// clip bounds arrive as "<= 0: no clip"; kernels turn that into +inf once so that a clip is two FMNMX
+__device__ __forceinline__ float clip_bound(float c) { return c > 0.f ? c : INFINITY; }
+__device__ __forceinline__ float clipb(float v, float bound) { return fminf(fmaxf(v, -bound), bound); }
 __device__ __forceinline__ float clipf(float v, float c) { return c > 0.f ? fminf(fmaxf(v, -c), c) : v; }
 
+// GELU with the exact (erf) definition, conf/model/base/fouriermlp.yaml:5-6:  v/2 (1 + erf(v / sqrt 2)).
+// erf(|x|) = 1 - 2^(|x| Q(|x|)) with a degree-6 minimax Q on [0, 4] (saturated beyond): absolute error of erf
+// 7.7e-8, of the GELU 1.6e-7 max(1, |v|) - the same as evaluating the erf formula in fp32 (tools/fit_erf.py).
+// One MUFU.EX2 and 9 FMA-pipe instructions instead of erff's ~25.
 __device__ __forceinline__ float gelu_exact(float v) {
-  return 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f));
+  const float t = fminf(fabsf(v), 5.656854249f);
+  float q = 8.857967404e-06f;
+  q = fmaf(q, t, -5.769414971e-05f);
+  q = fmaf(q, t, -4.069866499e-04f);
+  q = fmaf(q, t, 7.363130652e-03f);
+  q = fmaf(q, t, -5.266660834e-02f);
+  q = fmaf(q, t, -4.591643231e-01f);
+  q = fmaf(q, t, -1.151108839e+00f);
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(q * t));
+  const float r = copysignf(1.0f - e, v);
+  const float h = 0.5f * v;
+  return fmaf(h, r, h);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -40,8 +70,9 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
                                                uint32_t k1, uint32_t (&out)[4]) {
 #pragma unroll
   for (int r = 0; r < 10; ++r) {
-    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
-    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;  // one IMAD.WIDE each
+    const uint32_t hi0 = (uint32_t)(p0 >> 32), lo0 = (uint32_t)p0;
+    const uint32_t hi1 = (uint32_t)(p1 >> 32), lo1 = (uint32_t)p1;
     c0 = hi1 ^ c1 ^ k0;
     c1 = lo1;
     c2 = hi0 ^ c3 ^ k1;
@@ -55,7 +86,9 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
 __device__ __forceinline__ void box_muller(uint32_t ra, uint32_t rb, float& z0, float& z1) {
   const float u1 = (float)((ra >> 8) + 1u) * 5.9604644775390625e-08f;  // (0, 1]
   const float u2 = (float)(rb >> 8) * 5.9604644775390625e-08f;         // [0, 1)
-  const float rad = sqrtf(-2.0f * __logf(u1));
+  float l2, rad;  // sqrt(-2 ln u1) = sqrt(-2 ln2 * lg2 u1): two MUFU ops
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"(u1));
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rad) : "f"(l2 * -1.3862943611198906f));
   float s, c;
   __sincosf(fmaf(u2, 6.283185307179586f, -3.141592653589793f), &s, &c);
   z0 = rad * c;
@@ -74,95 +107,167 @@ __device__ __forceinline__ void normals4(uint64_t seed, uint32_t pidx, uint32_t 
 // ---------------------------------------------------------------------------------------------------
 // diagonal Gaussian mixture
 // ---------------------------------------------------------------------------------------------------
-struct GmmView {
-  int M;
-  const float* logc;
-  const float* mu;
-  const float* ivar;
+// Warp-uniform operand pointer.  SH = the operand block sits in shared memory (staged per step by the TMA engine:
+// one wavefront per warp-uniform LDS.128, 32-bit address arithmetic) instead of global memory (read-only path:
+// four wavefronts per warp-uniform LDG.128).
+template <bool SH>
+struct PPtr;
+template <>
+struct PPtr<false> {
+  const float* p;
+  __device__ __forceinline__ PPtr operator+(int floats) const { return PPtr{p + floats}; }
+  __device__ __forceinline__ float4 ld4(int i) const { return __ldg(reinterpret_cast<const float4*>(p) + i); }
+  __device__ __forceinline__ float ld1(int i) const { return __ldg(p + i); }
+};
+template <>
+struct PPtr<true> {
+  uint32_t a;  // shared-window byte address
+  __device__ __forceinline__ PPtr operator+(int floats) const { return PPtr{a + 4u * (uint32_t)floats}; }
+  __device__ __forceinline__ float4 ld4(int i) const {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a + 16u * (uint32_t)i));
+    return v;
+  }
+  __device__ __forceinline__ float ld1(int i) const {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a + 4u * (uint32_t)i));
+    return v;
+  }
 };
 
+template <bool SH>
+__device__ __forceinline__ float4 gld4(const float4* p) {  // plain pointers: shared is inferred by the compiler
+  if constexpr (SH) return *p;
+  else return __ldg(p);
+}
+
+template <bool SH>
+struct GmmViewT {
+  int M;
+  PPtr<SH> logc, mu, ivar, muiv;
+};
+using GmmView = GmmViewT<false>;
+
+// step_stride_param counts floats of the padded rows (M * d_pad per step)
 __device__ __forceinline__ GmmView gmm_at(const lrds_gmm& g, int step) {
   GmmView v;
   v.M = g.M;
-  v.logc = g.logc + (int64_t)step * g.step_stride_logc;
-  v.mu = g.mu + (int64_t)step * g.step_stride_param;
-  v.ivar = g.ivar + (int64_t)step * g.step_stride_param;
+  v.logc = PPtr<false>{g.logc + (int64_t)step * g.step_stride_logc};
+  v.mu = PPtr<false>{g.mu + (int64_t)step * g.step_stride_param};
+  v.ivar = PPtr<false>{g.ivar + (int64_t)step * g.step_stride_param};
+  v.muiv = PPtr<false>{g.muiv + (int64_t)step * g.step_stride_param};
   return v;
+}
+
+// Mixture parameters are rows of dp = d_pad floats (zero padded: mu = 0, 1/var = 0), read as warp-uniform float4.
+__device__ __forceinline__ void quad4(float& q, const float4& xv, const float4& mu, const float4& iv) {
+  float t;
+  t = xv.x - mu.x; q = fmaf(t * t, iv.x, q);
+  t = xv.y - mu.y; q = fmaf(t * t, iv.y, q);
+  t = xv.z - mu.z; q = fmaf(t * t, iv.z, q);
+  t = xv.w - mu.w; q = fmaf(t * t, iv.w, q);
 }
 
 // Pass 1: responsibilities r(m) = softmax_m(logc_m - q_m / 2), q_m = sum_j (x_j - mu_mj)^2 / var_mj.
 // Returns log sum_m exp(logit_m) (= the mixture log-density).  For M == 1, r is not touched.
-__device__ __forceinline__ float gmm_pass1(const GmmView& g, int d, const Col& x, const Col& r) {
+// r holds 4 * ceil(M / 4) entries; the tail beyond M is left at zero weight.
+template <bool SH>
+__device__ __forceinline__ float gmm_pass1(const GmmViewT<SH>& g, int dp, const Col4& x, const Col4& r) {
+  const int nq = dp >> 2;
+  const PPtr<SH> mu = g.mu, iv = g.ivar;
   if (g.M == 1) {
     float q = 0.f;
-    for (int j = 0; j < d; ++j) {
-      const float t = x(j) - __ldg(g.mu + j);
-      q = fmaf(t * t, __ldg(g.ivar + j), q);
-    }
-    return __ldg(g.logc) - 0.5f * q;
+    for (int c = 0; c < nq; ++c) quad4(q, x.ld4(c), mu.ld4(c), iv.ld4(c));
+    return g.logc.ld1(0) - 0.5f * q;
   }
   float mx = -INFINITY;
-  int m = 0;
-  for (; m + 4 <= g.M; m += 4) {  // 4 modes at a time so that one x_j load feeds 4 quadratic forms
-    float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
-    const float* mu = g.mu + (int64_t)m * d;
-    const float* iv = g.ivar + (int64_t)m * d;
+  const int M4 = (g.M + 3) >> 2;
+  for (int mb = 0; mb < M4; ++mb) {  // 4 modes at a time so that one x load feeds 4 quadratic forms
+    const int m = 4 * mb;
+    float4 l;
+    if (m + 4 <= g.M) {
+      float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
+      int o = m * nq;
 #pragma unroll 2
-    for (int j = 0; j < d; ++j) {
-      const float xj = x(j);
-      float t;
-      t = xj - __ldg(mu + j);         q0 = fmaf(t * t, __ldg(iv + j), q0);
-      t = xj - __ldg(mu + d + j);     q1 = fmaf(t * t, __ldg(iv + d + j), q1);
-      t = xj - __ldg(mu + 2 * d + j); q2 = fmaf(t * t, __ldg(iv + 2 * d + j), q2);
-      t = xj - __ldg(mu + 3 * d + j); q3 = fmaf(t * t, __ldg(iv + 3 * d + j), q3);
+      for (int c = 0; c < nq; ++c, ++o) {
+        const float4 xv = x.ld4(c);
+        quad4(q0, xv, mu.ld4(o), iv.ld4(o));
+        quad4(q1, xv, mu.ld4(o + nq), iv.ld4(o + nq));
+        quad4(q2, xv, mu.ld4(o + 2 * nq), iv.ld4(o + 2 * nq));
+        quad4(q3, xv, mu.ld4(o + 3 * nq), iv.ld4(o + 3 * nq));
+      }
+      const float4 lc = g.logc.ld4(mb);
+      l = make_float4(lc.x - 0.5f * q0, lc.y - 0.5f * q1, lc.z - 0.5f * q2, lc.w - 0.5f * q3);
+    } else {  // ragged tail: absent modes get logit -inf
+      float lv[4];
+      for (int i = 0; i < 4; ++i) {
+        lv[i] = -INFINITY;
+        if (m + i < g.M) {
+          float q = 0.f;
+          const int o = (m + i) * nq;
+          for (int c = 0; c < nq; ++c) quad4(q, x.ld4(c), mu.ld4(o + c), iv.ld4(o + c));
+          lv[i] = g.logc.ld1(m + i) - 0.5f * q;
+        }
+      }
+      l = make_float4(lv[0], lv[1], lv[2], lv[3]);
     }
-    const float l0 = __ldg(g.logc + m) - 0.5f * q0, l1 = __ldg(g.logc + m + 1) - 0.5f * q1;
-    const float l2 = __ldg(g.logc + m + 2) - 0.5f * q2, l3 = __ldg(g.logc + m + 3) - 0.5f * q3;
-    r(m) = l0; r(m + 1) = l1; r(m + 2) = l2; r(m + 3) = l3;
-    mx = fmaxf(fmaxf(mx, fmaxf(l0, l1)), fmaxf(l2, l3));
-  }
-  for (; m < g.M; ++m) {
-    float q = 0.f;
-    const float* mu = g.mu + (int64_t)m * d;
-    const float* iv = g.ivar + (int64_t)m * d;
-    for (int j = 0; j < d; ++j) {
-      const float t = x(j) - __ldg(mu + j);
-      q = fmaf(t * t, __ldg(iv + j), q);
-    }
-    const float l = __ldg(g.logc + m) - 0.5f * q;
-    r(m) = l;
-    mx = fmaxf(mx, l);
+    r.st4(mb, l);
+    mx = fmaxf(fmaxf(mx, fmaxf(l.x, l.y)), fmaxf(l.z, l.w));
   }
   float s = 0.f;
-  for (m = 0; m < g.M; ++m) {
-    const float e = expf(r(m) - mx);
-    r(m) = e;
-    s += e;
+  for (int mb = 0; mb < M4; ++mb) {
+    float4 l = r.ld4(mb);
+    l.x = __expf(l.x - mx); l.y = __expf(l.y - mx); l.z = __expf(l.z - mx); l.w = __expf(l.w - mx);
+    s += (l.x + l.y) + (l.z + l.w);
+    r.st4(mb, l);
   }
   const float inv = 1.0f / s;
-  for (m = 0; m < g.M; ++m) r(m) *= inv;
-  return mx + logf(s);
+  for (int mb = 0; mb < M4; ++mb) {
+    float4 l = r.ld4(mb);
+    l.x *= inv; l.y *= inv; l.z *= inv; l.w *= inv;
+    r.st4(mb, l);
+  }
+  return mx + __logf(s);
 }
 
-// Pass 2 for dims [j0, j0+JC): score_j = -sum_m r_m (x_j - mu_mj) / var_mj  (zero for j >= d)
-__device__ __forceinline__ void gmm_score_chunk(const GmmView& g, int d, const float (&xr)[JC], const Col& r, int j0,
+// Pass 2 for dims [j0, j0+JC):  score_j = -sum_m r_m (x_j - mu_mj) / var_mj, evaluated as
+//   sum_m r_m (mu / var)_mj  -  x_j sum_m r_m (1 / var)_mj      (two FFMA per mode and dim; zero for the padded dims)
+template <bool SH>
+__device__ __forceinline__ void gmm_score_chunk(const GmmViewT<SH>& g, int dp, const float (&xr)[JC], const Col4& r, int j0,
                                                 float (&out)[JC]) {
-#pragma unroll
-  for (int c = 0; c < JC; ++c) out[c] = 0.f;
-  if (g.M == 1) {
-#pragma unroll
-    for (int c = 0; c < JC; ++c)
-      if (j0 + c < d) out[c] = -((xr[c] - __ldg(g.mu + j0 + c)) * __ldg(g.ivar + j0 + c));
+  const int nq = dp >> 2;
+  const PPtr<SH> iv = g.ivar + j0, mv = g.muiv + j0;
+  if (g.M == 1) {  // -((x - mu) * ivar), the operation order of score_gauss (distr/gauss.py:124-126)
+    const PPtr<SH> mu = g.mu + j0;
+    const float4 m0 = mu.ld4(0), m1 = mu.ld4(1), i0 = iv.ld4(0), i1 = iv.ld4(1);
+    out[0] = -((xr[0] - m0.x) * i0.x); out[1] = -((xr[1] - m0.y) * i0.y);
+    out[2] = -((xr[2] - m0.z) * i0.z); out[3] = -((xr[3] - m0.w) * i0.w);
+    out[4] = -((xr[4] - m1.x) * i1.x); out[5] = -((xr[5] - m1.y) * i1.y);
+    out[6] = -((xr[6] - m1.z) * i1.z); out[7] = -((xr[7] - m1.w) * i1.w);
     return;
   }
-  for (int m = 0; m < g.M; ++m) {
-    const float rm = r(m);
-    const float* mu = g.mu + (int64_t)m * d + j0;
-    const float* iv = g.ivar + (int64_t)m * d + j0;
+  float a[JC], b[JC];
 #pragma unroll
-    for (int c = 0; c < JC; ++c)
-      if (j0 + c < d) out[c] = fmaf(-rm, (xr[c] - __ldg(mu + c)) * __ldg(iv + c), out[c]);
+  for (int c = 0; c < JC; ++c) a[c] = b[c] = 0.f;
+  auto mode = [&](float rm, int o) {
+    const float4 i0 = iv.ld4(o), i1 = iv.ld4(o + 1), v0 = mv.ld4(o), v1 = mv.ld4(o + 1);
+    a[0] = fmaf(rm, i0.x, a[0]); a[1] = fmaf(rm, i0.y, a[1]); a[2] = fmaf(rm, i0.z, a[2]); a[3] = fmaf(rm, i0.w, a[3]);
+    a[4] = fmaf(rm, i1.x, a[4]); a[5] = fmaf(rm, i1.y, a[5]); a[6] = fmaf(rm, i1.z, a[6]); a[7] = fmaf(rm, i1.w, a[7]);
+    b[0] = fmaf(rm, v0.x, b[0]); b[1] = fmaf(rm, v0.y, b[1]); b[2] = fmaf(rm, v0.z, b[2]); b[3] = fmaf(rm, v0.w, b[3]);
+    b[4] = fmaf(rm, v1.x, b[4]); b[5] = fmaf(rm, v1.y, b[5]); b[6] = fmaf(rm, v1.z, b[6]); b[7] = fmaf(rm, v1.w, b[7]);
+  };
+  const int M4 = g.M >> 2;
+  int o = 0;
+  for (int mb = 0; mb < M4; ++mb, o += 4 * nq) {
+    const float4 rm = r.ld4(mb);
+    mode(rm.x, o);
+    mode(rm.y, o + nq);
+    mode(rm.z, o + 2 * nq);
+    mode(rm.w, o + 3 * nq);
   }
+  for (int m = 4 * M4; m < g.M; ++m, o += nq) mode(r(m), o);
+#pragma unroll
+  for (int c = 0; c < JC; ++c) out[c] = fmaf(-xr[c], a[c], b[c]);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -175,16 +280,23 @@ __device__ __forceinline__ float phi4_score_1(const lrds_phi4& p, float coef, fl
 }
 
 // log-density -beta * U(x), U = coef * sum_{i=0..d} (x_{i+1}-x_i)^2/2 + sum((1-x^2)^2/4 + b x)/coef
-__device__ __forceinline__ float phi4_logp(const lrds_phi4& p, int d, const Col& x) {
+__device__ __forceinline__ float phi4_logp(const lrds_phi4& p, int d, const Col4& x) {
   const float coef = p.a * (float)d;
   float grad = 0.f, v = 0.f, prev = 0.f;
-  for (int j = 0; j < d; ++j) {
-    const float xj = x(j);
-    const float df = xj - prev;
-    grad += df * df * 0.5f;
-    const float w = 1.0f - xj * xj;
-    v += w * w * 0.25f + p.b * xj;
-    prev = xj;
+  for (int c = 0; 4 * c < d; ++c) {
+    const float4 q = x.ld4(c);
+    const float xs[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      if (4 * c + e < d) {
+        const float xj = xs[e];
+        const float df = xj - prev;
+        grad += df * df * 0.5f;
+        const float w = 1.0f - xj * xj;
+        v += w * w * 0.25f + p.b * xj;
+        prev = xj;
+      }
+    }
   }
   grad += prev * prev * 0.5f;
   return -p.beta * (grad * coef + v / coef);
@@ -195,18 +307,24 @@ __device__ __forceinline__ float phi4_logp(const lrds_phi4& p, int d, const Col&
 // ---------------------------------------------------------------------------------------------------
 // Pass 1: g(n) = m_n (y_n - sigma(z_n)), z_n = X_n . w + intercept, m_n = [eps <= sigma(z_n) <= 1 - eps].
 // With want_logp the log-posterior (likelihood + Normal priors) is returned.
-__device__ __forceinline__ float logreg_pass1(const lrds_logreg& L, int d, const Col& x, const Col& g, bool want_logp) {
+__device__ __forceinline__ float logreg_pass1(const lrds_logreg& L, int d, const Col4& x, const Col& g, bool want_logp) {
   const float icpt = x(d - 1);
   const float hi = 1.0f - L.eps;
   float ll = 0.f;
   for (int n = 0; n < L.N; n += 4) {
     float z0 = 0.f, z1 = 0.f, z2 = 0.f, z3 = 0.f;
     const float* xt = L.Xt + n;
-#pragma unroll 2
-    for (int j = 0; j < L.p; ++j) {
-      const float4 v = __ldg(reinterpret_cast<const float4*>(xt + (int64_t)j * L.n_pad));
-      const float xj = x(j);
-      z0 = fmaf(v.x, xj, z0); z1 = fmaf(v.y, xj, z1); z2 = fmaf(v.z, xj, z2); z3 = fmaf(v.w, xj, z3);
+    for (int jq = 0; 4 * jq < L.p; ++jq) {
+      const float4 xq = x.ld4(jq);
+      const float xs[4] = {xq.x, xq.y, xq.z, xq.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int j = 4 * jq + e;
+        if (j < L.p) {
+          const float4 v = __ldg(reinterpret_cast<const float4*>(xt + (int64_t)j * L.n_pad));
+          z0 = fmaf(v.x, xs[e], z0); z1 = fmaf(v.y, xs[e], z1); z2 = fmaf(v.z, xs[e], z2); z3 = fmaf(v.w, xs[e], z3);
+        }
+      }
     }
     const float zz[4] = {z0 + icpt, z1 + icpt, z2 + icpt, z3 + icpt};
 #pragma unroll
@@ -281,12 +399,22 @@ __device__ __forceinline__ void fma_row64(float (&acc)[C], const float* __restri
 }
 
 // hidden activations GELU(h_L) of the particle -> act(0..63)   (models/mlp.py:136-142)
-__device__ __forceinline__ void mlp_hidden(const lrds_mlp& w, const float* __restrict__ bias1, const Col& x,
+template <bool BIAS_SH>
+__device__ __forceinline__ void mlp_hidden(const lrds_mlp& w, const float* __restrict__ bias1, const Col4& x,
                                            const Col& act) {
   float acc[C];
 #pragma unroll
-  for (int n = 0; n < C; ++n) acc[n] = __ldg(bias1 + n);
-  for (int k = 0; k < w.d; ++k) fma_row64(acc, w.w_in_t + (int64_t)k * C, x(k));
+  for (int q = 0; q < C / 4; ++q) {
+    const float4 b = gld4<BIAS_SH>(reinterpret_cast<const float4*>(bias1) + q);
+    acc[4 * q] = b.x; acc[4 * q + 1] = b.y; acc[4 * q + 2] = b.z; acc[4 * q + 3] = b.w;
+  }
+  for (int kq = 0; 4 * kq < w.d; ++kq) {
+    const float4 xq = x.ld4(kq);
+    const float xs[4] = {xq.x, xq.y, xq.z, xq.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+      if (4 * kq + e < w.d) fma_row64(acc, w.w_in_t + (int64_t)(4 * kq + e) * C, xs[e]);
+  }
 #pragma unroll
   for (int n = 0; n < C; ++n) act(n) = gelu_exact(acc[n]);
   for (int l = 0; l < w.num_hidden; ++l) {

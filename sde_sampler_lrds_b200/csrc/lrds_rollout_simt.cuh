@@ -10,6 +10,7 @@
 // four GEMMs on tcgen05 with TMEM-resident operands.  Everything else is shared between the two.
 #pragma once
 #include "lrds_device.cuh"
+#include "lrds_tc_ptx.cuh"
 
 namespace lrds {
 
@@ -37,13 +38,13 @@ __host__ __device__ inline ColLayout col_layout(const lrds_spec& s) {
   L.act = off;
   if (s.precision == LRDS_PRECISION_FP32_SIMT) off += C;  // hidden activations: tensor-core backends keep them in TMEM
   L.rt = off;
-  if (s.target.kind == LRDS_DISTR_GMM && s.target.gmm.M > 1) off += s.target.gmm.M;
+  if (s.target.kind == LRDS_DISTR_GMM && s.target.gmm.M > 1) off += (s.target.gmm.M + 3) / 4 * 4;
   L.rr = off;
   {
     int m = 0;
     if (s.has_ref_ctrl && s.ref_t.M > 1) m = s.ref_t.M;
     if (s.ref_0.M > 1 && s.ref_0.M > m) m = s.ref_0.M;
-    off += m;
+    off += (m + 3) / 4 * 4;
   }
   L.g = off;
   if (s.target.kind == LRDS_DISTR_LOGREG) off += s.target.logreg.n_pad;
@@ -59,33 +60,102 @@ __host__ __device__ inline ColLayout col_layout(const lrds_spec& s) {
   return L;
 }
 
+// x, rt, rr are float4-grouped columns (their layout offsets are multiples of 4); the rest are scalar columns
 struct Particle {
-  Col x, rt, rr, g, us, tsd, db;
+  Col4 x, rt, rr;
+  Col g, us, tsd, db;
 };
+
+__device__ __forceinline__ Particle make_particle(float* smem, const ColLayout& L, int NT, int tid) {
+  Particle P;
+  P.x = Col4{smem + L.x * NT + 4 * tid, 4 * NT};
+  P.rt = Col4{smem + L.rt * NT + 4 * tid, 4 * NT};
+  P.rr = Col4{smem + L.rr * NT + 4 * tid, 4 * NT};
+  P.g = Col{smem + L.g * NT + tid, NT};
+  P.us = Col{smem + L.us * NT + tid, NT};
+  P.tsd = Col{smem + L.tsd * NT + tid, NT};
+  P.db = Col{smem + L.db * NT + tid, NT};
+  return P;
+}
+
+// ---- per-step operand staging (LINEAR kind) ----------------------------------------------------------------
+struct StageLayout {
+  uint32_t tgt_logc_bytes, tgt_param_bytes, tgt_bytes;  // target mixture (static): logc | mu | ivar | muiv
+  uint32_t ref_logc_bytes, ref_param_bytes, row_bytes;  // one step: table row | logc | mu | ivar | muiv
+  uint32_t buf_bytes, off_tgt, off_buf, total;
+};
+
+__host__ __device__ inline StageLayout stage_layout(const lrds_spec& s) {
+  StageLayout L{};
+  const uint32_t dp = (uint32_t)s.mlp.d_pad;
+  if (s.target.kind == LRDS_DISTR_GMM) {
+    L.tgt_logc_bytes = (uint32_t)((s.target.gmm.M + 3) / 4 * 4) * 4u;
+    L.tgt_param_bytes = (uint32_t)s.target.gmm.M * dp * 4u;
+    L.tgt_bytes = L.tgt_logc_bytes + 3u * L.tgt_param_bytes;
+  }
+  if (s.has_ref_ctrl) {
+    L.ref_logc_bytes = (uint32_t)((s.ref_t.M + 3) / 4 * 4) * 4u;
+    L.ref_param_bytes = (uint32_t)s.ref_t.M * dp * 4u;
+  }
+  L.row_bytes = LRDS_STEP_STRIDE * 4u;
+  L.buf_bytes = L.row_bytes + L.ref_logc_bytes + 3u * L.ref_param_bytes;
+  L.off_tgt = 16;  // two mbarriers in front
+  L.off_buf = L.off_tgt + L.tgt_bytes;
+  L.total = L.off_buf + 2u * L.buf_bytes;
+  return L;
+}
+
+// issued by one thread; the caller has armed `bar` with the byte count
+__device__ __forceinline__ void stage_gmm(uint8_t* dst, const GmmView& g, uint32_t logc_bytes, uint32_t param_bytes,
+                                          uint64_t* bar) {
+  ptx::bulk_g2s(dst, g.logc.p, logc_bytes, bar);
+  ptx::bulk_g2s(dst + logc_bytes, g.mu.p, param_bytes, bar);
+  ptx::bulk_g2s(dst + logc_bytes + param_bytes, g.ivar.p, param_bytes, bar);
+  ptx::bulk_g2s(dst + logc_bytes + 2 * param_bytes, g.muiv.p, param_bytes, bar);
+}
+__device__ __forceinline__ void stage_step(uint8_t* dst, const lrds_spec& s, const StageLayout& L, int k, uint64_t* bar) {
+  ptx::bulk_g2s(dst, s.steps + (int64_t)k * LRDS_STEP_STRIDE, L.row_bytes, bar);
+  if (s.has_ref_ctrl) stage_gmm(dst + L.row_bytes, gmm_at(s.ref_t, k), L.ref_logc_bytes, L.ref_param_bytes, bar);
+}
+__device__ __forceinline__ GmmViewT<true> staged_view(const uint8_t* src, int M, uint32_t logc_bytes, uint32_t param_bytes) {
+  GmmViewT<true> v;
+  const uint32_t a = ptx::smem_u32(src);
+  v.M = M;
+  v.logc = PPtr<true>{a};
+  v.mu = PPtr<true>{a + logc_bytes};
+  v.ivar = PPtr<true>{a + logc_bytes + param_bytes};
+  v.muiv = PPtr<true>{a + logc_bytes + 2 * param_bytes};
+  return v;
+}
 
 // fp32 FFMA drift network: hidden activations in 64 shared-memory columns per particle
 struct SimtMlp {
   const lrds_mlp& w;
   Col act;
-  __device__ __forceinline__ void hidden(const float* __restrict__ bias1, const Col& x) { mlp_hidden(w, bias1, x, act); }
+  template <bool BIAS_SH>
+  __device__ __forceinline__ void hidden(const float* __restrict__ bias1, const Col4& x) {
+    mlp_hidden<BIAS_SH>(w, bias1, x, act);
+  }
   __device__ __forceinline__ void out_chunk(int j0, float (&out)[JC]) { mlp_out_chunk(w, act, j0, out); }
 };
 
 // ---- target helpers ---------------------------------------------------------------------------------
-__device__ __forceinline__ float target_pass1(const lrds_spec& s, const Particle& P, bool want_logp) {
+template <bool SH>
+__device__ __forceinline__ float target_pass1(const lrds_spec& s, const GmmViewT<SH>& tv, const Particle& P, bool want_logp) {
   const lrds_distr& t = s.target;
-  if (t.kind == LRDS_DISTR_GMM) return gmm_pass1(gmm_at(t.gmm, 0), s.d, P.x, P.rt);
+  if (t.kind == LRDS_DISTR_GMM) return gmm_pass1(tv, s.mlp.d_pad, P.x, P.rt);
   if (t.kind == LRDS_DISTR_LOGREG) return logreg_pass1(t.logreg, s.d, P.x, P.g, want_logp);
   if (t.kind == LRDS_DISTR_PHI4) return want_logp ? phi4_logp(t.phi4, s.d, P.x) : 0.f;
   return 0.f;
 }
 
 // raw target score for dims [j0, j0+JC); xm / xp are x_{j0-1} / x_{j0+JC} of the SAME state as xr
-__device__ __forceinline__ void target_score_chunk(const lrds_spec& s, const Particle& P, const float (&xr)[JC],
-                                                   float xm, float xp, int j0, float (&out)[JC]) {
+template <bool SH>
+__device__ __forceinline__ void target_score_chunk(const lrds_spec& s, const GmmViewT<SH>& tv, const Particle& P,
+                                                   const float (&xr)[JC], float xm, float xp, int j0, float (&out)[JC]) {
   const lrds_distr& t = s.target;
   if (t.kind == LRDS_DISTR_GMM) {
-    gmm_score_chunk(gmm_at(t.gmm, 0), s.d, xr, P.rt, j0, out);
+    gmm_score_chunk(tv, s.mlp.d_pad, xr, P.rt, j0, out);
   } else if (t.kind == LRDS_DISTR_LOGREG) {
     logreg_score_chunk(t.logreg, s.d, s.mlp.d_pad, xr, P.g, j0, out);
   } else if (t.kind == LRDS_DISTR_PHI4) {
@@ -108,18 +178,34 @@ __device__ __forceinline__ void load_chunk(const Col& v, int j0, float (&out)[JC
 #pragma unroll
   for (int c = 0; c < JC; ++c) out[c] = v(j0 + c);
 }
+__device__ __forceinline__ void load_chunk(const Col4& v, int j0, float (&out)[JC]) {
+  const float4 a = v.ld4(j0 >> 2), b = v.ld4((j0 >> 2) + 1);
+  out[0] = a.x; out[1] = a.y; out[2] = a.z; out[3] = a.w; out[4] = b.x; out[5] = b.y; out[6] = b.z; out[7] = b.w;
+}
+__device__ __forceinline__ void store_chunk(const Col4& v, int j0, const float (&in)[JC]) {
+  v.st4(j0 >> 2, make_float4(in[0], in[1], in[2], in[3]));
+  v.st4((j0 >> 2) + 1, make_float4(in[4], in[5], in[6], in[7]));
+}
 
-// control u = generative_ctrl(tau, x) for dims [j0, j0+JC), given act = hidden activations at (tau, x),
-// the raw target score chunk `ts` (ScoreCtrl) and gamma = clip(score_model(tau)).
+// control u = generative_ctrl(tau, x) for dims [j0, j0+JC) after mlp.hidden(), given the raw target score chunk
+// `ts` (ScoreCtrl) and gamma = clip(score_model(tau)).   models/reparam.py:33-43, 112-117
+struct CtrlConst {
+  float bound_model, bound_score, scale_score;
+  bool score;
+  int d;
+};
+__device__ __forceinline__ CtrlConst ctrl_const(const lrds_spec& s) {
+  return CtrlConst{clip_bound(s.clip_model), clip_bound(s.clip_score), s.scale_score, s.ctrl_kind == LRDS_CTRL_SCORE, s.d};
+}
 template <class MLP>
-__device__ __forceinline__ void ctrl_chunk(const lrds_spec& s, MLP& mlp, int j0, const float (&ts)[JC], float gamma,
+__device__ __forceinline__ void ctrl_chunk(const CtrlConst& cc, MLP& mlp, int j0, const float (&ts)[JC], float gamma,
                                            float (&u)[JC]) {
   mlp.out_chunk(j0, u);
 #pragma unroll
   for (int c = 0; c < JC; ++c) {
-    float v = clipf(u[c], s.clip_model);
-    if (s.ctrl_kind == LRDS_CTRL_SCORE) v = v + (s.scale_score * clipf(ts[c], s.clip_score)) * gamma;
-    u[c] = (j0 + c < s.d) ? v : 0.f;
+    float v = clipb(u[c], cc.bound_model);
+    if (cc.score) v = v + (cc.scale_score * clipb(ts[c], cc.bound_score)) * gamma;
+    u[c] = (j0 + c < cc.d) ? v : 0.f;
   }
 }
 
@@ -157,8 +243,11 @@ __device__ __forceinline__ float langevin_drift(const lrds_spec& s, float ts, fl
 
 // `smem` = this CTA's column area (col_layout(s).total * blockDim.x floats); every thread of the CTA runs the body
 // with uniform control flow (idle lanes shadow the last particle), which the tensor-core policy relies on.
-template <int KIND, class MLP>
-__device__ __forceinline__ void rollout_body(const RolloutArgs& a, float* smem, MLP& mlp) {
+// STAGED (LINEAR kind): `stage` is a stage_layout(s).total-byte shared-memory area; the target mixture is copied
+// there once and the time-marginal reference block + table row of step k+1 are prefetched by the TMA engine
+// (cp.async.bulk + mbarrier, double buffered) while step k computes.  One CTA barrier per step keeps the buffers safe.
+template <int KIND, bool STAGED, class MLP>
+__device__ __forceinline__ void rollout_body(const RolloutArgs& a, float* smem, uint8_t* stage, MLP& mlp) {
   const lrds_spec& s = a.s;
   const int NT = blockDim.x;
   const int tid = threadIdx.x;
@@ -167,44 +256,72 @@ __device__ __forceinline__ void rollout_body(const RolloutArgs& a, float* smem, 
   const int b = live ? b_raw : s.B - 1;  // idle lanes shadow the last particle, results are not stored
   const int d = s.d, dp = s.mlp.d_pad, K = s.K;
   const ColLayout L = col_layout(s);
-  Particle P;
-  P.x = Col{smem + L.x * NT + tid, NT};
-  P.rt = Col{smem + L.rt * NT + tid, NT};
-  P.rr = Col{smem + L.rr * NT + tid, NT};
-  P.g = Col{smem + L.g * NT + tid, NT};
-  P.us = Col{smem + L.us * NT + tid, NT};
-  P.tsd = Col{smem + L.tsd * NT + tid, NT};
-  P.db = Col{smem + L.db * NT + tid, NT};
+  const Particle P = make_particle(smem, L, NT, tid);
 
   for (int j = 0; j < dp; ++j) P.x(j) = (j < d) ? __ldg(a.x0 + (int64_t)b * d + j) : 0.f;
   if (a.traj_out != nullptr && live)
     for (int j = 0; j < d; ++j) a.traj_out[(int64_t)b * d + j] = P.x(j);
 
   const bool score_ctrl = s.ctrl_kind == LRDS_CTRL_SCORE;
+  const bool need_nbr = s.target.kind == LRDS_DISTR_PHI4;  // lattice stencil reads x_{j0-1}, x_{j0+8}
+  const CtrlConst cc = ctrl_const(s);
+  const GmmView tv0 = gmm_at(s.target.gmm, 0);  // target mixture in global memory (dereferenced for GMM targets only)
   float rnd = 0.f;
 
   if constexpr (KIND == LRDS_ROLLOUT_LINEAR) {
+    constexpr bool SH = STAGED;
+    const StageLayout SL = stage_layout(s);
+    uint64_t* sbar = reinterpret_cast<uint64_t*>(stage);
+    GmmViewT<SH> tv{};
+    if constexpr (!STAGED) tv = tv0;
+    if constexpr (STAGED) {
+      if (tid == 0) {
+        ptx::mbar_init(sbar, 1);
+        ptx::mbar_init(sbar + 1, 1);
+        ptx::fence_mbar_init();
+      }
+      __syncthreads();
+      if (tid == 0) {
+        ptx::mbar_expect_tx(sbar, SL.tgt_bytes + SL.buf_bytes);
+        if (SL.tgt_bytes) stage_gmm(stage + SL.off_tgt, tv0, SL.tgt_logc_bytes, SL.tgt_param_bytes, sbar);
+        stage_step(stage + SL.off_buf, s, SL, 0, sbar);
+      }
+      tv = staged_view(stage + SL.off_tgt, tv0.M, SL.tgt_logc_bytes, SL.tgt_param_bytes);
+    }
     for (int k = 0; k < K; ++k) {
       const float* row = s.steps + (int64_t)k * LRDS_STEP_STRIDE;
-      const float A = __ldg(row + LRDS_STEP_A), Bc = __ldg(row + LRDS_STEP_B), Cc = __ldg(row + LRDS_STEP_C);
-      const float dt = __ldg(row + LRDS_STEP_DT), sqdt = __ldg(row + LRDS_STEP_SQRT_DT);
-      const float wcost = __ldg(row + LRDS_STEP_W_COST), wito = __ldg(row + LRDS_STEP_W_ITO);
-      const float gamma = __ldg(row + LRDS_STEP_GAMMA), sigu = __ldg(row + LRDS_STEP_SIGU);
-      if (score_ctrl) target_pass1(s, P, false);
-      GmmView rv{};
-      if (s.has_ref_ctrl) {
-        rv = gmm_at(s.ref_t, k);
-        if (rv.M > 1) gmm_pass1(rv, d, P.x, P.rr);
+      GmmViewT<SH> rv{};
+      PPtr<SH> rowp{};
+      if constexpr (STAGED) {
+        __syncthreads();  // every warp has finished step k-1, whose buffer the prefetch below overwrites
+        if (tid == 0 && k + 1 < K) {
+          ptx::mbar_expect_tx(sbar + ((k + 1) & 1), SL.buf_bytes);
+          stage_step(stage + SL.off_buf + ((k + 1) & 1) * SL.buf_bytes, s, SL, k + 1, sbar + ((k + 1) & 1));
+        }
+        ptx::mbar_wait(sbar + (k & 1), (uint32_t)(k >> 1) & 1u);
+        const uint8_t* buf = stage + SL.off_buf + (k & 1) * SL.buf_bytes;
+        row = reinterpret_cast<const float*>(buf);
+        rowp = PPtr<true>{ptx::smem_u32(buf)};
+        if (s.has_ref_ctrl) rv = staged_view(buf + SL.row_bytes, s.ref_t.M, SL.ref_logc_bytes, SL.ref_param_bytes);
+      } else {
+        rowp = PPtr<false>{row};
+        if (s.has_ref_ctrl) rv = gmm_at(s.ref_t, k);
       }
-      mlp.hidden(row + LRDS_STEP_BIAS1, P.x);
+      const float A = rowp.ld1(LRDS_STEP_A), Bc = rowp.ld1(LRDS_STEP_B), Cc = rowp.ld1(LRDS_STEP_C);
+      const float dt = rowp.ld1(LRDS_STEP_DT), sqdt = rowp.ld1(LRDS_STEP_SQRT_DT);
+      const float wcost = rowp.ld1(LRDS_STEP_W_COST), wito = rowp.ld1(LRDS_STEP_W_ITO);
+      const float gamma = rowp.ld1(LRDS_STEP_GAMMA), sigu = rowp.ld1(LRDS_STEP_SIGU);
+      if (score_ctrl) target_pass1(s, tv, P, false);
+      if (s.has_ref_ctrl && rv.M > 1) gmm_pass1(rv, dp, P.x, P.rr);
+      mlp.template hidden<SH>(row + LRDS_STEP_BIAS1, P.x);
       float su2 = 0.f, sito = 0.f, xm = 0.f;
       for (int j0 = 0; j0 < dp; j0 += JC) {
         float xr[JC], ts[JC], u[JC], rs[JC], z[JC], xn[JC];
         load_chunk(P.x, j0, xr);
-        const float xp = (j0 + JC < dp) ? P.x(j0 + JC) : 0.f;
-        if (score_ctrl) target_score_chunk(s, P, xr, xm, xp, j0, ts);
-        ctrl_chunk(s, mlp, j0, ts, gamma, u);
-        if (s.has_ref_ctrl) gmm_score_chunk(rv, d, xr, P.rr, j0, rs);
+        const float xp = (need_nbr && j0 + JC < dp) ? P.x(j0 + JC) : 0.f;
+        if (score_ctrl) target_score_chunk(s, tv, P, xr, xm, xp, j0, ts);
+        ctrl_chunk(cc, mlp, j0, ts, gamma, u);
+        if (s.has_ref_ctrl) gmm_score_chunk(rv, dp, xr, P.rr, j0, rs);
         noise_chunk(a, k, b, j0, z);
 #pragma unroll
         for (int c = 0; c < JC; ++c) {
@@ -223,8 +340,7 @@ __device__ __forceinline__ void rollout_body(const RolloutArgs& a, float* smem, 
           if (j0 + c >= d) xn[c] = 0.f;
         }
         xm = xr[JC - 1];
-#pragma unroll
-        for (int c = 0; c < JC; ++c) P.x(j0 + c) = xn[c];
+        store_chunk(P.x, j0, xn);
         if (a.traj_out != nullptr && live) store_traj(a, k + 1, b, j0, xn);
       }
       rnd += wcost * su2;
@@ -232,15 +348,15 @@ __device__ __forceinline__ void rollout_body(const RolloutArgs& a, float* smem, 
       else if (s.ito_form != LRDS_ITO_NONE) rnd += sito;
     }
     // terminal cost: rnd += reference_log_prob(x) - terminal_unnorm_log_prob(x)   (oc.py:290, 505, 645, 1389)
-    const float lref = gmm_pass1(gmm_at(s.ref_0, 0), d, P.x, P.rr);
-    const float ltgt = clipf(target_pass1(s, P, true), s.clip_target);
+    const float lref = gmm_pass1(gmm_at(s.ref_0, 0), dp, P.x, P.rr);
+    const float ltgt = clipf(target_pass1(s, tv, P, true), s.clip_target);
     rnd += lref - ltgt;
   }
 
   if constexpr (KIND == LRDS_ROLLOUT_EUBO_LINEAR) {
     {  // rnd = reference_log_prob(x) - terminal_unnorm_log_prob(x)   (oc.py:321, 536)
-      const float lref = gmm_pass1(gmm_at(s.ref_0, 0), d, P.x, P.rr);
-      const float ltgt = clipf(target_pass1(s, P, true), s.clip_target);
+      const float lref = gmm_pass1(gmm_at(s.ref_0, 0), dp, P.x, P.rr);
+      const float ltgt = clipf(target_pass1(s, tv0, P, true), s.clip_target);
       rnd = lref - ltgt;
     }
     for (int k = 0; k < K; ++k) {  // rows are stored in loop order (reversed time)
@@ -258,18 +374,18 @@ __device__ __forceinline__ void rollout_body(const RolloutArgs& a, float* smem, 
           P.x(j0 + c) = (j0 + c < d) ? fmaf(stdf, z[c], P.x(j0 + c) * mean) : 0.f;
         }
       }
-      if (score_ctrl) target_pass1(s, P, false);
+      if (score_ctrl) target_pass1(s, tv0, P, false);
       const GmmView rv = gmm_at(s.ref_t, k);
-      if (rv.M > 1) gmm_pass1(rv, d, P.x, P.rr);
-      mlp.hidden(row + LRDS_STEP_BIAS1, P.x);
+      if (rv.M > 1) gmm_pass1(rv, dp, P.x, P.rr);
+      mlp.template hidden<false>(row + LRDS_STEP_BIAS1, P.x);
       float cost = 0.f, gx = 0.f, gz = 0.f, xm = 0.f;
       for (int j0 = 0; j0 < dp; j0 += JC) {
         float xr[JC], ts[JC], u[JC], rs[JC];
         load_chunk(P.x, j0, xr);
-        const float xp = (j0 + JC < dp) ? P.x(j0 + JC) : 0.f;
-        if (score_ctrl) target_score_chunk(s, P, xr, xm, xp, j0, ts);
-        ctrl_chunk(s, mlp, j0, ts, gamma, u);
-        gmm_score_chunk(rv, d, xr, P.rr, j0, rs);
+        const float xp = (need_nbr && j0 + JC < dp) ? P.x(j0 + JC) : 0.f;
+        if (score_ctrl) target_score_chunk(s, tv0, P, xr, xm, xp, j0, ts);
+        ctrl_chunk(cc, mlp, j0, ts, gamma, u);
+        gmm_score_chunk(rv, dp, xr, P.rr, j0, rs);
 #pragma unroll
         for (int c = 0; c < JC; ++c) {
           const float g = (s.update_form == LRDS_UPDATE_EM) ? u[c] / sig : u[c];
@@ -293,20 +409,20 @@ __device__ __forceinline__ void rollout_body(const RolloutArgs& a, float* smem, 
     auto eval_point = [&](int rowi, bool first, float dtk, float frac_for_drift, float& c2, float& cdb) {
       const float* row = s.steps + (int64_t)rowi * LRDS_STEP_STRIDE;
       const float gamma = __ldg(row + LRDS_STEP_GAMMA);
-      target_pass1(s, P, false);
-      mlp.hidden(row + LRDS_STEP_BIAS1, P.x);
+      target_pass1(s, tv0, P, false);
+      mlp.template hidden<false>(row + LRDS_STEP_BIAS1, P.x);
       float xm = 0.f;
       for (int j0 = 0; j0 < dp; j0 += JC) {
         float xr[JC], ts[JC], u[JC];
         load_chunk(P.x, j0, xr);
-        const float xp = (j0 + JC < dp) ? P.x(j0 + JC) : 0.f;
-        target_score_chunk(s, P, xr, xm, xp, j0, ts);
-        ctrl_chunk(s, mlp, j0, ts, gamma, u);
+        const float xp = (need_nbr && j0 + JC < dp) ? P.x(j0 + JC) : 0.f;
+        target_score_chunk(s, tv0, P, xr, xm, xp, j0, ts);
+        ctrl_chunk(cc, mlp, j0, ts, gamma, u);
 #pragma unroll
         for (int c = 0; c < JC; ++c) {
           const int j = j0 + c;
           if (!first && j < d) {
-            const float ps = -((xr[c] - __ldg(prior.mu + j)) * __ldg(prior.ivar + j));
+            const float ps = -((xr[c] - prior.mu.ld1(j)) * prior.ivar.ld1(j));
             const float dnew = langevin_drift(s, ts[c], ps, frac_for_drift);
             // forward: cost = (drift_s + drift_t)/sig + u_s - u_t ; noising: (drift_s + drift_t)/sig + u_s - u_t
             // with (u_s, drift_s) the NEW point there (oc.py:737, 816)
@@ -324,7 +440,7 @@ __device__ __forceinline__ void rollout_body(const RolloutArgs& a, float* smem, 
     };
     float c2 = 0.f, cdb = 0.f;
     if constexpr (!EUBO) {
-      rnd = gmm_pass1(prior, d, P.x, P.rr);  // initial_log_prob(x), oc.py:698
+      rnd = gmm_pass1(prior, dp, P.x, P.rr);  // initial_log_prob(x), oc.py:698
       eval_point(0, true, 0.f, 0.f, c2, cdb);
       for (int k = 0; k < K; ++k) {
         const float* row = s.steps + (int64_t)k * LRDS_STEP_STRIDE;
@@ -339,7 +455,7 @@ __device__ __forceinline__ void rollout_body(const RolloutArgs& a, float* smem, 
             float y = 0.f;
             if (j < d) {
               const float xj = P.x(j);
-              const float ps = -((xj - __ldg(prior.mu + j)) * __ldg(prior.ivar + j));
+              const float ps = -((xj - prior.mu.ld1(j)) * prior.ivar.ld1(j));
               const float ds = langevin_drift(s, P.tsd(j), ps, fs);
               const float db = sqdt * z[c];
               y = xj + (ds + P.us(j) * sg) * dt + sg * db;
@@ -356,9 +472,9 @@ __device__ __forceinline__ void rollout_body(const RolloutArgs& a, float* smem, 
         rnd += 0.5f * c2 * dt;
         rnd += cdb;
       }
-      rnd -= clipf(target_pass1(s, P, true), s.clip_target);  // oc.py:750
+      rnd -= clipf(target_pass1(s, tv0, P, true), s.clip_target);  // oc.py:750
     } else {
-      rnd = -clipf(target_pass1(s, P, true), s.clip_target);  // oc.py:782
+      rnd = -clipf(target_pass1(s, tv0, P, true), s.clip_target);  // oc.py:782
       eval_point(K, true, 0.f, 0.f, c2, cdb);
       for (int i = 0; i < K; ++i) {
         const int kt = K - i, ks = K - 1 - i;  // t = ts[kt], s = ts[ks]
@@ -374,7 +490,7 @@ __device__ __forceinline__ void rollout_body(const RolloutArgs& a, float* smem, 
             float y = 0.f;
             if (j < d) {
               const float xj = P.x(j);
-              const float ps = -((xj - __ldg(prior.mu + j)) * __ldg(prior.ivar + j));
+              const float ps = -((xj - prior.mu.ld1(j)) * prior.ivar.ld1(j));
               const float dtt = langevin_drift(s, P.tsd(j), ps, ft);
               const float db = sqdt * z[c];
               y = xj + (dtt - P.us(j) * sg) * dt + sg * db;
@@ -389,7 +505,7 @@ __device__ __forceinline__ void rollout_body(const RolloutArgs& a, float* smem, 
         rnd -= 0.5f * c2 * dt;
         rnd -= cdb;
       }
-      rnd += gmm_pass1(prior, d, P.x, P.rr);  // oc.py:825
+      rnd += gmm_pass1(prior, dp, P.x, P.rr);  // oc.py:825
     }
   }
 
@@ -405,7 +521,7 @@ __global__ void __launch_bounds__(128) rollout_simt_kernel(const RolloutArgs a) 
   extern __shared__ float smem[];
   const ColLayout L = col_layout(a.s);
   SimtMlp mlp{a.s.mlp, Col{smem + L.act * blockDim.x + threadIdx.x, (int)blockDim.x}};
-  rollout_body<KIND>(a, smem, mlp);
+  rollout_body<KIND, false>(a, smem, nullptr, mlp);
 }
 
 }  // namespace lrds

@@ -20,6 +20,9 @@
 namespace lrds {
 
 constexpr int TC_MAX_WARPS = 16;
+// The 3-pass split needs 192 TMEM columns per tile, i.e. at most two tiles = 8 warps per CTA: compile it for 256
+// threads so that ptxas may use 255 registers and keep more operand loads in flight per warp.
+__host__ __device__ constexpr int tc_max_warps(int prec) { return prec == LRDS_PRECISION_TF32X3 ? 8 : TC_MAX_WARPS; }
 constexpr int TC_TAIL_BYTES = 64;  // mbarriers + TMEM slot after the image
 
 struct TcLayout {
@@ -163,22 +166,30 @@ struct TcMlp {
     }
   }
 
-  __device__ __forceinline__ void store_x(const Col& x) {
+  __device__ __forceinline__ void store_x(const Col4& x) {
     if (PREC == LRDS_PRECISION_BF16) {
-      for (int c0 = 0; c0 < L.Kin / 2; c0 += 8) {
+      for (int c0 = 0; c0 < L.Kin / 2; c0 += 8) {  // 16 dims -> 8 packed columns
+        float v[16];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int j0 = 2 * c0 + 8 * h;
+          float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+          if (j0 < dp) {
+            a = x.ld4(j0 >> 2);
+            b = x.ld4((j0 >> 2) + 1);
+          }
+          v[8 * h + 0] = a.x; v[8 * h + 1] = a.y; v[8 * h + 2] = a.z; v[8 * h + 3] = a.w;
+          v[8 * h + 4] = b.x; v[8 * h + 5] = b.y; v[8 * h + 6] = b.z; v[8 * h + 7] = b.w;
+        }
         uint32_t r[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int j = 2 * (c0 + i);
-          r[i] = ptx::pack_bf16x2(j < dp ? x(j) : 0.f, j + 1 < dp ? x(j + 1) : 0.f);
-        }
+        for (int i = 0; i < 8; ++i) r[i] = ptx::pack_bf16x2(v[2 * i], v[2 * i + 1]);
         ptx::tmem_st8(tm_lane + a_col(0) + c0, r);
       }
     } else {
       for (int c0 = 0; c0 < L.Kin; c0 += 8) {  // Kin == dp for the tf32 kinds
-        float v[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = x(c0 + i);
+        const float4 a = x.ld4(c0 >> 2), b = x.ld4((c0 >> 2) + 1);
+        const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
         store8(c0, v);
       }
     }
@@ -193,10 +204,14 @@ struct TcMlp {
       ptx::tmem_ld32(tm_lane + d_col() + c0, r);
       ptx::tmem_wait_ld();
       float g[32];
+      const float4* b4 = reinterpret_cast<const float4*>(bias + c0);  // warp-uniform, 16-byte aligned
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        const float b = GLOBAL_BIAS ? __ldg(bias + c0 + i) : bias[c0 + i];
-        g[i] = gelu_exact(__uint_as_float(r[i]) + b);
+      for (int i = 0; i < 8; ++i) {
+        const float4 b = GLOBAL_BIAS ? __ldg(b4 + i) : b4[i];
+        g[4 * i + 0] = gelu_exact(__uint_as_float(r[4 * i + 0]) + b.x);
+        g[4 * i + 1] = gelu_exact(__uint_as_float(r[4 * i + 1]) + b.y);
+        g[4 * i + 2] = gelu_exact(__uint_as_float(r[4 * i + 2]) + b.z);
+        g[4 * i + 3] = gelu_exact(__uint_as_float(r[4 * i + 3]) + b.w);
       }
       if (PREC == LRDS_PRECISION_BF16) {
         uint32_t p[16];
@@ -217,18 +232,20 @@ struct TcMlp {
     }
   }
 
-  __device__ __forceinline__ void hidden(const float* __restrict__ bias1, const Col& x) {
+  // BIAS_SH: the table row holding bias1 has been staged in shared memory
+  template <bool BIAS_SH>
+  __device__ __forceinline__ void hidden(const float* __restrict__ bias1, const Col4& x) {
     store_x(x);
     issue(L.off_in, L.Kin, C);
     const float* bh = reinterpret_cast<const float*>(img + L.off_bhid);
     for (int l = 0; l < L.nh; ++l) {
       wait();
-      if (l == 0) epilogue<true>(bias1);
+      if (l == 0) epilogue<!BIAS_SH>(bias1);
       else epilogue<false>(bh + (l - 1) * C);
       issue(L.off_hid + (uint32_t)(l * C * C * L.es), C, C);
     }
     wait();
-    if (L.nh == 0) epilogue<true>(bias1);
+    if (L.nh == 0) epilogue<!BIAS_SH>(bias1);
     else epilogue<false>(bh + (L.nh - 1) * C);
     issue(L.off_out, C, L.Nout);
     wait();
@@ -247,9 +264,12 @@ struct TcMlp {
   }
 };
 
+__host__ __device__ inline uint32_t tc_stage_bytes(const lrds_spec& s) { return (stage_layout(s).total + 15u) & ~15u; }
+
 // ---- kernel --------------------------------------------------------------------------------------------------------
-template <int KIND, int PREC>
-__global__ void __launch_bounds__(TC_MAX_WARPS * 32, 1)
+// shared memory: [weight image | mbarriers + TMEM slot | operand stage (STAGED) | particle columns]
+template <int KIND, int PREC, bool STAGED>
+__global__ void __launch_bounds__(tc_max_warps(PREC) * 32, 1)
 rollout_tc_kernel(const RolloutArgs a, const uint8_t* __restrict__ image, const uint32_t tmem_cols) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   const TcLayout TL = tc_layout(a.s.d, a.s.mlp.num_hidden, PREC);
@@ -257,7 +277,8 @@ rollout_tc_kernel(const RolloutArgs a, const uint8_t* __restrict__ image, const 
   uint8_t* img = smem_raw;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + TL.bytes);  // [0] image, [1 + t] tile t
   uint32_t* slot = reinterpret_cast<uint32_t*>(smem_raw + TL.bytes + 48);
-  float* cols = reinterpret_cast<float*>(smem_raw + TL.bytes + TC_TAIL_BYTES);
+  uint8_t* stage = smem_raw + TL.bytes + TC_TAIL_BYTES;
+  float* cols = reinterpret_cast<float*>(stage + (STAGED ? tc_stage_bytes(a.s) : 0u));
   if (warp == 0) ptx::tmem_alloc(slot, tmem_cols);
   if (tid == 0) {
     for (int i = 0; i < 5; ++i) ptx::mbar_init(bars + i, 1);
@@ -286,7 +307,7 @@ rollout_tc_kernel(const RolloutArgs a, const uint8_t* __restrict__ image, const 
   mlp.bar_threads = tile_warps * 32;
   mlp.issuer = (tid & 127) == 0;
   mlp.dp = a.s.mlp.d_pad;
-  rollout_body<KIND>(a, cols, mlp);
+  rollout_body<KIND, STAGED>(a, cols, stage, mlp);
   ptx::tc_fence_before();
   __syncthreads();
   if (warp == 0) ptx::tmem_dealloc(tmem, tmem_cols);
@@ -294,12 +315,13 @@ rollout_tc_kernel(const RolloutArgs a, const uint8_t* __restrict__ image, const 
 
 // ---- host side -------------------------------------------------------------------------------------------------------
 struct TcPlan {
-  int warps, grid;
+  int warps, grid, staged;
   uint32_t tmem_cols;
   size_t smem;
 };
 
 // Warps per CTA: as few waves as possible over the SMs (one CTA per SM), then as few idle lanes as possible.
+// Operand staging (LINEAR kind) is used when its shared-memory cost does not reduce the warps per CTA.
 inline int plan_rollout_tc(const lrds_spec& s, int smem_cap, int sms, TcPlan* out, const char** why) {
   const TcLayout TL = tc_layout(s.d, s.mlp.num_hidden, s.precision);
   const ColLayout CL = col_layout(s);
@@ -307,21 +329,32 @@ inline int plan_rollout_tc(const lrds_spec& s, int smem_cap, int sms, TcPlan* ou
   const size_t per_warp = (size_t)CL.total * 32 * sizeof(float);
   if (TL.tile_cols > 512) { *why = "TMEM columns of one tile exceed 512"; return LRDS_ERR_RESOURCES; }
   if (fixed + per_warp > (size_t)smem_cap) { *why = "weight image + one warp of particle state exceed shared memory"; return LRDS_ERR_RESOURCES; }
-  int wmax = (int)(((size_t)smem_cap - fixed) / per_warp);
-  wmax = wmax < TC_MAX_WARPS ? wmax : TC_MAX_WARPS;
   const int tmax = 512 / TL.tile_cols;
-  wmax = wmax < 4 * tmax ? wmax : 4 * tmax;
   const int need = (s.B + 31) / 32;
-  const int waves = (need + sms * wmax - 1) / (sms * wmax);
-  int w = (need + sms * waves - 1) / (sms * waves);
-  w = w < 1 ? 1 : (w > wmax ? wmax : w);
+  auto pick = [&](size_t extra, int* wmax_out) {
+    if (fixed + extra + per_warp > (size_t)smem_cap) { *wmax_out = 0; return 0; }
+    int wmax = (int)(((size_t)smem_cap - fixed - extra) / per_warp);
+    wmax = wmax < tc_max_warps(s.precision) ? wmax : tc_max_warps(s.precision);
+    wmax = wmax < 4 * tmax ? wmax : 4 * tmax;
+    *wmax_out = wmax;
+    const int waves = (need + sms * wmax - 1) / (sms * wmax);
+    int w = (need + sms * waves - 1) / (sms * waves);
+    return w < 1 ? 1 : (w > wmax ? wmax : w);
+  };
+  int wmax_plain = 0, wmax_staged = 0;
+  const int w_plain = pick(0, &wmax_plain);
+  const size_t stage = s.kind == LRDS_ROLLOUT_LINEAR ? tc_stage_bytes(s) : 0;
+  const int w_staged = stage ? pick(stage, &wmax_staged) : 0;
+  const bool staged = stage && w_staged >= w_plain;
+  const int w = staged ? w_staged : w_plain;
   const int tiles = (w + 3) / 4;
   uint32_t cols = 32;
   while ((int)cols < tiles * TL.tile_cols) cols <<= 1;
   out->warps = w;
   out->grid = (need + w - 1) / w;
+  out->staged = staged ? 1 : 0;
   out->tmem_cols = cols;
-  out->smem = fixed + per_warp * w;
+  out->smem = fixed + (staged ? stage : 0) + per_warp * w;
   return LRDS_OK;
 }
 

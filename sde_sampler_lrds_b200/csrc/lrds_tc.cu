@@ -11,9 +11,9 @@ namespace lrds {
 
 namespace {
 
-template <int KIND, int PREC>
+template <int KIND, int PREC, bool STAGED>
 int launch_one(const RolloutArgs& a, const TcPlan& p, cudaStream_t st, char* err, size_t n) {
-  auto kernel = rollout_tc_kernel<KIND, PREC>;
+  auto kernel = rollout_tc_kernel<KIND, PREC, STAGED>;
   cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
   if (e == cudaSuccess) {
     kernel<<<p.grid, p.warps * 32, p.smem, st>>>(a, static_cast<const uint8_t*>(a.s.mlp.tc_image), p.tmem_cols);
@@ -30,10 +30,12 @@ int launch_one(const RolloutArgs& a, const TcPlan& p, cudaStream_t st, char* err
 template <int PREC>
 int launch_kind(const RolloutArgs& a, const TcPlan& p, cudaStream_t st, char* err, size_t n) {
   switch (a.s.kind) {
-    case LRDS_ROLLOUT_LINEAR: return launch_one<LRDS_ROLLOUT_LINEAR, PREC>(a, p, st, err, n);
-    case LRDS_ROLLOUT_CMCD: return launch_one<LRDS_ROLLOUT_CMCD, PREC>(a, p, st, err, n);
-    case LRDS_ROLLOUT_EUBO_LINEAR: return launch_one<LRDS_ROLLOUT_EUBO_LINEAR, PREC>(a, p, st, err, n);
-    case LRDS_ROLLOUT_EUBO_CMCD: return launch_one<LRDS_ROLLOUT_EUBO_CMCD, PREC>(a, p, st, err, n);
+    case LRDS_ROLLOUT_LINEAR:
+      return p.staged ? launch_one<LRDS_ROLLOUT_LINEAR, PREC, true>(a, p, st, err, n)
+                      : launch_one<LRDS_ROLLOUT_LINEAR, PREC, false>(a, p, st, err, n);
+    case LRDS_ROLLOUT_CMCD: return launch_one<LRDS_ROLLOUT_CMCD, PREC, false>(a, p, st, err, n);
+    case LRDS_ROLLOUT_EUBO_LINEAR: return launch_one<LRDS_ROLLOUT_EUBO_LINEAR, PREC, false>(a, p, st, err, n);
+    case LRDS_ROLLOUT_EUBO_CMCD: return launch_one<LRDS_ROLLOUT_EUBO_CMCD, PREC, false>(a, p, st, err, n);
   }
   snprintf(err, n, "unknown rollout kind");
   return LRDS_ERR_INVALID;

@@ -20,26 +20,34 @@ DATA_DIR = Path(__file__).parents[2] / "data"
 
 
 def gmm_block(loc: torch.Tensor, var: torch.Tensor, weights: torch.Tensor | None, device):
-    """Packs a diagonal mixture into the (logc[M], mu[M][d], ivar[M][d]) block of lrds_gmm.
+    """Packs a diagonal mixture into the (logc, mu, ivar, muiv) block of lrds_gmm (include/lrds_b200.h).
 
     loc/var may carry a leading step axis ([S][M][d]) for the time-marginal reference.  logc follows
-    log_prob_gaussian (distr/gauss.py:67-73) + log of the normalised weights (gauss.py:100-104)."""
+    log_prob_gaussian (distr/gauss.py:67-73) + log of the normalised weights (gauss.py:100-104).  Rows are padded
+    to d_pad = 8 ceil(d/8) floats (mu = 0, 1/var = 0, mu/var = 0) and logc to a multiple of 4 entries, so that
+    the kernels read everything as aligned float4."""
     loc = loc.detach().to("cpu", torch.float32)
     var = var.detach().to("cpu", torch.float32).expand_as(loc)
-    d = loc.shape[-1]
+    d, M = loc.shape[-1], loc.shape[-2]
     logc = -0.5 * d * math.log(2.0 * math.pi) - 0.5 * torch.log(var).sum(dim=-1)
     if weights is not None:
         w = weights.detach().to("cpu", torch.float32)
         logc = logc + torch.log(w / w.sum())
     ivar = (1.0 / var.double()).float()
-    return (logc.contiguous().to(device), loc.contiguous().to(device), ivar.contiguous().to(device))
+    muiv = (loc.double() / var.double()).float()
+    pad = (-d) % 8
+    if pad:
+        loc, ivar, muiv = (torch.nn.functional.pad(t, (0, pad)) for t in (loc, ivar, muiv))
+    if (-M) % 4:
+        logc = torch.nn.functional.pad(logc, (0, (-M) % 4))
+    return tuple(t.contiguous().to(device) for t in (logc, loc, ivar, muiv))
 
 
 def fill_gmm(g: N.Gmm, block, stepped: bool = False):
-    logc, mu, ivar = block
+    logc, mu, ivar, muiv = block
     g.M = mu.shape[-2]
-    g.logc, g.mu, g.ivar = logc.data_ptr(), mu.data_ptr(), ivar.data_ptr()
-    g.step_stride_logc = g.M if stepped else 0
+    g.logc, g.mu, g.ivar, g.muiv = logc.data_ptr(), mu.data_ptr(), ivar.data_ptr(), muiv.data_ptr()
+    g.step_stride_logc = logc.shape[-1] if stepped else 0
     g.step_stride_param = g.M * mu.shape[-1] if stepped else 0
     return g
 

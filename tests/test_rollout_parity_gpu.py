@@ -87,3 +87,21 @@ def test_fast_modes_within_their_stated_tolerance(name, precision, device):
     for k, v in mref.items():
         if "log_norm_const" in k:
             assert abs(m[k] - v) <= ztol, (precision, k, m[k], v)
+
+
+def test_in_kernel_normals_follow_the_philox_spec(device):
+    """Production-mode noise: lrds_normals (the generator the rollout uses in-kernel) against oracle/philox_ref.py.
+    The device evaluates log/sqrt/sincos with the SFU approximations, hence the 2e-5 absolute tolerance."""
+    import ctypes as C
+
+    import numpy as np
+
+    from oracle import philox_ref
+    from sde_sampler_lrds_b200 import _native as N
+    K, B, d, seed, off = 3, 257, 50, 0x1234_5678_9ABC_DEF0, 1000
+    out = torch.empty(K, B, d, device=device)
+    N.check(N.lib().lrds_normals(C.c_uint64(seed), C.c_uint64(off), 0, K, B, d, N.ptr(out), N.stream_ptr(device)))
+    want = philox_ref.normals(seed, B, K, d, particle_offset=off)
+    got = out.cpu().numpy()
+    assert np.abs(got - want).max() < 2e-5
+    assert abs(got.mean()) < 0.02 and abs(got.std() - 1.0) < 0.02
