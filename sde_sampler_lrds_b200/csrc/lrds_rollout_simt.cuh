@@ -85,10 +85,11 @@ struct StageLayout {
   uint32_t buf_bytes, off_tgt, off_buf, total;
 };
 
-__host__ __device__ inline StageLayout stage_layout(const lrds_spec& s) {
+// level 1: table row + reference block per step; level 2: also the (static) target mixture
+__host__ __device__ inline StageLayout stage_layout(const lrds_spec& s, int level) {
   StageLayout L{};
   const uint32_t dp = (uint32_t)s.mlp.d_pad;
-  if (s.target.kind == LRDS_DISTR_GMM) {
+  if (level >= 2 && s.target.kind == LRDS_DISTR_GMM) {
     L.tgt_logc_bytes = (uint32_t)((s.target.gmm.M + 3) / 4 * 4) * 4u;
     L.tgt_param_bytes = (uint32_t)s.target.gmm.M * dp * 4u;
     L.tgt_bytes = L.tgt_logc_bytes + 3u * L.tgt_param_bytes;
@@ -243,10 +244,11 @@ __device__ __forceinline__ float langevin_drift(const lrds_spec& s, float ts, fl
 
 // `smem` = this CTA's column area (col_layout(s).total * blockDim.x floats); every thread of the CTA runs the body
 // with uniform control flow (idle lanes shadow the last particle), which the tensor-core policy relies on.
-// STAGED (LINEAR kind): `stage` is a stage_layout(s).total-byte shared-memory area; the target mixture is copied
-// there once and the time-marginal reference block + table row of step k+1 are prefetched by the TMA engine
-// (cp.async.bulk + mbarrier, double buffered) while step k computes.  One CTA barrier per step keeps the buffers safe.
-template <int KIND, bool STAGED, class MLP>
+// STAGE > 0 (LINEAR kind): `stage` is a stage_layout(s, STAGE).total-byte shared-memory area; the time-marginal
+// reference block + table row of step k+1 are prefetched by the TMA engine (cp.async.bulk + mbarrier, double
+// buffered) while step k computes, and with STAGE == 2 the target mixture is copied there once as well.
+// One CTA barrier per step keeps the buffers safe.
+template <int KIND, int STAGE, class MLP>
 __device__ __forceinline__ void rollout_body(const RolloutArgs& a, float* smem, uint8_t* stage, MLP& mlp) {
   const lrds_spec& s = a.s;
   const int NT = blockDim.x;
@@ -269,11 +271,12 @@ __device__ __forceinline__ void rollout_body(const RolloutArgs& a, float* smem, 
   float rnd = 0.f;
 
   if constexpr (KIND == LRDS_ROLLOUT_LINEAR) {
-    constexpr bool SH = STAGED;
-    const StageLayout SL = stage_layout(s);
+    constexpr bool STAGED = STAGE > 0;
+    constexpr bool SH = STAGED, TSH = STAGE > 1;
+    const StageLayout SL = stage_layout(s, STAGE);
     uint64_t* sbar = reinterpret_cast<uint64_t*>(stage);
-    GmmViewT<SH> tv{};
-    if constexpr (!STAGED) tv = tv0;
+    GmmViewT<TSH> tv{};
+    if constexpr (!TSH) tv = tv0;
     if constexpr (STAGED) {
       if (tid == 0) {
         ptx::mbar_init(sbar, 1);
@@ -286,7 +289,7 @@ __device__ __forceinline__ void rollout_body(const RolloutArgs& a, float* smem, 
         if (SL.tgt_bytes) stage_gmm(stage + SL.off_tgt, tv0, SL.tgt_logc_bytes, SL.tgt_param_bytes, sbar);
         stage_step(stage + SL.off_buf, s, SL, 0, sbar);
       }
-      tv = staged_view(stage + SL.off_tgt, tv0.M, SL.tgt_logc_bytes, SL.tgt_param_bytes);
+      if constexpr (TSH) tv = staged_view(stage + SL.off_tgt, tv0.M, SL.tgt_logc_bytes, SL.tgt_param_bytes);
     }
     for (int k = 0; k < K; ++k) {
       const float* row = s.steps + (int64_t)k * LRDS_STEP_STRIDE;
@@ -521,7 +524,7 @@ __global__ void __launch_bounds__(128) rollout_simt_kernel(const RolloutArgs a) 
   extern __shared__ float smem[];
   const ColLayout L = col_layout(a.s);
   SimtMlp mlp{a.s.mlp, Col{smem + L.act * blockDim.x + threadIdx.x, (int)blockDim.x}};
-  rollout_body<KIND, false>(a, smem, nullptr, mlp);
+  rollout_body<KIND, 0>(a, smem, nullptr, mlp);
 }
 
 }  // namespace lrds

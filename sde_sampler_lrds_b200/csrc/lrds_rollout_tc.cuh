@@ -264,11 +264,13 @@ struct TcMlp {
   }
 };
 
-__host__ __device__ inline uint32_t tc_stage_bytes(const lrds_spec& s) { return (stage_layout(s).total + 15u) & ~15u; }
+__host__ __device__ inline uint32_t tc_stage_bytes(const lrds_spec& s, int level) {
+  return level > 0 ? (stage_layout(s, level).total + 15u) & ~15u : 0u;
+}
 
 // ---- kernel --------------------------------------------------------------------------------------------------------
 // shared memory: [weight image | mbarriers + TMEM slot | operand stage (STAGED) | particle columns]
-template <int KIND, int PREC, bool STAGED>
+template <int KIND, int PREC, int STAGE>
 __global__ void __launch_bounds__(tc_max_warps(PREC) * 32, 1)
 rollout_tc_kernel(const RolloutArgs a, const uint8_t* __restrict__ image, const uint32_t tmem_cols) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -278,7 +280,7 @@ rollout_tc_kernel(const RolloutArgs a, const uint8_t* __restrict__ image, const 
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + TL.bytes);  // [0] image, [1 + t] tile t
   uint32_t* slot = reinterpret_cast<uint32_t*>(smem_raw + TL.bytes + 48);
   uint8_t* stage = smem_raw + TL.bytes + TC_TAIL_BYTES;
-  float* cols = reinterpret_cast<float*>(stage + (STAGED ? tc_stage_bytes(a.s) : 0u));
+  float* cols = reinterpret_cast<float*>(stage + tc_stage_bytes(a.s, STAGE));
   if (warp == 0) ptx::tmem_alloc(slot, tmem_cols);
   if (tid == 0) {
     for (int i = 0; i < 5; ++i) ptx::mbar_init(bars + i, 1);
@@ -307,7 +309,7 @@ rollout_tc_kernel(const RolloutArgs a, const uint8_t* __restrict__ image, const 
   mlp.bar_threads = tile_warps * 32;
   mlp.issuer = (tid & 127) == 0;
   mlp.dp = a.s.mlp.d_pad;
-  rollout_body<KIND, STAGED>(a, cols, stage, mlp);
+  rollout_body<KIND, STAGE>(a, cols, stage, mlp);
   ptx::tc_fence_before();
   __syncthreads();
   if (warp == 0) ptx::tmem_dealloc(tmem, tmem_cols);
@@ -341,18 +343,24 @@ inline int plan_rollout_tc(const lrds_spec& s, int smem_cap, int sms, TcPlan* ou
     int w = (need + sms * waves - 1) / (sms * waves);
     return w < 1 ? 1 : (w > wmax ? wmax : w);
   };
-  int wmax_plain = 0, wmax_staged = 0;
-  const int w_plain = pick(0, &wmax_plain);
-  const size_t stage = s.kind == LRDS_ROLLOUT_LINEAR ? tc_stage_bytes(s) : 0;
-  const int w_staged = stage ? pick(stage, &wmax_staged) : 0;
-  const bool staged = stage && w_staged >= w_plain;
-  const int w = staged ? w_staged : w_plain;
+  int wm = 0;
+  const int w_plain = pick(0, &wm);
+  int level = 0, w = w_plain;
+  size_t stage = 0;
+  if (s.kind == LRDS_ROLLOUT_LINEAR) {
+    for (int lv = 2; lv >= 1; --lv) {  // the deepest staging level that does not cost warps
+      const size_t bytes = tc_stage_bytes(s, lv);
+      const int wl = pick(bytes, &wm);
+      if (wl >= w_plain) { level = lv; w = wl; stage = bytes; break; }
+    }
+  }
+  const bool staged = level > 0;
   const int tiles = (w + 3) / 4;
   uint32_t cols = 32;
   while ((int)cols < tiles * TL.tile_cols) cols <<= 1;
   out->warps = w;
   out->grid = (need + w - 1) / w;
-  out->staged = staged ? 1 : 0;
+  out->staged = level;
   out->tmem_cols = cols;
   out->smem = fixed + (staged ? stage : 0) + per_warp * w;
   return LRDS_OK;

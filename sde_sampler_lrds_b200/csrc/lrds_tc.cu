@@ -11,9 +11,9 @@ namespace lrds {
 
 namespace {
 
-template <int KIND, int PREC, bool STAGED>
+template <int KIND, int PREC, int STAGE>
 int launch_one(const RolloutArgs& a, const TcPlan& p, cudaStream_t st, char* err, size_t n) {
-  auto kernel = rollout_tc_kernel<KIND, PREC, STAGED>;
+  auto kernel = rollout_tc_kernel<KIND, PREC, STAGE>;
   cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
   if (e == cudaSuccess) {
     kernel<<<p.grid, p.warps * 32, p.smem, st>>>(a, static_cast<const uint8_t*>(a.s.mlp.tc_image), p.tmem_cols);
@@ -31,11 +31,12 @@ template <int PREC>
 int launch_kind(const RolloutArgs& a, const TcPlan& p, cudaStream_t st, char* err, size_t n) {
   switch (a.s.kind) {
     case LRDS_ROLLOUT_LINEAR:
-      return p.staged ? launch_one<LRDS_ROLLOUT_LINEAR, PREC, true>(a, p, st, err, n)
-                      : launch_one<LRDS_ROLLOUT_LINEAR, PREC, false>(a, p, st, err, n);
-    case LRDS_ROLLOUT_CMCD: return launch_one<LRDS_ROLLOUT_CMCD, PREC, false>(a, p, st, err, n);
-    case LRDS_ROLLOUT_EUBO_LINEAR: return launch_one<LRDS_ROLLOUT_EUBO_LINEAR, PREC, false>(a, p, st, err, n);
-    case LRDS_ROLLOUT_EUBO_CMCD: return launch_one<LRDS_ROLLOUT_EUBO_CMCD, PREC, false>(a, p, st, err, n);
+      return p.staged == 2   ? launch_one<LRDS_ROLLOUT_LINEAR, PREC, 2>(a, p, st, err, n)
+             : p.staged == 1 ? launch_one<LRDS_ROLLOUT_LINEAR, PREC, 1>(a, p, st, err, n)
+                             : launch_one<LRDS_ROLLOUT_LINEAR, PREC, 0>(a, p, st, err, n);
+    case LRDS_ROLLOUT_CMCD: return launch_one<LRDS_ROLLOUT_CMCD, PREC, 0>(a, p, st, err, n);
+    case LRDS_ROLLOUT_EUBO_LINEAR: return launch_one<LRDS_ROLLOUT_EUBO_LINEAR, PREC, 0>(a, p, st, err, n);
+    case LRDS_ROLLOUT_EUBO_CMCD: return launch_one<LRDS_ROLLOUT_EUBO_CMCD, PREC, 0>(a, p, st, err, n);
   }
   snprintf(err, n, "unknown rollout kind");
   return LRDS_ERR_INVALID;
