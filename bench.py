@@ -70,13 +70,16 @@ class ClockSampler(threading.Thread):
             nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
             self.ready.set()
             while not self._stop_evt.is_set():
+                # polled continuously from before the warm-up (a first NVML query inside the timed region stalls the
+                # launch path for tens of ms); only samples taken while `recording` are reported
+                mhz = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
                 if self.recording:
-                    self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
-                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                    self.samples.append(mhz)
                     for bit, name in names.items():
                         if r & bit:
                             self.reasons.add(name)
-                time.sleep(0.02)
+                time.sleep(0.05)
         except Exception as e:  # pragma: no cover
             self.reasons.add(f"nvml_unavailable:{type(e).__name__}")
             self.ready.set()
