@@ -35,6 +35,7 @@ struct Col4 {
   int stride;  // 4 * blockDim.x floats between consecutive groups
   __device__ __forceinline__ float& operator()(int j) const { return p[(j >> 2) * stride + (j & 3)]; }
   __device__ __forceinline__ float4 ld4(int c) const { return *reinterpret_cast<const float4*>(p + c * stride); }
+  __device__ __forceinline__ ulonglong2 ldu(int c) const { return *reinterpret_cast<const ulonglong2*>(p + c * stride); }
   __device__ __forceinline__ void st4(int c, const float4& v) const { *reinterpret_cast<float4*>(p + c * stride) = v; }
 };
 
@@ -107,6 +108,33 @@ __device__ __forceinline__ void normals4(uint64_t seed, uint32_t pidx, uint32_t 
 // ---------------------------------------------------------------------------------------------------
 // diagonal Gaussian mixture
 // ---------------------------------------------------------------------------------------------------
+// Packed fp32x2 arithmetic (FFMA2 / FMUL2 on sm_100): one issue slot for two lanes of work.
+typedef unsigned long long u64;
+namespace f2 {
+__device__ __forceinline__ u64 pack(float a, float b) {
+  u64 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void unpack(u64 v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ u64 fma(u64 a, u64 b, u64 c) {
+  u64 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ u64 mul(u64 a, u64 b) {
+  u64 d;
+  asm("mul.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ float hsum(u64 a, u64 b) {  // (a.x + a.y) + (b.x + b.y)
+  float x, y, z, w;
+  unpack(a, x, y);
+  unpack(b, z, w);
+  return (x + y) + (z + w);
+}
+}  // namespace f2
+
 // Warp-uniform operand pointer.  SH = the operand block sits in shared memory (staged per step by the TMA engine:
 // one wavefront per warp-uniform LDS.128, 32-bit address arithmetic) instead of global memory (read-only path:
 // four wavefronts per warp-uniform LDG.128).
@@ -118,6 +146,7 @@ struct PPtr<false> {
   __device__ __forceinline__ PPtr operator+(int floats) const { return PPtr{p + floats}; }
   __device__ __forceinline__ float4 ld4(int i) const { return __ldg(reinterpret_cast<const float4*>(p) + i); }
   __device__ __forceinline__ float ld1(int i) const { return __ldg(p + i); }
+  __device__ __forceinline__ ulonglong2 ld2(int i) const { return __ldg(reinterpret_cast<const ulonglong2*>(p) + i); }
 };
 template <>
 struct PPtr<true> {
@@ -133,6 +162,11 @@ struct PPtr<true> {
     asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a + 4u * (uint32_t)i));
     return v;
   }
+  __device__ __forceinline__ ulonglong2 ld2(int i) const {  // the same 16 bytes as two packed fp32 pairs
+    ulonglong2 v;
+    asm volatile("ld.shared.v2.b64 {%0,%1}, [%2];" : "=l"(v.x), "=l"(v.y) : "r"(a + 16u * (uint32_t)i));
+    return v;
+  }
 };
 
 template <bool SH>
@@ -141,25 +175,30 @@ __device__ __forceinline__ float4 gld4(const float4* p) {  // plain pointers: sh
   else return __ldg(p);
 }
 
+// A mixture block.  Mixtures (M > 1) are evaluated from (logc, siv = 1/sigma, nm = -mu/sigma), possibly staged in
+// shared memory; single Gaussians (M == 1) from (glogc, mu, ivar) in global memory in the reference's operation order.
 template <bool SH>
 struct GmmViewT {
   int M;
-  PPtr<SH> logc, mu, ivar, muiv;
+  PPtr<SH> logc, siv, nm;
+  PPtr<false> glogc, mu, ivar;
 };
 using GmmView = GmmViewT<false>;
 
 // step_stride_param counts floats of the padded rows (M * d_pad per step)
 __device__ __forceinline__ GmmView gmm_at(const lrds_gmm& g, int step) {
   GmmView v;
+  const int64_t o = (int64_t)step * g.step_stride_param;
   v.M = g.M;
-  v.logc = PPtr<false>{g.logc + (int64_t)step * g.step_stride_logc};
-  v.mu = PPtr<false>{g.mu + (int64_t)step * g.step_stride_param};
-  v.ivar = PPtr<false>{g.ivar + (int64_t)step * g.step_stride_param};
-  v.muiv = PPtr<false>{g.muiv + (int64_t)step * g.step_stride_param};
+  v.logc = v.glogc = PPtr<false>{g.logc + (int64_t)step * g.step_stride_logc};
+  v.mu = PPtr<false>{g.mu + o};
+  v.ivar = PPtr<false>{g.ivar + o};
+  v.siv = PPtr<false>{g.siv + o};
+  v.nm = PPtr<false>{g.nmsiv + o};
   return v;
 }
 
-// Mixture parameters are rows of dp = d_pad floats (zero padded: mu = 0, 1/var = 0), read as warp-uniform float4.
+// Mixture parameters are rows of dp = d_pad floats (zero padded), read as warp-uniform 16-byte vectors.
 __device__ __forceinline__ void quad4(float& q, const float4& xv, const float4& mu, const float4& iv) {
   float t;
   t = xv.x - mu.x; q = fmaf(t * t, iv.x, q);
@@ -168,45 +207,104 @@ __device__ __forceinline__ void quad4(float& q, const float4& xv, const float4& 
   t = xv.w - mu.w; q = fmaf(t * t, iv.w, q);
 }
 
+// one mode, four dims:  w = x / sigma - mu / sigma (one FFMA2 per pair), q += w^2 (one FFMA2 per pair)
+template <bool SH>
+__device__ __forceinline__ void quad4p(u64& qa, u64& qb, const ulonglong2& xv, const PPtr<SH>& siv, const PPtr<SH>& nm, int o) {
+  const ulonglong2 s = siv.ld2(o), n = nm.ld2(o);
+  const u64 w0 = f2::fma(xv.x, s.x, n.x), w1 = f2::fma(xv.y, s.y, n.y);
+  qa = f2::fma(w0, w0, qa);
+  qb = f2::fma(w1, w1, qb);
+}
+
+// Operands of one pass-1 block: four dims of x and of four modes' (1/sigma, -mu/sigma).  The loops below keep two
+// of these in registers and load block c+1 while block c computes (ptxas does not pipeline loads across loop
+// iterations on its own, and with <= 2 warps per scheduler nothing else hides the operand latency).
+template <bool SH>
+struct Pass1Ops {
+  ulonglong2 xv, s[4], n[4];
+  __device__ __forceinline__ void load(const Col4& x, const PPtr<SH>& siv, const PPtr<SH>& nm, int c, int o, int rowq) {
+    xv = x.ldu(c);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      s[i] = siv.ld2(o + i * rowq);
+      n[i] = nm.ld2(o + i * rowq);
+    }
+  }
+  // w = x / sigma - mu / sigma (one FFMA2 per pair of dims), q += w^2 (one FFMA2 per pair)
+  __device__ __forceinline__ void accumulate(u64 (&qa)[4], u64 (&qb)[4]) const {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const u64 w0 = f2::fma(xv.x, s[i].x, n[i].x), w1 = f2::fma(xv.y, s[i].y, n[i].y);
+      qa[i] = f2::fma(w0, w0, qa[i]);
+      qb[i] = f2::fma(w1, w1, qb[i]);
+    }
+  }
+};
+
 // Pass 1: responsibilities r(m) = softmax_m(logc_m - q_m / 2), q_m = sum_j (x_j - mu_mj)^2 / var_mj.
 // Returns log sum_m exp(logit_m) (= the mixture log-density).  For M == 1, r is not touched.
 // r holds 4 * ceil(M / 4) entries; the tail beyond M is left at zero weight.
-template <bool SH>
-__device__ __forceinline__ float gmm_pass1(const GmmViewT<SH>& g, int dp, const Col4& x, const Col4& r) {
-  const int nq = dp >> 2;
-  const PPtr<SH> mu = g.mu, iv = g.ivar;
+// PIPE: software-pipelined operand loads (needs ~40 more registers; used by the kernels compiled for <= 256 threads)
+template <bool PIPE, bool SH>
+__device__ __forceinline__ float gmm_pass1(const GmmViewT<SH>& g, int d, int dp, const Col4& x, const Col4& r) {
+  const int nq = (d + 3) >> 2;  // 16-byte groups that hold real dims
+  const int rowq = dp >> 2;     // row pitch in 16-byte groups
   if (g.M == 1) {
     float q = 0.f;
-    for (int c = 0; c < nq; ++c) quad4(q, x.ld4(c), mu.ld4(c), iv.ld4(c));
-    return g.logc.ld1(0) - 0.5f * q;
+    for (int c = 0; c < nq; ++c) quad4(q, x.ld4(c), g.mu.ld4(c), g.ivar.ld4(c));
+    return g.glogc.ld1(0) - 0.5f * q;
   }
+  const PPtr<SH> siv = g.siv, nm = g.nm;
   float mx = -INFINITY;
   const int M4 = (g.M + 3) >> 2;
   for (int mb = 0; mb < M4; ++mb) {  // 4 modes at a time so that one x load feeds 4 quadratic forms
     const int m = 4 * mb;
     float4 l;
     if (m + 4 <= g.M) {
-      float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
-      int o = m * nq;
+      u64 qa[4] = {0, 0, 0, 0}, qb[4] = {0, 0, 0, 0};  // (even, odd) dim partial sums per mode
+      const int o = m * rowq;
+      if constexpr (PIPE) {
+        Pass1Ops<SH> A, B;
+        A.load(x, siv, nm, 0, o, rowq);
+        int c = 0;
+        for (; c + 1 < nq; c += 2) {
+          B.load(x, siv, nm, c + 1, o + c + 1, rowq);
+          A.accumulate(qa, qb);
+          if (c + 2 < nq) A.load(x, siv, nm, c + 2, o + c + 2, rowq);
+          B.accumulate(qa, qb);
+        }
+        if (c < nq) A.accumulate(qa, qb);
+      } else {
+        u64 qa0 = 0, qb0 = 0, qa1 = 0, qb1 = 0, qa2 = 0, qb2 = 0, qa3 = 0, qb3 = 0;
+        int oc = o;
 #pragma unroll 2
-      for (int c = 0; c < nq; ++c, ++o) {
-        const float4 xv = x.ld4(c);
-        quad4(q0, xv, mu.ld4(o), iv.ld4(o));
-        quad4(q1, xv, mu.ld4(o + nq), iv.ld4(o + nq));
-        quad4(q2, xv, mu.ld4(o + 2 * nq), iv.ld4(o + 2 * nq));
-        quad4(q3, xv, mu.ld4(o + 3 * nq), iv.ld4(o + 3 * nq));
+        for (int c = 0; c < nq; ++c, ++oc) {
+          const ulonglong2 xv = x.ldu(c);
+          quad4p(qa0, qb0, xv, siv, nm, oc);
+          quad4p(qa1, qb1, xv, siv, nm, oc + rowq);
+          quad4p(qa2, qb2, xv, siv, nm, oc + 2 * rowq);
+          quad4p(qa3, qb3, xv, siv, nm, oc + 3 * rowq);
+        }
+        qa[0] = qa0; qb[0] = qb0; qa[1] = qa1; qb[1] = qb1; qa[2] = qa2; qb[2] = qb2; qa[3] = qa3; qb[3] = qb3;
       }
       const float4 lc = g.logc.ld4(mb);
-      l = make_float4(lc.x - 0.5f * q0, lc.y - 0.5f * q1, lc.z - 0.5f * q2, lc.w - 0.5f * q3);
+      l = make_float4(lc.x - 0.5f * f2::hsum(qa[0], qb[0]), lc.y - 0.5f * f2::hsum(qa[1], qb[1]),
+                      lc.z - 0.5f * f2::hsum(qa[2], qb[2]), lc.w - 0.5f * f2::hsum(qa[3], qb[3]));
     } else {  // ragged tail: absent modes get logit -inf
       float lv[4];
+#pragma unroll
       for (int i = 0; i < 4; ++i) {
         lv[i] = -INFINITY;
         if (m + i < g.M) {
-          float q = 0.f;
-          const int o = (m + i) * nq;
-          for (int c = 0; c < nq; ++c) quad4(q, x.ld4(c), mu.ld4(o + c), iv.ld4(o + c));
-          lv[i] = g.logc.ld1(m + i) - 0.5f * q;
+          u64 qa = 0, qb = 0;
+          const int o = (m + i) * rowq;
+          for (int c = 0; c < nq; ++c) {
+            const ulonglong2 xv = x.ldu(c), sv = siv.ld2(o + c), nv = nm.ld2(o + c);
+            const u64 w0 = f2::fma(xv.x, sv.x, nv.x), w1 = f2::fma(xv.y, sv.y, nv.y);
+            qa = f2::fma(w0, w0, qa);
+            qb = f2::fma(w1, w1, qb);
+          }
+          lv[i] = g.logc.ld1(m + i) - 0.5f * f2::hsum(qa, qb);
         }
       }
       l = make_float4(lv[0], lv[1], lv[2], lv[3]);
@@ -230,15 +328,41 @@ __device__ __forceinline__ float gmm_pass1(const GmmViewT<SH>& g, int dp, const 
   return mx + __logf(s);
 }
 
-// Pass 2 for dims [j0, j0+JC):  score_j = -sum_m r_m (x_j - mu_mj) / var_mj, evaluated as
-//   sum_m r_m (mu / var)_mj  -  x_j sum_m r_m (1 / var)_mj      (two FFMA per mode and dim; zero for the padded dims)
+// Operands of one mode for an 8-dim chunk of pass 2
 template <bool SH>
-__device__ __forceinline__ void gmm_score_chunk(const GmmViewT<SH>& g, int dp, const float (&xr)[JC], const Col4& r, int j0,
-                                                float (&out)[JC]) {
-  const int nq = dp >> 2;
-  const PPtr<SH> iv = g.ivar + j0, mv = g.muiv + j0;
+struct Pass2Ops {
+  ulonglong2 s0, n0, s1, n1;
+  __device__ __forceinline__ void load(const PPtr<SH>& siv, const PPtr<SH>& nm, int o, bool two) {
+    s0 = siv.ld2(o);
+    n0 = nm.ld2(o);
+    if (two) {
+      s1 = siv.ld2(o + 1);
+      n1 = nm.ld2(o + 1);
+    }
+  }
+  // c = r / sigma;  a += c / sigma;  b += c (-mu / sigma)
+  __device__ __forceinline__ void accumulate(float rm, bool two, u64 (&a)[4], u64 (&b)[4]) const {
+    const u64 rm2 = f2::pack(rm, rm);
+    const u64 c0 = f2::mul(rm2, s0.x), c1 = f2::mul(rm2, s0.y);
+    a[0] = f2::fma(c0, s0.x, a[0]); b[0] = f2::fma(c0, n0.x, b[0]);
+    a[1] = f2::fma(c1, s0.y, a[1]); b[1] = f2::fma(c1, n0.y, b[1]);
+    if (two) {
+      const u64 c2 = f2::mul(rm2, s1.x), c3 = f2::mul(rm2, s1.y);
+      a[2] = f2::fma(c2, s1.x, a[2]); b[2] = f2::fma(c2, n1.x, b[2]);
+      a[3] = f2::fma(c3, s1.y, a[3]); b[3] = f2::fma(c3, n1.y, b[3]);
+    }
+  }
+};
+
+// Pass 2 for dims [j0, j0+JC):  score_j = -sum_m r_m (x_j - mu_mj) / var_mj.  With c_mj = r_m / sigma_mj:
+//   score_j = -( x_j sum_m c_mj / sigma_mj  +  sum_m c_mj (-mu_mj / sigma_mj) )
+// i.e. one FMUL2 + two FFMA2 per mode and pair of dims (zero for the padded dims).
+template <bool PIPE, bool SH>
+__device__ __forceinline__ void gmm_score_chunk(const GmmViewT<SH>& g, int d, int dp, const float (&xr)[JC], const Col4& r,
+                                                int j0, float (&out)[JC]) {
+  const int rowq = dp >> 2;
   if (g.M == 1) {  // -((x - mu) * ivar), the operation order of score_gauss (distr/gauss.py:124-126)
-    const PPtr<SH> mu = g.mu + j0;
+    const PPtr<false> mu = g.mu + j0, iv = g.ivar + j0;
     const float4 m0 = mu.ld4(0), m1 = mu.ld4(1), i0 = iv.ld4(0), i1 = iv.ld4(1);
     out[0] = -((xr[0] - m0.x) * i0.x); out[1] = -((xr[1] - m0.y) * i0.y);
     out[2] = -((xr[2] - m0.z) * i0.z); out[3] = -((xr[3] - m0.w) * i0.w);
@@ -246,28 +370,64 @@ __device__ __forceinline__ void gmm_score_chunk(const GmmViewT<SH>& g, int dp, c
     out[6] = -((xr[6] - m1.z) * i1.z); out[7] = -((xr[7] - m1.w) * i1.w);
     return;
   }
-  float a[JC], b[JC];
-#pragma unroll
-  for (int c = 0; c < JC; ++c) a[c] = b[c] = 0.f;
-  auto mode = [&](float rm, int o) {
-    const float4 i0 = iv.ld4(o), i1 = iv.ld4(o + 1), v0 = mv.ld4(o), v1 = mv.ld4(o + 1);
-    a[0] = fmaf(rm, i0.x, a[0]); a[1] = fmaf(rm, i0.y, a[1]); a[2] = fmaf(rm, i0.z, a[2]); a[3] = fmaf(rm, i0.w, a[3]);
-    a[4] = fmaf(rm, i1.x, a[4]); a[5] = fmaf(rm, i1.y, a[5]); a[6] = fmaf(rm, i1.z, a[6]); a[7] = fmaf(rm, i1.w, a[7]);
-    b[0] = fmaf(rm, v0.x, b[0]); b[1] = fmaf(rm, v0.y, b[1]); b[2] = fmaf(rm, v0.z, b[2]); b[3] = fmaf(rm, v0.w, b[3]);
-    b[4] = fmaf(rm, v1.x, b[4]); b[5] = fmaf(rm, v1.y, b[5]); b[6] = fmaf(rm, v1.z, b[6]); b[7] = fmaf(rm, v1.w, b[7]);
-  };
+  const PPtr<SH> siv = g.siv + j0, nm = g.nm + j0;
+  const bool two = j0 + 4 < d;  // the second 16-byte group of the chunk holds real dims
+  u64 a[4] = {0, 0, 0, 0}, b[4] = {0, 0, 0, 0};
   const int M4 = g.M >> 2;
   int o = 0;
-  for (int mb = 0; mb < M4; ++mb, o += 4 * nq) {
-    const float4 rm = r.ld4(mb);
-    mode(rm.x, o);
-    mode(rm.y, o + nq);
-    mode(rm.z, o + 2 * nq);
-    mode(rm.w, o + 3 * nq);
+  if (!PIPE) {
+    u64 a0 = 0, a1 = 0, a2 = 0, a3 = 0, b0 = 0, b1 = 0, b2 = 0, b3 = 0;
+    auto mode = [&](float rm, int oo) {
+      const u64 rm2 = f2::pack(rm, rm);
+      {
+        const ulonglong2 sv = siv.ld2(oo), nv = nm.ld2(oo);
+        const u64 c0 = f2::mul(rm2, sv.x), c1 = f2::mul(rm2, sv.y);
+        a0 = f2::fma(c0, sv.x, a0); b0 = f2::fma(c0, nv.x, b0);
+        a1 = f2::fma(c1, sv.y, a1); b1 = f2::fma(c1, nv.y, b1);
+      }
+      if (two) {
+        const ulonglong2 sv = siv.ld2(oo + 1), nv = nm.ld2(oo + 1);
+        const u64 c0 = f2::mul(rm2, sv.x), c1 = f2::mul(rm2, sv.y);
+        a2 = f2::fma(c0, sv.x, a2); b2 = f2::fma(c0, nv.x, b2);
+        a3 = f2::fma(c1, sv.y, a3); b3 = f2::fma(c1, nv.y, b3);
+      }
+    };
+    for (int mb = 0; mb < M4; ++mb, o += 4 * rowq) {
+      const float4 rm = r.ld4(mb);
+      mode(rm.x, o);
+      mode(rm.y, o + rowq);
+      mode(rm.z, o + 2 * rowq);
+      mode(rm.w, o + 3 * rowq);
+    }
+    a[0] = a0; a[1] = a1; a[2] = a2; a[3] = a3; b[0] = b0; b[1] = b1; b[2] = b2; b[3] = b3;
+  } else if (M4 > 0) {  // operands of mode m+1 are loaded while mode m accumulates
+    Pass2Ops<SH> A, B;
+    A.load(siv, nm, 0, two);
+    for (int mb = 0; mb < M4; ++mb, o += 4 * rowq) {
+      const float4 rm = r.ld4(mb);
+      B.load(siv, nm, o + rowq, two);
+      A.accumulate(rm.x, two, a, b);
+      A.load(siv, nm, o + 2 * rowq, two);
+      B.accumulate(rm.y, two, a, b);
+      B.load(siv, nm, o + 3 * rowq, two);
+      A.accumulate(rm.z, two, a, b);
+      if (mb + 1 < M4) A.load(siv, nm, o + 4 * rowq, two);
+      B.accumulate(rm.w, two, a, b);
+    }
   }
-  for (int m = 4 * M4; m < g.M; ++m, o += nq) mode(r(m), o);
+  for (int m = 4 * M4; m < g.M; ++m, o += rowq) {
+    Pass2Ops<SH> T;
+    T.load(siv, nm, o, two);
+    T.accumulate(r(m), two, a, b);
+  }
 #pragma unroll
-  for (int c = 0; c < JC; ++c) out[c] = fmaf(-xr[c], a[c], b[c]);
+  for (int p = 0; p < 4; ++p) {
+    float ax, ay, bx, by;
+    f2::unpack(a[p], ax, ay);
+    f2::unpack(b[p], bx, by);
+    out[2 * p] = -fmaf(xr[2 * p], ax, bx);
+    out[2 * p + 1] = -fmaf(xr[2 * p + 1], ay, by);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------

@@ -80,8 +80,8 @@ __device__ __forceinline__ Particle make_particle(float* smem, const ColLayout& 
 
 // ---- per-step operand staging (LINEAR kind) ----------------------------------------------------------------
 struct StageLayout {
-  uint32_t tgt_logc_bytes, tgt_param_bytes, tgt_bytes;  // target mixture (static): logc | mu | ivar | muiv
-  uint32_t ref_logc_bytes, ref_param_bytes, row_bytes;  // one step: table row | logc | mu | ivar | muiv
+  uint32_t tgt_logc_bytes, tgt_param_bytes, tgt_bytes;  // target mixture (static, M > 1): logc | siv | nmsiv
+  uint32_t ref_logc_bytes, ref_param_bytes, row_bytes;  // one step: table row | logc | siv | nmsiv (M > 1)
   uint32_t buf_bytes, off_tgt, off_buf, total;
 };
 
@@ -89,17 +89,17 @@ struct StageLayout {
 __host__ __device__ inline StageLayout stage_layout(const lrds_spec& s, int level) {
   StageLayout L{};
   const uint32_t dp = (uint32_t)s.mlp.d_pad;
-  if (level >= 2 && s.target.kind == LRDS_DISTR_GMM) {
+  if (level >= 2 && s.target.kind == LRDS_DISTR_GMM && s.target.gmm.M > 1) {
     L.tgt_logc_bytes = (uint32_t)((s.target.gmm.M + 3) / 4 * 4) * 4u;
     L.tgt_param_bytes = (uint32_t)s.target.gmm.M * dp * 4u;
-    L.tgt_bytes = L.tgt_logc_bytes + 3u * L.tgt_param_bytes;
+    L.tgt_bytes = L.tgt_logc_bytes + 2u * L.tgt_param_bytes;
   }
-  if (s.has_ref_ctrl) {
+  if (s.has_ref_ctrl && s.ref_t.M > 1) {  // single Gaussians are read from global memory
     L.ref_logc_bytes = (uint32_t)((s.ref_t.M + 3) / 4 * 4) * 4u;
     L.ref_param_bytes = (uint32_t)s.ref_t.M * dp * 4u;
   }
   L.row_bytes = LRDS_STEP_STRIDE * 4u;
-  L.buf_bytes = L.row_bytes + L.ref_logc_bytes + 3u * L.ref_param_bytes;
+  L.buf_bytes = L.row_bytes + L.ref_logc_bytes + 2u * L.ref_param_bytes;
   L.off_tgt = 16;  // two mbarriers in front
   L.off_buf = L.off_tgt + L.tgt_bytes;
   L.total = L.off_buf + 2u * L.buf_bytes;
@@ -110,27 +110,31 @@ __host__ __device__ inline StageLayout stage_layout(const lrds_spec& s, int leve
 __device__ __forceinline__ void stage_gmm(uint8_t* dst, const GmmView& g, uint32_t logc_bytes, uint32_t param_bytes,
                                           uint64_t* bar) {
   ptx::bulk_g2s(dst, g.logc.p, logc_bytes, bar);
-  ptx::bulk_g2s(dst + logc_bytes, g.mu.p, param_bytes, bar);
-  ptx::bulk_g2s(dst + logc_bytes + param_bytes, g.ivar.p, param_bytes, bar);
-  ptx::bulk_g2s(dst + logc_bytes + 2 * param_bytes, g.muiv.p, param_bytes, bar);
+  ptx::bulk_g2s(dst + logc_bytes, g.siv.p, param_bytes, bar);
+  ptx::bulk_g2s(dst + logc_bytes + param_bytes, g.nm.p, param_bytes, bar);
 }
 __device__ __forceinline__ void stage_step(uint8_t* dst, const lrds_spec& s, const StageLayout& L, int k, uint64_t* bar) {
   ptx::bulk_g2s(dst, s.steps + (int64_t)k * LRDS_STEP_STRIDE, L.row_bytes, bar);
-  if (s.has_ref_ctrl) stage_gmm(dst + L.row_bytes, gmm_at(s.ref_t, k), L.ref_logc_bytes, L.ref_param_bytes, bar);
+  if (L.ref_param_bytes) stage_gmm(dst + L.row_bytes, gmm_at(s.ref_t, k), L.ref_logc_bytes, L.ref_param_bytes, bar);
 }
-__device__ __forceinline__ GmmViewT<true> staged_view(const uint8_t* src, int M, uint32_t logc_bytes, uint32_t param_bytes) {
+// `g` = the same block in global memory (its single-Gaussian members stay valid in the staged view)
+__device__ __forceinline__ GmmViewT<true> staged_view(const uint8_t* src, const GmmView& g, uint32_t logc_bytes,
+                                                     uint32_t param_bytes) {
   GmmViewT<true> v;
   const uint32_t a = ptx::smem_u32(src);
-  v.M = M;
+  v.M = g.M;
   v.logc = PPtr<true>{a};
-  v.mu = PPtr<true>{a + logc_bytes};
-  v.ivar = PPtr<true>{a + logc_bytes + param_bytes};
-  v.muiv = PPtr<true>{a + logc_bytes + 2 * param_bytes};
+  v.siv = PPtr<true>{a + logc_bytes};
+  v.nm = PPtr<true>{a + logc_bytes + param_bytes};
+  v.glogc = g.glogc;
+  v.mu = g.mu;
+  v.ivar = g.ivar;
   return v;
 }
 
 // fp32 FFMA drift network: hidden activations in 64 shared-memory columns per particle
 struct SimtMlp {
+  static constexpr bool kPipe = true;  // 128-thread CTAs: registers to spare for operand prefetch
   const lrds_mlp& w;
   Col act;
   template <bool BIAS_SH>
@@ -141,22 +145,22 @@ struct SimtMlp {
 };
 
 // ---- target helpers ---------------------------------------------------------------------------------
-template <bool SH>
+template <bool PIPE, bool SH>
 __device__ __forceinline__ float target_pass1(const lrds_spec& s, const GmmViewT<SH>& tv, const Particle& P, bool want_logp) {
   const lrds_distr& t = s.target;
-  if (t.kind == LRDS_DISTR_GMM) return gmm_pass1(tv, s.mlp.d_pad, P.x, P.rt);
+  if (t.kind == LRDS_DISTR_GMM) return gmm_pass1<PIPE>(tv, s.d, s.mlp.d_pad, P.x, P.rt);
   if (t.kind == LRDS_DISTR_LOGREG) return logreg_pass1(t.logreg, s.d, P.x, P.g, want_logp);
   if (t.kind == LRDS_DISTR_PHI4) return want_logp ? phi4_logp(t.phi4, s.d, P.x) : 0.f;
   return 0.f;
 }
 
 // raw target score for dims [j0, j0+JC); xm / xp are x_{j0-1} / x_{j0+JC} of the SAME state as xr
-template <bool SH>
+template <bool PIPE, bool SH>
 __device__ __forceinline__ void target_score_chunk(const lrds_spec& s, const GmmViewT<SH>& tv, const Particle& P,
                                                    const float (&xr)[JC], float xm, float xp, int j0, float (&out)[JC]) {
   const lrds_distr& t = s.target;
   if (t.kind == LRDS_DISTR_GMM) {
-    gmm_score_chunk(tv, s.mlp.d_pad, xr, P.rt, j0, out);
+    gmm_score_chunk<PIPE>(tv, s.d, s.mlp.d_pad, xr, P.rt, j0, out);
   } else if (t.kind == LRDS_DISTR_LOGREG) {
     logreg_score_chunk(t.logreg, s.d, s.mlp.d_pad, xr, P.g, j0, out);
   } else if (t.kind == LRDS_DISTR_PHI4) {
@@ -250,6 +254,7 @@ __device__ __forceinline__ float langevin_drift(const lrds_spec& s, float ts, fl
 // One CTA barrier per step keeps the buffers safe.
 template <int KIND, int STAGE, class MLP>
 __device__ __forceinline__ void rollout_body(const RolloutArgs& a, float* smem, uint8_t* stage, MLP& mlp) {
+  constexpr bool PIPE = MLP::kPipe;
   const lrds_spec& s = a.s;
   const int NT = blockDim.x;
   const int tid = threadIdx.x;
@@ -289,7 +294,7 @@ __device__ __forceinline__ void rollout_body(const RolloutArgs& a, float* smem, 
         if (SL.tgt_bytes) stage_gmm(stage + SL.off_tgt, tv0, SL.tgt_logc_bytes, SL.tgt_param_bytes, sbar);
         stage_step(stage + SL.off_buf, s, SL, 0, sbar);
       }
-      if constexpr (TSH) tv = staged_view(stage + SL.off_tgt, tv0.M, SL.tgt_logc_bytes, SL.tgt_param_bytes);
+      if constexpr (TSH) tv = staged_view(stage + SL.off_tgt, tv0, SL.tgt_logc_bytes, SL.tgt_param_bytes);
     }
     for (int k = 0; k < K; ++k) {
       const float* row = s.steps + (int64_t)k * LRDS_STEP_STRIDE;
@@ -305,7 +310,7 @@ __device__ __forceinline__ void rollout_body(const RolloutArgs& a, float* smem, 
         const uint8_t* buf = stage + SL.off_buf + (k & 1) * SL.buf_bytes;
         row = reinterpret_cast<const float*>(buf);
         rowp = PPtr<true>{ptx::smem_u32(buf)};
-        if (s.has_ref_ctrl) rv = staged_view(buf + SL.row_bytes, s.ref_t.M, SL.ref_logc_bytes, SL.ref_param_bytes);
+        if (s.has_ref_ctrl) rv = staged_view(buf + SL.row_bytes, gmm_at(s.ref_t, k), SL.ref_logc_bytes, SL.ref_param_bytes);
       } else {
         rowp = PPtr<false>{row};
         if (s.has_ref_ctrl) rv = gmm_at(s.ref_t, k);
@@ -314,17 +319,17 @@ __device__ __forceinline__ void rollout_body(const RolloutArgs& a, float* smem, 
       const float dt = rowp.ld1(LRDS_STEP_DT), sqdt = rowp.ld1(LRDS_STEP_SQRT_DT);
       const float wcost = rowp.ld1(LRDS_STEP_W_COST), wito = rowp.ld1(LRDS_STEP_W_ITO);
       const float gamma = rowp.ld1(LRDS_STEP_GAMMA), sigu = rowp.ld1(LRDS_STEP_SIGU);
-      if (score_ctrl) target_pass1(s, tv, P, false);
-      if (s.has_ref_ctrl && rv.M > 1) gmm_pass1(rv, dp, P.x, P.rr);
+      if (score_ctrl) target_pass1<PIPE>(s, tv, P, false);
+      if (s.has_ref_ctrl && rv.M > 1) gmm_pass1<PIPE>(rv, d, dp, P.x, P.rr);
       mlp.template hidden<SH>(row + LRDS_STEP_BIAS1, P.x);
       float su2 = 0.f, sito = 0.f, xm = 0.f;
       for (int j0 = 0; j0 < dp; j0 += JC) {
         float xr[JC], ts[JC], u[JC], rs[JC], z[JC], xn[JC];
         load_chunk(P.x, j0, xr);
         const float xp = (need_nbr && j0 + JC < dp) ? P.x(j0 + JC) : 0.f;
-        if (score_ctrl) target_score_chunk(s, tv, P, xr, xm, xp, j0, ts);
+        if (score_ctrl) target_score_chunk<PIPE>(s, tv, P, xr, xm, xp, j0, ts);
         ctrl_chunk(cc, mlp, j0, ts, gamma, u);
-        if (s.has_ref_ctrl) gmm_score_chunk(rv, dp, xr, P.rr, j0, rs);
+        if (s.has_ref_ctrl) gmm_score_chunk<PIPE>(rv, d, dp, xr, P.rr, j0, rs);
         noise_chunk(a, k, b, j0, z);
 #pragma unroll
         for (int c = 0; c < JC; ++c) {
@@ -351,15 +356,15 @@ __device__ __forceinline__ void rollout_body(const RolloutArgs& a, float* smem, 
       else if (s.ito_form != LRDS_ITO_NONE) rnd += sito;
     }
     // terminal cost: rnd += reference_log_prob(x) - terminal_unnorm_log_prob(x)   (oc.py:290, 505, 645, 1389)
-    const float lref = gmm_pass1(gmm_at(s.ref_0, 0), dp, P.x, P.rr);
-    const float ltgt = clipf(target_pass1(s, tv, P, true), s.clip_target);
+    const float lref = gmm_pass1<PIPE>(gmm_at(s.ref_0, 0), d, dp, P.x, P.rr);
+    const float ltgt = clipf(target_pass1<PIPE>(s, tv, P, true), s.clip_target);
     rnd += lref - ltgt;
   }
 
   if constexpr (KIND == LRDS_ROLLOUT_EUBO_LINEAR) {
     {  // rnd = reference_log_prob(x) - terminal_unnorm_log_prob(x)   (oc.py:321, 536)
-      const float lref = gmm_pass1(gmm_at(s.ref_0, 0), dp, P.x, P.rr);
-      const float ltgt = clipf(target_pass1(s, tv0, P, true), s.clip_target);
+      const float lref = gmm_pass1<PIPE>(gmm_at(s.ref_0, 0), d, dp, P.x, P.rr);
+      const float ltgt = clipf(target_pass1<PIPE>(s, tv0, P, true), s.clip_target);
       rnd = lref - ltgt;
     }
     for (int k = 0; k < K; ++k) {  // rows are stored in loop order (reversed time)
@@ -377,18 +382,18 @@ __device__ __forceinline__ void rollout_body(const RolloutArgs& a, float* smem, 
           P.x(j0 + c) = (j0 + c < d) ? fmaf(stdf, z[c], P.x(j0 + c) * mean) : 0.f;
         }
       }
-      if (score_ctrl) target_pass1(s, tv0, P, false);
+      if (score_ctrl) target_pass1<PIPE>(s, tv0, P, false);
       const GmmView rv = gmm_at(s.ref_t, k);
-      if (rv.M > 1) gmm_pass1(rv, dp, P.x, P.rr);
+      if (rv.M > 1) gmm_pass1<PIPE>(rv, d, dp, P.x, P.rr);
       mlp.template hidden<false>(row + LRDS_STEP_BIAS1, P.x);
       float cost = 0.f, gx = 0.f, gz = 0.f, xm = 0.f;
       for (int j0 = 0; j0 < dp; j0 += JC) {
         float xr[JC], ts[JC], u[JC], rs[JC];
         load_chunk(P.x, j0, xr);
         const float xp = (need_nbr && j0 + JC < dp) ? P.x(j0 + JC) : 0.f;
-        if (score_ctrl) target_score_chunk(s, tv0, P, xr, xm, xp, j0, ts);
+        if (score_ctrl) target_score_chunk<PIPE>(s, tv0, P, xr, xm, xp, j0, ts);
         ctrl_chunk(cc, mlp, j0, ts, gamma, u);
-        gmm_score_chunk(rv, dp, xr, P.rr, j0, rs);
+        gmm_score_chunk<PIPE>(rv, d, dp, xr, P.rr, j0, rs);
 #pragma unroll
         for (int c = 0; c < JC; ++c) {
           const float g = (s.update_form == LRDS_UPDATE_EM) ? u[c] / sig : u[c];
@@ -412,14 +417,14 @@ __device__ __forceinline__ void rollout_body(const RolloutArgs& a, float* smem, 
     auto eval_point = [&](int rowi, bool first, float dtk, float frac_for_drift, float& c2, float& cdb) {
       const float* row = s.steps + (int64_t)rowi * LRDS_STEP_STRIDE;
       const float gamma = __ldg(row + LRDS_STEP_GAMMA);
-      target_pass1(s, tv0, P, false);
+      target_pass1<PIPE>(s, tv0, P, false);
       mlp.template hidden<false>(row + LRDS_STEP_BIAS1, P.x);
       float xm = 0.f;
       for (int j0 = 0; j0 < dp; j0 += JC) {
         float xr[JC], ts[JC], u[JC];
         load_chunk(P.x, j0, xr);
         const float xp = (need_nbr && j0 + JC < dp) ? P.x(j0 + JC) : 0.f;
-        target_score_chunk(s, tv0, P, xr, xm, xp, j0, ts);
+        target_score_chunk<PIPE>(s, tv0, P, xr, xm, xp, j0, ts);
         ctrl_chunk(cc, mlp, j0, ts, gamma, u);
 #pragma unroll
         for (int c = 0; c < JC; ++c) {
@@ -443,7 +448,7 @@ __device__ __forceinline__ void rollout_body(const RolloutArgs& a, float* smem, 
     };
     float c2 = 0.f, cdb = 0.f;
     if constexpr (!EUBO) {
-      rnd = gmm_pass1(prior, dp, P.x, P.rr);  // initial_log_prob(x), oc.py:698
+      rnd = gmm_pass1<PIPE>(prior, d, dp, P.x, P.rr);  // initial_log_prob(x), oc.py:698
       eval_point(0, true, 0.f, 0.f, c2, cdb);
       for (int k = 0; k < K; ++k) {
         const float* row = s.steps + (int64_t)k * LRDS_STEP_STRIDE;
@@ -475,9 +480,9 @@ __device__ __forceinline__ void rollout_body(const RolloutArgs& a, float* smem, 
         rnd += 0.5f * c2 * dt;
         rnd += cdb;
       }
-      rnd -= clipf(target_pass1(s, tv0, P, true), s.clip_target);  // oc.py:750
+      rnd -= clipf(target_pass1<PIPE>(s, tv0, P, true), s.clip_target);  // oc.py:750
     } else {
-      rnd = -clipf(target_pass1(s, tv0, P, true), s.clip_target);  // oc.py:782
+      rnd = -clipf(target_pass1<PIPE>(s, tv0, P, true), s.clip_target);  // oc.py:782
       eval_point(K, true, 0.f, 0.f, c2, cdb);
       for (int i = 0; i < K; ++i) {
         const int kt = K - i, ks = K - 1 - i;  // t = ts[kt], s = ts[ks]
@@ -508,7 +513,7 @@ __device__ __forceinline__ void rollout_body(const RolloutArgs& a, float* smem, 
         rnd -= 0.5f * c2 * dt;
         rnd -= cdb;
       }
-      rnd += gmm_pass1(prior, dp, P.x, P.rr);  // oc.py:825
+      rnd += gmm_pass1<PIPE>(prior, d, dp, P.x, P.rr);  // oc.py:825
     }
   }
 

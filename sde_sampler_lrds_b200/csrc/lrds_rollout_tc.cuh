@@ -97,6 +97,7 @@ __global__ void pack_tc_image_kernel(const lrds_mlp w, const TcLayout L, uint8_t
 // ---- the policy --------------------------------------------------------------------------------------------------
 template <int PREC>
 struct TcMlp {
+  static constexpr bool kPipe = tc_max_warps(PREC) <= 8;  // 255-register kernels prefetch their mixture operands
   TcLayout L;
   const uint8_t* img;  // weight image in shared memory
   uint32_t img_s;      // its shared-window address

@@ -20,11 +20,11 @@ DATA_DIR = Path(__file__).parents[2] / "data"
 
 
 def gmm_block(loc: torch.Tensor, var: torch.Tensor, weights: torch.Tensor | None, device):
-    """Packs a diagonal mixture into the (logc, mu, ivar, muiv) block of lrds_gmm (include/lrds_b200.h).
+    """Packs a diagonal mixture into the (logc, mu, ivar, siv, nmsiv) block of lrds_gmm (include/lrds_b200.h).
 
     loc/var may carry a leading step axis ([S][M][d]) for the time-marginal reference.  logc follows
     log_prob_gaussian (distr/gauss.py:67-73) + log of the normalised weights (gauss.py:100-104).  Rows are padded
-    to d_pad = 8 ceil(d/8) floats (mu = 0, 1/var = 0, mu/var = 0) and logc to a multiple of 4 entries, so that
+    to d_pad = 8 ceil(d/8) floats (all zero) and logc to a multiple of 4 entries, so that
     the kernels read everything as aligned float4."""
     loc = loc.detach().to("cpu", torch.float32)
     var = var.detach().to("cpu", torch.float32).expand_as(loc)
@@ -34,19 +34,21 @@ def gmm_block(loc: torch.Tensor, var: torch.Tensor, weights: torch.Tensor | None
         w = weights.detach().to("cpu", torch.float32)
         logc = logc + torch.log(w / w.sum())
     ivar = (1.0 / var.double()).float()
-    muiv = (loc.double() / var.double()).float()
+    siv64 = 1.0 / var.double().sqrt()
+    siv, nmsiv = siv64.float(), (-(loc.double() * siv64)).float()
     pad = (-d) % 8
     if pad:
-        loc, ivar, muiv = (torch.nn.functional.pad(t, (0, pad)) for t in (loc, ivar, muiv))
+        loc, ivar, siv, nmsiv = (torch.nn.functional.pad(t, (0, pad)) for t in (loc, ivar, siv, nmsiv))
     if (-M) % 4:
         logc = torch.nn.functional.pad(logc, (0, (-M) % 4))
-    return tuple(t.contiguous().to(device) for t in (logc, loc, ivar, muiv))
+    return tuple(t.contiguous().to(device) for t in (logc, loc, ivar, siv, nmsiv))
 
 
 def fill_gmm(g: N.Gmm, block, stepped: bool = False):
-    logc, mu, ivar, muiv = block
+    logc, mu, ivar, siv, nmsiv = block
     g.M = mu.shape[-2]
-    g.logc, g.mu, g.ivar, g.muiv = logc.data_ptr(), mu.data_ptr(), ivar.data_ptr(), muiv.data_ptr()
+    g.logc, g.mu, g.ivar = logc.data_ptr(), mu.data_ptr(), ivar.data_ptr()
+    g.siv, g.nmsiv = siv.data_ptr(), nmsiv.data_ptr()
     g.step_stride_logc = logc.shape[-1] if stepped else 0
     g.step_stride_param = g.M * mu.shape[-1] if stepped else 0
     return g
