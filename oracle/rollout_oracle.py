@@ -501,9 +501,11 @@ def simulate_cmcd(ts, x, noise, ctrl, drift, diff, terminal_unnorm_log_prob, ini
     return x, rnd, (torch.stack(xs) if return_traj else None)
 
 
-def eubo_em(ts, x, noise, ctrl, sde, reference_ctrl, terminal_unnorm_log_prob, reference_log_prob):
-    """EMReferenceSDELoss.compute_eubo, losses/oc.py:298-362 (use_rescaling=True).  ``x`` is not
-    mutated here (the reference mutates its input in place, lines 336-337)."""
+def eubo_em(ts, x, noise, ctrl, sde, reference_ctrl, terminal_unnorm_log_prob, reference_log_prob,
+            use_rescaling: bool = True):
+    """EMReferenceSDELoss.compute_eubo, losses/oc.py:298-362.  ``use_rescaling`` is True for the EM loss and False
+    for DDPMLikeReferenceSDELoss, which inherits this method (oc.py:571-582).  ``x`` is not mutated here (the
+    reference mutates its input in place, lines 336-337)."""
     rnd = reference_log_prob(x).view((-1, 1)) - terminal_unnorm_log_prob(x)
     T = ts[-1]
     times_s = ts[:-1].flip((0,))
@@ -517,7 +519,8 @@ def eubo_em(ts, x, noise, ctrl, sde, reference_ctrl, terminal_unnorm_log_prob, r
         ref = reference_ctrl(T - s, x)
         sde_diff = sde.diff(T - s)
         dt = t - s
-        g = g / sde_diff
+        if use_rescaling:  # oc.py:345-346
+            g = g / sde_diff
         running_cost = g * (ref + 0.5 * g)
         rnd = rnd - running_cost.sum(dim=-1, keepdim=True) * dt * sde_diff ** 2
         rnd = rnd + (g * x).sum(dim=-1, keepdim=True) * (1.0 / mean_factors[i] - 1.0 + sde.drift_coeff(T - s) * dt)
@@ -676,8 +679,9 @@ def rollout(problem: dict, x0: torch.Tensor, noise: torch.Tensor, *, eubo: bool 
             sde = make_sde(problem["sde"], dtype)
             ref_ctrl, ref_logp = make_reference(problem["ref"], sde)
             if eubo:
-                fn = eubo_em if method == "em" else eubo_ei
-                return fn(ts, x0, noise, ctrl, sde, ref_ctrl, target_logp, ref_logp)
+                if method == "ei":
+                    return eubo_ei(ts, x0, noise, ctrl, sde, ref_ctrl, target_logp, ref_logp)
+                return eubo_em(ts, x0, noise, ctrl, sde, ref_ctrl, target_logp, ref_logp, use_rescaling=(method == "em"))
             if method == "em":
                 return simulate_em(ts, x0, noise, ctrl, sde, ref_ctrl, target_logp, ref_logp, return_traj)
             return simulate_ei(ts, x0, noise, ctrl, sde, ref_ctrl, target_logp, ref_logp, return_traj,

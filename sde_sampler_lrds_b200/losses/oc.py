@@ -183,8 +183,6 @@ class EMReferenceSDELoss(BaseOCLoss):
         def build():
             if eubo and ref is None:
                 raise NotImplementedError("compute_eubo needs a reference control (the reference calls it unconditionally)")
-            if eubo and self._variant == "ddpm":
-                raise NotImplementedError("the reference has no DDPM-like compute_eubo of its own (it inherits the EM one)")
             sde = self.sde.host()
             tsc, pairs = pack._scalar_rows(ts)
             T = tsc[-1]
@@ -195,7 +193,9 @@ class EMReferenceSDELoss(BaseOCLoss):
             _terminal(spec, keep, device, terminal_unnorm_log_prob, info)
             spec.K = K
             spec.kind = N.ROLLOUT_EUBO_LINEAR if eubo else N.ROLLOUT_LINEAR
-            spec.update_form = N.UPDATE_EM if self._variant == "em" else N.UPDATE_AXPY
+            # DDPM-like compute_eubo is the EM formula without the 1/sigma rescaling of the control (oc.py:571-582, 343-346)
+            em_formulas = self._variant == "em" or (eubo and self._variant == "ddpm")
+            spec.update_form = N.UPDATE_EM if em_formulas else N.UPDATE_AXPY
             spec.ito_form = N.ITO_EM if self._variant == "em" else N.ITO_SCALED
             spec.has_ref_ctrl = int(ref is not None)
             table = torch.zeros(K, N.STEP_STRIDE)
@@ -212,9 +212,9 @@ class EMReferenceSDELoss(BaseOCLoss):
                     row = table[i]
                     dt = t - s
                     row[N.STEP_EU_A], row[N.STEP_EU_B] = mean[i], std[i]
-                    if self._variant == "em":  # oc.py:343-359
+                    if em_formulas:  # oc.py:343-359
                         sig = sde.diff(T - s)
-                        row[N.STEP_B] = sig
+                        row[N.STEP_B] = sig if self._variant == "em" else 1.0  # divisor of the control (use_rescaling)
                         row[N.STEP_W_COST] = dt * sig ** 2
                         row[N.STEP_EU_C] = 1.0 / mean[i] - 1.0 + sde.drift_coeff_t(T - s) * dt
                         row[N.STEP_W_ITO] = std[i] / mean[i]
@@ -280,9 +280,6 @@ class DDPMLikeReferenceSDELoss(EMReferenceSDELoss):
         kwargs.pop("use_rescaling", None)
         super().__init__(*args, reference_ctrl=reference_ctrl, use_rescaling=False, **kwargs)
 
-    def compute_eubo(self, *a, **k):
-        raise NotImplementedError("DDPM-like compute_eubo: the reference inherits the EM formula with use_rescaling=False; "
-                                  "not built")
 
 
 class ExponentialIntegratorSDELoss(BaseOCLoss):

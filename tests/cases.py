@@ -250,6 +250,7 @@ CASES = {
     "eubo_em_two_modes": lambda: _eubo(case_em_two_modes("score"), 201),
     "eubo_ei_many_modes": lambda: _eubo(case_ei_many_modes(K=100, B=100), 202),
     "eubo_cmcd_gmm": lambda: _eubo(case_cmcd_gmm(), 203),
+    "eubo_ddpm_snr": lambda: _eubo(case_ddpm_snr(), 204),
 }
 
 

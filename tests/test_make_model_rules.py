@@ -1,0 +1,58 @@
+"""CPU: make_model / make_target_details keep the reference's selectors, defaults and forbidden combinations
+(experiments/benchmark_utils.py:41-159; conf/solver/*.yaml - SURVEY.md Appendix A).  Nothing here touches a GPU."""
+import pytest
+
+from sde_sampler_lrds_b200 import benchmark_utils as BU
+from sde_sampler_lrds_b200.losses import oc as L
+from sde_sampler_lrds_b200.solver import oc as S
+
+TRAIN = {"train_steps": 16, "train_batch_size": 8, "eval_batch_size": 8}
+
+
+def mk(**kw):
+    args = dict(solver_type="vp-ref", ref_type="default", loss_type="lv", integrator_type="ei",
+                model_type="target_informed_zero_init", time_type="uniform", solver_details={"sigma": 1.0},
+                target_details=BU.make_target_details("two_modes"), training_details=TRAIN)
+    args.update(kw)
+    return BU.make_model(**args)
+
+
+@pytest.mark.parametrize("kw, msg", [
+    (dict(solver_type="pis_orig", model_type="base_zero_init", integrator_type="em"), "Only target_informed_zero_init"),
+    (dict(solver_type="pis_orig", integrator_type="em", time_type="snr"), "Only uniform time"),
+    (dict(solver_type="dds_orig", integrator_type="ei"), "Can't use EI or DDPM-like discretization"),
+    (dict(solver_type="pbm-ref", time_type="uniform"), "PBM schedule is unstable"),
+    (dict(integrator_type="ddpm_like", time_type="uniform"), "DDPM with uniform times"),
+    (dict(solver_type="pis_orig", integrator_type="em", ref_type="gmm"), "Only ref models"),
+    (dict(solver_type="cmcd", integrator_type="em", model_type="base_zero_init", force_base_zero_init=True,
+          ref_type="gmm"), "Can't use ref other than gaussian"),
+    (dict(force_vp20=True, force_vp_cosine=True), "at the same time"),
+    (dict(model_type="target_informed_lerp_tempering"), "lerp_tempering is not supported"),
+])
+def test_forbidden_combinations_raise_like_the_reference(kw, msg):
+    with pytest.raises(ValueError, match=msg):
+        mk(**kw)
+
+
+def test_target_details_defaults_including_the_reference_typo():
+    d = BU.make_target_details("two_modes")
+    assert d == {"name": "two_modes", "dim": 5, "ill_conditioned": "medium", "a": 1.0}
+    assert BU.make_target_details("many_modes", dim=50, n_modes=16)["n_modes"] == 16
+    assert BU.make_target_details("phi_four") == {"name": "phi_four", "dim": 100, "b": 0.0}
+    assert BU.make_target_details("sonar") == {"name": "sonar"}
+
+
+def test_default_config_resolves_the_yaml_defaults():
+    c = BU._resolve(BU.default_config("vp-ref", "target_informed_zero_init", "lv", BU.make_target_details("many_modes")))
+    assert c["solver"] is S.RDS and c["loss"]["_target_"] is L.EMReferenceSDELoss and c["loss"]["max_rnd"] == 1e8
+    assert c["sde"]["diff_coeff_sq_max"] == 10.0 and c["prior"]["scale"] == 1.0
+    assert c["train_timesteps"]["end"] == 1.0 and c["train_timesteps"]["steps"] == 100
+    c = BU._resolve(BU.default_config("dds_orig", "target_informed_zero_init", "lv", BU.make_target_details("phi_four")))
+    assert c["solver"] is S.DDS and c["sde"] is None and c["train_timesteps"]["dt"] == 0.05 and c["train_timesteps"]["end"] == 6.4
+    assert c["prior"]["scale"] == 1.0 and c["target"]["beta"] == 20.0 and c["target"]["dim"] == 100
+    c = BU._resolve(BU.default_config("cmcd", "base_zero_init", "lv", BU.make_target_details("two_modes")))
+    assert c["solver"] is S.CMCD and c["prior"]["scale"] == 5.0 and c["loss"]["max_rnd"] is None and c["sde"]["clip_score"] == 1e5
+    c = BU._resolve(BU.default_config("pbm-ref", "base_zero_init", "lv", BU.make_target_details("two_modes")))
+    assert c["train_timesteps"]["start"] == 1e-4 and c["train_timesteps"]["end"] == 5.0
+    with pytest.raises(NotImplementedError):
+        BU.default_config("dis_orig", "target_informed_zero_init", "lv", BU.make_target_details("two_modes"))

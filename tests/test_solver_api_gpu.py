@@ -1,0 +1,118 @@
+"""GPU: the reference-level entry points above the loss objects - make_model, Solver.compute_results,
+TrainableWrapper.evaluate / evaluate_eubo, EulerIntegrator - run through the fused kernels and agree with the
+oracle's estimators on the log-weights they produce."""
+import math
+
+import pytest
+import torch
+
+from oracle import rollout_oracle as O
+
+pytestmark = pytest.mark.gpu
+TRAIN = {"train_steps": 16, "train_batch_size": 64, "eval_batch_size": 1000}
+
+
+def _gmm_ref(d, M, seed=3):
+    g = torch.Generator().manual_seed(seed)
+    return {"weights_ref": torch.rand(M, generator=g) + 0.5, "means_ref": torch.randn(M, d, generator=g) * 2.0,
+            "variances_ref": torch.rand(M, d, generator=g) + 0.5}
+
+
+def _randomise_last_layers(model, gain=0.5):
+    """The reference zero-inits the control (scale 1e-6); give it O(1) outputs so that the test is not vacuous."""
+    g = torch.Generator().manual_seed(11)
+    with torch.no_grad():
+        for m in (model.generative_ctrl.base_model.out_layer, getattr(model.generative_ctrl, "score_model", None) and
+                  model.generative_ctrl.score_model.out_layer):
+            if m:
+                m.weight.copy_((torch.rand(m.weight.shape, generator=g) * 2 - 1) * gain / math.sqrt(m.weight.shape[1]))
+                m.bias.copy_((torch.rand(m.bias.shape, generator=g) * 2 - 1) * 0.1 + 0.2)
+
+
+@pytest.mark.parametrize("solver_type, kw", [
+    ("vp-ref", dict(ref_type="gmm", integrator_type="ei", time_type="snr")),
+    ("vp-ref", dict(ref_type="gaussian", integrator_type="ddpm_like", time_type="snr")),
+    ("vp-ref", dict(ref_type="default", integrator_type="em", time_type="uniform", model_type="base_zero_init")),
+    ("pbm-ref", dict(ref_type="default", integrator_type="ei", time_type="snr")),
+    ("pis_orig", dict(ref_type="default", integrator_type="em", time_type="uniform")),
+    ("dds_orig", dict(ref_type="default", integrator_type="em", time_type="uniform")),
+    ("cmcd", dict(ref_type="gaussian", integrator_type="em", time_type="uniform")),
+])
+def test_make_model_evaluate(solver_type, kw, device):
+    from sde_sampler_lrds_b200 import benchmark_utils as BU
+    from sde_sampler_lrds_b200.additions.hacking import TrainableWrapper
+    d, M = 6, 5
+    details = {"sigma": 1.0, **_gmm_ref(d, M), "mean_ref": torch.zeros(d), "var_ref": torch.full((d,), 2.0),
+               "mean": torch.zeros(d), "var": torch.full((d,), 4.0)}
+    args = dict(solver_type=solver_type, loss_type="lv", model_type="target_informed_zero_init",
+                solver_details=details, target_details=BU.make_target_details("many_modes", dim=d, n_modes=M),
+                training_details=TRAIN, n_steps=24, device=str(device))
+    args.update(kw)
+    model = BU.make_model(**args)
+    _randomise_last_layers(model)
+    res = TrainableWrapper(model, verbose=False).evaluate()
+    B = TRAIN["eval_batch_size"]
+    K1 = len(model.eval_ts)
+    assert res.samples.shape == (B, d) and res.weights.shape == (B, 1) and res.xs.shape == (K1, B, d)
+    assert torch.isfinite(res.samples).all() and abs(res.weights.sum().item() - 1.0) < 1e-4
+    for k in ("eval/elbo", "eval/lv_loss", "eval/sample_time"):
+        assert math.isfinite(res.metrics[k]), k
+    assert math.isfinite(res.log_norm_const_preds["log_norm_const_is"])
+    if model.eubo_available:
+        for k in ("eval/eubo", "eval/log_norm_const_is_f", "eval/effective_sample_size_f"):
+            assert math.isfinite(res.metrics[k]), k
+        assert 1.0 <= res.metrics["eval/effective_sample_size_f"] <= B + 1e-3
+    if solver_type == "dds_orig":
+        assert K1 == 129  # cosine grid, dt 0.05, end 6.4: n_steps is ignored (benchmark_utils.py:184)
+    # the estimators agree with the oracle's formulas on the very same log-weights
+    x, rnd, _ = model.loss.simulate(model.eval_ts, model.prior.sample((B,)), model.clipped_target_unnorm_log_prob,
+                                    *( [model.reference_distr.log_prob] if hasattr(model, "reference_distr") else []),
+                                    **({"initial_log_prob": model.prior.log_prob, "train": False} if solver_type == "cmcd" else {}),
+                                    seed=5)
+    got = type(model.loss).compute_results(rnd, compute_weights=True)
+    want = O.compute_results(rnd.cpu())
+    assert abs(got.metrics["eval/elbo"] - want["eval/elbo"]) < 1e-4 * max(1, abs(want["eval/elbo"]))
+    assert abs(got.log_norm_const_preds["log_norm_const_is"] - want["log_norm_const_is"]) < 1e-3
+    assert abs(got.metrics["eval/lv_loss"] - want["eval/lv_loss"]) < 1e-3 * max(1, want["eval/lv_loss"])
+
+
+def test_results_do_not_depend_on_how_particles_are_sharded(device):
+    """Counter-based noise keyed by the global particle index: integrating [0, B) in one launch equals integrating
+    [0, B/2) and [B/2, B) as two ranks would (particle_offset), bit for bit."""
+    from tests.cases import CASES, initial_state
+    from tests.product_builders import Built
+    case = CASES["ei_many_modes"]()
+    x0 = initial_state(case)
+    built = Built(case, device, "tf32x3")
+    xa, ra, _ = built.simulate(x0, None, seed=77, particle_offset=1000)
+    h = x0.shape[0] // 2
+    xb0, rb0, _ = built.simulate(x0[:h], None, seed=77, particle_offset=1000)
+    xb1, rb1, _ = built.simulate(x0[h:], None, seed=77, particle_offset=1000 + h)
+    assert torch.equal(xa, torch.cat([xb0, xb1])) and torch.equal(ra, torch.cat([rb0, rb1]))
+    xc, rc, _ = built.simulate(x0, None, seed=78, particle_offset=1000)
+    assert not torch.equal(ra, rc)
+
+
+def test_euler_integrator_matches_its_definition(device):
+    from sde_sampler_lrds_b200.eq.integrator import EulerIntegrator
+    from sde_sampler_lrds_b200.eq.sdes import VP
+    sde = VP(diff_coeff_sq_min=0.1, diff_coeff_sq_max=10.0, scale_diff_coeff=1.0, terminal_t=1.0).to(device)
+    ts = torch.linspace(0, 1, 17, device=device)
+    g = torch.Generator().manual_seed(2)
+    x0 = torch.randn(300, 7, generator=g).to(device)
+    incs = torch.randn(16, 300, 7, generator=g).to(device)
+    k = {"i": 0}
+
+    def bm(s, t):
+        k["i"] += 1
+        return incs[k["i"] - 1] * torch.sqrt(t - s)
+    xs = EulerIntegrator().integrate(sde=sde, ts=ts, x_init=x0, timesteps=ts, bm=bm)
+    assert xs.shape == (17, 300, 7) and torch.equal(xs[0], x0)
+    h = sde.host()
+    x = x0.double().cpu()
+    for i, (s, t) in enumerate(zip(ts[:-1].cpu(), ts[1:].cpu())):
+        x = x + (h.drift_coeff_t(s).double() * x) * (t - s).double() + h.diff(s).double() * (incs[i].double().cpu() * torch.sqrt(t - s).double())
+    assert (xs[-1].double().cpu() - x).abs().max() < 1e-4
+    # without an injected Brownian motion: finite, right scale
+    xs2 = EulerIntegrator().integrate(sde=sde, ts=ts, x_init=x0, timesteps=ts)
+    assert torch.isfinite(xs2).all() and 0.2 < xs2[-1].std().item() < 5.0
