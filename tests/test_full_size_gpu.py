@@ -1,0 +1,76 @@
+"""GPU: BASELINE.json's full-size shapes.  The oracle cannot run 10^5 particles in seconds, so full-size results are
+tied to it through size-independent properties of the path:
+
+  1. particles are independent and the production noise is keyed by the global particle index, hence the first n
+     particles of a full-size launch must equal, BIT FOR BIT, a launch of only those n particles;
+  2. production mode (in-kernel Philox) must equal, bit for bit, validation mode fed with the same generator's
+     normals (lrds_normals), which is the mode the oracle / golden parity tests cover;
+  3. that n-particle validation run is compared with the CPU oracle at the north-star tolerance.
+
+Shapes (configs[1..3] of BASELINE.json): ManyModes d=50 EI K=200 B=65536; PhiFour d=100 PIS (EM) and DDS K=256
+B=131072; logistic regression (sonar shape, synthetic data) CMCD K=100 B=262144."""
+import ctypes as C
+
+import pytest
+import torch
+
+from oracle import rollout_oracle as O
+from tests import cases as T
+
+pytestmark = pytest.mark.gpu
+N_CHECK = 96
+
+
+def _full_cases():
+    return {
+        "many_modes_ei": (lambda: T.case_ei_many_modes(K=200, B=65536), "tf32x3"),
+        "phi4_pis": (lambda: T.case_pis_phi4(K=256, B=131072), "tf32x3"),
+        "phi4_dds": (lambda: _dds256(), "bf16"),
+        "logreg_cmcd": (lambda: T.case_cmcd_logreg(166, 60, K=100, B=262144), "fp32"),
+    }
+
+
+def _dds256():
+    case = T.case_dds_phi4(True, B=131072)
+    ts = T.cosine_ts(end=6.4, dt=0.025)  # K = 256+ steps: the reference-expressible twin of "256 steps" 
+    case["problem"]["ts"] = ts
+    return case
+
+
+@pytest.mark.parametrize("name", list(_full_cases()))
+def test_full_size_rollout_is_tied_to_the_oracle(name, device):
+    from sde_sampler_lrds_b200 import _native as N
+    from tests.product_builders import Built
+    make, precision = _full_cases()[name]
+    case = make()
+    p = case["problem"]
+    B = case["B"]
+    d = p["target"]["loc"].shape[1] if p["target"]["kind"] == "gmm" else p["target"]["dim"]
+    K = len(p["ts"]) - 1
+    built = Built(case, device, precision)
+    g = torch.Generator().manual_seed(case["seed"])
+    if case["prior"][0] == "delta":
+        x0 = torch.zeros(B, d)
+    else:
+        x0 = torch.randn(B, d, generator=g) * float(case["prior"][2]) + float(case["prior"][1])
+    seed, off = 0xC0FFEE + case["seed"], 7 * B
+    x_full, rnd_full, _ = built.simulate(x0, None, seed=seed, particle_offset=off)
+    assert x_full.shape == (B, d) and rnd_full.shape == (B, 1)
+    assert torch.isfinite(x_full).all() and torch.isfinite(rnd_full).all()
+    # 1. shard independence, bit for bit (a slice in the middle of the batch, not tile aligned)
+    lo = B // 2 + 37
+    xs, rs, _ = built.simulate(x0[lo:lo + N_CHECK], None, seed=seed, particle_offset=off + lo)
+    assert torch.equal(xs, x_full[lo:lo + N_CHECK]) and torch.equal(rs, rnd_full[lo:lo + N_CHECK])
+    # 2. production mode == validation mode on the generator's own normals
+    noise = torch.empty(K, N_CHECK, d, device=device)
+    N.check(N.lib().lrds_normals(C.c_uint64(seed), C.c_uint64(off + lo), 0, K, N_CHECK, d, N.ptr(noise), N.stream_ptr(device)))
+    xv, rv, _ = built.simulate(x0[lo:lo + N_CHECK], noise)
+    assert torch.equal(xv, xs) and torch.equal(rv, rs)
+    # 3. the same increments through the CPU oracle
+    xo, ro, _ = O.rollout(p, x0[lo:lo + N_CHECK], noise.cpu(), compute_ito_int=case.get("compute_ito_int", True))
+    tol = 1e-2 if precision == "bf16" else 1e-4
+    need = 0.99 if (p["target"]["kind"] == "logreg" or precision == "bf16") else 1.0
+    ex = ((xv.cpu() - xo).abs() / xo.abs().clamp(min=1.0)).max(dim=1).values
+    er = ((rv.cpu() - ro).abs() / ro.abs().clamp(min=1.0)).reshape(-1)
+    assert (ex <= tol).float().mean().item() >= need, f"x_T: worst {ex.max().item():.2e}"
+    assert (er <= tol).float().mean().item() >= need, f"rnd: worst {er.max().item():.2e}"
