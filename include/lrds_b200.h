@@ -17,7 +17,7 @@
 extern "C" {
 #endif
 
-#define LRDS_ABI_VERSION 3
+#define LRDS_ABI_VERSION 4
 #define LRDS_CHANNELS 64 /* FourierMLP / TimeEmbed width, conf/model/base/fouriermlp.yaml:4 */
 
 typedef enum {
@@ -111,13 +111,15 @@ typedef struct {
 typedef struct {
   int32_t M;
   int32_t reserved;
-  const float* logc; /* [4 ceil(M/4)]  log w_m - d/2 log(2 pi) - 1/2 sum_j log var_mj (w normalised), 16-byte aligned */
+  const float* logc; /* [4 ceil(M/4)]  log w_m - d/2 log(2 pi) - 1/2 sum_j log var_mj (w normalised); padding = -inf; 16-byte aligned */
   const float* mu;   /* [M][d_pad]  rows padded with 0 to d_pad = 8 ceil(d / 8) floats, 16-byte aligned */
   const float* ivar; /* [M][d_pad]  1 / var, padded with 0 */
-  const float* siv;  /* [M][d_pad]  1 / sigma, padded with 0          } operands of the mixture kernels (M > 1): */
-  const float* nmsiv;/* [M][d_pad]  -mu / sigma, padded with 0        } (x - mu)/sigma = x * siv + nmsiv in one FMA */
+  const float* sn;   /* [ceil(M/4)][d_pad/4][4][8]  operands of the mixture kernels (M > 1): for mode block b, dim group c
+                      * and mode i = 4 b + i': {1/sigma_{i,4c..4c+3}, -mu/sigma_{i,4c..4c+3}}, zero for padded dims and modes, so
+                      * that (x - mu)/sigma = x * (1/sigma) + (-mu/sigma) is one FMA and every load has an immediate offset */
   int64_t step_stride_logc;  /* floats between consecutive steps of logc (4 ceil(M/4)) */
-  int64_t step_stride_param; /* floats between consecutive steps of mu / ivar / siv / nmsiv (M * d_pad) */
+  int64_t step_stride_param; /* floats between consecutive steps of mu / ivar (M * d_pad) */
+  int64_t step_stride_sn;    /* floats between consecutive steps of sn (8 ceil(M/4) * d_pad) */
 } lrds_gmm;
 
 typedef struct {

@@ -18,7 +18,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(CSRC, "liblrds_b200.so")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 CHANNELS = 64
 STEP_STRIDE = 80
 (STEP_A, STEP_B, STEP_C, STEP_DT, STEP_SQRT_DT, STEP_W_COST, STEP_W_ITO, STEP_GAMMA, STEP_FRAC, STEP_SIGU,
@@ -42,8 +42,8 @@ class Mlp(C.Structure):
 
 
 class Gmm(C.Structure):
-    _fields_ = [("M", C.c_int32), ("reserved", C.c_int32), ("logc", FP), ("mu", FP), ("ivar", FP), ("siv", FP), ("nmsiv", FP),
-                ("step_stride_logc", C.c_int64), ("step_stride_param", C.c_int64)]
+    _fields_ = [("M", C.c_int32), ("reserved", C.c_int32), ("logc", FP), ("mu", FP), ("ivar", FP), ("sn", FP),
+                ("step_stride_logc", C.c_int64), ("step_stride_param", C.c_int64), ("step_stride_sn", C.c_int64)]
 
 
 class Phi4(C.Structure):

@@ -42,7 +42,7 @@ int pick_threads(int floats_per_particle, int smem_cap) {
 }
 
 int validate_gmm(const lrds_gmm& g, const char* name) {
-  if (g.M < 1 || !g.logc || !g.mu || !g.ivar || !g.siv || !g.nmsiv) return fail(LRDS_ERR_INVALID, "%s: incomplete mixture block", name);
+  if (g.M < 1 || !g.logc || !g.mu || !g.ivar || !g.sn) return fail(LRDS_ERR_INVALID, "%s: incomplete mixture block", name);
   return LRDS_OK;
 }
 

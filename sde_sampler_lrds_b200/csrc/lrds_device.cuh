@@ -175,17 +175,17 @@ __device__ __forceinline__ float4 gld4(const float4* p) {  // plain pointers: sh
   else return __ldg(p);
 }
 
-// A mixture block.  Mixtures (M > 1) are evaluated from (logc, siv = 1/sigma, nm = -mu/sigma), possibly staged in
-// shared memory; single Gaussians (M == 1) from (glogc, mu, ivar) in global memory in the reference's operation order.
+// A mixture block.  Mixtures (M > 1) are evaluated from (logc, sn = interleaved 1/sigma and -mu/sigma, see
+// lrds_gmm), possibly staged in shared memory; single Gaussians (M == 1) from (glogc, mu, ivar) in global memory in
+// the reference's operation order.
 template <bool SH>
 struct GmmViewT {
   int M;
-  PPtr<SH> logc, siv, nm;
+  PPtr<SH> logc, sn;
   PPtr<false> glogc, mu, ivar;
 };
 using GmmView = GmmViewT<false>;
 
-// step_stride_param counts floats of the padded rows (M * d_pad per step)
 __device__ __forceinline__ GmmView gmm_at(const lrds_gmm& g, int step) {
   GmmView v;
   const int64_t o = (int64_t)step * g.step_stride_param;
@@ -193,8 +193,7 @@ __device__ __forceinline__ GmmView gmm_at(const lrds_gmm& g, int step) {
   v.logc = v.glogc = PPtr<false>{g.logc + (int64_t)step * g.step_stride_logc};
   v.mu = PPtr<false>{g.mu + o};
   v.ivar = PPtr<false>{g.ivar + o};
-  v.siv = PPtr<false>{g.siv + o};
-  v.nm = PPtr<false>{g.nmsiv + o};
+  v.sn = PPtr<false>{g.sn + (int64_t)step * g.step_stride_sn};
   return v;
 }
 
@@ -207,27 +206,18 @@ __device__ __forceinline__ void quad4(float& q, const float4& xv, const float4& 
   t = xv.w - mu.w; q = fmaf(t * t, iv.w, q);
 }
 
-// one mode, four dims:  w = x / sigma - mu / sigma (one FFMA2 per pair), q += w^2 (one FFMA2 per pair)
-template <bool SH>
-__device__ __forceinline__ void quad4p(u64& qa, u64& qb, const ulonglong2& xv, const PPtr<SH>& siv, const PPtr<SH>& nm, int o) {
-  const ulonglong2 s = siv.ld2(o), n = nm.ld2(o);
-  const u64 w0 = f2::fma(xv.x, s.x, n.x), w1 = f2::fma(xv.y, s.y, n.y);
-  qa = f2::fma(w0, w0, qa);
-  qb = f2::fma(w1, w1, qb);
-}
-
-// Operands of one pass-1 block: four dims of x and of four modes' (1/sigma, -mu/sigma).  The loops below keep two
-// of these in registers and load block c+1 while block c computes (ptxas does not pipeline loads across loop
-// iterations on its own, and with <= 2 warps per scheduler nothing else hides the operand latency).
+// Operands of one pass-1 block: four dims of x and of four modes' (1/sigma, -mu/sigma) = 8 consecutive 16-byte
+// vectors of `sn`.  PIPE keeps two of these in registers and loads block c+1 while block c computes (ptxas does not
+// pipeline loads across loop iterations on its own, and with <= 2 warps per scheduler nothing else hides the latency).
 template <bool SH>
 struct Pass1Ops {
   ulonglong2 xv, s[4], n[4];
-  __device__ __forceinline__ void load(const Col4& x, const PPtr<SH>& siv, const PPtr<SH>& nm, int c, int o, int rowq) {
+  __device__ __forceinline__ void load(const Col4& x, int c, const PPtr<SH>& p) {  // p = sn + (block * rowq + c) * 32
     xv = x.ldu(c);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      s[i] = siv.ld2(o + i * rowq);
-      n[i] = nm.ld2(o + i * rowq);
+      s[i] = p.ld2(2 * i);
+      n[i] = p.ld2(2 * i + 1);
     }
   }
   // w = x / sigma - mu / sigma (one FFMA2 per pair of dims), q += w^2 (one FFMA2 per pair)
@@ -243,72 +233,44 @@ struct Pass1Ops {
 
 // Pass 1: responsibilities r(m) = softmax_m(logc_m - q_m / 2), q_m = sum_j (x_j - mu_mj)^2 / var_mj.
 // Returns log sum_m exp(logit_m) (= the mixture log-density).  For M == 1, r is not touched.
-// r holds 4 * ceil(M / 4) entries; the tail beyond M is left at zero weight.
+// r holds 4 * ceil(M / 4) entries; padded modes carry logc = -inf, i.e. weight zero.
 // PIPE: software-pipelined operand loads (needs ~40 more registers; used by the kernels compiled for <= 256 threads)
 template <bool PIPE, bool SH>
 __device__ __forceinline__ float gmm_pass1(const GmmViewT<SH>& g, int d, int dp, const Col4& x, const Col4& r) {
   const int nq = (d + 3) >> 2;  // 16-byte groups that hold real dims
-  const int rowq = dp >> 2;     // row pitch in 16-byte groups
+  const int rowq = dp >> 2;     // groups per mode block in `sn`
   if (g.M == 1) {
     float q = 0.f;
     for (int c = 0; c < nq; ++c) quad4(q, x.ld4(c), g.mu.ld4(c), g.ivar.ld4(c));
     return g.glogc.ld1(0) - 0.5f * q;
   }
-  const PPtr<SH> siv = g.siv, nm = g.nm;
   float mx = -INFINITY;
   const int M4 = (g.M + 3) >> 2;
   for (int mb = 0; mb < M4; ++mb) {  // 4 modes at a time so that one x load feeds 4 quadratic forms
-    const int m = 4 * mb;
-    float4 l;
-    if (m + 4 <= g.M) {
-      u64 qa[4] = {0, 0, 0, 0}, qb[4] = {0, 0, 0, 0};  // (even, odd) dim partial sums per mode
-      const int o = m * rowq;
-      if constexpr (PIPE) {
-        Pass1Ops<SH> A, B;
-        A.load(x, siv, nm, 0, o, rowq);
-        int c = 0;
-        for (; c + 1 < nq; c += 2) {
-          B.load(x, siv, nm, c + 1, o + c + 1, rowq);
-          A.accumulate(qa, qb);
-          if (c + 2 < nq) A.load(x, siv, nm, c + 2, o + c + 2, rowq);
-          B.accumulate(qa, qb);
-        }
-        if (c < nq) A.accumulate(qa, qb);
-      } else {
-        u64 qa0 = 0, qb0 = 0, qa1 = 0, qb1 = 0, qa2 = 0, qb2 = 0, qa3 = 0, qb3 = 0;
-        int oc = o;
+    u64 qa[4] = {0, 0, 0, 0}, qb[4] = {0, 0, 0, 0};  // (even, odd) dim partial sums per mode
+    PPtr<SH> p = g.sn + mb * rowq * 32;
+    if constexpr (PIPE) {
+      Pass1Ops<SH> A, B;
+      A.load(x, 0, p);
+      int c = 0;
+      for (; c + 1 < nq; c += 2, p = p + 64) {
+        B.load(x, c + 1, p + 32);
+        A.accumulate(qa, qb);
+        if (c + 2 < nq) A.load(x, c + 2, p + 64);
+        B.accumulate(qa, qb);
+      }
+      if (c < nq) A.accumulate(qa, qb);
+    } else {
 #pragma unroll 2
-        for (int c = 0; c < nq; ++c, ++oc) {
-          const ulonglong2 xv = x.ldu(c);
-          quad4p(qa0, qb0, xv, siv, nm, oc);
-          quad4p(qa1, qb1, xv, siv, nm, oc + rowq);
-          quad4p(qa2, qb2, xv, siv, nm, oc + 2 * rowq);
-          quad4p(qa3, qb3, xv, siv, nm, oc + 3 * rowq);
-        }
-        qa[0] = qa0; qb[0] = qb0; qa[1] = qa1; qb[1] = qb1; qa[2] = qa2; qb[2] = qb2; qa[3] = qa3; qb[3] = qb3;
+      for (int c = 0; c < nq; ++c, p = p + 32) {
+        Pass1Ops<SH> A;
+        A.load(x, c, p);
+        A.accumulate(qa, qb);
       }
-      const float4 lc = g.logc.ld4(mb);
-      l = make_float4(lc.x - 0.5f * f2::hsum(qa[0], qb[0]), lc.y - 0.5f * f2::hsum(qa[1], qb[1]),
-                      lc.z - 0.5f * f2::hsum(qa[2], qb[2]), lc.w - 0.5f * f2::hsum(qa[3], qb[3]));
-    } else {  // ragged tail: absent modes get logit -inf
-      float lv[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        lv[i] = -INFINITY;
-        if (m + i < g.M) {
-          u64 qa = 0, qb = 0;
-          const int o = (m + i) * rowq;
-          for (int c = 0; c < nq; ++c) {
-            const ulonglong2 xv = x.ldu(c), sv = siv.ld2(o + c), nv = nm.ld2(o + c);
-            const u64 w0 = f2::fma(xv.x, sv.x, nv.x), w1 = f2::fma(xv.y, sv.y, nv.y);
-            qa = f2::fma(w0, w0, qa);
-            qb = f2::fma(w1, w1, qb);
-          }
-          lv[i] = g.logc.ld1(m + i) - 0.5f * f2::hsum(qa, qb);
-        }
-      }
-      l = make_float4(lv[0], lv[1], lv[2], lv[3]);
     }
+    const float4 lc = g.logc.ld4(mb);
+    const float4 l = make_float4(lc.x - 0.5f * f2::hsum(qa[0], qb[0]), lc.y - 0.5f * f2::hsum(qa[1], qb[1]),
+                                 lc.z - 0.5f * f2::hsum(qa[2], qb[2]), lc.w - 0.5f * f2::hsum(qa[3], qb[3]));
     r.st4(mb, l);
     mx = fmaxf(fmaxf(mx, fmaxf(l.x, l.y)), fmaxf(l.z, l.w));
   }
@@ -328,16 +290,16 @@ __device__ __forceinline__ float gmm_pass1(const GmmViewT<SH>& g, int d, int dp,
   return mx + __logf(s);
 }
 
-// Operands of one mode for an 8-dim chunk of pass 2
+// Operands of one mode for an 8-dim chunk of pass 2: mode i of the block at p = sn + (block * rowq + j0 / 4) * 32
 template <bool SH>
 struct Pass2Ops {
   ulonglong2 s0, n0, s1, n1;
-  __device__ __forceinline__ void load(const PPtr<SH>& siv, const PPtr<SH>& nm, int o, bool two) {
-    s0 = siv.ld2(o);
-    n0 = nm.ld2(o);
+  __device__ __forceinline__ void load(const PPtr<SH>& p, int i, bool two) {
+    s0 = p.ld2(2 * i);
+    n0 = p.ld2(2 * i + 1);
     if (two) {
-      s1 = siv.ld2(o + 1);
-      n1 = nm.ld2(o + 1);
+      s1 = p.ld2(8 + 2 * i);
+      n1 = p.ld2(9 + 2 * i);
     }
   }
   // c = r / sigma;  a += c / sigma;  b += c (-mu / sigma)
@@ -356,11 +318,10 @@ struct Pass2Ops {
 
 // Pass 2 for dims [j0, j0+JC):  score_j = -sum_m r_m (x_j - mu_mj) / var_mj.  With c_mj = r_m / sigma_mj:
 //   score_j = -( x_j sum_m c_mj / sigma_mj  +  sum_m c_mj (-mu_mj / sigma_mj) )
-// i.e. one FMUL2 + two FFMA2 per mode and pair of dims (zero for the padded dims).
+// i.e. one FMUL2 + two FFMA2 per mode and pair of dims (zero for the padded dims and modes).
 template <bool PIPE, bool SH>
 __device__ __forceinline__ void gmm_score_chunk(const GmmViewT<SH>& g, int d, int dp, const float (&xr)[JC], const Col4& r,
                                                 int j0, float (&out)[JC]) {
-  const int rowq = dp >> 2;
   if (g.M == 1) {  // -((x - mu) * ivar), the operation order of score_gauss (distr/gauss.py:124-126)
     const PPtr<false> mu = g.mu + j0, iv = g.ivar + j0;
     const float4 m0 = mu.ld4(0), m1 = mu.ld4(1), i0 = iv.ld4(0), i1 = iv.ld4(1);
@@ -370,63 +331,44 @@ __device__ __forceinline__ void gmm_score_chunk(const GmmViewT<SH>& g, int d, in
     out[6] = -((xr[6] - m1.z) * i1.z); out[7] = -((xr[7] - m1.w) * i1.w);
     return;
   }
-  const PPtr<SH> siv = g.siv + j0, nm = g.nm + j0;
-  const bool two = j0 + 4 < d;  // the second 16-byte group of the chunk holds real dims
+  const int blk = (dp >> 2) * 32;  // floats per mode block of `sn`
+  const bool two = j0 + 4 < d;     // the second 16-byte group of the chunk holds real dims
   u64 a[4] = {0, 0, 0, 0}, b[4] = {0, 0, 0, 0};
-  const int M4 = g.M >> 2;
-  int o = 0;
-  if (!PIPE) {
-    u64 a0 = 0, a1 = 0, a2 = 0, a3 = 0, b0 = 0, b1 = 0, b2 = 0, b3 = 0;
-    auto mode = [&](float rm, int oo) {
-      const u64 rm2 = f2::pack(rm, rm);
-      {
-        const ulonglong2 sv = siv.ld2(oo), nv = nm.ld2(oo);
-        const u64 c0 = f2::mul(rm2, sv.x), c1 = f2::mul(rm2, sv.y);
-        a0 = f2::fma(c0, sv.x, a0); b0 = f2::fma(c0, nv.x, b0);
-        a1 = f2::fma(c1, sv.y, a1); b1 = f2::fma(c1, nv.y, b1);
-      }
-      if (two) {
-        const ulonglong2 sv = siv.ld2(oo + 1), nv = nm.ld2(oo + 1);
-        const u64 c0 = f2::mul(rm2, sv.x), c1 = f2::mul(rm2, sv.y);
-        a2 = f2::fma(c0, sv.x, a2); b2 = f2::fma(c0, nv.x, b2);
-        a3 = f2::fma(c1, sv.y, a3); b3 = f2::fma(c1, nv.y, b3);
-      }
-    };
-    for (int mb = 0; mb < M4; ++mb, o += 4 * rowq) {
-      const float4 rm = r.ld4(mb);
-      mode(rm.x, o);
-      mode(rm.y, o + rowq);
-      mode(rm.z, o + 2 * rowq);
-      mode(rm.w, o + 3 * rowq);
-    }
-    a[0] = a0; a[1] = a1; a[2] = a2; a[3] = a3; b[0] = b0; b[1] = b1; b[2] = b2; b[3] = b3;
-  } else if (M4 > 0) {  // operands of mode m+1 are loaded while mode m accumulates
+  const int M4 = (g.M + 3) >> 2;
+  PPtr<SH> p = g.sn + (j0 >> 2) * 32;
+  if constexpr (PIPE) {  // operands of mode m+1 are loaded while mode m accumulates
     Pass2Ops<SH> A, B;
-    A.load(siv, nm, 0, two);
-    for (int mb = 0; mb < M4; ++mb, o += 4 * rowq) {
+    A.load(p, 0, two);
+    for (int mb = 0; mb < M4; ++mb, p = p + blk) {
       const float4 rm = r.ld4(mb);
-      B.load(siv, nm, o + rowq, two);
+      B.load(p, 1, two);
       A.accumulate(rm.x, two, a, b);
-      A.load(siv, nm, o + 2 * rowq, two);
+      A.load(p, 2, two);
       B.accumulate(rm.y, two, a, b);
-      B.load(siv, nm, o + 3 * rowq, two);
+      B.load(p, 3, two);
       A.accumulate(rm.z, two, a, b);
-      if (mb + 1 < M4) A.load(siv, nm, o + 4 * rowq, two);
+      if (mb + 1 < M4) A.load(p + blk, 0, two);
       B.accumulate(rm.w, two, a, b);
     }
-  }
-  for (int m = 4 * M4; m < g.M; ++m, o += rowq) {
-    Pass2Ops<SH> T;
-    T.load(siv, nm, o, two);
-    T.accumulate(r(m), two, a, b);
+  } else {
+    for (int mb = 0; mb < M4; ++mb, p = p + blk) {
+      const float4 rm = r.ld4(mb);
+      const float rms[4] = {rm.x, rm.y, rm.z, rm.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        Pass2Ops<SH> T;
+        T.load(p, i, two);
+        T.accumulate(rms[i], two, a, b);
+      }
+    }
   }
 #pragma unroll
-  for (int p = 0; p < 4; ++p) {
+  for (int q = 0; q < 4; ++q) {
     float ax, ay, bx, by;
-    f2::unpack(a[p], ax, ay);
-    f2::unpack(b[p], bx, by);
-    out[2 * p] = -fmaf(xr[2 * p], ax, bx);
-    out[2 * p + 1] = -fmaf(xr[2 * p + 1], ay, by);
+    f2::unpack(a[q], ax, ay);
+    f2::unpack(b[q], bx, by);
+    out[2 * q] = -fmaf(xr[2 * q], ax, bx);
+    out[2 * q + 1] = -fmaf(xr[2 * q + 1], ay, by);
   }
 }
 

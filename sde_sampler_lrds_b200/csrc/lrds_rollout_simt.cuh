@@ -80,8 +80,8 @@ __device__ __forceinline__ Particle make_particle(float* smem, const ColLayout& 
 
 // ---- per-step operand staging (LINEAR kind) ----------------------------------------------------------------
 struct StageLayout {
-  uint32_t tgt_logc_bytes, tgt_param_bytes, tgt_bytes;  // target mixture (static, M > 1): logc | siv | nmsiv
-  uint32_t ref_logc_bytes, ref_param_bytes, row_bytes;  // one step: table row | logc | siv | nmsiv (M > 1)
+  uint32_t tgt_logc_bytes, tgt_param_bytes, tgt_bytes;  // target mixture (static, M > 1): logc | sn
+  uint32_t ref_logc_bytes, ref_param_bytes, row_bytes;  // one step: table row | logc | sn (M > 1)
   uint32_t buf_bytes, off_tgt, off_buf, total;
 };
 
@@ -91,15 +91,15 @@ __host__ __device__ inline StageLayout stage_layout(const lrds_spec& s, int leve
   const uint32_t dp = (uint32_t)s.mlp.d_pad;
   if (level >= 2 && s.target.kind == LRDS_DISTR_GMM && s.target.gmm.M > 1) {
     L.tgt_logc_bytes = (uint32_t)((s.target.gmm.M + 3) / 4 * 4) * 4u;
-    L.tgt_param_bytes = (uint32_t)s.target.gmm.M * dp * 4u;
-    L.tgt_bytes = L.tgt_logc_bytes + 2u * L.tgt_param_bytes;
+    L.tgt_param_bytes = (uint32_t)((s.target.gmm.M + 3) / 4) * dp * 32u;  // sn: 8 floats per mode (padded to 4) and dim
+    L.tgt_bytes = L.tgt_logc_bytes + L.tgt_param_bytes;
   }
   if (s.has_ref_ctrl && s.ref_t.M > 1) {  // single Gaussians are read from global memory
     L.ref_logc_bytes = (uint32_t)((s.ref_t.M + 3) / 4 * 4) * 4u;
-    L.ref_param_bytes = (uint32_t)s.ref_t.M * dp * 4u;
+    L.ref_param_bytes = (uint32_t)((s.ref_t.M + 3) / 4) * dp * 32u;
   }
   L.row_bytes = LRDS_STEP_STRIDE * 4u;
-  L.buf_bytes = L.row_bytes + L.ref_logc_bytes + 2u * L.ref_param_bytes;
+  L.buf_bytes = L.row_bytes + L.ref_logc_bytes + L.ref_param_bytes;
   L.off_tgt = 16;  // two mbarriers in front
   L.off_buf = L.off_tgt + L.tgt_bytes;
   L.total = L.off_buf + 2u * L.buf_bytes;
@@ -110,8 +110,7 @@ __host__ __device__ inline StageLayout stage_layout(const lrds_spec& s, int leve
 __device__ __forceinline__ void stage_gmm(uint8_t* dst, const GmmView& g, uint32_t logc_bytes, uint32_t param_bytes,
                                           uint64_t* bar) {
   ptx::bulk_g2s(dst, g.logc.p, logc_bytes, bar);
-  ptx::bulk_g2s(dst + logc_bytes, g.siv.p, param_bytes, bar);
-  ptx::bulk_g2s(dst + logc_bytes + param_bytes, g.nm.p, param_bytes, bar);
+  ptx::bulk_g2s(dst + logc_bytes, g.sn.p, param_bytes, bar);
 }
 __device__ __forceinline__ void stage_step(uint8_t* dst, const lrds_spec& s, const StageLayout& L, int k, uint64_t* bar) {
   ptx::bulk_g2s(dst, s.steps + (int64_t)k * LRDS_STEP_STRIDE, L.row_bytes, bar);
@@ -124,8 +123,7 @@ __device__ __forceinline__ GmmViewT<true> staged_view(const uint8_t* src, const 
   const uint32_t a = ptx::smem_u32(src);
   v.M = g.M;
   v.logc = PPtr<true>{a};
-  v.siv = PPtr<true>{a + logc_bytes};
-  v.nm = PPtr<true>{a + logc_bytes + param_bytes};
+  v.sn = PPtr<true>{a + logc_bytes};
   v.glogc = g.glogc;
   v.mu = g.mu;
   v.ivar = g.ivar;

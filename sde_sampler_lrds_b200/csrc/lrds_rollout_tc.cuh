@@ -109,6 +109,12 @@ struct TcMlp {
   bool issuer;
   int dp;              // columns of x held by the body (d rounded up to 8, zero padded)
 
+  // tf32 operand bits of an activation.  The 3-pass split truncates (one LOP3): hi = top 19 bits, lo = v - hi is
+  // exact in fp32 and the tensor core drops its bits below tf32 itself (error 2^-21 of v); the one-pass mode rounds.
+  static __device__ __forceinline__ uint32_t split_hi(float v) {
+    if (PREC == LRDS_PRECISION_TF32X3) return __float_as_uint(v) & 0xFFFFE000u;
+    return __float_as_uint(ptx::to_tf32(v));
+  }
   __device__ __forceinline__ uint32_t a_col(int part) const { return (uint32_t)(part * L.a_cols); }
   __device__ __forceinline__ uint32_t d_col() const { return (uint32_t)(L.parts * L.a_cols); }
 
@@ -156,12 +162,12 @@ struct TcMlp {
     } else {
       uint32_t hi[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) hi[i] = __float_as_uint(ptx::to_tf32(v[i]));
+      for (int i = 0; i < 8; ++i) hi[i] = split_hi(v[i]);
       ptx::tmem_st8(tm_lane + a_col(0) + c0, hi);
       if (PREC == LRDS_PRECISION_TF32X3) {
         uint32_t lo[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) lo[i] = __float_as_uint(ptx::to_tf32(v[i] - __uint_as_float(hi[i])));
+        for (int i = 0; i < 8; ++i) lo[i] = __float_as_uint(v[i] - __uint_as_float(hi[i]));
         ptx::tmem_st8(tm_lane + a_col(1) + c0, lo);
       }
     }
@@ -222,11 +228,11 @@ struct TcMlp {
       } else {
         uint32_t hi[32];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) hi[i] = __float_as_uint(ptx::to_tf32(g[i]));
+        for (int i = 0; i < 32; ++i) hi[i] = split_hi(g[i]);
         ptx::tmem_st32(tm_lane + a_col(0) + c0, hi);
         if (PREC == LRDS_PRECISION_TF32X3) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) hi[i] = __float_as_uint(ptx::to_tf32(g[i] - __uint_as_float(hi[i])));
+          for (int i = 0; i < 32; ++i) hi[i] = __float_as_uint(g[i] - __uint_as_float(hi[i]));
           ptx::tmem_st32(tm_lane + a_col(1) + c0, hi);
         }
       }

@@ -20,12 +20,12 @@ DATA_DIR = Path(__file__).parents[2] / "data"
 
 
 def gmm_block(loc: torch.Tensor, var: torch.Tensor, weights: torch.Tensor | None, device):
-    """Packs a diagonal mixture into the (logc, mu, ivar, siv, nmsiv) block of lrds_gmm (include/lrds_b200.h).
+    """Packs a diagonal mixture into the (logc, mu, ivar, sn) block of lrds_gmm (include/lrds_b200.h).
 
     loc/var may carry a leading step axis ([S][M][d]) for the time-marginal reference.  logc follows
     log_prob_gaussian (distr/gauss.py:67-73) + log of the normalised weights (gauss.py:100-104).  Rows are padded
-    to d_pad = 8 ceil(d/8) floats (all zero) and logc to a multiple of 4 entries, so that
-    the kernels read everything as aligned float4."""
+    to d_pad = 8 ceil(d/8) floats and logc to a multiple of 4 entries (-inf), so that the kernels read everything
+    as aligned 16-byte vectors; ``sn`` interleaves 1/sigma and -mu/sigma per (mode block, dim group, mode)."""
     loc = loc.detach().to("cpu", torch.float32)
     var = var.detach().to("cpu", torch.float32).expand_as(loc)
     d, M = loc.shape[-1], loc.shape[-2]
@@ -36,21 +36,24 @@ def gmm_block(loc: torch.Tensor, var: torch.Tensor, weights: torch.Tensor | None
     ivar = (1.0 / var.double()).float()
     siv64 = 1.0 / var.double().sqrt()
     siv, nmsiv = siv64.float(), (-(loc.double() * siv64)).float()
-    pad = (-d) % 8
-    if pad:
-        loc, ivar, siv, nmsiv = (torch.nn.functional.pad(t, (0, pad)) for t in (loc, ivar, siv, nmsiv))
-    if (-M) % 4:
-        logc = torch.nn.functional.pad(logc, (0, (-M) % 4))
-    return tuple(t.contiguous().to(device) for t in (logc, loc, ivar, siv, nmsiv))
+    pad, mpad = (-d) % 8, (-M) % 4
+    F = torch.nn.functional
+    loc, ivar = F.pad(loc, (0, pad)), F.pad(ivar, (0, pad))
+    logc = F.pad(logc, (0, mpad), value=float("-inf"))
+    lead = loc.shape[:-2]
+    m4, nq = (M + mpad) // 4, (d + pad) // 4
+    sn = torch.stack([F.pad(t, (0, pad, 0, mpad)).reshape(*lead, m4, 4, nq, 4).transpose(-3, -2) for t in (siv, nmsiv)],
+                     dim=-2)  # [.., m4, nq, 4 modes, 2, 4 dims]
+    return tuple(t.contiguous().to(device) for t in (logc, loc, ivar, sn.reshape(*lead, m4 * nq * 32)))
 
 
 def fill_gmm(g: N.Gmm, block, stepped: bool = False):
-    logc, mu, ivar, siv, nmsiv = block
+    logc, mu, ivar, sn = block
     g.M = mu.shape[-2]
-    g.logc, g.mu, g.ivar = logc.data_ptr(), mu.data_ptr(), ivar.data_ptr()
-    g.siv, g.nmsiv = siv.data_ptr(), nmsiv.data_ptr()
+    g.logc, g.mu, g.ivar, g.sn = logc.data_ptr(), mu.data_ptr(), ivar.data_ptr(), sn.data_ptr()
     g.step_stride_logc = logc.shape[-1] if stepped else 0
     g.step_stride_param = g.M * mu.shape[-1] if stepped else 0
+    g.step_stride_sn = sn.shape[-1] if stepped else 0
     return g
 
 

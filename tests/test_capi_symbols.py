@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
 def test_struct_sizes_match_header():
     # field-by-field mirror of include/lrds_b200.h (natural alignment, no packing pragmas)
     assert C.sizeof(N.Mlp) == 16 + 6 * 8
-    assert C.sizeof(N.Gmm) == 8 + 5 * 8 + 16
+    assert C.sizeof(N.Gmm) == 8 + 4 * 8 + 24
     assert C.sizeof(N.Phi4) == 16
     assert C.sizeof(N.LogReg) == 16 + 24 + 24
     assert C.sizeof(N.Distr) == 8 + C.sizeof(N.Gmm) + C.sizeof(N.Phi4) + C.sizeof(N.LogReg)
