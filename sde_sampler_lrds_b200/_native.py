@@ -103,6 +103,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     res = subprocess.run(["nvcc", *LINK_FLAGS, "-o", LIB_PATH, *objs], capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("link failed:\n" + res.stdout + res.stderr)
+    for o in objs:  # only the .so travels with the repository snapshot
+        os.remove(o)
     if verbose:
         print(log)
     return LIB_PATH

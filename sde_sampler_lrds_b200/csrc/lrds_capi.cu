@@ -177,14 +177,14 @@ __global__ void __launch_bounds__(128) ctrl_forward_kernel(const lrds_spec s, in
   for (int j = 0; j < dp; ++j) P.x(j) = (j < d) ? __ldg(x + (int64_t)b * d + j) : 0.f;
   const float* row = s.steps + (int64_t)rowi * LRDS_STEP_STRIDE;
   const bool score_ctrl = s.ctrl_kind == LRDS_CTRL_SCORE;
-  if (score_ctrl) target_pass1<false>(s, tv0, P, false);
+  if (score_ctrl) target_pass1<false>(s, s.target.kind, tv0, P, false);
   mlp.template hidden<false>(row + LRDS_STEP_BIAS1, P.x);
   float xm = 0.f;
   for (int j0 = 0; j0 < dp; j0 += JC) {
     float xr[JC], ts[JC], u[JC];
     load_chunk(P.x, j0, xr);
     const float xp = (j0 + JC < dp) ? P.x(j0 + JC) : 0.f;
-    if (score_ctrl) target_score_chunk<false>(s, tv0, P, xr, xm, xp, j0, ts);
+    if (score_ctrl) target_score_chunk<false>(s, s.target.kind, tv0, P, xr, xm, xp, j0, ts);
     ctrl_chunk(ctrl_const(s), mlp, j0, ts, __ldg(row + LRDS_STEP_GAMMA), u);
     xm = xr[JC - 1];
     if (live)
@@ -207,7 +207,7 @@ __global__ void __launch_bounds__(128) distr_eval_kernel(const lrds_spec s, cons
   const GmmView tv0 = gmm_at(s.target.gmm, 0);
   const int d = s.d, dp = s.mlp.d_pad;
   for (int j = 0; j < dp; ++j) P.x(j) = (j < d) ? __ldg(x + (int64_t)b * d + j) : 0.f;
-  const float lp = target_pass1<false>(s, tv0, P, logp_out != nullptr);
+  const float lp = target_pass1<false>(s, s.target.kind, tv0, P, logp_out != nullptr);
   if (live && logp_out) logp_out[b] = lp;
   if (!score_out) return;
   float xm = 0.f;
@@ -215,7 +215,7 @@ __global__ void __launch_bounds__(128) distr_eval_kernel(const lrds_spec s, cons
     float xr[JC], ts[JC];
     load_chunk(P.x, j0, xr);
     const float xp = (j0 + JC < dp) ? P.x(j0 + JC) : 0.f;
-    target_score_chunk<false>(s, tv0, P, xr, xm, xp, j0, ts);
+    target_score_chunk<false>(s, s.target.kind, tv0, P, xr, xm, xp, j0, ts);
     xm = xr[JC - 1];
     if (live)
 #pragma unroll

@@ -235,11 +235,12 @@ struct Pass1Ops {
 // Returns log sum_m exp(logit_m) (= the mixture log-density).  For M == 1, r is not touched.
 // r holds 4 * ceil(M / 4) entries; padded modes carry logc = -inf, i.e. weight zero.
 // PIPE: software-pipelined operand loads (needs ~40 more registers; used by the kernels compiled for <= 256 threads)
-template <bool PIPE, bool SH>
+// MIX: the caller knows M > 1 (skips the single-Gaussian branch)
+template <bool PIPE, bool MIX = false, bool SH>
 __device__ __forceinline__ float gmm_pass1(const GmmViewT<SH>& g, int d, int dp, const Col4& x, const Col4& r) {
   const int nq = (d + 3) >> 2;  // 16-byte groups that hold real dims
   const int rowq = dp >> 2;     // groups per mode block in `sn`
-  if (g.M == 1) {
+  if (!MIX && g.M == 1) {
     float q = 0.f;
     for (int c = 0; c < nq; ++c) quad4(q, x.ld4(c), g.mu.ld4(c), g.ivar.ld4(c));
     return g.glogc.ld1(0) - 0.5f * q;
@@ -319,10 +320,10 @@ struct Pass2Ops {
 // Pass 2 for dims [j0, j0+JC):  score_j = -sum_m r_m (x_j - mu_mj) / var_mj.  With c_mj = r_m / sigma_mj:
 //   score_j = -( x_j sum_m c_mj / sigma_mj  +  sum_m c_mj (-mu_mj / sigma_mj) )
 // i.e. one FMUL2 + two FFMA2 per mode and pair of dims (zero for the padded dims and modes).
-template <bool PIPE, bool SH>
+template <bool PIPE, bool MIX = false, bool SH>
 __device__ __forceinline__ void gmm_score_chunk(const GmmViewT<SH>& g, int d, int dp, const float (&xr)[JC], const Col4& r,
                                                 int j0, float (&out)[JC]) {
-  if (g.M == 1) {  // -((x - mu) * ivar), the operation order of score_gauss (distr/gauss.py:124-126)
+  if (!MIX && g.M == 1) {  // -((x - mu) * ivar), the operation order of score_gauss (distr/gauss.py:124-126)
     const PPtr<false> mu = g.mu + j0, iv = g.ivar + j0;
     const float4 m0 = mu.ld4(0), m1 = mu.ld4(1), i0 = iv.ld4(0), i1 = iv.ld4(1);
     out[0] = -((xr[0] - m0.x) * i0.x); out[1] = -((xr[1] - m0.y) * i0.y);

@@ -130,6 +130,29 @@ __device__ __forceinline__ GmmViewT<true> staged_view(const uint8_t* src, const 
   return v;
 }
 
+// ---- compile-time specialisation of the LINEAR loop ----------------------------------------------------------
+// The loop is driven by warp-uniform switches of the spec (update / Ito form, control kind, target kind, reference).
+// Evaluated at run time they cost a branch sequence per 8-dim chunk each (~20% of the warp time in the ncu source
+// view); a Traits type fixes them at compile time for the configurations the solvers actually build (-1 = run time).
+template <int UPDATE = -1, int ITO = -1, int TARGET = -1, int SCORE = -1, int REF = -1, int MIX = 0>
+struct LinearTraits {
+  static constexpr bool kMix = MIX != 0;  // every mixture block on the path (target if GMM, reference) has M > 1
+  static constexpr int kUpdate = UPDATE;  // lrds_update_form
+  static constexpr int kIto = ITO;        // lrds_ito_form
+  static constexpr int kTarget = TARGET;  // lrds_distr_kind
+  static constexpr int kScore = SCORE;    // 1 = ScoreCtrl, 0 = ClippedCtrl
+  static constexpr int kRef = REF;        // 0 = no reference control, 1 = Gaussian (M == 1), 2 = mixture (M > 1)
+};
+using RuntimeTraits = LinearTraits<>;
+__host__ __device__ inline int ref_class(const lrds_spec& s) { return !s.has_ref_ctrl ? 0 : (s.ref_t.M > 1 ? 2 : 1); }
+template <class TR>
+__host__ __device__ inline bool traits_match(const lrds_spec& s) {
+  return (TR::kUpdate < 0 || TR::kUpdate == s.update_form) && (TR::kIto < 0 || TR::kIto == s.ito_form) &&
+         (TR::kTarget < 0 || TR::kTarget == s.target.kind) && (TR::kScore < 0 || TR::kScore == (s.ctrl_kind == LRDS_CTRL_SCORE)) &&
+         (TR::kRef < 0 || TR::kRef == ref_class(s)) &&
+         (!TR::kMix || ((s.target.kind != LRDS_DISTR_GMM || s.target.gmm.M > 1) && (!s.has_ref_ctrl || s.ref_t.M > 1)));
+}
+
 // fp32 FFMA drift network: hidden activations in 64 shared-memory columns per particle
 struct SimtMlp {
   static constexpr bool kPipe = true;  // 128-thread CTAs: registers to spare for operand prefetch
@@ -143,25 +166,26 @@ struct SimtMlp {
 };
 
 // ---- target helpers ---------------------------------------------------------------------------------
-template <bool PIPE, bool SH>
-__device__ __forceinline__ float target_pass1(const lrds_spec& s, const GmmViewT<SH>& tv, const Particle& P, bool want_logp) {
+template <bool PIPE, bool MIX = false, bool SH>
+__device__ __forceinline__ float target_pass1(const lrds_spec& s, int kind, const GmmViewT<SH>& tv, const Particle& P,
+                                              bool want_logp) {
   const lrds_distr& t = s.target;
-  if (t.kind == LRDS_DISTR_GMM) return gmm_pass1<PIPE>(tv, s.d, s.mlp.d_pad, P.x, P.rt);
-  if (t.kind == LRDS_DISTR_LOGREG) return logreg_pass1(t.logreg, s.d, P.x, P.g, want_logp);
-  if (t.kind == LRDS_DISTR_PHI4) return want_logp ? phi4_logp(t.phi4, s.d, P.x) : 0.f;
+  if (kind == LRDS_DISTR_GMM) return gmm_pass1<PIPE, MIX>(tv, s.d, s.mlp.d_pad, P.x, P.rt);
+  if (kind == LRDS_DISTR_LOGREG) return logreg_pass1(t.logreg, s.d, P.x, P.g, want_logp);
+  if (kind == LRDS_DISTR_PHI4) return want_logp ? phi4_logp(t.phi4, s.d, P.x) : 0.f;
   return 0.f;
 }
 
 // raw target score for dims [j0, j0+JC); xm / xp are x_{j0-1} / x_{j0+JC} of the SAME state as xr
-template <bool PIPE, bool SH>
-__device__ __forceinline__ void target_score_chunk(const lrds_spec& s, const GmmViewT<SH>& tv, const Particle& P,
+template <bool PIPE, bool MIX = false, bool SH>
+__device__ __forceinline__ void target_score_chunk(const lrds_spec& s, int kind, const GmmViewT<SH>& tv, const Particle& P,
                                                    const float (&xr)[JC], float xm, float xp, int j0, float (&out)[JC]) {
   const lrds_distr& t = s.target;
-  if (t.kind == LRDS_DISTR_GMM) {
-    gmm_score_chunk<PIPE>(tv, s.d, s.mlp.d_pad, xr, P.rt, j0, out);
-  } else if (t.kind == LRDS_DISTR_LOGREG) {
+  if (kind == LRDS_DISTR_GMM) {
+    gmm_score_chunk<PIPE, MIX>(tv, s.d, s.mlp.d_pad, xr, P.rt, j0, out);
+  } else if (kind == LRDS_DISTR_LOGREG) {
     logreg_score_chunk(t.logreg, s.d, s.mlp.d_pad, xr, P.g, j0, out);
-  } else if (t.kind == LRDS_DISTR_PHI4) {
+  } else if (kind == LRDS_DISTR_PHI4) {
     const float coef = t.phi4.a * (float)s.d;
 #pragma unroll
     for (int c = 0; c < JC; ++c) {
@@ -250,7 +274,7 @@ __device__ __forceinline__ float langevin_drift(const lrds_spec& s, float ts, fl
 // reference block + table row of step k+1 are prefetched by the TMA engine (cp.async.bulk + mbarrier, double
 // buffered) while step k computes, and with STAGE == 2 the target mixture is copied there once as well.
 // One CTA barrier per step keeps the buffers safe.
-template <int KIND, int STAGE, class MLP>
+template <int KIND, int STAGE, class TR = RuntimeTraits, class MLP>
 __device__ __forceinline__ void rollout_body(const RolloutArgs& a, float* smem, uint8_t* stage, MLP& mlp) {
   constexpr bool PIPE = MLP::kPipe;
   const lrds_spec& s = a.s;
@@ -267,9 +291,14 @@ __device__ __forceinline__ void rollout_body(const RolloutArgs& a, float* smem, 
   if (a.traj_out != nullptr && live)
     for (int j = 0; j < d; ++j) a.traj_out[(int64_t)b * d + j] = P.x(j);
 
-  const bool score_ctrl = s.ctrl_kind == LRDS_CTRL_SCORE;
-  const bool need_nbr = s.target.kind == LRDS_DISTR_PHI4;  // lattice stencil reads x_{j0-1}, x_{j0+8}
-  const CtrlConst cc = ctrl_const(s);
+  const int tkind = TR::kTarget >= 0 ? TR::kTarget : s.target.kind;
+  const bool score_ctrl = TR::kScore >= 0 ? TR::kScore != 0 : s.ctrl_kind == LRDS_CTRL_SCORE;
+  const bool has_ref = TR::kRef >= 0 ? TR::kRef != 0 : s.has_ref_ctrl != 0;
+  const int update_form = TR::kUpdate >= 0 ? TR::kUpdate : s.update_form;
+  const int ito_form = TR::kIto >= 0 ? TR::kIto : s.ito_form;
+  const bool need_nbr = tkind == LRDS_DISTR_PHI4;  // lattice stencil reads x_{j0-1}, x_{j0+8}
+  CtrlConst cc = ctrl_const(s);
+  cc.score = score_ctrl;
   const GmmView tv0 = gmm_at(s.target.gmm, 0);  // target mixture in global memory (dereferenced for GMM targets only)
   float rnd = 0.f;
 
@@ -308,41 +337,41 @@ __device__ __forceinline__ void rollout_body(const RolloutArgs& a, float* smem, 
         const uint8_t* buf = stage + SL.off_buf + (k & 1) * SL.buf_bytes;
         row = reinterpret_cast<const float*>(buf);
         rowp = PPtr<true>{ptx::smem_u32(buf)};
-        if (s.has_ref_ctrl) rv = staged_view(buf + SL.row_bytes, gmm_at(s.ref_t, k), SL.ref_logc_bytes, SL.ref_param_bytes);
+        if (has_ref) rv = staged_view(buf + SL.row_bytes, gmm_at(s.ref_t, k), SL.ref_logc_bytes, SL.ref_param_bytes);
       } else {
         rowp = PPtr<false>{row};
-        if (s.has_ref_ctrl) rv = gmm_at(s.ref_t, k);
+        if (has_ref) rv = gmm_at(s.ref_t, k);
       }
       const float A = rowp.ld1(LRDS_STEP_A), Bc = rowp.ld1(LRDS_STEP_B), Cc = rowp.ld1(LRDS_STEP_C);
       const float dt = rowp.ld1(LRDS_STEP_DT), sqdt = rowp.ld1(LRDS_STEP_SQRT_DT);
       const float wcost = rowp.ld1(LRDS_STEP_W_COST), wito = rowp.ld1(LRDS_STEP_W_ITO);
       const float gamma = rowp.ld1(LRDS_STEP_GAMMA), sigu = rowp.ld1(LRDS_STEP_SIGU);
-      if (score_ctrl) target_pass1<PIPE>(s, tv, P, false);
-      if (s.has_ref_ctrl && rv.M > 1) gmm_pass1<PIPE>(rv, d, dp, P.x, P.rr);
+      if (score_ctrl) target_pass1<PIPE, TR::kMix>(s, tkind, tv, P, false);
+      if (has_ref && (TR::kRef == 2 || rv.M > 1)) gmm_pass1<PIPE, TR::kMix>(rv, d, dp, P.x, P.rr);
       mlp.template hidden<SH>(row + LRDS_STEP_BIAS1, P.x);
       float su2 = 0.f, sito = 0.f, xm = 0.f;
       for (int j0 = 0; j0 < dp; j0 += JC) {
         float xr[JC], ts[JC], u[JC], rs[JC], z[JC], xn[JC];
         load_chunk(P.x, j0, xr);
         const float xp = (need_nbr && j0 + JC < dp) ? P.x(j0 + JC) : 0.f;
-        if (score_ctrl) target_score_chunk<PIPE>(s, tv, P, xr, xm, xp, j0, ts);
+        if (score_ctrl) target_score_chunk<PIPE, TR::kMix>(s, tkind, tv, P, xr, xm, xp, j0, ts);
         ctrl_chunk(cc, mlp, j0, ts, gamma, u);
-        if (s.has_ref_ctrl) gmm_score_chunk<PIPE>(rv, d, dp, xr, P.rr, j0, rs);
+        if (has_ref) gmm_score_chunk<PIPE, TR::kMix>(rv, d, dp, xr, P.rr, j0, rs);
         noise_chunk(a, k, b, j0, z);
 #pragma unroll
         for (int c = 0; c < JC; ++c) {
-          const float r = s.has_ref_ctrl ? rs[c] : 0.f;
+          const float r = has_ref ? rs[c] : 0.f;
           su2 = fmaf(u[c], u[c], su2);
-          if (s.update_form == LRDS_UPDATE_AXPY) {
+          if (update_form == LRDS_UPDATE_AXPY) {
             xn[c] = (A * xr[c] + Bc * (r + u[c])) + Cc * z[c];
           } else {  // EM: A = f(tau), Bc = sigma, Cc = sigma^2
             float drift = -(A * xr[c]);
-            if (s.has_ref_ctrl) drift += Cc * r;
+            if (has_ref) drift += Cc * r;
             xn[c] = xr[c] + (drift + Bc * u[c]) * dt + Bc * (z[c] * sqdt);
           }
-          if (s.ito_form == LRDS_ITO_SCALED) sito = fmaf(u[c], z[c], sito);
-          else if (s.ito_form == LRDS_ITO_EM) sito = fmaf(u[c], z[c] * sqdt, sito);
-          else if (s.ito_form == LRDS_ITO_DDS) sito += ((sigu * u[c]) * z[c]) * wito;
+          if (ito_form == LRDS_ITO_SCALED) sito = fmaf(u[c], z[c], sito);
+          else if (ito_form == LRDS_ITO_EM) sito = fmaf(u[c], z[c] * sqdt, sito);
+          else if (ito_form == LRDS_ITO_DDS) sito += ((sigu * u[c]) * z[c]) * wito;
           if (j0 + c >= d) xn[c] = 0.f;
         }
         xm = xr[JC - 1];
@@ -350,19 +379,19 @@ __device__ __forceinline__ void rollout_body(const RolloutArgs& a, float* smem, 
         if (a.traj_out != nullptr && live) store_traj(a, k + 1, b, j0, xn);
       }
       rnd += wcost * su2;
-      if (s.ito_form == LRDS_ITO_SCALED) rnd += wito * sito;
-      else if (s.ito_form != LRDS_ITO_NONE) rnd += sito;
+      if (ito_form == LRDS_ITO_SCALED) rnd += wito * sito;
+      else if (ito_form != LRDS_ITO_NONE) rnd += sito;
     }
     // terminal cost: rnd += reference_log_prob(x) - terminal_unnorm_log_prob(x)   (oc.py:290, 505, 645, 1389)
     const float lref = gmm_pass1<PIPE>(gmm_at(s.ref_0, 0), d, dp, P.x, P.rr);
-    const float ltgt = clipf(target_pass1<PIPE>(s, tv, P, true), s.clip_target);
+    const float ltgt = clipf(target_pass1<PIPE>(s, tkind, tv, P, true), s.clip_target);
     rnd += lref - ltgt;
   }
 
   if constexpr (KIND == LRDS_ROLLOUT_EUBO_LINEAR) {
     {  // rnd = reference_log_prob(x) - terminal_unnorm_log_prob(x)   (oc.py:321, 536)
       const float lref = gmm_pass1<PIPE>(gmm_at(s.ref_0, 0), d, dp, P.x, P.rr);
-      const float ltgt = clipf(target_pass1<PIPE>(s, tv0, P, true), s.clip_target);
+      const float ltgt = clipf(target_pass1<PIPE>(s, tkind, tv0, P, true), s.clip_target);
       rnd = lref - ltgt;
     }
     for (int k = 0; k < K; ++k) {  // rows are stored in loop order (reversed time)
@@ -380,7 +409,7 @@ __device__ __forceinline__ void rollout_body(const RolloutArgs& a, float* smem, 
           P.x(j0 + c) = (j0 + c < d) ? fmaf(stdf, z[c], P.x(j0 + c) * mean) : 0.f;
         }
       }
-      if (score_ctrl) target_pass1<PIPE>(s, tv0, P, false);
+      if (score_ctrl) target_pass1<PIPE>(s, tkind, tv0, P, false);
       const GmmView rv = gmm_at(s.ref_t, k);
       if (rv.M > 1) gmm_pass1<PIPE>(rv, d, dp, P.x, P.rr);
       mlp.template hidden<false>(row + LRDS_STEP_BIAS1, P.x);
@@ -389,7 +418,7 @@ __device__ __forceinline__ void rollout_body(const RolloutArgs& a, float* smem, 
         float xr[JC], ts[JC], u[JC], rs[JC];
         load_chunk(P.x, j0, xr);
         const float xp = (need_nbr && j0 + JC < dp) ? P.x(j0 + JC) : 0.f;
-        if (score_ctrl) target_score_chunk<PIPE>(s, tv0, P, xr, xm, xp, j0, ts);
+        if (score_ctrl) target_score_chunk<PIPE>(s, tkind, tv0, P, xr, xm, xp, j0, ts);
         ctrl_chunk(cc, mlp, j0, ts, gamma, u);
         gmm_score_chunk<PIPE>(rv, d, dp, xr, P.rr, j0, rs);
 #pragma unroll
@@ -415,14 +444,14 @@ __device__ __forceinline__ void rollout_body(const RolloutArgs& a, float* smem, 
     auto eval_point = [&](int rowi, bool first, float dtk, float frac_for_drift, float& c2, float& cdb) {
       const float* row = s.steps + (int64_t)rowi * LRDS_STEP_STRIDE;
       const float gamma = __ldg(row + LRDS_STEP_GAMMA);
-      target_pass1<PIPE>(s, tv0, P, false);
+      target_pass1<PIPE>(s, tkind, tv0, P, false);
       mlp.template hidden<false>(row + LRDS_STEP_BIAS1, P.x);
       float xm = 0.f;
       for (int j0 = 0; j0 < dp; j0 += JC) {
         float xr[JC], ts[JC], u[JC];
         load_chunk(P.x, j0, xr);
         const float xp = (need_nbr && j0 + JC < dp) ? P.x(j0 + JC) : 0.f;
-        target_score_chunk<PIPE>(s, tv0, P, xr, xm, xp, j0, ts);
+        target_score_chunk<PIPE>(s, tkind, tv0, P, xr, xm, xp, j0, ts);
         ctrl_chunk(cc, mlp, j0, ts, gamma, u);
 #pragma unroll
         for (int c = 0; c < JC; ++c) {
@@ -478,9 +507,9 @@ __device__ __forceinline__ void rollout_body(const RolloutArgs& a, float* smem, 
         rnd += 0.5f * c2 * dt;
         rnd += cdb;
       }
-      rnd -= clipf(target_pass1<PIPE>(s, tv0, P, true), s.clip_target);  // oc.py:750
+      rnd -= clipf(target_pass1<PIPE>(s, tkind, tv0, P, true), s.clip_target);  // oc.py:750
     } else {
-      rnd = -clipf(target_pass1<PIPE>(s, tv0, P, true), s.clip_target);  // oc.py:782
+      rnd = -clipf(target_pass1<PIPE>(s, tkind, tv0, P, true), s.clip_target);  // oc.py:782
       eval_point(K, true, 0.f, 0.f, c2, cdb);
       for (int i = 0; i < K; ++i) {
         const int kt = K - i, ks = K - 1 - i;  // t = ts[kt], s = ts[ks]
@@ -527,7 +556,7 @@ __global__ void __launch_bounds__(128) rollout_simt_kernel(const RolloutArgs a) 
   extern __shared__ float smem[];
   const ColLayout L = col_layout(a.s);
   SimtMlp mlp{a.s.mlp, Col{smem + L.act * blockDim.x + threadIdx.x, (int)blockDim.x}};
-  rollout_body<KIND, 0>(a, smem, nullptr, mlp);
+  rollout_body<KIND, 0, RuntimeTraits>(a, smem, nullptr, mlp);
 }
 
 }  // namespace lrds

@@ -57,7 +57,7 @@ __host__ __device__ inline TcLayout tc_layout(int d, int nh, int prec) {
 
 // ---- weight image ------------------------------------------------------------------------------------------------
 // B operand of layer (N x K, K-major, no swizzle): 16-byte K chunk kc of row n at  kc * N * 16 + n * 16.
-__global__ void pack_tc_image_kernel(const lrds_mlp w, const TcLayout L, uint8_t* __restrict__ img) {
+static __global__ void pack_tc_image_kernel(const lrds_mlp w, const TcLayout L, uint8_t* __restrict__ img) {
   const int E = 16 / L.es;
   const int n_in = C * L.Kin, n_hid = L.nh * C * C, n_out = L.Nout * C;
   const int total = n_in + n_hid + n_out;
@@ -277,7 +277,7 @@ __host__ __device__ inline uint32_t tc_stage_bytes(const lrds_spec& s, int level
 
 // ---- kernel --------------------------------------------------------------------------------------------------------
 // shared memory: [weight image | mbarriers + TMEM slot | operand stage (STAGED) | particle columns]
-template <int KIND, int PREC, int STAGE>
+template <int KIND, int PREC, int STAGE, class TR>
 __global__ void __launch_bounds__(tc_max_warps(PREC) * 32, 1)
 rollout_tc_kernel(const RolloutArgs a, const uint8_t* __restrict__ image, const uint32_t tmem_cols) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -316,7 +316,7 @@ rollout_tc_kernel(const RolloutArgs a, const uint8_t* __restrict__ image, const 
   mlp.bar_threads = tile_warps * 32;
   mlp.issuer = (tid & 127) == 0;
   mlp.dp = a.s.mlp.d_pad;
-  rollout_body<KIND, STAGE>(a, cols, stage, mlp);
+  rollout_body<KIND, STAGE, TR>(a, cols, stage, mlp);
   ptx::tc_fence_before();
   __syncthreads();
   if (warp == 0) ptx::tmem_dealloc(tmem, tmem_cols);

@@ -1,5 +1,4 @@
-// Tensor-core rollout: kernel instantiations, launch planning and the weight-image packer (its own translation
-// unit so that it compiles in parallel with lrds_capi.cu).
+// Tensor-core rollout: launch planning, dispatch to the per-precision translation units and the weight-image packer.
 #include <cuda_runtime.h>
 
 #include <cstdio>
@@ -9,40 +8,11 @@
 
 namespace lrds {
 
-namespace {
-
-template <int KIND, int PREC, int STAGE>
-int launch_one(const RolloutArgs& a, const TcPlan& p, cudaStream_t st, char* err, size_t n) {
-  auto kernel = rollout_tc_kernel<KIND, PREC, STAGE>;
-  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
-  if (e == cudaSuccess) {
-    kernel<<<p.grid, p.warps * 32, p.smem, st>>>(a, static_cast<const uint8_t*>(a.s.mlp.tc_image), p.tmem_cols);
-    e = cudaGetLastError();
-  }
-  if (e != cudaSuccess) {
-    snprintf(err, n, "tensor-core rollout launch (grid %d x %d threads, %zu B smem, %u TMEM cols): %s", p.grid,
-             p.warps * 32, p.smem, p.tmem_cols, cudaGetErrorString(e));
-    return LRDS_ERR_CUDA;
-  }
-  return LRDS_OK;
-}
-
 template <int PREC>
-int launch_kind(const RolloutArgs& a, const TcPlan& p, cudaStream_t st, char* err, size_t n) {
-  switch (a.s.kind) {
-    case LRDS_ROLLOUT_LINEAR:
-      return p.staged == 2   ? launch_one<LRDS_ROLLOUT_LINEAR, PREC, 2>(a, p, st, err, n)
-             : p.staged == 1 ? launch_one<LRDS_ROLLOUT_LINEAR, PREC, 1>(a, p, st, err, n)
-                             : launch_one<LRDS_ROLLOUT_LINEAR, PREC, 0>(a, p, st, err, n);
-    case LRDS_ROLLOUT_CMCD: return launch_one<LRDS_ROLLOUT_CMCD, PREC, 0>(a, p, st, err, n);
-    case LRDS_ROLLOUT_EUBO_LINEAR: return launch_one<LRDS_ROLLOUT_EUBO_LINEAR, PREC, 0>(a, p, st, err, n);
-    case LRDS_ROLLOUT_EUBO_CMCD: return launch_one<LRDS_ROLLOUT_EUBO_CMCD, PREC, 0>(a, p, st, err, n);
-  }
-  snprintf(err, n, "unknown rollout kind");
-  return LRDS_ERR_INVALID;
-}
-
-}  // namespace
+int launch_prec(const RolloutArgs& a, const TcPlan& p, cudaStream_t st, char* err, size_t n);  // lrds_tc_<precision>.cu
+extern template int launch_prec<LRDS_PRECISION_TF32X3>(const RolloutArgs&, const TcPlan&, cudaStream_t, char*, size_t);
+extern template int launch_prec<LRDS_PRECISION_BF16>(const RolloutArgs&, const TcPlan&, cudaStream_t, char*, size_t);
+extern template int launch_prec<LRDS_PRECISION_TF32>(const RolloutArgs&, const TcPlan&, cudaStream_t, char*, size_t);
 
 int launch_rollout_tc(const RolloutArgs& a, cudaStream_t st, char* err, size_t n) {
   const lrds_spec& s = a.s;
@@ -61,9 +31,9 @@ int launch_rollout_tc(const RolloutArgs& a, cudaStream_t st, char* err, size_t n
     return r;
   }
   switch (s.precision) {
-    case LRDS_PRECISION_TF32X3: return launch_kind<LRDS_PRECISION_TF32X3>(a, p, st, err, n);
-    case LRDS_PRECISION_BF16: return launch_kind<LRDS_PRECISION_BF16>(a, p, st, err, n);
-    case LRDS_PRECISION_TF32: return launch_kind<LRDS_PRECISION_TF32>(a, p, st, err, n);
+    case LRDS_PRECISION_TF32X3: return launch_prec<LRDS_PRECISION_TF32X3>(a, p, st, err, n);
+    case LRDS_PRECISION_BF16: return launch_prec<LRDS_PRECISION_BF16>(a, p, st, err, n);
+    case LRDS_PRECISION_TF32: return launch_prec<LRDS_PRECISION_TF32>(a, p, st, err, n);
   }
   snprintf(err, n, "unknown precision %d", s.precision);
   return LRDS_ERR_INVALID;
