@@ -44,6 +44,33 @@ __device__ __forceinline__ float clip_bound(float c) { return c > 0.f ? c : INFI
 __device__ __forceinline__ float clipb(float v, float bound) { return fminf(fmaxf(v, -bound), bound); }
 __device__ __forceinline__ float clipf(float v, float c) { return c > 0.f ? fminf(fmaxf(v, -c), c) : v; }
 
+// Packed fp32x2 arithmetic (FFMA2 / FMUL2 on sm_100): one issue slot for two lanes of work.
+typedef unsigned long long u64;
+namespace f2 {
+__device__ __forceinline__ u64 pack(float a, float b) {
+  u64 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void unpack(u64 v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ u64 fma(u64 a, u64 b, u64 c) {
+  u64 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ u64 mul(u64 a, u64 b) {
+  u64 d;
+  asm("mul.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ float hsum(u64 a, u64 b) {  // (a.x + a.y) + (b.x + b.y)
+  float x, y, z, w;
+  unpack(a, x, y);
+  unpack(b, z, w);
+  return (x + y) + (z + w);
+}
+}  // namespace f2
+
 // GELU with the exact (erf) definition, conf/model/base/fouriermlp.yaml:5-6:  v/2 (1 + erf(v / sqrt 2)).
 // erf(|x|) = 1 - 2^(|x| Q(|x|)) with a degree-6 minimax Q on [0, 4] (saturated beyond): absolute error of erf
 // 7.7e-8, of the GELU 1.6e-7 max(1, |v|) - the same as evaluating the erf formula in fp32 (tools/fit_erf.py).
@@ -62,6 +89,25 @@ __device__ __forceinline__ float gelu_exact(float v) {
   const float r = copysignf(1.0f - e, v);
   const float h = 0.5f * v;
   return fmaf(h, r, h);
+}
+
+// The same for two values at once on packed fp32x2 arithmetic (one issue slot per pair for the polynomial).
+__device__ __forceinline__ void gelu_exact2(float va, float vb, float& ga, float& gb) {
+  const u64 t = f2::pack(fminf(fabsf(va), 5.656854249f), fminf(fabsf(vb), 5.656854249f));
+  u64 q = f2::pack(8.857967404e-06f, 8.857967404e-06f);
+  q = f2::fma(q, t, f2::pack(-5.769414971e-05f, -5.769414971e-05f));
+  q = f2::fma(q, t, f2::pack(-4.069866499e-04f, -4.069866499e-04f));
+  q = f2::fma(q, t, f2::pack(7.363130652e-03f, 7.363130652e-03f));
+  q = f2::fma(q, t, f2::pack(-5.266660834e-02f, -5.266660834e-02f));
+  q = f2::fma(q, t, f2::pack(-4.591643231e-01f, -4.591643231e-01f));
+  q = f2::fma(q, t, f2::pack(-1.151108839e+00f, -1.151108839e+00f));
+  float pa, pb, ea, eb;
+  f2::unpack(f2::mul(q, t), pa, pb);
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ea) : "f"(pa));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(eb) : "f"(pb));
+  const u64 r = f2::pack(copysignf(1.0f - ea, va), copysignf(1.0f - eb, vb));
+  const u64 h = f2::mul(f2::pack(0.5f, 0.5f), f2::pack(va, vb));
+  f2::unpack(f2::fma(h, r, h), ga, gb);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -108,33 +154,6 @@ __device__ __forceinline__ void normals4(uint64_t seed, uint32_t pidx, uint32_t 
 // ---------------------------------------------------------------------------------------------------
 // diagonal Gaussian mixture
 // ---------------------------------------------------------------------------------------------------
-// Packed fp32x2 arithmetic (FFMA2 / FMUL2 on sm_100): one issue slot for two lanes of work.
-typedef unsigned long long u64;
-namespace f2 {
-__device__ __forceinline__ u64 pack(float a, float b) {
-  u64 r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
-  return r;
-}
-__device__ __forceinline__ void unpack(u64 v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
-__device__ __forceinline__ u64 fma(u64 a, u64 b, u64 c) {
-  u64 d;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-  return d;
-}
-__device__ __forceinline__ u64 mul(u64 a, u64 b) {
-  u64 d;
-  asm("mul.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-  return d;
-}
-__device__ __forceinline__ float hsum(u64 a, u64 b) {  // (a.x + a.y) + (b.x + b.y)
-  float x, y, z, w;
-  unpack(a, x, y);
-  unpack(b, z, w);
-  return (x + y) + (z + w);
-}
-}  // namespace f2
-
 // Warp-uniform operand pointer.  SH = the operand block sits in shared memory (staged per step by the TMA engine:
 // one wavefront per warp-uniform LDS.128, 32-bit address arithmetic) instead of global memory (read-only path:
 // four wavefronts per warp-uniform LDG.128).

@@ -215,10 +215,8 @@ struct TcMlp {
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const float4 b = GLOBAL_BIAS ? __ldg(b4 + i) : b4[i];
-        g[4 * i + 0] = gelu_exact(__uint_as_float(r[4 * i + 0]) + b.x);
-        g[4 * i + 1] = gelu_exact(__uint_as_float(r[4 * i + 1]) + b.y);
-        g[4 * i + 2] = gelu_exact(__uint_as_float(r[4 * i + 2]) + b.z);
-        g[4 * i + 3] = gelu_exact(__uint_as_float(r[4 * i + 3]) + b.w);
+        gelu_exact2(__uint_as_float(r[4 * i + 0]) + b.x, __uint_as_float(r[4 * i + 1]) + b.y, g[4 * i + 0], g[4 * i + 1]);
+        gelu_exact2(__uint_as_float(r[4 * i + 2]) + b.z, __uint_as_float(r[4 * i + 3]) + b.w, g[4 * i + 2], g[4 * i + 3]);
       }
       if (PREC == LRDS_PRECISION_BF16) {
         uint32_t p[16];
