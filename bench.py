@@ -222,7 +222,7 @@ def run_ours(args):
 
     # ---- reduced-precision fast mode, reported separately ------------------------------------------------------
     fast = None
-    if args.precision == "tf32x3" and not args.no_fast_mode:
+    if args.precision in ("tf32x3", "f16x3") and not args.no_fast_mode:
         built_fast = Built(case, dev, "bf16")
         for w in range(3):
             built_fast.simulate(x0, None, seed=4000 + w, particle_offset=offset)
@@ -309,7 +309,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default="tf32x3", choices=["fp32", "tf32x3", "tf32", "bf16"])
+    ap.add_argument("--precision", default="tf32x3", choices=["fp32", "tf32x3", "f16x3", "tf32", "bf16"])
     ap.add_argument("--no-fast-mode", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -17,7 +17,7 @@
 extern "C" {
 #endif
 
-#define LRDS_ABI_VERSION 4
+#define LRDS_ABI_VERSION 5
 #define LRDS_CHANNELS 64 /* FourierMLP / TimeEmbed width, conf/model/base/fouriermlp.yaml:4 */
 
 typedef enum {
@@ -66,7 +66,11 @@ typedef enum {
   LRDS_PRECISION_FP32_SIMT = 0, /* FFMA everywhere (parity anchor) */
   LRDS_PRECISION_TF32X3 = 1,    /* tcgen05 kind::tf32, 3-pass (hi, lo) split: fp32-grade drift MLP on tensor cores */
   LRDS_PRECISION_BF16 = 2,      /* tcgen05 kind::f16 single pass: reduced-precision fast mode, reported separately */
-  LRDS_PRECISION_TF32 = 3       /* tcgen05 kind::tf32 single pass: reduced-precision fast mode, reported separately */
+  LRDS_PRECISION_TF32 = 3,      /* tcgen05 kind::tf32 single pass: reduced-precision fast mode, reported separately */
+  LRDS_PRECISION_F16X3 = 4      /* tcgen05 kind::f16, 3-pass (hi, lo) fp16 split of power-of-two scaled operands: fp32-grade
+                                 * like TF32X3 (22 mantissa bits per operand) at half its shared-memory / TMEM footprint and
+                                 * twice its tensor rate; operands must stay below 65504 (particle coordinates) resp. 1023
+                                 * (hidden activations) in magnitude, beyond that they saturate */
 } lrds_precision;
 
 /* Per-step table: one row of `step_stride` floats per grid time (K rows; K+1 for the CMCD kinds, whose

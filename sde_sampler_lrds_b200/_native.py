@@ -18,7 +18,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(CSRC, "liblrds_b200.so")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 CHANNELS = 64
 STEP_STRIDE = 80
 (STEP_A, STEP_B, STEP_C, STEP_DT, STEP_SQRT_DT, STEP_W_COST, STEP_W_ITO, STEP_GAMMA, STEP_FRAC, STEP_SIGU,
@@ -30,8 +30,9 @@ UPDATE_AXPY, UPDATE_EM = range(2)
 ITO_NONE, ITO_SCALED, ITO_EM, ITO_DDS = range(4)
 CTRL_CLIPPED, CTRL_SCORE = range(2)
 DISTR_NONE, DISTR_GMM, DISTR_PHI4, DISTR_LOGREG = range(4)
-PRECISION_FP32_SIMT, PRECISION_TF32X3, PRECISION_BF16, PRECISION_TF32 = range(4)
-PRECISIONS = {"fp32": PRECISION_FP32_SIMT, "tf32x3": PRECISION_TF32X3, "bf16": PRECISION_BF16, "tf32": PRECISION_TF32}
+PRECISION_FP32_SIMT, PRECISION_TF32X3, PRECISION_BF16, PRECISION_TF32, PRECISION_F16X3 = range(5)
+PRECISIONS = {"fp32": PRECISION_FP32_SIMT, "tf32x3": PRECISION_TF32X3, "bf16": PRECISION_BF16, "tf32": PRECISION_TF32,
+              "f16x3": PRECISION_F16X3}
 
 FP = C.c_void_p  # device pointers travel as integers
 

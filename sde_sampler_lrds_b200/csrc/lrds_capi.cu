@@ -318,7 +318,7 @@ int lrds_rollout(const lrds_spec* spec, const float* x0, const float* noise, uin
 }
 
 int64_t lrds_tc_image_bytes(int32_t d, int32_t num_hidden, int32_t precision) {
-  if (d < 1 || num_hidden < 0 || precision == LRDS_PRECISION_FP32_SIMT || precision < 0 || precision > LRDS_PRECISION_TF32)
+  if (d < 1 || num_hidden < 0 || precision == LRDS_PRECISION_FP32_SIMT || precision < 0 || precision > LRDS_PRECISION_F16X3)
     return fail(LRDS_ERR_INVALID, "tc_image_bytes: bad arguments");
   return (int64_t)lrds::tc_image_bytes(d, num_hidden, precision);
 }
@@ -327,7 +327,8 @@ int lrds_pack_mlp_tc(const lrds_mlp* mlp, int32_t precision, void* image_out, vo
   if (!mlp || !image_out || !mlp->w_in_t || !mlp->w_out_t || !mlp->b_out || mlp->d < 1 ||
       mlp->d_pad != ((mlp->d + 7) / 8) * 8 || (mlp->num_hidden > 0 && (!mlp->w_hid_t || !mlp->b_hid)))
     return fail(LRDS_ERR_INVALID, "pack_mlp_tc: incomplete mlp block");
-  if (precision != LRDS_PRECISION_TF32X3 && precision != LRDS_PRECISION_BF16 && precision != LRDS_PRECISION_TF32)
+  if (precision != LRDS_PRECISION_TF32X3 && precision != LRDS_PRECISION_BF16 && precision != LRDS_PRECISION_TF32 &&
+      precision != LRDS_PRECISION_F16X3)
     return fail(LRDS_ERR_INVALID, "pack_mlp_tc: not a tensor-core precision");
   const int r = lrds::pack_tc_image(*mlp, precision, image_out, (cudaStream_t)stream, g_err, sizeof(g_err));
   if (r == LRDS_OK) g_launches.fetch_add(1);

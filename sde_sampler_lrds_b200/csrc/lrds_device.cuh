@@ -92,7 +92,8 @@ __device__ __forceinline__ float gelu_exact(float v) {
 }
 
 // The same for two values at once on packed fp32x2 arithmetic (one issue slot per pair for the polynomial).
-__device__ __forceinline__ void gelu_exact2(float va, float vb, float& ga, float& gb) {
+// `half_scale` = 0.5 * s returns s * GELU (s a power of two: the fp16 tensor-core operands are pre-scaled).
+__device__ __forceinline__ void gelu_exact2(float va, float vb, float& ga, float& gb, float half_scale = 0.5f) {
   const u64 t = f2::pack(fminf(fabsf(va), 5.656854249f), fminf(fabsf(vb), 5.656854249f));
   u64 q = f2::pack(8.857967404e-06f, 8.857967404e-06f);
   q = f2::fma(q, t, f2::pack(-5.769414971e-05f, -5.769414971e-05f));
@@ -106,7 +107,7 @@ __device__ __forceinline__ void gelu_exact2(float va, float vb, float& ga, float
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ea) : "f"(pa));
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(eb) : "f"(pb));
   const u64 r = f2::pack(copysignf(1.0f - ea, va), copysignf(1.0f - eb, vb));
-  const u64 h = f2::mul(f2::pack(0.5f, 0.5f), f2::pack(va, vb));
+  const u64 h = f2::mul(f2::pack(half_scale, half_scale), f2::pack(va, vb));
   f2::unpack(f2::fma(h, r, h), ga, gb);
 }
 

@@ -12,33 +12,45 @@
 // other tiles' SIMT work (scores, noise, integrator).
 //
 // Precisions: TF32X3 splits both operands into tf32 (hi, lo) and accumulates lo*hi + hi*lo + hi*hi (fp32-grade
-// products, the parity mode); TF32 and BF16 are single-pass reduced-precision modes reported separately.
+// products, the parity mode); F16X3 does the same with fp16 (hi, lo) pairs of power-of-two scaled operands (weights
+// scaled per layer so that max |W| lands in [2^14, 2^15), hidden activations by 64; the accumulator is scaled back by
+// the bias FFMA of the epilogue): the same 22 mantissa bits per operand at half the shared-memory image, half the
+// TMEM columns (=> twice the resident tiles) and twice the tensor rate.  TF32 and BF16 are single-pass
+// reduced-precision modes reported separately.
 #pragma once
+#include <cuda_fp16.h>
+
 #include "lrds_rollout_simt.cuh"
 #include "lrds_tc_ptx.cuh"
 
 namespace lrds {
 
 constexpr int TC_MAX_WARPS = 16;
-// The 3-pass split needs 192 TMEM columns per tile, i.e. at most two tiles = 8 warps per CTA: compile it for 256
-// threads so that ptxas may use 255 registers and keep more operand loads in flight per warp.
-__host__ __device__ constexpr int tc_max_warps(int prec) { return prec == LRDS_PRECISION_TF32X3 ? 8 : TC_MAX_WARPS; }
+// The tf32 3-pass split needs 192 TMEM columns per tile, i.e. at most two tiles = 8 warps per CTA: compile it for 256
+// threads so that ptxas may use 255 registers and keep more operand loads in flight per warp.  The fp16 split needs
+// 128 columns per tile; its kernels are compiled for three tiles = 12 warps (168 registers).
+__host__ __device__ constexpr int tc_max_warps(int prec) {
+  return prec == LRDS_PRECISION_TF32X3 ? 8 : prec == LRDS_PRECISION_F16X3 ? 12 : TC_MAX_WARPS;
+}
 constexpr int TC_TAIL_BYTES = 64;  // mbarriers + TMEM slot after the image
+constexpr float TC_ACT_SCALE = 64.f;  // F16X3: hidden activations enter the tensor core as 64 * GELU(h)
+__host__ __device__ constexpr bool tc_is_x3(int prec) { return prec == LRDS_PRECISION_TF32X3 || prec == LRDS_PRECISION_F16X3; }
+__host__ __device__ constexpr bool tc_is_half(int prec) { return prec == LRDS_PRECISION_BF16 || prec == LRDS_PRECISION_F16X3; }
 
 struct TcLayout {
   int prec, parts, es, kstep;
   int Kin, Nout, nh;
   uint32_t part_bytes, off_in, off_hid, off_out;  // one part = all layers of one (hi | lo) image
-  uint32_t off_bhid, off_bout, bytes;             // fp32 biases behind the parts; total bytes (multiple of 16)
+  uint32_t off_bhid, off_bout, off_scale, bytes;  // fp32 biases + 16 scale floats behind the parts; total bytes (multiple of 16)
   int a_cols, d_cols, tile_cols;                  // TMEM columns: one A part, the accumulator, one tile
 };
 
 __host__ __device__ inline TcLayout tc_layout(int d, int nh, int prec) {
   TcLayout L{};
   L.prec = prec;
-  L.parts = prec == LRDS_PRECISION_TF32X3 ? 2 : 1;
-  L.es = prec == LRDS_PRECISION_BF16 ? 2 : 4;
-  L.kstep = prec == LRDS_PRECISION_BF16 ? 16 : 8;
+  L.parts = tc_is_x3(prec) ? 2 : 1;
+  L.es = tc_is_half(prec) ? 2 : 4;
+  L.kstep = tc_is_half(prec) ? 16 : 8;
   L.Kin = (d + L.kstep - 1) / L.kstep * L.kstep;
   L.Nout = (d + 15) / 16 * 16;
   L.nh = nh;
@@ -48,7 +60,8 @@ __host__ __device__ inline TcLayout tc_layout(int d, int nh, int prec) {
   L.part_bytes = L.off_out + (uint32_t)(L.Nout * C * L.es);
   L.off_bhid = L.parts * L.part_bytes;
   L.off_bout = L.off_bhid + (uint32_t)((nh > 0 ? nh : 1) * C * 4);
-  L.bytes = L.off_bout + (uint32_t)(L.Nout * 4);
+  L.off_scale = L.off_bout + (uint32_t)(L.Nout * 4);  // [0..8) weight multipliers, [8..16) accumulator un-scales per layer
+  L.bytes = L.off_scale + 64u;
   L.a_cols = (L.Kin > C ? L.Kin : C) * L.es / 4;
   L.d_cols = L.Nout > C ? L.Nout : C;
   L.tile_cols = L.parts * L.a_cols + L.d_cols;
@@ -56,30 +69,61 @@ __host__ __device__ inline TcLayout tc_layout(int d, int nh, int prec) {
 }
 
 // ---- weight image ------------------------------------------------------------------------------------------------
+// F16X3 scales (one block): layer l = 0 (input), 1..nh (hidden), nh+1 (output): multiplier 2^k with max |W| 2^k in
+// [2^14, 2^15) and the accumulator un-scale 2^-k (/ TC_ACT_SCALE for the layers fed by hidden activations).
+static __global__ void tc_scales_kernel(const lrds_mlp w, const TcLayout L, uint8_t* __restrict__ img) {
+  __shared__ float red[32];
+  float* sc = reinterpret_cast<float*>(img + L.off_scale);
+  for (int l = 0; l < L.nh + 2; ++l) {
+    const float* p = l == 0 ? w.w_in_t : (l <= L.nh ? w.w_hid_t + (int64_t)(l - 1) * C * C : w.w_out_t);
+    const int n = l == 0 ? w.d * C : (l <= L.nh ? C * C : C * w.d_pad);
+    float m = 0.f;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) m = fmaxf(m, fabsf(p[i]));
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int i = 1; i < (int)(blockDim.x >> 5); ++i) m = fmaxf(m, red[i]);
+      int k = 0;
+      if (m > 0.f && m < INFINITY) k = 14 - ilogbf(m);
+      k = k > 100 ? 100 : (k < -100 ? -100 : k);
+      sc[l] = ldexpf(1.0f, k);
+      sc[8 + l] = ldexpf(1.0f, -k) / (l == 0 ? 1.0f : TC_ACT_SCALE);
+    }
+  }
+}
+
 // B operand of layer (N x K, K-major, no swizzle): 16-byte K chunk kc of row n at  kc * N * 16 + n * 16.
 static __global__ void pack_tc_image_kernel(const lrds_mlp w, const TcLayout L, uint8_t* __restrict__ img) {
   const int E = 16 / L.es;
   const int n_in = C * L.Kin, n_hid = L.nh * C * C, n_out = L.Nout * C;
   const int total = n_in + n_hid + n_out;
+  const float* sc = reinterpret_cast<const float*>(img + L.off_scale);  // written by tc_scales_kernel (F16X3)
   for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
     float v;
     uint32_t off;
-    int n, k, N;
+    int n, k, N, layer;
     if (idx < n_in) {
-      n = idx / L.Kin; k = idx % L.Kin; N = C; off = L.off_in;
+      n = idx / L.Kin; k = idx % L.Kin; N = C; off = L.off_in; layer = 0;
       v = k < w.d ? w.w_in_t[(int64_t)k * C + n] : 0.f;
     } else if (idx < n_in + n_hid) {
       const int r = idx - n_in, l = r / (C * C);
-      n = (r / C) % C; k = r % C; N = C; off = L.off_hid + (uint32_t)(l * C * C * L.es);
+      n = (r / C) % C; k = r % C; N = C; off = L.off_hid + (uint32_t)(l * C * C * L.es); layer = 1 + l;
       v = w.w_hid_t[(int64_t)l * C * C + (int64_t)k * C + n];
     } else {
       const int r = idx - n_in - n_hid;
-      n = r / C; k = r % C; N = L.Nout; off = L.off_out;
+      n = r / C; k = r % C; N = L.Nout; off = L.off_out; layer = L.nh + 1;
       v = n < w.d_pad ? w.w_out_t[(int64_t)k * w.d_pad + n] : 0.f;
     }
     const uint32_t byte = off + (uint32_t)(k / E) * N * 16u + (uint32_t)n * 16u + (uint32_t)(k % E) * L.es;
     if (L.prec == LRDS_PRECISION_BF16) {
       *reinterpret_cast<uint16_t*>(img + byte) = (uint16_t)(ptx::pack_bf16x2(v, 0.f) & 0xFFFFu);
+    } else if (L.prec == LRDS_PRECISION_F16X3) {
+      const float vs = v * sc[layer];  // exact (power of two)
+      const __half hi = __float2half_rn(vs);
+      *reinterpret_cast<__half*>(img + byte) = hi;
+      *reinterpret_cast<__half*>(img + L.part_bytes + byte) = __float2half_rn(vs - __half2float(hi));
     } else {
       const float hi = ptx::to_tf32(v);
       *reinterpret_cast<float*>(img + byte) = hi;
@@ -97,6 +141,9 @@ static __global__ void pack_tc_image_kernel(const lrds_mlp w, const TcLayout L, 
 // ---- the policy --------------------------------------------------------------------------------------------------
 template <int PREC>
 struct TcMlp {
+  static constexpr bool kX3 = tc_is_x3(PREC);
+  static constexpr bool kHalf = tc_is_half(PREC);
+  static constexpr bool kF16 = PREC == LRDS_PRECISION_F16X3;
   static constexpr bool kPipe = tc_max_warps(PREC) <= 8;  // 255-register kernels prefetch their mixture operands
   TcLayout L;
   const uint8_t* img;  // weight image in shared memory
@@ -109,14 +156,18 @@ struct TcMlp {
   bool issuer;
   int dp;              // columns of x held by the body (d rounded up to 8, zero padded)
 
-  // tf32 operand bits of an activation.  The 3-pass split truncates (one LOP3): hi = top 19 bits, lo = v - hi is
-  // exact in fp32 and the tensor core drops its bits below tf32 itself (error 2^-21 of v); the one-pass mode rounds.
+  // (hi, lo) operand bits of an activation.  The 3-pass splits truncate (one LOP3): hi = the top 11 significand bits,
+  // lo = v - hi is exact in fp32; the tf32 tensor core drops lo's bits below tf32 itself, the fp16 conversion rounds
+  // them (error 2^-22 of v either way).  The one-pass tf32 mode rounds.
   static __device__ __forceinline__ uint32_t split_hi(float v) {
-    if (PREC == LRDS_PRECISION_TF32X3) return __float_as_uint(v) & 0xFFFFE000u;
+    if (kX3) return __float_as_uint(v) & 0xFFFFE000u;
     return __float_as_uint(ptx::to_tf32(v));
   }
   __device__ __forceinline__ uint32_t a_col(int part) const { return (uint32_t)(part * L.a_cols); }
   __device__ __forceinline__ uint32_t d_col() const { return (uint32_t)(L.parts * L.a_cols); }
+  __device__ __forceinline__ float unscale(int layer) const {  // F16X3: accumulator -> pre-activation
+    return reinterpret_cast<const float*>(img + L.off_scale)[8 + layer];
+  }
 
   // every particle thread has stored its A row: make it visible to the tensor core, then one thread issues the
   // layer's MMAs and commits them to the tile's mbarrier.
@@ -126,7 +177,9 @@ struct TcMlp {
     ptx::bar_sync(bar_id, bar_threads);
     if (issuer) {
       ptx::tc_fence_after();
-      const uint32_t idesc = PREC == LRDS_PRECISION_BF16 ? ptx::make_idesc_bf16(128, N) : ptx::make_idesc_tf32(128, N);
+      const uint32_t idesc = PREC == LRDS_PRECISION_BF16 ? ptx::make_idesc_bf16(128, N)
+                             : kF16                      ? ptx::make_idesc_f16(128, N)
+                                                         : ptx::make_idesc_tf32(128, N);
       const uint32_t dcol = tm_tile + d_col();
       const int ksteps = K / L.kstep;
       const uint32_t kbytes = 2u * (uint32_t)N * 16u;  // one MMA consumes two 16-byte K chunks
@@ -136,12 +189,12 @@ struct TcMlp {
         const uint32_t bbase = img_s + (uint32_t)b_part * L.part_bytes + b_off;
         for (int ks = 0; ks < ksteps; ++ks) {
           const uint64_t bdesc = ptx::make_smem_desc(bbase + (uint32_t)ks * kbytes, (uint32_t)N * 16u, 128u);
-          if (PREC == LRDS_PRECISION_BF16) ptx::mma_bf16_ts(dcol, abase + ks * 8, bdesc, idesc, acc);
+          if (kHalf) ptx::mma_bf16_ts(dcol, abase + ks * 8, bdesc, idesc, acc);  // kind::f16 (bf16 or fp16 per idesc)
           else ptx::mma_tf32_ts(dcol, abase + ks * 8, bdesc, idesc, acc);
           acc = 1;
         }
       };
-      if (PREC == LRDS_PRECISION_TF32X3) {  // small terms first
+      if (kX3) {  // small terms first
         pass(1, 0);
         pass(0, 1);
       }
@@ -155,26 +208,41 @@ struct TcMlp {
     ptx::tc_fence_after();
   }
 
-  // A operand <- 8 consecutive fp32 values (columns c0 .. c0+7 of the K axis)
+  // A operand <- 8 consecutive fp32 values (columns c0 .. c0+7 of the K axis), tf32 kinds
   __device__ __forceinline__ void store8(int c0, const float (&v)[8]) {
-    if (PREC == LRDS_PRECISION_BF16) {
-      // handled by store16_bf16
+    uint32_t hi[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) hi[i] = split_hi(v[i]);
+    ptx::tmem_st8(tm_lane + a_col(0) + c0, hi);
+    if (kX3) {
+      uint32_t lo[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) lo[i] = __float_as_uint(v[i] - __uint_as_float(hi[i]));
+      ptx::tmem_st8(tm_lane + a_col(1) + c0, lo);
+    }
+  }
+  // A operand <- 16 consecutive fp32 values as 8 packed columns c0 .. c0+7, 16-bit kinds
+  __device__ __forceinline__ void store16_half(int c0, const float (&v)[16]) {
+    uint32_t r[8];
+    if (kF16) {
+      float hi[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) hi[i] = __uint_as_float(split_hi(v[i]));
+#pragma unroll
+      for (int i = 0; i < 8; ++i) r[i] = ptx::pack_f16x2(hi[2 * i], hi[2 * i + 1]);
+      ptx::tmem_st8(tm_lane + a_col(0) + c0, r);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) r[i] = ptx::pack_f16x2(v[2 * i] - hi[2 * i], v[2 * i + 1] - hi[2 * i + 1]);
+      ptx::tmem_st8(tm_lane + a_col(1) + c0, r);
     } else {
-      uint32_t hi[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) hi[i] = split_hi(v[i]);
-      ptx::tmem_st8(tm_lane + a_col(0) + c0, hi);
-      if (PREC == LRDS_PRECISION_TF32X3) {
-        uint32_t lo[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) lo[i] = __float_as_uint(v[i] - __uint_as_float(hi[i]));
-        ptx::tmem_st8(tm_lane + a_col(1) + c0, lo);
-      }
+      for (int i = 0; i < 8; ++i) r[i] = ptx::pack_bf16x2(v[2 * i], v[2 * i + 1]);
+      ptx::tmem_st8(tm_lane + a_col(0) + c0, r);
     }
   }
 
   __device__ __forceinline__ void store_x(const Col4& x) {
-    if (PREC == LRDS_PRECISION_BF16) {
+    if (kHalf) {
       for (int c0 = 0; c0 < L.Kin / 2; c0 += 8) {  // 16 dims -> 8 packed columns
         float v[16];
 #pragma unroll
@@ -188,10 +256,7 @@ struct TcMlp {
           v[8 * h + 0] = a.x; v[8 * h + 1] = a.y; v[8 * h + 2] = a.z; v[8 * h + 3] = a.w;
           v[8 * h + 4] = b.x; v[8 * h + 5] = b.y; v[8 * h + 6] = b.z; v[8 * h + 7] = b.w;
         }
-        uint32_t r[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) r[i] = ptx::pack_bf16x2(v[2 * i], v[2 * i + 1]);
-        ptx::tmem_st8(tm_lane + a_col(0) + c0, r);
+        store16_half(c0, v);
       }
     } else {
       for (int c0 = 0; c0 < L.Kin; c0 += 8) {  // Kin == dp for the tf32 kinds
@@ -202,9 +267,11 @@ struct TcMlp {
     }
   }
 
-  // accumulator (64 columns) + bias -> GELU -> A operand of the next layer
+  // accumulator (64 columns) [* un-scale] + bias -> GELU -> A operand of the next layer
   template <bool GLOBAL_BIAS>
-  __device__ __forceinline__ void epilogue(const float* __restrict__ bias) {
+  __device__ __forceinline__ void epilogue(const float* __restrict__ bias, int layer) {
+    const float us = kF16 ? unscale(layer) : 1.0f;
+    const float gs = kF16 ? 0.5f * TC_ACT_SCALE : 0.5f;
 #pragma unroll 1
     for (int c0 = 0; c0 < C; c0 += 32) {
       uint32_t r[32];
@@ -215,20 +282,26 @@ struct TcMlp {
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const float4 b = GLOBAL_BIAS ? __ldg(b4 + i) : b4[i];
-        gelu_exact2(__uint_as_float(r[4 * i + 0]) + b.x, __uint_as_float(r[4 * i + 1]) + b.y, g[4 * i + 0], g[4 * i + 1]);
-        gelu_exact2(__uint_as_float(r[4 * i + 2]) + b.z, __uint_as_float(r[4 * i + 3]) + b.w, g[4 * i + 2], g[4 * i + 3]);
+        if (kF16) {
+          gelu_exact2(fmaf(__uint_as_float(r[4 * i + 0]), us, b.x), fmaf(__uint_as_float(r[4 * i + 1]), us, b.y), g[4 * i + 0], g[4 * i + 1], gs);
+          gelu_exact2(fmaf(__uint_as_float(r[4 * i + 2]), us, b.z), fmaf(__uint_as_float(r[4 * i + 3]), us, b.w), g[4 * i + 2], g[4 * i + 3], gs);
+        } else {
+          gelu_exact2(__uint_as_float(r[4 * i + 0]) + b.x, __uint_as_float(r[4 * i + 1]) + b.y, g[4 * i + 0], g[4 * i + 1]);
+          gelu_exact2(__uint_as_float(r[4 * i + 2]) + b.z, __uint_as_float(r[4 * i + 3]) + b.w, g[4 * i + 2], g[4 * i + 3]);
+        }
       }
-      if (PREC == LRDS_PRECISION_BF16) {
-        uint32_t p[16];
+      if (kHalf) {
+        float lo16[16], hi16[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) p[i] = ptx::pack_bf16x2(g[2 * i], g[2 * i + 1]);
-        ptx::tmem_st16(tm_lane + a_col(0) + c0 / 2, p);
+        for (int i = 0; i < 16; ++i) { lo16[i] = g[i]; hi16[i] = g[16 + i]; }
+        store16_half(c0 / 2, lo16);
+        store16_half(c0 / 2 + 8, hi16);
       } else {
         uint32_t hi[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) hi[i] = split_hi(g[i]);
         ptx::tmem_st32(tm_lane + a_col(0) + c0, hi);
-        if (PREC == LRDS_PRECISION_TF32X3) {
+        if (kX3) {
 #pragma unroll
           for (int i = 0; i < 32; ++i) hi[i] = __float_as_uint(g[i] - __uint_as_float(hi[i]));
           ptx::tmem_st32(tm_lane + a_col(1) + c0, hi);
@@ -245,13 +318,13 @@ struct TcMlp {
     const float* bh = reinterpret_cast<const float*>(img + L.off_bhid);
     for (int l = 0; l < L.nh; ++l) {
       wait();
-      if (l == 0) epilogue<!BIAS_SH>(bias1);
-      else epilogue<false>(bh + (l - 1) * C);
+      if (l == 0) epilogue<!BIAS_SH>(bias1, 0);
+      else epilogue<false>(bh + (l - 1) * C, l);
       issue(L.off_hid + (uint32_t)(l * C * C * L.es), C, C);
     }
     wait();
-    if (L.nh == 0) epilogue<!BIAS_SH>(bias1);
-    else epilogue<false>(bh + (L.nh - 1) * C);
+    if (L.nh == 0) epilogue<!BIAS_SH>(bias1, 0);
+    else epilogue<false>(bh + (L.nh - 1) * C, L.nh);
     issue(L.off_out, C, L.Nout);
     wait();
   }
@@ -262,10 +335,15 @@ struct TcMlp {
     ptx::tmem_wait_ld();
     const float4* b4 = reinterpret_cast<const float4*>(img + L.off_bout + j0 * 4);
     const float4 a = b4[0], b = b4[1];
-    out[0] = __uint_as_float(r[0]) + a.x; out[1] = __uint_as_float(r[1]) + a.y;
-    out[2] = __uint_as_float(r[2]) + a.z; out[3] = __uint_as_float(r[3]) + a.w;
-    out[4] = __uint_as_float(r[4]) + b.x; out[5] = __uint_as_float(r[5]) + b.y;
-    out[6] = __uint_as_float(r[6]) + b.z; out[7] = __uint_as_float(r[7]) + b.w;
+    const float bs[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    if (kF16) {
+      const float us = unscale(L.nh + 1);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) out[c] = fmaf(__uint_as_float(r[c]), us, bs[c]);
+    } else {
+#pragma unroll
+      for (int c = 0; c < 8; ++c) out[c] = __uint_as_float(r[c]) + bs[c];
+    }
   }
 };
 

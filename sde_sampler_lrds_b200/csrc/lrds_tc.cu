@@ -13,6 +13,7 @@ int launch_prec(const RolloutArgs& a, const TcPlan& p, cudaStream_t st, char* er
 extern template int launch_prec<LRDS_PRECISION_TF32X3>(const RolloutArgs&, const TcPlan&, cudaStream_t, char*, size_t);
 extern template int launch_prec<LRDS_PRECISION_BF16>(const RolloutArgs&, const TcPlan&, cudaStream_t, char*, size_t);
 extern template int launch_prec<LRDS_PRECISION_TF32>(const RolloutArgs&, const TcPlan&, cudaStream_t, char*, size_t);
+extern template int launch_prec<LRDS_PRECISION_F16X3>(const RolloutArgs&, const TcPlan&, cudaStream_t, char*, size_t);
 
 int launch_rollout_tc(const RolloutArgs& a, cudaStream_t st, char* err, size_t n) {
   const lrds_spec& s = a.s;
@@ -34,6 +35,7 @@ int launch_rollout_tc(const RolloutArgs& a, cudaStream_t st, char* err, size_t n
     case LRDS_PRECISION_TF32X3: return launch_prec<LRDS_PRECISION_TF32X3>(a, p, st, err, n);
     case LRDS_PRECISION_BF16: return launch_prec<LRDS_PRECISION_BF16>(a, p, st, err, n);
     case LRDS_PRECISION_TF32: return launch_prec<LRDS_PRECISION_TF32>(a, p, st, err, n);
+    case LRDS_PRECISION_F16X3: return launch_prec<LRDS_PRECISION_F16X3>(a, p, st, err, n);
   }
   snprintf(err, n, "unknown precision %d", s.precision);
   return LRDS_ERR_INVALID;
@@ -43,6 +45,13 @@ size_t tc_image_bytes(int d, int num_hidden, int precision) { return tc_layout(d
 
 int pack_tc_image(const lrds_mlp& w, int precision, void* image, cudaStream_t st, char* err, size_t n) {
   const TcLayout L = tc_layout(w.d, w.num_hidden, precision);
+  if (precision == LRDS_PRECISION_F16X3) {
+    if (w.num_hidden > 6) {
+      snprintf(err, n, "pack_tc_image: f16x3 supports at most 6 hidden layers");
+      return LRDS_ERR_UNSUPPORTED;
+    }
+    tc_scales_kernel<<<1, 256, 0, st>>>(w, L, static_cast<uint8_t*>(image));
+  }
   pack_tc_image_kernel<<<32, 256, 0, st>>>(w, L, static_cast<uint8_t*>(image));
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {

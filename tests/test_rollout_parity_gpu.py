@@ -17,7 +17,7 @@ pytestmark = pytest.mark.gpu
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
 # "fp32" = FFMA drift network (parity anchor); "tf32x3" = the same network on tcgen05 tensor cores with the 3-pass
 # (hi, lo) tf32 split.  Both are held to the north-star tolerance.
-PRECISIONS = ["fp32", "tf32x3"]
+PRECISIONS = ["fp32", "tf32x3", "f16x3"]
 # Reduced-precision tensor-core modes, reported separately (DESIGN.md "Precision modes"): tolerance on
 # (fraction of log-weights within 1e-2 relative, |log Z - oracle|).
 FAST_MODES = {"tf32": (0.99, 5e-3), "bf16": (0.99, 5e-2)}
