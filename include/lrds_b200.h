@@ -124,6 +124,14 @@ typedef struct {
   int64_t step_stride_logc;  /* floats between consecutive steps of logc (4 ceil(M/4)) */
   int64_t step_stride_param; /* floats between consecutive steps of mu / ivar (M * d_pad) */
   int64_t step_stride_sn;    /* floats between consecutive steps of sn (8 ceil(M/4) * d_pad) */
+  const void* mix_tc;        /* optional (M > 1; NULL = evaluate the score contraction on the SIMT pipes): tensor-core operand
+                              * of  score_j = sum_m r_m mu_mj/var_mj - x_j sum_m r_m/var_mj.  Per step one block of
+                              * lrds_gmm_mix_tc_bytes(M, d_pad) bytes: the matrix B[n][m], rows n = 16 c + i over the 8-dim
+                              * chunks c (i < 8: 1/var_{m,8c+i}; i >= 8: mu/var_{m,8c+i-8}), multiplied by the power of two
+                              * that puts its largest entry into [2^14, 2^15) and split into fp16 hi | lo parts, each in the
+                              * K-major no-swizzle tcgen05 layout [m/8][n][m%8] with m padded to a multiple of 16; then 16
+                              * bytes whose first float is the un-scale.  16-byte aligned. */
+  int64_t step_stride_mix_tc;/* BYTES between consecutive steps of mix_tc */
 } lrds_gmm;
 
 typedef struct {
@@ -190,6 +198,7 @@ int lrds_rollout(const lrds_spec* spec, const float* x0, const float* noise, uin
  * lrds_tc_image_bytes(d, num_hidden, precision) bytes; set mlp.tc_image to it before lrds_rollout.  Repack after
  * every weight update. */
 int64_t lrds_tc_image_bytes(int32_t d, int32_t num_hidden, int32_t precision);
+int64_t lrds_gmm_mix_tc_bytes(int32_t M, int32_t d_pad); /* one block of lrds_gmm.mix_tc */
 int lrds_pack_mlp_tc(const lrds_mlp* mlp, int32_t precision, void* image_out, void* stream);
 
 /* ---- estimator partials: replaces BaseOCLoss.compute_results (oc.py:134-173), ESS (eval/metrics.py:134-140)

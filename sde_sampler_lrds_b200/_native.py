@@ -44,7 +44,8 @@ class Mlp(C.Structure):
 
 class Gmm(C.Structure):
     _fields_ = [("M", C.c_int32), ("reserved", C.c_int32), ("logc", FP), ("mu", FP), ("ivar", FP), ("sn", FP),
-                ("step_stride_logc", C.c_int64), ("step_stride_param", C.c_int64), ("step_stride_sn", C.c_int64)]
+                ("step_stride_logc", C.c_int64), ("step_stride_param", C.c_int64), ("step_stride_sn", C.c_int64),
+                ("mix_tc", FP), ("step_stride_mix_tc", C.c_int64)]
 
 
 class Phi4(C.Structure):
@@ -71,7 +72,7 @@ class Spec(C.Structure):
                 ("steps", FP), ("mlp", Mlp), ("target", Distr), ("ref_t", Gmm), ("ref_0", Gmm)]
 
 
-EXPORTS = ["lrds_rollout", "lrds_tc_image_bytes", "lrds_pack_mlp_tc", "lrds_estimator_blocks", "lrds_estimator_partials", "lrds_ctrl_forward",
+EXPORTS = ["lrds_rollout", "lrds_tc_image_bytes", "lrds_gmm_mix_tc_bytes", "lrds_pack_mlp_tc", "lrds_estimator_blocks", "lrds_estimator_partials", "lrds_ctrl_forward",
            "lrds_distr_eval", "lrds_axpy_step", "lrds_normals", "lrds_last_error", "lrds_abi_version",
            "lrds_launch_count"]
 

@@ -323,6 +323,11 @@ int64_t lrds_tc_image_bytes(int32_t d, int32_t num_hidden, int32_t precision) {
   return (int64_t)lrds::tc_image_bytes(d, num_hidden, precision);
 }
 
+int64_t lrds_gmm_mix_tc_bytes(int32_t M, int32_t d_pad) {
+  if (M < 2 || d_pad < 8 || d_pad % 8 != 0) return fail(LRDS_ERR_INVALID, "gmm_mix_tc_bytes: bad arguments");
+  return (int64_t)lrds::gmm_mix_tc_bytes(M, d_pad);
+}
+
 int lrds_pack_mlp_tc(const lrds_mlp* mlp, int32_t precision, void* image_out, void* stream) {
   if (!mlp || !image_out || !mlp->w_in_t || !mlp->w_out_t || !mlp->b_out || mlp->d < 1 ||
       mlp->d_pad != ((mlp->d + 7) / 8) * 8 || (mlp->num_hidden > 0 && (!mlp->w_hid_t || !mlp->b_hid)))

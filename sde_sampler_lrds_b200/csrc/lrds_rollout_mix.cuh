@@ -1,0 +1,340 @@
+// The LRDS benchmark loop with BOTH dense contractions of a step on the tensor core: the drift network
+// (lrds_rollout_tc.cuh) and the mixture-score contractions
+//     score_j = sum_m r_m mu_mj / var_mj  -  x_j sum_m r_m / var_mj          (distr/gauss.py:97-107)
+// of the target mixture (ScoreCtrl, models/reparam.py:112-117) and of the time-marginal reference mixture
+// (eq/sdes.py:329-345), as [128 x 16] . [16 x 16] fp16 (hi, lo) 3-pass GEMMs per 8-dim chunk.  The responsibilities
+// r = softmax_m(logc_m - q_m / 2) stay on the SIMT pipes: their quadratic forms q_m cannot be expanded into a GEMM
+// at fp32 parity (cancellation).  They never touch shared memory: registers -> TMEM (A operand) -> accumulator.
+//
+// Configuration: LINEAR kind, exponential-integrator / DDPM-like update (LRDS_UPDATE_AXPY, LRDS_ITO_SCALED), ScoreCtrl
+// over a mixture target, mixture reference, both with 2..16 components, precision F16X3 (traits_match<TraitsLrds> and
+// mix_tc_applicable below); everything else runs the kernels of lrds_rollout_tc.cuh.
+//
+// TMEM columns of a tile (F16X3, d <= 64): [0,32) A hi | [32,64) A lo | [64,128) accumulator D.  After the output
+// GEMM of the network the A region is free: [0,32) holds R = (r_target hi | lo | r_reference hi | lo), 8 packed columns
+// each, [32,64) the 8-dim chunk of the contraction (target a8 b8 | reference a8 b8) while D still holds the network's
+// output.  One chunk is in flight at a time: chunk c+1 is issued as soon as every warp of the tile has read chunk c.
+#pragma once
+#include "lrds_rollout_tc.cuh"
+
+namespace lrds {
+
+constexpr int MIX_MAX_M = 16;
+constexpr int MIX_MAX_WARPS = 14;  // 3.5 tiles: one wave for 65536 particles on 148 SMs; 144 registers per thread
+
+__host__ __device__ inline bool mix_tc_applicable(const lrds_spec& s) {
+  return s.precision == LRDS_PRECISION_F16X3 && s.kind == LRDS_ROLLOUT_LINEAR && s.update_form == LRDS_UPDATE_AXPY &&
+         s.ito_form == LRDS_ITO_SCALED && s.ctrl_kind == LRDS_CTRL_SCORE && s.target.kind == LRDS_DISTR_GMM &&
+         s.has_ref_ctrl && s.target.gmm.M > 1 && s.target.gmm.M <= MIX_MAX_M && s.ref_t.M > 1 && s.ref_t.M <= MIX_MAX_M &&
+         s.target.gmm.mix_tc != nullptr && s.ref_t.mix_tc != nullptr && s.mlp.d_pad <= 64;
+}
+
+// Responsibilities of a mixture with M <= 16 components in registers (the arithmetic of gmm_pass1); returns the
+// mixture log-density.  Modes beyond M get weight zero.
+template <bool PIPE, bool SH>
+__device__ __forceinline__ float gmm_pass1_regs(const GmmViewT<SH>& g, int d, int dp, const Col4& x, float (&r)[MIX_MAX_M]) {
+  const int nq = (d + 3) >> 2;
+  const int rowq = dp >> 2;
+  const int M4 = (g.M + 3) >> 2;
+  float mx = -INFINITY;
+#pragma unroll
+  for (int mb = 0; mb < MIX_MAX_M / 4; ++mb) {
+    if (mb < M4) {
+      u64 qa[4] = {0, 0, 0, 0}, qb[4] = {0, 0, 0, 0};
+      PPtr<SH> p = g.sn + mb * rowq * 32;
+      if constexpr (PIPE) {
+        Pass1Ops<SH> A, B;
+        A.load(x, 0, p);
+        int c = 0;
+        for (; c + 1 < nq; c += 2, p = p + 64) {
+          B.load(x, c + 1, p + 32);
+          A.accumulate(qa, qb);
+          if (c + 2 < nq) A.load(x, c + 2, p + 64);
+          B.accumulate(qa, qb);
+        }
+        if (c < nq) A.accumulate(qa, qb);
+      } else {
+#pragma unroll 2
+        for (int c = 0; c < nq; ++c, p = p + 32) {
+          Pass1Ops<SH> A;
+          A.load(x, c, p);
+          A.accumulate(qa, qb);
+        }
+      }
+      const float4 lc = g.logc.ld4(mb);
+      r[4 * mb + 0] = lc.x - 0.5f * f2::hsum(qa[0], qb[0]);
+      r[4 * mb + 1] = lc.y - 0.5f * f2::hsum(qa[1], qb[1]);
+      r[4 * mb + 2] = lc.z - 0.5f * f2::hsum(qa[2], qb[2]);
+      r[4 * mb + 3] = lc.w - 0.5f * f2::hsum(qa[3], qb[3]);
+      mx = fmaxf(fmaxf(mx, fmaxf(r[4 * mb], r[4 * mb + 1])), fmaxf(r[4 * mb + 2], r[4 * mb + 3]));
+    } else {
+      r[4 * mb] = r[4 * mb + 1] = r[4 * mb + 2] = r[4 * mb + 3] = -INFINITY;
+    }
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int mb = 0; mb < MIX_MAX_M / 4; ++mb) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) r[4 * mb + i] = __expf(r[4 * mb + i] - mx);
+    s += (r[4 * mb] + r[4 * mb + 1]) + (r[4 * mb + 2] + r[4 * mb + 3]);
+  }
+  const float inv = 1.0f / s;
+#pragma unroll
+  for (int i = 0; i < MIX_MAX_M; ++i) r[i] *= inv;
+  return mx + __logf(s);
+}
+
+// log-density of a reference / prior block that may be a single Gaussian (the terminal cost)
+template <bool PIPE>
+__device__ __forceinline__ float gmm_logp_any(const GmmView& g, int d, int dp, const Col4& x) {
+  if (g.M == 1) {
+    const int nq = (d + 3) >> 2;
+    float q = 0.f;
+    for (int c = 0; c < nq; ++c) quad4(q, x.ld4(c), g.mu.ld4(c), g.ivar.ld4(c));
+    return g.glogc.ld1(0) - 0.5f * q;
+  }
+  float r[MIX_MAX_M];
+  return gmm_pass1_regs<PIPE>(g, d, dp, x, r);
+}
+
+// ---- tensor-core side of the contraction (extends the drift-network policy; same tile, mbarrier and phase) --------
+template <int PREC>
+struct MixTc : TcMlp<PREC> {
+  using Base = TcMlp<PREC>;
+  static constexpr uint32_t kRCol = 0, kDCol = 32;
+  uint32_t lbo;  // bytes between the two 16-byte K chunks (modes 0-7 | 8-15) of an image part: 2 d_pad * 16
+  uint32_t part_bytes;
+
+  // r (16 responsibilities) -> fp16 (hi, lo) A operand `which` (0 target, 1 reference)
+  __device__ __forceinline__ void store_r(int which, const float (&r)[MIX_MAX_M]) {
+    uint32_t p[8];
+    float hi[MIX_MAX_M];
+#pragma unroll
+    for (int i = 0; i < MIX_MAX_M; ++i) hi[i] = __uint_as_float(__float_as_uint(r[i]) & 0xFFFFE000u);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) p[i] = ptx::pack_f16x2(hi[2 * i], hi[2 * i + 1]);
+    ptx::tmem_st8(this->tm_lane + kRCol + which * 16, p);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) p[i] = ptx::pack_f16x2(r[2 * i] - hi[2 * i], r[2 * i + 1] - hi[2 * i + 1]);
+    ptx::tmem_st8(this->tm_lane + kRCol + which * 16 + 8, p);
+  }
+
+  // chunk c of both contractions -> columns [32, 64); images = shared-window addresses of the (hi | lo) blocks
+  __device__ __forceinline__ void issue_chunk(int c, uint32_t tgt_img, uint32_t ref_img) {
+    ptx::tmem_wait_st();
+    ptx::tc_fence_before();
+    ptx::bar_sync(this->bar_id, this->bar_threads);
+    if (this->issuer) {
+      ptx::tc_fence_after();
+      const uint32_t idesc = ptx::make_idesc_f16(128, 16);
+#pragma unroll
+      for (int which = 0; which < 2; ++which) {
+        const uint32_t img = (which ? ref_img : tgt_img) + (uint32_t)c * 256u;  // 16 rows of 16 bytes per chunk
+        const uint32_t dcol = this->tm_tile + kDCol + which * 16;
+        const uint32_t a_hi = this->tm_tile + kRCol + which * 16, a_lo = a_hi + 8;
+        const uint64_t b_hi = ptx::make_smem_desc(img, lbo, 128u), b_lo = ptx::make_smem_desc(img + part_bytes, lbo, 128u);
+        ptx::mma_bf16_ts(dcol, a_lo, b_hi, idesc, 0);
+        ptx::mma_bf16_ts(dcol, a_hi, b_lo, idesc, 1);
+        ptx::mma_bf16_ts(dcol, a_hi, b_hi, idesc, 1);
+      }
+      ptx::mma_commit(this->bar);
+    }
+  }
+  __device__ __forceinline__ void load_chunk(uint32_t (&m)[32]) {
+    ptx::tmem_ld32(this->tm_lane + kDCol, m);
+    ptx::tmem_wait_ld();
+  }
+};
+
+// ---- the loop ------------------------------------------------------------------------------------------------------
+template <int PREC>
+__device__ __forceinline__ void rollout_body_mix(const RolloutArgs& a, float* smem, uint8_t* stage, MixTc<PREC>& mlp) {
+  constexpr bool PIPE = MixTc<PREC>::kPipe;
+  const lrds_spec& s = a.s;
+  const int NT = blockDim.x;
+  const int tid = threadIdx.x;
+  const int b_raw = blockIdx.x * NT + tid;
+  const bool live = b_raw < s.B;
+  const int b = live ? b_raw : s.B - 1;  // idle lanes shadow the last particle, results are not stored
+  const int d = s.d, dp = s.mlp.d_pad, K = s.K;
+  const ColLayout L = col_layout(s, true);
+  const Particle P = make_particle(smem, L, NT, tid);
+
+  for (int j = 0; j < dp; ++j) P.x(j) = (j < d) ? __ldg(a.x0 + (int64_t)b * d + j) : 0.f;
+  if (a.traj_out != nullptr && live)
+    for (int j = 0; j < d; ++j) a.traj_out[(int64_t)b * d + j] = P.x(j);
+
+  CtrlConst cc = ctrl_const(s);
+  const GmmView tv0 = gmm_at(s.target.gmm, 0);
+  const StageLayout SL = stage_layout(s, 2, true);
+  uint64_t* sbar = reinterpret_cast<uint64_t*>(stage);
+  const uint8_t* tmix_g = static_cast<const uint8_t*>(s.target.gmm.mix_tc);
+  const uint8_t* rmix_g = static_cast<const uint8_t*>(s.ref_t.mix_tc);
+  const uint32_t mix_off_t = SL.tgt_logc_bytes + SL.tgt_param_bytes;                // inside the target area
+  const uint32_t mix_off_r = SL.row_bytes + SL.ref_logc_bytes + SL.ref_param_bytes;  // inside a step buffer
+  auto stage_step_mix = [&](uint8_t* dst, int k, uint64_t* bar) {
+    stage_step(dst, s, SL, k, bar);
+    ptx::bulk_g2s(dst + mix_off_r, rmix_g + (int64_t)k * s.ref_t.step_stride_mix_tc, SL.ref_mix_bytes, bar);
+  };
+  if (tid == 0) {
+    ptx::mbar_init(sbar, 1);
+    ptx::mbar_init(sbar + 1, 1);
+    ptx::fence_mbar_init();
+  }
+  __syncthreads();
+  if (tid == 0) {
+    ptx::mbar_expect_tx(sbar, SL.tgt_bytes + SL.buf_bytes);
+    stage_gmm(stage + SL.off_tgt, tv0, SL.tgt_logc_bytes, SL.tgt_param_bytes, sbar);
+    ptx::bulk_g2s(stage + SL.off_tgt + mix_off_t, tmix_g, SL.tgt_mix_bytes, sbar);
+    stage_step_mix(stage + SL.off_buf, 0, sbar);
+  }
+  const GmmViewT<true> tv = staged_view(stage + SL.off_tgt, tv0, SL.tgt_logc_bytes, SL.tgt_param_bytes);
+  const uint32_t tgt_img = ptx::smem_u32(stage + SL.off_tgt + mix_off_t);
+  const uint32_t tgt_img_bytes = SL.tgt_mix_bytes - 16u, ref_img_bytes = SL.ref_mix_bytes - 16u;
+  mlp.lbo = (uint32_t)(2 * dp) * 16u;
+  mlp.part_bytes = tgt_img_bytes / 2u;  // both mixtures are padded to 16 modes: equal image sizes
+  const int nchunk = dp / JC;
+  float rnd = 0.f;
+
+  for (int k = 0; k < K; ++k) {
+    __syncthreads();  // every warp has finished step k-1, whose buffer the prefetch below overwrites
+    if (tid == 0 && k + 1 < K) {
+      ptx::mbar_expect_tx(sbar + ((k + 1) & 1), SL.buf_bytes);
+      stage_step_mix(stage + SL.off_buf + ((k + 1) & 1) * SL.buf_bytes, k + 1, sbar + ((k + 1) & 1));
+    }
+    ptx::mbar_wait(sbar + (k & 1), (uint32_t)(k >> 1) & 1u);
+    const uint8_t* buf = stage + SL.off_buf + (k & 1) * SL.buf_bytes;
+    const float* row = reinterpret_cast<const float*>(buf);
+    const PPtr<true> rowp{ptx::smem_u32(buf)};
+    const GmmViewT<true> rv = staged_view(buf + SL.row_bytes, gmm_at(s.ref_t, k), SL.ref_logc_bytes, SL.ref_param_bytes);
+    const uint32_t ref_img = ptx::smem_u32(buf + mix_off_r);
+    const float A = rowp.ld1(LRDS_STEP_A), Bc = rowp.ld1(LRDS_STEP_B), Cc = rowp.ld1(LRDS_STEP_C);
+    const float wcost = rowp.ld1(LRDS_STEP_W_COST), wito = rowp.ld1(LRDS_STEP_W_ITO);
+    const float gamma = rowp.ld1(LRDS_STEP_GAMMA);
+    const float ust = *reinterpret_cast<const float*>(stage + SL.off_tgt + mix_off_t + tgt_img_bytes);
+    const float usr = *reinterpret_cast<const float*>(buf + mix_off_r + ref_img_bytes);
+
+    mlp.template hidden<true>(row + LRDS_STEP_BIAS1, P.x);  // ends with the output GEMM complete: A region free
+    {
+      float r[MIX_MAX_M];
+      gmm_pass1_regs<PIPE>(tv, d, dp, P.x, r);
+      mlp.store_r(0, r);
+      gmm_pass1_regs<PIPE>(rv, d, dp, P.x, r);
+      mlp.store_r(1, r);
+    }
+    mlp.issue_chunk(0, tgt_img, ref_img);
+    float su2 = 0.f, sito = 0.f;
+    for (int c = 0; c < nchunk; ++c) {
+      const int j0 = c * JC;
+      uint32_t m[32];
+      mlp.wait();
+      mlp.load_chunk(m);
+      if (c + 1 < nchunk) mlp.issue_chunk(c + 1, tgt_img, ref_img);
+      float xr[JC], u[JC], z[JC], xn[JC];
+      lrds::load_chunk(P.x, j0, xr);
+      mlp.out_chunk(j0, u);
+      noise_chunk(a, k, b, j0, z);
+#pragma unroll
+      for (int i = 0; i < JC; ++i) {
+        const float ts = fmaf(-xr[i], __uint_as_float(m[i]), __uint_as_float(m[8 + i])) * ust;
+        const float rs = fmaf(-xr[i], __uint_as_float(m[16 + i]), __uint_as_float(m[24 + i])) * usr;
+        float v = clipb(u[i], cc.bound_model);
+        v = v + (cc.scale_score * clipb(ts, cc.bound_score)) * gamma;
+        v = (j0 + i < d) ? v : 0.f;
+        su2 = fmaf(v, v, su2);
+        sito = fmaf(v, z[i], sito);
+        xn[i] = (A * xr[i] + Bc * (rs + v)) + Cc * z[i];
+        if (j0 + i >= d) xn[i] = 0.f;
+      }
+      store_chunk(P.x, j0, xn);
+      if (a.traj_out != nullptr && live) store_traj(a, k + 1, b, j0, xn);
+    }
+    rnd += wcost * su2;
+    rnd += wito * sito;
+  }
+  // terminal cost: rnd += reference_log_prob(x) - terminal_unnorm_log_prob(x)   (oc.py:505, 645)
+  const float lref = gmm_logp_any<PIPE>(gmm_at(s.ref_0, 0), d, dp, P.x);
+  float rt[MIX_MAX_M];
+  const float ltgt = clipf(gmm_pass1_regs<PIPE>(tv, d, dp, P.x, rt), s.clip_target);
+  rnd += lref - ltgt;
+
+  if (live) {
+    a.rnd_out[b] = rnd;
+    if (a.x_out != nullptr)
+      for (int j = 0; j < d; ++j) a.x_out[(int64_t)b * d + j] = P.x(j);
+  }
+}
+
+// shared memory: [weight image | mbarriers + TMEM slot | operand stage | particle columns]
+template <int PREC>
+__global__ void __launch_bounds__(MIX_MAX_WARPS * 32, 1)
+rollout_mix_kernel(const RolloutArgs a, const uint8_t* __restrict__ image, const uint32_t tmem_cols) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  const TcLayout TL = tc_layout(a.s.d, a.s.mlp.num_hidden, PREC);
+  const int tid = threadIdx.x, warp = tid >> 5, nwarps = blockDim.x >> 5;
+  uint8_t* img = smem_raw;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + TL.bytes);  // [0] image, [1 + t] tile t
+  uint32_t* slot = reinterpret_cast<uint32_t*>(smem_raw + TL.bytes + 48);
+  uint8_t* stage = smem_raw + TL.bytes + TC_TAIL_BYTES;
+  float* cols = reinterpret_cast<float*>(stage + ((stage_layout(a.s, 2, true).total + 15u) & ~15u));
+  if (warp == 0) ptx::tmem_alloc(slot, tmem_cols);
+  if (tid == 0) {
+    for (int i = 0; i < 5; ++i) ptx::mbar_init(bars + i, 1);
+    ptx::fence_mbar_init();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  if (tid == 0) {  // drift weights staged once per CTA by the TMA engine
+    ptx::mbar_expect_tx(bars, TL.bytes);
+    ptx::bulk_g2s(img, image, TL.bytes, bars);
+  }
+  ptx::mbar_wait(bars, 0);
+  const uint32_t tmem = *slot;
+  const int tile = warp >> 2;
+  const int tile_warps = min(4, nwarps - 4 * tile);
+  MixTc<PREC> mlp;
+  mlp.L = TL;
+  mlp.img = img;
+  mlp.img_s = ptx::smem_u32(img);
+  mlp.tm_tile = tmem + (uint32_t)(tile * TL.tile_cols);
+  mlp.tm_lane = mlp.tm_tile + ((uint32_t)((warp & 3) * 32) << 16);
+  mlp.bar = bars + 1 + tile;
+  mlp.phase = 0;
+  mlp.bar_id = 1 + tile;
+  mlp.bar_threads = tile_warps * 32;
+  mlp.issuer = (tid & 127) == 0;
+  mlp.dp = a.s.mlp.d_pad;
+  rollout_body_mix<PREC>(a, cols, stage, mlp);
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) ptx::tmem_dealloc(tmem, tmem_cols);
+}
+
+// Launch shape of the mix kernel: one CTA per SM, as few waves as possible, then as few idle lanes as possible.
+inline bool plan_rollout_mix(const lrds_spec& s, int smem_cap, int sms, TcPlan* out) {
+  if (!mix_tc_applicable(s)) return false;
+  const TcLayout TL = tc_layout(s.d, s.mlp.num_hidden, s.precision);
+  if (TL.tile_cols != 128 || TL.parts * TL.a_cols < 64) return false;
+  const ColLayout CL = col_layout(s, true);
+  const size_t fixed = (size_t)TL.bytes + TC_TAIL_BYTES + ((stage_layout(s, 2, true).total + 15u) & ~15u);
+  const size_t per_warp = (size_t)CL.total * 32 * sizeof(float);
+  if (fixed + per_warp > (size_t)smem_cap) return false;
+  int wmax = (int)(((size_t)smem_cap - fixed) / per_warp);
+  wmax = wmax < MIX_MAX_WARPS ? wmax : MIX_MAX_WARPS;
+  const int need = (s.B + 31) / 32;
+  const int waves = (need + sms * wmax - 1) / (sms * wmax);
+  int w = (need + sms * waves - 1) / (sms * waves);
+  w = w < 1 ? 1 : (w > wmax ? wmax : w);
+  const int tiles = (w + 3) / 4;
+  uint32_t cols = 32;
+  while ((int)cols < tiles * TL.tile_cols) cols <<= 1;
+  out->warps = w;
+  out->grid = (need + w - 1) / w;
+  out->staged = 2;
+  out->tmem_cols = cols;
+  out->smem = fixed + per_warp * w;
+  return true;
+}
+
+}  // namespace lrds

@@ -30,7 +30,9 @@ struct ColLayout {
   int x, act, rt, rr, g, us, tsd, db, total;
 };
 
-__host__ __device__ inline ColLayout col_layout(const lrds_spec& s) {
+// mix_tc: the mixture-score contractions run on the tensor core (lrds_rollout_mix.cuh): responsibilities live in
+// registers / TMEM, not in shared-memory columns
+__host__ __device__ inline ColLayout col_layout(const lrds_spec& s, bool mix_tc = false) {
   ColLayout L{};
   int off = 0;
   const int dp = s.mlp.d_pad;
@@ -38,9 +40,9 @@ __host__ __device__ inline ColLayout col_layout(const lrds_spec& s) {
   L.act = off;
   if (s.precision == LRDS_PRECISION_FP32_SIMT) off += C;  // hidden activations: tensor-core backends keep them in TMEM
   L.rt = off;
-  if (s.target.kind == LRDS_DISTR_GMM && s.target.gmm.M > 1) off += (s.target.gmm.M + 3) / 4 * 4;
+  if (!mix_tc && s.target.kind == LRDS_DISTR_GMM && s.target.gmm.M > 1) off += (s.target.gmm.M + 3) / 4 * 4;
   L.rr = off;
-  {
+  if (!mix_tc) {
     int m = 0;
     if (s.has_ref_ctrl && s.ref_t.M > 1) m = s.ref_t.M;
     if (s.ref_0.M > 1 && s.ref_0.M > m) m = s.ref_0.M;
@@ -82,24 +84,30 @@ __device__ __forceinline__ Particle make_particle(float* smem, const ColLayout& 
 struct StageLayout {
   uint32_t tgt_logc_bytes, tgt_param_bytes, tgt_bytes;  // target mixture (static, M > 1): logc | sn
   uint32_t ref_logc_bytes, ref_param_bytes, row_bytes;  // one step: table row | logc | sn (M > 1)
+  uint32_t tgt_mix_bytes, ref_mix_bytes;                // tensor-core images of the score contractions (mix_tc)
   uint32_t buf_bytes, off_tgt, off_buf, total;
 };
+__host__ __device__ inline uint32_t gmm_mix_tc_bytes(int M, int d_pad) {
+  return 2u * (uint32_t)((M + 15) / 16 * 2) * (uint32_t)(2 * d_pad) * 16u + 16u;
+}
 
 // level 1: table row + reference block per step; level 2: also the (static) target mixture
-__host__ __device__ inline StageLayout stage_layout(const lrds_spec& s, int level) {
+__host__ __device__ inline StageLayout stage_layout(const lrds_spec& s, int level, bool mix_tc = false) {
   StageLayout L{};
   const uint32_t dp = (uint32_t)s.mlp.d_pad;
   if (level >= 2 && s.target.kind == LRDS_DISTR_GMM && s.target.gmm.M > 1) {
     L.tgt_logc_bytes = (uint32_t)((s.target.gmm.M + 3) / 4 * 4) * 4u;
     L.tgt_param_bytes = (uint32_t)((s.target.gmm.M + 3) / 4) * dp * 32u;  // sn: 8 floats per mode (padded to 4) and dim
-    L.tgt_bytes = L.tgt_logc_bytes + L.tgt_param_bytes;
+    if (mix_tc) L.tgt_mix_bytes = gmm_mix_tc_bytes(s.target.gmm.M, s.mlp.d_pad);
+    L.tgt_bytes = L.tgt_logc_bytes + L.tgt_param_bytes + L.tgt_mix_bytes;
   }
   if (s.has_ref_ctrl && s.ref_t.M > 1) {  // single Gaussians are read from global memory
     L.ref_logc_bytes = (uint32_t)((s.ref_t.M + 3) / 4 * 4) * 4u;
     L.ref_param_bytes = (uint32_t)((s.ref_t.M + 3) / 4) * dp * 32u;
+    if (mix_tc) L.ref_mix_bytes = gmm_mix_tc_bytes(s.ref_t.M, s.mlp.d_pad);
   }
   L.row_bytes = LRDS_STEP_STRIDE * 4u;
-  L.buf_bytes = L.row_bytes + L.ref_logc_bytes + L.ref_param_bytes;
+  L.buf_bytes = L.row_bytes + L.ref_logc_bytes + L.ref_param_bytes + L.ref_mix_bytes;
   L.off_tgt = 16;  // two mbarriers in front
   L.off_buf = L.off_tgt + L.tgt_bytes;
   L.total = L.off_buf + 2u * L.buf_bytes;

@@ -44,16 +44,50 @@ def gmm_block(loc: torch.Tensor, var: torch.Tensor, weights: torch.Tensor | None
     m4, nq = (M + mpad) // 4, (d + pad) // 4
     sn = torch.stack([F.pad(t, (0, pad, 0, mpad)).reshape(*lead, m4, 4, nq, 4).transpose(-3, -2) for t in (siv, nmsiv)],
                      dim=-2)  # [.., m4, nq, 4 modes, 2, 4 dims]
-    return tuple(t.contiguous().to(device) for t in (logc, loc, ivar, sn.reshape(*lead, m4 * nq * 32)))
+    out = [logc, loc, ivar, sn.reshape(*lead, m4 * nq * 32)]
+    if M > 1:
+        out.append(gmm_mix_tc_image(loc[..., :d], var, d + pad))
+    return tuple(t.contiguous().to(device) for t in out)
+
+
+def gmm_mix_tc_image(loc: torch.Tensor, var: torch.Tensor, d_pad: int) -> torch.Tensor:
+    """Tensor-core operand of the mixture-score contraction (lrds_gmm.mix_tc, include/lrds_b200.h): per block the
+    matrix B[n][m] with rows n = 16 c + i over 8-dim chunks c (i < 8: 1/var_{m, 8c+i}; i >= 8: mu/var_{m, 8c+i-8}),
+    scaled by the power of two that puts its largest entry into [2^14, 2^15) and split into fp16 (hi, lo), each part
+    in the K-major no-swizzle tcgen05 layout [m/8][n][m%8], followed by 16 bytes holding the float un-scale."""
+    lead = loc.shape[:-2]
+    M, d = loc.shape[-2:]
+    Mp = (M + 15) // 16 * 16
+    iv = 1.0 / var.double()
+    a, b = iv.float(), (loc.double() * iv).float()
+    F = torch.nn.functional
+    T = torch.stack([F.pad(t, (0, d_pad - d, 0, Mp - M)).reshape(*lead, Mp, d_pad // 8, 8) for t in (a, b)], dim=-2)
+    V = T.reshape(*lead, Mp, 2 * d_pad)                       # [.., m, n]
+    amax = V.abs().flatten(-2).max(dim=-1).values.double().clamp(min=1e-30)
+    k = 14 - torch.floor(torch.log2(amax))
+    scale = torch.pow(torch.tensor(2.0, dtype=torch.float64), k)
+    Vs = (V.double() * scale[..., None, None]).float()        # exact: power-of-two scaling
+    hi = Vs.half()
+    lo = (Vs - hi.float()).half()
+    parts = [t.reshape(*lead, Mp // 8, 8, 2 * d_pad).transpose(-1, -2).contiguous().reshape(*lead, -1).view(torch.uint8)
+             for t in (hi, lo)]
+    tail = torch.zeros(*lead, 4, dtype=torch.float32)
+    tail[..., 0] = (1.0 / scale).float()
+    return torch.cat(parts + [tail.view(torch.uint8)], dim=-1).contiguous()
 
 
 def fill_gmm(g: N.Gmm, block, stepped: bool = False):
-    logc, mu, ivar, sn = block
+    logc, mu, ivar, sn = block[:4]
     g.M = mu.shape[-2]
     g.logc, g.mu, g.ivar, g.sn = logc.data_ptr(), mu.data_ptr(), ivar.data_ptr(), sn.data_ptr()
     g.step_stride_logc = logc.shape[-1] if stepped else 0
     g.step_stride_param = g.M * mu.shape[-1] if stepped else 0
     g.step_stride_sn = sn.shape[-1] if stepped else 0
+    if len(block) > 4:
+        g.mix_tc = block[4].data_ptr()
+        g.step_stride_mix_tc = block[4].shape[-1] if stepped else 0
+    else:
+        g.mix_tc, g.step_stride_mix_tc = None, 0
     return g
 
 
