@@ -185,9 +185,14 @@ def run_ours(args):
     sampler = ClockSampler(local)
     sampler.start()
     sampler.ready.wait(timeout=10)
+    prev = None
     for w in range(args.warmup):
-        step(x0, 1000 + w)
+        # two generations of outputs stay alive, as in the timed loop: the caching allocator then owns every buffer
+        # the timed iterations need (a cudaMalloc inside the timed region would stall the launch path for milliseconds)
+        cur = step(x0, 1000 + w)
+        prev = cur
     barrier()
+    del prev, cur
 
     # ---- device-resident timing (value) + the dominant kernel alone (roofline) -----------------------------------
     sampler.recording = True

@@ -20,7 +20,8 @@
 namespace lrds {
 
 constexpr int MIX_MAX_M = 16;
-constexpr int MIX_MAX_WARPS = 14;  // 3.5 tiles: one wave for 65536 particles on 148 SMs; 144 registers per thread
+constexpr int MIX_TAIL_BYTES = 64;  // the kernel's extra mbarriers
+constexpr int MIX_MAX_WARPS = 14;  // 3.5 tiles: one wave for 65536 particles on 148 SMs (128 registers: four warps share one 16K-register SM sub-partition)
 
 __host__ __device__ inline bool mix_tc_applicable(const lrds_spec& s) {
   return s.precision == LRDS_PRECISION_F16X3 && s.kind == LRDS_ROLLOUT_LINEAR && s.update_form == LRDS_UPDATE_AXPY &&
@@ -84,6 +85,96 @@ __device__ __forceinline__ float gmm_pass1_regs(const GmmViewT<SH>& g, int d, in
   return mx + __logf(s);
 }
 
+// The same responsibilities with the operand traffic halved.  The quadratic forms are bound by the shared-memory
+// pipe, not by the FMA pipe: every (1/sigma, -mu/sigma) pair is used once per particle and a warp-uniform LDS.128
+// (one wavefront) feeds only two FFMA2.  Here the two half-warps split the mode blocks, and every thread evaluates
+// its modes for TWO particles - its own and the one of lane ^ 16 - so that each operand vector feeds four FFMA2;
+// the dims are the outer loop, so that a particle's coordinates are read once per call instead of once per mode
+// block.  The halves swap their partner results with one SHFL per mode.
+template <bool SH>
+__device__ __forceinline__ float gmm_pass1_pair(const GmmViewT<SH>& g, int d, int dp, const Col4& x, float (&r)[MIX_MAX_M]) {
+  const int lane = threadIdx.x & 31, h = lane >> 4;
+  const int nq = (d + 3) >> 2;
+  const int rowq = dp >> 2;
+  const int M4 = (g.M + 3) >> 2;
+  const int nb = (M4 + 1) >> 1;  // mode blocks per half-warp (warp-uniform): 1 or 2
+  const int b0 = h * nb;
+  const Col4 xo{x.p + ((lane ^ 16) - lane) * 4, x.stride};  // the partner's coordinates
+  const int blk0 = min(b0, M4 - 1), blk1 = min(b0 + 1, M4 - 1);  // clamped: results of blocks >= M4 are discarded
+  PPtr<SH> p0 = g.sn + blk0 * rowq * 32, p1 = g.sn + blk1 * rowq * 32;
+  u64 qa[8] = {0, 0, 0, 0, 0, 0, 0, 0}, qb[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // own / partner particle, (even, odd) dims
+  auto block = [&](const PPtr<SH>& p, const ulonglong2& xa, const ulonglong2& xb, int o) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const ulonglong2 sv = p.ld2(2 * i), nv = p.ld2(2 * i + 1);
+      const u64 a0 = f2::fma(xa.x, sv.x, nv.x), a1 = f2::fma(xa.y, sv.y, nv.y);
+      const u64 c0 = f2::fma(xb.x, sv.x, nv.x), c1 = f2::fma(xb.y, sv.y, nv.y);
+      qa[o + i] = f2::fma(a0, a0, qa[o + i]);
+      qb[o + i] = f2::fma(c0, c0, qb[o + i]);
+      qa[o + i] = f2::fma(a1, a1, qa[o + i]);
+      qb[o + i] = f2::fma(c1, c1, qb[o + i]);
+    }
+  };
+  if (nb > 1) {
+    for (int c = 0; c < nq; ++c, p0 = p0 + 32, p1 = p1 + 32) {
+      const ulonglong2 xa = x.ldu(c), xb = xo.ldu(c);
+      block(p0, xa, xb, 0);
+      block(p1, xa, xb, 4);
+    }
+  } else {
+    for (int c = 0; c < nq; ++c, p0 = p0 + 32) {
+      const ulonglong2 xa = x.ldu(c), xb = xo.ldu(c);
+      block(p0, xa, xb, 0);
+    }
+  }
+  float own[8], oth[8];
+  {
+    const float4 l0 = g.logc.ld4(blk0), l1 = g.logc.ld4(blk1);
+    const float lc[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
+    const bool v0 = b0 < M4, v1 = nb > 1 && b0 + 1 < M4;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const bool v = k < 4 ? v0 : v1;
+      float ax, ay, bx, by;
+      f2::unpack(qa[k], ax, ay);
+      f2::unpack(qb[k], bx, by);
+      own[k] = v ? lc[k] - 0.5f * (ax + ay) : -INFINITY;
+      oth[k] = v ? lc[k] - 0.5f * (bx + by) : -INFINITY;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) oth[k] = __shfl_xor_sync(0xffffffffu, oth[k], 16);  // my particle, the other half's modes
+  if (nb > 1) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      r[k] = h ? oth[k] : own[k];
+      r[8 + k] = h ? own[k] : oth[k];
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      r[k] = h ? oth[k] : own[k];
+      r[4 + k] = h ? own[k] : oth[k];
+    }
+#pragma unroll
+    for (int k = 8; k < MIX_MAX_M; ++k) r[k] = -INFINITY;
+  }
+  float mx = r[0];
+#pragma unroll
+  for (int i = 1; i < MIX_MAX_M; ++i) mx = fmaxf(mx, r[i]);
+  float s = 0.f;
+#pragma unroll
+  for (int mb = 0; mb < MIX_MAX_M / 4; ++mb) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) r[4 * mb + i] = __expf(r[4 * mb + i] - mx);
+    s += (r[4 * mb] + r[4 * mb + 1]) + (r[4 * mb + 2] + r[4 * mb + 3]);
+  }
+  const float inv = 1.0f / s;
+#pragma unroll
+  for (int i = 0; i < MIX_MAX_M; ++i) r[i] *= inv;
+  return mx + __logf(s);
+}
+
 // log-density of a reference / prior block that may be a single Gaussian (the terminal cost)
 template <bool PIPE>
 __device__ __forceinline__ float gmm_logp_any(const GmmView& g, int d, int dp, const Col4& x) {
@@ -98,12 +189,17 @@ __device__ __forceinline__ float gmm_logp_any(const GmmView& g, int d, int dp, c
 }
 
 // ---- tensor-core side of the contraction (extends the drift-network policy; same tile, mbarrier and phase) --------
-template <int PREC>
+// VARIANT bit 0: chunk hand-off by mbarrier (else named barrier); bit 1: step-buffer release by mbarrier (else CTA
+// barrier); bit 2: two-particle quadratic forms (gmm_pass1_pair)
+template <int PREC, int VARIANT>
 struct MixTc : TcMlp<PREC> {
   using Base = TcMlp<PREC>;
   static constexpr uint32_t kRCol = 0, kDCol = 32;
   uint32_t lbo;  // bytes between the two 16-byte K chunks (modes 0-7 | 8-15) of an image part: 2 d_pad * 16
   uint32_t part_bytes;
+  uint64_t* ebar;  // the CTA's two "step buffer released" barriers
+  uint64_t* cbar;  // "columns [0, 64) of the tile are ready for the next contraction": one arrival per warp of the tile
+  uint32_t cphase;
 
   // r (16 responsibilities) -> fp16 (hi, lo) A operand `which` (0 target, 1 reference)
   __device__ __forceinline__ void store_r(int which, const float (&r)[MIX_MAX_M]) {
@@ -120,11 +216,19 @@ struct MixTc : TcMlp<PREC> {
   }
 
   // chunk c of both contractions -> columns [32, 64); images = shared-window addresses of the (hi | lo) blocks
+  // The hand-off is an mbarrier, not a named barrier: a warp that has stored its R rows / read its chunk arrives and
+  // goes on with its SIMT work; only the issuing thread waits for the tile's other warps.
   __device__ __forceinline__ void issue_chunk(int c, uint32_t tgt_img, uint32_t ref_img) {
     ptx::tmem_wait_st();
     ptx::tc_fence_before();
-    ptx::bar_sync(this->bar_id, this->bar_threads);
+    if constexpr (VARIANT & 1) {
+      __syncwarp();
+      if ((threadIdx.x & 31) == 0) ptx::mbar_arrive(cbar);
+    } else {
+      ptx::bar_sync(this->bar_id, this->bar_threads);
+    }
     if (this->issuer) {
+      if constexpr (VARIANT & 1) ptx::mbar_wait(cbar, cphase);
       ptx::tc_fence_after();
       const uint32_t idesc = ptx::make_idesc_f16(128, 16);
 #pragma unroll
@@ -139,6 +243,7 @@ struct MixTc : TcMlp<PREC> {
       }
       ptx::mma_commit(this->bar);
     }
+    cphase ^= 1u;
   }
   __device__ __forceinline__ void load_chunk(uint32_t (&m)[32]) {
     ptx::tmem_ld32(this->tm_lane + kDCol, m);
@@ -147,9 +252,11 @@ struct MixTc : TcMlp<PREC> {
 };
 
 // ---- the loop ------------------------------------------------------------------------------------------------------
-template <int PREC>
-__device__ __forceinline__ void rollout_body_mix(const RolloutArgs& a, float* smem, uint8_t* stage, MixTc<PREC>& mlp) {
-  constexpr bool PIPE = MixTc<PREC>::kPipe;
+template <int PREC, int VARIANT>
+__device__ __forceinline__ void rollout_body_mix(const RolloutArgs& a, float* smem, uint8_t* stage, MixTc<PREC, VARIANT>& mlp) {
+  constexpr bool PIPE = MixTc<PREC, VARIANT>::kPipe;
+  constexpr bool EBAR = (VARIANT & 2) != 0;
+  constexpr bool PAIR = (VARIANT & 4) != 0;
   const lrds_spec& s = a.s;
   const int NT = blockDim.x;
   const int tid = threadIdx.x;
@@ -176,9 +283,15 @@ __device__ __forceinline__ void rollout_body_mix(const RolloutArgs& a, float* sm
     stage_step(dst, s, SL, k, bar);
     ptx::bulk_g2s(dst + mix_off_r, rmix_g + (int64_t)k * s.ref_t.step_stride_mix_tc, SL.ref_mix_bytes, bar);
   };
+  // sbar[0..1]: "step buffer filled" (TMA transaction bytes); ebar[0..1] (behind the tile barriers of the kernel):
+  // "step buffer released", one arrival per warp.  No CTA-wide barrier inside the loop: tiles may drift apart by up
+  // to one step, which keeps their tensor-core waits out of phase.
+  uint64_t* ebar = mlp.ebar;
   if (tid == 0) {
     ptx::mbar_init(sbar, 1);
     ptx::mbar_init(sbar + 1, 1);
+    ptx::mbar_init(ebar, NT >> 5);
+    ptx::mbar_init(ebar + 1, NT >> 5);
     ptx::fence_mbar_init();
   }
   __syncthreads();
@@ -197,8 +310,10 @@ __device__ __forceinline__ void rollout_body_mix(const RolloutArgs& a, float* sm
   float rnd = 0.f;
 
   for (int k = 0; k < K; ++k) {
-    __syncthreads();  // every warp has finished step k-1, whose buffer the prefetch below overwrites
+    if constexpr (!EBAR) __syncthreads();
     if (tid == 0 && k + 1 < K) {
+      // every warp has released the buffer of step k-1, which the prefetch overwrites
+      if (EBAR && k >= 1) ptx::mbar_wait(ebar + ((k + 1) & 1), (uint32_t)((k - 1) >> 1) & 1u);
       ptx::mbar_expect_tx(sbar + ((k + 1) & 1), SL.buf_bytes);
       stage_step_mix(stage + SL.off_buf + ((k + 1) & 1) * SL.buf_bytes, k + 1, sbar + ((k + 1) & 1));
     }
@@ -217,9 +332,11 @@ __device__ __forceinline__ void rollout_body_mix(const RolloutArgs& a, float* sm
     mlp.template hidden<true>(row + LRDS_STEP_BIAS1, P.x);  // ends with the output GEMM complete: A region free
     {
       float r[MIX_MAX_M];
-      gmm_pass1_regs<PIPE>(tv, d, dp, P.x, r);
+      if constexpr (PAIR) gmm_pass1_pair(tv, d, dp, P.x, r);
+      else gmm_pass1_regs<PIPE>(tv, d, dp, P.x, r);
       mlp.store_r(0, r);
-      gmm_pass1_regs<PIPE>(rv, d, dp, P.x, r);
+      if constexpr (PAIR) gmm_pass1_pair(rv, d, dp, P.x, r);
+      else gmm_pass1_regs<PIPE>(rv, d, dp, P.x, r);
       mlp.store_r(1, r);
     }
     mlp.issue_chunk(0, tgt_img, ref_img);
@@ -251,11 +368,15 @@ __device__ __forceinline__ void rollout_body_mix(const RolloutArgs& a, float* sm
     }
     rnd += wcost * su2;
     rnd += wito * sito;
+    if constexpr (EBAR) {
+      __syncwarp();  // the last contraction of the step has completed (wait() above): this warp is done with the buffer
+      if ((tid & 31) == 0) ptx::mbar_arrive(ebar + (k & 1));
+    }
   }
   // terminal cost: rnd += reference_log_prob(x) - terminal_unnorm_log_prob(x)   (oc.py:505, 645)
   const float lref = gmm_logp_any<PIPE>(gmm_at(s.ref_0, 0), d, dp, P.x);
   float rt[MIX_MAX_M];
-  const float ltgt = clipf(gmm_pass1_regs<PIPE>(tv, d, dp, P.x, rt), s.clip_target);
+  const float ltgt = clipf(PAIR ? gmm_pass1_pair(tv, d, dp, P.x, rt) : gmm_pass1_regs<PIPE>(tv, d, dp, P.x, rt), s.clip_target);
   rnd += lref - ltgt;
 
   if (live) {
@@ -266,7 +387,7 @@ __device__ __forceinline__ void rollout_body_mix(const RolloutArgs& a, float* sm
 }
 
 // shared memory: [weight image | mbarriers + TMEM slot | operand stage | particle columns]
-template <int PREC>
+template <int PREC, int VARIANT>
 __global__ void __launch_bounds__(MIX_MAX_WARPS * 32, 1)
 rollout_mix_kernel(const RolloutArgs a, const uint8_t* __restrict__ image, const uint32_t tmem_cols) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -275,11 +396,13 @@ rollout_mix_kernel(const RolloutArgs a, const uint8_t* __restrict__ image, const
   uint8_t* img = smem_raw;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + TL.bytes);  // [0] image, [1 + t] tile t
   uint32_t* slot = reinterpret_cast<uint32_t*>(smem_raw + TL.bytes + 48);
-  uint8_t* stage = smem_raw + TL.bytes + TC_TAIL_BYTES;
+  uint64_t* xbars = reinterpret_cast<uint64_t*>(smem_raw + TL.bytes + TC_TAIL_BYTES);  // [0..3] chunk hand-off per tile, [4..5] buffer release
+  uint8_t* stage = smem_raw + TL.bytes + TC_TAIL_BYTES + MIX_TAIL_BYTES;
   float* cols = reinterpret_cast<float*>(stage + ((stage_layout(a.s, 2, true).total + 15u) & ~15u));
   if (warp == 0) ptx::tmem_alloc(slot, tmem_cols);
   if (tid == 0) {
     for (int i = 0; i < 5; ++i) ptx::mbar_init(bars + i, 1);
+    for (int t = 0; t < 4; ++t) ptx::mbar_init(xbars + t, (uint32_t)max(1, min(4, nwarps - 4 * t)));
     ptx::fence_mbar_init();
   }
   ptx::tc_fence_before();
@@ -293,7 +416,10 @@ rollout_mix_kernel(const RolloutArgs a, const uint8_t* __restrict__ image, const
   const uint32_t tmem = *slot;
   const int tile = warp >> 2;
   const int tile_warps = min(4, nwarps - 4 * tile);
-  MixTc<PREC> mlp;
+  MixTc<PREC, VARIANT> mlp;
+  mlp.cbar = xbars + tile;
+  mlp.cphase = 0;
+  mlp.ebar = xbars + 4;
   mlp.L = TL;
   mlp.img = img;
   mlp.img_s = ptx::smem_u32(img);
@@ -305,7 +431,7 @@ rollout_mix_kernel(const RolloutArgs a, const uint8_t* __restrict__ image, const
   mlp.bar_threads = tile_warps * 32;
   mlp.issuer = (tid & 127) == 0;
   mlp.dp = a.s.mlp.d_pad;
-  rollout_body_mix<PREC>(a, cols, stage, mlp);
+  rollout_body_mix<PREC, VARIANT>(a, cols, stage, mlp);
   ptx::tc_fence_before();
   __syncthreads();
   if (warp == 0) ptx::tmem_dealloc(tmem, tmem_cols);
@@ -317,7 +443,7 @@ inline bool plan_rollout_mix(const lrds_spec& s, int smem_cap, int sms, TcPlan* 
   const TcLayout TL = tc_layout(s.d, s.mlp.num_hidden, s.precision);
   if (TL.tile_cols != 128 || TL.parts * TL.a_cols < 64) return false;
   const ColLayout CL = col_layout(s, true);
-  const size_t fixed = (size_t)TL.bytes + TC_TAIL_BYTES + ((stage_layout(s, 2, true).total + 15u) & ~15u);
+  const size_t fixed = (size_t)TL.bytes + TC_TAIL_BYTES + MIX_TAIL_BYTES + ((stage_layout(s, 2, true).total + 15u) & ~15u);
   const size_t per_warp = (size_t)CL.total * 32 * sizeof(float);
   if (fixed + per_warp > (size_t)smem_cap) return false;
   int wmax = (int)(((size_t)smem_cap - fixed) / per_warp);

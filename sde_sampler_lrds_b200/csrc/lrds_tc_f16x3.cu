@@ -1,13 +1,16 @@
 // Tensor-core rollout kernels of one precision (own translation unit: the precisions compile in parallel), plus the
 // kernel that also runs the mixture-score contractions on the tensor core (lrds_rollout_mix.cuh).
+#include <cstdlib>
+
 #include "lrds_rollout_mix.cuh"
 #include "lrds_tc_launch.cuh"
 
 namespace lrds {
 template int launch_prec<LRDS_PRECISION_F16X3>(const RolloutArgs&, const TcPlan&, cudaStream_t, char*, size_t);
 
-int launch_mix_f16x3(const RolloutArgs& a, const TcPlan& p, cudaStream_t st, char* err, size_t n) {
-  auto kernel = rollout_mix_kernel<LRDS_PRECISION_F16X3>;
+template <int VARIANT>
+static int launch_mix_variant(const RolloutArgs& a, const TcPlan& p, cudaStream_t st, char* err, size_t n) {
+  auto kernel = rollout_mix_kernel<LRDS_PRECISION_F16X3, VARIANT>;
   cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
   if (e == cudaSuccess) {
     kernel<<<p.grid, p.warps * 32, p.smem, st>>>(a, static_cast<const uint8_t*>(a.s.mlp.tc_image), p.tmem_cols);
@@ -19,5 +22,17 @@ int launch_mix_f16x3(const RolloutArgs& a, const TcPlan& p, cudaStream_t st, cha
     return LRDS_ERR_CUDA;
   }
   return LRDS_OK;
+}
+
+int launch_mix_f16x3(const RolloutArgs& a, const TcPlan& p, cudaStream_t st, char* err, size_t n) {
+  const char* v = getenv("LRDS_MIX_VARIANT");  // tuning switch for the synchronisation scheme (default: mbarriers)
+  switch (v ? atoi(v) : 4) {
+    case 0: return launch_mix_variant<0>(a, p, st, err, n);
+    case 1: return launch_mix_variant<1>(a, p, st, err, n);
+    case 2: return launch_mix_variant<2>(a, p, st, err, n);
+    case 3: return launch_mix_variant<3>(a, p, st, err, n);
+    case 6: return launch_mix_variant<6>(a, p, st, err, n);
+    default: return launch_mix_variant<4>(a, p, st, err, n);
+  }
 }
 }  // namespace lrds
