@@ -125,9 +125,9 @@ typedef struct {
   int64_t step_stride_param; /* floats between consecutive steps of mu / ivar (M * d_pad) */
   int64_t step_stride_sn;    /* floats between consecutive steps of sn (8 ceil(M/4) * d_pad) */
   const void* mix_tc;        /* optional (M > 1; NULL = evaluate the score contraction on the SIMT pipes): tensor-core operand
-                              * of  score_j = sum_m r_m mu_mj/var_mj - x_j sum_m r_m/var_mj.  Per step one block of
+                              * of  score_j = x_j sum_m r_m (-1/var_mj) + sum_m r_m mu_mj/var_mj.  Per step one block of
                               * lrds_gmm_mix_tc_bytes(M, d_pad) bytes: the matrix B[n][m], rows n = 16 c + i over the 8-dim
-                              * chunks c (i < 8: 1/var_{m,8c+i}; i >= 8: mu/var_{m,8c+i-8}), multiplied by the power of two
+                              * chunks c (i < 8: -1/var_{m,8c+i}; i >= 8: mu/var_{m,8c+i-8}), multiplied by the power of two
                               * that puts its largest entry into [2^14, 2^15) and split into fp16 hi | lo parts, each in the
                               * K-major no-swizzle tcgen05 layout [m/8][n][m%8] with m padded to a multiple of 16; then 16
                               * bytes whose first float is the un-scale.  16-byte aligned. */

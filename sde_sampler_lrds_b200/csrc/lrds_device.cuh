@@ -37,6 +37,7 @@ struct Col4 {
   __device__ __forceinline__ float4 ld4(int c) const { return *reinterpret_cast<const float4*>(p + c * stride); }
   __device__ __forceinline__ ulonglong2 ldu(int c) const { return *reinterpret_cast<const ulonglong2*>(p + c * stride); }
   __device__ __forceinline__ void st4(int c, const float4& v) const { *reinterpret_cast<float4*>(p + c * stride) = v; }
+  __device__ __forceinline__ void stu(int c, const ulonglong2& v) const { *reinterpret_cast<ulonglong2*>(p + c * stride) = v; }
 };
 
 // clip bounds arrive as "<= 0: no clip"; kernels turn that into +inf once so that a clip is two FMNMX
@@ -62,6 +63,17 @@ __device__ __forceinline__ u64 mul(u64 a, u64 b) {
   u64 d;
   asm("mul.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
   return d;
+}
+__device__ __forceinline__ u64 pk(float a) { return pack(a, a); }
+__device__ __forceinline__ float hsum1(u64 a) {
+  float x, y;
+  unpack(a, x, y);
+  return x + y;
+}
+// (hi, lo) of a pair for the 3-pass operand splits: hi = the top 11 significand bits of each lane, lo = v - hi (exact)
+__device__ __forceinline__ void split(u64 v, u64& hi, u64& lo) {
+  hi = v & 0xFFFFE000FFFFE000ull;
+  lo = fma(hi, pk(-1.0f), v);
 }
 __device__ __forceinline__ float hsum(u64 a, u64 b) {  // (a.x + a.y) + (b.x + b.y)
   float x, y, z, w;
@@ -109,6 +121,29 @@ __device__ __forceinline__ void gelu_exact2(float va, float vb, float& ga, float
   const u64 r = f2::pack(copysignf(1.0f - ea, va), copysignf(1.0f - eb, vb));
   const u64 h = f2::mul(f2::pack(half_scale, half_scale), f2::pack(va, vb));
   f2::unpack(f2::fma(h, r, h), ga, gb);
+}
+
+// The same GELU for a pair in the form  s GELU(v) = s relu(v) + nt (s/2) 2^(t Q(t)),  nt = -t = -min(|v|, 4 sqrt 2):
+// no sign transfer and no 1 - e; the polynomial runs in nt (P(nt) = -Q(-nt)) and s/2 = 2^k2 enters through the
+// exponent.  `s` is a power of two (1, or the fp16 operand scale of the tensor-core path).
+__device__ __forceinline__ u64 gelu_pair(u64 v2, float k2, float s) {
+  float va, vb;
+  f2::unpack(v2, va, vb);
+  const u64 nt = f2::pack(fmaxf(-fabsf(va), -5.656854249f), fmaxf(-fabsf(vb), -5.656854249f));
+  u64 q = f2::pk(-8.857967404e-06f);
+  q = f2::fma(q, nt, f2::pk(-5.769414971e-05f));
+  q = f2::fma(q, nt, f2::pk(4.069866499e-04f));
+  q = f2::fma(q, nt, f2::pk(7.363130652e-03f));
+  q = f2::fma(q, nt, f2::pk(5.266660834e-02f));
+  q = f2::fma(q, nt, f2::pk(-4.591643231e-01f));
+  q = f2::fma(q, nt, f2::pk(1.151108839e+00f));
+  float pa, pb, ea, eb;
+  f2::unpack(f2::fma(q, nt, f2::pk(k2)), pa, pb);
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ea) : "f"(pa));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(eb) : "f"(pb));
+  u64 r = f2::pack(fmaxf(va, 0.f), fmaxf(vb, 0.f));
+  if (s != 1.0f) r = f2::mul(r, f2::pk(s));
+  return f2::fma(nt, f2::pack(ea, eb), r);
 }
 
 // ---------------------------------------------------------------------------------------------------

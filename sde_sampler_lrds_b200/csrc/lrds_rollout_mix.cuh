@@ -203,16 +203,19 @@ struct MixTc : TcMlp<PREC> {
 
   // r (16 responsibilities) -> fp16 (hi, lo) A operand `which` (0 target, 1 reference)
   __device__ __forceinline__ void store_r(int which, const float (&r)[MIX_MAX_M]) {
-    uint32_t p[8];
-    float hi[MIX_MAX_M];
+    uint32_t ph[8], pl[8];
 #pragma unroll
-    for (int i = 0; i < MIX_MAX_M; ++i) hi[i] = __uint_as_float(__float_as_uint(r[i]) & 0xFFFFE000u);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) p[i] = ptx::pack_f16x2(hi[2 * i], hi[2 * i + 1]);
-    ptx::tmem_st8(this->tm_lane + kRCol + which * 16, p);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) p[i] = ptx::pack_f16x2(r[2 * i] - hi[2 * i], r[2 * i + 1] - hi[2 * i + 1]);
-    ptx::tmem_st8(this->tm_lane + kRCol + which * 16 + 8, p);
+    for (int i = 0; i < 8; ++i) {
+      u64 hi, lo;
+      f2::split(f2::pack(r[2 * i], r[2 * i + 1]), hi, lo);
+      float h0, h1, l0, l1;
+      f2::unpack(hi, h0, h1);
+      f2::unpack(lo, l0, l1);
+      ph[i] = ptx::pack_f16x2(h0, h1);
+      pl[i] = ptx::pack_f16x2(l0, l1);
+    }
+    ptx::tmem_st8(this->tm_lane + kRCol + which * 16, ph);
+    ptx::tmem_st8(this->tm_lane + kRCol + which * 16 + 8, pl);
   }
 
   // chunk c of both contractions -> columns [32, 64); images = shared-window addresses of the (hi | lo) blocks
@@ -340,34 +343,55 @@ __device__ __forceinline__ void rollout_body_mix(const RolloutArgs& a, float* sm
       mlp.store_r(1, r);
     }
     mlp.issue_chunk(0, tgt_img, ref_img);
-    float su2 = 0.f, sito = 0.f;
+    // The integrator update on packed fp32x2 pairs of dims.  The images hold -1/var, so a score is one FFMA2; their
+    // power-of-two un-scales are folded into the ScoreCtrl factor / the clip bound (target) and into the FFMA that
+    // adds the control (reference).  Padded dims need no masks: their image rows, output weights, biases and noise
+    // are zero, so u = scores = z = 0 and x stays 0.
+    const u64 A2 = f2::pk(A), B2 = f2::pk(Bc), C2 = f2::pk(Cc), usr2 = f2::pk(usr);
+    const u64 gs2 = f2::pk((cc.scale_score * gamma) * ust);
+    const float bts = cc.bound_score / ust;
+    u64 su2 = 0, sito = 0;
     for (int c = 0; c < nchunk; ++c) {
       const int j0 = c * JC;
       uint32_t m[32];
       mlp.wait();
       mlp.load_chunk(m);
       if (c + 1 < nchunk) mlp.issue_chunk(c + 1, tgt_img, ref_img);
-      float xr[JC], u[JC], z[JC], xn[JC];
-      lrds::load_chunk(P.x, j0, xr);
-      mlp.out_chunk(j0, u);
+      const ulonglong2 xa = P.x.ldu(2 * c), xb = P.x.ldu(2 * c + 1);
+      const u64 X[4] = {xa.x, xa.y, xb.x, xb.y};
+      u64 U[4], XN[4];
+      float z[JC];
+      mlp.out_chunk2(j0, U);
       noise_chunk(a, k, b, j0, z);
 #pragma unroll
-      for (int i = 0; i < JC; ++i) {
-        const float ts = fmaf(-xr[i], __uint_as_float(m[i]), __uint_as_float(m[8 + i])) * ust;
-        const float rs = fmaf(-xr[i], __uint_as_float(m[16 + i]), __uint_as_float(m[24 + i])) * usr;
-        float v = clipb(u[i], cc.bound_model);
-        v = v + (cc.scale_score * clipb(ts, cc.bound_score)) * gamma;
-        v = (j0 + i < d) ? v : 0.f;
-        su2 = fmaf(v, v, su2);
-        sito = fmaf(v, z[i], sito);
-        xn[i] = (A * xr[i] + Bc * (rs + v)) + Cc * z[i];
-        if (j0 + i >= d) xn[i] = 0.f;
+      for (int q = 0; q < 4; ++q) {
+        const u64 ta = f2::pack(__uint_as_float(m[2 * q]), __uint_as_float(m[2 * q + 1]));
+        const u64 tb = f2::pack(__uint_as_float(m[8 + 2 * q]), __uint_as_float(m[9 + 2 * q]));
+        const u64 ra = f2::pack(__uint_as_float(m[16 + 2 * q]), __uint_as_float(m[17 + 2 * q]));
+        const u64 rb = f2::pack(__uint_as_float(m[24 + 2 * q]), __uint_as_float(m[25 + 2 * q]));
+        float t0, t1, u0, u1;
+        f2::unpack(f2::fma(X[q], ta, tb), t0, t1);  // raw target score (image units)
+        f2::unpack(U[q], u0, u1);
+        const u64 tsc = f2::pack(clipb(t0, bts), clipb(t1, bts));
+        const u64 uc = f2::pack(clipb(u0, cc.bound_model), clipb(u1, cc.bound_model));
+        const u64 v = f2::fma(tsc, gs2, uc);  // control u
+        const u64 z2 = f2::pack(z[2 * q], z[2 * q + 1]);
+        su2 = f2::fma(v, v, su2);
+        sito = f2::fma(v, z2, sito);
+        const u64 rv2 = f2::fma(f2::fma(X[q], ra, rb), usr2, v);  // reference score + u
+        XN[q] = f2::fma(C2, z2, f2::fma(A2, X[q], f2::mul(B2, rv2)));
       }
-      store_chunk(P.x, j0, xn);
-      if (a.traj_out != nullptr && live) store_traj(a, k + 1, b, j0, xn);
+      P.x.stu(2 * c, ulonglong2{XN[0], XN[1]});
+      P.x.stu(2 * c + 1, ulonglong2{XN[2], XN[3]});
+      if (a.traj_out != nullptr && live) {
+        float xn[JC];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) f2::unpack(XN[q], xn[2 * q], xn[2 * q + 1]);
+        store_traj(a, k + 1, b, j0, xn);
+      }
     }
-    rnd += wcost * su2;
-    rnd += wito * sito;
+    rnd += wcost * f2::hsum1(su2);
+    rnd += wito * f2::hsum1(sito);
     if constexpr (EBAR) {
       __syncwarp();  // the last contraction of the step has completed (wait() above): this warp is done with the buffer
       if ((tid & 31) == 0) ptx::mbar_arrive(ebar + (k & 1));

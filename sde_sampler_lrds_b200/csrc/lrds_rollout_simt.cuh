@@ -256,9 +256,11 @@ __device__ __forceinline__ void noise_chunk(const RolloutArgs& a, int step, int 
     z[0] = z4[0]; z[1] = z4[1]; z[2] = z4[2]; z[3] = z4[3];
     normals4(a.seed, pidx, (uint32_t)step, (uint32_t)(j0 >> 2) + 1u, 0u, z4);
     z[4] = z4[0]; z[5] = z4[1]; z[6] = z4[2]; z[7] = z4[3];
+    if (j0 + JC > a.s.d) {  // only the last chunk holds padded dims
 #pragma unroll
-    for (int c = 0; c < JC; ++c)
-      if (j0 + c >= a.s.d) z[c] = 0.f;
+      for (int c = 0; c < JC; ++c)
+        if (j0 + c >= a.s.d) z[c] = 0.f;
+    }
   }
 }
 

@@ -225,15 +225,19 @@ struct TcMlp {
   __device__ __forceinline__ void store16_half(int c0, const float (&v)[16]) {
     uint32_t r[8];
     if (kF16) {
-      float hi[16];
+      uint32_t rl[8];
 #pragma unroll
-      for (int i = 0; i < 16; ++i) hi[i] = __uint_as_float(split_hi(v[i]));
-#pragma unroll
-      for (int i = 0; i < 8; ++i) r[i] = ptx::pack_f16x2(hi[2 * i], hi[2 * i + 1]);
+      for (int i = 0; i < 8; ++i) {
+        u64 hi, lo;
+        f2::split(f2::pack(v[2 * i], v[2 * i + 1]), hi, lo);
+        float h0, h1, l0, l1;
+        f2::unpack(hi, h0, h1);
+        f2::unpack(lo, l0, l1);
+        r[i] = ptx::pack_f16x2(h0, h1);
+        rl[i] = ptx::pack_f16x2(l0, l1);
+      }
       ptx::tmem_st8(tm_lane + a_col(0) + c0, r);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) r[i] = ptx::pack_f16x2(v[2 * i] - hi[2 * i], v[2 * i + 1] - hi[2 * i + 1]);
-      ptx::tmem_st8(tm_lane + a_col(1) + c0, r);
+      ptx::tmem_st8(tm_lane + a_col(1) + c0, rl);
     } else {
 #pragma unroll
       for (int i = 0; i < 8; ++i) r[i] = ptx::pack_bf16x2(v[2 * i], v[2 * i + 1]);
@@ -267,9 +271,46 @@ struct TcMlp {
     }
   }
 
+  // F16X3: the whole epilogue on packed fp32x2 arithmetic
+  template <bool GLOBAL_BIAS>
+  __device__ __forceinline__ void epilogue_f16(const float* __restrict__ bias, int layer) {
+    const u64 us2 = f2::pk(unscale(layer));
+#pragma unroll 1
+    for (int c0 = 0; c0 < C; c0 += 32) {
+      uint32_t r[32];
+      ptx::tmem_ld32(tm_lane + d_col() + c0, r);
+      ptx::tmem_wait_ld();
+      const float4* b4 = reinterpret_cast<const float4*>(bias + c0);  // warp-uniform, 16-byte aligned
+      uint32_t ph[16], pl[16];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float4 b = GLOBAL_BIAS ? __ldg(b4 + i) : b4[i];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const u64 acc = f2::pack(__uint_as_float(r[4 * i + 2 * e]), __uint_as_float(r[4 * i + 2 * e + 1]));
+          const u64 v = f2::fma(acc, us2, e ? f2::pack(b.z, b.w) : f2::pack(b.x, b.y));
+          const u64 g = gelu_pair(v, 5.0f, TC_ACT_SCALE);  // TC_ACT_SCALE / 2 = 2^5
+          u64 hi, lo;
+          f2::split(g, hi, lo);
+          float h0, h1, l0, l1;
+          f2::unpack(hi, h0, h1);
+          f2::unpack(lo, l0, l1);
+          ph[2 * i + e] = ptx::pack_f16x2(h0, h1);
+          pl[2 * i + e] = ptx::pack_f16x2(l0, l1);
+        }
+      }
+      ptx::tmem_st16(tm_lane + a_col(0) + c0 / 2, ph);
+      ptx::tmem_st16(tm_lane + a_col(1) + c0 / 2, pl);
+    }
+  }
+
   // accumulator (64 columns) [* un-scale] + bias -> GELU -> A operand of the next layer
   template <bool GLOBAL_BIAS>
   __device__ __forceinline__ void epilogue(const float* __restrict__ bias, int layer) {
+    if constexpr (kF16) {
+      epilogue_f16<GLOBAL_BIAS>(bias, layer);
+      return;
+    }
     const float us = kF16 ? unscale(layer) : 1.0f;
     const float gs = kF16 ? 0.5f * TC_ACT_SCALE : 0.5f;
 #pragma unroll 1
@@ -327,6 +368,20 @@ struct TcMlp {
     else epilogue<false>(bh + (L.nh - 1) * C, L.nh);
     issue(L.off_out, C, L.Nout);
     wait();
+  }
+
+  // the same as four (dim 2q, dim 2q+1) pairs (F16X3)
+  __device__ __forceinline__ void out_chunk2(int j0, u64 (&out)[JC / 2]) {
+    uint32_t r[8];
+    ptx::tmem_ld8(tm_lane + d_col() + j0, r);
+    ptx::tmem_wait_ld();
+    const ulonglong2* b2 = reinterpret_cast<const ulonglong2*>(img + L.off_bout + j0 * 4);
+    const ulonglong2 a = b2[0], b = b2[1];
+    const u64 us2 = f2::pk(unscale(L.nh + 1));
+    out[0] = f2::fma(f2::pack(__uint_as_float(r[0]), __uint_as_float(r[1])), us2, a.x);
+    out[1] = f2::fma(f2::pack(__uint_as_float(r[2]), __uint_as_float(r[3])), us2, a.y);
+    out[2] = f2::fma(f2::pack(__uint_as_float(r[4]), __uint_as_float(r[5])), us2, b.x);
+    out[3] = f2::fma(f2::pack(__uint_as_float(r[6]), __uint_as_float(r[7])), us2, b.y);
   }
 
   __device__ __forceinline__ void out_chunk(int j0, float (&out)[JC]) {

@@ -52,14 +52,14 @@ def gmm_block(loc: torch.Tensor, var: torch.Tensor, weights: torch.Tensor | None
 
 def gmm_mix_tc_image(loc: torch.Tensor, var: torch.Tensor, d_pad: int) -> torch.Tensor:
     """Tensor-core operand of the mixture-score contraction (lrds_gmm.mix_tc, include/lrds_b200.h): per block the
-    matrix B[n][m] with rows n = 16 c + i over 8-dim chunks c (i < 8: 1/var_{m, 8c+i}; i >= 8: mu/var_{m, 8c+i-8}),
+    matrix B[n][m] with rows n = 16 c + i over 8-dim chunks c (i < 8: -1/var_{m, 8c+i}; i >= 8: mu/var_{m, 8c+i-8}),
     scaled by the power of two that puts its largest entry into [2^14, 2^15) and split into fp16 (hi, lo), each part
     in the K-major no-swizzle tcgen05 layout [m/8][n][m%8], followed by 16 bytes holding the float un-scale."""
     lead = loc.shape[:-2]
     M, d = loc.shape[-2:]
     Mp = (M + 15) // 16 * 16
     iv = 1.0 / var.double()
-    a, b = iv.float(), (loc.double() * iv).float()
+    a, b = (-iv).float(), (loc.double() * iv).float()
     F = torch.nn.functional
     T = torch.stack([F.pad(t, (0, d_pad - d, 0, Mp - M)).reshape(*lead, Mp, d_pad // 8, 8) for t in (a, b)], dim=-2)
     V = T.reshape(*lead, Mp, 2 * d_pad)                       # [.., m, n]
