@@ -1,11 +1,12 @@
 #!/usr/bin/env python
 """Benchmark of the fused trajectory rollout (BASELINE.json metric: particle-steps/s).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--precision tf32x3|fp32|tf32|bf16]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--precision f16x3|tf32x3|fp32|tf32|bf16]
 
-The headline number is measured in the fp32-grade mode (tf32x3: the drift network on tcgen05 tensor cores with the
-3-pass tf32 split, parity-tested to the north-star tolerance); the reduced-precision bf16 mode is timed in the same
-run and reported separately under "fast_mode" with its tolerance.
+The headline number is measured in the fp32-grade mode f16x3 (drift network AND mixture-score contractions on tcgen05
+tensor cores with the 3-pass fp16 (hi, lo) split of power-of-two scaled operands; parity-tested to the north-star
+tolerance like tf32x3 and the fp32 SIMT anchor).  --fast-mode additionally times the reduced-precision bf16 kernel
+and reports it separately with its tolerance.
 
 A "step" is one complete rollout of the workload's particle batch through all grid times (the quantity the
 reference times as eval/sample_time, solver/oc.py:148-158) followed by the estimator reduction; under
@@ -34,8 +35,10 @@ B_PER_GPU, K_STEPS, DIM, MODES = 65536, 200, 50, 16
 FLOPS_PER_PARTICLE_STEP = (256 * DIM + 16384) + 2 * 8 * MODES * DIM
 METRIC, UNIT = "particle_steps_per_sec", "particle-steps/s"
 CPU_SAMPLE_B = 16384
-# FMA-pipe lane-operations per particle-step of the tf32x3 kernel, counted by ncu (profiles/r01_*_summary.md): the
-# SIMT work (mixture quadratic forms, erf GELU, Philox + Box-Muller, integrator) that bounds this path, DESIGN.md.
+# Executed warp-instructions per particle-step of the f16x3 benchmark kernel, counted by ncu
+# (profiles/r01_mix_summary.md: smsp__inst_executed.sum / (B K)): the SIMT work (mixture quadratic forms, erf GELU,
+# Philox + Box-Muller, integrator) that bounds this path; used for the issue-slot figure in "roofline".
+WARP_INSTR_PER_PARTICLE_STEP = {"f16x3": 3.704e9 / (B_PER_GPU * K_STEPS)}
 FAST_MODE_TOLERANCE = "log Z within 5e-2 abs, 99% of log-weights within 1e-2 rel (tests/test_rollout_parity_gpu.py)"
 
 
@@ -227,7 +230,7 @@ def run_ours(args):
 
     # ---- reduced-precision fast mode, reported separately ------------------------------------------------------
     fast = None
-    if args.precision in ("tf32x3", "f16x3") and not args.no_fast_mode:
+    if args.fast_mode:
         built_fast = Built(case, dev, "bf16")
         for w in range(3):
             built_fast.simulate(x0, None, seed=4000 + w, particle_offset=offset)
@@ -297,6 +300,15 @@ def run_ours(args):
                      "flops_per_particle_step": FLOPS_PER_PARTICLE_STEP},
         "check": {"log_norm_const_is": m["log_norm_const_is"], "elbo": m["elbo"], "ess": m["effective_sample_size"]},
     }
+    wi = WARP_INSTR_PER_PARTICLE_STEP.get(args.precision)
+    if wi is not None and clocks.get("sm_mhz"):
+        # explanatory: the kernel is bound by SIMT instruction issue, not by the tensor pipe
+        sms = torch.cuda.get_device_properties(dev).multi_processor_count
+        issued = wi * B * K_STEPS / (kern_ms * 1e-3)
+        slots = sms * 4 * clocks["sm_mhz"] * 1e6
+        line["roofline"]["simt_issue"] = {"achieved": issued / 1e9, "peak": slots / 1e9, "unit": "G warp-instr/s",
+                                          "frac": issued / slots, "warp_instr_per_particle_step": wi,
+                                          "source": "ncu smsp__inst_executed.sum (profiles/r01_mix_summary.md) / live kernel time"}
     if fast is not None:
         line["fast_mode"] = fast
     if cpu_value is not None:
@@ -314,8 +326,9 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default="tf32x3", choices=["fp32", "tf32x3", "f16x3", "tf32", "bf16"])
-    ap.add_argument("--no-fast-mode", action="store_true")
+    ap.add_argument("--precision", default="f16x3", choices=["fp32", "tf32x3", "f16x3", "tf32", "bf16"])
+    ap.add_argument("--fast-mode", action="store_true", help="also time the reduced-precision bf16 kernel")
+    ap.add_argument("--no-fast-mode", action="store_true", help=argparse.SUPPRESS)  # accepted for older command lines
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

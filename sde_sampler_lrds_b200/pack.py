@@ -18,11 +18,12 @@ from .distr.gauss import GMM
 from .models.mlp import FourierMLP, TimeEmbed
 from .models.reparam import ClippedCtrl, ScoreCtrl
 
-_DEFAULT_PRECISION = "fp32"
+_DEFAULT_PRECISION = "f16x3"
 
 
 def set_default_precision(name: str):
-    """'fp32' (SIMT parity anchor), 'tf32x3' (tcgen05, fp32-equivalent) or 'bf16' (reduced-precision fast mode)."""
+    """'f16x3' (default: tcgen05 with the 3-pass fp16 split, fp32-grade), 'tf32x3' (the same with tf32 operands),
+    'fp32' (SIMT parity anchor), or the reduced-precision fast modes 'tf32' / 'bf16'."""
     global _DEFAULT_PRECISION
     if name not in N.PRECISIONS:
         raise ValueError(f"unknown precision {name!r}")

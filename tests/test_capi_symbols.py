@@ -1,6 +1,7 @@
 """CPU: the C-ABI library builds, loads, and exports every symbol include/lrds_b200.h declares; argument
 validation answers without a GPU."""
 import ctypes as C
+import math
 import os
 import re
 
@@ -23,7 +24,7 @@ def test_library_exports_every_declared_symbol():
 def test_struct_sizes_match_header():
     # field-by-field mirror of include/lrds_b200.h (natural alignment, no packing pragmas)
     assert C.sizeof(N.Mlp) == 16 + 6 * 8
-    assert C.sizeof(N.Gmm) == 8 + 4 * 8 + 24
+    assert C.sizeof(N.Gmm) == 8 + 4 * 8 + 24 + 16
     assert C.sizeof(N.Phi4) == 16
     assert C.sizeof(N.LogReg) == 16 + 24 + 24
     assert C.sizeof(N.Distr) == 8 + C.sizeof(N.Gmm) + C.sizeof(N.Phi4) + C.sizeof(N.LogReg)
@@ -39,3 +40,32 @@ def test_invalid_arguments_are_rejected_without_a_gpu():
     assert lib.lrds_rollout(C.byref(spec), None, None, 0, 0, None, None, None, None) == -1
     assert lib.lrds_estimator_blocks(1) == 1 and lib.lrds_estimator_blocks(8193) == 2
     assert lib.lrds_estimator_partials(None, 0, None, None, None) == -1
+
+
+def test_mixture_tensor_core_image_layout():
+    """lrds_gmm.mix_tc (include/lrds_b200.h): B[n][m] with rows n = 16 c + i (i < 8: -1/var, i >= 8: mu/var of dim
+    8 c + i % 8), power-of-two scaled, fp16 hi | lo parts in the K-major [m/8][n][m%8] layout, un-scale in the tail."""
+    import torch
+    from sde_sampler_lrds_b200.distr.base import gmm_mix_tc_image
+    torch.manual_seed(0)
+    S, M, d, dp = 3, 5, 11, 16
+    loc, var = torch.randn(S, M, d) * 7, torch.rand(S, M, d) * 2 + 0.05
+    img = gmm_mix_tc_image(loc, var, dp)
+    lib = N.lib()
+    lib.lrds_gmm_mix_tc_bytes.restype = C.c_int64
+    nbytes = lib.lrds_gmm_mix_tc_bytes(M, dp)
+    assert img.shape == (S, nbytes) and img.dtype == torch.uint8 and nbytes % 16 == 0
+    part = (nbytes - 16) // 2
+    for s in range(S):
+        unscale = img[s, 2 * part:2 * part + 4].view(torch.float32).item()
+        assert unscale > 0 and math.log2(unscale) == round(math.log2(unscale))
+        hi = img[s, :part].view(torch.float16).float().reshape(2, 2 * dp, 8)      # [m/8][n][m%8], M padded to 16
+        lo = img[s, part:2 * part].view(torch.float16).float().reshape(2, 2 * dp, 8)
+        Bm = ((hi + lo) * unscale).permute(0, 2, 1).reshape(16, 2 * dp)            # [m][n]
+        assert hi.abs().max() < 2 ** 15 and hi.abs().max() >= 2 ** 14
+        for m in range(16):
+            for n in range(2 * dp):
+                c, i = divmod(n, 16)
+                j = 8 * c + i % 8
+                want = 0.0 if (m >= M or j >= d) else (-1.0 / var[s, m, j] if i < 8 else loc[s, m, j] / var[s, m, j]).item()
+                assert abs(Bm[m, n].item() - want) <= 2.0 ** -20 * max(abs(want), 2.0 ** -10), (s, m, n)

@@ -78,14 +78,15 @@ def test_make_model_evaluate(solver_type, kw, device):
     assert abs(got.metrics["eval/lv_loss"] - want["eval/lv_loss"]) < 1e-3 * max(1, want["eval/lv_loss"])
 
 
-def test_results_do_not_depend_on_how_particles_are_sharded(device):
+@pytest.mark.parametrize("precision", ["tf32x3", "f16x3"])
+def test_results_do_not_depend_on_how_particles_are_sharded(device, precision):
     """Counter-based noise keyed by the global particle index: integrating [0, B) in one launch equals integrating
     [0, B/2) and [B/2, B) as two ranks would (particle_offset), bit for bit."""
     from tests.cases import CASES, initial_state
     from tests.product_builders import Built
     case = CASES["ei_many_modes"]()
     x0 = initial_state(case)
-    built = Built(case, device, "tf32x3")
+    built = Built(case, device, precision)
     xa, ra, _ = built.simulate(x0, None, seed=77, particle_offset=1000)
     h = x0.shape[0] // 2
     xb0, rb0, _ = built.simulate(x0[:h], None, seed=77, particle_offset=1000)
