@@ -213,7 +213,7 @@ def run_ours(args):
         scratch = torch.empty(8 * (blocks + 1), device=dev, dtype=torch.float64)
         out = torch.empty(8, device=dev, dtype=torch.float64)
         N.check(N.lib().lrds_estimator_partials(N.ptr(r), r.numel(), N.ptr(out), N.ptr(scratch), N.stream_ptr(dev)))
-        last = gather_and_merge(out, group) if group is not None else out
+        last = gather_and_merge(out, group, on_device=True) if group is not None else out
         c.record()
     barrier()
     launches = N.launch_count() - launches0

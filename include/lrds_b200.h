@@ -209,6 +209,8 @@ int lrds_pack_mlp_tc(const lrds_mlp* mlp, int32_t precision, void* image_out, vo
  * `scratch` must hold at least 8 * (blocks + 1) doubles where blocks = lrds_estimator_blocks(B). */
 int lrds_estimator_blocks(int32_t B);
 int lrds_estimator_partials(const float* rnd, int32_t B, double* partials, double* scratch, void* stream);
+/* Merge of n partial records parts[n][8] (the all_gather result) into out[8], on the device. */
+int lrds_estimator_merge(const double* parts, int32_t n, double* out, void* stream);
 
 /* ---- drop-in pieces of the same arithmetic, for the reference's smaller public interfaces.
  * control u = generative_ctrl(t, x) for the time of table row `row` (models/reparam.py:33-43, 112-117). */

@@ -160,6 +160,15 @@ __global__ void __launch_bounds__(EST_THREADS) estimator_kernel(const float* __r
   }
 }
 
+// merge of n partial records (one per rank, gathered by the caller) on the device: the result stays on the GPU, so the
+// multi-GPU estimator needs no host round trip between the collective and whatever consumes the scalars
+__global__ void estimator_merge_kernel(const double* __restrict__ parts, int n, double* __restrict__ out) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int k = 0; k < n; ++k) merge8(acc, parts + 8 * k);
+  for (int i = 0; i < 8; ++i) out[i] = acc[i];
+}
+
 // ---- evaluation kernels for the small public interfaces -------------------------------------------------
 __global__ void __launch_bounds__(128) ctrl_forward_kernel(const lrds_spec s, int rowi, const float* __restrict__ x,
                                                            float* __restrict__ out) {
@@ -352,6 +361,15 @@ int lrds_estimator_partials(const float* rnd, int32_t B, double* partials, doubl
   estimator_kernel<<<blocks, EST_THREADS, 0, st>>>(rnd, B, partials, scratch, counter);
   e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "estimator launch");
+  g_launches.fetch_add(1);
+  return LRDS_OK;
+}
+
+int lrds_estimator_merge(const double* parts, int32_t n, double* out, void* stream) {
+  if (!parts || !out || n < 1) return fail(LRDS_ERR_INVALID, "estimator_merge: bad arguments");
+  estimator_merge_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(parts, n, out);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "estimator_merge launch");
   g_launches.fetch_add(1);
   return LRDS_OK;
 }

@@ -52,13 +52,22 @@ def merge_partials(parts: torch.Tensor) -> torch.Tensor:
     return out
 
 
-def gather_and_merge(partials: torch.Tensor, group=None) -> torch.Tensor:
-    """One all_gather of 8 doubles per rank (NCCL for CUDA tensors, gloo for CPU tensors) + host merge."""
+def gather_and_merge(partials: torch.Tensor, group=None, on_device: bool = False) -> torch.Tensor:
+    """One all_gather of 8 doubles per rank (NCCL for CUDA tensors, gloo for CPU tensors) + the associative merge.
+    CUDA tensors are merged by lrds_estimator_merge on the GPU; with ``on_device`` the merged record is returned
+    without a host synchronisation (the caller reads it when it needs the scalars)."""
     import torch.distributed as dist
     world = dist.get_world_size(group)
+    if partials.is_cuda:
+        buf = torch.empty(world * 8, device=partials.device, dtype=torch.float64)
+        dist.all_gather_into_tensor(buf, partials.contiguous(), group=group)
+        out = torch.empty(8, device=partials.device, dtype=torch.float64)
+        with torch.cuda.device(partials.device):
+            N.check(N.lib().lrds_estimator_merge(N.ptr(buf), world, N.ptr(out), N.stream_ptr(partials.device)))
+        return out if on_device else out.cpu()
     buf = [torch.empty_like(partials) for _ in range(world)]
     dist.all_gather(buf, partials.contiguous(), group=group)
-    return merge_partials(torch.stack([b.cpu() for b in buf]))
+    return merge_partials(torch.stack(buf))
 
 
 def metrics_from_partials(p: torch.Tensor) -> dict:

@@ -1,0 +1,76 @@
+#!/usr/bin/env python
+"""Kernel time of the BASELINE.json shapes other than the bench workload (production mode, in-kernel noise), per
+precision:   python tools/shape_bench.py [--precisions f16x3,tf32x3,bf16,fp32] [--json out.json]"""
+import argparse
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+from tests import cases as T  # noqa: E402
+from tests.product_builders import Built  # noqa: E402
+
+
+def dds256():
+    case = T.case_dds_phi4(True, B=131072)
+    case["problem"]["ts"] = T.cosine_ts(end=6.4, dt=0.025)
+    return case
+
+
+SHAPES = {
+    "cfg1 two_modes d=2 EM K=100 B=2048": lambda: dict(T.case_em_two_modes("score"), B=2048),
+    "cfg2 many_modes d=50 M=16 EI K=200 B=65536": lambda: T.case_ei_many_modes(K=200, B=65536),
+    "cfg3 phi4 d=100 PIS K=256 B=131072": lambda: T.case_pis_phi4(K=256, B=131072),
+    "cfg3 phi4 d=100 DDS K=256 B=131072": dds256,
+    "cfg4 logreg sonar d=61 CMCD K=100 B=262144": lambda: T.case_cmcd_logreg(166, 60, K=100, B=262144),
+    "cfg4 logreg iono d=34 CMCD K=100 B=262144": lambda: T.case_cmcd_logreg(280, 33, K=100, B=262144),
+}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--precisions", default="f16x3,tf32x3,bf16,fp32")
+    ap.add_argument("--json", default=None)
+    ap.add_argument("--only", default=None)
+    args = ap.parse_args()
+    dev = torch.device("cuda:0")
+    rows = []
+    for name, make in SHAPES.items():
+        if args.only and args.only not in name:
+            continue
+        case = make()
+        p = case["problem"]
+        B = case["B"]
+        d = p["target"]["loc"].shape[1] if p["target"]["kind"] == "gmm" else p["target"]["dim"]
+        K = len(p["ts"]) - 1
+        g = torch.Generator().manual_seed(1)
+        x0 = (torch.zeros(B, d) if case["prior"][0] == "delta" else torch.randn(B, d, generator=g)).to(dev)
+        for prec in args.precisions.split(","):
+            row = {"shape": name, "precision": prec, "B": B, "K": K, "d": d}
+            try:
+                built = Built(case, dev, prec)
+                for w in range(2):
+                    built.simulate(x0, None, seed=w)
+                torch.cuda.synchronize()
+                ev = [(torch.cuda.Event(True), torch.cuda.Event(True)) for _ in range(3)]
+                for i, (a, b) in enumerate(ev):
+                    a.record()
+                    built.simulate(x0, None, seed=10 + i)
+                    b.record()
+                torch.cuda.synchronize()
+                ms = min(a.elapsed_time(b) for a, b in ev)
+                row.update(ms=ms, particle_steps_per_s=B * K / (ms * 1e-3))
+            except Exception as e:
+                row["error"] = f"{type(e).__name__}: {e}"[:200]
+            rows.append(row)
+            print(json.dumps(row), flush=True)
+    if args.json:
+        json.dump(rows, open(args.json, "w"), indent=1)
+
+
+if __name__ == "__main__":
+    main()
