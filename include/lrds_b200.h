@@ -150,6 +150,12 @@ typedef struct {
   float threshold;    /* 1e-8, logistic_regression.py:27,56 */
   float eps;          /* float32 machine eps used by probs_to_logits (2^-23) */
   float reserved2;
+  const void* x_tc;   /* optional (NULL = both passes on the SIMT pipes): tensor-core operand of the logit GEMM z = X w + b and
+                       * of the gradient GEMM sum_n g_n X_n.  Img[n][k] = X[n][k] (k < p), 1 (k = p), 0 beyond, n padded to
+                       * N16 = 16 ceil(N/16) and k to K16 = 16 ceil((p+1)/16), times the power of two that puts its largest
+                       * entry into [2^14, 2^15), as fp16 hi | lo parts, each K-major no-swizzle [k/8][n][k%8] (the gradient
+                       * GEMM reads the same bytes MN-major); then 16 bytes whose first float is the un-scale; then y as N16
+                       * floats.  16-byte aligned; 4 N16 K16 + 16 + 4 N16 bytes. */
 } lrds_logreg;
 
 typedef struct {

@@ -56,7 +56,7 @@ class LogReg(C.Structure):
     _fields_ = [("N", C.c_int32), ("p", C.c_int32), ("n_pad", C.c_int32), ("reserved", C.c_int32),
                 ("X", FP), ("Xt", FP), ("y", FP),
                 ("weight_scale", C.c_float), ("intercept_mean", C.c_float), ("intercept_scale", C.c_float),
-                ("threshold", C.c_float), ("eps", C.c_float), ("reserved2", C.c_float)]
+                ("threshold", C.c_float), ("eps", C.c_float), ("reserved2", C.c_float), ("x_tc", FP)]
 
 
 class Distr(C.Structure):

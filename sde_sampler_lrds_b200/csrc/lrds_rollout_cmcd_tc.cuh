@@ -1,0 +1,390 @@
+// CMCD rollout over the Bayesian logistic-regression posterior (ControlledLangevinSDELoss.simulate, losses/oc.py:666-755;
+// target distr/logistic_regression.py:41-61 with its autograd score, distr/base.py:146-154) with ALL THREE dense
+// contractions of a step on the tensor core:
+//     logits    z_n   = sum_j X_nj w_j + b                          [128 x K16] . Img^T      (K-major B operand)
+//     gradient  s_j   = sum_n g_n X_nj,  g_n = m_n (y_n - sigma(z_n))   [128 x N16] . Img    (the SAME image, MN-major)
+//     drift network (lrds_rollout_tc.cuh)
+// in the F16X3 precision (fp16 (hi, lo) 3-pass split, fp32-grade).  The SIMT pipes keep what is not a GEMM: the sigmoid
+// and clamp mask per (particle, datum), the GELU epilogues, the noise and the integrator / cost update.
+//
+// One 128-particle tile per CTA (thread <-> particle <-> TMEM lane), TMEM columns:
+//     [0,64) A: x (hi | lo), then the hidden activations      [64,128) D: drift-network accumulator
+//     [128, 128+N16) Z: logits, overwritten IN PLACE by g as fp16 (hi | lo) per 16 data (A operand of the gradient GEMM)
+//     [.., +K16) T: gradient accumulator                      [.., +d_pad) the Brownian increment of the last step
+// so the per-datum residuals g_n (166 / 280 floats per particle, which limit the SIMT kernel to 4 warps per SM through
+// shared memory and make it LSU-bound) never leave the tensor memory.  The sigmoid pass is split over the three waits
+// of the drift network, whose MMAs it hides.  Shared memory: weight image | data image | columns x, u, drift.
+//
+// The loop is the reference's with the (u_t, drift_t) -> next step's (u_s, drift_s) carry-over and the
+// update fused into the evaluation of the point it starts from: per grid time k the point x_k is evaluated ONCE.
+#pragma once
+#include "lrds_rollout_tc.cuh"
+
+namespace lrds {
+
+struct CmcdTcLayout {
+  int N16, K16, dp;
+  uint32_t z_col, t_col, db_col, cols;   // TMEM columns
+  uint32_t part_bytes, img_bytes;        // data image: one (hi | lo) part; parts + tail + labels
+  uint32_t off_tail, off_y;
+};
+
+__host__ __device__ inline CmcdTcLayout cmcd_tc_layout(const lrds_spec& s) {
+  CmcdTcLayout L{};
+  L.N16 = (s.target.logreg.N + 15) / 16 * 16;
+  L.K16 = (s.d + 15) / 16 * 16;
+  L.dp = s.mlp.d_pad;
+  L.z_col = 128;
+  L.t_col = L.z_col + (uint32_t)L.N16;
+  L.db_col = L.t_col + (uint32_t)L.K16;
+  L.cols = L.db_col + (uint32_t)L.dp;
+  L.part_bytes = (uint32_t)L.N16 * (uint32_t)L.K16 * 2u;
+  L.off_tail = 2u * L.part_bytes;
+  L.off_y = L.off_tail + 16u;
+  L.img_bytes = L.off_y + (uint32_t)L.N16 * 4u;
+  return L;
+}
+
+__host__ __device__ inline bool cmcd_tc_applicable(const lrds_spec& s) {
+  if (!(s.precision == LRDS_PRECISION_F16X3 && s.kind == LRDS_ROLLOUT_CMCD && s.target.kind == LRDS_DISTR_LOGREG &&
+        s.target.logreg.x_tc != nullptr && s.ref_0.M == 1 && s.mlp.d_pad <= 64))
+    return false;
+  return cmcd_tc_layout(s).cols <= 512;
+}
+
+// log-posterior only (the terminal cost): the SIMT logit pass without storing the residuals
+__device__ __forceinline__ float logreg_logp(const lrds_logreg& L, int d, const Col4& x) {
+  const float icpt = x(d - 1);
+  const float hi = 1.0f - L.eps;
+  float ll = 0.f;
+  for (int n = 0; n < L.N; n += 4) {
+    float z[4] = {0.f, 0.f, 0.f, 0.f};
+    const float* xt = L.Xt + n;
+    for (int jq = 0; 4 * jq < L.p; ++jq) {
+      const float4 xq = x.ld4(jq);
+      const float xs[4] = {xq.x, xq.y, xq.z, xq.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int j = 4 * jq + e;
+        if (j < L.p) {
+          const float4 v = __ldg(reinterpret_cast<const float4*>(xt + (int64_t)j * L.n_pad));
+          z[0] = fmaf(v.x, xs[e], z[0]); z[1] = fmaf(v.y, xs[e], z[1]); z[2] = fmaf(v.z, xs[e], z[2]); z[3] = fmaf(v.w, xs[e], z[3]);
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if (n + i < L.N) {
+        const float yn = __ldg(L.y + n + i);
+        const float sig = 1.0f / (1.0f + expf(-(z[i] + icpt)));
+        const float ps = fminf(fmaxf(fmaxf(sig, L.threshold), L.eps), hi);
+        ll += yn * logf(ps) + (1.0f - yn) * log1pf(-ps);
+      }
+    }
+  }
+  const float hl2pi = 0.91893853320467274178f;
+  float pr = 0.f;
+  const float iw = 1.0f / (2.0f * L.weight_scale * L.weight_scale);
+  for (int j = 0; j < L.p; ++j) {
+    const float w = x(j);
+    pr += -(w * w) * iw;
+  }
+  pr += (float)L.p * (-logf(L.weight_scale) - hl2pi);
+  const float di = icpt - L.intercept_mean;
+  pr += -(di * di) / (2.0f * L.intercept_scale * L.intercept_scale) - logf(L.intercept_scale) - hl2pi;
+  return ll + pr;
+}
+
+struct CmcdTc : TcMlp<LRDS_PRECISION_F16X3> {
+  CmcdTcLayout CL;
+  uint32_t ximg_s;       // shared-window address of the data image
+  const uint8_t* ximg;   // the same, generic
+  float usx;             // its un-scale
+
+  __device__ __forceinline__ void sync_issue() {
+    ptx::tmem_wait_st();
+    ptx::tc_fence_before();
+    ptx::bar_sync(bar_id, bar_threads);
+  }
+  // D[dcol] (+)= A (hi at a_hi, lo at a_lo; 8 packed columns per K step) . B (hi image at b, lo at b + part), 3 passes
+  __device__ __forceinline__ void mma_x3(uint32_t dcol, uint32_t a_hi, uint32_t a_lo, uint32_t a_step, uint32_t b, uint32_t b_part,
+                                         uint32_t b_step, uint32_t lbo, uint32_t sbo, int ksteps, uint32_t idesc) {
+    uint32_t acc = 0;
+#pragma unroll 1
+    for (int pass = 0; pass < 3; ++pass) {  // small terms first: lo.hi, hi.lo, hi.hi
+      const uint32_t a = pass == 0 ? a_lo : a_hi;
+      const uint32_t bb = b + (pass == 1 ? b_part : 0u);
+      for (int ks = 0; ks < ksteps; ++ks) {
+        ptx::mma_bf16_ts(dcol, a + (uint32_t)ks * a_step, ptx::make_smem_desc(bb + (uint32_t)ks * b_step, lbo, sbo), idesc, acc);
+        acc = 1;
+      }
+    }
+  }
+
+  // x -> A; first drift-network layer AND the logit GEMM (N16 may exceed the 256-column MMA limit: split)
+  __device__ __forceinline__ void issue_first(const Col4& x) {
+    store_x(x);
+    sync_issue();
+    if (issuer) {
+      ptx::tc_fence_after();
+      const uint32_t a_hi = tm_tile + a_col(0), a_lo = tm_tile + a_col(1);
+      mma_x3(tm_tile + d_col(), a_hi, a_lo, 8u, img_s + L.off_in, L.part_bytes, 2u * (uint32_t)C * 16u, (uint32_t)C * 16u, 128u,
+             L.Kin / 16, ptx::make_idesc_f16(128, C));
+      const int nsplit = (CL.N16 + 255) / 256;
+      const int per = ((CL.N16 / 16 + nsplit - 1) / nsplit) * 16;
+      for (int n0 = 0; n0 < CL.N16; n0 += per) {
+        const int nn = min(per, CL.N16 - n0);
+        mma_x3(tm_tile + CL.z_col + (uint32_t)n0, a_hi, a_lo, 8u, ximg_s + (uint32_t)n0 * 16u, CL.part_bytes,
+               2u * (uint32_t)CL.N16 * 16u, (uint32_t)CL.N16 * 16u, 128u, CL.K16 / 16, ptx::make_idesc_f16(128, nn));
+      }
+      ptx::mma_commit(bar);
+    }
+  }
+  // gradient GEMM: A = g (hi | lo per 16 data, in place of the logits), B = the data image read MN-major
+  __device__ __forceinline__ void issue_gradient() {
+    sync_issue();
+    if (issuer) {
+      ptx::tc_fence_after();
+      const uint32_t zc = tm_tile + CL.z_col;
+      mma_x3(tm_tile + CL.t_col, zc, zc + 8u, 16u, ximg_s, CL.part_bytes, 256u, 128u, (uint32_t)CL.N16 * 16u, CL.N16 / 16,
+             ptx::make_idesc_f16(128, CL.K16) | (1u << 16));
+      ptx::mma_commit(bar);
+    }
+  }
+
+  // logits of data [16 t0, 16 t1) -> g = m (y - sigma(z)), m = [eps <= sigma <= 1 - eps] (and >= threshold), as fp16
+  // (hi | lo) in place.  Rows beyond N meet zero image rows in the gradient GEMM, whatever g they get.
+  __device__ __forceinline__ void sigmoid_units(const lrds_logreg& LR, int t0, int t1) {
+    const float kz = -1.4426950408889634f * usx;
+    const float hi1 = 1.0f - LR.eps;
+    const float* y = reinterpret_cast<const float*>(ximg + CL.off_y);
+#pragma unroll 1
+    for (int t = t0; t < t1; ++t) {
+      uint32_t zr[16];
+      ptx::tmem_ld16(tm_lane + CL.z_col + 16u * (uint32_t)t, zr);
+      ptx::tmem_wait_ld();
+      uint32_t ph[8], pl[8];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 yv = reinterpret_cast<const float4*>(y + 16 * t)[q];
+        const float ys[4] = {yv.x, yv.y, yv.z, yv.w};
+        float g[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          float e, sig;
+          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(__uint_as_float(zr[4 * q + i]) * kz));
+          asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(sig) : "f"(1.0f + e));
+          const bool inside = (sig >= LR.threshold) && (sig >= LR.eps) && (sig <= hi1);
+          g[i] = inside ? (ys[i] - sig) : 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          u64 h2, l2;
+          f2::split(f2::pack(g[2 * i], g[2 * i + 1]), h2, l2);
+          float h0, h1, l0, l1;
+          f2::unpack(h2, h0, h1);
+          f2::unpack(l2, l0, l1);
+          ph[2 * q + i] = ptx::pack_f16x2(h0, h1);
+          pl[2 * q + i] = ptx::pack_f16x2(l0, l1);
+        }
+      }
+      ptx::tmem_st8(tm_lane + CL.z_col + 16u * (uint32_t)t, ph);
+      ptx::tmem_st8(tm_lane + CL.z_col + 16u * (uint32_t)t + 8u, pl);
+    }
+  }
+
+  // everything on the tensor core for the point x: afterwards D holds the network output, T the data gradient
+  __device__ __forceinline__ void eval(const lrds_logreg& LR, const float* __restrict__ bias1, const Col4& x) {
+    const int units = CL.N16 / 16, per = (units + L.nh) / (L.nh + 1);
+    issue_first(x);
+    const float* bh = reinterpret_cast<const float*>(img + L.off_bhid);
+    int done = 0;
+    for (int l = 0; l < L.nh; ++l) {
+      wait();
+      if (l == 0) epilogue<true>(bias1, 0);
+      else epilogue<false>(bh + (l - 1) * C, l);
+      issue(L.off_hid + (uint32_t)(l * C * C * L.es), C, C);
+      const int upto = min(units, done + per);
+      sigmoid_units(LR, done, upto);  // in the shadow of the layer's MMAs
+      done = upto;
+    }
+    wait();
+    if (L.nh == 0) epilogue<true>(bias1, 0);
+    else epilogue<false>(bh + (L.nh - 1) * C, L.nh);
+    issue(L.off_out, C, L.Nout);
+    sigmoid_units(LR, done, units);
+    wait();
+    issue_gradient();
+    wait();
+  }
+  __device__ __forceinline__ void ld8f(uint32_t col, float (&out)[8]) {
+    uint32_t r[8];
+    ptx::tmem_ld8(tm_lane + col, r);
+    ptx::tmem_wait_ld();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) out[i] = __uint_as_float(r[i]);
+  }
+  __device__ __forceinline__ void st8f(uint32_t col, const float (&v)[8]) {
+    uint32_t r[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r[i] = __float_as_uint(v[i]);
+    ptx::tmem_st8(tm_lane + col, r);
+  }
+};
+
+// shared memory: [weight image | mbarriers + TMEM slot | data image | columns x, u, drift]
+template <int PREC>  // LRDS_PRECISION_F16X3 (a template so that only the precision's translation unit instantiates it)
+__global__ void __launch_bounds__(128, 1)
+rollout_cmcd_tc_kernel(const RolloutArgs a, const uint8_t* __restrict__ image, const uint32_t tmem_cols) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  const lrds_spec& s = a.s;
+  const TcLayout TL = tc_layout(s.d, s.mlp.num_hidden, LRDS_PRECISION_F16X3);
+  const CmcdTcLayout CL = cmcd_tc_layout(s);
+  const lrds_logreg& LR = s.target.logreg;
+  const int tid = threadIdx.x, warp = tid >> 5, NT = blockDim.x;
+  uint8_t* img = smem_raw;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + TL.bytes);
+  uint32_t* slot = reinterpret_cast<uint32_t*>(smem_raw + TL.bytes + 48);
+  uint8_t* ximg = smem_raw + TL.bytes + TC_TAIL_BYTES;
+  float* cols = reinterpret_cast<float*>(ximg + ((CL.img_bytes + 15u) & ~15u));
+  if (warp == 0) ptx::tmem_alloc(slot, tmem_cols);
+  if (tid == 0) {
+    for (int i = 0; i < 2; ++i) ptx::mbar_init(bars + i, 1);
+    ptx::fence_mbar_init();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  if (tid == 0) {  // drift weights and the data image, staged once per CTA by the TMA engine
+    ptx::mbar_expect_tx(bars, TL.bytes + CL.img_bytes);
+    ptx::bulk_g2s(img, image, TL.bytes, bars);
+    ptx::bulk_g2s(ximg, LR.x_tc, CL.img_bytes, bars);
+  }
+  ptx::mbar_wait(bars, 0);
+  const uint32_t tmem = *slot;
+  CmcdTc mlp;
+  mlp.L = TL;
+  mlp.img = img;
+  mlp.img_s = ptx::smem_u32(img);
+  mlp.tm_tile = tmem;
+  mlp.tm_lane = tmem + ((uint32_t)(warp * 32) << 16);
+  mlp.bar = bars + 1;
+  mlp.phase = 0;
+  mlp.bar_id = 1;
+  mlp.bar_threads = NT;
+  mlp.issuer = tid == 0;
+  mlp.dp = s.mlp.d_pad;
+  mlp.CL = CL;
+  mlp.ximg = ximg;
+  mlp.ximg_s = ptx::smem_u32(ximg);
+  mlp.usx = *reinterpret_cast<const float*>(ximg + CL.off_tail);
+
+  const int b_raw = blockIdx.x * NT + tid;
+  const bool live = b_raw < s.B;
+  const int b = live ? b_raw : s.B - 1;  // idle lanes shadow the last particle, results are not stored
+  const int d = s.d, dp = s.mlp.d_pad, K = s.K, p = LR.p;
+  const Col4 X{cols + 4 * tid, 4 * NT}, U{cols + dp * NT + 4 * tid, 4 * NT}, DR{cols + 2 * dp * NT + 4 * tid, 4 * NT};
+  for (int j = 0; j < dp; ++j) {
+    X(j) = (j < d) ? __ldg(a.x0 + (int64_t)b * d + j) : 0.f;
+    U(j) = 0.f;
+    DR(j) = 0.f;
+  }
+  if (a.traj_out != nullptr && live)
+    for (int j = 0; j < d; ++j) a.traj_out[(int64_t)b * d + j] = X(j);
+
+  const GmmView prior = gmm_at(s.ref_0, 0);
+  const CtrlConst cc = ctrl_const(s);
+  const float sg = s.cmcd_diff, iw = 1.0f / (LR.weight_scale * LR.weight_scale),
+              ib = 1.0f / (LR.intercept_scale * LR.intercept_scale);
+  float rnd;
+  {  // initial_log_prob(x), oc.py:698
+    float q = 0.f;
+    for (int c = 0; 4 * c < d; ++c) quad4(q, X.ld4(c), prior.mu.ld4(c), prior.ivar.ld4(c));
+    rnd = prior.glogc.ld1(0) - 0.5f * q;
+  }
+  float dt_prev = 0.f;
+  for (int k = 0; k <= K; ++k) {  // point x_k at time ts[k]
+    const float* row = s.steps + (int64_t)k * LRDS_STEP_STRIDE;
+    const float gamma = __ldg(row + LRDS_STEP_GAMMA), frac = __ldg(row + LRDS_STEP_FRAC);
+    const bool step = k < K;
+    const float dt = step ? __ldg(row + LRDS_STEP_DT) : 0.f, sqdt = step ? __ldg(row + LRDS_STEP_SQRT_DT) : 0.f;
+    mlp.eval(LR, row + LRDS_STEP_BIAS1, X);
+    float c2 = 0.f, cdb = 0.f;
+    for (int j0 = 0; j0 < dp; j0 += JC) {
+      float xr[JC], uo[JC], dro[JC], T[JC], um[JC], dbo[JC], z[JC], xn[JC], un[JC], drn[JC], dbn[JC];
+      load_chunk(X, j0, xr);
+      load_chunk(U, j0, uo);
+      load_chunk(DR, j0, dro);
+      mlp.ld8f(CL.t_col + (uint32_t)j0, T);
+      mlp.out_chunk(j0, um);
+      if (k > 0) mlp.ld8f(CL.db_col + (uint32_t)j0, dbo);
+      if (step) noise_chunk(a, k, b, j0, z);
+      const float4 m0 = prior.mu.ld4(j0 >> 2), m1 = prior.mu.ld4((j0 >> 2) + 1);
+      const float4 v0 = prior.ivar.ld4(j0 >> 2), v1 = prior.ivar.ld4((j0 >> 2) + 1);
+      const float pm[JC] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+      const float pv[JC] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+#pragma unroll
+      for (int i = 0; i < JC; ++i) {
+        const int j = j0 + i;
+        // target score: sum_n g_n X_nj - w_j / s_w^2 ; intercept: sum_n g_n - (b - m) / s_b^2
+        float sc = T[i] * mlp.usx;
+        if (j < p) sc -= xr[i] * iw;
+        else if (j == p) sc -= (xr[i] - LR.intercept_mean) * ib;
+        else sc = 0.f;
+        float v = clipb(um[i], cc.bound_model);
+        if (cc.score) v = v + (cc.scale_score * clipb(sc, cc.bound_score)) * gamma;
+        v = (j < d) ? v : 0.f;
+        const float ps = -((xr[i] - pm[i]) * pv[i]);
+        const float dnew = (j < d) ? langevin_drift(s, sc, ps, frac) : 0.f;
+        if (k > 0 && j < d) {  // cost = (drift_s + drift_t) / sigma + u_s - u_t   (oc.py:737)
+          const float cst = (dro[i] + dnew) / sg + uo[i] - v;
+          c2 = fmaf(cst, cst, c2);
+          cdb = fmaf(cst, dbo[i], cdb);
+        }
+        const float db = sqdt * z[i];
+        xn[i] = (step && j < d) ? xr[i] + (dnew + v * sg) * dt + sg * db : xr[i];  // oc.py:722-724
+        un[i] = v;
+        drn[i] = dnew;
+        dbn[i] = db;
+      }
+      if (step) {
+        store_chunk(X, j0, xn);
+        store_chunk(U, j0, un);
+        store_chunk(DR, j0, drn);
+        mlp.st8f(CL.db_col + (uint32_t)j0, dbn);
+        if (a.traj_out != nullptr && live) store_traj(a, k + 1, b, j0, xn);
+      }
+    }
+    if (k > 0) {
+      rnd += 0.5f * c2 * dt_prev;
+      rnd += cdb;
+    }
+    dt_prev = dt;
+  }
+  rnd -= clipf(logreg_logp(LR, d, X), s.clip_target);  // oc.py:750
+  if (live) {
+    a.rnd_out[b] = rnd;
+    if (a.x_out != nullptr)
+      for (int j = 0; j < d; ++j) a.x_out[(int64_t)b * d + j] = X(j);
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) ptx::tmem_dealloc(tmem, tmem_cols);
+}
+
+inline bool plan_rollout_cmcd_tc(const lrds_spec& s, int smem_cap, TcPlan* out) {
+  if (!cmcd_tc_applicable(s)) return false;
+  const TcLayout TL = tc_layout(s.d, s.mlp.num_hidden, s.precision);
+  if (TL.tile_cols != 128) return false;
+  const CmcdTcLayout CL = cmcd_tc_layout(s);
+  const size_t smem = (size_t)TL.bytes + TC_TAIL_BYTES + ((CL.img_bytes + 15u) & ~15u) + (size_t)3 * s.mlp.d_pad * 128 * sizeof(float);
+  if (smem > (size_t)smem_cap) return false;
+  out->warps = 4;
+  out->grid = (s.B + 127) / 128;
+  out->staged = 0;
+  out->tmem_cols = 512;
+  out->smem = smem;
+  return true;
+}
+
+}  // namespace lrds

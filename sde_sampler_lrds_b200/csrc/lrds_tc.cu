@@ -4,6 +4,7 @@
 #include <cstdio>
 
 #include "lrds_internal.h"
+#include "lrds_rollout_cmcd_tc.cuh"
 #include "lrds_rollout_mix.cuh"
 
 namespace lrds {
@@ -15,7 +16,8 @@ extern template int launch_prec<LRDS_PRECISION_BF16>(const RolloutArgs&, const T
 extern template int launch_prec<LRDS_PRECISION_TF32>(const RolloutArgs&, const TcPlan&, cudaStream_t, char*, size_t);
 extern template int launch_prec<LRDS_PRECISION_F16X3>(const RolloutArgs&, const TcPlan&, cudaStream_t, char*, size_t);
 
-int launch_mix_f16x3(const RolloutArgs& a, const TcPlan& p, cudaStream_t st, char* err, size_t n);  // lrds_tc_f16x3.cu
+int launch_mix_f16x3(const RolloutArgs& a, const TcPlan& p, cudaStream_t st, char* err, size_t n);      // lrds_tc_f16x3.cu
+int launch_cmcd_tc_f16x3(const RolloutArgs& a, const TcPlan& p, cudaStream_t st, char* err, size_t n);  // lrds_tc_f16x3.cu
 
 int launch_rollout_tc(const RolloutArgs& a, cudaStream_t st, char* err, size_t n) {
   const lrds_spec& s = a.s;
@@ -30,6 +32,7 @@ int launch_rollout_tc(const RolloutArgs& a, cudaStream_t st, char* err, size_t n
   TcPlan p{};
   const char* why = "";
   if (plan_rollout_mix(s, cap, sms, &p)) return launch_mix_f16x3(a, p, st, err, n);
+  if (plan_rollout_cmcd_tc(s, cap, &p)) return launch_cmcd_tc_f16x3(a, p, st, err, n);
   if (int r = plan_rollout_tc(s, cap, sms, &p, &why)) {
     snprintf(err, n, "tensor-core rollout does not fit (d=%d, precision %d): %s", s.d, s.precision, why);
     return r;

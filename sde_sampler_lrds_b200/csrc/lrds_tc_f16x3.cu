@@ -2,6 +2,7 @@
 // kernel that also runs the mixture-score contractions on the tensor core (lrds_rollout_mix.cuh).
 #include <cstdlib>
 
+#include "lrds_rollout_cmcd_tc.cuh"
 #include "lrds_rollout_mix.cuh"
 #include "lrds_tc_launch.cuh"
 
@@ -19,6 +20,20 @@ static int launch_mix_variant(const RolloutArgs& a, const TcPlan& p, cudaStream_
   if (e != cudaSuccess) {
     snprintf(err, n, "mixture tensor-core rollout launch (grid %d x %d threads, %zu B smem, %u TMEM cols): %s", p.grid,
              p.warps * 32, p.smem, p.tmem_cols, cudaGetErrorString(e));
+    return LRDS_ERR_CUDA;
+  }
+  return LRDS_OK;
+}
+
+int launch_cmcd_tc_f16x3(const RolloutArgs& a, const TcPlan& p, cudaStream_t st, char* err, size_t n) {
+  cudaError_t e = cudaFuncSetAttribute(rollout_cmcd_tc_kernel<LRDS_PRECISION_F16X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
+  if (e == cudaSuccess) {
+    rollout_cmcd_tc_kernel<LRDS_PRECISION_F16X3><<<p.grid, p.warps * 32, p.smem, st>>>(a, static_cast<const uint8_t*>(a.s.mlp.tc_image), p.tmem_cols);
+    e = cudaGetLastError();
+  }
+  if (e != cudaSuccess) {
+    snprintf(err, n, "CMCD tensor-core rollout launch (grid %d x %d threads, %zu B smem): %s", p.grid, p.warps * 32, p.smem,
+             cudaGetErrorString(e));
     return LRDS_ERR_CUDA;
   }
   return LRDS_OK;

@@ -26,7 +26,7 @@ def test_struct_sizes_match_header():
     assert C.sizeof(N.Mlp) == 16 + 6 * 8
     assert C.sizeof(N.Gmm) == 8 + 4 * 8 + 24 + 16
     assert C.sizeof(N.Phi4) == 16
-    assert C.sizeof(N.LogReg) == 16 + 24 + 24
+    assert C.sizeof(N.LogReg) == 16 + 24 + 24 + 8
     assert C.sizeof(N.Distr) == 8 + C.sizeof(N.Gmm) + C.sizeof(N.Phi4) + C.sizeof(N.LogReg)
     assert C.sizeof(N.Spec) == 40 + 24 + 8 + C.sizeof(N.Mlp) + C.sizeof(N.Distr) + 2 * C.sizeof(N.Gmm)
 

@@ -27,7 +27,8 @@ def _full_cases():
         "many_modes_ei_tf32x3": (lambda: T.case_ei_many_modes(K=200, B=65536), "tf32x3"),
         "phi4_pis": (lambda: T.case_pis_phi4(K=256, B=131072), "tf32x3"),
         "phi4_dds": (lambda: _dds256(), "bf16"),
-        "logreg_cmcd": (lambda: T.case_cmcd_logreg(166, 60, K=100, B=262144), "fp32"),
+        "logreg_cmcd": (lambda: T.case_cmcd_logreg(166, 60, K=100, B=262144), "f16x3"),  # logit / gradient GEMMs on tcgen05
+        "logreg_cmcd_fp32": (lambda: T.case_cmcd_logreg(166, 60, K=100, B=32768), "fp32"),
     }
 
 

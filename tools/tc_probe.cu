@@ -92,6 +92,69 @@ __global__ void __launch_bounds__(128) probe_kernel(const float* __restrict__ A,
   if (warp == 0) tmem_dealloc(tmem, TMEM_COLS);
 }
 
+// MN-major B operand: the SAME shared-memory image (matrix Img[N][K], K-major, as above) read as the B operand of
+//   D2[128 x K] = A2[128 x N] * Img          (contraction over the image's rows)
+// i.e. B2[j][n] = Img[n][j] with the "MN" index j contiguous: instruction-descriptor bit 16 (b_major) = 1 and, per
+// the canonical no-swizzle MN-major layout ((T,1,m),(8,k)):((1,T,SBO),(1T,LBO)), SBO = byte distance between groups of
+// 8 MN elements (= N*16, the image's K-chunk stride) and LBO = byte distance between groups of 8 K rows (= 128).
+__global__ void __launch_bounds__(128) probe_mn_kernel(const float* __restrict__ A2, const float* __restrict__ Img,
+                                                       float* __restrict__ D, int K, int N) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  if (warp == 0) tmem_alloc(&tmem_base_s, TMEM_COLS);
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    fence_mbar_init();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+  for (int idx = tid; idx < N * K; idx += 128) {
+    const int n = idx / K, k = idx % K, kc = k / 8, e = k % 8;
+    reinterpret_cast<__nv_bfloat16*>(smem + (size_t)kc * N * 16 + n * 16)[e] = __float2bfloat16(Img[idx]);
+  }
+  fence_proxy_async();
+  const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+  const float* arow = A2 + (size_t)tid * N;
+  for (int c0 = 0; c0 < N / 2; c0 += 8) {
+    uint32_t r[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const __nv_bfloat162 v = __floats2bfloat162_rn(arow[2 * (c0 + i)], arow[2 * (c0 + i) + 1]);
+      r[i] = *reinterpret_cast<const uint32_t*>(&v);
+    }
+    tmem_st8(tmem + lane_base + A_COL + c0, r);
+  }
+  tmem_wait_st();
+  tc_fence_before();
+  __syncthreads();
+  if (tid == 0) {
+    tc_fence_after();
+    const uint32_t sbase = smem_u32(smem);
+    const uint32_t idesc = make_idesc_bf16(128, K) | (1u << 16);
+    for (int ks = 0; ks < N / 16; ++ks) {  // 16 image rows per MMA: two groups of 8, 128 bytes apart
+      const uint64_t bdesc = make_smem_desc(sbase + (uint32_t)ks * 256u, 128u, (uint32_t)N * 16u);
+      mma_bf16_ts(tmem + D_COL, tmem + A_COL + ks * 8, bdesc, idesc, ks > 0);
+    }
+    mma_commit(&bar);
+  }
+  mbar_wait(&bar, 0);
+  tc_fence_after();
+  for (int c0 = 0; c0 < K; c0 += 8) {
+    uint32_t r[8];
+    tmem_ld8(tmem + lane_base + D_COL + c0, r);
+    tmem_wait_ld();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) D[(size_t)tid * K + c0 + i] = __uint_as_float(r[i]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, TMEM_COLS);
+}
+
 static float round_tf32(float v) {
   uint32_t u;
   memcpy(&u, &v, 4);
@@ -143,8 +206,45 @@ int run_case(int K, int N) {
   return worst < 1e-4 ? 0 : 1;
 }
 
+int run_mn_case(int K, int N) {  // image [N][K]; contraction over N
+  std::vector<float> A(128 * N), B(N * K), D(128 * K, -1.f);
+  srand(K * 17 + N);
+  for (auto& v : A) v = round_bf16((rand() % 2001 - 1000) / 500.f);
+  for (auto& v : B) v = round_bf16((rand() % 2001 - 1000) / 700.f);
+  float *dA, *dB, *dD;
+  cudaMalloc(&dA, A.size() * 4);
+  cudaMalloc(&dB, B.size() * 4);
+  cudaMalloc(&dD, D.size() * 4);
+  cudaMemcpy(dA, A.data(), A.size() * 4, cudaMemcpyHostToDevice);
+  cudaMemcpy(dB, B.data(), B.size() * 4, cudaMemcpyHostToDevice);
+  const size_t smem = (size_t)N * K * 2;
+  cudaFuncSetAttribute(probe_mn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  probe_mn_kernel<<<1, 128, smem>>>(dA, dB, dD, K, N);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) {
+    printf("mn-major K=%d N=%d: CUDA error %s\n", K, N, cudaGetErrorString(e));
+    return 1;
+  }
+  cudaMemcpy(D.data(), dD, D.size() * 4, cudaMemcpyDeviceToHost);
+  double worst = 0;
+  for (int m = 0; m < 128; ++m)
+    for (int j = 0; j < K; ++j) {
+      double ref = 0;
+      for (int n = 0; n < N; ++n) ref += (double)A[m * N + n] * (double)B[n * K + j];
+      worst = fmax(worst, fabs(ref - D[m * K + j]));
+    }
+  printf("bf16 MN-major B: image [%3d][%3d], contraction over rows: max abs err %.3e  %s\n", N, K, worst, worst < 1e-3 ? "OK" : "MISMATCH");
+  cudaFree(dA);
+  cudaFree(dB);
+  cudaFree(dD);
+  return worst < 1e-3 ? 0 : 1;
+}
+
 int main() {
   int bad = 0;
+  bad += run_mn_case(64, 176);
+  bad += run_mn_case(48, 96);
+  bad += run_mn_case(16, 16);
   bad += run_case<false>(8, 16);
   bad += run_case<false>(56, 64);
   bad += run_case<false>(64, 64);
