@@ -156,7 +156,7 @@ struct CmcdTc : TcMlp<LRDS_PRECISION_F16X3> {
   // (hi | lo) in place.  Rows beyond N meet zero image rows in the gradient GEMM, whatever g they get.
   __device__ __forceinline__ void sigmoid_units(const lrds_logreg& LR, int t0, int t1) {
     const float kz = -1.4426950408889634f * usx;
-    const float hi1 = 1.0f - LR.eps;
+    const float hi1 = 1.0f - LR.eps, lo1 = fmaxf(LR.threshold, LR.eps);
     const float* y = reinterpret_cast<const float*>(ximg + CL.off_y);
 #pragma unroll 1
     for (int t = t0; t < t1; ++t) {
@@ -174,7 +174,7 @@ struct CmcdTc : TcMlp<LRDS_PRECISION_F16X3> {
           float e, sig;
           asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(__uint_as_float(zr[4 * q + i]) * kz));
           asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(sig) : "f"(1.0f + e));
-          const bool inside = (sig >= LR.threshold) && (sig >= LR.eps) && (sig <= hi1);
+          const bool inside = (sig >= lo1) && (sig <= hi1);
           g[i] = inside ? (ys[i] - sig) : 0.f;
         }
 #pragma unroll
@@ -246,7 +246,8 @@ rollout_cmcd_tc_kernel(const RolloutArgs a, const uint8_t* __restrict__ image, c
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + TL.bytes);
   uint32_t* slot = reinterpret_cast<uint32_t*>(smem_raw + TL.bytes + 48);
   uint8_t* ximg = smem_raw + TL.bytes + TC_TAIL_BYTES;
-  float* cols = reinterpret_cast<float*>(ximg + ((CL.img_bytes + 15u) & ~15u));
+  float* dimtab = reinterpret_cast<float*>(ximg + ((CL.img_bytes + 15u) & ~15u));  // [4][dp] per-dim constants
+  float* cols = dimtab + 4 * a.s.mlp.d_pad;
   if (warp == 0) ptx::tmem_alloc(slot, tmem_cols);
   if (tid == 0) {
     for (int i = 0; i < 2; ++i) ptx::mbar_init(bars + i, 1);
@@ -294,8 +295,17 @@ rollout_cmcd_tc_kernel(const RolloutArgs a, const uint8_t* __restrict__ image, c
 
   const GmmView prior = gmm_at(s.ref_0, 0);
   const CtrlConst cc = ctrl_const(s);
-  const float sg = s.cmcd_diff, iw = 1.0f / (LR.weight_scale * LR.weight_scale),
-              ib = 1.0f / (LR.intercept_scale * LR.intercept_scale);
+  const float sg = s.cmcd_diff, isg = 1.0f / sg, hd = 0.5f * sg * sg, cb = clip_bound(s.cmcd_clip);
+  {  // per-dim table [4][dp]
+    const float iw = 1.0f / (LR.weight_scale * LR.weight_scale), ib = 1.0f / (LR.intercept_scale * LR.intercept_scale);
+    for (int j = tid; j < dp; j += NT) {
+      dimtab[j] = j < d ? prior.mu.ld1(j) : 0.f;
+      dimtab[dp + j] = j < d ? prior.ivar.ld1(j) : 0.f;
+      dimtab[2 * dp + j] = j == p ? LR.intercept_mean : 0.f;
+      dimtab[3 * dp + j] = j < p ? iw : (j == p ? ib : 0.f);
+    }
+    __syncthreads();
+  }
   float rnd;
   {  // initial_log_prob(x), oc.py:698
     float q = 0.f;
@@ -318,31 +328,40 @@ rollout_cmcd_tc_kernel(const RolloutArgs a, const uint8_t* __restrict__ image, c
       mlp.ld8f(CL.t_col + (uint32_t)j0, T);
       mlp.out_chunk(j0, um);
       if (k > 0) mlp.ld8f(CL.db_col + (uint32_t)j0, dbo);
-      if (step) noise_chunk(a, k, b, j0, z);
-      const float4 m0 = prior.mu.ld4(j0 >> 2), m1 = prior.mu.ld4((j0 >> 2) + 1);
-      const float4 v0 = prior.ivar.ld4(j0 >> 2), v1 = prior.ivar.ld4((j0 >> 2) + 1);
-      const float pm[JC] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
-      const float pv[JC] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+      if (step) {
+        noise_chunk(a, k, b, j0, z);
+      } else {
+#pragma unroll
+        for (int i = 0; i < JC; ++i) z[i] = 0.f;
+      }
+      // per-dim constants (prior mean, prior 1/var, score mean, score 1/var) from the shared-memory table; padded dims
+      // need no masks: their gradient, output weights, biases, table entries and noise are zero, so everything stays 0
+      const float* tb = dimtab + j0;
+      float pm[JC], pv[JC], sm[JC], si[JC];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const float4 a0 = reinterpret_cast<const float4*>(tb)[h], a1 = reinterpret_cast<const float4*>(tb + dp)[h];
+        const float4 a2 = reinterpret_cast<const float4*>(tb + 2 * dp)[h], a3 = reinterpret_cast<const float4*>(tb + 3 * dp)[h];
+        pm[4 * h] = a0.x; pm[4 * h + 1] = a0.y; pm[4 * h + 2] = a0.z; pm[4 * h + 3] = a0.w;
+        pv[4 * h] = a1.x; pv[4 * h + 1] = a1.y; pv[4 * h + 2] = a1.z; pv[4 * h + 3] = a1.w;
+        sm[4 * h] = a2.x; sm[4 * h + 1] = a2.y; sm[4 * h + 2] = a2.z; sm[4 * h + 3] = a2.w;
+        si[4 * h] = a3.x; si[4 * h + 1] = a3.y; si[4 * h + 2] = a3.z; si[4 * h + 3] = a3.w;
+      }
 #pragma unroll
       for (int i = 0; i < JC; ++i) {
-        const int j = j0 + i;
         // target score: sum_n g_n X_nj - w_j / s_w^2 ; intercept: sum_n g_n - (b - m) / s_b^2
-        float sc = T[i] * mlp.usx;
-        if (j < p) sc -= xr[i] * iw;
-        else if (j == p) sc -= (xr[i] - LR.intercept_mean) * ib;
-        else sc = 0.f;
+        const float sc = T[i] * mlp.usx - (xr[i] - sm[i]) * si[i];
         float v = clipb(um[i], cc.bound_model);
         if (cc.score) v = v + (cc.scale_score * clipb(sc, cc.bound_score)) * gamma;
-        v = (j < d) ? v : 0.f;
         const float ps = -((xr[i] - pm[i]) * pv[i]);
-        const float dnew = (j < d) ? langevin_drift(s, sc, ps, frac) : 0.f;
-        if (k > 0 && j < d) {  // cost = (drift_s + drift_t) / sigma + u_s - u_t   (oc.py:737)
-          const float cst = (dro[i] + dnew) / sg + uo[i] - v;
+        const float dnew = clipb((sc * frac + ps * (1.0f - frac)) * hd, cb);  // ControlledLangevinSDE.drift, eq/sdes.py:101-110
+        if (k > 0) {  // cost = (drift_s + drift_t) / sigma + u_s - u_t   (oc.py:737)
+          const float cst = (dro[i] + dnew) * isg + uo[i] - v;
           c2 = fmaf(cst, cst, c2);
           cdb = fmaf(cst, dbo[i], cdb);
         }
         const float db = sqdt * z[i];
-        xn[i] = (step && j < d) ? xr[i] + (dnew + v * sg) * dt + sg * db : xr[i];  // oc.py:722-724
+        xn[i] = xr[i] + (dnew + v * sg) * dt + sg * db;  // oc.py:722-724 (dt = 0 beyond the last grid time)
         un[i] = v;
         drn[i] = dnew;
         dbn[i] = db;
@@ -377,7 +396,7 @@ inline bool plan_rollout_cmcd_tc(const lrds_spec& s, int smem_cap, TcPlan* out) 
   const TcLayout TL = tc_layout(s.d, s.mlp.num_hidden, s.precision);
   if (TL.tile_cols != 128) return false;
   const CmcdTcLayout CL = cmcd_tc_layout(s);
-  const size_t smem = (size_t)TL.bytes + TC_TAIL_BYTES + ((CL.img_bytes + 15u) & ~15u) + (size_t)3 * s.mlp.d_pad * 128 * sizeof(float);
+  const size_t smem = (size_t)TL.bytes + TC_TAIL_BYTES + ((CL.img_bytes + 15u) & ~15u) + (size_t)(4 + 3 * 128) * s.mlp.d_pad * sizeof(float);
   if (smem > (size_t)smem_cap) return false;
   out->warps = 4;
   out->grid = (s.B + 127) / 128;
