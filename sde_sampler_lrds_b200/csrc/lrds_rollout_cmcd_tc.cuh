@@ -46,7 +46,8 @@ __host__ __device__ inline CmcdTcLayout cmcd_tc_layout(const lrds_spec& s) {
 }
 
 __host__ __device__ inline bool cmcd_tc_applicable(const lrds_spec& s) {
-  if (!(s.precision == LRDS_PRECISION_F16X3 && s.kind == LRDS_ROLLOUT_CMCD && s.target.kind == LRDS_DISTR_LOGREG &&
+  if (!(s.precision == LRDS_PRECISION_F16X3 && (s.kind == LRDS_ROLLOUT_CMCD || s.kind == LRDS_ROLLOUT_EUBO_CMCD) &&
+        s.target.kind == LRDS_DISTR_LOGREG &&
         s.target.logreg.x_tc != nullptr && s.ref_0.M == 1 && s.mlp.d_pad <= 64))
     return false;
   return cmcd_tc_layout(s).cols <= 512;
@@ -233,7 +234,10 @@ struct CmcdTc : TcMlp<LRDS_PRECISION_F16X3> {
 };
 
 // shared memory: [weight image | mbarriers + TMEM slot | data image | columns x, u, drift]
-template <int PREC>  // LRDS_PRECISION_F16X3 (a template so that only the precision's translation unit instantiates it)
+// EUBO: the noising rollout of compute_eubo (oc.py:757-828): starts at target samples, walks the grid backwards
+// (points at rows K, K-1, .., 0), control enters the update with the opposite sign, the cost is subtracted, and the
+// drift of the NEW point inside the cost is evaluated at the time of the OLD one (the reference's quirk, oc.py:807).
+template <int PREC, bool EUBO>  // PREC = LRDS_PRECISION_F16X3 (a template so that only that translation unit instantiates it)
 __global__ void __launch_bounds__(128, 1)
 rollout_cmcd_tc_kernel(const RolloutArgs a, const uint8_t* __restrict__ image, const uint32_t tmem_cols) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -290,7 +294,7 @@ rollout_cmcd_tc_kernel(const RolloutArgs a, const uint8_t* __restrict__ image, c
     U(j) = 0.f;
     DR(j) = 0.f;
   }
-  if (a.traj_out != nullptr && live)
+  if (!EUBO && a.traj_out != nullptr && live)
     for (int j = 0; j < d; ++j) a.traj_out[(int64_t)b * d + j] = X(j);
 
   const GmmView prior = gmm_at(s.ref_0, 0);
@@ -306,18 +310,23 @@ rollout_cmcd_tc_kernel(const RolloutArgs a, const uint8_t* __restrict__ image, c
     }
     __syncthreads();
   }
-  float rnd;
-  {  // initial_log_prob(x), oc.py:698
+  auto prior_logp = [&]() {
     float q = 0.f;
     for (int c = 0; 4 * c < d; ++c) quad4(q, X.ld4(c), prior.mu.ld4(c), prior.ivar.ld4(c));
-    rnd = prior.glogc.ld1(0) - 0.5f * q;
-  }
-  float dt_prev = 0.f;
-  for (int k = 0; k <= K; ++k) {  // point x_k at time ts[k]
-    const float* row = s.steps + (int64_t)k * LRDS_STEP_STRIDE;
+    return prior.glogc.ld1(0) - 0.5f * q;
+  };
+  // forward: initial_log_prob(x), oc.py:698; noising: -terminal_unnorm_log_prob(x), oc.py:782
+  float rnd = EUBO ? -clipf(logreg_logp(LR, d, X), s.clip_target) : prior_logp();
+  const float usign = EUBO ? -sg : sg;  // the control's sign in the update (oc.py:724 / 804)
+  float dt_prev = 0.f, frac_prev = 0.f;
+  for (int k = 0; k <= K; ++k) {  // forward: point x_k at row k; noising: the k-th point, at row K - k
+    const int rk = EUBO ? K - k : k;
+    const float* row = s.steps + (int64_t)rk * LRDS_STEP_STRIDE;
     const float gamma = __ldg(row + LRDS_STEP_GAMMA), frac = __ldg(row + LRDS_STEP_FRAC);
     const bool step = k < K;
-    const float dt = step ? __ldg(row + LRDS_STEP_DT) : 0.f, sqdt = step ? __ldg(row + LRDS_STEP_SQRT_DT) : 0.f;
+    const float* rowd = EUBO ? row - LRDS_STEP_STRIDE : row;  // the row holding dt of the step that leaves this point
+    const float dt = step ? __ldg(rowd + LRDS_STEP_DT) : 0.f, sqdt = step ? __ldg(rowd + LRDS_STEP_SQRT_DT) : 0.f;
+    const float fcost = EUBO ? frac_prev : frac;  // time at which the cost evaluates the new point's drift
     mlp.eval(LR, row + LRDS_STEP_BIAS1, X);
     float c2 = 0.f, cdb = 0.f;
     for (int j0 = 0; j0 < dp; j0 += JC) {
@@ -355,13 +364,14 @@ rollout_cmcd_tc_kernel(const RolloutArgs a, const uint8_t* __restrict__ image, c
         if (cc.score) v = v + (cc.scale_score * clipb(sc, cc.bound_score)) * gamma;
         const float ps = -((xr[i] - pm[i]) * pv[i]);
         const float dnew = clipb((sc * frac + ps * (1.0f - frac)) * hd, cb);  // ControlledLangevinSDE.drift, eq/sdes.py:101-110
-        if (k > 0) {  // cost = (drift_s + drift_t) / sigma + u_s - u_t   (oc.py:737)
-          const float cst = (dro[i] + dnew) * isg + uo[i] - v;
+        if (k > 0) {  // cost = (drift_s + drift_t) / sigma + u_s - u_t   (oc.py:737, 816)
+          const float dc = EUBO ? clipb((sc * fcost + ps * (1.0f - fcost)) * hd, cb) : dnew;
+          const float cst = EUBO ? (dc + dro[i]) * isg + v - uo[i] : (dro[i] + dc) * isg + uo[i] - v;
           c2 = fmaf(cst, cst, c2);
           cdb = fmaf(cst, dbo[i], cdb);
         }
         const float db = sqdt * z[i];
-        xn[i] = xr[i] + (dnew + v * sg) * dt + sg * db;  // oc.py:722-724 (dt = 0 beyond the last grid time)
+        xn[i] = xr[i] + (dnew + v * usign) * dt + sg * db;  // oc.py:722-724 / 802-804 (dt = 0 beyond the last point)
         un[i] = v;
         drn[i] = dnew;
         dbn[i] = db;
@@ -371,16 +381,23 @@ rollout_cmcd_tc_kernel(const RolloutArgs a, const uint8_t* __restrict__ image, c
         store_chunk(U, j0, un);
         store_chunk(DR, j0, drn);
         mlp.st8f(CL.db_col + (uint32_t)j0, dbn);
-        if (a.traj_out != nullptr && live) store_traj(a, k + 1, b, j0, xn);
+        if (!EUBO && a.traj_out != nullptr && live) store_traj(a, k + 1, b, j0, xn);
       }
     }
     if (k > 0) {
-      rnd += 0.5f * c2 * dt_prev;
-      rnd += cdb;
+      if (EUBO) {
+        rnd -= 0.5f * c2 * dt_prev;
+        rnd -= cdb;
+      } else {
+        rnd += 0.5f * c2 * dt_prev;
+        rnd += cdb;
+      }
     }
     dt_prev = dt;
+    frac_prev = frac;
   }
-  rnd -= clipf(logreg_logp(LR, d, X), s.clip_target);  // oc.py:750
+  if (EUBO) rnd += prior_logp();                                   // oc.py:825
+  else rnd -= clipf(logreg_logp(LR, d, X), s.clip_target);         // oc.py:750
   if (live) {
     a.rnd_out[b] = rnd;
     if (a.x_out != nullptr)

@@ -26,9 +26,11 @@ static int launch_mix_variant(const RolloutArgs& a, const TcPlan& p, cudaStream_
 }
 
 int launch_cmcd_tc_f16x3(const RolloutArgs& a, const TcPlan& p, cudaStream_t st, char* err, size_t n) {
-  cudaError_t e = cudaFuncSetAttribute(rollout_cmcd_tc_kernel<LRDS_PRECISION_F16X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
+  auto kernel = a.s.kind == LRDS_ROLLOUT_EUBO_CMCD ? rollout_cmcd_tc_kernel<LRDS_PRECISION_F16X3, true>
+                                                    : rollout_cmcd_tc_kernel<LRDS_PRECISION_F16X3, false>;
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
   if (e == cudaSuccess) {
-    rollout_cmcd_tc_kernel<LRDS_PRECISION_F16X3><<<p.grid, p.warps * 32, p.smem, st>>>(a, static_cast<const uint8_t*>(a.s.mlp.tc_image), p.tmem_cols);
+    kernel<<<p.grid, p.warps * 32, p.smem, st>>>(a, static_cast<const uint8_t*>(a.s.mlp.tc_image), p.tmem_cols);
     e = cudaGetLastError();
   }
   if (e != cudaSuccess) {
