@@ -15,13 +15,15 @@
 // each, [32,64) the 8-dim chunk of the contraction (target a8 b8 | reference a8 b8) while D still holds the network's
 // output.  One chunk is in flight at a time: chunk c+1 is issued as soon as every warp of the tile has read chunk c.
 #pragma once
+#include <cstdlib>
+
 #include "lrds_rollout_tc.cuh"
 
 namespace lrds {
 
 constexpr int MIX_MAX_M = 16;
 constexpr int MIX_TAIL_BYTES = 64;  // the kernel's extra mbarriers
-constexpr int MIX_MAX_WARPS = 14;  // 3.5 tiles: one wave for 65536 particles on 148 SMs (128 registers: four warps share one 16K-register SM sub-partition)
+constexpr int MIX_MAX_WARPS = 16;  // 3.5 tiles: one wave for 65536 particles on 148 SMs (128 registers: four warps share one 16K-register SM sub-partition)
 
 __host__ __device__ inline bool mix_tc_applicable(const lrds_spec& s) {
   return s.precision == LRDS_PRECISION_F16X3 && s.kind == LRDS_ROLLOUT_LINEAR && s.update_form == LRDS_UPDATE_AXPY &&
@@ -476,6 +478,10 @@ inline bool plan_rollout_mix(const lrds_spec& s, int smem_cap, int sms, TcPlan* 
   const int waves = (need + sms * wmax - 1) / (sms * wmax);
   int w = (need + sms * waves - 1) / (sms * waves);
   w = w < 1 ? 1 : (w > wmax ? wmax : w);
+  if (const char* e = getenv("LRDS_MIX_WARPS")) {  // tuning override
+    const int v = atoi(e);
+    if (v >= 1 && v <= wmax) w = v;
+  }
   const int tiles = (w + 3) / 4;
   uint32_t cols = 32;
   while ((int)cols < tiles * TL.tile_cols) cols <<= 1;
