@@ -205,6 +205,12 @@ int lrds_rollout(const lrds_spec* spec, const float* x0, const float* noise, uin
  * every weight update. */
 int64_t lrds_tc_image_bytes(int32_t d, int32_t num_hidden, int32_t precision);
 int64_t lrds_gmm_mix_tc_bytes(int32_t M, int32_t d_pad); /* one block of lrds_gmm.mix_tc */
+/* Builds lrds_gmm.mix_tc from gmm->mu / ivar (M > 1): `steps` consecutive blocks (1 for a static mixture, K for the
+ * time-marginal reference, read with step_stride_param) of lrds_gmm_mix_tc_bytes(M, d_pad) bytes each. */
+int lrds_pack_gmm_mix_tc(const lrds_gmm* gmm, int32_t d_pad, int32_t steps, void* image_out, void* stream);
+/* Builds lrds_logreg.x_tc (lrds_logreg_tc_bytes(N, p) bytes) from logreg->X ([N][d_pad]) and logreg->y. */
+int64_t lrds_logreg_tc_bytes(int32_t N, int32_t p);
+int lrds_pack_logreg_tc(const lrds_logreg* logreg, int32_t d_pad, void* image_out, void* stream);
 int lrds_pack_mlp_tc(const lrds_mlp* mlp, int32_t precision, void* image_out, void* stream);
 
 /* ---- estimator partials: replaces BaseOCLoss.compute_results (oc.py:134-173), ESS (eval/metrics.py:134-140)

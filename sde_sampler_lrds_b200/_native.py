@@ -72,7 +72,8 @@ class Spec(C.Structure):
                 ("steps", FP), ("mlp", Mlp), ("target", Distr), ("ref_t", Gmm), ("ref_0", Gmm)]
 
 
-EXPORTS = ["lrds_rollout", "lrds_tc_image_bytes", "lrds_gmm_mix_tc_bytes", "lrds_pack_mlp_tc", "lrds_estimator_blocks", "lrds_estimator_partials", "lrds_estimator_merge", "lrds_ctrl_forward",
+EXPORTS = ["lrds_rollout", "lrds_tc_image_bytes", "lrds_gmm_mix_tc_bytes", "lrds_pack_gmm_mix_tc", "lrds_logreg_tc_bytes",
+           "lrds_pack_logreg_tc", "lrds_pack_mlp_tc", "lrds_estimator_blocks", "lrds_estimator_partials", "lrds_estimator_merge", "lrds_ctrl_forward",
            "lrds_distr_eval", "lrds_axpy_step", "lrds_normals", "lrds_last_error", "lrds_abi_version",
            "lrds_launch_count"]
 
@@ -135,6 +136,12 @@ def lib():
                 L.lrds_pack_mlp_tc.argtypes = [C.POINTER(Mlp), C.c_int32, FP, FP]
                 L.lrds_estimator_blocks.argtypes = [C.c_int32]
                 L.lrds_estimator_partials.argtypes = [FP, C.c_int32, FP, FP, FP]
+                L.lrds_gmm_mix_tc_bytes.restype = C.c_int64
+                L.lrds_gmm_mix_tc_bytes.argtypes = [C.c_int32, C.c_int32]
+                L.lrds_pack_gmm_mix_tc.argtypes = [C.POINTER(Gmm), C.c_int32, C.c_int32, FP, FP]
+                L.lrds_logreg_tc_bytes.restype = C.c_int64
+                L.lrds_logreg_tc_bytes.argtypes = [C.c_int32, C.c_int32]
+                L.lrds_pack_logreg_tc.argtypes = [C.POINTER(LogReg), C.c_int32, FP, FP]
                 L.lrds_estimator_merge.argtypes = [FP, C.c_int32, FP, FP]
                 L.lrds_ctrl_forward.argtypes = [C.POINTER(Spec), C.c_int32, FP, C.c_int32, FP, FP]
                 L.lrds_distr_eval.argtypes = [C.POINTER(Distr), C.c_int32, FP, C.c_int32, FP, FP, FP]

@@ -1,5 +1,6 @@
 // C ABI of liblrds_b200.so (declared in include/lrds_b200.h): argument validation, launch configuration and
 // the small auxiliary kernels (estimator partials, control / distribution evaluation, axpy step, RNG dump).
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
 #include <atomic>
@@ -169,6 +170,75 @@ __global__ void estimator_merge_kernel(const double* __restrict__ parts, int n, 
   for (int i = 0; i < 8; ++i) out[i] = acc[i];
 }
 
+// ---- packers of the tensor-core operand images (layouts in include/lrds_b200.h) --------------------------------------
+__device__ float block_max_256(float m, float* red) {
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  float r = 0.f;
+  for (int i = 0; i < (int)(blockDim.x >> 5); ++i) r = fmaxf(r, red[i]);
+  return r;
+}
+__device__ __forceinline__ void put_hi_lo(uint8_t* out, uint32_t part_bytes, uint32_t byte, float vs) {
+  const __half hi = __float2half_rn(vs);
+  *reinterpret_cast<__half*>(out + byte) = hi;
+  *reinterpret_cast<__half*>(out + part_bytes + byte) = __float2half_rn(vs - __half2float(hi));
+}
+__device__ __forceinline__ int pow2_exponent_for(float amax) {  // amax * 2^k in [2^14, 2^15)
+  int k = 0;
+  if (amax > 0.f && amax < INFINITY) k = 14 - ilogbf(amax);
+  return k > 100 ? 100 : (k < -100 ? -100 : k);
+}
+
+// one block per step
+__global__ void __launch_bounds__(256) pack_gmm_mix_kernel(const lrds_gmm g, int d_pad, uint8_t* __restrict__ out) {
+  __shared__ float red[8];
+  const int Mp = (g.M + 15) / 16 * 16, N2 = 2 * d_pad;
+  const uint32_t part_bytes = (uint32_t)(Mp / 8) * (uint32_t)N2 * 16u;
+  const float* mu = g.mu + (int64_t)blockIdx.x * g.step_stride_param;
+  const float* iv = g.ivar + (int64_t)blockIdx.x * g.step_stride_param;
+  uint8_t* o = out + (int64_t)blockIdx.x * (2 * (int64_t)part_bytes + 16);
+  auto value = [&](int m, int n) -> float {
+    if (m >= g.M) return 0.f;
+    const int c = n >> 4, i = n & 15, j = 8 * c + (i & 7);
+    const float a = iv[(int64_t)m * d_pad + j];
+    return i < 8 ? -a : mu[(int64_t)m * d_pad + j] * a;
+  };
+  float amax = 0.f;
+  for (int idx = threadIdx.x; idx < Mp * N2; idx += blockDim.x) amax = fmaxf(amax, fabsf(value(idx / N2, idx % N2)));
+  amax = block_max_256(amax, red);
+  const int k = pow2_exponent_for(amax);
+  const float sc = ldexpf(1.0f, k);
+  for (int idx = threadIdx.x; idx < Mp * N2; idx += blockDim.x) {
+    const int m = idx / N2, n = idx % N2;
+    put_hi_lo(o, part_bytes, (uint32_t)(m >> 3) * (uint32_t)N2 * 16u + (uint32_t)n * 16u + (uint32_t)(m & 7) * 2u, value(m, n) * sc);
+  }
+  if (threadIdx.x < 4) reinterpret_cast<float*>(o + 2 * part_bytes)[threadIdx.x] = threadIdx.x == 0 ? ldexpf(1.0f, -k) : 0.f;
+}
+
+__global__ void __launch_bounds__(256) pack_logreg_kernel(const lrds_logreg L, int d_pad, uint8_t* __restrict__ out) {
+  __shared__ float red[8];
+  const int N16 = (L.N + 15) / 16 * 16, K16 = (L.p + 1 + 15) / 16 * 16;
+  const uint32_t part_bytes = (uint32_t)N16 * (uint32_t)K16 * 2u;
+  auto value = [&](int n, int k) -> float {
+    if (n >= L.N || k > L.p) return 0.f;
+    return k == L.p ? 1.0f : L.X[(int64_t)n * d_pad + k];
+  };
+  float amax = 0.f;
+  for (int idx = threadIdx.x; idx < N16 * K16; idx += blockDim.x) amax = fmaxf(amax, fabsf(value(idx / K16, idx % K16)));
+  amax = block_max_256(amax, red);
+  const int e = pow2_exponent_for(amax);
+  const float sc = ldexpf(1.0f, e);
+  for (int idx = threadIdx.x; idx < N16 * K16; idx += blockDim.x) {
+    const int n = idx / K16, k = idx % K16;
+    put_hi_lo(out, part_bytes, (uint32_t)(k >> 3) * (uint32_t)N16 * 16u + (uint32_t)n * 16u + (uint32_t)(k & 7) * 2u, value(n, k) * sc);
+  }
+  float* tail = reinterpret_cast<float*>(out + 2 * part_bytes);
+  if (threadIdx.x < 4) tail[threadIdx.x] = threadIdx.x == 0 ? ldexpf(1.0f, -e) : 0.f;
+  for (int n = threadIdx.x; n < N16; n += blockDim.x) tail[4 + n] = n < L.N ? L.y[n] : 0.f;
+}
+
 // ---- evaluation kernels for the small public interfaces -------------------------------------------------
 __global__ void __launch_bounds__(128) ctrl_forward_kernel(const lrds_spec s, int rowi, const float* __restrict__ x,
                                                            float* __restrict__ out) {
@@ -335,6 +405,32 @@ int64_t lrds_tc_image_bytes(int32_t d, int32_t num_hidden, int32_t precision) {
 int64_t lrds_gmm_mix_tc_bytes(int32_t M, int32_t d_pad) {
   if (M < 2 || d_pad < 8 || d_pad % 8 != 0) return fail(LRDS_ERR_INVALID, "gmm_mix_tc_bytes: bad arguments");
   return (int64_t)lrds::gmm_mix_tc_bytes(M, d_pad);
+}
+
+int lrds_pack_gmm_mix_tc(const lrds_gmm* gmm, int32_t d_pad, int32_t steps, void* image_out, void* stream) {
+  if (!gmm || !image_out || !gmm->mu || !gmm->ivar || gmm->M < 2 || d_pad < 8 || d_pad % 8 != 0 || steps < 1)
+    return fail(LRDS_ERR_INVALID, "pack_gmm_mix_tc: bad arguments");
+  pack_gmm_mix_kernel<<<steps, 256, 0, (cudaStream_t)stream>>>(*gmm, d_pad, static_cast<uint8_t*>(image_out));
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "pack_gmm_mix_tc launch");
+  g_launches.fetch_add(1);
+  return LRDS_OK;
+}
+
+int64_t lrds_logreg_tc_bytes(int32_t N, int32_t p) {
+  if (N < 1 || p < 1) return fail(LRDS_ERR_INVALID, "logreg_tc_bytes: bad arguments");
+  const int64_t N16 = (N + 15) / 16 * 16, K16 = (p + 1 + 15) / 16 * 16;
+  return 4 * N16 * K16 + 16 + 4 * N16;
+}
+
+int lrds_pack_logreg_tc(const lrds_logreg* logreg, int32_t d_pad, void* image_out, void* stream) {
+  if (!logreg || !image_out || !logreg->X || !logreg->y || logreg->N < 1 || logreg->p < 1 || d_pad < logreg->p + 1)
+    return fail(LRDS_ERR_INVALID, "pack_logreg_tc: bad arguments");
+  pack_logreg_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(*logreg, d_pad, static_cast<uint8_t*>(image_out));
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "pack_logreg_tc launch");
+  g_launches.fetch_add(1);
+  return LRDS_OK;
 }
 
 int lrds_pack_mlp_tc(const lrds_mlp* mlp, int32_t precision, void* image_out, void* stream) {
