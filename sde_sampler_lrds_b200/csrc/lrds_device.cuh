@@ -149,13 +149,16 @@ __device__ __forceinline__ u64 gelu_pair(u64 v2, float k2, float s) {
 // ---------------------------------------------------------------------------------------------------
 // Philox4x32-10 + Box-Muller; spec in oracle/philox_ref.py (the numpy statement the tests compare with)
 // ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mulwide(uint32_t a, uint32_t m, uint32_t& hi, uint32_t& lo) {  // one IMAD.WIDE.U32
+  asm("{\n\t.reg .b64 t;\n\tmul.wide.u32 t, %2, %3;\n\tmov.b64 {%0, %1}, t;\n\t}" : "=r"(lo), "=r"(hi) : "r"(a), "r"(m));
+}
 __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
                                                uint32_t k1, uint32_t (&out)[4]) {
 #pragma unroll
   for (int r = 0; r < 10; ++r) {
-    const uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;  // one IMAD.WIDE each
-    const uint32_t hi0 = (uint32_t)(p0 >> 32), lo0 = (uint32_t)p0;
-    const uint32_t hi1 = (uint32_t)(p1 >> 32), lo1 = (uint32_t)p1;
+    uint32_t hi0, lo0, hi1, lo1;
+    mulwide(c0, 0xD2511F53u, hi0, lo0);
+    mulwide(c2, 0xCD9E8D57u, hi1, lo1);
     c0 = hi1 ^ c1 ^ k0;
     c1 = lo1;
     c2 = hi0 ^ c3 ^ k1;
