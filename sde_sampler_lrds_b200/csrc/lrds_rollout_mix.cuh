@@ -26,8 +26,9 @@ constexpr int MIX_TAIL_BYTES = 64;  // the kernel's extra mbarriers
 constexpr int MIX_MAX_WARPS = 16;  // 3.5 tiles: one wave for 65536 particles on 148 SMs (128 registers: four warps share one 16K-register SM sub-partition)
 
 __host__ __device__ inline bool mix_tc_applicable(const lrds_spec& s) {
-  return s.precision == LRDS_PRECISION_F16X3 && s.kind == LRDS_ROLLOUT_LINEAR && s.update_form == LRDS_UPDATE_AXPY &&
-         s.ito_form == LRDS_ITO_SCALED && s.ctrl_kind == LRDS_CTRL_SCORE && s.target.kind == LRDS_DISTR_GMM &&
+  return s.precision == LRDS_PRECISION_F16X3 && (s.kind == LRDS_ROLLOUT_LINEAR || s.kind == LRDS_ROLLOUT_EUBO_LINEAR) &&
+         s.update_form == LRDS_UPDATE_AXPY && s.ito_form == LRDS_ITO_SCALED && s.ctrl_kind == LRDS_CTRL_SCORE &&
+         s.target.kind == LRDS_DISTR_GMM &&
          s.has_ref_ctrl && s.target.gmm.M > 1 && s.target.gmm.M <= MIX_MAX_M && s.ref_t.M > 1 && s.ref_t.M <= MIX_MAX_M &&
          s.target.gmm.mix_tc != nullptr && s.ref_t.mix_tc != nullptr && s.mlp.d_pad <= 64;
 }
@@ -257,7 +258,10 @@ struct MixTc : TcMlp<PREC> {
 };
 
 // ---- the loop ------------------------------------------------------------------------------------------------------
-template <int PREC, int VARIANT>
+// EUBO: the noising rollout of compute_eubo (losses/oc.py:512-568): per step x <- mean x + std z first, then the
+// control and the reference score at the new point enter the cost; x is not integrated by the control.  The step's
+// increments are generated twice (for the update and for the cost) instead of being kept per particle.
+template <int PREC, int VARIANT, bool EUBO>
 __device__ __forceinline__ void rollout_body_mix(const RolloutArgs& a, float* smem, uint8_t* stage, MixTc<PREC, VARIANT>& mlp) {
   constexpr bool PIPE = MixTc<PREC, VARIANT>::kPipe;
   constexpr bool EBAR = (VARIANT & 2) != 0;
@@ -273,7 +277,7 @@ __device__ __forceinline__ void rollout_body_mix(const RolloutArgs& a, float* sm
   const Particle P = make_particle(smem, L, NT, tid);
 
   for (int j = 0; j < dp; ++j) P.x(j) = (j < d) ? __ldg(a.x0 + (int64_t)b * d + j) : 0.f;
-  if (a.traj_out != nullptr && live)
+  if (!EUBO && a.traj_out != nullptr && live)
     for (int j = 0; j < d; ++j) a.traj_out[(int64_t)b * d + j] = P.x(j);
 
   CtrlConst cc = ctrl_const(s);
@@ -313,6 +317,13 @@ __device__ __forceinline__ void rollout_body_mix(const RolloutArgs& a, float* sm
   mlp.part_bytes = tgt_img_bytes / 2u;  // both mixtures are padded to 16 modes: equal image sizes
   const int nchunk = dp / JC;
   float rnd = 0.f;
+  if constexpr (EUBO) {  // rnd = reference_log_prob(x) - terminal_unnorm_log_prob(x)   (oc.py:536)
+    ptx::mbar_wait(sbar, 0);  // the staged target mixture (the same phase as the first step's buffer)
+    float rt[MIX_MAX_M];
+    const float lref = gmm_logp_any<PIPE>(gmm_at(s.ref_0, 0), d, dp, P.x);
+    const float ltgt = clipf(PAIR ? gmm_pass1_pair(tv, d, dp, P.x, rt) : gmm_pass1_regs<PIPE>(tv, d, dp, P.x, rt), s.clip_target);
+    rnd = lref - ltgt;
+  }
 
   for (int k = 0; k < K; ++k) {
     if constexpr (!EBAR) __syncthreads();
@@ -334,6 +345,18 @@ __device__ __forceinline__ void rollout_body_mix(const RolloutArgs& a, float* sm
     const float ust = *reinterpret_cast<const float*>(stage + SL.off_tgt + mix_off_t + tgt_img_bytes);
     const float usr = *reinterpret_cast<const float*>(buf + mix_off_r + ref_img_bytes);
 
+    if constexpr (EUBO) {  // x <- mean x + std z   (oc.py:550-552)
+      const u64 mean2 = f2::pk(rowp.ld1(LRDS_STEP_EU_A)), std2 = f2::pk(rowp.ld1(LRDS_STEP_EU_B));
+      for (int c = 0; c < nchunk; ++c) {
+        float z[JC];
+        noise_chunk(a, k, b, c * JC, z);
+        const ulonglong2 xa = P.x.ldu(2 * c), xb = P.x.ldu(2 * c + 1);
+        P.x.stu(2 * c, ulonglong2{f2::fma(std2, f2::pack(z[0], z[1]), f2::mul(xa.x, mean2)),
+                                  f2::fma(std2, f2::pack(z[2], z[3]), f2::mul(xa.y, mean2))});
+        P.x.stu(2 * c + 1, ulonglong2{f2::fma(std2, f2::pack(z[4], z[5]), f2::mul(xb.x, mean2)),
+                                      f2::fma(std2, f2::pack(z[6], z[7]), f2::mul(xb.y, mean2))});
+      }
+    }
     mlp.template hidden<true>(row + LRDS_STEP_BIAS1, P.x);  // ends with the output GEMM complete: A region free
     {
       float r[MIX_MAX_M];
@@ -378,11 +401,17 @@ __device__ __forceinline__ void rollout_body_mix(const RolloutArgs& a, float* sm
         const u64 uc = f2::pack(clipb(u0, cc.bound_model), clipb(u1, cc.bound_model));
         const u64 v = f2::fma(tsc, gs2, uc);  // control u
         const u64 z2 = f2::pack(z[2 * q], z[2 * q + 1]);
+        if constexpr (EUBO) {  // cost += u (r + u / 2),  gz += u z   (oc.py:556-563; g = u for the axpy updates)
+          su2 = f2::fma(v, f2::fma(v, f2::pk(0.5f), f2::mul(f2::fma(X[q], ra, rb), usr2)), su2);
+          sito = f2::fma(v, z2, sito);
+          continue;
+        }
         su2 = f2::fma(v, v, su2);
         sito = f2::fma(v, z2, sito);
         const u64 rv2 = f2::fma(f2::fma(X[q], ra, rb), usr2, v);  // reference score + u
         XN[q] = f2::fma(C2, z2, f2::fma(A2, X[q], f2::mul(B2, rv2)));
       }
+      if constexpr (EUBO) continue;
       P.x.stu(2 * c, ulonglong2{XN[0], XN[1]});
       P.x.stu(2 * c + 1, ulonglong2{XN[2], XN[3]});
       if (a.traj_out != nullptr && live) {
@@ -392,18 +421,24 @@ __device__ __forceinline__ void rollout_body_mix(const RolloutArgs& a, float* sm
         store_traj(a, k + 1, b, j0, xn);
       }
     }
-    rnd += wcost * f2::hsum1(su2);
-    rnd += wito * f2::hsum1(sito);
+    if constexpr (EUBO) {
+      rnd -= f2::hsum1(su2) * wcost;
+      rnd -= f2::hsum1(sito) * wito;
+    } else {
+      rnd += wcost * f2::hsum1(su2);
+      rnd += wito * f2::hsum1(sito);
+    }
     if constexpr (EBAR) {
       __syncwarp();  // the last contraction of the step has completed (wait() above): this warp is done with the buffer
       if ((tid & 31) == 0) ptx::mbar_arrive(ebar + (k & 1));
     }
   }
-  // terminal cost: rnd += reference_log_prob(x) - terminal_unnorm_log_prob(x)   (oc.py:505, 645)
-  const float lref = gmm_logp_any<PIPE>(gmm_at(s.ref_0, 0), d, dp, P.x);
-  float rt[MIX_MAX_M];
-  const float ltgt = clipf(PAIR ? gmm_pass1_pair(tv, d, dp, P.x, rt) : gmm_pass1_regs<PIPE>(tv, d, dp, P.x, rt), s.clip_target);
-  rnd += lref - ltgt;
+  if constexpr (!EUBO) {  // terminal cost: rnd += reference_log_prob(x) - terminal_unnorm_log_prob(x)   (oc.py:505, 645)
+    const float lref = gmm_logp_any<PIPE>(gmm_at(s.ref_0, 0), d, dp, P.x);
+    float rt[MIX_MAX_M];
+    const float ltgt = clipf(PAIR ? gmm_pass1_pair(tv, d, dp, P.x, rt) : gmm_pass1_regs<PIPE>(tv, d, dp, P.x, rt), s.clip_target);
+    rnd += lref - ltgt;
+  }
 
   if (live) {
     a.rnd_out[b] = rnd;
@@ -413,7 +448,7 @@ __device__ __forceinline__ void rollout_body_mix(const RolloutArgs& a, float* sm
 }
 
 // shared memory: [weight image | mbarriers + TMEM slot | operand stage | particle columns]
-template <int PREC, int VARIANT>
+template <int PREC, int VARIANT, bool EUBO>
 __global__ void __launch_bounds__(MIX_MAX_WARPS * 32, 1)
 rollout_mix_kernel(const RolloutArgs a, const uint8_t* __restrict__ image, const uint32_t tmem_cols) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -457,7 +492,7 @@ rollout_mix_kernel(const RolloutArgs a, const uint8_t* __restrict__ image, const
   mlp.bar_threads = tile_warps * 32;
   mlp.issuer = (tid & 127) == 0;
   mlp.dp = a.s.mlp.d_pad;
-  rollout_body_mix<PREC, VARIANT>(a, cols, stage, mlp);
+  rollout_body_mix<PREC, VARIANT, EUBO>(a, cols, stage, mlp);
   ptx::tc_fence_before();
   __syncthreads();
   if (warp == 0) ptx::tmem_dealloc(tmem, tmem_cols);

@@ -11,7 +11,8 @@ template int launch_prec<LRDS_PRECISION_F16X3>(const RolloutArgs&, const TcPlan&
 
 template <int VARIANT>
 static int launch_mix_variant(const RolloutArgs& a, const TcPlan& p, cudaStream_t st, char* err, size_t n) {
-  auto kernel = rollout_mix_kernel<LRDS_PRECISION_F16X3, VARIANT>;
+  auto kernel = a.s.kind == LRDS_ROLLOUT_EUBO_LINEAR ? rollout_mix_kernel<LRDS_PRECISION_F16X3, VARIANT, true>
+                                                      : rollout_mix_kernel<LRDS_PRECISION_F16X3, VARIANT, false>;
   cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
   if (e == cudaSuccess) {
     kernel<<<p.grid, p.warps * 32, p.smem, st>>>(a, static_cast<const uint8_t*>(a.s.mlp.tc_image), p.tmem_cols);

@@ -28,6 +28,9 @@ SHAPES = {
     "cfg3 phi4 d=100 DDS K=256 B=131072": dds256,
     "cfg4 logreg sonar d=61 CMCD K=100 B=262144": lambda: T.case_cmcd_logreg(166, 60, K=100, B=262144),
     "cfg4 logreg iono d=34 CMCD K=100 B=262144": lambda: T.case_cmcd_logreg(280, 33, K=100, B=262144),
+    # compute_eubo (the noising rollout behind evaluate_eubo) of the same shapes
+    "eubo cfg2 many_modes d=50 M=16 EI K=200 B=65536": lambda: dict(T.case_ei_many_modes(K=200, B=65536), eubo=True),
+    "eubo cfg4 logreg sonar d=61 CMCD K=100 B=262144": lambda: dict(T.case_cmcd_logreg(166, 60, K=100, B=262144), eubo=True),
 }
 
 
@@ -53,13 +56,15 @@ def main():
             row = {"shape": name, "precision": prec, "B": B, "K": K, "d": d}
             try:
                 built = Built(case, dev, prec)
+                run = (lambda seed: built.compute_eubo(x0, None, seed=seed)) if case.get("eubo") else \
+                    (lambda seed: built.simulate(x0, None, seed=seed))
                 for w in range(2):
-                    built.simulate(x0, None, seed=w)
+                    run(w)
                 torch.cuda.synchronize()
                 ev = [(torch.cuda.Event(True), torch.cuda.Event(True)) for _ in range(3)]
                 for i, (a, b) in enumerate(ev):
                     a.record()
-                    built.simulate(x0, None, seed=10 + i)
+                    run(10 + i)
                     b.record()
                 torch.cuda.synchronize()
                 ms = min(a.elapsed_time(b) for a, b in ev)
