@@ -1,0 +1,196 @@
+// The LINEAR loop WITHOUT a reference control - PIS (EMReferenceSDELoss with reference_ctrl=None, losses/oc.py:218-296)
+// and DDS (ExponentialIntegratorSDELoss.simulate, oc.py:1319-1397) - over the PhiFour lattice (distr/phi_four.py:45-96)
+// or any target without a per-particle pass (none / ClippedCtrl), in the F16X3 precision, written like the benchmark
+// kernel (lrds_rollout_mix.cuh): the drift network on tcgen05, everything per dim on packed fp32x2 pairs, no padding
+// masks (padded dims have zero output weights, biases and noise, and the lattice score is masked once per chunk), the
+// Ito forms folded into one per-step weight.  The general kernel (lrds_rollout_tc.cuh) evaluates the same loop with
+// run-time switches per 8-dim chunk and scalar arithmetic: 12.5 k warp-instructions per warp and step against 6 k here.
+#pragma once
+#include "lrds_rollout_tc.cuh"
+
+namespace lrds {
+
+__host__ __device__ inline bool lin_tc_applicable(const lrds_spec& s) {
+  return s.precision == LRDS_PRECISION_F16X3 && s.kind == LRDS_ROLLOUT_LINEAR && !s.has_ref_ctrl &&
+         (s.target.kind == LRDS_DISTR_PHI4 || s.target.kind == LRDS_DISTR_NONE ||
+          (s.target.kind == LRDS_DISTR_GMM && s.ctrl_kind == LRDS_CTRL_CLIPPED && s.target.gmm.M == 1));
+}
+
+// EM: update form LRDS_UPDATE_EM (else AXPY); PHI4: ScoreCtrl over the lattice target
+template <int PREC, bool EM, bool PHI4>
+__global__ void __launch_bounds__(tc_max_warps(PREC) * 32, 1)
+rollout_lin_kernel(const RolloutArgs a, const uint8_t* __restrict__ image, const uint32_t tmem_cols) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  const lrds_spec& s = a.s;
+  const TcLayout TL = tc_layout(s.d, s.mlp.num_hidden, PREC);
+  const int tid = threadIdx.x, warp = tid >> 5, nwarps = blockDim.x >> 5, NT = blockDim.x;
+  uint8_t* img = smem_raw;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + TL.bytes);  // [0] image, [1 + t] tile t
+  uint32_t* slot = reinterpret_cast<uint32_t*>(smem_raw + TL.bytes + 48);
+  float* cols = reinterpret_cast<float*>(smem_raw + TL.bytes + TC_TAIL_BYTES);
+  if (warp == 0) ptx::tmem_alloc(slot, tmem_cols);
+  if (tid == 0) {
+    for (int i = 0; i < 5; ++i) ptx::mbar_init(bars + i, 1);
+    ptx::fence_mbar_init();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  if (tid == 0) {
+    ptx::mbar_expect_tx(bars, TL.bytes);
+    ptx::bulk_g2s(img, image, TL.bytes, bars);
+  }
+  ptx::mbar_wait(bars, 0);
+  const uint32_t tmem = *slot;
+  const int tile = warp >> 2;
+  TcMlp<PREC> mlp;
+  mlp.L = TL;
+  mlp.img = img;
+  mlp.img_s = ptx::smem_u32(img);
+  mlp.tm_tile = tmem + (uint32_t)(tile * TL.tile_cols);
+  mlp.tm_lane = mlp.tm_tile + ((uint32_t)((warp & 3) * 32) << 16);
+  mlp.bar = bars + 1 + tile;
+  mlp.phase = 0;
+  mlp.bar_id = 1 + tile;
+  mlp.bar_threads = min(4, nwarps - 4 * tile) * 32;
+  mlp.issuer = (tid & 127) == 0;
+  mlp.dp = s.mlp.d_pad;
+
+  const int b_raw = blockIdx.x * NT + tid;
+  const bool live = b_raw < s.B;
+  const int b = live ? b_raw : s.B - 1;  // idle lanes shadow the last particle, results are not stored
+  const int d = s.d, dp = s.mlp.d_pad, K = s.K;
+  const Col4 X{cols + 4 * tid, 4 * NT};
+  for (int j = 0; j < dp; ++j) X(j) = (j < d) ? __ldg(a.x0 + (int64_t)b * d + j) : 0.f;
+  if (a.traj_out != nullptr && live)
+    for (int j = 0; j < d; ++j) a.traj_out[(int64_t)b * d + j] = X(j);
+
+  const CtrlConst cc = ctrl_const(s);
+  // lattice score: -beta [ (b - x (1 - x^2)) / coef + coef (2 x - x_{j+1} - x_{j-1}) ]  (distr/phi_four.py:81-96)
+  //              = x (p1 + p3 x^2) + p0 + pn ((x_{j+1} + x_{j-1}) - 2 x),  p1 = beta / coef = -p3,  pn = beta coef
+  // (the lattice Laplacian stays a difference of neighbours: no cancellation between large terms)
+  const float coef = s.target.phi4.a * (float)d, beta = s.target.phi4.beta;
+  const u64 p0 = f2::pk(-beta * s.target.phi4.b / coef), p1 = f2::pk(beta / coef), p3 = f2::pk(-beta / coef),
+            pn = f2::pk(beta * coef), m2 = f2::pk(-2.0f);
+  const int nchunk = dp / JC;
+  float rnd = 0.f;
+
+  for (int k = 0; k < K; ++k) {
+    const float* row = s.steps + (int64_t)k * LRDS_STEP_STRIDE;
+    const float A = __ldg(row + LRDS_STEP_A), Bc = __ldg(row + LRDS_STEP_B), Cc = __ldg(row + LRDS_STEP_C);
+    const float dt = __ldg(row + LRDS_STEP_DT), sqdt = __ldg(row + LRDS_STEP_SQRT_DT);
+    const float wcost = __ldg(row + LRDS_STEP_W_COST), wito = __ldg(row + LRDS_STEP_W_ITO);
+    const float gamma = __ldg(row + LRDS_STEP_GAMMA), sigu = __ldg(row + LRDS_STEP_SIGU);
+    // one weight for sum(u z): sqrt(omega) (scaled), sqrt(dt) (EM), sigma beta_k (DDS), 0 (none)
+    const float wz = s.ito_form == LRDS_ITO_SCALED ? wito
+                     : s.ito_form == LRDS_ITO_EM   ? sqdt
+                     : s.ito_form == LRDS_ITO_DDS  ? sigu * wito
+                                                   : 0.f;
+    // update as x' = xa x + xu u + xz z:  AXPY (A, B, C);  EM x + (-(f x) + sigma u) dt + sigma (z sqrt dt)
+    const u64 xa2 = f2::pk(EM ? 1.0f - A * dt : A), xu2 = f2::pk(EM ? Bc * dt : Bc), xz2 = f2::pk(EM ? Bc * sqdt : Cc);
+    const u64 gs2 = f2::pk(cc.scale_score * gamma);
+    mlp.template hidden<false>(row + LRDS_STEP_BIAS1, X);
+    u64 su2 = 0, sito = 0;
+    float xm = 0.f;  // x_{j0-1} of the state BEFORE this step's update (the chunk before has been overwritten)
+    for (int c = 0; c < nchunk; ++c) {
+      const int j0 = c * JC;
+      const ulonglong2 xa = X.ldu(2 * c), xb = X.ldu(2 * c + 1);
+      const u64 XV[4] = {xa.x, xa.y, xb.x, xb.y};
+      u64 U[4], XN[4];
+      float z[JC];
+      mlp.out_chunk2(j0, U);
+      noise_chunk(a, k, b, j0, z);
+      float xs[JC + 2];
+      xs[0] = xm;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) f2::unpack(XV[q], xs[1 + 2 * q], xs[2 + 2 * q]);
+      xs[JC + 1] = (PHI4 && j0 + JC < dp) ? X(j0 + JC) : 0.f;
+      xm = xs[JC];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float u0, u1;
+        f2::unpack(U[q], u0, u1);
+        u64 v = f2::pack(clipb(u0, cc.bound_model), clipb(u1, cc.bound_model));
+        if constexpr (PHI4) {
+          const u64 xq = XV[q];
+          const u64 nb = f2::pack(xs[2 * q] + xs[2 * q + 2], xs[2 * q + 1] + xs[2 * q + 3]);  // left + right neighbours
+          u64 t = f2::fma(f2::mul(xq, xq), p3, p1);
+          t = f2::fma(xq, t, f2::fma(pn, f2::fma(xq, m2, nb), p0));
+          float t0, t1;
+          f2::unpack(t, t0, t1);
+          if (j0 + JC > d) {  // the chunk holding the lattice end: padded sites have no score
+            if (j0 + 2 * q >= d) t0 = 0.f;
+            if (j0 + 2 * q + 1 >= d) t1 = 0.f;
+          }
+          if (cc.score) v = f2::fma(f2::pack(clipb(t0, cc.bound_score), clipb(t1, cc.bound_score)), gs2, v);
+        }
+        const u64 z2 = f2::pack(z[2 * q], z[2 * q + 1]);
+        su2 = f2::fma(v, v, su2);
+        sito = f2::fma(v, z2, sito);
+        XN[q] = f2::fma(xz2, z2, f2::fma(xa2, XV[q], f2::mul(xu2, v)));
+      }
+      X.stu(2 * c, ulonglong2{XN[0], XN[1]});
+      X.stu(2 * c + 1, ulonglong2{XN[2], XN[3]});
+      if (a.traj_out != nullptr && live) {
+        float xn[JC];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) f2::unpack(XN[q], xn[2 * q], xn[2 * q + 1]);
+        store_traj(a, k + 1, b, j0, xn);
+      }
+    }
+    rnd += wcost * f2::hsum1(su2);
+    rnd += wz * f2::hsum1(sito);
+  }
+  // terminal cost: rnd += reference_log_prob(x) - terminal_unnorm_log_prob(x)   (oc.py:290, 1389)
+  {
+    const GmmView r0 = gmm_at(s.ref_0, 0);
+    float q = 0.f;
+    for (int c = 0; 4 * c < d; ++c) quad4(q, X.ld4(c), r0.mu.ld4(c), r0.ivar.ld4(c));
+    const float lref = r0.glogc.ld1(0) - 0.5f * q;
+    float ltgt = 0.f;
+    if (s.target.kind == LRDS_DISTR_PHI4) ltgt = phi4_logp(s.target.phi4, d, X);
+    else if (s.target.kind == LRDS_DISTR_GMM) {
+      const GmmView t0 = gmm_at(s.target.gmm, 0);
+      float qt = 0.f;
+      for (int c = 0; 4 * c < d; ++c) quad4(qt, X.ld4(c), t0.mu.ld4(c), t0.ivar.ld4(c));
+      ltgt = t0.glogc.ld1(0) - 0.5f * qt;
+    }
+    rnd += lref - clipf(ltgt, s.clip_target);
+  }
+  if (live) {
+    a.rnd_out[b] = rnd;
+    if (a.x_out != nullptr)
+      for (int j = 0; j < d; ++j) a.x_out[(int64_t)b * d + j] = X(j);
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) ptx::tmem_dealloc(tmem, tmem_cols);
+}
+
+inline bool plan_rollout_lin(const lrds_spec& s, int smem_cap, int sms, TcPlan* out) {
+  if (!lin_tc_applicable(s) || s.ref_0.M != 1) return false;
+  const TcLayout TL = tc_layout(s.d, s.mlp.num_hidden, s.precision);
+  if (TL.tile_cols > 512) return false;
+  const size_t fixed = (size_t)TL.bytes + TC_TAIL_BYTES;
+  const size_t per_warp = (size_t)s.mlp.d_pad * 32 * sizeof(float);
+  if (fixed + per_warp > (size_t)smem_cap) return false;
+  int wmax = (int)(((size_t)smem_cap - fixed) / per_warp);
+  const int tmax = 512 / TL.tile_cols;
+  wmax = wmax < tc_max_warps(s.precision) ? wmax : tc_max_warps(s.precision);
+  wmax = wmax < 4 * tmax ? wmax : 4 * tmax;
+  const int need = (s.B + 31) / 32;
+  const int waves = (need + sms * wmax - 1) / (sms * wmax);
+  int w = (need + sms * waves - 1) / (sms * waves);
+  w = w < 1 ? 1 : (w > wmax ? wmax : w);
+  const int tiles = (w + 3) / 4;
+  uint32_t cols = 32;
+  while ((int)cols < tiles * TL.tile_cols) cols <<= 1;
+  out->warps = w;
+  out->grid = (need + w - 1) / w;
+  out->staged = 0;
+  out->tmem_cols = cols;
+  out->smem = fixed + per_warp * w;
+  return true;
+}
+
+}  // namespace lrds

@@ -5,6 +5,7 @@
 
 #include "lrds_internal.h"
 #include "lrds_rollout_cmcd_tc.cuh"
+#include "lrds_rollout_lin.cuh"
 #include "lrds_rollout_mix.cuh"
 
 namespace lrds {
@@ -18,6 +19,7 @@ extern template int launch_prec<LRDS_PRECISION_F16X3>(const RolloutArgs&, const 
 
 int launch_mix_f16x3(const RolloutArgs& a, const TcPlan& p, cudaStream_t st, char* err, size_t n);      // lrds_tc_f16x3.cu
 int launch_cmcd_tc_f16x3(const RolloutArgs& a, const TcPlan& p, cudaStream_t st, char* err, size_t n);  // lrds_tc_f16x3.cu
+int launch_lin_f16x3(const RolloutArgs& a, const TcPlan& p, cudaStream_t st, char* err, size_t n);      // lrds_tc_f16x3.cu
 
 int launch_rollout_tc(const RolloutArgs& a, cudaStream_t st, char* err, size_t n) {
   const lrds_spec& s = a.s;
@@ -33,6 +35,7 @@ int launch_rollout_tc(const RolloutArgs& a, cudaStream_t st, char* err, size_t n
   const char* why = "";
   if (plan_rollout_mix(s, cap, sms, &p)) return launch_mix_f16x3(a, p, st, err, n);
   if (plan_rollout_cmcd_tc(s, cap, &p)) return launch_cmcd_tc_f16x3(a, p, st, err, n);
+  if (plan_rollout_lin(s, cap, sms, &p)) return launch_lin_f16x3(a, p, st, err, n);
   if (int r = plan_rollout_tc(s, cap, sms, &p, &why)) {
     snprintf(err, n, "tensor-core rollout does not fit (d=%d, precision %d): %s", s.d, s.precision, why);
     return r;
