@@ -15,6 +15,11 @@
 // shared memory and make it LSU-bound) never leave the tensor memory.  The sigmoid pass is split over the three waits
 // of the drift network, whose MMAs it hides.  Shared memory: weight image | data image | columns x, u, drift.
 //
+// TWO threads per particle: the tile's 128 particles are served by 8 warps; warps w and w + 4 own the same TMEM lanes and
+// split every per-particle loop (operand columns, epilogue halves, sigmoid units, 8-dim chunks) - with one 4-warp tile
+// per SM the kernel is latency-bound, and halving each thread's work nearly halves the step.  The cost sums are linear,
+// so each thread keeps its own partial log-weight and the two are added once, at the end.
+//
 // The loop is the reference's with the (u_t, drift_t) -> next step's (u_s, drift_s) carry-over and the
 // update fused into the evaluation of the point it starts from: per grid time k the point x_k is evaluated ONCE.
 #pragma once
@@ -44,6 +49,9 @@ __host__ __device__ inline CmcdTcLayout cmcd_tc_layout(const lrds_spec& s) {
   L.img_bytes = L.off_y + (uint32_t)L.N16 * 4u;
   return L;
 }
+
+// per-dim table [4][d_pad]; at least 128 floats (the second threads' partial log-weights at the end)
+__host__ __device__ inline int cmcd_tab_floats(int d_pad) { return 4 * d_pad > 128 ? 4 * d_pad : 128; }
 
 __host__ __device__ inline bool cmcd_tc_applicable(const lrds_spec& s) {
   if (!(s.precision == LRDS_PRECISION_F16X3 && (s.kind == LRDS_ROLLOUT_CMCD || s.kind == LRDS_ROLLOUT_EUBO_CMCD) &&
@@ -98,6 +106,7 @@ __device__ __forceinline__ float logreg_logp(const lrds_logreg& L, int d, const 
 
 struct CmcdTc : TcMlp<LRDS_PRECISION_F16X3> {
   CmcdTcLayout CL;
+  int half;              // 0 / 1: which of the particle's two threads this is
   uint32_t ximg_s;       // shared-window address of the data image
   const uint8_t* ximg;   // the same, generic
   float usx;             // its un-scale
@@ -124,7 +133,21 @@ struct CmcdTc : TcMlp<LRDS_PRECISION_F16X3> {
 
   // x -> A; first drift-network layer AND the logit GEMM (N16 may exceed the 256-column MMA limit: split)
   __device__ __forceinline__ void issue_first(const Col4& x) {
-    store_x(x);
+    for (int c0 = 8 * half; c0 < L.Kin / 2; c0 += 16) {  // this thread's 16-dim groups -> 8 packed columns each
+      float v[16];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int j0 = 2 * c0 + 8 * h;
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+        if (j0 < dp) {
+          a = x.ld4(j0 >> 2);
+          b = x.ld4((j0 >> 2) + 1);
+        }
+        v[8 * h + 0] = a.x; v[8 * h + 1] = a.y; v[8 * h + 2] = a.z; v[8 * h + 3] = a.w;
+        v[8 * h + 4] = b.x; v[8 * h + 5] = b.y; v[8 * h + 6] = b.z; v[8 * h + 7] = b.w;
+      }
+      store16_half(c0, v);
+    }
     sync_issue();
     if (issuer) {
       ptx::tc_fence_after();
@@ -160,7 +183,7 @@ struct CmcdTc : TcMlp<LRDS_PRECISION_F16X3> {
     const float hi1 = 1.0f - LR.eps, lo1 = fmaxf(LR.threshold, LR.eps);
     const float* y = reinterpret_cast<const float*>(ximg + CL.off_y);
 #pragma unroll 1
-    for (int t = t0; t < t1; ++t) {
+    for (int t = t0 + half; t < t1; t += 2) {
       uint32_t zr[16];
       ptx::tmem_ld16(tm_lane + CL.z_col + 16u * (uint32_t)t, zr);
       ptx::tmem_wait_ld();
@@ -202,16 +225,16 @@ struct CmcdTc : TcMlp<LRDS_PRECISION_F16X3> {
     int done = 0;
     for (int l = 0; l < L.nh; ++l) {
       wait();
-      if (l == 0) epilogue<true>(bias1, 0);
-      else epilogue<false>(bh + (l - 1) * C, l);
+      if (l == 0) epilogue_f16<true>(bias1, 0, 32 * half, 32 * half + 32);
+      else epilogue_f16<false>(bh + (l - 1) * C, l, 32 * half, 32 * half + 32);
       issue(L.off_hid + (uint32_t)(l * C * C * L.es), C, C);
       const int upto = min(units, done + per);
       sigmoid_units(LR, done, upto);  // in the shadow of the layer's MMAs
       done = upto;
     }
     wait();
-    if (L.nh == 0) epilogue<true>(bias1, 0);
-    else epilogue<false>(bh + (L.nh - 1) * C, L.nh);
+    if (L.nh == 0) epilogue_f16<true>(bias1, 0, 32 * half, 32 * half + 32);
+    else epilogue_f16<false>(bh + (L.nh - 1) * C, L.nh, 32 * half, 32 * half + 32);
     issue(L.off_out, C, L.Nout);
     sigmoid_units(LR, done, units);
     wait();
@@ -238,20 +261,22 @@ struct CmcdTc : TcMlp<LRDS_PRECISION_F16X3> {
 // (points at rows K, K-1, .., 0), control enters the update with the opposite sign, the cost is subtracted, and the
 // drift of the NEW point inside the cost is evaluated at the time of the OLD one (the reference's quirk, oc.py:807).
 template <int PREC, bool EUBO>  // PREC = LRDS_PRECISION_F16X3 (a template so that only that translation unit instantiates it)
-__global__ void __launch_bounds__(128, 1)
+__global__ void __launch_bounds__(256, 1)
 rollout_cmcd_tc_kernel(const RolloutArgs a, const uint8_t* __restrict__ image, const uint32_t tmem_cols) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   const lrds_spec& s = a.s;
   const TcLayout TL = tc_layout(s.d, s.mlp.num_hidden, LRDS_PRECISION_F16X3);
   const CmcdTcLayout CL = cmcd_tc_layout(s);
   const lrds_logreg& LR = s.target.logreg;
-  const int tid = threadIdx.x, warp = tid >> 5, NT = blockDim.x;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  constexpr int NT = 128;                          // particles per CTA; 256 threads = two per particle
+  const int pt = tid & (NT - 1), half = tid >> 7;  // particle slot and which of its two threads
   uint8_t* img = smem_raw;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + TL.bytes);
   uint32_t* slot = reinterpret_cast<uint32_t*>(smem_raw + TL.bytes + 48);
   uint8_t* ximg = smem_raw + TL.bytes + TC_TAIL_BYTES;
   float* dimtab = reinterpret_cast<float*>(ximg + ((CL.img_bytes + 15u) & ~15u));  // [4][dp] per-dim constants
-  float* cols = dimtab + 4 * a.s.mlp.d_pad;
+  float* cols = dimtab + cmcd_tab_floats(a.s.mlp.d_pad);
   if (warp == 0) ptx::tmem_alloc(slot, tmem_cols);
   if (tid == 0) {
     for (int i = 0; i < 2; ++i) ptx::mbar_init(bars + i, 1);
@@ -272,37 +297,38 @@ rollout_cmcd_tc_kernel(const RolloutArgs a, const uint8_t* __restrict__ image, c
   mlp.img = img;
   mlp.img_s = ptx::smem_u32(img);
   mlp.tm_tile = tmem;
-  mlp.tm_lane = tmem + ((uint32_t)(warp * 32) << 16);
+  mlp.tm_lane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
   mlp.bar = bars + 1;
   mlp.phase = 0;
   mlp.bar_id = 1;
-  mlp.bar_threads = NT;
+  mlp.bar_threads = 2 * NT;
   mlp.issuer = tid == 0;
+  mlp.half = half;
   mlp.dp = s.mlp.d_pad;
   mlp.CL = CL;
   mlp.ximg = ximg;
   mlp.ximg_s = ptx::smem_u32(ximg);
   mlp.usx = *reinterpret_cast<const float*>(ximg + CL.off_tail);
 
-  const int b_raw = blockIdx.x * NT + tid;
+  const int b_raw = blockIdx.x * NT + pt;
   const bool live = b_raw < s.B;
   const int b = live ? b_raw : s.B - 1;  // idle lanes shadow the last particle, results are not stored
   const int d = s.d, dp = s.mlp.d_pad, K = s.K, p = LR.p;
-  const Col4 X{cols + 4 * tid, 4 * NT}, U{cols + dp * NT + 4 * tid, 4 * NT}, DR{cols + 2 * dp * NT + 4 * tid, 4 * NT};
-  for (int j = 0; j < dp; ++j) {
+  const Col4 X{cols + 4 * pt, 4 * NT}, U{cols + dp * NT + 4 * pt, 4 * NT}, DR{cols + 2 * dp * NT + 4 * pt, 4 * NT};
+  for (int j = half; j < dp; j += 2) {
     X(j) = (j < d) ? __ldg(a.x0 + (int64_t)b * d + j) : 0.f;
     U(j) = 0.f;
     DR(j) = 0.f;
   }
   if (!EUBO && a.traj_out != nullptr && live)
-    for (int j = 0; j < d; ++j) a.traj_out[(int64_t)b * d + j] = X(j);
+    for (int j = half; j < d; j += 2) a.traj_out[(int64_t)b * d + j] = __ldg(a.x0 + (int64_t)b * d + j);
 
   const GmmView prior = gmm_at(s.ref_0, 0);
   const CtrlConst cc = ctrl_const(s);
   const float sg = s.cmcd_diff, isg = 1.0f / sg, hd = 0.5f * sg * sg, cb = clip_bound(s.cmcd_clip);
   {  // per-dim table [4][dp]
     const float iw = 1.0f / (LR.weight_scale * LR.weight_scale), ib = 1.0f / (LR.intercept_scale * LR.intercept_scale);
-    for (int j = tid; j < dp; j += NT) {
+    for (int j = tid; j < dp; j += 2 * NT) {
       dimtab[j] = j < d ? prior.mu.ld1(j) : 0.f;
       dimtab[dp + j] = j < d ? prior.ivar.ld1(j) : 0.f;
       dimtab[2 * dp + j] = j == p ? LR.intercept_mean : 0.f;
@@ -315,8 +341,9 @@ rollout_cmcd_tc_kernel(const RolloutArgs a, const uint8_t* __restrict__ image, c
     for (int c = 0; 4 * c < d; ++c) quad4(q, X.ld4(c), prior.mu.ld4(c), prior.ivar.ld4(c));
     return prior.glogc.ld1(0) - 0.5f * q;
   };
-  // forward: initial_log_prob(x), oc.py:698; noising: -terminal_unnorm_log_prob(x), oc.py:782
-  float rnd = EUBO ? -clipf(logreg_logp(LR, d, X), s.clip_target) : prior_logp();
+  // forward: initial_log_prob(x), oc.py:698; noising: -terminal_unnorm_log_prob(x), oc.py:782 (first thread of the pair;
+  // the second one starts its partial sum at zero)
+  float rnd = half ? 0.f : (EUBO ? -clipf(logreg_logp(LR, d, X), s.clip_target) : prior_logp());
   const float usign = EUBO ? -sg : sg;  // the control's sign in the update (oc.py:724 / 804)
   float dt_prev = 0.f, frac_prev = 0.f;
   for (int k = 0; k <= K; ++k) {  // forward: point x_k at row k; noising: the k-th point, at row K - k
@@ -327,9 +354,10 @@ rollout_cmcd_tc_kernel(const RolloutArgs a, const uint8_t* __restrict__ image, c
     const float* rowd = EUBO ? row - LRDS_STEP_STRIDE : row;  // the row holding dt of the step that leaves this point
     const float dt = step ? __ldg(rowd + LRDS_STEP_DT) : 0.f, sqdt = step ? __ldg(rowd + LRDS_STEP_SQRT_DT) : 0.f;
     const float fcost = EUBO ? frac_prev : frac;  // time at which the cost evaluates the new point's drift
+    __syncthreads();  // the pair's writes of x (previous chunk loop / initial load) are visible to both threads
     mlp.eval(LR, row + LRDS_STEP_BIAS1, X);
     float c2 = 0.f, cdb = 0.f;
-    for (int j0 = 0; j0 < dp; j0 += JC) {
+    for (int j0 = JC * half; j0 < dp; j0 += 2 * JC) {  // this thread's 8-dim chunks
       float xr[JC], uo[JC], dro[JC], T[JC], um[JC], dbo[JC], z[JC], xn[JC], un[JC], drn[JC], dbn[JC];
       load_chunk(X, j0, xr);
       load_chunk(U, j0, uo);
@@ -396,13 +424,17 @@ rollout_cmcd_tc_kernel(const RolloutArgs a, const uint8_t* __restrict__ image, c
     dt_prev = dt;
     frac_prev = frac;
   }
-  if (EUBO) rnd += prior_logp();                                   // oc.py:825
-  else rnd -= clipf(logreg_logp(LR, d, X), s.clip_target);         // oc.py:750
-  if (live) {
-    a.rnd_out[b] = rnd;
-    if (a.x_out != nullptr)
-      for (int j = 0; j < d; ++j) a.x_out[(int64_t)b * d + j] = X(j);
+  __syncthreads();  // final state complete; the table is dead: its first 128 floats carry the second threads' partial sums
+  if (half) dimtab[pt] = rnd;
+  __syncthreads();
+  if (!half) {
+    rnd += dimtab[pt];
+    if (EUBO) rnd += prior_logp();                                   // oc.py:825
+    else rnd -= clipf(logreg_logp(LR, d, X), s.clip_target);         // oc.py:750
+    if (live) a.rnd_out[b] = rnd;
   }
+  if (live && a.x_out != nullptr)
+    for (int j = half; j < d; j += 2) a.x_out[(int64_t)b * d + j] = X(j);
   ptx::tc_fence_before();
   __syncthreads();
   if (warp == 0) ptx::tmem_dealloc(tmem, tmem_cols);
@@ -413,9 +445,9 @@ inline bool plan_rollout_cmcd_tc(const lrds_spec& s, int smem_cap, TcPlan* out) 
   const TcLayout TL = tc_layout(s.d, s.mlp.num_hidden, s.precision);
   if (TL.tile_cols != 128) return false;
   const CmcdTcLayout CL = cmcd_tc_layout(s);
-  const size_t smem = (size_t)TL.bytes + TC_TAIL_BYTES + ((CL.img_bytes + 15u) & ~15u) + (size_t)(4 + 3 * 128) * s.mlp.d_pad * sizeof(float);
+  const size_t smem = (size_t)TL.bytes + TC_TAIL_BYTES + ((CL.img_bytes + 15u) & ~15u) + ((size_t)cmcd_tab_floats(s.mlp.d_pad) + (size_t)3 * 128 * s.mlp.d_pad) * sizeof(float);
   if (smem > (size_t)smem_cap) return false;
-  out->warps = 4;
+  out->warps = 8;  // two threads per particle
   out->grid = (s.B + 127) / 128;
   out->staged = 0;
   out->tmem_cols = 512;

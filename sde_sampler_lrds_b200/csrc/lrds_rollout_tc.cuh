@@ -273,10 +273,10 @@ struct TcMlp {
 
   // F16X3: the whole epilogue on packed fp32x2 arithmetic
   template <bool GLOBAL_BIAS>
-  __device__ __forceinline__ void epilogue_f16(const float* __restrict__ bias, int layer) {
+  __device__ __forceinline__ void epilogue_f16(const float* __restrict__ bias, int layer, int c_begin = 0, int c_end = C) {
     const u64 us2 = f2::pk(unscale(layer));
 #pragma unroll 1
-    for (int c0 = 0; c0 < C; c0 += 32) {
+    for (int c0 = c_begin; c0 < c_end; c0 += 32) {
       uint32_t r[32];
       ptx::tmem_ld32(tm_lane + d_col() + c0, r);
       ptx::tmem_wait_ld();

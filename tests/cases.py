@@ -251,8 +251,9 @@ CASES = {
     "eubo_ei_many_modes": lambda: _eubo(case_ei_many_modes(K=100, B=100), 202),
     "eubo_cmcd_gmm": lambda: _eubo(case_cmcd_gmm(), 203),
     "eubo_ddpm_snr": lambda: _eubo(case_ddpm_snr(), 204),
-    "eubo_cmcd_logreg_sonar": lambda: _eubo(case_cmcd_logreg(166, 60), 205),
-    "eubo_cmcd_logreg_iono": lambda: _eubo(case_cmcd_logreg(280, 33, ctrl_kind="clipped"), 206),
+    # 256 particles: the >= 99 % agreement bar of the clamp-mask target then tolerates two particles
+    "eubo_cmcd_logreg_sonar": lambda: _eubo(case_cmcd_logreg(166, 60, B=256), 205),
+    "eubo_cmcd_logreg_iono": lambda: _eubo(case_cmcd_logreg(280, 33, B=256, ctrl_kind="clipped"), 206),
 }
 
 
