@@ -39,6 +39,8 @@ CPU_SAMPLE_B = 16384
 # (profiles/r01_mix_summary.md: smsp__inst_executed.sum / (B K)): the SIMT work (mixture quadratic forms, erf GELU,
 # Philox + Box-Muller, integrator) that bounds this path; used for the issue-slot figure in "roofline".
 WARP_INSTR_PER_PARTICLE_STEP = {"f16x3": 3.6036e9 / (B_PER_GPU * K_STEPS)}
+# dram__bytes_read.sum + dram__bytes_write.sum of one launch of the same kernel (same capture)
+DRAM_BYTES_PER_LAUNCH = {"f16x3": 16_285_184 + 2_560}
 FAST_MODE_TOLERANCE = "log Z within 5e-2 abs, 99% of log-weights within 1e-2 rel (tests/test_rollout_parity_gpu.py)"
 
 
@@ -296,7 +298,7 @@ def run_ours(args):
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": int(launches),
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                     "traffic": None, "kernel_ms": kern_ms, "kernel_ms_each": kern_ms_each, "peak_source": how + ", dense bf16 burst",
+                     "traffic": DRAM_BYTES_PER_LAUNCH.get(args.precision), "kernel_ms": kern_ms, "kernel_ms_each": kern_ms_each, "peak_source": how + ", dense bf16 burst",
                      "flops_per_particle_step": FLOPS_PER_PARTICLE_STEP},
         "check": {"log_norm_const_is": m["log_norm_const_is"], "elbo": m["elbo"], "ess": m["effective_sample_size"]},
     }

@@ -218,9 +218,9 @@ struct CmcdTc : TcMlp<LRDS_PRECISION_F16X3> {
   }
 
   // everything on the tensor core for the point x: afterwards D holds the network output, T the data gradient
-  __device__ __forceinline__ void eval(const lrds_logreg& LR, const float* __restrict__ bias1, const Col4& x) {
+  // (the caller generates the step's noise between issue_first() and finish(): it hides the first GEMMs)
+  __device__ __forceinline__ void finish(const lrds_logreg& LR, const float* __restrict__ bias1) {
     const int units = CL.N16 / 16, per = (units + L.nh) / (L.nh + 1);
-    issue_first(x);
     const float* bh = reinterpret_cast<const float*>(img + L.off_bhid);
     int done = 0;
     for (int l = 0; l < L.nh; ++l) {
@@ -355,22 +355,46 @@ rollout_cmcd_tc_kernel(const RolloutArgs a, const uint8_t* __restrict__ image, c
     const float dt = step ? __ldg(rowd + LRDS_STEP_DT) : 0.f, sqdt = step ? __ldg(rowd + LRDS_STEP_SQRT_DT) : 0.f;
     const float fcost = EUBO ? frac_prev : frac;  // time at which the cost evaluates the new point's drift
     __syncthreads();  // the pair's writes of x (previous chunk loop / initial load) are visible to both threads
-    mlp.eval(LR, row + LRDS_STEP_BIAS1, X);
+    mlp.issue_first(X);
+    float zs[4][JC];  // the step's increments for this thread's (at most four) chunks, generated behind the first GEMMs
+#pragma unroll
+    for (int ci = 0; ci < 4; ++ci) {
+      const int j0 = JC * (2 * ci + half);
+      if (step && j0 < dp) {
+        noise_chunk(a, k, b, j0, zs[ci]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < JC; ++i) zs[ci][i] = 0.f;
+      }
+    }
+    mlp.finish(LR, row + LRDS_STEP_BIAS1);
     float c2 = 0.f, cdb = 0.f;
-    for (int j0 = JC * half; j0 < dp; j0 += 2 * JC) {  // this thread's 8-dim chunks
-      float xr[JC], uo[JC], dro[JC], T[JC], um[JC], dbo[JC], z[JC], xn[JC], un[JC], drn[JC], dbn[JC];
+#pragma unroll
+    for (int ci = 0; ci < 4; ++ci) {  // this thread's 8-dim chunks
+      const int j0 = JC * (2 * ci + half);
+      if (j0 >= dp) break;
+      float xr[JC], uo[JC], dro[JC], T[JC], um[JC], dbo[JC], xn[JC], un[JC], drn[JC], dbn[JC];
+      const float (&z)[JC] = zs[ci];
+      {  // the chunk's three TMEM reads (gradient, network output, last increment) behind one wait
+        uint32_t r0[8], r1[8], r2[8];
+        ptx::tmem_ld8(mlp.tm_lane + CL.t_col + (uint32_t)j0, r0);
+        ptx::tmem_ld8(mlp.tm_lane + mlp.d_col() + (uint32_t)j0, r1);
+        if (k > 0) ptx::tmem_ld8(mlp.tm_lane + CL.db_col + (uint32_t)j0, r2);
+        ptx::tmem_wait_ld();
+        const float4* b4 = reinterpret_cast<const float4*>(mlp.img + mlp.L.off_bout + j0 * 4);
+        const float4 ba = b4[0], bb = b4[1];
+        const float bs[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
+        const float uso = mlp.unscale(mlp.L.nh + 1);
+#pragma unroll
+        for (int i = 0; i < JC; ++i) {
+          T[i] = __uint_as_float(r0[i]);
+          um[i] = fmaf(__uint_as_float(r1[i]), uso, bs[i]);
+          dbo[i] = k > 0 ? __uint_as_float(r2[i]) : 0.f;
+        }
+      }
       load_chunk(X, j0, xr);
       load_chunk(U, j0, uo);
       load_chunk(DR, j0, dro);
-      mlp.ld8f(CL.t_col + (uint32_t)j0, T);
-      mlp.out_chunk(j0, um);
-      if (k > 0) mlp.ld8f(CL.db_col + (uint32_t)j0, dbo);
-      if (step) {
-        noise_chunk(a, k, b, j0, z);
-      } else {
-#pragma unroll
-        for (int i = 0; i < JC; ++i) z[i] = 0.f;
-      }
       // per-dim constants (prior mean, prior 1/var, score mean, score 1/var) from the shared-memory table; padded dims
       // need no masks: their gradient, output weights, biases, table entries and noise are zero, so everything stays 0
       const float* tb = dimtab + j0;

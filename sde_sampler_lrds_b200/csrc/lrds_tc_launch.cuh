@@ -37,7 +37,7 @@ int launch_linear(const RolloutArgs& a, const TcPlan& p, cudaStream_t st, char* 
   if constexpr (STAGE > 0) {
     if (traits_match<TraitsLrds>(a.s)) return launch_one<LRDS_ROLLOUT_LINEAR, PREC, STAGE, TraitsLrds>(a, p, st, err, n);
   }
-  if constexpr (STAGE == 1) {
+  if constexpr (STAGE > 0) {
     if (traits_match<TraitsPis>(a.s)) return launch_one<LRDS_ROLLOUT_LINEAR, PREC, STAGE, TraitsPis>(a, p, st, err, n);
     if (traits_match<TraitsDds>(a.s)) return launch_one<LRDS_ROLLOUT_LINEAR, PREC, STAGE, TraitsDds>(a, p, st, err, n);
   }
