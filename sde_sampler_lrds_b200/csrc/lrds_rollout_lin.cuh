@@ -53,7 +53,7 @@ rollout_lin_kernel(const RolloutArgs a, const uint8_t* __restrict__ image, const
   mlp.phase = 0;
   mlp.bar_id = 1 + tile;
   mlp.bar_threads = min(4, nwarps - 4 * tile) * 32;
-  mlp.issuer = (tid & 127) == 0;
+  mlp.issuer = (tid & 127) == 32 * (min(4, nwarps - 4 * tile) - 1);  // the tile's last warp: the lightest sub-partition
   mlp.dp = s.mlp.d_pad;
 
   const int b_raw = blockIdx.x * NT + tid;

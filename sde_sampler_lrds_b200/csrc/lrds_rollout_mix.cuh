@@ -490,7 +490,10 @@ rollout_mix_kernel(const RolloutArgs a, const uint8_t* __restrict__ image, const
   mlp.phase = 0;
   mlp.bar_id = 1 + tile;
   mlp.bar_threads = tile_warps * 32;
-  mlp.issuer = (tid & 127) == 0;
+  // the tile's LAST warp issues the MMAs: with 14 warps the sub-partitions of warps 0/1 (mod 4) carry four warps and
+  // those of warps 2/3 three, so the issuing work (descriptor arithmetic, ~540 instructions per tile and step) goes
+  // to the lightly loaded ones wherever the tile has four warps
+  mlp.issuer = (tid & 127) == 32 * (tile_warps - 1);
   mlp.dp = a.s.mlp.d_pad;
   rollout_body_mix<PREC, VARIANT, EUBO>(a, cols, stage, mlp);
   ptx::tc_fence_before();

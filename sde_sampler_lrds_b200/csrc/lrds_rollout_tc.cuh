@@ -445,7 +445,7 @@ rollout_tc_kernel(const RolloutArgs a, const uint8_t* __restrict__ image, const 
   mlp.phase = 0;
   mlp.bar_id = 1 + tile;
   mlp.bar_threads = tile_warps * 32;
-  mlp.issuer = (tid & 127) == 0;
+  mlp.issuer = (tid & 127) == 32 * (tile_warps - 1);  // the tile's last warp: its sub-partition carries the fewest warps
   mlp.dp = a.s.mlp.d_pad;
   rollout_body<KIND, STAGE, TR>(a, cols, stage, mlp);
   ptx::tc_fence_before();
