@@ -256,14 +256,19 @@ def run_ours(args):
     # ---- end to end through the public API with host buffers ----------------------------------------------------
     x_host_out = torch.empty(B, DIM).pin_memory()
     rnd_host_out = torch.empty(B, 1).pin_memory()
-    barrier()
-    t0 = time.perf_counter()
-    for i in range(args.steps):
+    def e2e_step(seed):
         xd = x0_host.to(dev, non_blocking=True)
-        x, rnd, part = step(xd, 3000 + i)
+        x, rnd, part = step(xd, seed)
         x_host_out.copy_(x, non_blocking=True)
         rnd_host_out.copy_(rnd, non_blocking=True)
         torch.cuda.synchronize(dev)
+
+    for w in range(2):  # untimed: first touch of the pinned buffers, allocator entries of the staging tensors
+        e2e_step(2900 + w)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        e2e_step(3000 + i)
     barrier()
     e2e_s = time.perf_counter() - t0
     t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
