@@ -38,9 +38,9 @@ CPU_SAMPLE_B = 16384
 # Executed warp-instructions per particle-step of the f16x3 benchmark kernel, counted by ncu
 # (profiles/r01_mix_summary.md: smsp__inst_executed.sum / (B K)): the SIMT work (mixture quadratic forms, erf GELU,
 # Philox + Box-Muller, integrator) that bounds this path; used for the issue-slot figure in "roofline".
-WARP_INSTR_PER_PARTICLE_STEP = {"f16x3": 3.6036e9 / (B_PER_GPU * K_STEPS)}
+WARP_INSTR_PER_PARTICLE_STEP = {"f16x3": 3.5232e9 / (B_PER_GPU * K_STEPS)}
 # dram__bytes_read.sum + dram__bytes_write.sum of one launch of the same kernel (same capture)
-DRAM_BYTES_PER_LAUNCH = {"f16x3": 16_285_184 + 2_560}
+DRAM_BYTES_PER_LAUNCH = {"f16x3": 16_284_672 + 768}
 FAST_MODE_TOLERANCE = "log Z within 5e-2 abs, 99% of log-weights within 1e-2 rel (tests/test_rollout_parity_gpu.py)"
 
 
