@@ -157,6 +157,8 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: the contract is ONE JSON line
         dist.init_process_group("nccl", device_id=dev)
     group = dist.group.WORLD if world > 1 else None
 
