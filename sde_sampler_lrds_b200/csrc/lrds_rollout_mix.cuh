@@ -15,14 +15,11 @@
 // each, [32,64) the 8-dim chunk of the contraction (target a8 b8 | reference a8 b8) while D still holds the network's
 // output.  One chunk is in flight at a time: chunk c+1 is issued as soon as every warp of the tile has read chunk c.
 #pragma once
-#include <cstdlib>
-
 #include "lrds_rollout_tc.cuh"
 
 namespace lrds {
 
 constexpr int MIX_MAX_M = 16;
-constexpr int MIX_TAIL_BYTES = 64;  // the kernel's extra mbarriers
 constexpr int MIX_MAX_WARPS = 16;  // 3.5 tiles: one wave for 65536 particles on 148 SMs (128 registers: four warps share one 16K-register SM sub-partition)
 
 __host__ __device__ inline bool mix_tc_applicable(const lrds_spec& s) {
@@ -33,63 +30,9 @@ __host__ __device__ inline bool mix_tc_applicable(const lrds_spec& s) {
          s.target.gmm.mix_tc != nullptr && s.ref_t.mix_tc != nullptr && s.mlp.d_pad <= 64;
 }
 
-// Responsibilities of a mixture with M <= 16 components in registers (the arithmetic of gmm_pass1); returns the
-// mixture log-density.  Modes beyond M get weight zero.
-template <bool PIPE, bool SH>
-__device__ __forceinline__ float gmm_pass1_regs(const GmmViewT<SH>& g, int d, int dp, const Col4& x, float (&r)[MIX_MAX_M]) {
-  const int nq = (d + 3) >> 2;
-  const int rowq = dp >> 2;
-  const int M4 = (g.M + 3) >> 2;
-  float mx = -INFINITY;
-#pragma unroll
-  for (int mb = 0; mb < MIX_MAX_M / 4; ++mb) {
-    if (mb < M4) {
-      u64 qa[4] = {0, 0, 0, 0}, qb[4] = {0, 0, 0, 0};
-      PPtr<SH> p = g.sn + mb * rowq * 32;
-      if constexpr (PIPE) {
-        Pass1Ops<SH> A, B;
-        A.load(x, 0, p);
-        int c = 0;
-        for (; c + 1 < nq; c += 2, p = p + 64) {
-          B.load(x, c + 1, p + 32);
-          A.accumulate(qa, qb);
-          if (c + 2 < nq) A.load(x, c + 2, p + 64);
-          B.accumulate(qa, qb);
-        }
-        if (c < nq) A.accumulate(qa, qb);
-      } else {
-#pragma unroll 2
-        for (int c = 0; c < nq; ++c, p = p + 32) {
-          Pass1Ops<SH> A;
-          A.load(x, c, p);
-          A.accumulate(qa, qb);
-        }
-      }
-      const float4 lc = g.logc.ld4(mb);
-      r[4 * mb + 0] = lc.x - 0.5f * f2::hsum(qa[0], qb[0]);
-      r[4 * mb + 1] = lc.y - 0.5f * f2::hsum(qa[1], qb[1]);
-      r[4 * mb + 2] = lc.z - 0.5f * f2::hsum(qa[2], qb[2]);
-      r[4 * mb + 3] = lc.w - 0.5f * f2::hsum(qa[3], qb[3]);
-      mx = fmaxf(fmaxf(mx, fmaxf(r[4 * mb], r[4 * mb + 1])), fmaxf(r[4 * mb + 2], r[4 * mb + 3]));
-    } else {
-      r[4 * mb] = r[4 * mb + 1] = r[4 * mb + 2] = r[4 * mb + 3] = -INFINITY;
-    }
-  }
-  float s = 0.f;
-#pragma unroll
-  for (int mb = 0; mb < MIX_MAX_M / 4; ++mb) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) r[4 * mb + i] = __expf(r[4 * mb + i] - mx);
-    s += (r[4 * mb] + r[4 * mb + 1]) + (r[4 * mb + 2] + r[4 * mb + 3]);
-  }
-  const float inv = 1.0f / s;
-#pragma unroll
-  for (int i = 0; i < MIX_MAX_M; ++i) r[i] *= inv;
-  return mx + __logf(s);
-}
-
-// The same responsibilities with the operand traffic halved.  The quadratic forms are bound by the shared-memory
-// pipe, not by the FMA pipe: every (1/sigma, -mu/sigma) pair is used once per particle and a warp-uniform LDS.128
+// Responsibilities r = softmax_m(logc_m - q_m / 2) of a mixture with M <= 16 components in registers (the arithmetic
+// of gmm_pass1, lrds_device.cuh); returns the mixture log-density; modes beyond M get weight zero.  The quadratic forms
+// are bound by the shared-memory pipe, not by the FMA pipe: every (1/sigma, -mu/sigma) pair is used once per particle and a warp-uniform LDS.128
 // (one wavefront) feeds only two FFMA2.  Here the two half-warps split the mode blocks, and every thread evaluates
 // its modes for TWO particles - its own and the one of lane ^ 16 - so that each operand vector feeds four FFMA2;
 // the dims are the outer loop, so that a particle's coordinates are read once per call instead of once per mode
@@ -179,7 +122,6 @@ __device__ __forceinline__ float gmm_pass1_pair(const GmmViewT<SH>& g, int d, in
 }
 
 // log-density of a reference / prior block that may be a single Gaussian (the terminal cost)
-template <bool PIPE>
 __device__ __forceinline__ float gmm_logp_any(const GmmView& g, int d, int dp, const Col4& x) {
   if (g.M == 1) {
     const int nq = (d + 3) >> 2;
@@ -188,21 +130,16 @@ __device__ __forceinline__ float gmm_logp_any(const GmmView& g, int d, int dp, c
     return g.glogc.ld1(0) - 0.5f * q;
   }
   float r[MIX_MAX_M];
-  return gmm_pass1_regs<PIPE>(g, d, dp, x, r);
+  return gmm_pass1_pair(g, d, dp, x, r);
 }
 
 // ---- tensor-core side of the contraction (extends the drift-network policy; same tile, mbarrier and phase) --------
-// VARIANT bit 0: chunk hand-off by mbarrier (else named barrier); bit 1: step-buffer release by mbarrier (else CTA
-// barrier); bit 2: two-particle quadratic forms (gmm_pass1_pair)
-template <int PREC, int VARIANT>
+template <int PREC>
 struct MixTc : TcMlp<PREC> {
   using Base = TcMlp<PREC>;
   static constexpr uint32_t kRCol = 0, kDCol = 32;
   uint32_t lbo;  // bytes between the two 16-byte K chunks (modes 0-7 | 8-15) of an image part: 2 d_pad * 16
   uint32_t part_bytes;
-  uint64_t* ebar;  // the CTA's two "step buffer released" barriers
-  uint64_t* cbar;  // "columns [0, 64) of the tile are ready for the next contraction": one arrival per warp of the tile
-  uint32_t cphase;
 
   // r (16 responsibilities) -> fp16 (hi, lo) A operand `which` (0 target, 1 reference)
   __device__ __forceinline__ void store_r(int which, const float (&r)[MIX_MAX_M]) {
@@ -222,19 +159,13 @@ struct MixTc : TcMlp<PREC> {
   }
 
   // chunk c of both contractions -> columns [32, 64); images = shared-window addresses of the (hi | lo) blocks
-  // The hand-off is an mbarrier, not a named barrier: a warp that has stored its R rows / read its chunk arrives and
-  // goes on with its SIMT work; only the issuing thread waits for the tile's other warps.
+  // Named-barrier hand-off: every warp of the tile has stored its R rows / read the previous chunk.  (An mbarrier
+  // hand-off, where only the issuing thread waits, measured 4 % slower.)
   __device__ __forceinline__ void issue_chunk(int c, uint32_t tgt_img, uint32_t ref_img) {
     ptx::tmem_wait_st();
     ptx::tc_fence_before();
-    if constexpr (VARIANT & 1) {
-      __syncwarp();
-      if ((threadIdx.x & 31) == 0) ptx::mbar_arrive(cbar);
-    } else {
-      ptx::bar_sync(this->bar_id, this->bar_threads);
-    }
+    ptx::bar_sync(this->bar_id, this->bar_threads);
     if (this->issuer) {
-      if constexpr (VARIANT & 1) ptx::mbar_wait(cbar, cphase);
       ptx::tc_fence_after();
       const uint32_t idesc = ptx::make_idesc_f16(128, 16);
 #pragma unroll
@@ -249,7 +180,6 @@ struct MixTc : TcMlp<PREC> {
       }
       ptx::mma_commit(this->bar);
     }
-    cphase ^= 1u;
   }
   __device__ __forceinline__ void load_chunk(uint32_t (&m)[32]) {
     ptx::tmem_ld32(this->tm_lane + kDCol, m);
@@ -261,11 +191,8 @@ struct MixTc : TcMlp<PREC> {
 // EUBO: the noising rollout of compute_eubo (losses/oc.py:512-568): per step x <- mean x + std z first, then the
 // control and the reference score at the new point enter the cost; x is not integrated by the control.  The step's
 // increments are generated twice (for the update and for the cost) instead of being kept per particle.
-template <int PREC, int VARIANT, bool EUBO>
-__device__ __forceinline__ void rollout_body_mix(const RolloutArgs& a, float* smem, uint8_t* stage, MixTc<PREC, VARIANT>& mlp) {
-  constexpr bool PIPE = MixTc<PREC, VARIANT>::kPipe;
-  constexpr bool EBAR = (VARIANT & 2) != 0;
-  constexpr bool PAIR = (VARIANT & 4) != 0;
+template <int PREC, bool EUBO>
+__device__ __forceinline__ void rollout_body_mix(const RolloutArgs& a, float* smem, uint8_t* stage, MixTc<PREC>& mlp) {
   const lrds_spec& s = a.s;
   const int NT = blockDim.x;
   const int tid = threadIdx.x;
@@ -292,15 +219,11 @@ __device__ __forceinline__ void rollout_body_mix(const RolloutArgs& a, float* sm
     stage_step(dst, s, SL, k, bar);
     ptx::bulk_g2s(dst + mix_off_r, rmix_g + (int64_t)k * s.ref_t.step_stride_mix_tc, SL.ref_mix_bytes, bar);
   };
-  // sbar[0..1]: "step buffer filled" (TMA transaction bytes); ebar[0..1] (behind the tile barriers of the kernel):
-  // "step buffer released", one arrival per warp.  No CTA-wide barrier inside the loop: tiles may drift apart by up
-  // to one step, which keeps their tensor-core waits out of phase.
-  uint64_t* ebar = mlp.ebar;
+  // sbar[0..1]: "step buffer filled" (TMA transaction bytes); a CTA barrier per step protects the buffer the prefetch
+  // overwrites (an mbarrier release that lets the tiles drift apart by a step measured the same)
   if (tid == 0) {
     ptx::mbar_init(sbar, 1);
     ptx::mbar_init(sbar + 1, 1);
-    ptx::mbar_init(ebar, NT >> 5);
-    ptx::mbar_init(ebar + 1, NT >> 5);
     ptx::fence_mbar_init();
   }
   __syncthreads();
@@ -320,16 +243,14 @@ __device__ __forceinline__ void rollout_body_mix(const RolloutArgs& a, float* sm
   if constexpr (EUBO) {  // rnd = reference_log_prob(x) - terminal_unnorm_log_prob(x)   (oc.py:536)
     ptx::mbar_wait(sbar, 0);  // the staged target mixture (the same phase as the first step's buffer)
     float rt[MIX_MAX_M];
-    const float lref = gmm_logp_any<PIPE>(gmm_at(s.ref_0, 0), d, dp, P.x);
-    const float ltgt = clipf(PAIR ? gmm_pass1_pair(tv, d, dp, P.x, rt) : gmm_pass1_regs<PIPE>(tv, d, dp, P.x, rt), s.clip_target);
+    const float lref = gmm_logp_any(gmm_at(s.ref_0, 0), d, dp, P.x);
+    const float ltgt = clipf(gmm_pass1_pair(tv, d, dp, P.x, rt), s.clip_target);
     rnd = lref - ltgt;
   }
 
   for (int k = 0; k < K; ++k) {
-    if constexpr (!EBAR) __syncthreads();
+    __syncthreads();  // every warp has finished step k-1, whose buffer the prefetch below overwrites
     if (tid == 0 && k + 1 < K) {
-      // every warp has released the buffer of step k-1, which the prefetch overwrites
-      if (EBAR && k >= 1) ptx::mbar_wait(ebar + ((k + 1) & 1), (uint32_t)((k - 1) >> 1) & 1u);
       ptx::mbar_expect_tx(sbar + ((k + 1) & 1), SL.buf_bytes);
       stage_step_mix(stage + SL.off_buf + ((k + 1) & 1) * SL.buf_bytes, k + 1, sbar + ((k + 1) & 1));
     }
@@ -360,11 +281,9 @@ __device__ __forceinline__ void rollout_body_mix(const RolloutArgs& a, float* sm
     mlp.template hidden<true>(row + LRDS_STEP_BIAS1, P.x);  // ends with the output GEMM complete: A region free
     {
       float r[MIX_MAX_M];
-      if constexpr (PAIR) gmm_pass1_pair(tv, d, dp, P.x, r);
-      else gmm_pass1_regs<PIPE>(tv, d, dp, P.x, r);
+      gmm_pass1_pair(tv, d, dp, P.x, r);
       mlp.store_r(0, r);
-      if constexpr (PAIR) gmm_pass1_pair(rv, d, dp, P.x, r);
-      else gmm_pass1_regs<PIPE>(rv, d, dp, P.x, r);
+      gmm_pass1_pair(rv, d, dp, P.x, r);
       mlp.store_r(1, r);
     }
     mlp.issue_chunk(0, tgt_img, ref_img);
@@ -428,15 +347,11 @@ __device__ __forceinline__ void rollout_body_mix(const RolloutArgs& a, float* sm
       rnd += wcost * f2::hsum1(su2);
       rnd += wito * f2::hsum1(sito);
     }
-    if constexpr (EBAR) {
-      __syncwarp();  // the last contraction of the step has completed (wait() above): this warp is done with the buffer
-      if ((tid & 31) == 0) ptx::mbar_arrive(ebar + (k & 1));
-    }
   }
   if constexpr (!EUBO) {  // terminal cost: rnd += reference_log_prob(x) - terminal_unnorm_log_prob(x)   (oc.py:505, 645)
-    const float lref = gmm_logp_any<PIPE>(gmm_at(s.ref_0, 0), d, dp, P.x);
+    const float lref = gmm_logp_any(gmm_at(s.ref_0, 0), d, dp, P.x);
     float rt[MIX_MAX_M];
-    const float ltgt = clipf(PAIR ? gmm_pass1_pair(tv, d, dp, P.x, rt) : gmm_pass1_regs<PIPE>(tv, d, dp, P.x, rt), s.clip_target);
+    const float ltgt = clipf(gmm_pass1_pair(tv, d, dp, P.x, rt), s.clip_target);
     rnd += lref - ltgt;
   }
 
@@ -448,7 +363,7 @@ __device__ __forceinline__ void rollout_body_mix(const RolloutArgs& a, float* sm
 }
 
 // shared memory: [weight image | mbarriers + TMEM slot | operand stage | particle columns]
-template <int PREC, int VARIANT, bool EUBO>
+template <int PREC, bool EUBO>
 __global__ void __launch_bounds__(MIX_MAX_WARPS * 32, 1)
 rollout_mix_kernel(const RolloutArgs a, const uint8_t* __restrict__ image, const uint32_t tmem_cols) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -457,13 +372,11 @@ rollout_mix_kernel(const RolloutArgs a, const uint8_t* __restrict__ image, const
   uint8_t* img = smem_raw;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + TL.bytes);  // [0] image, [1 + t] tile t
   uint32_t* slot = reinterpret_cast<uint32_t*>(smem_raw + TL.bytes + 48);
-  uint64_t* xbars = reinterpret_cast<uint64_t*>(smem_raw + TL.bytes + TC_TAIL_BYTES);  // [0..3] chunk hand-off per tile, [4..5] buffer release
-  uint8_t* stage = smem_raw + TL.bytes + TC_TAIL_BYTES + MIX_TAIL_BYTES;
+  uint8_t* stage = smem_raw + TL.bytes + TC_TAIL_BYTES;
   float* cols = reinterpret_cast<float*>(stage + ((stage_layout(a.s, 2, true).total + 15u) & ~15u));
   if (warp == 0) ptx::tmem_alloc(slot, tmem_cols);
   if (tid == 0) {
     for (int i = 0; i < 5; ++i) ptx::mbar_init(bars + i, 1);
-    for (int t = 0; t < 4; ++t) ptx::mbar_init(xbars + t, (uint32_t)max(1, min(4, nwarps - 4 * t)));
     ptx::fence_mbar_init();
   }
   ptx::tc_fence_before();
@@ -477,10 +390,7 @@ rollout_mix_kernel(const RolloutArgs a, const uint8_t* __restrict__ image, const
   const uint32_t tmem = *slot;
   const int tile = warp >> 2;
   const int tile_warps = min(4, nwarps - 4 * tile);
-  MixTc<PREC, VARIANT> mlp;
-  mlp.cbar = xbars + tile;
-  mlp.cphase = 0;
-  mlp.ebar = xbars + 4;
+  MixTc<PREC> mlp;
   mlp.L = TL;
   mlp.img = img;
   mlp.img_s = ptx::smem_u32(img);
@@ -495,7 +405,7 @@ rollout_mix_kernel(const RolloutArgs a, const uint8_t* __restrict__ image, const
   // to the lightly loaded ones wherever the tile has four warps
   mlp.issuer = (tid & 127) == 32 * (tile_warps - 1);
   mlp.dp = a.s.mlp.d_pad;
-  rollout_body_mix<PREC, VARIANT, EUBO>(a, cols, stage, mlp);
+  rollout_body_mix<PREC, EUBO>(a, cols, stage, mlp);
   ptx::tc_fence_before();
   __syncthreads();
   if (warp == 0) ptx::tmem_dealloc(tmem, tmem_cols);
@@ -507,7 +417,7 @@ inline bool plan_rollout_mix(const lrds_spec& s, int smem_cap, int sms, TcPlan* 
   const TcLayout TL = tc_layout(s.d, s.mlp.num_hidden, s.precision);
   if (TL.tile_cols != 128 || TL.parts * TL.a_cols < 64) return false;
   const ColLayout CL = col_layout(s, true);
-  const size_t fixed = (size_t)TL.bytes + TC_TAIL_BYTES + MIX_TAIL_BYTES + ((stage_layout(s, 2, true).total + 15u) & ~15u);
+  const size_t fixed = (size_t)TL.bytes + TC_TAIL_BYTES + ((stage_layout(s, 2, true).total + 15u) & ~15u);
   const size_t per_warp = (size_t)CL.total * 32 * sizeof(float);
   if (fixed + per_warp > (size_t)smem_cap) return false;
   int wmax = (int)(((size_t)smem_cap - fixed) / per_warp);
@@ -516,10 +426,6 @@ inline bool plan_rollout_mix(const lrds_spec& s, int smem_cap, int sms, TcPlan* 
   const int waves = (need + sms * wmax - 1) / (sms * wmax);
   int w = (need + sms * waves - 1) / (sms * waves);
   w = w < 1 ? 1 : (w > wmax ? wmax : w);
-  if (const char* e = getenv("LRDS_MIX_WARPS")) {  // tuning override
-    const int v = atoi(e);
-    if (v >= 1 && v <= wmax) w = v;
-  }
   const int tiles = (w + 3) / 4;
   uint32_t cols = 32;
   while ((int)cols < tiles * TL.tile_cols) cols <<= 1;

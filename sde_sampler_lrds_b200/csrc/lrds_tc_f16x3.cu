@@ -1,7 +1,5 @@
 // Tensor-core rollout kernels of one precision (own translation unit: the precisions compile in parallel), plus the
 // kernel that also runs the mixture-score contractions on the tensor core (lrds_rollout_mix.cuh).
-#include <cstdlib>
-
 #include "lrds_rollout_cmcd_tc.cuh"
 #include "lrds_rollout_lin.cuh"
 #include "lrds_rollout_mix.cuh"
@@ -9,23 +7,6 @@
 
 namespace lrds {
 template int launch_prec<LRDS_PRECISION_F16X3>(const RolloutArgs&, const TcPlan&, cudaStream_t, char*, size_t);
-
-template <int VARIANT>
-static int launch_mix_variant(const RolloutArgs& a, const TcPlan& p, cudaStream_t st, char* err, size_t n) {
-  auto kernel = a.s.kind == LRDS_ROLLOUT_EUBO_LINEAR ? rollout_mix_kernel<LRDS_PRECISION_F16X3, VARIANT, true>
-                                                      : rollout_mix_kernel<LRDS_PRECISION_F16X3, VARIANT, false>;
-  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
-  if (e == cudaSuccess) {
-    kernel<<<p.grid, p.warps * 32, p.smem, st>>>(a, static_cast<const uint8_t*>(a.s.mlp.tc_image), p.tmem_cols);
-    e = cudaGetLastError();
-  }
-  if (e != cudaSuccess) {
-    snprintf(err, n, "mixture tensor-core rollout launch (grid %d x %d threads, %zu B smem, %u TMEM cols): %s", p.grid,
-             p.warps * 32, p.smem, p.tmem_cols, cudaGetErrorString(e));
-    return LRDS_ERR_CUDA;
-  }
-  return LRDS_OK;
-}
 
 template <bool EM, bool PHI4>
 static int launch_lin_variant(const RolloutArgs& a, const TcPlan& p, cudaStream_t st, char* err, size_t n) {
@@ -66,14 +47,18 @@ int launch_cmcd_tc_f16x3(const RolloutArgs& a, const TcPlan& p, cudaStream_t st,
 }
 
 int launch_mix_f16x3(const RolloutArgs& a, const TcPlan& p, cudaStream_t st, char* err, size_t n) {
-  const char* v = getenv("LRDS_MIX_VARIANT");  // tuning switch for the synchronisation scheme (default: mbarriers)
-  switch (v ? atoi(v) : 4) {
-    case 0: return launch_mix_variant<0>(a, p, st, err, n);
-    case 1: return launch_mix_variant<1>(a, p, st, err, n);
-    case 2: return launch_mix_variant<2>(a, p, st, err, n);
-    case 3: return launch_mix_variant<3>(a, p, st, err, n);
-    case 6: return launch_mix_variant<6>(a, p, st, err, n);
-    default: return launch_mix_variant<4>(a, p, st, err, n);
+  auto kernel = a.s.kind == LRDS_ROLLOUT_EUBO_LINEAR ? rollout_mix_kernel<LRDS_PRECISION_F16X3, true>
+                                                      : rollout_mix_kernel<LRDS_PRECISION_F16X3, false>;
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
+  if (e == cudaSuccess) {
+    kernel<<<p.grid, p.warps * 32, p.smem, st>>>(a, static_cast<const uint8_t*>(a.s.mlp.tc_image), p.tmem_cols);
+    e = cudaGetLastError();
   }
+  if (e != cudaSuccess) {
+    snprintf(err, n, "mixture tensor-core rollout launch (grid %d x %d threads, %zu B smem, %u TMEM cols): %s", p.grid,
+             p.warps * 32, p.smem, p.tmem_cols, cudaGetErrorString(e));
+    return LRDS_ERR_CUDA;
+  }
+  return LRDS_OK;
 }
 }  // namespace lrds
