@@ -152,13 +152,16 @@ def run_ours(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # The contract is ONE JSON line on stdout: libraries that print there (NCCL's version banner at communicator
+    # creation) are sent to stderr; the line is written to the saved descriptor at the end.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the rollout has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: the contract is ONE JSON line
         dist.init_process_group("nccl", device_id=dev)
     group = dist.group.WORLD if world > 1 else None
 
@@ -324,7 +327,8 @@ def run_ours(args):
         line["cpu_baseline"] = {"value": cpu_value, "unit": UNIT, "cores": threads, "kind": "port",
                                 "sample": f"B={CPU_SAMPLE_B} of {B} particles, all K={K_STEPS} steps, d={DIM}; "
                                           f"{cpu_dt:.1f} s per rollout, torch {torch.__version__} CPU threads={threads}"}
-    print(json.dumps(line))
+    sys.stdout.flush()
+    os.write(real_stdout, (json.dumps(line) + "\n").encode())
     if group is not None:
         dist.destroy_process_group()
 
