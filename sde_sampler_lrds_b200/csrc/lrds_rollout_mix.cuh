@@ -22,13 +22,42 @@ namespace lrds {
 constexpr int MIX_MAX_M = 16;
 constexpr int MIX_MAX_WARPS = 16;  // 3.5 tiles: one wave for 65536 particles on 148 SMs (128 registers: four warps share one 16K-register SM sub-partition)
 
-__host__ __device__ inline bool mix_tc_applicable(const lrds_spec& s) {
-  return s.precision == LRDS_PRECISION_F16X3 && (s.kind == LRDS_ROLLOUT_LINEAR || s.kind == LRDS_ROLLOUT_EUBO_LINEAR) &&
-         s.update_form == LRDS_UPDATE_AXPY && s.ito_form == LRDS_ITO_SCALED && s.ctrl_kind == LRDS_CTRL_SCORE &&
-         s.target.kind == LRDS_DISTR_GMM &&
-         s.has_ref_ctrl && s.target.gmm.M > 1 && s.target.gmm.M <= MIX_MAX_M && s.ref_t.M > 1 && s.ref_t.M <= MIX_MAX_M &&
-         s.target.gmm.mix_tc != nullptr && s.ref_t.mix_tc != nullptr && s.mlp.d_pad <= 64;
+// Compile-time configuration of the kernel: which of the two score contractions run on the tensor core, and the update.
+//   TGT  1: ScoreCtrl over a mixture target (contraction on tcgen05)   2: ScoreCtrl over the PhiFour lattice (stencil)
+//        0: ClippedCtrl (no target score)
+//   REFMIX  the time-marginal reference is a mixture (contraction on tcgen05) / a single Gaussian (one FMA per dim)
+//   EM   Euler-Maruyama update and Ito term (losses/oc.py:277-284) instead of the exponential-integrator axpy
+template <bool EUBO_, int TGT_, bool REFMIX_, bool EM_>
+struct MixCfg {
+  static constexpr bool kEubo = EUBO_, kRefMix = REFMIX_, kEm = EM_;
+  static constexpr int kTgt = TGT_;
+};
+using MixBench = MixCfg<false, 1, true, false>;  // the benchmark configuration
+
+// index of the configuration that serves `s` (see launch_mix_f16x3), or -1
+__host__ __device__ inline int mix_tc_config(const lrds_spec& s) {
+  if (s.precision != LRDS_PRECISION_F16X3 || !s.has_ref_ctrl || s.mlp.d_pad > 64) return -1;
+  const bool tmix = s.ctrl_kind == LRDS_CTRL_SCORE && s.target.kind == LRDS_DISTR_GMM && s.target.gmm.M > 1 &&
+                    s.target.gmm.M <= MIX_MAX_M && s.target.gmm.mix_tc != nullptr;
+  const bool tphi = s.ctrl_kind == LRDS_CTRL_SCORE && s.target.kind == LRDS_DISTR_PHI4;
+  const bool tnone = s.ctrl_kind == LRDS_CTRL_CLIPPED &&
+                     (s.target.kind != LRDS_DISTR_GMM || s.target.gmm.M <= MIX_MAX_M) && s.target.kind != LRDS_DISTR_LOGREG;
+  const bool rmix = s.ref_t.M > 1 && s.ref_t.M <= MIX_MAX_M && s.ref_t.mix_tc != nullptr;
+  const bool rgauss = s.ref_t.M == 1;
+  const bool axpy = s.update_form == LRDS_UPDATE_AXPY && s.ito_form == LRDS_ITO_SCALED;
+  const bool em = s.update_form == LRDS_UPDATE_EM && s.ito_form == LRDS_ITO_EM;
+  if (s.ref_0.M > MIX_MAX_M) return -1;
+  if (s.target.kind == LRDS_DISTR_GMM && s.target.gmm.M > 1 && s.target.gmm.mix_tc == nullptr) return -1;  // staged with the target
+  if (s.kind == LRDS_ROLLOUT_EUBO_LINEAR) return (tmix && rmix && axpy) ? 1 : -1;
+  if (s.kind != LRDS_ROLLOUT_LINEAR) return -1;
+  if (tmix && rmix && axpy) return 0;
+  if (tmix && rgauss && axpy) return 2;
+  if (tmix && rgauss && em) return 3;
+  if (tphi && rmix && axpy) return 4;
+  if (tnone && rmix && axpy) return 5;
+  return -1;
 }
+__host__ __device__ inline bool mix_tc_applicable(const lrds_spec& s) { return mix_tc_config(s) >= 0; }
 
 // Responsibilities r = softmax_m(logc_m - q_m / 2) of a mixture with M <= 16 components in registers (the arithmetic
 // of gmm_pass1, lrds_device.cuh); returns the mixture log-density; modes beyond M get weight zero.  The quadratic forms
@@ -161,6 +190,7 @@ struct MixTc : TcMlp<PREC> {
   // chunk c of both contractions -> columns [32, 64); images = shared-window addresses of the (hi | lo) blocks
   // Named-barrier hand-off: every warp of the tile has stored its R rows / read the previous chunk.  (An mbarrier
   // hand-off, where only the issuing thread waits, measured 4 % slower.)
+  template <bool TGT = true, bool REF = true>
   __device__ __forceinline__ void issue_chunk(int c, uint32_t tgt_img, uint32_t ref_img) {
     ptx::tmem_wait_st();
     ptx::tc_fence_before();
@@ -169,7 +199,7 @@ struct MixTc : TcMlp<PREC> {
       ptx::tc_fence_after();
       const uint32_t idesc = ptx::make_idesc_f16(128, 16);
 #pragma unroll
-      for (int which = 0; which < 2; ++which) {
+      for (int which = TGT ? 0 : 1; which < (REF ? 2 : 1); ++which) {
         const uint32_t img = (which ? ref_img : tgt_img) + (uint32_t)c * 256u;  // 16 rows of 16 bytes per chunk
         const uint32_t dcol = this->tm_tile + kDCol + which * 16;
         const uint32_t a_hi = this->tm_tile + kRCol + which * 16, a_lo = a_hi + 8;
@@ -191,8 +221,9 @@ struct MixTc : TcMlp<PREC> {
 // EUBO: the noising rollout of compute_eubo (losses/oc.py:512-568): per step x <- mean x + std z first, then the
 // control and the reference score at the new point enter the cost; x is not integrated by the control.  The step's
 // increments are generated twice (for the update and for the cost) instead of being kept per particle.
-template <int PREC, bool EUBO>
+template <int PREC, class CFG>
 __device__ __forceinline__ void rollout_body_mix(const RolloutArgs& a, float* smem, uint8_t* stage, MixTc<PREC>& mlp) {
+  constexpr bool EUBO = CFG::kEubo, TMIX = CFG::kTgt == 1, TPHI = CFG::kTgt == 2, RMIX = CFG::kRefMix, EM = CFG::kEm;
   const lrds_spec& s = a.s;
   const int NT = blockDim.x;
   const int tid = threadIdx.x;
@@ -217,7 +248,7 @@ __device__ __forceinline__ void rollout_body_mix(const RolloutArgs& a, float* sm
   const uint32_t mix_off_r = SL.row_bytes + SL.ref_logc_bytes + SL.ref_param_bytes;  // inside a step buffer
   auto stage_step_mix = [&](uint8_t* dst, int k, uint64_t* bar) {
     stage_step(dst, s, SL, k, bar);
-    ptx::bulk_g2s(dst + mix_off_r, rmix_g + (int64_t)k * s.ref_t.step_stride_mix_tc, SL.ref_mix_bytes, bar);
+    if constexpr (RMIX) ptx::bulk_g2s(dst + mix_off_r, rmix_g + (int64_t)k * s.ref_t.step_stride_mix_tc, SL.ref_mix_bytes, bar);
   };
   // sbar[0..1]: "step buffer filled" (TMA transaction bytes); a CTA barrier per step protects the buffer the prefetch
   // overwrites (an mbarrier release that lets the tiles drift apart by a step measured the same)
@@ -229,23 +260,37 @@ __device__ __forceinline__ void rollout_body_mix(const RolloutArgs& a, float* sm
   __syncthreads();
   if (tid == 0) {
     ptx::mbar_expect_tx(sbar, SL.tgt_bytes + SL.buf_bytes);
-    stage_gmm(stage + SL.off_tgt, tv0, SL.tgt_logc_bytes, SL.tgt_param_bytes, sbar);
-    ptx::bulk_g2s(stage + SL.off_tgt + mix_off_t, tmix_g, SL.tgt_mix_bytes, sbar);
+    if (SL.tgt_bytes) {  // a mixture target is staged whether or not the control uses its score (terminal cost)
+      stage_gmm(stage + SL.off_tgt, tv0, SL.tgt_logc_bytes, SL.tgt_param_bytes, sbar);
+      ptx::bulk_g2s(stage + SL.off_tgt + mix_off_t, tmix_g, SL.tgt_mix_bytes, sbar);
+    }
     stage_step_mix(stage + SL.off_buf, 0, sbar);
   }
   const GmmViewT<true> tv = staged_view(stage + SL.off_tgt, tv0, SL.tgt_logc_bytes, SL.tgt_param_bytes);
   const uint32_t tgt_img = ptx::smem_u32(stage + SL.off_tgt + mix_off_t);
   const uint32_t tgt_img_bytes = SL.tgt_mix_bytes - 16u, ref_img_bytes = SL.ref_mix_bytes - 16u;
   mlp.lbo = (uint32_t)(2 * dp) * 16u;
-  mlp.part_bytes = tgt_img_bytes / 2u;  // both mixtures are padded to 16 modes: equal image sizes
+  mlp.part_bytes = (TMIX ? tgt_img_bytes : ref_img_bytes) / 2u;  // mixtures are padded to 16 modes: equal image sizes
+  // terminal_unnorm_log_prob(x) of whatever the target is (clipped by the caller)
+  auto target_logp = [&]() -> float {
+    if (s.target.kind == LRDS_DISTR_GMM) {
+      if (s.target.gmm.M == 1) return gmm_logp_any(tv0, d, dp, P.x);
+      float rt[MIX_MAX_M];
+      return gmm_pass1_pair(tv, d, dp, P.x, rt);
+    }
+    if (s.target.kind == LRDS_DISTR_PHI4) return phi4_logp(s.target.phi4, d, P.x);
+    return 0.f;
+  };
+  // lattice score (lrds_rollout_lin.cuh): x (p1 + p3 x^2) + p0 + pn ((x_{j+1} + x_{j-1}) - 2 x)
+  const float coef = s.target.phi4.a * (float)d, beta = s.target.phi4.beta;
+  const u64 p0 = f2::pk(-beta * s.target.phi4.b / coef), p1 = f2::pk(beta / coef), p3 = f2::pk(-beta / coef),
+            pn = f2::pk(beta * coef), m2 = f2::pk(-2.0f);
   const int nchunk = dp / JC;
   float rnd = 0.f;
   if constexpr (EUBO) {  // rnd = reference_log_prob(x) - terminal_unnorm_log_prob(x)   (oc.py:536)
     ptx::mbar_wait(sbar, 0);  // the staged target mixture (the same phase as the first step's buffer)
-    float rt[MIX_MAX_M];
     const float lref = gmm_logp_any(gmm_at(s.ref_0, 0), d, dp, P.x);
-    const float ltgt = clipf(gmm_pass1_pair(tv, d, dp, P.x, rt), s.clip_target);
-    rnd = lref - ltgt;
+    rnd = lref - clipf(target_logp(), s.clip_target);
   }
 
   for (int k = 0; k < K; ++k) {
@@ -263,8 +308,9 @@ __device__ __forceinline__ void rollout_body_mix(const RolloutArgs& a, float* sm
     const float A = rowp.ld1(LRDS_STEP_A), Bc = rowp.ld1(LRDS_STEP_B), Cc = rowp.ld1(LRDS_STEP_C);
     const float wcost = rowp.ld1(LRDS_STEP_W_COST), wito = rowp.ld1(LRDS_STEP_W_ITO);
     const float gamma = rowp.ld1(LRDS_STEP_GAMMA);
-    const float ust = *reinterpret_cast<const float*>(stage + SL.off_tgt + mix_off_t + tgt_img_bytes);
-    const float usr = *reinterpret_cast<const float*>(buf + mix_off_r + ref_img_bytes);
+    const float ust = TMIX ? *reinterpret_cast<const float*>(stage + SL.off_tgt + mix_off_t + tgt_img_bytes) : 1.0f;
+    const float usr = RMIX ? *reinterpret_cast<const float*>(buf + mix_off_r + ref_img_bytes) : 1.0f;
+    const GmmView rg = gmm_at(s.ref_t, k);  // single-Gaussian reference: read from global memory (!RMIX)
 
     if constexpr (EUBO) {  // x <- mean x + std z   (oc.py:550-552)
       const u64 mean2 = f2::pk(rowp.ld1(LRDS_STEP_EU_A)), std2 = f2::pk(rowp.ld1(LRDS_STEP_EU_B));
@@ -281,54 +327,92 @@ __device__ __forceinline__ void rollout_body_mix(const RolloutArgs& a, float* sm
     mlp.template hidden<true>(row + LRDS_STEP_BIAS1, P.x);  // ends with the output GEMM complete: A region free
     {
       float r[MIX_MAX_M];
-      gmm_pass1_pair(tv, d, dp, P.x, r);
-      mlp.store_r(0, r);
-      gmm_pass1_pair(rv, d, dp, P.x, r);
-      mlp.store_r(1, r);
+      if constexpr (TMIX) {
+        gmm_pass1_pair(tv, d, dp, P.x, r);
+        mlp.store_r(0, r);
+      }
+      if constexpr (RMIX) {
+        gmm_pass1_pair(rv, d, dp, P.x, r);
+        mlp.store_r(1, r);
+      }
     }
-    mlp.issue_chunk(0, tgt_img, ref_img);
+    mlp.template issue_chunk<TMIX, RMIX>(0, tgt_img, ref_img);
     // The integrator update on packed fp32x2 pairs of dims.  The images hold -1/var, so a score is one FFMA2; their
     // power-of-two un-scales are folded into the ScoreCtrl factor / the clip bound (target) and into the FFMA that
     // adds the control (reference).  Padded dims need no masks: their image rows, output weights, biases and noise
     // are zero, so u = scores = z = 0 and x stays 0.
-    const u64 A2 = f2::pk(A), B2 = f2::pk(Bc), C2 = f2::pk(Cc), usr2 = f2::pk(usr);
+    // update x' = ca x + cr r + cu u + cz z:  axpy (A, B, B, C);  EM x + ((-(f x) + sigma^2 r) + sigma u) dt + sigma (z sqrt dt)
+    const float dt = EM ? rowp.ld1(LRDS_STEP_DT) : 0.f, sqdt = EM ? rowp.ld1(LRDS_STEP_SQRT_DT) : 0.f;
+    const u64 A2 = f2::pk(EM ? 1.0f - A * dt : A), B2 = f2::pk(EM ? Bc * dt : Bc), C2 = f2::pk(EM ? Bc * sqdt : Cc);
+    const u64 usr2 = f2::pk(usr), R2 = f2::pk((EM ? Cc * dt : Bc) * usr);
     const u64 gs2 = f2::pk((cc.scale_score * gamma) * ust);
     const float bts = cc.bound_score / ust;
+    const float wz = EM ? sqdt : wito;  // weight of sum(u z) in the log-weight (oc.py:284 / 499)
     u64 su2 = 0, sito = 0;
+    float xm = 0.f;  // lattice target: x_{j0-1} of the state before this step's update
     for (int c = 0; c < nchunk; ++c) {
       const int j0 = c * JC;
       uint32_t m[32];
       mlp.wait();
       mlp.load_chunk(m);
-      if (c + 1 < nchunk) mlp.issue_chunk(c + 1, tgt_img, ref_img);
+      if (c + 1 < nchunk) mlp.template issue_chunk<TMIX, RMIX>(c + 1, tgt_img, ref_img);
       const ulonglong2 xa = P.x.ldu(2 * c), xb = P.x.ldu(2 * c + 1);
       const u64 X[4] = {xa.x, xa.y, xb.x, xb.y};
       u64 U[4], XN[4];
       float z[JC];
       mlp.out_chunk2(j0, U);
       noise_chunk(a, k, b, j0, z);
+      float xs[JC + 2];  // lattice target: the chunk with its two neighbours (state before the update)
+      if constexpr (TPHI) {
+        xs[0] = xm;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) f2::unpack(X[q], xs[1 + 2 * q], xs[2 + 2 * q]);
+        xs[JC + 1] = (j0 + JC < dp) ? P.x(j0 + JC) : 0.f;
+        xm = xs[JC];
+      }
+      u64 GM[4], GI[4];  // single-Gaussian reference: mean and 1/var of the chunk
+      if constexpr (!RMIX) {
+        const ulonglong2 g0 = rg.mu.ld2(2 * c), g1 = rg.mu.ld2(2 * c + 1), i0 = rg.ivar.ld2(2 * c), i1 = rg.ivar.ld2(2 * c + 1);
+        GM[0] = g0.x; GM[1] = g0.y; GM[2] = g1.x; GM[3] = g1.y;
+        GI[0] = i0.x; GI[1] = i0.y; GI[2] = i1.x; GI[3] = i1.y;
+      }
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         const u64 ta = f2::pack(__uint_as_float(m[2 * q]), __uint_as_float(m[2 * q + 1]));
         const u64 tb = f2::pack(__uint_as_float(m[8 + 2 * q]), __uint_as_float(m[9 + 2 * q]));
         const u64 ra = f2::pack(__uint_as_float(m[16 + 2 * q]), __uint_as_float(m[17 + 2 * q]));
         const u64 rb = f2::pack(__uint_as_float(m[24 + 2 * q]), __uint_as_float(m[25 + 2 * q]));
-        float t0, t1, u0, u1;
-        f2::unpack(f2::fma(X[q], ta, tb), t0, t1);  // raw target score (image units)
+        float t0 = 0.f, t1 = 0.f, u0, u1;
+        if constexpr (TMIX) f2::unpack(f2::fma(X[q], ta, tb), t0, t1);  // raw target score (image units)
+        if constexpr (TPHI) {
+          const u64 nb = f2::pack(xs[2 * q] + xs[2 * q + 2], xs[2 * q + 1] + xs[2 * q + 3]);
+          const u64 t = f2::fma(X[q], f2::fma(f2::mul(X[q], X[q]), p3, p1), f2::fma(pn, f2::fma(X[q], m2, nb), p0));
+          f2::unpack(t, t0, t1);
+          if (j0 + JC > d) {  // padded lattice sites have no score
+            if (j0 + 2 * q >= d) t0 = 0.f;
+            if (j0 + 2 * q + 1 >= d) t1 = 0.f;
+          }
+        }
         f2::unpack(U[q], u0, u1);
-        const u64 tsc = f2::pack(clipb(t0, bts), clipb(t1, bts));
         const u64 uc = f2::pack(clipb(u0, cc.bound_model), clipb(u1, cc.bound_model));
-        const u64 v = f2::fma(tsc, gs2, uc);  // control u
+        u64 v = uc;  // control u
+        if constexpr (TMIX || TPHI) v = f2::fma(f2::pack(clipb(t0, bts), clipb(t1, bts)), gs2, uc);
+        // reference score in the units of R2: mixture = accumulator (image units), Gaussian = -(x - mu) / var
+        const u64 rraw = RMIX ? f2::fma(X[q], ra, rb) : f2::mul(f2::fma(X[q], f2::pk(-1.0f), GM[q]), GI[q]);
         const u64 z2 = f2::pack(z[2 * q], z[2 * q + 1]);
         if constexpr (EUBO) {  // cost += u (r + u / 2),  gz += u z   (oc.py:556-563; g = u for the axpy updates)
-          su2 = f2::fma(v, f2::fma(v, f2::pk(0.5f), f2::mul(f2::fma(X[q], ra, rb), usr2)), su2);
+          su2 = f2::fma(v, f2::fma(v, f2::pk(0.5f), f2::mul(rraw, usr2)), su2);
           sito = f2::fma(v, z2, sito);
           continue;
         }
         su2 = f2::fma(v, v, su2);
         sito = f2::fma(v, z2, sito);
-        const u64 rv2 = f2::fma(f2::fma(X[q], ra, rb), usr2, v);  // reference score + u
-        XN[q] = f2::fma(C2, z2, f2::fma(A2, X[q], f2::mul(B2, rv2)));
+        if constexpr (EM) {
+          XN[q] = f2::fma(C2, z2, f2::fma(A2, X[q], f2::fma(R2, rraw, f2::mul(B2, v))));
+        } else {
+          const u64 rv2 = f2::fma(rraw, usr2, v);  // reference score + u
+          XN[q] = f2::fma(C2, z2, f2::fma(A2, X[q], f2::mul(B2, rv2)));
+        }
       }
       if constexpr (EUBO) continue;
       P.x.stu(2 * c, ulonglong2{XN[0], XN[1]});
@@ -345,14 +429,12 @@ __device__ __forceinline__ void rollout_body_mix(const RolloutArgs& a, float* sm
       rnd -= f2::hsum1(sito) * wito;
     } else {
       rnd += wcost * f2::hsum1(su2);
-      rnd += wito * f2::hsum1(sito);
+      rnd += wz * f2::hsum1(sito);
     }
   }
-  if constexpr (!EUBO) {  // terminal cost: rnd += reference_log_prob(x) - terminal_unnorm_log_prob(x)   (oc.py:505, 645)
+  if constexpr (!EUBO) {  // terminal cost: rnd += reference_log_prob(x) - terminal_unnorm_log_prob(x)   (oc.py:290, 505, 645)
     const float lref = gmm_logp_any(gmm_at(s.ref_0, 0), d, dp, P.x);
-    float rt[MIX_MAX_M];
-    const float ltgt = clipf(gmm_pass1_pair(tv, d, dp, P.x, rt), s.clip_target);
-    rnd += lref - ltgt;
+    rnd += lref - clipf(target_logp(), s.clip_target);
   }
 
   if (live) {
@@ -363,7 +445,7 @@ __device__ __forceinline__ void rollout_body_mix(const RolloutArgs& a, float* sm
 }
 
 // shared memory: [weight image | mbarriers + TMEM slot | operand stage | particle columns]
-template <int PREC, bool EUBO>
+template <int PREC, class CFG>
 __global__ void __launch_bounds__(MIX_MAX_WARPS * 32, 1)
 rollout_mix_kernel(const RolloutArgs a, const uint8_t* __restrict__ image, const uint32_t tmem_cols) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -405,7 +487,7 @@ rollout_mix_kernel(const RolloutArgs a, const uint8_t* __restrict__ image, const
   // to the lightly loaded ones wherever the tile has four warps
   mlp.issuer = (tid & 127) == 32 * (tile_warps - 1);
   mlp.dp = a.s.mlp.d_pad;
-  rollout_body_mix<PREC, EUBO>(a, cols, stage, mlp);
+  rollout_body_mix<PREC, CFG>(a, cols, stage, mlp);
   ptx::tc_fence_before();
   __syncthreads();
   if (warp == 0) ptx::tmem_dealloc(tmem, tmem_cols);

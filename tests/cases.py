@@ -160,6 +160,42 @@ def case_ei_many_modes(K=200, B=200, d=50, M=16):
         "B": B, "seed": 102, "prior": ("iso", 0.0, 1.0)}
 
 
+def case_ei_two_modes_gauss():
+    """RDS vp-ref with a Gaussian reference and the EI integrator over a mixture target (cfg 1's solver with cfg 2's
+    integrator): target score on the tensor core, reference score one FMA per dim."""
+    d = 7
+    return {
+        "problem": {"method": "ei", "sde": VP10, "ts": uniform_ts(1.0, 60), "target": two_modes(d),
+                    "ctrl": ctrl(d, "score", seed=21, out_gain=0.5, gamma=0.002),
+                    "ref": {"kind": "gauss", "mean": 0.1 * torch.ones(d), "var": 1.5 * torch.ones(d)}},
+        "B": 150, "seed": 111, "prior": ("iso", 0.0, 1.0)}
+
+
+def case_ei_phi4_gmm():
+    """RDS with a mixture reference over the PhiFour lattice (the reference's experiments/sample_phi_four_gmm_mcmc.py):
+    lattice stencil for the target score, reference contraction on the tensor core."""
+    d = 20
+    g = torch.Generator().manual_seed(9)
+    means = torch.stack([torch.ones(d), -torch.ones(d), 0.2 * torch.randn(d, generator=g)])
+    ref = {"kind": "gmm", "means": means, "variances": 0.3 + 0.2 * torch.rand(3, d, generator=g),
+           "weights": torch.tensor([2.0, 2.0, 1.0])}
+    return {
+        "problem": {"method": "ei", "sde": VP10, "ts": uniform_ts(1.0, 80), "target": phi4(d),
+                    "ctrl": ctrl(d, "score", seed=22, out_gain=0.3, gamma=0.004), "ref": ref},
+        "B": 120, "seed": 112, "prior": ("iso", 0.0, 1.0)}
+
+
+def case_ei_many_modes_clipped():
+    """RDS with a mixture reference and the plain ClippedCtrl drift (base_zero_init): no target score."""
+    d, M = 12, 6
+    tgt = many_modes(M, d)
+    ref = {"kind": "gmm", "means": tgt["loc"] - 0.2, "variances": 1.5 * tgt["scale"] ** 2, "weights": torch.ones(M)}
+    return {
+        "problem": {"method": "ei", "sde": VP20, "ts": uniform_ts(1.0, 70), "target": tgt,
+                    "ctrl": ctrl(d, "clipped", seed=23, out_gain=1.0), "ref": ref},
+        "B": 100, "seed": 113, "prior": ("iso", 0.0, 1.0)}
+
+
 def case_ddpm_snr():
     """DDPM-like integrator on an snr grid (API parity), TwoModes d=5, GMM ref."""
     d = 5
@@ -240,6 +276,9 @@ CASES = {
     "em_two_modes_clipped": lambda: case_em_two_modes("clipped"),
     "ei_many_modes": lambda: case_ei_many_modes(),
     "ddpm_snr": case_ddpm_snr,
+    "ei_two_modes_gauss": case_ei_two_modes_gauss,
+    "ei_phi4_gmm": case_ei_phi4_gmm,
+    "ei_many_modes_clipped": case_ei_many_modes_clipped,
     "ei_pbm": case_ei_pbm,
     "pis_phi4": lambda: case_pis_phi4(),
     "dds_phi4_ito": lambda: case_dds_phi4(True),
