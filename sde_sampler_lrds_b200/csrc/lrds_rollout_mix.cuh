@@ -10,7 +10,7 @@
 // over a mixture target, mixture reference, both with 2..16 components, precision F16X3 (traits_match<TraitsLrds> and
 // mix_tc_applicable below); everything else runs the kernels of lrds_rollout_tc.cuh.
 //
-// TMEM columns of a tile (F16X3, d <= 64): [0,32) A hi | [32,64) A lo | [64,128) accumulator D.  After the output
+// TMEM columns of a tile (F16X3, d <= 64; wider A / D regions beyond): [0,32) A hi | [32,64) A lo | [64,128) accumulator D.  After the output
 // GEMM of the network the A region is free: [0,32) holds R = (r_target hi | lo | r_reference hi | lo), 8 packed columns
 // each, [32,64) the 8-dim chunk of the contraction (target a8 b8 | reference a8 b8) while D still holds the network's
 // output.  One chunk is in flight at a time: chunk c+1 is issued as soon as every warp of the tile has read chunk c.
@@ -36,7 +36,7 @@ using MixBench = MixCfg<false, 1, true, false>;  // the benchmark configuration
 
 // index of the configuration that serves `s` (see launch_mix_f16x3), or -1
 __host__ __device__ inline int mix_tc_config(const lrds_spec& s) {
-  if (s.precision != LRDS_PRECISION_F16X3 || !s.has_ref_ctrl || s.mlp.d_pad > 64) return -1;
+  if (s.precision != LRDS_PRECISION_F16X3 || !s.has_ref_ctrl || s.mlp.d_pad > 128) return -1;
   const bool tmix = s.ctrl_kind == LRDS_CTRL_SCORE && s.target.kind == LRDS_DISTR_GMM && s.target.gmm.M > 1 &&
                     s.target.gmm.M <= MIX_MAX_M && s.target.gmm.mix_tc != nullptr;
   const bool tphi = s.ctrl_kind == LRDS_CTRL_SCORE && s.target.kind == LRDS_DISTR_PHI4;
@@ -497,13 +497,14 @@ rollout_mix_kernel(const RolloutArgs a, const uint8_t* __restrict__ image, const
 inline bool plan_rollout_mix(const lrds_spec& s, int smem_cap, int sms, TcPlan* out) {
   if (!mix_tc_applicable(s)) return false;
   const TcLayout TL = tc_layout(s.d, s.mlp.num_hidden, s.precision);
-  if (TL.tile_cols != 128 || TL.parts * TL.a_cols < 64) return false;
+  if (TL.tile_cols > 512 || TL.parts * TL.a_cols < 64) return false;  // R and the chunk live in 64 columns of the A region
   const ColLayout CL = col_layout(s, true);
   const size_t fixed = (size_t)TL.bytes + TC_TAIL_BYTES + ((stage_layout(s, 2, true).total + 15u) & ~15u);
   const size_t per_warp = (size_t)CL.total * 32 * sizeof(float);
   if (fixed + per_warp > (size_t)smem_cap) return false;
   int wmax = (int)(((size_t)smem_cap - fixed) / per_warp);
   wmax = wmax < MIX_MAX_WARPS ? wmax : MIX_MAX_WARPS;
+  wmax = wmax < 4 * (512 / TL.tile_cols) ? wmax : 4 * (512 / TL.tile_cols);
   const int need = (s.B + 31) / 32;
   const int waves = (need + sms * wmax - 1) / (sms * wmax);
   int w = (need + sms * waves - 1) / (sms * waves);

@@ -48,6 +48,20 @@ def test_mixture_kernel_shapes(M, d, B, K, device):
     _check(dict(case, eubo=True, seed=900 + M), device)
 
 
+def test_lattice_target_with_mixture_reference_at_d100(device):
+    """RDS with a mixture reference over the d = 100 PhiFour lattice (experiments/sample_phi_four_gmm_mcmc.py): the
+    mixture kernel with the wide (224-column) tile layout."""
+    case = T.case_ei_phi4_gmm()
+    d = 100
+    g = torch.Generator().manual_seed(19)
+    case["problem"]["target"] = T.phi4(d)
+    case["problem"]["ctrl"] = T.ctrl(d, "score", seed=41, out_gain=0.3, gamma=0.004)
+    case["problem"]["ref"] = {"kind": "gmm", "means": torch.stack([torch.ones(d), -torch.ones(d), 0.2 * torch.randn(d, generator=g)]),
+                              "variances": 0.3 + 0.2 * torch.rand(3, d, generator=g), "weights": torch.tensor([2.0, 2.0, 1.0])}
+    case["B"] = 70
+    _check(case, device)
+
+
 @pytest.mark.parametrize("d,B", [(8, 1), (13, 37), (16, 160), (100, 5)])
 @pytest.mark.parametrize("which", ["pis", "dds_ito", "dds_noito"])
 def test_reference_free_kernel_shapes(which, d, B, device):
