@@ -55,6 +55,7 @@ __host__ __device__ inline int mix_tc_config(const lrds_spec& s) {
   if (tmix && rgauss && em) return 3;
   if (tphi && rmix && axpy) return 4;
   if (tnone && rmix && axpy) return 5;
+  if (tmix && rmix && em) return 6;
   return -1;
 }
 __host__ __device__ inline bool mix_tc_applicable(const lrds_spec& s) { return mix_tc_config(s) >= 0; }

@@ -70,6 +70,7 @@ int launch_mix_f16x3(const RolloutArgs& a, const TcPlan& p, cudaStream_t st, cha
     case 3: return launch_mix_cfg<MixCfg<false, 1, false, true>>(a, p, st, err, n);
     case 4: return launch_mix_cfg<MixCfg<false, 2, true, false>>(a, p, st, err, n);
     case 5: return launch_mix_cfg<MixCfg<false, 0, true, false>>(a, p, st, err, n);
+    case 6: return launch_mix_cfg<MixCfg<false, 1, true, true>>(a, p, st, err, n);
   }
   snprintf(err, n, "mixture tensor-core rollout: configuration not built");
   return LRDS_ERR_UNSUPPORTED;

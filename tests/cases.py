@@ -196,6 +196,17 @@ def case_ei_many_modes_clipped():
         "B": 100, "seed": 113, "prior": ("iso", 0.0, 1.0)}
 
 
+def case_em_many_modes_gmm():
+    """RDS with a mixture reference and the Euler-Maruyama integrator (integrator_type='em' with ref_type='gmm')."""
+    d, M = 9, 5
+    tgt = many_modes(M, d)
+    ref = {"kind": "gmm", "means": tgt["loc"] + 0.1, "variances": 1.3 * tgt["scale"] ** 2, "weights": tgt["weights"].clone()}
+    return {
+        "problem": {"method": "em", "sde": VP10, "ts": uniform_ts(1.0, 120), "target": tgt,
+                    "ctrl": ctrl(d, "score", seed=24, out_gain=1.0, gamma=0.05), "ref": ref},
+        "B": 110, "seed": 114, "prior": ("iso", 0.0, 1.0)}
+
+
 def case_ddpm_snr():
     """DDPM-like integrator on an snr grid (API parity), TwoModes d=5, GMM ref."""
     d = 5
@@ -279,6 +290,7 @@ CASES = {
     "ei_two_modes_gauss": case_ei_two_modes_gauss,
     "ei_phi4_gmm": case_ei_phi4_gmm,
     "ei_many_modes_clipped": case_ei_many_modes_clipped,
+    "em_many_modes_gmm": case_em_many_modes_gmm,
     "ei_pbm": case_ei_pbm,
     "pis_phi4": lambda: case_pis_phi4(),
     "dds_phi4_ito": lambda: case_dds_phi4(True),
