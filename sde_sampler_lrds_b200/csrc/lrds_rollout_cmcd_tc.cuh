@@ -53,9 +53,12 @@ __host__ __device__ inline CmcdTcLayout cmcd_tc_layout(const lrds_spec& s) {
 // per-dim table [4][d_pad]; at least 128 floats (the second threads' partial log-weights at the end)
 __host__ __device__ inline int cmcd_tab_floats(int d_pad) { return 4 * d_pad > 128 ? 4 * d_pad : 128; }
 
+// CMCD simulate / compute_eubo, and the LINEAR loop without a reference control (PIS / DDS with ScoreCtrl, the other
+// solvers of the reference's experiments/sample_bayesian_logreg_competing.py) over the same posterior
 __host__ __device__ inline bool cmcd_tc_applicable(const lrds_spec& s) {
-  if (!(s.precision == LRDS_PRECISION_F16X3 && (s.kind == LRDS_ROLLOUT_CMCD || s.kind == LRDS_ROLLOUT_EUBO_CMCD) &&
-        s.target.kind == LRDS_DISTR_LOGREG &&
+  const bool cmcd = s.kind == LRDS_ROLLOUT_CMCD || s.kind == LRDS_ROLLOUT_EUBO_CMCD;
+  const bool lin = s.kind == LRDS_ROLLOUT_LINEAR && !s.has_ref_ctrl && s.ctrl_kind == LRDS_CTRL_SCORE;
+  if (!(s.precision == LRDS_PRECISION_F16X3 && (cmcd || lin) && s.target.kind == LRDS_DISTR_LOGREG &&
         s.target.logreg.x_tc != nullptr && s.ref_0.M == 1 && s.mlp.d_pad <= 64))
     return false;
   return cmcd_tc_layout(s).cols <= 512;
@@ -260,10 +263,13 @@ struct CmcdTc : TcMlp<LRDS_PRECISION_F16X3> {
 // EUBO: the noising rollout of compute_eubo (oc.py:757-828): starts at target samples, walks the grid backwards
 // (points at rows K, K-1, .., 0), control enters the update with the opposite sign, the cost is subtracted, and the
 // drift of the NEW point inside the cost is evaluated at the time of the OLD one (the reference's quirk, oc.py:807).
-template <int PREC, bool EUBO>  // PREC = LRDS_PRECISION_F16X3 (a template so that only that translation unit instantiates it)
+// MODE 2 (LINEAR): x' = ca x + cu u + cz z with u = clip(net) + gamma clip(score); rnd += w_cost sum u^2 + w_z sum u z per
+// step (losses/oc.py:218-296 with reference_ctrl=None, 1319-1397) and the terminal cost reference - target log-density.
+template <int PREC, int MODE>  // PREC = LRDS_PRECISION_F16X3 (a template so that only that translation unit instantiates it)
 __global__ void __launch_bounds__(256, 1)
 rollout_cmcd_tc_kernel(const RolloutArgs a, const uint8_t* __restrict__ image, const uint32_t tmem_cols) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
+  constexpr bool EUBO = MODE == 1, LIN = MODE == 2;
   const lrds_spec& s = a.s;
   const TcLayout TL = tc_layout(s.d, s.mlp.num_hidden, LRDS_PRECISION_F16X3);
   const CmcdTcLayout CL = cmcd_tc_layout(s);
@@ -343,10 +349,65 @@ rollout_cmcd_tc_kernel(const RolloutArgs a, const uint8_t* __restrict__ image, c
   };
   // forward: initial_log_prob(x), oc.py:698; noising: -terminal_unnorm_log_prob(x), oc.py:782 (first thread of the pair;
   // the second one starts its partial sum at zero)
-  float rnd = half ? 0.f : (EUBO ? -clipf(logreg_logp(LR, d, X), s.clip_target) : prior_logp());
+  float rnd = (half || LIN) ? 0.f : (EUBO ? -clipf(logreg_logp(LR, d, X), s.clip_target) : prior_logp());
   const float usign = EUBO ? -sg : sg;  // the control's sign in the update (oc.py:724 / 804)
   float dt_prev = 0.f, frac_prev = 0.f;
-  for (int k = 0; k <= K; ++k) {  // forward: point x_k at row k; noising: the k-th point, at row K - k
+  if constexpr (LIN) {
+    for (int k = 0; k < K; ++k) {
+      const float* row = s.steps + (int64_t)k * LRDS_STEP_STRIDE;
+      const float A = __ldg(row + LRDS_STEP_A), Bc = __ldg(row + LRDS_STEP_B), Cc = __ldg(row + LRDS_STEP_C);
+      const float dt = __ldg(row + LRDS_STEP_DT), sqdt = __ldg(row + LRDS_STEP_SQRT_DT);
+      const float wcost = __ldg(row + LRDS_STEP_W_COST), wito = __ldg(row + LRDS_STEP_W_ITO);
+      const float gamma = __ldg(row + LRDS_STEP_GAMMA), sigu = __ldg(row + LRDS_STEP_SIGU);
+      const bool em = s.update_form == LRDS_UPDATE_EM;
+      const float wz = s.ito_form == LRDS_ITO_SCALED ? wito
+                       : s.ito_form == LRDS_ITO_EM   ? sqdt
+                       : s.ito_form == LRDS_ITO_DDS  ? sigu * wito
+                                                     : 0.f;
+      const float ca = em ? 1.0f - A * dt : A, cu = em ? Bc * dt : Bc, cz = em ? Bc * sqdt : Cc;
+      __syncthreads();  // the pair's writes of x are visible to both threads
+      mlp.issue_first(X);
+      float zs[4][JC];
+#pragma unroll
+      for (int ci = 0; ci < 4; ++ci) {
+        const int j0 = JC * (2 * ci + half);
+        if (j0 < dp) {
+          noise_chunk(a, k, b, j0, zs[ci]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < JC; ++i) zs[ci][i] = 0.f;
+        }
+      }
+      mlp.finish(LR, row + LRDS_STEP_BIAS1);
+      float su2 = 0.f, sito = 0.f;
+#pragma unroll
+      for (int ci = 0; ci < 4; ++ci) {
+        const int j0 = JC * (2 * ci + half);
+        if (j0 >= dp) break;
+        float xr[JC], T[JC], um[JC], xn[JC];
+        mlp.ld8f(CL.t_col + (uint32_t)j0, T);
+        mlp.out_chunk(j0, um);
+        load_chunk(X, j0, xr);
+        const float4 s0 = reinterpret_cast<const float4*>(dimtab + 2 * dp + j0)[0], s1 = reinterpret_cast<const float4*>(dimtab + 2 * dp + j0)[1];
+        const float4 i0 = reinterpret_cast<const float4*>(dimtab + 3 * dp + j0)[0], i1 = reinterpret_cast<const float4*>(dimtab + 3 * dp + j0)[1];
+        const float sm[JC] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+        const float si[JC] = {i0.x, i0.y, i0.z, i0.w, i1.x, i1.y, i1.z, i1.w};
+#pragma unroll
+        for (int i = 0; i < JC; ++i) {
+          const float sc = T[i] * mlp.usx - (xr[i] - sm[i]) * si[i];
+          const float v = clipb(um[i], cc.bound_model) + (cc.scale_score * clipb(sc, cc.bound_score)) * gamma;
+          su2 = fmaf(v, v, su2);
+          sito = fmaf(v, zs[ci][i], sito);
+          xn[i] = (ca * xr[i] + cu * v) + cz * zs[ci][i];
+        }
+        store_chunk(X, j0, xn);
+        if (a.traj_out != nullptr && live) store_traj(a, k + 1, b, j0, xn);
+      }
+      rnd += wcost * su2;
+      rnd += wz * sito;
+    }
+  }
+  for (int k = 0; !LIN && k <= K; ++k) {  // forward: point x_k at row k; noising: the k-th point, at row K - k
     const int rk = EUBO ? K - k : k;
     const float* row = s.steps + (int64_t)rk * LRDS_STEP_STRIDE;
     const float gamma = __ldg(row + LRDS_STEP_GAMMA), frac = __ldg(row + LRDS_STEP_FRAC);
@@ -454,6 +515,7 @@ rollout_cmcd_tc_kernel(const RolloutArgs a, const uint8_t* __restrict__ image, c
   if (!half) {
     rnd += dimtab[pt];
     if (EUBO) rnd += prior_logp();                                   // oc.py:825
+    else if (LIN) rnd += prior_logp() - clipf(logreg_logp(LR, d, X), s.clip_target);  // ref_0 - target, oc.py:290, 1389
     else rnd -= clipf(logreg_logp(LR, d, X), s.clip_target);         // oc.py:750
     if (live) a.rnd_out[b] = rnd;
   }

@@ -31,8 +31,9 @@ int launch_lin_f16x3(const RolloutArgs& a, const TcPlan& p, cudaStream_t st, cha
 }
 
 int launch_cmcd_tc_f16x3(const RolloutArgs& a, const TcPlan& p, cudaStream_t st, char* err, size_t n) {
-  auto kernel = a.s.kind == LRDS_ROLLOUT_EUBO_CMCD ? rollout_cmcd_tc_kernel<LRDS_PRECISION_F16X3, true>
-                                                    : rollout_cmcd_tc_kernel<LRDS_PRECISION_F16X3, false>;
+  auto kernel = a.s.kind == LRDS_ROLLOUT_EUBO_CMCD ? rollout_cmcd_tc_kernel<LRDS_PRECISION_F16X3, 1>
+                : a.s.kind == LRDS_ROLLOUT_LINEAR  ? rollout_cmcd_tc_kernel<LRDS_PRECISION_F16X3, 2>
+                                                    : rollout_cmcd_tc_kernel<LRDS_PRECISION_F16X3, 0>;
   cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
   if (e == cudaSuccess) {
     kernel<<<p.grid, p.warps * 32, p.smem, st>>>(a, static_cast<const uint8_t*>(a.s.mlp.tc_image), p.tmem_cols);

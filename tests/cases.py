@@ -262,6 +262,26 @@ def case_cmcd_logreg(n=166, p=60, K=32, B=96, ctrl_kind="score"):
         "B": B, "seed": 107, "prior": ("iso", 0.0, 5.0)}
 
 
+def case_pis_logreg(n=166, p=60, K=40, B=96):
+    """PIS over the logistic-regression posterior (experiments/sample_bayesian_logreg_competing.py, pis_orig)."""
+    d = p + 1
+    return {
+        "problem": {"method": "em", "sde": BM, "ts": uniform_ts(5.0, K), "target": logreg_synthetic(n, p),
+                    "ctrl": ctrl(d, "score", seed=25, out_gain=0.5, gamma=0.01),
+                    "ref": {"kind": "pis", "loc": torch.zeros(d)}},
+        "B": B, "seed": 115, "prior": ("delta", 0.0)}
+
+
+def case_dds_logreg(n=280, p=33, B=96):
+    """DDS over the logistic-regression posterior (dds_orig; cosine grid), ionosphere shape."""
+    d = p + 1
+    return {
+        "problem": {"method": "dds", "sde": None, "alpha": 1.0, "sigma": 1.0, "ts": cosine_ts(6.4, 0.1),
+                    "target": logreg_synthetic(n, p), "ctrl": ctrl(d, "score", seed=26, out_gain=0.3, gamma=0.01),
+                    "ref": {"kind": "iso", "loc": 0.0, "scale": 1.0}},
+        "B": B, "seed": 116, "prior": ("iso", 0.0, 1.0), "compute_ito_int": True}
+
+
 def case_cmcd_gmm():
     """CMCD on a GMM target with a fitted diagonal Gaussian prior (CMCD.update_prior, solver/oc.py:291-303)."""
     d = 8
@@ -298,6 +318,8 @@ CASES = {
     "cmcd_logreg_sonar": lambda: case_cmcd_logreg(166, 60),
     "cmcd_logreg_iono": lambda: case_cmcd_logreg(280, 33, ctrl_kind="clipped"),
     "cmcd_gmm": case_cmcd_gmm,
+    "pis_logreg": lambda: case_pis_logreg(),
+    "dds_logreg": lambda: case_dds_logreg(),
     "eubo_em_two_modes": lambda: _eubo(case_em_two_modes("score"), 201),
     "eubo_ei_many_modes": lambda: _eubo(case_ei_many_modes(K=100, B=100), 202),
     "eubo_cmcd_gmm": lambda: _eubo(case_cmcd_gmm(), 203),

@@ -28,6 +28,7 @@ SHAPES = {
     "cfg3 phi4 d=100 DDS K=256 B=131072": dds256,
     "cfg4 logreg sonar d=61 CMCD K=100 B=262144": lambda: T.case_cmcd_logreg(166, 60, K=100, B=262144),
     "cfg4 logreg iono d=34 CMCD K=100 B=262144": lambda: T.case_cmcd_logreg(280, 33, K=100, B=262144),
+    "logreg sonar d=61 PIS K=100 B=262144": lambda: T.case_pis_logreg(166, 60, K=100, B=262144),
     # compute_eubo (the noising rollout behind evaluate_eubo) of the same shapes
     "eubo cfg2 many_modes d=50 M=16 EI K=200 B=65536": lambda: dict(T.case_ei_many_modes(K=200, B=65536), eubo=True),
     "eubo cfg4 logreg sonar d=61 CMCD K=100 B=262144": lambda: dict(T.case_cmcd_logreg(166, 60, K=100, B=262144), eubo=True),
