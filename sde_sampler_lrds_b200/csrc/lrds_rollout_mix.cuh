@@ -25,26 +25,28 @@ constexpr int MIX_MAX_WARPS = 16;  // 3.5 tiles: one wave for 65536 particles on
 // Compile-time configuration of the kernel: which of the two score contractions run on the tensor core, and the update.
 //   TGT  1: ScoreCtrl over a mixture target (contraction on tcgen05)   2: ScoreCtrl over the PhiFour lattice (stencil)
 //        0: ClippedCtrl (no target score)
-//   REFMIX  the time-marginal reference is a mixture (contraction on tcgen05) / a single Gaussian (one FMA per dim)
+//   REF  2: the time-marginal reference is a mixture (contraction on tcgen05)   1: a single Gaussian (one FMA per dim)
+//        0: no reference control (PIS / DDS over a mixture target)
 //   EM   Euler-Maruyama update and Ito term (losses/oc.py:277-284) instead of the exponential-integrator axpy
-template <bool EUBO_, int TGT_, bool REFMIX_, bool EM_>
+template <bool EUBO_, int TGT_, int REF_, bool EM_>
 struct MixCfg {
-  static constexpr bool kEubo = EUBO_, kRefMix = REFMIX_, kEm = EM_;
-  static constexpr int kTgt = TGT_;
+  static constexpr bool kEubo = EUBO_, kEm = EM_;
+  static constexpr int kTgt = TGT_, kRef = REF_;
 };
-using MixBench = MixCfg<false, 1, true, false>;  // the benchmark configuration
+using MixBench = MixCfg<false, 1, 2, false>;  // the benchmark configuration
 
 // index of the configuration that serves `s` (see launch_mix_f16x3), or -1
 __host__ __device__ inline int mix_tc_config(const lrds_spec& s) {
-  if (s.precision != LRDS_PRECISION_F16X3 || !s.has_ref_ctrl || s.mlp.d_pad > 128) return -1;
+  if (s.precision != LRDS_PRECISION_F16X3 || s.mlp.d_pad > 128) return -1;
   const bool tmix = s.ctrl_kind == LRDS_CTRL_SCORE && s.target.kind == LRDS_DISTR_GMM && s.target.gmm.M > 1 &&
                     s.target.gmm.M <= MIX_MAX_M && s.target.gmm.mix_tc != nullptr;
   const bool tphi = s.ctrl_kind == LRDS_CTRL_SCORE && s.target.kind == LRDS_DISTR_PHI4;
   const bool tnone = s.ctrl_kind == LRDS_CTRL_CLIPPED &&
                      (s.target.kind != LRDS_DISTR_GMM || s.target.gmm.M <= MIX_MAX_M) && s.target.kind != LRDS_DISTR_LOGREG;
-  const bool rmix = s.ref_t.M > 1 && s.ref_t.M <= MIX_MAX_M && s.ref_t.mix_tc != nullptr;
-  const bool rgauss = s.ref_t.M == 1;
-  const bool axpy = s.update_form == LRDS_UPDATE_AXPY && s.ito_form == LRDS_ITO_SCALED;
+  const bool rnone = !s.has_ref_ctrl;
+  const bool rmix = s.has_ref_ctrl && s.ref_t.M > 1 && s.ref_t.M <= MIX_MAX_M && s.ref_t.mix_tc != nullptr;
+  const bool rgauss = s.has_ref_ctrl && s.ref_t.M == 1;
+  const bool axpy = s.update_form == LRDS_UPDATE_AXPY && (s.ito_form == LRDS_ITO_SCALED || (rnone && s.ito_form != LRDS_ITO_EM));
   const bool em = s.update_form == LRDS_UPDATE_EM && s.ito_form == LRDS_ITO_EM;
   if (s.ref_0.M > MIX_MAX_M) return -1;
   if (s.target.kind == LRDS_DISTR_GMM && s.target.gmm.M > 1 && s.target.gmm.mix_tc == nullptr) return -1;  // staged with the target
@@ -56,6 +58,9 @@ __host__ __device__ inline int mix_tc_config(const lrds_spec& s) {
   if (tphi && rmix && axpy) return 4;
   if (tnone && rmix && axpy) return 5;
   if (tmix && rmix && em) return 6;
+  if (tmix && rnone && em) return 7;    // PIS over a mixture target
+  if (tmix && rnone && axpy) return 8;  // DDS over a mixture target (any Ito form but EM)
+  if (tphi && rgauss && axpy) return 9;
   return -1;
 }
 __host__ __device__ inline bool mix_tc_applicable(const lrds_spec& s) { return mix_tc_config(s) >= 0; }
@@ -224,7 +229,7 @@ struct MixTc : TcMlp<PREC> {
 // increments are generated twice (for the update and for the cost) instead of being kept per particle.
 template <int PREC, class CFG>
 __device__ __forceinline__ void rollout_body_mix(const RolloutArgs& a, float* smem, uint8_t* stage, MixTc<PREC>& mlp) {
-  constexpr bool EUBO = CFG::kEubo, TMIX = CFG::kTgt == 1, TPHI = CFG::kTgt == 2, RMIX = CFG::kRefMix, EM = CFG::kEm;
+  constexpr bool EUBO = CFG::kEubo, TMIX = CFG::kTgt == 1, TPHI = CFG::kTgt == 2, RMIX = CFG::kRef == 2, RGAUSS = CFG::kRef == 1, EM = CFG::kEm;
   const lrds_spec& s = a.s;
   const int NT = blockDim.x;
   const int tid = threadIdx.x;
@@ -348,7 +353,11 @@ __device__ __forceinline__ void rollout_body_mix(const RolloutArgs& a, float* sm
     const u64 usr2 = f2::pk(usr), R2 = f2::pk((EM ? Cc * dt : Bc) * usr);
     const u64 gs2 = f2::pk((cc.scale_score * gamma) * ust);
     const float bts = cc.bound_score / ust;
-    const float wz = EM ? sqdt : wito;  // weight of sum(u z) in the log-weight (oc.py:284 / 499)
+    // weight of sum(u z) in the log-weight (oc.py:284 / 499); without a reference control also the DDS forms (oc.py:1380-1383)
+    const float wz = EM ? sqdt
+                     : (RMIX || RGAUSS || s.ito_form == LRDS_ITO_SCALED) ? wito
+                     : s.ito_form == LRDS_ITO_DDS ? rowp.ld1(LRDS_STEP_SIGU) * wito
+                                                  : 0.f;
     u64 su2 = 0, sito = 0;
     float xm = 0.f;  // lattice target: x_{j0-1} of the state before this step's update
     for (int c = 0; c < nchunk; ++c) {
@@ -372,7 +381,7 @@ __device__ __forceinline__ void rollout_body_mix(const RolloutArgs& a, float* sm
         xm = xs[JC];
       }
       u64 GM[4], GI[4];  // single-Gaussian reference: mean and 1/var of the chunk
-      if constexpr (!RMIX) {
+      if constexpr (RGAUSS) {
         const ulonglong2 g0 = rg.mu.ld2(2 * c), g1 = rg.mu.ld2(2 * c + 1), i0 = rg.ivar.ld2(2 * c), i1 = rg.ivar.ld2(2 * c + 1);
         GM[0] = g0.x; GM[1] = g0.y; GM[2] = g1.x; GM[3] = g1.y;
         GI[0] = i0.x; GI[1] = i0.y; GI[2] = i1.x; GI[3] = i1.y;
@@ -399,7 +408,7 @@ __device__ __forceinline__ void rollout_body_mix(const RolloutArgs& a, float* sm
         u64 v = uc;  // control u
         if constexpr (TMIX || TPHI) v = f2::fma(f2::pack(clipb(t0, bts), clipb(t1, bts)), gs2, uc);
         // reference score in the units of R2: mixture = accumulator (image units), Gaussian = -(x - mu) / var
-        const u64 rraw = RMIX ? f2::fma(X[q], ra, rb) : f2::mul(f2::fma(X[q], f2::pk(-1.0f), GM[q]), GI[q]);
+        const u64 rraw = RMIX ? f2::fma(X[q], ra, rb) : RGAUSS ? f2::mul(f2::fma(X[q], f2::pk(-1.0f), GM[q]), GI[q]) : 0ull;
         const u64 z2 = f2::pack(z[2 * q], z[2 * q + 1]);
         if constexpr (EUBO) {  // cost += u (r + u / 2),  gz += u z   (oc.py:556-563; g = u for the axpy updates)
           su2 = f2::fma(v, f2::fma(v, f2::pk(0.5f), f2::mul(rraw, usr2)), su2);
@@ -408,7 +417,9 @@ __device__ __forceinline__ void rollout_body_mix(const RolloutArgs& a, float* sm
         }
         su2 = f2::fma(v, v, su2);
         sito = f2::fma(v, z2, sito);
-        if constexpr (EM) {
+        if constexpr (!RMIX && !RGAUSS) {
+          XN[q] = f2::fma(C2, z2, f2::fma(A2, X[q], f2::mul(B2, v)));
+        } else if constexpr (EM) {
           XN[q] = f2::fma(C2, z2, f2::fma(A2, X[q], f2::fma(R2, rraw, f2::mul(B2, v))));
         } else {
           const u64 rv2 = f2::fma(rraw, usr2, v);  // reference score + u

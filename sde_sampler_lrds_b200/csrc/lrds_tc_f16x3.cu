@@ -47,33 +47,4 @@ int launch_cmcd_tc_f16x3(const RolloutArgs& a, const TcPlan& p, cudaStream_t st,
   return LRDS_OK;
 }
 
-template <class CFG>
-static int launch_mix_cfg(const RolloutArgs& a, const TcPlan& p, cudaStream_t st, char* err, size_t n) {
-  auto kernel = rollout_mix_kernel<LRDS_PRECISION_F16X3, CFG>;
-  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
-  if (e == cudaSuccess) {
-    kernel<<<p.grid, p.warps * 32, p.smem, st>>>(a, static_cast<const uint8_t*>(a.s.mlp.tc_image), p.tmem_cols);
-    e = cudaGetLastError();
-  }
-  if (e != cudaSuccess) {
-    snprintf(err, n, "mixture tensor-core rollout launch (grid %d x %d threads, %zu B smem, %u TMEM cols): %s", p.grid,
-             p.warps * 32, p.smem, p.tmem_cols, cudaGetErrorString(e));
-    return LRDS_ERR_CUDA;
-  }
-  return LRDS_OK;
-}
-
-int launch_mix_f16x3(const RolloutArgs& a, const TcPlan& p, cudaStream_t st, char* err, size_t n) {
-  switch (mix_tc_config(a.s)) {  // <EUBO, TGT, REFMIX, EM>
-    case 0: return launch_mix_cfg<MixBench>(a, p, st, err, n);
-    case 1: return launch_mix_cfg<MixCfg<true, 1, true, false>>(a, p, st, err, n);
-    case 2: return launch_mix_cfg<MixCfg<false, 1, false, false>>(a, p, st, err, n);
-    case 3: return launch_mix_cfg<MixCfg<false, 1, false, true>>(a, p, st, err, n);
-    case 4: return launch_mix_cfg<MixCfg<false, 2, true, false>>(a, p, st, err, n);
-    case 5: return launch_mix_cfg<MixCfg<false, 0, true, false>>(a, p, st, err, n);
-    case 6: return launch_mix_cfg<MixCfg<false, 1, true, true>>(a, p, st, err, n);
-  }
-  snprintf(err, n, "mixture tensor-core rollout: configuration not built");
-  return LRDS_ERR_UNSUPPORTED;
-}
 }  // namespace lrds

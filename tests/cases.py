@@ -207,6 +207,36 @@ def case_em_many_modes_gmm():
         "B": 110, "seed": 114, "prior": ("iso", 0.0, 1.0)}
 
 
+def case_pis_many_modes():
+    """PIS over a mixture target (pis_orig of experiments/sample_many_modes_competing.py)."""
+    d, M = 10, 7
+    return {
+        "problem": {"method": "em", "sde": BM, "ts": uniform_ts(5.0, 90), "target": many_modes(M, d),
+                    "ctrl": ctrl(d, "score", seed=27, out_gain=0.5, gamma=0.02),
+                    "ref": {"kind": "pis", "loc": torch.zeros(d)}},
+        "B": 120, "seed": 117, "prior": ("delta", 0.0)}
+
+
+def case_dds_many_modes(compute_ito_int=True):
+    """DDS over a mixture target (dds_orig)."""
+    d, M = 10, 7
+    return {
+        "problem": {"method": "dds", "sde": None, "alpha": 1.0, "sigma": 2.0, "ts": cosine_ts(6.4, 0.08),
+                    "target": many_modes(M, d), "ctrl": ctrl(d, "score", seed=28, out_gain=0.5, gamma=0.02),
+                    "ref": {"kind": "iso", "loc": 0.0, "scale": 2.0}},
+        "B": 120, "seed": 118, "prior": ("iso", 0.0, 2.0), "compute_ito_int": compute_ito_int}
+
+
+def case_ei_phi4_gauss():
+    """RDS vp-ref with its default Gaussian reference over the PhiFour lattice (experiments/sample_phi_four_competing.py)."""
+    d = 24
+    return {
+        "problem": {"method": "ei", "sde": VP10, "ts": uniform_ts(1.0, 80), "target": phi4(d),
+                    "ctrl": ctrl(d, "score", seed=29, out_gain=0.3, gamma=0.004),
+                    "ref": {"kind": "gauss", "mean": torch.zeros(d), "var": 1.2 * torch.ones(d)}},
+        "B": 100, "seed": 119, "prior": ("iso", 0.0, 1.0)}
+
+
 def case_ddpm_snr():
     """DDPM-like integrator on an snr grid (API parity), TwoModes d=5, GMM ref."""
     d = 5
@@ -311,6 +341,10 @@ CASES = {
     "ei_phi4_gmm": case_ei_phi4_gmm,
     "ei_many_modes_clipped": case_ei_many_modes_clipped,
     "em_many_modes_gmm": case_em_many_modes_gmm,
+    "pis_many_modes": case_pis_many_modes,
+    "dds_many_modes_ito": lambda: case_dds_many_modes(True),
+    "dds_many_modes_noito": lambda: case_dds_many_modes(False),
+    "ei_phi4_gauss": case_ei_phi4_gauss,
     "ei_pbm": case_ei_pbm,
     "pis_phi4": lambda: case_pis_phi4(),
     "dds_phi4_ito": lambda: case_dds_phi4(True),
