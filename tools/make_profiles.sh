@@ -2,7 +2,7 @@
 # Regenerates the tracked profiles/ artefacts of a round from gpurun_out/ (tools/bin/run10.sh):  tools/make_profiles.sh r01
 set -e
 R=${1:-r01}
-tools/prof_report.sh gpurun_out/prof_mix_final.ncu-rep lrds_tc_f16x3 rollout_mix_kernelILi4ELi4ELb0 40 > /tmp/mixsum.md 2>/dev/null
+tools/prof_report.sh gpurun_out/prof_mix_final.ncu-rep lrds_tc_mix_a rollout_mix_kernelILi4ENS_6MixCfgILb0ELi1ELi2ELb0 40 > /tmp/mixsum.md 2>/dev/null
 { echo "## $R f16x3 benchmark kernel (rollout_mix_kernel: drift network + mixture-score contractions on tcgen05) - bench workload, B200"; echo; echo "Command: \`ncu --set full --clock-control none --import-source on -k regex:rollout_mix_kernel -s 3 -c 1 python bench.py --steps 1 --warmup 3 --no-cpu-baseline\` (one launch, cold-cache and serialised; the live timing of the same kernel is in ${R}_final_bench.json)."; echo; tail -n +3 /tmp/mixsum.md; } > profiles/${R}_mix_summary.md
 python - "$R" <<'PY'
 import csv, collections, sys

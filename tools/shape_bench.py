@@ -21,6 +21,29 @@ def dds256():
     return case
 
 
+def cmcd_many_modes():
+    case = T.case_cmcd_gmm()
+    d = 50
+    case["problem"]["target"] = T.many_modes(16, d)
+    case["problem"]["ctrl"] = T.ctrl(d, "score", seed=18, out_gain=0.5, gamma=0.02)
+    case["problem"]["ts"] = T.uniform_ts(1.0, 200)
+    case["problem"]["prior"] = {"loc": torch.zeros(d), "scale": 5.0 * torch.ones(d), "isotropic": True}
+    case["prior"] = ("iso", 0.0, 5.0)
+    case["B"] = 65536
+    return case
+
+
+def pis_many_modes():
+    case = T.case_pis_many_modes()
+    d = 50
+    case["problem"]["target"] = T.many_modes(16, d)
+    case["problem"]["ctrl"] = T.ctrl(d, "score", seed=27, out_gain=0.5, gamma=0.02)
+    case["problem"]["ref"] = {"kind": "pis", "loc": torch.zeros(d)}
+    case["problem"]["ts"] = T.uniform_ts(5.0, 200)
+    case["B"] = 65536
+    return case
+
+
 SHAPES = {
     "cfg1 two_modes d=2 EM K=100 B=2048": lambda: dict(T.case_em_two_modes("score"), B=2048),
     "cfg2 many_modes d=50 M=16 EI K=200 B=65536": lambda: T.case_ei_many_modes(K=200, B=65536),
@@ -29,6 +52,8 @@ SHAPES = {
     "cfg4 logreg sonar d=61 CMCD K=100 B=262144": lambda: T.case_cmcd_logreg(166, 60, K=100, B=262144),
     "cfg4 logreg iono d=34 CMCD K=100 B=262144": lambda: T.case_cmcd_logreg(280, 33, K=100, B=262144),
     "logreg sonar d=61 PIS K=100 B=262144": lambda: T.case_pis_logreg(166, 60, K=100, B=262144),
+    "many_modes d=50 M=16 CMCD K=200 B=65536": lambda: cmcd_many_modes(),
+    "many_modes d=50 M=16 PIS K=200 B=65536": lambda: pis_many_modes(),
     # compute_eubo (the noising rollout behind evaluate_eubo) of the same shapes
     "eubo cfg2 many_modes d=50 M=16 EI K=200 B=65536": lambda: dict(T.case_ei_many_modes(K=200, B=65536), eubo=True),
     "eubo cfg4 logreg sonar d=61 CMCD K=100 B=262144": lambda: dict(T.case_cmcd_logreg(166, 60, K=100, B=262144), eubo=True),
