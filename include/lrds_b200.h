@@ -17,7 +17,7 @@
 extern "C" {
 #endif
 
-#define LRDS_ABI_VERSION 5
+#define LRDS_ABI_VERSION 6
 #define LRDS_CHANNELS 64 /* FourierMLP / TimeEmbed width, conf/model/base/fouriermlp.yaml:4 */
 
 typedef enum {
@@ -181,6 +181,12 @@ typedef struct {
   float clip_target;   /* <= 0: none (TrainableDiff.clip_target, solver/oc.py:33,80-87) */
   float cmcd_diff;     /* ControlledLangevinSDE.diff_coeff, eq/sdes.py:93 */
   float cmcd_clip;     /* ControlledLangevinSDE.clip_score, <= 0: none */
+  int32_t init_cost;   /* LINEAR (simulate only): 0 = rnd starts at 0 and ends with + reference_log_prob(x_T), ref_0 being the
+                        * reference (RDS / PIS / DDS: oc.py:245, 290, 1389); 1 = rnd starts at initial_log_prob(x_0) + rnd_offset,
+                        * ref_0 being the PRIOR, and ends with the target term alone (DIS: TimeReversalLoss.simulate,
+                        * oc.py:1164-1168, 1230) */
+  float rnd_offset;    /* init_cost: state-independent part of the log-weight, -sum_k sde.drift_div_int(s_k, t_k, x)
+                        * (OU.drift_div_int = d * int_drift_coeff_t, eq/sdes.py:137-141; oc.py:1217-1218, train=False) */
   const float* steps;  /* per-step table, LRDS_STEP_STRIDE floats per row */
   lrds_mlp mlp;
   lrds_distr target;   /* terminal_unnorm_log_prob + ScoreCtrl.target_score */

@@ -168,6 +168,13 @@ def run_reference(case):
             x, rnd, xs = loss.simulate(ts, x0, target_logp, prior.log_prob,
                                        compute_ito_int=case.get("compute_ito_int", True), return_traj=True)
             out = {"x_T": x, "rnd": rnd, "xs_mid": xs[len(xs) // 2]}
+        elif method == "dis":  # solver/oc.py:185-262 (Bridge, inference_ctrl=None), eval = TimeReversalLoss.eval, oc.py:1274-1307
+            sde = build_reference_sde(p["sde"])
+            prior = IsotropicGauss(dim=d, loc=p["ref"]["loc"], scale=p["ref"]["scale"])
+            loss = oc.TimeReversalLoss(sde=sde, inference_ctrl=None, **kw)
+            x, rnd, xs = loss.simulate(ts, x0, target_logp, initial_log_prob=prior.log_prob, train=False,
+                                       compute_ito_int=case.get("compute_ito_int", True), return_traj=True)
+            out = {"x_T": x, "rnd": rnd, "xs_mid": xs[len(xs) // 2]}
         elif method == "cmcd":
             pr = p["prior"]
             if pr.get("isotropic"):

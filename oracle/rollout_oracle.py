@@ -244,6 +244,9 @@ class VP:
     def diff(self, t):  # 465-467
         return self.c * torch.sqrt(self.beta(t))
 
+    def int_drift_coeff(self, s, t):  # int_drift_coeff_t, 469-477
+        return -0.25 * (self.beta(t) + self.beta(s)) * (t - s)
+
     def alpha_(self, t):  # 490-493
         return self.bmin * t + (0.5 * t ** 2 / self.T) * (self.bmax - self.bmin)
 
@@ -469,6 +472,31 @@ def simulate_dds(ts, x, noise, ctrl, alpha, sigma, terminal_unnorm_log_prob, ref
     return x, rnd, (torch.stack(xs) if return_traj else None)
 
 
+def simulate_dis(ts, x, noise, ctrl, sde, terminal_unnorm_log_prob, initial_log_prob, compute_ito_int=True,
+                 return_traj=False):
+    """TimeReversalLoss.simulate, losses/oc.py:1133-1238, as DIS evaluates it (solver/oc.py:185-262 Bridge with
+    inference_ctrl=None; eval passes train=False, change_sde_ctrl=False, use_rescaling=True): the control is taken at
+    the loop time s (not T - s), the drift is +sde.drift(s, x), the log-weight starts at the prior log-density and
+    carries the divergence integral OU.drift_div_int = d * int_drift_coeff_t (eq/sdes.py:137-141)."""
+    rnd = initial_log_prob(x)
+    d = x.shape[-1]
+    xs = [x] if return_traj else None
+    for k, (s, t) in enumerate(zip(ts[:-1], ts[1:])):
+        u = ctrl(s, x)
+        sde_diff = sde.diff(s)
+        dt = t - s
+        rnd = rnd + 0.5 * (u ** 2).sum(dim=-1, keepdim=True) * dt
+        rnd = rnd - sde.int_drift_coeff(s, t) * d
+        db = noise[k] * dt.sqrt()
+        x = x + (sde.drift_coeff(s) * x + sde_diff * u) * dt + sde_diff * db
+        if compute_ito_int:
+            rnd = rnd + (u * db).sum(dim=-1, keepdim=True)
+        if return_traj:
+            xs.append(x)
+    rnd = rnd - terminal_unnorm_log_prob(x)
+    return x, rnd, (torch.stack(xs) if return_traj else None)
+
+
 def langevin_drift(t, x, target_score, prior_score, diff, T, clip_score):
     """ControlledLangevinSDE.drift, sde_sampler/eq/sdes.py:101-110."""
     drift = target_score(x) * (t / T) + prior_score(x) * (1.0 - t / T)
@@ -686,6 +714,10 @@ def rollout(problem: dict, x0: torch.Tensor, noise: torch.Tensor, *, eubo: bool 
                 return simulate_em(ts, x0, noise, ctrl, sde, ref_ctrl, target_logp, ref_logp, return_traj)
             return simulate_ei(ts, x0, noise, ctrl, sde, ref_ctrl, target_logp, ref_logp, return_traj,
                                ddpm=(method == "ddpm"))
+        if method == "dis":  # prior = IsotropicGauss (conf/prior/gauss.yaml), scale = sde.scale_diff_coeff (conf/solver/dis.yaml)
+            sde = make_sde(problem["sde"], dtype)
+            _, prior_logp = make_reference(problem["ref"], None)
+            return simulate_dis(ts, x0, noise, ctrl, sde, target_logp, prior_logp, compute_ito_int, return_traj)
         if method == "dds":
             _, ref_logp = make_reference(problem["ref"], None)
             return simulate_dds(ts, x0, noise, ctrl, problem["alpha"], problem["sigma"], target_logp, ref_logp,

@@ -18,7 +18,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(CSRC, "liblrds_b200.so")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 CHANNELS = 64
 STEP_STRIDE = 80
 (STEP_A, STEP_B, STEP_C, STEP_DT, STEP_SQRT_DT, STEP_W_COST, STEP_W_ITO, STEP_GAMMA, STEP_FRAC, STEP_SIGU,
@@ -69,6 +69,7 @@ class Spec(C.Structure):
                 ("K", C.c_int32), ("has_ref_ctrl", C.c_int32),
                 ("clip_model", C.c_float), ("clip_score", C.c_float), ("scale_score", C.c_float),
                 ("clip_target", C.c_float), ("cmcd_diff", C.c_float), ("cmcd_clip", C.c_float),
+                ("init_cost", C.c_int32), ("rnd_offset", C.c_float),
                 ("steps", FP), ("mlp", Mlp), ("target", Distr), ("ref_t", Gmm), ("ref_0", Gmm)]
 
 

@@ -3,7 +3,7 @@
 (conf/solver/*.yaml and the groups they pull in) into a plain dict and ``make_model`` applies
 the same patches in the same order (benchmark_utils.py:176-262).
 
-Differences, all loud: the 'dis_orig' solver, the U-Net / lerp / langevin-init controls and 'nn' references raise
+Differences, all loud: the U-Net / lerp / langevin-init controls and 'nn' references raise
 NotImplementedError (rows of SURVEY.md 8f), sample-based metrics (Sinkhorn / MMD / KS) are not attached, and the
 logistic-regression targets read ``<data_dir>/<name>.pkl`` (pass ``target_details['data_dir']`` or set
 ``LRDS_DATA_DIR``; the datasets are not redistributed here).
@@ -129,8 +129,15 @@ def default_config(solver_type: str, model_type: str, loss_type: str, target_det
         loss = {"_target_": L.ControlledLangevinSDELoss, "method": loss_type, "traj_per_sample": 1, "max_rnd": None,
                 "sde_ctrl_noise": None, "sde_ctrl_dropout": None}
         base.update(solver=S.CMCD, sde=sde, loss=loss, prior={"_target_": IsotropicGauss, "dim": dim, "scale": 5.0})
+    elif name == "dis":  # conf/solver/dis.yaml + conf/loss/time_reversal[_lv].yaml
+        sde = {"_target_": VP, "diff_coeff_sq_min": 0.1, "diff_coeff_sq_max": 20.0 if force_vp20 else 10.0,
+               "scale_diff_coeff": 1.0, "terminal_t": 1.0}
+        loss = {"_target_": L.TimeReversalLoss, "method": loss_type, "traj_per_sample": 1,
+                "max_rnd": 1e8 if loss_type == "lv" else None, "sde_ctrl_noise": None, "sde_ctrl_dropout": None}
+        base.update(solver=S.Bridge, sde=sde, loss=loss,
+                    prior={"_target_": IsotropicGauss, "dim": dim, "scale": "${sde.scale_diff_coeff}"})
     else:
-        raise NotImplementedError(f"solver {solver_type!r} (time-reversal / DIS losses) is a later row (SURVEY.md 8f item 2)")
+        raise NotImplementedError(f"solver {solver_type!r} is unknown")
     return base
 
 
@@ -224,6 +231,8 @@ def make_model(solver_type, ref_type, loss_type, integrator_type, model_type, ti
             cfg["train_timesteps"]["end"] = force_T_cosine
     elif solver_type == "pis_orig":
         cfg["sde"]["diff_coeff"] = solver_details["sigma"]
+    elif (solver_type == "dis_orig") or (solver_type == "dis_discrete"):
+        cfg["sde"]["scale_diff_coeff"] = solver_details["sigma"]
     elif ("ref" in solver_type) and (ref_type == "default"):
         if "pbm" in solver_type:
             cfg["sde"]["diff_coeff"] = solver_details["sigma"]

@@ -287,7 +287,7 @@ __global__ void __launch_bounds__(128) distr_eval_kernel(const lrds_spec s, cons
   const int d = s.d, dp = s.mlp.d_pad;
   for (int j = 0; j < dp; ++j) P.x(j) = (j < d) ? __ldg(x + (int64_t)b * d + j) : 0.f;
   const float lp = target_pass1<false>(s, s.target.kind, tv0, P, logp_out != nullptr);
-  if (live && logp_out) logp_out[b] = lp;
+  if (live && logp_out) logp_out[b] = lp + s.rnd_offset;
   if (!score_out) return;
   float xm = 0.f;
   for (int j0 = 0; j0 < dp; j0 += JC) {
@@ -345,6 +345,38 @@ int launch_cols(KernelT kernel, const lrds_spec& s, int floats, cudaStream_t st,
   return LRDS_OK;
 }
 
+// shared by lrds_distr_eval and the initial-cost pre-pass of lrds_rollout: logp_out = log-density + offset
+int distr_eval_launch(const lrds_distr* distr, int32_t d, const float* x, int32_t B, float* logp_out, float* score_out,
+                      float offset, cudaStream_t st) {
+  if (!distr || !x || B < 1 || d < 1 || (!logp_out && !score_out)) return fail(LRDS_ERR_INVALID, "distr_eval: bad arguments");
+  lrds_spec s;
+  memset(&s, 0, sizeof(s));
+  s.abi_version = LRDS_ABI_VERSION;
+  s.B = B;
+  s.d = d;
+  s.mlp.d = d;
+  s.mlp.d_pad = ((d + 7) / 8) * 8;
+  s.target = *distr;
+  s.ctrl_kind = LRDS_CTRL_CLIPPED;
+  s.rnd_offset = offset;
+  if (distr->kind == LRDS_DISTR_GMM) {
+    if (int r = validate_gmm(distr->gmm, "distr")) return r;
+  } else if (distr->kind == LRDS_DISTR_LOGREG) {
+    if (distr->logreg.p + 1 != d) return fail(LRDS_ERR_INVALID, "logreg: d must be p + 1");
+  } else if (distr->kind != LRDS_DISTR_PHI4) {
+    return fail(LRDS_ERR_UNSUPPORTED, "distr_eval: unknown distribution kind");
+  }
+  const lrds::ColLayout L = lrds::col_layout(s);
+  int nt = 0;
+  size_t smem = 0;
+  if (int r = launch_cols(distr_eval_kernel, s, L.total, st, &nt, &smem)) return r;
+  distr_eval_kernel<<<(B + nt - 1) / nt, nt, smem, st>>>(s, x, logp_out, score_out);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "distr_eval launch");
+  g_launches.fetch_add(1);
+  return LRDS_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -368,6 +400,14 @@ int lrds_rollout(const lrds_spec* spec, const float* x0, const float* noise, uin
   if (!linear && s.target.kind == LRDS_DISTR_NONE) return fail(LRDS_ERR_INVALID, "CMCD needs a target");
   cudaStream_t st = (cudaStream_t)stream;
   lrds::RolloutArgs a{s, x0, noise, seed, particle_offset, x_out, rnd_out, traj_out};
+  if (s.init_cost) {  // DIS (oc.py:1164-1168): rnd_out = initial_log_prob(x_0) + rnd_offset; the rollout kernel adds it
+    if (s.kind != LRDS_ROLLOUT_LINEAR) return fail(LRDS_ERR_INVALID, "init_cost is defined for the LINEAR simulate loop only");
+    lrds_distr prior;
+    memset(&prior, 0, sizeof(prior));
+    prior.kind = LRDS_DISTR_GMM;
+    prior.gmm = s.ref_0;
+    if (int r = distr_eval_launch(&prior, s.d, x0, s.B, rnd_out, nullptr, s.rnd_offset, st)) return r;
+  }
 
   if (s.precision != LRDS_PRECISION_FP32_SIMT) {
     const int r = lrds::launch_rollout_tc(a, st, g_err, sizeof(g_err));
@@ -493,33 +533,7 @@ int lrds_ctrl_forward(const lrds_spec* spec, int32_t row, const float* x, int32_
 
 int lrds_distr_eval(const lrds_distr* distr, int32_t d, const float* x, int32_t B, float* logp_out, float* score_out,
                     void* stream) {
-  if (!distr || !x || B < 1 || d < 1 || (!logp_out && !score_out)) return fail(LRDS_ERR_INVALID, "distr_eval: bad arguments");
-  lrds_spec s;
-  memset(&s, 0, sizeof(s));
-  s.abi_version = LRDS_ABI_VERSION;
-  s.B = B;
-  s.d = d;
-  s.mlp.d = d;
-  s.mlp.d_pad = ((d + 7) / 8) * 8;
-  s.target = *distr;
-  s.ctrl_kind = LRDS_CTRL_CLIPPED;
-  if (distr->kind == LRDS_DISTR_GMM) {
-    if (int r = validate_gmm(distr->gmm, "distr")) return r;
-  } else if (distr->kind == LRDS_DISTR_LOGREG) {
-    if (distr->logreg.p + 1 != d) return fail(LRDS_ERR_INVALID, "logreg: d must be p + 1");
-  } else if (distr->kind != LRDS_DISTR_PHI4) {
-    return fail(LRDS_ERR_UNSUPPORTED, "distr_eval: unknown distribution kind");
-  }
-  const lrds::ColLayout L = lrds::col_layout(s);
-  int nt = 0;
-  size_t smem = 0;
-  cudaStream_t st = (cudaStream_t)stream;
-  if (int r = launch_cols(distr_eval_kernel, s, L.total, st, &nt, &smem)) return r;
-  distr_eval_kernel<<<(B + nt - 1) / nt, nt, smem, st>>>(s, x, logp_out, score_out);
-  cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) return cuda_fail(e, "distr_eval launch");
-  g_launches.fetch_add(1);
-  return LRDS_OK;
+  return distr_eval_launch(distr, d, x, B, logp_out, score_out, 0.f, (cudaStream_t)stream);
 }
 
 int lrds_axpy_step(const float* x, const float* s, const float* z, float a, float b, float c, float* out, int64_t n,

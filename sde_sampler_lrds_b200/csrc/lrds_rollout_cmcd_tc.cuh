@@ -515,7 +515,8 @@ rollout_cmcd_tc_kernel(const RolloutArgs a, const uint8_t* __restrict__ image, c
   if (!half) {
     rnd += dimtab[pt];
     if (EUBO) rnd += prior_logp();                                   // oc.py:825
-    else if (LIN) rnd += prior_logp() - clipf(logreg_logp(LR, d, X), s.clip_target);  // ref_0 - target, oc.py:290, 1389
+    else if (LIN)  // ref_0 - target, oc.py:290, 1389; init_cost (DIS): the pre-pass result in rnd_out replaces ref_0(x_T)
+      rnd += (s.init_cost ? a.rnd_out[b] : prior_logp()) - clipf(logreg_logp(LR, d, X), s.clip_target);
     else rnd -= clipf(logreg_logp(LR, d, X), s.clip_target);         // oc.py:750
     if (live) a.rnd_out[b] = rnd;
   }

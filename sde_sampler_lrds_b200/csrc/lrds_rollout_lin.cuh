@@ -190,7 +190,8 @@ rollout_lin_kernel(const RolloutArgs a, const uint8_t* __restrict__ image, const
     const GmmView r0 = gmm_at(s.ref_0, 0);
     float q = 0.f;
     for (int c = 0; 4 * c < d; ++c) quad4(q, X.ld4(c), r0.mu.ld4(c), r0.ivar.ld4(c));
-    const float lref = r0.glogc.ld1(0) - 0.5f * q;
+    // init_cost (DIS): the pre-pass of lrds_rollout left initial_log_prob(x_0) + rnd_offset in rnd_out (oc.py:1164-1168)
+    const float lref = s.init_cost ? a.rnd_out[b] : r0.glogc.ld1(0) - 0.5f * q;
     float ltgt = 0.f;
     if (s.target.kind == LRDS_DISTR_PHI4) ltgt = phi4_logp(s.target.phi4, d, X);
     else if (s.target.kind == LRDS_DISTR_GMM) {

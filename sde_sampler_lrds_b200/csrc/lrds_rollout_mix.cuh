@@ -445,7 +445,8 @@ __device__ __forceinline__ void rollout_body_mix(const RolloutArgs& a, float* sm
     }
   }
   if constexpr (!EUBO) {  // terminal cost: rnd += reference_log_prob(x) - terminal_unnorm_log_prob(x)   (oc.py:290, 505, 645)
-    const float lref = gmm_logp_any(gmm_at(s.ref_0, 0), d, dp, P.x);
+    // init_cost (DIS): the pre-pass of lrds_rollout left initial_log_prob(x_0) + rnd_offset in rnd_out (oc.py:1164-1168)
+    const float lref = s.init_cost ? a.rnd_out[b] : gmm_logp_any(gmm_at(s.ref_0, 0), d, dp, P.x);
     rnd += lref - clipf(target_logp(), s.clip_target);
   }
 

@@ -392,8 +392,10 @@ __device__ __forceinline__ void rollout_body(const RolloutArgs& a, float* smem, 
       if (ito_form == LRDS_ITO_SCALED) rnd += wito * sito;
       else if (ito_form != LRDS_ITO_NONE) rnd += sito;
     }
-    // terminal cost: rnd += reference_log_prob(x) - terminal_unnorm_log_prob(x)   (oc.py:290, 505, 645, 1389)
-    const float lref = gmm_pass1<PIPE>(gmm_at(s.ref_0, 0), d, dp, P.x, P.rr);
+    // terminal cost: rnd += reference_log_prob(x) - terminal_unnorm_log_prob(x)   (oc.py:290, 505, 645, 1389);
+    // init_cost (DIS): the initial cost initial_log_prob(x_0) + rnd_offset, written to rnd_out by lrds_rollout's pre-pass,
+    // takes the place of the reference term (oc.py:1164-1168, 1230)
+    const float lref = s.init_cost ? a.rnd_out[b] : gmm_pass1<PIPE>(gmm_at(s.ref_0, 0), d, dp, P.x, P.rr);
     const float ltgt = clipf(target_pass1<PIPE>(s, tkind, tv, P, true), s.clip_target);
     rnd += lref - ltgt;
   }

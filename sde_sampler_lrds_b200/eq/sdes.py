@@ -130,6 +130,13 @@ class OU(TorchSDE):
     def drift_div(self, t, x):
         return self.drift_coeff_t(t) * x.shape[-1]
 
+    def int_drift_coeff_t(self, s, t):
+        raise NotImplementedError
+
+    def drift_div_int(self, s, t, x):
+        """Integral from s to t of the divergence of the drift (eq/sdes.py:137-141)."""
+        return self.int_drift_coeff_t(s, t) * x.shape[-1]
+
     def transition_params(self, s, t):
         """X_t = mean X_s + sqrt(var) Z for s < t (generic form, eq/sdes.py:167-178)."""
         mean = torch.exp(torch.log(self.s(t)) - torch.log(self.s(s)))
@@ -206,6 +213,9 @@ class ConstOU(OU):
     def diff_coeff_t(self, t):
         return self.diff_coeff
 
+    def int_drift_coeff_t(self, s, t):  # eq/sdes.py:385-389
+        return -self.drift_coeff * (t - s)
+
     def s(self, t):
         return torch.exp(-self.drift_coeff * t)
 
@@ -244,6 +254,9 @@ class VP(OU):
 
     def diff_coeff_t(self, t):
         return self.scale_diff_coeff * torch.sqrt(self._diff_coeff_sq_t(t))
+
+    def int_drift_coeff_t(self, s, t):  # eq/sdes.py:469-477
+        return -0.25 * (self._diff_coeff_sq_t(t) + self._diff_coeff_sq_t(s)) * (t - s)
 
     def alpha_(self, t):
         return self.diff_coeff_sq_min * t + (0.5 * t ** 2 / self.terminal_t) * (

@@ -7,6 +7,7 @@ signatures (sde_sampler/losses/oc.py): ``simulate`` / ``eval`` / ``compute_eubo`
     DDPMLikeReferenceSDELoss      oc.py:571-651
     ControlledLangevinSDELoss     oc.py:654-894   (CMCD)
     ExponentialIntegratorSDELoss  oc.py:1310-1467 (DDS)
+    TimeReversalLoss              oc.py:1105-1307 (DIS: inference_ctrl=None)
 
 Extra keyword arguments (not in the reference, all optional): ``noise`` = recorded standard normals [K, B, d]
 to consume instead of in-kernel Philox draws (validation mode), ``seed`` / ``particle_offset`` for the
@@ -341,6 +342,81 @@ class ExponentialIntegratorSDELoss(BaseOCLoss):
         samples, rnd, xs = self.simulate(ts, x, terminal_unnorm_log_prob=terminal_unnorm_log_prob,
                                          reference_log_prob=reference_log_prob, compute_ito_int=compute_weights,
                                          change_sde_ctrl=False, return_traj=return_traj, use_ema=use_ema, **kw)
+        return BaseOCLoss.compute_results(rnd, compute_weights=compute_weights, ts=ts, samples=samples, xs=xs)
+
+
+class TimeReversalLoss(BaseOCLoss):
+    """Original DIS loss, evaluation side (Bridge with ``inference_ctrl=None``, solver/oc.py:185-262): Euler-Maruyama
+    with the control taken at the loop time, log-weight = initial_log_prob(x_0) + running cost - divergence integral
+    [+ Ito term] - target(x_T)  (oc.py:1164-1230)."""
+
+    def __init__(self, *args, inference_ctrl: Callable | None = None, div_estimator: str | None = None,
+                 use_rescaling: bool = True, **kwargs):
+        super().__init__(*args, **kwargs)
+        if inference_ctrl is not None:
+            raise NotImplementedError("a learned inference control (the general bridge sampler, divergence through "
+                                      "autograd) has no fused kernel; DIS uses inference_ctrl=None (SURVEY.md 8f item 2)")
+        if not use_rescaling:
+            raise ValueError("use_rescaling must be True for TimeReversalLoss.")
+        self.inference_ctrl = None
+        self.div_estimator = div_estimator
+        self.use_rescaling = use_rescaling
+
+    def _plan(self, ts, device, use_ema, terminal_unnorm_log_prob, initial_log_prob, compute_ito_int):
+        info = self._ctrl(use_ema)
+        prior, _ = pack.resolve_log_prob(initial_log_prob)
+        key = self._key(("dis", bool(compute_ito_int)), ts, device, info, (id(prior), id(terminal_unnorm_log_prob)))
+
+        def build():
+            sde = self.sde.host()
+            tsc, pairs = pack._scalar_rows(ts)
+            K = len(pairs)
+            spec = pack.new_spec(self.precision)
+            keep: list = []
+            pack.fill_ctrl(spec, info, device, keep)
+            _terminal(spec, keep, device, terminal_unnorm_log_prob, info)
+            spec.K, spec.kind = K, N.ROLLOUT_LINEAR
+            spec.update_form = N.UPDATE_EM
+            spec.ito_form = N.ITO_EM if compute_ito_int else N.ITO_NONE
+            spec.has_ref_ctrl = 0
+            table = torch.zeros(K, N.STEP_STRIDE)
+            div = torch.zeros(())
+            for k, (s, t) in enumerate(pairs):  # oc.py:1171-1230
+                row = table[k]
+                dt = t - s
+                sig = sde.diff(s)
+                # the EM update of the kernel is x + ((-(A x)) + sig u) dt + sig z sqrt(dt): A = -drift_coeff_t(s) gives +drift
+                row[N.STEP_A], row[N.STEP_B], row[N.STEP_C] = -sde.drift_coeff_t(s), sig, torch.square(sig)
+                row[N.STEP_W_COST] = 0.5 * dt
+                row[N.STEP_DT], row[N.STEP_SQRT_DT] = dt, dt.sqrt()
+                div = div - sde.int_drift_coeff_t(s, t) * spec.d  # rnd -= sde.drift_div_int(s, t, x), train=False (1217-1218)
+            spec_table = pack.finish_table(table, info, tsc[:-1], device)
+            spec.steps = spec_table.data_ptr()
+            keep.append(spec_table)
+            blk0 = pack.gauss_block_from(prior, device)
+            if blk0[1].shape[0] != 1:
+                raise NotImplementedError("DIS needs a Gaussian prior (solver/oc.py:207-208)")
+            fill_gmm(spec.ref_0, blk0)
+            keep.append(blk0)
+            spec.init_cost, spec.rnd_offset = 1, float(div)
+            return pack.Plan(spec, keep, rows=K, noise_steps=K)
+        return self._cached(key, build)
+
+    def simulate(self, ts, x, terminal_unnorm_log_prob, initial_log_prob=None, train: bool = True,
+                 compute_ito_int: bool = False, change_sde_ctrl: bool = False, return_traj: bool = False,
+                 use_ema: bool = False, noise=None, seed=None, particle_offset: int = 0):
+        self._check_plain(change_sde_ctrl)
+        if train:
+            raise NotImplementedError("the training variant (no divergence integral, rnd starting at 0 for kl; "
+                                      "oc.py:1164-1168, 1217) is part of SURVEY.md 8f item 1; eval passes train=False")
+        plan = self._plan(ts, x.device, use_ema, terminal_unnorm_log_prob, initial_log_prob, compute_ito_int)
+        return pack.run_rollout(plan, x, noise, self._seed(seed), particle_offset, return_traj)
+
+    def eval(self, ts, x, terminal_unnorm_log_prob, initial_log_prob=None, compute_weights: bool = True,
+             return_traj: bool = True, use_ema: bool = True, **kw) -> Results:
+        samples, rnd, xs = self.simulate(ts, x, terminal_unnorm_log_prob=terminal_unnorm_log_prob,
+                                         initial_log_prob=initial_log_prob, compute_ito_int=compute_weights,
+                                         train=False, return_traj=return_traj, use_ema=use_ema, **kw)
         return BaseOCLoss.compute_results(rnd, compute_weights=compute_weights, ts=ts, samples=samples, xs=xs)
 
 

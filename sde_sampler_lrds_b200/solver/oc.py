@@ -1,5 +1,5 @@
 """Diffusion-based samplers with the reference's class names and evaluation entry points
-(sde_sampler/solver/oc.py: TrainableDiff 22-182, CMCD 264-346, PIS 349-423, DDS 426-492, RDS 495-666; the parts of
+(sde_sampler/solver/oc.py: TrainableDiff 22-182, Bridge 185-262 (DIS), CMCD 264-346, PIS 349-423, DDS 426-492, RDS 495-666; the parts of
 sde_sampler/solver/base.py they rely on: seed 52-55, device 57-61, target 64-65).
 
 The reference builds these objects from a Hydra config; Hydra / OmegaConf are not part of this image, so the
@@ -128,6 +128,30 @@ class TrainableDiff(torch.nn.Module):
         return results
 
     evaluate = compute_results
+
+
+class Bridge(TrainableDiff):
+    """DIS (``inference_ctrl`` absent; solver/oc.py:185-262).  The general bridge sampler with a learned inference
+    control needs the divergence of a network through autograd and has no fused kernel."""
+
+    def setup_models(self):
+        super().setup_models()
+        if self.cfg.get("inference_ctrl") is not None:
+            raise NotImplementedError("Bridge with a learned inference_ctrl has no B200 kernel (SURVEY.md 8f item 2); "
+                                      "DIS (inference_ctrl=None) does")
+        self.inference_ctrl = None
+        self.inference_sde = build(self.cfg["sde"]).to(self.device)
+        if not isinstance(self.prior, Gauss):
+            raise ValueError("Can only be used with Gaussian prior.")
+        self.loss: BaseOCLoss = build(self.cfg["loss"], generative_ctrl=self.generative_ctrl,
+                                      generative_ctrl_ema=self.generative_ctrl_ema, sde=self.sde,
+                                      inference_ctrl=self.inference_ctrl,
+                                      filter_samples=getattr(self.target, "filter", None))
+
+    def _compute_results(self, ts, x, use_ema=True, compute_weights=True, return_traj=True) -> Results:
+        return self.loss.eval(ts, x, self.clipped_target_unnorm_log_prob, use_ema=use_ema,
+                              initial_log_prob=self.prior.log_prob, compute_weights=compute_weights,
+                              return_traj=return_traj)
 
 
 class CMCD(TrainableDiff):

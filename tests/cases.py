@@ -227,6 +227,23 @@ def case_dds_many_modes(compute_ito_int=True):
         "B": 120, "seed": 118, "prior": ("iso", 0.0, 2.0), "compute_ito_int": compute_ito_int}
 
 
+def case_dis(target="many_modes", compute_ito_int=True, scale=1.0):
+    """DIS (dis_orig: solver Bridge + TimeReversalLoss with inference_ctrl=None, conf/solver/dis.yaml): VP 0.1..10,
+    Euler-Maruyama, control at the loop time, prior IsotropicGauss(scale=sde.scale_diff_coeff), ScoreCtrl drift
+    (model_type target_informed_zero_init)."""
+    sde = dict(VP10, scale=scale)
+    if target == "many_modes":
+        d, K, B, tgt, c = 10, 90, 120, many_modes(7, 10), dict(seed=31, out_gain=0.5, gamma=0.02)
+    elif target == "phi4":
+        d, K, B, tgt, c = 24, 80, 100, phi4(24), dict(seed=32, out_gain=0.3, gamma=0.004)
+    else:
+        d, K, B, tgt, c = 61, 40, 96, logreg_synthetic(166, 60), dict(seed=33, out_gain=0.5, gamma=0.01)
+    return {
+        "problem": {"method": "dis", "sde": sde, "ts": uniform_ts(1.0, K), "target": tgt, "ctrl": ctrl(d, "score", **c),
+                    "ref": {"kind": "iso", "loc": 0.0, "scale": scale}},
+        "B": B, "seed": 120 + len(target), "prior": ("iso", 0.0, scale), "compute_ito_int": compute_ito_int}
+
+
 def case_ei_phi4_gauss():
     """RDS vp-ref with its default Gaussian reference over the PhiFour lattice (experiments/sample_phi_four_competing.py)."""
     d = 24
@@ -354,6 +371,10 @@ CASES = {
     "cmcd_gmm": case_cmcd_gmm,
     "pis_logreg": lambda: case_pis_logreg(),
     "dds_logreg": lambda: case_dds_logreg(),
+    "dis_many_modes_ito": lambda: case_dis("many_modes", True),
+    "dis_many_modes_noito": lambda: case_dis("many_modes", False, scale=1.5),
+    "dis_phi4": lambda: case_dis("phi4"),
+    "dis_logreg": lambda: case_dis("logreg"),
     "eubo_em_two_modes": lambda: _eubo(case_em_two_modes("score"), 201),
     "eubo_ei_many_modes": lambda: _eubo(case_ei_many_modes(K=100, B=100), 202),
     "eubo_cmcd_gmm": lambda: _eubo(case_cmcd_gmm(), 203),

@@ -87,6 +87,13 @@ class Built:
             self.loss = oc.ExponentialIntegratorSDELoss(alpha=p["alpha"], sigma=p["sigma"], sde=None, **kw)
             self.args = (self.target.unnorm_log_prob, self.prior.log_prob)
             self.kwargs = {"compute_ito_int": case.get("compute_ito_int", True)}
+        elif method == "dis":
+            self.sde = build_sde(p["sde"], device)
+            self.prior = IsotropicGauss(dim=d, loc=p["ref"]["loc"], scale=p["ref"]["scale"]).to(device)
+            self.loss = oc.TimeReversalLoss(sde=self.sde, inference_ctrl=None, **kw)
+            self.args = (self.target.unnorm_log_prob,)
+            self.kwargs = {"initial_log_prob": self.prior.log_prob, "train": False,
+                           "compute_ito_int": case.get("compute_ito_int", True)}
         elif method == "cmcd":
             pr = p["prior"]
             if pr.get("isotropic"):

@@ -54,5 +54,7 @@ def test_default_config_resolves_the_yaml_defaults():
     assert c["solver"] is S.CMCD and c["prior"]["scale"] == 5.0 and c["loss"]["max_rnd"] is None and c["sde"]["clip_score"] == 1e5
     c = BU._resolve(BU.default_config("pbm-ref", "base_zero_init", "lv", BU.make_target_details("two_modes")))
     assert c["train_timesteps"]["start"] == 1e-4 and c["train_timesteps"]["end"] == 5.0
-    with pytest.raises(NotImplementedError):
-        BU.default_config("dis_orig", "target_informed_zero_init", "lv", BU.make_target_details("two_modes"))
+    c = BU._resolve(BU.default_config("dis_orig", "target_informed_zero_init", "lv", BU.make_target_details("two_modes"),
+                                      force_vp20=True))
+    assert c["solver"] is S.Bridge and c["loss"]["_target_"] is L.TimeReversalLoss and c["loss"]["max_rnd"] == 1e8
+    assert c["sde"]["diff_coeff_sq_max"] == 20.0 and c["prior"]["scale"] == 1.0 and c["train_timesteps"]["end"] == 1.0

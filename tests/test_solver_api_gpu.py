@@ -37,6 +37,8 @@ def _randomise_last_layers(model, gain=0.5):
     ("pis_orig", dict(ref_type="default", integrator_type="em", time_type="uniform")),
     ("dds_orig", dict(ref_type="default", integrator_type="em", time_type="uniform")),
     ("cmcd", dict(ref_type="gaussian", integrator_type="em", time_type="uniform")),
+    ("dis_orig", dict(ref_type="default", integrator_type="em", time_type="uniform")),
+    ("dis_orig", dict(ref_type="default", integrator_type="em", time_type="uniform", force_vp20=True)),
 ])
 def test_make_model_evaluate(solver_type, kw, device):
     from sde_sampler_lrds_b200 import benchmark_utils as BU
@@ -58,7 +60,7 @@ def test_make_model_evaluate(solver_type, kw, device):
     for k in ("eval/elbo", "eval/lv_loss", "eval/sample_time"):
         assert math.isfinite(res.metrics[k]), k
     assert math.isfinite(res.log_norm_const_preds["log_norm_const_is"])
-    if model.eubo_available:
+    if model.eubo_available and hasattr(model.loss, "compute_eubo"):  # TimeReversalLoss has none (hacking.py:84)
         for k in ("eval/eubo", "eval/log_norm_const_is_f", "eval/effective_sample_size_f"):
             assert math.isfinite(res.metrics[k]), k
         assert 1.0 <= res.metrics["eval/effective_sample_size_f"] <= B + 1e-3
@@ -69,7 +71,7 @@ def test_make_model_evaluate(solver_type, kw, device):
     # the estimators agree with the oracle's formulas on the very same log-weights
     x, rnd, _ = model.loss.simulate(model.eval_ts, model.prior.sample((B,)), model.clipped_target_unnorm_log_prob,
                                     *( [model.reference_distr.log_prob] if hasattr(model, "reference_distr") else []),
-                                    **({"initial_log_prob": model.prior.log_prob, "train": False} if solver_type == "cmcd" else {}),
+                                    **({"initial_log_prob": model.prior.log_prob, "train": False} if solver_type in ("cmcd", "dis_orig") else {}),
                                     seed=5)
     got = type(model.loss).compute_results(rnd, compute_weights=True)
     want = O.compute_results(rnd.cpu())
