@@ -52,7 +52,14 @@ typedef enum {
 
 typedef enum {
   LRDS_CTRL_CLIPPED = 0, /* ClippedCtrl.forward, models/reparam.py:33-43 (base_zero_init) */
-  LRDS_CTRL_SCORE = 1    /* ScoreCtrl.forward, models/reparam.py:112-117 (target_informed_zero_init) */
+  LRDS_CTRL_SCORE = 1,   /* ScoreCtrl.forward, models/reparam.py:112-117 (target_informed_zero_init) */
+  /* The two DIS parametrisations (LINEAR simulate and lrds_ctrl_forward only; they run the run-time-switched kernels): */
+  LRDS_CTRL_CANCEL_DRIFT = 2, /* CancelDriftCtrl.forward, models/reparam.py:131-147 (target_informed_langevin_init):
+                               * u = (clip(net) + CX x) + GSCALE ((scale_score clip(target_score)) gamma),  CX = f(t)/sigma(t),
+                               * GSCALE = sigma(t)/2 */
+  LRDS_CTRL_LERP = 3     /* LerpCtrl.forward, models/reparam.py:189-199 (target_informed_lerp_tempering, hard_constrain=False):
+                          * u = clip(net) + GSCALE ((scale_score clip(lerp(prior_score, target_score, LERP))) gamma),
+                          * GSCALE = sigma(t), LERP = t / terminal_t, prior_score from ref_0 (a diagonal Gaussian: the prior) */
 } lrds_ctrl_kind;
 
 typedef enum {
@@ -90,6 +97,9 @@ enum {
   LRDS_STEP_EU_A = 10,   /* EUBO: mean factor                                                              */
   LRDS_STEP_EU_B = 11,   /* EUBO: std factor                                                               */
   LRDS_STEP_EU_C = 12,   /* EUBO-EM: 1/mean - 1 + f(tau) dt ; EUBO ito weight in W_ITO                      */
+  LRDS_STEP_CX = 13,     /* LRDS_CTRL_CANCEL_DRIFT: sde.drift_coeff_t(t) / sde.diff(t)                         */
+  LRDS_STEP_LERP = 14,   /* LRDS_CTRL_LERP: t / sde.terminal_t                                                */
+  LRDS_STEP_GSCALE = 15, /* LRDS_CTRL_CANCEL_DRIFT: sde.diff(t) / 2 ; LRDS_CTRL_LERP: sde.diff(t)              */
   LRDS_STEP_BIAS1 = 16,  /* 64 floats: input_embed.bias + TimeEmbed_2(tau), models/mlp.py:136-139           */
   LRDS_STEP_STRIDE = 80
 };

@@ -92,14 +92,21 @@ def build_reference_target(ss, tgt):
 
 def build_reference_ctrl(c, d, target_score):
     from sde_sampler.models.mlp import FourierMLP, TimeEmbed
-    from sde_sampler.models.reparam import ClippedCtrl, ScoreCtrl
+    from sde_sampler.distr.gauss import IsotropicGauss
+    from sde_sampler.models.reparam import CancelDriftCtrl, ClippedCtrl, LerpCtrl, ScoreCtrl
     num_hidden = sum(1 for k in c["sd"] if k.startswith("base_model.hidden_layer.") and k.endswith(".weight"))
     base = FourierMLP(dim=d, activation=torch.nn.GELU(), num_layers=num_hidden + 2, channels=64)
-    if c["kind"] == "score":
-        m = ScoreCtrl(base_model=base, score_model=TimeEmbed(dim_out=1, activation=torch.nn.GELU(), num_layers=4,
-                                                             channels=64),
-                      target_score=target_score, detach_score=False, clip_score=c["clip_score"],
-                      clip_model=c["clip_model"], scale_score=c["scale_score"])
+    if c["kind"] in ("score", "cancel", "lerp"):
+        kw = dict(base_model=base, score_model=TimeEmbed(dim_out=1, activation=torch.nn.GELU(), num_layers=4, channels=64),
+                  target_score=target_score, detach_score=False, clip_score=c["clip_score"],
+                  clip_model=c["clip_model"], scale_score=c["scale_score"])
+        if c["kind"] == "score":
+            m = ScoreCtrl(**kw)
+        elif c["kind"] == "cancel":  # conf/model/langevin_init.yaml
+            m = CancelDriftCtrl(sde=build_reference_sde(c["sde"]), langevin_init=True, **kw)
+        else:  # conf/model/lerp.yaml (its 'hard_constraint' key is swallowed by ClippedCtrl's **kwargs)
+            prior = IsotropicGauss(dim=d, loc=c["prior"]["loc"], scale=c["prior"]["scale"])
+            m = LerpCtrl(sde=build_reference_sde(c["sde"]), prior_score=prior.score, hard_constraint=False, **kw)
     else:
         m = ClippedCtrl(base_model=base, clip_model=c["clip_model"])
     missing, unexpected = m.load_state_dict({k: v.clone() for k, v in c["sd"].items()}, strict=True)

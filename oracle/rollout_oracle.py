@@ -69,20 +69,32 @@ def clip(x: torch.Tensor, max_norm) -> torch.Tensor:
     return x if max_norm is None else x.clip(min=-1.0 * max_norm, max=max_norm)
 
 
-def make_ctrl(ctrl: dict, target_score: Callable | None) -> Callable:
-    """ClippedCtrl.forward (models/reparam.py:33-43) / ScoreCtrl.forward (models/reparam.py:91-117).
+def make_ctrl(ctrl: dict, target_score: Callable | None, dtype=torch.float32) -> Callable:
+    """ClippedCtrl.forward (models/reparam.py:33-43) / ScoreCtrl.forward (91-117) / CancelDriftCtrl.forward (131-147,
+    use_rescaling=True) / LerpCtrl.forward (170-199, hard_constrain=False).
 
-    ctrl = {"kind": "clipped"|"score", "sd": state_dict, "clip_model", "clip_score", "scale_score"}.
+    ctrl = {"kind": "clipped"|"score"|"cancel"|"lerp", "sd": state_dict, "clip_model", "clip_score", "scale_score"
+            [, "sde": sde dict (cancel, lerp)] [, "prior": {"loc", "scale"} of the IsotropicGauss prior (lerp)]}.
     """
     sd = ctrl["sd"]
+    kind = ctrl["kind"]
+    sde = make_sde(ctrl["sde"], dtype) if kind in ("cancel", "lerp") else None
 
     def forward(t: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
         base = clip(fourier_mlp(sd, "base_model.", t, x), ctrl.get("clip_model"))
-        if ctrl["kind"] == "clipped":
+        if kind == "clipped":
             return base
-        score = ctrl.get("scale_score", 1.0) * clip(target_score(x), ctrl.get("clip_score"))
+        raw = target_score(x)
+        if kind == "lerp":  # clipped_interpolated_score, reparam.py:170-183; IsotropicGauss.score, distr/gauss.py:764-766
+            pr = ctrl["prior"]
+            raw = torch.lerp((pr["loc"] - x) / pr["scale"] ** 2, raw, t / sde.T)
+        score = ctrl.get("scale_score", 1.0) * clip(raw, ctrl.get("clip_score"))
         if any(k.startswith("score_model.") for k in sd):
             score = score * clip(time_embed(sd, "score_model.", t), ctrl.get("clip_model"))
+        if kind == "cancel":  # reparam.py:135-145
+            return base + (sde.drift_coeff(t) * x) / sde.diff(t) + 0.5 * sde.diff(t) * score
+        if kind == "lerp":  # reparam.py:199
+            return base + sde.diff(t) * score
         return base + score
 
     return forward
@@ -700,7 +712,7 @@ def rollout(problem: dict, x0: torch.Tensor, noise: torch.Tensor, *, eubo: bool 
     if problem.get("clip_target") is not None:  # TrainableDiff.clipped_target_unnorm_log_prob, solver/oc.py:80-87
         raw = target_logp
         target_logp = lambda x: clip(raw(x), problem["clip_target"])  # noqa: E731
-    ctrl = make_ctrl(problem["ctrl"], target_score)
+    ctrl = make_ctrl(problem["ctrl"], target_score, dtype)
     method = problem["method"]
     with torch.no_grad():
         if method in ("em", "ei", "ddpm"):

@@ -22,13 +22,13 @@ ABI_VERSION = 6
 CHANNELS = 64
 STEP_STRIDE = 80
 (STEP_A, STEP_B, STEP_C, STEP_DT, STEP_SQRT_DT, STEP_W_COST, STEP_W_ITO, STEP_GAMMA, STEP_FRAC, STEP_SIGU,
- STEP_EU_A, STEP_EU_B, STEP_EU_C) = range(13)
+ STEP_EU_A, STEP_EU_B, STEP_EU_C, STEP_CX, STEP_LERP, STEP_GSCALE) = range(16)
 STEP_BIAS1 = 16
 
 ROLLOUT_LINEAR, ROLLOUT_CMCD, ROLLOUT_EUBO_LINEAR, ROLLOUT_EUBO_CMCD = range(4)
 UPDATE_AXPY, UPDATE_EM = range(2)
 ITO_NONE, ITO_SCALED, ITO_EM, ITO_DDS = range(4)
-CTRL_CLIPPED, CTRL_SCORE = range(2)
+CTRL_CLIPPED, CTRL_SCORE, CTRL_CANCEL_DRIFT, CTRL_LERP = range(4)
 DISTR_NONE, DISTR_GMM, DISTR_PHI4, DISTR_LOGREG = range(4)
 PRECISION_FP32_SIMT, PRECISION_TF32X3, PRECISION_BF16, PRECISION_TF32, PRECISION_F16X3 = range(5)
 PRECISIONS = {"fp32": PRECISION_FP32_SIMT, "tf32x3": PRECISION_TF32X3, "bf16": PRECISION_BF16, "tf32": PRECISION_TF32,

@@ -3,8 +3,7 @@
 (conf/solver/*.yaml and the groups they pull in) into a plain dict and ``make_model`` applies
 the same patches in the same order (benchmark_utils.py:176-262).
 
-Differences, all loud: the U-Net / lerp / langevin-init controls and 'nn' references raise
-NotImplementedError (rows of SURVEY.md 8f), sample-based metrics (Sinkhorn / MMD / KS) are not attached, and the
+Differences, all loud: the U-Net controls and 'nn' references raise NotImplementedError (rows of SURVEY.md 8f), sample-based metrics (Sinkhorn / MMD / KS) are not attached, and the
 logistic-regression targets read ``<data_dir>/<name>.pkl`` (pass ``target_details['data_dir']`` or set
 ``LRDS_DATA_DIR``; the datasets are not redistributed here).
 """
@@ -23,8 +22,8 @@ from .distr.phi_four import PhiFour
 from .eq.sdes import VP, ControlledLangevinSDE, PinnedBM, ScaledBM
 from .losses import oc as L
 from .models.mlp import FourierMLP, TimeEmbed
-from .models.reparam import ClippedCtrl, ScoreCtrl
-from .models.utils import init_bias_uniform_zeros, kaiming_uniform_zeros_
+from .models.reparam import CancelDriftCtrl, ClippedCtrl, LerpCtrl, ScoreCtrl
+from .models.utils import init_bias_uniform_constant, init_bias_uniform_zeros, kaiming_uniform_zeros_
 from .solver import oc as S
 from .utils.common import get_timesteps
 
@@ -94,7 +93,17 @@ def _model_cfg(model_type: str, dim: int) -> dict:
                                 "last_bias_init": {"_target_": init_bias_uniform_zeros, "_partial_": True},
                                 "last_weight_init": {"_target_": kaiming_uniform_zeros_, "_partial_": True}},
                 "detach_score": False, "clip_score": 1e4, "clip_model": 1e4, "scale_score": 1.0}
-    raise NotImplementedError(f"model_type {model_type!r} has no B200 kernel yet (SURVEY.md 8f items 2-3)")
+    if model_types[model_type] in ("langevin_init", "lerp"):  # conf/model/langevin_init.yaml, conf/model/lerp.yaml
+        cfg = _model_cfg("target_informed_zero_init", dim)
+        cfg["score_model"]["last_bias_init"] = {"_target_": init_bias_uniform_constant, "val": 1.0, "_partial_": True}
+        cfg["_wants_sde"] = True
+        if model_types[model_type] == "langevin_init":
+            cfg.update({"_target_": CancelDriftCtrl, "langevin_init": True})
+            del cfg["scale_score"]
+        else:
+            cfg.update({"_target_": LerpCtrl, "_wants_prior_score": True, "hard_constraint": False})
+        return cfg
+    raise NotImplementedError(f"model_type {model_type!r} has no B200 kernel yet (SURVEY.md 8f item 3)")
 
 
 def default_config(solver_type: str, model_type: str, loss_type: str, target_details: dict, force_vp20=False) -> dict:
@@ -206,6 +215,10 @@ def make_model(solver_type, ref_type, loss_type, integrator_type, model_type, ti
         raise ValueError("Can't use ref other than gaussian for CMCD.")
     if (model_type == "target_informed_langevin_init") and (integrator_type in ["ei", "ddpm_like"]):
         raise ValueError("Can't use EI or DDPM-like with Langevin score.")
+    if (model_type == "target_informed_langevin_init") and ("ref" in solver_type):
+        raise NotImplementedError("the reference wraps this control in RemoveReferenceCtrl(..., sde=None) whose forward "
+                                  "dereferences the missing sde (benchmark_utils.py:261-262, models/reparam.py:58-64): "
+                                  "there is no reference behaviour to reproduce")
     if force_vp_cosine:
         raise NotImplementedError("CosineVP is not on the rollout path built here (SURVEY.md section 2 row 2: secondary)")
 

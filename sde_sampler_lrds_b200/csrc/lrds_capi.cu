@@ -56,7 +56,9 @@ int validate_spec(const lrds_spec* s, bool need_steps) {
       (s->mlp.num_hidden > 0 && (!s->mlp.w_hid_t || !s->mlp.b_hid)))
     return fail(LRDS_ERR_INVALID, "mlp weight pointers missing");
   if (need_steps && !s->steps) return fail(LRDS_ERR_INVALID, "per-step table missing");
-  if (s->ctrl_kind != LRDS_CTRL_CLIPPED && s->ctrl_kind != LRDS_CTRL_SCORE) return fail(LRDS_ERR_INVALID, "unknown ctrl_kind");
+  if (s->ctrl_kind < LRDS_CTRL_CLIPPED || s->ctrl_kind > LRDS_CTRL_LERP) return fail(LRDS_ERR_INVALID, "unknown ctrl_kind");
+  if (s->ctrl_kind == LRDS_CTRL_LERP && (s->ref_0.M != 1 || !s->ref_0.mu || !s->ref_0.ivar))
+    return fail(LRDS_ERR_INVALID, "LerpCtrl needs the diagonal Gaussian prior in ref_0");
   switch (s->target.kind) {
     case LRDS_DISTR_GMM:
       if (int r = validate_gmm(s->target.gmm, "target")) return r;
@@ -69,7 +71,7 @@ int validate_spec(const lrds_spec* s, bool need_steps) {
         return fail(LRDS_ERR_INVALID, "logistic-regression block inconsistent");
       break;
     case LRDS_DISTR_NONE:
-      if (s->ctrl_kind == LRDS_CTRL_SCORE) return fail(LRDS_ERR_INVALID, "ScoreCtrl needs a target");
+      if (s->ctrl_kind != LRDS_CTRL_CLIPPED) return fail(LRDS_ERR_INVALID, "ScoreCtrl needs a target");
       break;
     default:
       return fail(LRDS_ERR_UNSUPPORTED, "unknown target kind");
@@ -255,7 +257,8 @@ __global__ void __launch_bounds__(128) ctrl_forward_kernel(const lrds_spec s, in
   const int d = s.d, dp = s.mlp.d_pad;
   for (int j = 0; j < dp; ++j) P.x(j) = (j < d) ? __ldg(x + (int64_t)b * d + j) : 0.f;
   const float* row = s.steps + (int64_t)rowi * LRDS_STEP_STRIDE;
-  const bool score_ctrl = s.ctrl_kind == LRDS_CTRL_SCORE;
+  const bool score_ctrl = s.ctrl_kind != LRDS_CTRL_CLIPPED;
+  const CtrlConst cc = ctrl_const(s);
   if (score_ctrl) target_pass1<false>(s, s.target.kind, tv0, P, false);
   mlp.template hidden<false>(row + LRDS_STEP_BIAS1, P.x);
   float xm = 0.f;
@@ -264,7 +267,13 @@ __global__ void __launch_bounds__(128) ctrl_forward_kernel(const lrds_spec s, in
     load_chunk(P.x, j0, xr);
     const float xp = (j0 + JC < dp) ? P.x(j0 + JC) : 0.f;
     if (score_ctrl) target_score_chunk<false>(s, s.target.kind, tv0, P, xr, xm, xp, j0, ts);
-    ctrl_chunk(ctrl_const(s), mlp, j0, ts, __ldg(row + LRDS_STEP_GAMMA), u);
+    if (s.ctrl_kind >= LRDS_CTRL_CANCEL_DRIFT) {
+      float ps[JC] = {};
+      if (s.ctrl_kind == LRDS_CTRL_LERP) gmm_score_chunk<false, false>(gmm_at(s.ref_0, 0), d, dp, xr, P.rr, j0, ps);
+      ctrl_chunk_dis(cc, mlp, j0, ts, xr, ps, ctrl_step(row), u);
+    } else {
+      ctrl_chunk(cc, mlp, j0, ts, __ldg(row + LRDS_STEP_GAMMA), u);
+    }
     xm = xr[JC - 1];
     if (live)
 #pragma unroll
@@ -394,6 +403,8 @@ int lrds_rollout(const lrds_spec* spec, const float* x0, const float* noise, uin
   if (int r = validate_gmm(s.ref_0, "ref_0")) return r;
   const bool linear = s.kind == LRDS_ROLLOUT_LINEAR || s.kind == LRDS_ROLLOUT_EUBO_LINEAR;
   if (s.kind == LRDS_ROLLOUT_EUBO_LINEAR && !s.has_ref_ctrl) return fail(LRDS_ERR_INVALID, "compute_eubo needs a reference control");
+  if (s.ctrl_kind >= LRDS_CTRL_CANCEL_DRIFT && s.kind != LRDS_ROLLOUT_LINEAR)
+    return fail(LRDS_ERR_UNSUPPORTED, "CancelDriftCtrl / LerpCtrl are built for the LINEAR simulate loop (DIS) only");
   if (linear && s.has_ref_ctrl)
     if (int r = validate_gmm(s.ref_t, "ref_t")) return r;
   if (!linear && s.ref_0.M != 1) return fail(LRDS_ERR_UNSUPPORTED, "CMCD needs a diagonal Gaussian prior");
@@ -518,7 +529,7 @@ int lrds_ctrl_forward(const lrds_spec* spec, int32_t row, const float* x, int32_
   s.kind = LRDS_ROLLOUT_LINEAR;
   s.precision = LRDS_PRECISION_FP32_SIMT;  // this entry point evaluates the network with fp32 FFMA
   s.has_ref_ctrl = 0;
-  s.ref_0.M = 0;
+  if (s.ctrl_kind != LRDS_CTRL_LERP) s.ref_0.M = 0;  // LerpCtrl reads the prior from ref_0
   const lrds::ColLayout L = lrds::col_layout(s);
   int nt = 0;
   size_t smem = 0;

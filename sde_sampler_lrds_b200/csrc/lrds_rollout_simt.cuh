@@ -156,7 +156,8 @@ __host__ __device__ inline int ref_class(const lrds_spec& s) { return !s.has_ref
 template <class TR>
 __host__ __device__ inline bool traits_match(const lrds_spec& s) {
   return (TR::kUpdate < 0 || TR::kUpdate == s.update_form) && (TR::kIto < 0 || TR::kIto == s.ito_form) &&
-         (TR::kTarget < 0 || TR::kTarget == s.target.kind) && (TR::kScore < 0 || TR::kScore == (s.ctrl_kind == LRDS_CTRL_SCORE)) &&
+         (TR::kTarget < 0 || TR::kTarget == s.target.kind) &&
+         (TR::kScore < 0 || (s.ctrl_kind <= LRDS_CTRL_SCORE && TR::kScore == (s.ctrl_kind == LRDS_CTRL_SCORE))) &&
          (TR::kRef < 0 || TR::kRef == ref_class(s)) &&
          (!TR::kMix || ((s.target.kind != LRDS_DISTR_GMM || s.target.gmm.M > 1) && (!s.has_ref_ctrl || s.ref_t.M > 1)));
 }
@@ -226,11 +227,13 @@ __device__ __forceinline__ void store_chunk(const Col4& v, int j0, const float (
 // `ts` (ScoreCtrl) and gamma = clip(score_model(tau)).   models/reparam.py:33-43, 112-117
 struct CtrlConst {
   float bound_model, bound_score, scale_score;
-  bool score;
+  bool score;  // the control has a target-score term (every kind but ClippedCtrl)
   int d;
+  int kind;    // lrds_ctrl_kind
 };
 __device__ __forceinline__ CtrlConst ctrl_const(const lrds_spec& s) {
-  return CtrlConst{clip_bound(s.clip_model), clip_bound(s.clip_score), s.scale_score, s.ctrl_kind == LRDS_CTRL_SCORE, s.d};
+  return CtrlConst{clip_bound(s.clip_model), clip_bound(s.clip_score), s.scale_score, s.ctrl_kind != LRDS_CTRL_CLIPPED, s.d,
+                   s.ctrl_kind};
 }
 template <class MLP>
 __device__ __forceinline__ void ctrl_chunk(const CtrlConst& cc, MLP& mlp, int j0, const float (&ts)[JC], float gamma,
@@ -240,6 +243,32 @@ __device__ __forceinline__ void ctrl_chunk(const CtrlConst& cc, MLP& mlp, int j0
   for (int c = 0; c < JC; ++c) {
     float v = clipb(u[c], cc.bound_model);
     if (cc.score) v = v + (cc.scale_score * clipb(ts[c], cc.bound_score)) * gamma;
+    u[c] = (j0 + c < cc.d) ? v : 0.f;
+  }
+}
+
+// The DIS parametrisations CancelDriftCtrl / LerpCtrl (models/reparam.py:131-147, 189-199): time-only coefficients of
+// the table row, the state chunk `xr` and (LerpCtrl) the prior-score chunk `ps`.
+struct CtrlStep {
+  float gamma, cx, gscale, w;
+};
+__device__ __forceinline__ CtrlStep ctrl_step(const float* __restrict__ row) {
+  return CtrlStep{__ldg(row + LRDS_STEP_GAMMA), __ldg(row + LRDS_STEP_CX), __ldg(row + LRDS_STEP_GSCALE), __ldg(row + LRDS_STEP_LERP)};
+}
+__device__ __forceinline__ float lerpf(float a, float b, float w) {  // torch.lerp's two-sided formula
+  return w < 0.5f ? a + w * (b - a) : b - (b - a) * (1.0f - w);
+}
+template <class MLP>
+__device__ __forceinline__ void ctrl_chunk_dis(const CtrlConst& cc, MLP& mlp, int j0, const float (&ts)[JC],
+                                               const float (&xr)[JC], const float (&ps)[JC], const CtrlStep& st, float (&u)[JC]) {
+  mlp.out_chunk(j0, u);
+#pragma unroll
+  for (int c = 0; c < JC; ++c) {
+    float v = clipb(u[c], cc.bound_model);
+    const float sc = cc.kind == LRDS_CTRL_LERP ? lerpf(ps[c], ts[c], st.w) : ts[c];
+    const float t = (cc.scale_score * clipb(sc, cc.bound_score)) * st.gamma;
+    if (cc.kind == LRDS_CTRL_CANCEL_DRIFT) v = v + st.cx * xr[c];
+    v = v + st.gscale * t;
     u[c] = (j0 + c < cc.d) ? v : 0.f;
   }
 }
@@ -302,7 +331,8 @@ __device__ __forceinline__ void rollout_body(const RolloutArgs& a, float* smem, 
     for (int j = 0; j < d; ++j) a.traj_out[(int64_t)b * d + j] = P.x(j);
 
   const int tkind = TR::kTarget >= 0 ? TR::kTarget : s.target.kind;
-  const bool score_ctrl = TR::kScore >= 0 ? TR::kScore != 0 : s.ctrl_kind == LRDS_CTRL_SCORE;
+  const bool score_ctrl = TR::kScore >= 0 ? TR::kScore != 0 : s.ctrl_kind != LRDS_CTRL_CLIPPED;
+  const bool dis_ctrl = TR::kScore < 0 && s.ctrl_kind >= LRDS_CTRL_CANCEL_DRIFT;  // CancelDriftCtrl / LerpCtrl
   const bool has_ref = TR::kRef >= 0 ? TR::kRef != 0 : s.has_ref_ctrl != 0;
   const int update_form = TR::kUpdate >= 0 ? TR::kUpdate : s.update_form;
   const int ito_form = TR::kIto >= 0 ? TR::kIto : s.ito_form;
@@ -365,7 +395,13 @@ __device__ __forceinline__ void rollout_body(const RolloutArgs& a, float* smem, 
         load_chunk(P.x, j0, xr);
         const float xp = (need_nbr && j0 + JC < dp) ? P.x(j0 + JC) : 0.f;
         if (score_ctrl) target_score_chunk<PIPE, TR::kMix>(s, tkind, tv, P, xr, xm, xp, j0, ts);
-        ctrl_chunk(cc, mlp, j0, ts, gamma, u);
+        if (dis_ctrl) {
+          float ps[JC] = {};
+          if (cc.kind == LRDS_CTRL_LERP) gmm_score_chunk<false, false>(gmm_at(s.ref_0, 0), d, dp, xr, P.rr, j0, ps);
+          ctrl_chunk_dis(cc, mlp, j0, ts, xr, ps, ctrl_step(s.steps + (int64_t)k * LRDS_STEP_STRIDE), u);
+        } else {
+          ctrl_chunk(cc, mlp, j0, ts, gamma, u);
+        }
         if (has_ref) gmm_score_chunk<PIPE, TR::kMix>(rv, d, dp, xr, P.rr, j0, rs);
         noise_chunk(a, k, b, j0, z);
 #pragma unroll

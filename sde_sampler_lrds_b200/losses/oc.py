@@ -131,7 +131,7 @@ class BaseOCLoss:
         if info.score_model is not None:
             vers += tuple((p.data_ptr(), p._version) for p in info.score_model.parameters())
         return (tag, tsc.numpy().tobytes(), str(device), vers, id(info.target), self.precision or pack.default_precision(),
-                extra)
+                info.kind, extra)
 
 
 def _terminal(spec, keep, device, terminal_unnorm_log_prob, info):
@@ -373,7 +373,7 @@ class TimeReversalLoss(BaseOCLoss):
             K = len(pairs)
             spec = pack.new_spec(self.precision)
             keep: list = []
-            pack.fill_ctrl(spec, info, device, keep)
+            pack.fill_ctrl(spec, info, device, keep, prior=prior)
             _terminal(spec, keep, device, terminal_unnorm_log_prob, info)
             spec.K, spec.kind = K, N.ROLLOUT_LINEAR
             spec.update_form = N.UPDATE_EM

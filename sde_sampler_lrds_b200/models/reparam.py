@@ -1,5 +1,7 @@
 """Control parametrisations with the reference's names (sde_sampler/models/reparam.py: ClippedCtrl 18-43 =
-``base_zero_init``, ScoreCtrl 67-117 = ``target_informed_zero_init``).  ``forward(t, x)`` runs lrds_ctrl_forward."""
+``base_zero_init``, ScoreCtrl 67-117 = ``target_informed_zero_init``, CancelDriftCtrl 120-147 =
+``target_informed_langevin_init``, LerpCtrl 150-199 = ``target_informed_lerp_tempering``).  ``forward(t, x)`` runs
+lrds_ctrl_forward."""
 from __future__ import annotations
 
 from typing import Callable
@@ -34,3 +36,33 @@ class ScoreCtrl(ClippedCtrl):
         self.detach_score = detach_score
         self.scale_score = scale_score
         self.clip_score = clip_score
+
+
+class CancelDriftCtrl(ScoreCtrl):
+    """Langevin initialisation (DIS): clip(base) + sde.drift(t, x) / sde.diff(t) + 0.5 sde.diff(t) score."""
+
+    def __init__(self, *args, sde, langevin_init: bool = True, use_rescaling=True, **kwargs):
+        super().__init__(*args, **kwargs)
+        if sde.noise_type not in ["diagonal", "scalar"]:
+            raise ValueError(f"Invalid sde noise type {sde.noise_type}.")
+        if not use_rescaling:
+            raise NotImplementedError("use_rescaling=False is unreachable from the shipped configs (SURVEY.md App. B.4)")
+        self.sde = sde
+        self.langevin_init = langevin_init
+        self.use_rescaling = use_rescaling
+
+
+class LerpCtrl(ScoreCtrl):
+    """clip(base) + sde.diff(t) * scale_score * clip(lerp(prior_score(x), target_score(x), t / T)) * clip(score_model(t)).
+    ``prior_score`` must be the bound ``score`` of the (diagonal Gaussian) prior the rollout starts from."""
+
+    def __init__(self, *args, sde, prior_score: Callable, hard_constrain: bool = False, scale_lerp: float = 1.0, **kwargs):
+        super().__init__(*args, **kwargs)
+        if sde.noise_type not in ["diagonal", "scalar"]:
+            raise ValueError(f"Invalid sde noise type {sde.noise_type}.")
+        if hard_constrain:
+            raise NotImplementedError("hard_constrain=True is not set by any shipped config (conf/model/lerp.yaml)")
+        self.sde = sde
+        self.prior_score = prior_score
+        self.hard_constrain = hard_constrain
+        self.scale_lerp = scale_lerp

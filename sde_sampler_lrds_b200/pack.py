@@ -16,7 +16,7 @@ from . import _native as N
 from .distr.base import Distribution, fill_gmm, gmm_block
 from .distr.gauss import GMM
 from .models.mlp import FourierMLP, TimeEmbed
-from .models.reparam import ClippedCtrl, ScoreCtrl
+from .models.reparam import CancelDriftCtrl, ClippedCtrl, LerpCtrl, ScoreCtrl
 
 _DEFAULT_PRECISION = "f16x3"
 
@@ -46,6 +46,8 @@ class CtrlInfo:
     clip_model: float | None = None
     clip_score: float | None = None
     scale_score: float = 1.0
+    sde: object | None = None              # CancelDriftCtrl / LerpCtrl: the OU SDE of their time-only coefficients
+    prior: Distribution | None = None      # LerpCtrl: the prior whose score is interpolated
 
 
 def resolve_ctrl(ctrl) -> CtrlInfo:
@@ -62,8 +64,18 @@ def resolve_ctrl(ctrl) -> CtrlInfo:
             raise NotImplementedError(f"drift backbone {type(ctrl.base_model).__name__} has no B200 kernel")
         if ctrl.score_model is not None and not (isinstance(ctrl.score_model, TimeEmbed) and ctrl.score_model.dim_out == 1):
             raise NotImplementedError("score_model must be a TimeEmbed with dim_out=1 (conf/model/score.yaml)")
-        return CtrlInfo(N.CTRL_SCORE, ctrl.base_model, ctrl.score_model, target, ctrl.clip_model, ctrl.clip_score,
+        info = CtrlInfo(N.CTRL_SCORE, ctrl.base_model, ctrl.score_model, target, ctrl.clip_model, ctrl.clip_score,
                         float(ctrl.scale_score))
+        if isinstance(ctrl, CancelDriftCtrl):
+            info.kind, info.sde = N.CTRL_CANCEL_DRIFT, ctrl.sde
+        elif isinstance(ctrl, LerpCtrl):
+            prior = getattr(ctrl.prior_score, "__self__", None)
+            if not isinstance(prior, GMM) or prior.loc.shape[0] != 1:
+                raise NotImplementedError("LerpCtrl.prior_score must be the bound .score of a diagonal Gaussian prior")
+            info.kind, info.sde, info.prior = N.CTRL_LERP, ctrl.sde, prior
+        elif type(ctrl) is not ScoreCtrl:
+            raise NotImplementedError(f"control of type {type(ctrl).__name__} has no B200 kernel (no fallback is provided)")
+        return info
     if isinstance(ctrl, ClippedCtrl):
         if not isinstance(ctrl.base_model, FourierMLP):
             raise NotImplementedError(f"drift backbone {type(ctrl.base_model).__name__} has no B200 kernel")
@@ -87,7 +99,7 @@ def resolve_log_prob(fn):
 def time_rows(info: CtrlInfo, taus: torch.Tensor):
     """Host rows (bias1[S][64], gamma[S]) of the time-only parts of the control for times ``taus``."""
     bias1 = info.base.bias_rows(taus)
-    if info.kind == N.CTRL_SCORE and info.score_model is not None:
+    if info.kind != N.CTRL_CLIPPED and info.score_model is not None:
         gamma = info.score_model.rows(taus, "cpu").reshape(-1)
         if info.clip_model is not None:
             gamma = gamma.clip(-info.clip_model, info.clip_model)
@@ -96,7 +108,25 @@ def time_rows(info: CtrlInfo, taus: torch.Tensor):
     return bias1, gamma
 
 
-def fill_ctrl(spec: N.Spec, info: CtrlInfo, device, keep: list):
+def dis_ctrl_rows(info: CtrlInfo, taus: torch.Tensor, table: torch.Tensor):
+    """Time-only coefficients of CancelDriftCtrl / LerpCtrl (models/reparam.py:131-147, 189-199) in the reference's
+    float32 scalar formulas: columns STEP_CX, STEP_LERP, STEP_GSCALE of the per-step table."""
+    if info.kind not in (N.CTRL_CANCEL_DRIFT, N.CTRL_LERP):
+        return
+    sde = info.sde.host()
+    for k, t in enumerate(taus.detach().to("cpu", torch.float32).reshape(-1)):
+        sig = sde.diff(t)
+        if info.kind == N.CTRL_CANCEL_DRIFT:
+            table[k, N.STEP_CX], table[k, N.STEP_GSCALE] = sde.drift_coeff_t(t) / sig, 0.5 * sig
+        else:
+            table[k, N.STEP_LERP], table[k, N.STEP_GSCALE] = t / sde.terminal_t, sig
+
+
+def fill_ctrl(spec: N.Spec, info: CtrlInfo, device, keep: list, prior: Distribution | None = None):
+    """``prior`` = the distribution that fills spec.ref_0 when it is the rollout's prior (DIS); LerpCtrl needs it."""
+    if info.kind == N.CTRL_LERP and prior is not info.prior:
+        raise NotImplementedError("LerpCtrl runs in the DIS rollout from the prior whose score it interpolates "
+                                  "(TimeReversalLoss with initial_log_prob = that prior's log_prob)")
     spec.ctrl_kind = info.kind
     spec.clip_model = float(info.clip_model) if info.clip_model is not None else 0.0
     spec.clip_score = float(info.clip_score) if info.clip_score is not None else 0.0
@@ -127,7 +157,11 @@ def ctrl_forward(module, t: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
     info = resolve_ctrl(module)
     keep: list = []
     spec = new_spec("fp32")
-    fill_ctrl(spec, info, x.device, keep)
+    fill_ctrl(spec, info, x.device, keep, prior=info.prior)
+    if info.kind == N.CTRL_LERP:
+        blk0 = gauss_block_from(info.prior, x.device)
+        fill_gmm(spec.ref_0, blk0)
+        keep.append(blk0)
     t = torch.as_tensor(t)
     if t.numel() != 1:
         if not bool((t.reshape(-1) == t.reshape(-1)[0]).all()):
@@ -137,6 +171,7 @@ def ctrl_forward(module, t: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
     bias1, gamma = time_rows(info, t.reshape(1))
     table[0, N.STEP_BIAS1:N.STEP_BIAS1 + N.CHANNELS] = bias1[0]
     table[0, N.STEP_GAMMA] = gamma[0]
+    dis_ctrl_rows(info, t.reshape(1), table)
     table = table.to(x.device)
     spec.steps = table.data_ptr()
     lead = x.shape[:-1]
@@ -175,6 +210,7 @@ def finish_table(table: torch.Tensor, info: CtrlInfo, taus: torch.Tensor, device
     bias1, gamma = time_rows(info, taus)
     table[:, N.STEP_BIAS1:N.STEP_BIAS1 + N.CHANNELS] = bias1
     table[:, N.STEP_GAMMA] = gamma
+    dis_ctrl_rows(info, taus, table)
     return table.contiguous().to(device)
 
 

@@ -81,6 +81,10 @@ class TrainableDiff(torch.nn.Module):
             self.sde.to(self.device)
         gen = dict(self.cfg["generative_ctrl"])
         extra = {"target_score": self.target.score} if gen.pop("_wants_target_score", False) else {}
+        if gen.pop("_wants_sde", False):  # CancelDriftCtrl / LerpCtrl (the reference passes these to every control)
+            extra["sde"] = self.sde
+        if gen.pop("_wants_prior_score", False):
+            extra["prior_score"] = self.prior.score
         self.generative_ctrl = build(gen, **extra).to(self.device)
         if self.use_ema:
             total = self.cfg["train_steps"] / (self.cfg["train_batch_size"] * self.cfg.get("ema_steps", 10))

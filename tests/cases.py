@@ -52,9 +52,16 @@ def ctrl_state_dict(d: int, kind: str, seed: int, out_gain: float = 1.0, gamma: 
     return sd
 
 
-def ctrl(d, kind, seed, **kw):
-    return {"kind": kind, "sd": ctrl_state_dict(d, kind, seed, **kw), "clip_model": 1e4,
-            "clip_score": 1e4 if kind == "score" else None, "scale_score": 1.0}
+def ctrl(d, kind, seed, sde=None, prior=None, **kw):
+    """kind: 'clipped' (ClippedCtrl), 'score' (ScoreCtrl), and the two DIS parametrisations 'cancel' (CancelDriftCtrl,
+    needs ``sde``) and 'lerp' (LerpCtrl, needs ``sde`` and the IsotropicGauss ``prior`` {'loc', 'scale'})."""
+    out = {"kind": kind, "sd": ctrl_state_dict(d, "clipped" if kind == "clipped" else "score", seed, **kw),
+           "clip_model": 1e4, "clip_score": None if kind == "clipped" else 1e4, "scale_score": 1.0}
+    if kind in ("cancel", "lerp"):
+        out["sde"] = dict(sde)
+    if kind == "lerp":
+        out["prior"] = dict(prior)
+    return out
 
 
 # ---- targets (parameters restated from the reference constructors) --------------------------
@@ -227,11 +234,13 @@ def case_dds_many_modes(compute_ito_int=True):
         "B": 120, "seed": 118, "prior": ("iso", 0.0, 2.0), "compute_ito_int": compute_ito_int}
 
 
-def case_dis(target="many_modes", compute_ito_int=True, scale=1.0):
+def case_dis(target="many_modes", compute_ito_int=True, scale=1.0, ctrl_kind="score"):
     """DIS (dis_orig: solver Bridge + TimeReversalLoss with inference_ctrl=None, conf/solver/dis.yaml): VP 0.1..10,
-    Euler-Maruyama, control at the loop time, prior IsotropicGauss(scale=sde.scale_diff_coeff), ScoreCtrl drift
-    (model_type target_informed_zero_init)."""
+    Euler-Maruyama, control at the loop time, prior IsotropicGauss(scale=sde.scale_diff_coeff); drift models ScoreCtrl
+    (target_informed_zero_init), CancelDriftCtrl (target_informed_langevin_init) or LerpCtrl (the solver's default,
+    target_informed_lerp_tempering)."""
     sde = dict(VP10, scale=scale)
+    prior = {"loc": 0.0, "scale": scale}
     if target == "many_modes":
         d, K, B, tgt, c = 10, 90, 120, many_modes(7, 10), dict(seed=31, out_gain=0.5, gamma=0.02)
     elif target == "phi4":
@@ -239,8 +248,8 @@ def case_dis(target="many_modes", compute_ito_int=True, scale=1.0):
     else:
         d, K, B, tgt, c = 61, 40, 96, logreg_synthetic(166, 60), dict(seed=33, out_gain=0.5, gamma=0.01)
     return {
-        "problem": {"method": "dis", "sde": sde, "ts": uniform_ts(1.0, K), "target": tgt, "ctrl": ctrl(d, "score", **c),
-                    "ref": {"kind": "iso", "loc": 0.0, "scale": scale}},
+        "problem": {"method": "dis", "sde": sde, "ts": uniform_ts(1.0, K), "target": tgt,
+                    "ctrl": ctrl(d, ctrl_kind, sde=sde, prior=prior, **c), "ref": {"kind": "iso", **prior}},
         "B": B, "seed": 120 + len(target), "prior": ("iso", 0.0, scale), "compute_ito_int": compute_ito_int}
 
 
@@ -375,6 +384,10 @@ CASES = {
     "dis_many_modes_noito": lambda: case_dis("many_modes", False, scale=1.5),
     "dis_phi4": lambda: case_dis("phi4"),
     "dis_logreg": lambda: case_dis("logreg"),
+    "dis_many_modes_lerp": lambda: case_dis("many_modes", ctrl_kind="lerp", scale=1.25),
+    "dis_many_modes_langevin": lambda: case_dis("many_modes", ctrl_kind="cancel"),
+    "dis_phi4_langevin": lambda: case_dis("phi4", False, ctrl_kind="cancel"),
+    "dis_logreg_lerp": lambda: case_dis("logreg", ctrl_kind="lerp"),
     "eubo_em_two_modes": lambda: _eubo(case_em_two_modes("score"), 201),
     "eubo_ei_many_modes": lambda: _eubo(case_ei_many_modes(K=100, B=100), 202),
     "eubo_cmcd_gmm": lambda: _eubo(case_cmcd_gmm(), 203),

@@ -10,7 +10,7 @@ from sde_sampler_lrds_b200.distr.phi_four import PhiFour
 from sde_sampler_lrds_b200.eq.sdes import VP, ControlledLangevinSDE, MarginalReference, PinnedBM, ScaledBM
 from sde_sampler_lrds_b200.losses import oc
 from sde_sampler_lrds_b200.models.mlp import FourierMLP, TimeEmbed
-from sde_sampler_lrds_b200.models.reparam import ClippedCtrl, ScoreCtrl
+from sde_sampler_lrds_b200.models.reparam import CancelDriftCtrl, ClippedCtrl, LerpCtrl, ScoreCtrl
 
 
 def build_target(tgt, device):
@@ -27,13 +27,19 @@ def build_target(tgt, device):
     return t.to(device)
 
 
-def build_ctrl(c, d, target, device):
+def build_ctrl(c, d, target, device, prior=None):
     num_hidden = sum(1 for k in c["sd"] if k.startswith("base_model.hidden_layer.") and k.endswith(".weight"))
     base = FourierMLP(dim=d, activation=torch.nn.GELU(), num_layers=num_hidden + 2, channels=64)
-    if c["kind"] == "score":
-        m = ScoreCtrl(base_model=base, score_model=TimeEmbed(dim_out=1, activation=torch.nn.GELU(), num_layers=4, channels=64),
-                      target_score=target.score, detach_score=False, clip_score=c["clip_score"],
-                      clip_model=c["clip_model"], scale_score=c["scale_score"])
+    if c["kind"] in ("score", "cancel", "lerp"):
+        kw = dict(base_model=base, score_model=TimeEmbed(dim_out=1, activation=torch.nn.GELU(), num_layers=4, channels=64),
+                  target_score=target.score, detach_score=False, clip_score=c["clip_score"],
+                  clip_model=c["clip_model"], scale_score=c["scale_score"])
+        if c["kind"] == "score":
+            m = ScoreCtrl(**kw)
+        elif c["kind"] == "cancel":
+            m = CancelDriftCtrl(sde=build_sde(c["sde"], device), langevin_init=True, **kw)
+        else:
+            m = LerpCtrl(sde=build_sde(c["sde"], device), prior_score=prior.score, hard_constraint=False, **kw)
     else:
         m = ClippedCtrl(base_model=base, clip_model=c["clip_model"])
     m.load_state_dict({k: v.clone() for k, v in c["sd"].items()}, strict=True)
@@ -59,7 +65,9 @@ class Built:
         self.case, self.device = case, device
         self.target = build_target(p["target"], device)
         d = self.target.dim
-        self.ctrl = build_ctrl(p["ctrl"], d, self.target, device)
+        if p["method"] == "dis":  # LerpCtrl interpolates the score of the very prior the rollout starts from
+            self.prior = IsotropicGauss(dim=d, loc=p["ref"]["loc"], scale=p["ref"]["scale"]).to(device)
+        self.ctrl = build_ctrl(p["ctrl"], d, self.target, device, prior=getattr(self, "prior", None))
         self.ts = p["ts"].clone().to(device)
         method = p["method"]
         kw = dict(generative_ctrl=self.ctrl, generative_ctrl_ema=self.ctrl, method="lv", max_rnd=1e8, precision=precision)
@@ -89,7 +97,6 @@ class Built:
             self.kwargs = {"compute_ito_int": case.get("compute_ito_int", True)}
         elif method == "dis":
             self.sde = build_sde(p["sde"], device)
-            self.prior = IsotropicGauss(dim=d, loc=p["ref"]["loc"], scale=p["ref"]["scale"]).to(device)
             self.loss = oc.TimeReversalLoss(sde=self.sde, inference_ctrl=None, **kw)
             self.args = (self.target.unnorm_log_prob,)
             self.kwargs = {"initial_log_prob": self.prior.log_prob, "train": False,

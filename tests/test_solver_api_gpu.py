@@ -39,6 +39,8 @@ def _randomise_last_layers(model, gain=0.5):
     ("cmcd", dict(ref_type="gaussian", integrator_type="em", time_type="uniform")),
     ("dis_orig", dict(ref_type="default", integrator_type="em", time_type="uniform")),
     ("dis_orig", dict(ref_type="default", integrator_type="em", time_type="uniform", force_vp20=True)),
+    ("dis_orig", dict(ref_type="default", integrator_type="em", time_type="uniform", model_type="target_informed_lerp_tempering")),
+    ("dis_orig", dict(ref_type="default", integrator_type="em", time_type="uniform", model_type="target_informed_langevin_init")),
 ])
 def test_make_model_evaluate(solver_type, kw, device):
     from sde_sampler_lrds_b200 import benchmark_utils as BU
@@ -78,6 +80,26 @@ def test_make_model_evaluate(solver_type, kw, device):
     assert abs(got.metrics["eval/elbo"] - want["eval/elbo"]) < 1e-4 * max(1, abs(want["eval/elbo"]))
     assert abs(got.log_norm_const_preds["log_norm_const_is"] - want["log_norm_const_is"]) < 1e-3
     assert abs(got.metrics["eval/lv_loss"] - want["eval/lv_loss"]) < 1e-3 * max(1, want["eval/lv_loss"])
+
+
+@pytest.mark.parametrize("name", ["dis_many_modes_lerp", "dis_many_modes_langevin", "dis_logreg_lerp", "dis_many_modes_ito"])
+def test_drift_model_forward_matches_the_oracle(name, device):
+    """``generative_ctrl(t, x)`` (lrds_ctrl_forward) of ScoreCtrl / CancelDriftCtrl / LerpCtrl against the oracle's
+    restatement of models/reparam.py, at three times."""
+    from tests.cases import CASES, initial_state
+    from tests.product_builders import Built
+    case = CASES[name]()
+    p = case["problem"]
+    built = Built(case, device, "fp32")
+    _, target_score = O.make_target(p["target"])
+    want_fn = O.make_ctrl(p["ctrl"], target_score)
+    x = initial_state(case)
+    for t in (0.05, 0.5, 0.93):
+        t = torch.tensor(t)
+        got = built.ctrl(t.to(device), x.to(device)).cpu()
+        want = want_fn(t, x)
+        err = ((got - want).abs() / want.abs().clamp(min=1.0)).max().item()
+        assert err < 1e-4, (name, float(t), err)
 
 
 @pytest.mark.parametrize("precision", ["tf32x3", "f16x3"])
