@@ -28,9 +28,11 @@ constexpr int MIX_MAX_WARPS = 16;  // 3.5 tiles: one wave for 65536 particles on
 //   REF  2: the time-marginal reference is a mixture (contraction on tcgen05)   1: a single Gaussian (one FMA per dim)
 //        0: no reference control (PIS / DDS over a mixture target)
 //   EM   Euler-Maruyama update and Ito term (losses/oc.py:277-284) instead of the exponential-integrator axpy
-template <bool EUBO_, int TGT_, int REF_, bool EM_>
+//   DIS  the control is one of the DIS parametrisations over a mixture target (TGT 1): CancelDriftCtrl or LerpCtrl
+//        (models/reparam.py:131-147, 189-199; which one is a warp-uniform run-time switch)
+template <bool EUBO_, int TGT_, int REF_, bool EM_, bool DIS_ = false>
 struct MixCfg {
-  static constexpr bool kEubo = EUBO_, kEm = EM_;
+  static constexpr bool kEubo = EUBO_, kEm = EM_, kDis = DIS_;
   static constexpr int kTgt = TGT_, kRef = REF_;
 };
 using MixBench = MixCfg<false, 1, 2, false>;  // the benchmark configuration
@@ -40,6 +42,8 @@ __host__ __device__ inline int mix_tc_config(const lrds_spec& s) {
   if (s.precision != LRDS_PRECISION_F16X3 || s.mlp.d_pad > 128) return -1;
   const bool tmix = s.ctrl_kind == LRDS_CTRL_SCORE && s.target.kind == LRDS_DISTR_GMM && s.target.gmm.M > 1 &&
                     s.target.gmm.M <= MIX_MAX_M && s.target.gmm.mix_tc != nullptr;
+  const bool tdis = s.ctrl_kind >= LRDS_CTRL_CANCEL_DRIFT && s.target.kind == LRDS_DISTR_GMM && s.target.gmm.M > 1 &&
+                    s.target.gmm.M <= MIX_MAX_M && s.target.gmm.mix_tc != nullptr;
   const bool tphi = s.ctrl_kind == LRDS_CTRL_SCORE && s.target.kind == LRDS_DISTR_PHI4;
   const bool tnone = s.ctrl_kind == LRDS_CTRL_CLIPPED &&
                      (s.target.kind != LRDS_DISTR_GMM || s.target.gmm.M <= MIX_MAX_M) && s.target.kind != LRDS_DISTR_LOGREG;
@@ -47,7 +51,8 @@ __host__ __device__ inline int mix_tc_config(const lrds_spec& s) {
   const bool rmix = s.has_ref_ctrl && s.ref_t.M > 1 && s.ref_t.M <= MIX_MAX_M && s.ref_t.mix_tc != nullptr;
   const bool rgauss = s.has_ref_ctrl && s.ref_t.M == 1;
   const bool axpy = s.update_form == LRDS_UPDATE_AXPY && (s.ito_form == LRDS_ITO_SCALED || (rnone && s.ito_form != LRDS_ITO_EM));
-  const bool em = s.update_form == LRDS_UPDATE_EM && s.ito_form == LRDS_ITO_EM;
+  // Euler-Maruyama; without a reference control also with the Ito term switched off (DIS with compute_weights=False)
+  const bool em = s.update_form == LRDS_UPDATE_EM && (s.ito_form == LRDS_ITO_EM || (rnone && s.ito_form == LRDS_ITO_NONE));
   if (s.ref_0.M > MIX_MAX_M) return -1;
   if (s.target.kind == LRDS_DISTR_GMM && s.target.gmm.M > 1 && s.target.gmm.mix_tc == nullptr) return -1;  // staged with the target
   if (s.kind == LRDS_ROLLOUT_EUBO_LINEAR) return (tmix && rmix && axpy) ? 1 : -1;
@@ -61,6 +66,7 @@ __host__ __device__ inline int mix_tc_config(const lrds_spec& s) {
   if (tmix && rnone && em) return 7;    // PIS over a mixture target
   if (tmix && rnone && axpy) return 8;  // DDS over a mixture target (any Ito form but EM)
   if (tphi && rgauss && axpy) return 9;
+  if (tdis && rnone && em) return 10;   // DIS with CancelDriftCtrl / LerpCtrl over a mixture target
   return -1;
 }
 __host__ __device__ inline bool mix_tc_applicable(const lrds_spec& s) { return mix_tc_config(s) >= 0; }
@@ -229,7 +235,7 @@ struct MixTc : TcMlp<PREC> {
 // increments are generated twice (for the update and for the cost) instead of being kept per particle.
 template <int PREC, class CFG>
 __device__ __forceinline__ void rollout_body_mix(const RolloutArgs& a, float* smem, uint8_t* stage, MixTc<PREC>& mlp) {
-  constexpr bool EUBO = CFG::kEubo, TMIX = CFG::kTgt == 1, TPHI = CFG::kTgt == 2, RMIX = CFG::kRef == 2, RGAUSS = CFG::kRef == 1, EM = CFG::kEm;
+  constexpr bool EUBO = CFG::kEubo, TMIX = CFG::kTgt == 1, TPHI = CFG::kTgt == 2, RMIX = CFG::kRef == 2, RGAUSS = CFG::kRef == 1, EM = CFG::kEm, DIS = CFG::kDis;
   const lrds_spec& s = a.s;
   const int NT = blockDim.x;
   const int tid = threadIdx.x;
@@ -351,10 +357,17 @@ __device__ __forceinline__ void rollout_body_mix(const RolloutArgs& a, float* sm
     const float dt = EM ? rowp.ld1(LRDS_STEP_DT) : 0.f, sqdt = EM ? rowp.ld1(LRDS_STEP_SQRT_DT) : 0.f;
     const u64 A2 = f2::pk(EM ? 1.0f - A * dt : A), B2 = f2::pk(EM ? Bc * dt : Bc), C2 = f2::pk(EM ? Bc * sqdt : Cc);
     const u64 usr2 = f2::pk(usr), R2 = f2::pk((EM ? Cc * dt : Bc) * usr);
-    const u64 gs2 = f2::pk((cc.scale_score * gamma) * ust);
-    const float bts = cc.bound_score / ust;
+    // DIS parametrisations: u = (clip(net) + CX x) + GSCALE ((scale clip(sc)) gamma), sc = the target score (CancelDriftCtrl)
+    // or lerp(prior score, target score, LERP) evaluated in true units (LerpCtrl)
+    const bool lerp = DIS && s.ctrl_kind == LRDS_CTRL_LERP;
+    const float gsc = DIS ? rowp.ld1(LRDS_STEP_GSCALE) : 1.0f, wl = DIS ? rowp.ld1(LRDS_STEP_LERP) : 0.f;
+    const u64 cx2 = f2::pk(DIS ? rowp.ld1(LRDS_STEP_CX) : 0.f), ust2 = f2::pk(ust);
+    const u64 wl2 = f2::pk(wl < 0.5f ? wl : -(1.0f - wl));
+    const GmmView pg = gmm_at(s.ref_0, 0);  // LerpCtrl: the prior (a diagonal Gaussian)
+    const u64 gs2 = f2::pk(((cc.scale_score * gamma) * gsc) * (lerp ? 1.0f : ust));
+    const float bts = lerp ? cc.bound_score : cc.bound_score / ust;
     // weight of sum(u z) in the log-weight (oc.py:284 / 499); without a reference control also the DDS forms (oc.py:1380-1383)
-    const float wz = EM ? sqdt
+    const float wz = EM ? (s.ito_form == LRDS_ITO_NONE ? 0.f : sqdt)
                      : (RMIX || RGAUSS || s.ito_form == LRDS_ITO_SCALED) ? wito
                      : s.ito_form == LRDS_ITO_DDS ? rowp.ld1(LRDS_STEP_SIGU) * wito
                                                   : 0.f;
@@ -386,6 +399,13 @@ __device__ __forceinline__ void rollout_body_mix(const RolloutArgs& a, float* sm
         GM[0] = g0.x; GM[1] = g0.y; GM[2] = g1.x; GM[3] = g1.y;
         GI[0] = i0.x; GI[1] = i0.y; GI[2] = i1.x; GI[3] = i1.y;
       }
+      if constexpr (DIS) {
+        if (lerp) {
+          const ulonglong2 g0 = pg.mu.ld2(2 * c), g1 = pg.mu.ld2(2 * c + 1), i0 = pg.ivar.ld2(2 * c), i1 = pg.ivar.ld2(2 * c + 1);
+          GM[0] = g0.x; GM[1] = g0.y; GM[2] = g1.x; GM[3] = g1.y;
+          GI[0] = i0.x; GI[1] = i0.y; GI[2] = i1.x; GI[3] = i1.y;
+        }
+      }
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         const u64 ta = f2::pack(__uint_as_float(m[2 * q]), __uint_as_float(m[2 * q + 1]));
@@ -394,6 +414,14 @@ __device__ __forceinline__ void rollout_body_mix(const RolloutArgs& a, float* sm
         const u64 rb = f2::pack(__uint_as_float(m[24 + 2 * q]), __uint_as_float(m[25 + 2 * q]));
         float t0 = 0.f, t1 = 0.f, u0, u1;
         if constexpr (TMIX) f2::unpack(f2::fma(X[q], ta, tb), t0, t1);  // raw target score (image units)
+        if constexpr (DIS) {
+          if (lerp) {  // torch.lerp(prior_score, target_score, w): a + w (b - a) for w < 1/2, else b - (b - a)(1 - w)
+            const u64 tt = f2::mul(f2::pack(t0, t1), ust2);
+            const u64 pr = f2::mul(f2::fma(X[q], f2::pk(-1.0f), GM[q]), GI[q]);
+            const u64 df = f2::fma(pr, f2::pk(-1.0f), tt);
+            f2::unpack(f2::fma(df, wl2, wl < 0.5f ? pr : tt), t0, t1);
+          }
+        }
         if constexpr (TPHI) {
           const u64 nb = f2::pack(xs[2 * q] + xs[2 * q + 2], xs[2 * q + 1] + xs[2 * q + 3]);
           const u64 t = f2::fma(X[q], f2::fma(f2::mul(X[q], X[q]), p3, p1), f2::fma(pn, f2::fma(X[q], m2, nb), p0));
@@ -406,7 +434,8 @@ __device__ __forceinline__ void rollout_body_mix(const RolloutArgs& a, float* sm
         f2::unpack(U[q], u0, u1);
         const u64 uc = f2::pack(clipb(u0, cc.bound_model), clipb(u1, cc.bound_model));
         u64 v = uc;  // control u
-        if constexpr (TMIX || TPHI) v = f2::fma(f2::pack(clipb(t0, bts), clipb(t1, bts)), gs2, uc);
+        if constexpr (DIS) v = f2::fma(X[q], cx2, v);
+        if constexpr (TMIX || TPHI) v = f2::fma(f2::pack(clipb(t0, bts), clipb(t1, bts)), gs2, v);
         // reference score in the units of R2: mixture = accumulator (image units), Gaussian = -(x - mu) / var
         const u64 rraw = RMIX ? f2::fma(X[q], ra, rb) : RGAUSS ? f2::mul(f2::fma(X[q], f2::pk(-1.0f), GM[q]), GI[q]) : 0ull;
         const u64 z2 = f2::pack(z[2 * q], z[2 * q + 1]);

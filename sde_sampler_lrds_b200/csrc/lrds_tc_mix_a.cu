@@ -34,7 +34,7 @@ int launch_mix_f16x3(const RolloutArgs& a, const TcPlan& p, cudaStream_t st, cha
     case 2: return launch_mix_cfg<MixCfg<false, 1, 1, false>>(a, p, st, err, n);
     case 3: return launch_mix_cfg<MixCfg<false, 1, 1, true>>(a, p, st, err, n);
     case 4: case 5: case 6: return launch_mix_b(cfg, a, p, st, err, n);
-    case 7: case 8: case 9: return launch_mix_c(cfg, a, p, st, err, n);
+    case 7: case 8: case 9: case 10: return launch_mix_c(cfg, a, p, st, err, n);
   }
   snprintf(err, n, "mixture tensor-core rollout: configuration not built");
   return LRDS_ERR_UNSUPPORTED;

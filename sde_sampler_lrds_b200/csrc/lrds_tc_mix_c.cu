@@ -27,6 +27,7 @@ int launch_mix_c(int cfg, const RolloutArgs& a, const TcPlan& p, cudaStream_t st
   switch (cfg) {
     case 7: return launch_mix_cfg<MixCfg<false, 1, 0, true>>(a, p, st, err, n);
     case 8: return launch_mix_cfg<MixCfg<false, 1, 0, false>>(a, p, st, err, n);
+    case 10: return launch_mix_cfg<MixCfg<false, 1, 0, true, true>>(a, p, st, err, n);
     default: return launch_mix_cfg<MixCfg<false, 2, 1, false>>(a, p, st, err, n);
   }
 }

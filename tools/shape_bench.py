@@ -44,6 +44,22 @@ def pis_many_modes():
     return case
 
 
+def dis(target, ctrl_kind, B, K=200):
+    case = T.case_dis(target, True, ctrl_kind=ctrl_kind)
+    p = case["problem"]
+    if target == "many_modes":
+        d = 50
+        p["target"] = T.many_modes(16, d)
+        p["ctrl"] = T.ctrl(d, ctrl_kind, seed=31, out_gain=0.5, gamma=0.02, sde=p["sde"], prior={"loc": 0.0, "scale": 1.0})
+    elif target == "phi4":
+        d = 100
+        p["target"] = T.phi4(d)
+        p["ctrl"] = T.ctrl(d, ctrl_kind, seed=32, out_gain=0.3, gamma=0.004, sde=p["sde"], prior={"loc": 0.0, "scale": 1.0})
+    p["ts"] = T.uniform_ts(1.0, K)
+    case["B"] = B
+    return case
+
+
 SHAPES = {
     "cfg1 two_modes d=2 EM K=100 B=2048": lambda: dict(T.case_em_two_modes("score"), B=2048),
     "cfg2 many_modes d=50 M=16 EI K=200 B=65536": lambda: T.case_ei_many_modes(K=200, B=65536),
@@ -54,6 +70,12 @@ SHAPES = {
     "logreg sonar d=61 PIS K=100 B=262144": lambda: T.case_pis_logreg(166, 60, K=100, B=262144),
     "many_modes d=50 M=16 CMCD K=200 B=65536": lambda: cmcd_many_modes(),
     "many_modes d=50 M=16 PIS K=200 B=65536": lambda: pis_many_modes(),
+    # DIS (Bridge + TimeReversalLoss) with its three drift models
+    "many_modes d=50 M=16 DIS ScoreCtrl K=200 B=65536": lambda: dis("many_modes", "score", 65536),
+    "many_modes d=50 M=16 DIS LerpCtrl K=200 B=65536": lambda: dis("many_modes", "lerp", 65536),
+    "many_modes d=50 M=16 DIS CancelDriftCtrl K=200 B=65536": lambda: dis("many_modes", "cancel", 65536),
+    "phi4 d=100 DIS ScoreCtrl K=256 B=131072": lambda: dis("phi4", "score", 131072, K=256),
+    "logreg sonar d=61 DIS ScoreCtrl K=100 B=262144": lambda: dis("logreg", "score", 262144, K=100),
     # compute_eubo (the noising rollout behind evaluate_eubo) of the same shapes
     "eubo cfg2 many_modes d=50 M=16 EI K=200 B=65536": lambda: dict(T.case_ei_many_modes(K=200, B=65536), eubo=True),
     "eubo cfg4 logreg sonar d=61 CMCD K=100 B=262144": lambda: dict(T.case_cmcd_logreg(166, 60, K=100, B=262144), eubo=True),
