@@ -48,6 +48,20 @@ def test_mixture_kernel_shapes(M, d, B, K, device):
     _check(dict(case, eubo=True, seed=900 + M), device)
 
 
+@pytest.mark.parametrize("ctrl_kind", ["score", "cancel", "lerp"])
+@pytest.mark.parametrize("M,d,B,K,ito", [(2, 3, 1, 1, True), (5, 17, 33, 4, False), (16, 50, 130, 3, True), (9, 64, 200, 2, True)])
+def test_dis_mixture_kernel_shapes(ctrl_kind, M, d, B, K, ito, device):
+    """DIS over a mixture target on the mixture kernel (configurations 7 and 10): the initial-cost pre-pass, the three
+    drift models, with and without the Ito term."""
+    case = T.case_dis("many_modes", ito, scale=1.25, ctrl_kind=ctrl_kind)
+    p = case["problem"]
+    p["target"] = T.many_modes(M, d)
+    p["ctrl"] = T.ctrl(d, ctrl_kind, seed=51, out_gain=0.5, gamma=0.02, sde=p["sde"], prior={"loc": 0.0, "scale": 1.25})
+    p["ts"] = T.uniform_ts(1.0, 100)[:K + 1].clone()
+    case["B"] = B
+    _check(case, device)
+
+
 def test_lattice_target_with_mixture_reference_at_d100(device):
     """RDS with a mixture reference over the d = 100 PhiFour lattice (experiments/sample_phi_four_gmm_mcmc.py): the
     mixture kernel with the wide (224-column) tile layout."""
