@@ -124,8 +124,10 @@ def build_reference_sde(s):
     return ScaledBM(diff_coeff=s["diff"], terminal_t=s["T"])
 
 
-def run_reference(case):
-    """Returns dict(x_T, rnd[, xs_last]) from the reference for the case."""
+def run_reference(case, grads=False):
+    """Returns dict(x_T, rnd[, xs_last]) from the reference for the case; with ``grads`` the training objective
+    ``loss(ts, x, ...)`` (method='lv': losses/oc.py:364-394, 1240-1272, 1399-1431) and its autograd gradient with
+    respect to every parameter of the control."""
     from sde_sampler.distr.gauss import Gauss, IsotropicGauss
     from sde_sampler.eq.sdes import ControlledLangevinSDE
     from sde_sampler.losses import oc
@@ -145,7 +147,13 @@ def run_reference(case):
         return out if clip_t is None else out.clip(-clip_t, clip_t)
 
     kw = dict(generative_ctrl=ctrl, generative_ctrl_ema=ctrl, method="lv", max_rnd=1e8)
-    with torch.no_grad(), ReplayNoise(noise) as rp:
+    def train(loss, *args, **kwargs):
+        val, _ = loss(ts, x0, target_logp, *args, **kwargs)
+        val.backward()
+        return {"loss": val.detach(), "grads": {n: (q.grad.clone() if q.grad is not None else torch.zeros_like(q))
+                                                for n, q in ctrl.named_parameters()}}
+
+    with (torch.enable_grad() if grads else torch.no_grad()), ReplayNoise(noise) as rp:
         if method in ("em", "ei", "ddpm"):
             sde = build_reference_sde(p["sde"])
             ref = p["ref"]
@@ -163,7 +171,9 @@ def run_reference(case):
                 ref_distr = sde.marginal_distr(t=sde.terminal_t, x_init=ref["loc"].clone())
             cls = {"em": oc.EMReferenceSDELoss, "ei": oc.EIReferenceSDELoss, "ddpm": oc.DDPMLikeReferenceSDELoss}[method]
             loss = cls(sde=sde, reference_ctrl=ref_ctrl, **kw)
-            if case.get("eubo"):
+            if grads:
+                out = train(loss, ref_distr.log_prob)
+            elif case.get("eubo"):
                 rnd = loss.compute_eubo(ts, x0.clone(), target_logp, ref_distr.log_prob)
                 out = {"rnd": rnd}
             else:
@@ -172,16 +182,22 @@ def run_reference(case):
         elif method == "dds":
             prior = IsotropicGauss(dim=d, loc=p["ref"]["loc"], scale=p["ref"]["scale"])
             loss = oc.ExponentialIntegratorSDELoss(alpha=p["alpha"], sigma=p["sigma"], sde=None, **kw)
-            x, rnd, xs = loss.simulate(ts, x0, target_logp, prior.log_prob,
-                                       compute_ito_int=case.get("compute_ito_int", True), return_traj=True)
-            out = {"x_T": x, "rnd": rnd, "xs_mid": xs[len(xs) // 2]}
+            if grads:
+                out = train(loss, prior.log_prob)
+            else:
+                x, rnd, xs = loss.simulate(ts, x0, target_logp, prior.log_prob,
+                                           compute_ito_int=case.get("compute_ito_int", True), return_traj=True)
+                out = {"x_T": x, "rnd": rnd, "xs_mid": xs[len(xs) // 2]}
         elif method == "dis":  # solver/oc.py:185-262 (Bridge, inference_ctrl=None), eval = TimeReversalLoss.eval, oc.py:1274-1307
             sde = build_reference_sde(p["sde"])
             prior = IsotropicGauss(dim=d, loc=p["ref"]["loc"], scale=p["ref"]["scale"])
             loss = oc.TimeReversalLoss(sde=sde, inference_ctrl=None, **kw)
-            x, rnd, xs = loss.simulate(ts, x0, target_logp, initial_log_prob=prior.log_prob, train=False,
-                                       compute_ito_int=case.get("compute_ito_int", True), return_traj=True)
-            out = {"x_T": x, "rnd": rnd, "xs_mid": xs[len(xs) // 2]}
+            if grads:
+                out = train(loss, prior.log_prob)
+            else:
+                x, rnd, xs = loss.simulate(ts, x0, target_logp, initial_log_prob=prior.log_prob, train=False,
+                                           compute_ito_int=case.get("compute_ito_int", True), return_traj=True)
+                out = {"x_T": x, "rnd": rnd, "xs_mid": xs[len(xs) // 2]}
         elif method == "cmcd":
             pr = p["prior"]
             if pr.get("isotropic"):
@@ -202,6 +218,8 @@ def run_reference(case):
         else:
             raise ValueError(method)
         assert rp.i == len(noise), (rp.i, len(noise))
+    if grads:
+        return out
     rnd = out["rnd"]
     if case.get("eubo"):
         from sde_sampler.additions.hacking import evaluate_eubo  # noqa: F401  (formulas restated below)
@@ -223,8 +241,18 @@ def run_reference(case):
 def main(argv):
     from tests.cases import CASES
     import_reference()
-    names = argv or list(CASES)
     os.makedirs(os.path.join(REPO, "tests", "golden"), exist_ok=True)
+    if argv and argv[0] == "--grads":  # python -m oracle.make_golden --grads [case ...]
+        from tests.cases import GRAD_CASES
+        for name in argv[1:] or GRAD_CASES:
+            out = run_reference(CASES[name](), grads=True)
+            out["torch_version"] = str(torch.__version__)
+            path = os.path.join(REPO, "tests", "golden", "grad_" + name + ".pt")
+            torch.save(out, path)
+            gmax = max(float(g.abs().max()) for g in out["grads"].values())
+            print(f"grad_{name:24s} loss {float(out['loss']):.6g} max |grad| {gmax:.4g} | {os.path.getsize(path)} B")
+        return
+    names = argv or list(CASES)
     for name in names:
         case = CASES[name]()
         out = run_reference(case)

@@ -417,24 +417,34 @@ def make_reference(ref: dict | None, sde):
 # --------------------------------------------------------------------------------------
 
 
+def _running_cost(g, lv):
+    """(generative_ctrl, sde_ctrl, cost density): with ``lv`` the training form of the losses with change_sde_ctrl=True
+    (BaseOCLoss.generative_and_sde_ctrl, losses/oc.py:83-103, no control noise / dropout: the SDE follows the detached
+    control and the cost is g (sde_ctrl - g / 2), e.g. oc.py:272-273, 489-490); else 0.5 g^2 (oc.py:275, 492)."""
+    if lv:
+        u = g.detach()
+        return u, (g * (u - 0.5 * g)).sum(dim=-1, keepdim=True)
+    return g, 0.5 * (g ** 2).sum(dim=-1, keepdim=True)
+
+
 def simulate_em(ts, x, noise, ctrl, sde, reference_ctrl, terminal_unnorm_log_prob, reference_log_prob,
-                return_traj=False):
-    """EMReferenceSDELoss.simulate, sde_sampler/losses/oc.py:218-296 (change_sde_ctrl=False,
-    use_rescaling=True)."""
+                return_traj=False, lv=False):
+    """EMReferenceSDELoss.simulate, sde_sampler/losses/oc.py:218-296 (use_rescaling=True; ``lv`` = change_sde_ctrl)."""
     rnd = 0.0
     T = ts[-1]
     xs = [x] if return_traj else None
     for k, (s, t) in enumerate(zip(ts[:-1], ts[1:])):
-        u = ctrl(T - s, x)
+        g = ctrl(T - s, x)
+        u, cost = _running_cost(g, lv)
         sde_diff = sde.diff(T - s)
         dt = t - s
-        rnd = rnd + 0.5 * (u ** 2).sum(dim=-1, keepdim=True) * dt
+        rnd = rnd + cost * dt
         db = noise[k] * dt.sqrt()
         drift_ = -(sde.drift_coeff(T - s) * x)
         if reference_ctrl is not None:
             drift_ = drift_ + torch.square(sde_diff) * reference_ctrl(T - s, x)
         x = x + (drift_ + sde_diff * u) * dt + sde_diff * db
-        rnd = rnd + (u * db).sum(dim=-1, keepdim=True)
+        rnd = rnd + (g * db).sum(dim=-1, keepdim=True)
         if return_traj:
             xs.append(x)
     rnd = rnd + reference_log_prob(x).view((-1, 1)) - terminal_unnorm_log_prob(x)
@@ -442,7 +452,7 @@ def simulate_em(ts, x, noise, ctrl, sde, reference_ctrl, terminal_unnorm_log_pro
 
 
 def simulate_ei(ts, x, noise, ctrl, sde, reference_ctrl, terminal_unnorm_log_prob, reference_log_prob,
-                return_traj=False, ddpm=False):
+                return_traj=False, ddpm=False, lv=False):
     """EIReferenceSDELoss.simulate, losses/oc.py:444-510; with ddpm=True
     DDPMLikeReferenceSDELoss.simulate, losses/oc.py:584-651."""
     rnd = 0.0
@@ -451,11 +461,12 @@ def simulate_ei(ts, x, noise, ctrl, sde, reference_ctrl, terminal_unnorm_log_pro
     omega = sde.omega_ddpm if ddpm else sde.omega
     step = sde.ddpm_step if ddpm else sde.ei_step
     for k, (s, t) in enumerate(zip(ts[:-1], ts[1:])):
-        u = ctrl(T - s, x)
-        rnd = rnd + 0.5 * omega(s, t) * (u ** 2).sum(dim=-1, keepdim=True)
+        g = ctrl(T - s, x)
+        u, cost = _running_cost(g, lv)
+        rnd = rnd + (omega(s, t) * cost if lv else 0.5 * omega(s, t) * (g ** 2).sum(dim=-1, keepdim=True))
         z = noise[k]
         x = step(x, s, t, reference_ctrl(T - s, x) + u, z)
-        rnd = rnd + torch.sqrt(omega(s, t)) * (u * z).sum(dim=-1, keepdim=True)
+        rnd = rnd + torch.sqrt(omega(s, t)) * (g * z).sum(dim=-1, keepdim=True)
         if return_traj:
             xs.append(x)
     rnd = rnd + reference_log_prob(x).view((-1, 1)) - terminal_unnorm_log_prob(x)
@@ -463,13 +474,13 @@ def simulate_ei(ts, x, noise, ctrl, sde, reference_ctrl, terminal_unnorm_log_pro
 
 
 def simulate_dds(ts, x, noise, ctrl, alpha, sigma, terminal_unnorm_log_prob, reference_log_prob,
-                 compute_ito_int=True, return_traj=False):
-    """ExponentialIntegratorSDELoss.simulate, losses/oc.py:1319-1397 (forward time, change_sde_ctrl=False)."""
+                 compute_ito_int=True, return_traj=False, lv=False):
+    """ExponentialIntegratorSDELoss.simulate, losses/oc.py:1319-1397 (forward time; ``lv`` = change_sde_ctrl)."""
     rnd = 0.0
     xs = [x] if return_traj else None
     for k, (s, t) in enumerate(zip(ts[:-1], ts[1:])):
-        u = ctrl(s, x)
-        running_cost = 0.5 * (u ** 2).sum(dim=-1, keepdim=True)
+        g = ctrl(s, x)
+        u, running_cost = _running_cost(g, lv)
         dt = t - s
         beta_k = torch.clip(alpha * dt.sqrt(), 0, 1)
         alpha_k = torch.sqrt(1.0 - beta_k ** 2)
@@ -477,7 +488,7 @@ def simulate_dds(ts, x, noise, ctrl, alpha, sigma, terminal_unnorm_log_prob, ref
         z = noise[k]
         x = x * alpha_k + (beta_k ** 2) * (sigma ** 2) * u + sigma * beta_k * z
         if compute_ito_int:
-            rnd = rnd + (sigma * u * z * beta_k).sum(dim=-1, keepdim=True)
+            rnd = rnd + (sigma * g * z * beta_k).sum(dim=-1, keepdim=True)
         if return_traj:
             xs.append(x)
     rnd = rnd + reference_log_prob(x).view((-1, 1)) - terminal_unnorm_log_prob(x)
@@ -485,7 +496,7 @@ def simulate_dds(ts, x, noise, ctrl, alpha, sigma, terminal_unnorm_log_prob, ref
 
 
 def simulate_dis(ts, x, noise, ctrl, sde, terminal_unnorm_log_prob, initial_log_prob, compute_ito_int=True,
-                 return_traj=False):
+                 return_traj=False, lv=False):
     """TimeReversalLoss.simulate, losses/oc.py:1133-1238, as DIS evaluates it (solver/oc.py:185-262 Bridge with
     inference_ctrl=None; eval passes train=False, change_sde_ctrl=False, use_rescaling=True): the control is taken at
     the loop time s (not T - s), the drift is +sde.drift(s, x), the log-weight starts at the prior log-density and
@@ -494,15 +505,17 @@ def simulate_dis(ts, x, noise, ctrl, sde, terminal_unnorm_log_prob, initial_log_
     d = x.shape[-1]
     xs = [x] if return_traj else None
     for k, (s, t) in enumerate(zip(ts[:-1], ts[1:])):
-        u = ctrl(s, x)
+        g = ctrl(s, x)
+        u, cost = _running_cost(g, lv)
         sde_diff = sde.diff(s)
         dt = t - s
-        rnd = rnd + 0.5 * (u ** 2).sum(dim=-1, keepdim=True) * dt
-        rnd = rnd - sde.int_drift_coeff(s, t) * d
+        rnd = rnd + cost * dt
+        if not lv:  # `if not train` (oc.py:1217-1218): the training rollout leaves the divergence integral out
+            rnd = rnd - sde.int_drift_coeff(s, t) * d
         db = noise[k] * dt.sqrt()
         x = x + (sde.drift_coeff(s) * x + sde_diff * u) * dt + sde_diff * db
         if compute_ito_int:
-            rnd = rnd + (u * db).sum(dim=-1, keepdim=True)
+            rnd = rnd + (g * db).sum(dim=-1, keepdim=True)
         if return_traj:
             xs.append(x)
     rnd = rnd - terminal_unnorm_log_prob(x)
@@ -701,10 +714,13 @@ def _cast(obj, dtype):
 
 
 def rollout(problem: dict, x0: torch.Tensor, noise: torch.Tensor, *, eubo: bool = False,
-            compute_ito_int: bool = True, return_traj: bool = False, dtype=torch.float32):
+            compute_ito_int: bool = True, return_traj: bool = False, dtype=torch.float32, lv: bool = False):
     """Runs the rollout named by ``problem`` (keys: method, sde, ctrl, target, ref, ts, and for
     dds alpha/sigma, for cmcd diff/T/clip_score/prior).  Returns (x_T, rnd, xs) for the generative
-    rollout, or rnd for ``eubo=True`` (x0 = target samples)."""
+    rollout, or rnd for ``eubo=True`` (x0 = target samples).  ``lv=True`` runs the TRAINING form of the linear
+    losses (change_sde_ctrl=True, autograd through the control; see lv_loss_and_grads)."""
+    if lv and (eubo or problem["method"] == "cmcd"):
+        raise ValueError("the lv training form is restated for the linear simulate loops only")
     problem = _cast(problem, dtype)
     x0, noise = x0.to(dtype), noise.to(dtype)
     ts = problem["ts"]
@@ -714,7 +730,7 @@ def rollout(problem: dict, x0: torch.Tensor, noise: torch.Tensor, *, eubo: bool 
         target_logp = lambda x: clip(raw(x), problem["clip_target"])  # noqa: E731
     ctrl = make_ctrl(problem["ctrl"], target_score, dtype)
     method = problem["method"]
-    with torch.no_grad():
+    with (torch.enable_grad() if lv else torch.no_grad()):
         if method in ("em", "ei", "ddpm"):
             sde = make_sde(problem["sde"], dtype)
             ref_ctrl, ref_logp = make_reference(problem["ref"], sde)
@@ -723,17 +739,17 @@ def rollout(problem: dict, x0: torch.Tensor, noise: torch.Tensor, *, eubo: bool 
                     return eubo_ei(ts, x0, noise, ctrl, sde, ref_ctrl, target_logp, ref_logp)
                 return eubo_em(ts, x0, noise, ctrl, sde, ref_ctrl, target_logp, ref_logp, use_rescaling=(method == "em"))
             if method == "em":
-                return simulate_em(ts, x0, noise, ctrl, sde, ref_ctrl, target_logp, ref_logp, return_traj)
+                return simulate_em(ts, x0, noise, ctrl, sde, ref_ctrl, target_logp, ref_logp, return_traj, lv=lv)
             return simulate_ei(ts, x0, noise, ctrl, sde, ref_ctrl, target_logp, ref_logp, return_traj,
-                               ddpm=(method == "ddpm"))
+                               ddpm=(method == "ddpm"), lv=lv)
         if method == "dis":  # prior = IsotropicGauss (conf/prior/gauss.yaml), scale = sde.scale_diff_coeff (conf/solver/dis.yaml)
             sde = make_sde(problem["sde"], dtype)
             _, prior_logp = make_reference(problem["ref"], None)
-            return simulate_dis(ts, x0, noise, ctrl, sde, target_logp, prior_logp, compute_ito_int, return_traj)
+            return simulate_dis(ts, x0, noise, ctrl, sde, target_logp, prior_logp, compute_ito_int, return_traj, lv=lv)
         if method == "dds":
             _, ref_logp = make_reference(problem["ref"], None)
             return simulate_dds(ts, x0, noise, ctrl, problem["alpha"], problem["sigma"], target_logp, ref_logp,
-                                compute_ito_int, return_traj)
+                                compute_ito_int, return_traj, lv=lv)
         if method == "cmcd":
             prior = problem["prior"]  # Gauss(loc, scale) diag; IsotropicGauss is the same arithmetic family
             ploc, pscale = prior["loc"], prior["scale"]
@@ -750,3 +766,23 @@ def rollout(problem: dict, x0: torch.Tensor, noise: torch.Tensor, *, eubo: bool 
                 return eubo_cmcd(ts, x0, noise, ctrl, drift, diff, target_logp, prior_logp)
             return simulate_cmcd(ts, x0, noise, ctrl, drift, diff, target_logp, prior_logp, return_traj)
     raise ValueError(method)
+
+
+def lv_loss_and_grads(problem: dict, x0: torch.Tensor, noise: torch.Tensor, max_rnd: float | None = 1e8,
+                      dtype=torch.float32):
+    """The training objective ``loss(ts, x, ...)`` of the linear rollout losses with method='lv' and its gradient:
+    __call__ (losses/oc.py:364-394, 1240-1272, 1399-1431: change_sde_ctrl=True, compute_ito_int=True) ->
+    BaseOCLoss.compute_loss (105-131: ``rnd[mask].var()`` over the particles that pass ``filter``, 67-81).
+    Returns (loss, {state_dict key: d loss / d parameter}, rnd)."""
+    problem = dict(problem)
+    ctrl = dict(problem["ctrl"])
+    ctrl["sd"] = {k: v.detach().to(dtype).clone().requires_grad_(True) for k, v in ctrl["sd"].items()}
+    problem["ctrl"] = ctrl
+    cast = _cast({k: v for k, v in problem.items() if k != "ctrl"}, dtype)
+    cast["ctrl"] = ctrl
+    _, rnd, _ = rollout(cast, x0, noise, compute_ito_int=True, dtype=dtype, lv=True)
+    mask = rnd.isfinite() if max_rnd is None else rnd < max_rnd
+    loss = rnd[mask].var()
+    names = list(ctrl["sd"])
+    grads = torch.autograd.grad(loss, [ctrl["sd"][k] for k in names], allow_unused=True)
+    return loss.detach(), {k: (g if g is not None else torch.zeros_like(ctrl["sd"][k])) for k, g in zip(names, grads)}, rnd.detach()
