@@ -1,7 +1,9 @@
 """Evaluation helpers with the reference's names (sde_sampler/additions/hacking.py): ``evaluate_eubo`` (14-33) and
 ``TrainableWrapper.evaluate / compute_results_eubo`` (68-91).  The forward (EUBO) estimators come from the same fp64
-partials as the backward ones (estimators.py); training (``TrainableWrapper.run``) is out of scope."""
+partials as the backward ones (estimators.py); ``TrainableWrapper.run`` (36-66) trains with the solver's ``step``."""
 from __future__ import annotations
+
+import time
 
 import torch
 
@@ -32,7 +34,23 @@ class TrainableWrapper(torch.nn.Module):
         self.verbose = verbose
 
     def run(self, keep_training_metrics=False):
-        raise NotImplementedError("training through the fused rollout is the next row of the scope table (SURVEY.md 8f item 1)")
+        """train_steps stochastic gradient steps, then the evaluation with the EUBO metrics (hacking.py:43-66)."""
+        t = self.trainable
+        t.train()
+        training_metrics, training_time = [], 0.0
+        for i in range(t.n_steps, t.train_steps):
+            start = time.time()
+            metrics = t.step(i)
+            training_time += time.time() - start
+            if keep_training_metrics:
+                training_metrics.append(metrics)
+            if self.verbose:
+                print("step {} loss={:.2e}".format(i, metrics["train/loss"]))
+        results = self.evaluate(use_ema=t.use_ema)
+        results.metrics["eval/training_time"] = training_time
+        if keep_training_metrics:
+            return results, {k: [m[k] for m in training_metrics if k in m] for k in training_metrics[0]}
+        return results
 
     def compute_results_eubo(self, results, use_ema=True):
         t = self.trainable

@@ -12,7 +12,9 @@ signatures (sde_sampler/losses/oc.py): ``simulate`` / ``eval`` / ``compute_eubo`
 Extra keyword arguments (not in the reference, all optional): ``noise`` = recorded standard normals [K, B, d]
 to consume instead of in-kernel Philox draws (validation mode), ``seed`` / ``particle_offset`` for the
 counter-based generator (global particle index => results independent of the GPU count).
-Training (``__call__`` with autograd through the control) is the next row of SURVEY.md 8f and raises.
+Training: ``loss(ts, x, ...)`` with method 'lv' / 'lv_traj' returns a scalar whose ``backward()`` fills the control's
+parameter gradients (train.py: fused rollout + one batched gradient pass); 'kl' (pathwise gradient through the
+trajectory) and the CMCD loss raise.
 """
 from __future__ import annotations
 
@@ -94,9 +96,40 @@ class BaseOCLoss:
             return mask & rnd.isfinite()
         return mask & (rnd < self.max_rnd)
 
+    def compute_loss(self, rnd: torch.Tensor, samples: torch.Tensor | None = None):
+        """The variational loss from the log-weights (oc.py:105-131): variance ('lv'), per-sample variance over the
+        repeated trajectories ('lv_traj') or mean ('kl') of the particles that pass ``filter``."""
+        mask = self.filter(rnd, samples=samples)
+        assert mask.shape == rnd.shape
+        if self.method == "lv_traj":
+            rnd = rnd.reshape(self.traj_per_sample, -1, 1)
+            mask = mask.reshape(self.traj_per_sample, -1, 1).all(dim=0)
+            self.n_filtered += self.traj_per_sample * (mask.numel() - mask.sum()).item()
+            loss = rnd[:, mask].var(dim=0).mean()
+        else:
+            self.n_filtered += (mask.numel() - mask.sum()).item()
+            loss = rnd[mask].var() if self.method == "lv" else rnd[mask].mean()
+        return loss, {"train/n_filtered_cumulative": self.n_filtered}
+
+    def _train(self, make_plan, x, noise=None, seed=None, particle_offset: int = 0):
+        """[TRAINING] shared by the ``__call__`` of the linear losses: repeat the initial values, run the fused rollout
+        with the detached control driving the SDE, return (loss, metrics) with the LV gradient attached (train.py)."""
+        from .. import train
+        if self.method not in ("lv", "lv_traj"):
+            raise NotImplementedError("method 'kl' / 'kl_ito' differentiates through the trajectory (pathwise gradient): "
+                                      "not built; the shipped solver configs train with loss_type 'lv' or 'kl' "
+                                      "(SURVEY.md 8f item 1)")
+        if self.sde_ctrl_noise is not None or self.sde_ctrl_dropout is not None:
+            raise NotImplementedError("sde_ctrl_noise / sde_ctrl_dropout are not set by any shipped config")
+        if self.traj_per_sample != 1:
+            x = x.repeat(self.traj_per_sample, 1, 1).reshape(-1, x.shape[-1])
+        info = self._ctrl(False)
+        return train.lv_objective(self, make_plan(x.device), info, x, self._seed(seed), noise=noise,
+                                  particle_offset=particle_offset)
+
     def __call__(self, ts, x, *args, **kwargs):
-        raise NotImplementedError("training through the fused rollout (LV/KL gradient) is the next row of the "
-                                  "scope table (SURVEY.md 8f item 1); only simulate / eval / compute_eubo are built")
+        raise NotImplementedError("training through this loss is not built (SURVEY.md 8f item 1): the linear losses "
+                                  "(EM / EI / DDPM-like reference losses, DDS, DIS) train with method 'lv'")
 
     def load_state_dict(self, state_dict: dict):
         self.n_filtered = state_dict["n_filtered"]
@@ -234,8 +267,13 @@ class EMReferenceSDELoss(BaseOCLoss):
             blk0 = pack.gauss_block_from(ref0, device)
             fill_gmm(spec.ref_0, blk0)
             keep.append(blk0)
-            return pack.Plan(spec, keep, rows=K, noise_steps=K)
+            return pack.Plan(spec, keep, rows=K, noise_steps=K, taus=taus, ito_w=pack.ito_weights(table, spec.ito_form))
         return self._cached(key, build)
+
+    def __call__(self, ts, x, terminal_unnorm_log_prob, reference_log_prob, **kw):
+        """[TRAINING] (loss, metrics) of oc.py:364-394."""
+        return self._train(lambda dev: self._plan(ts, dev, False, terminal_unnorm_log_prob, reference_log_prob, eubo=False),
+                           x, **kw)
 
     def simulate(self, ts, x, terminal_unnorm_log_prob, reference_log_prob, change_sde_ctrl: bool = False,
                  return_traj: bool = False, use_ema: bool = False, noise=None, seed=None, particle_offset: int = 0):
@@ -327,8 +365,12 @@ class ExponentialIntegratorSDELoss(BaseOCLoss):
             blk0 = pack.gauss_block_from(ref0, device)
             fill_gmm(spec.ref_0, blk0)
             keep.append(blk0)
-            return pack.Plan(spec, keep, rows=K, noise_steps=K)
+            return pack.Plan(spec, keep, rows=K, noise_steps=K, taus=tsc[:-1], ito_w=pack.ito_weights(table, spec.ito_form))
         return self._cached(key, build)
+
+    def __call__(self, ts, x, terminal_unnorm_log_prob, reference_log_prob, **kw):
+        """[TRAINING] (loss, metrics) of oc.py:1399-1431 (compute_ito_int = method != 'kl')."""
+        return self._train(lambda dev: self._plan(ts, dev, False, terminal_unnorm_log_prob, reference_log_prob, True), x, **kw)
 
     def simulate(self, ts, x, terminal_unnorm_log_prob, reference_log_prob, compute_ito_int: bool = False,
                  change_sde_ctrl: bool = False, return_traj: bool = False, use_ema: bool = False, noise=None,
@@ -362,10 +404,11 @@ class TimeReversalLoss(BaseOCLoss):
         self.div_estimator = div_estimator
         self.use_rescaling = use_rescaling
 
-    def _plan(self, ts, device, use_ema, terminal_unnorm_log_prob, initial_log_prob, compute_ito_int):
+    def _plan(self, ts, device, use_ema, terminal_unnorm_log_prob, initial_log_prob, compute_ito_int, train=False):
         info = self._ctrl(use_ema)
         prior, _ = pack.resolve_log_prob(initial_log_prob)
-        key = self._key(("dis", bool(compute_ito_int)), ts, device, info, (id(prior), id(terminal_unnorm_log_prob)))
+        key = self._key(("dis", bool(compute_ito_int), bool(train)), ts, device, info,
+                        (id(prior), id(terminal_unnorm_log_prob)))
 
         def build():
             sde = self.sde.host()
@@ -398,18 +441,24 @@ class TimeReversalLoss(BaseOCLoss):
                 raise NotImplementedError("DIS needs a Gaussian prior (solver/oc.py:207-208)")
             fill_gmm(spec.ref_0, blk0)
             keep.append(blk0)
-            spec.init_cost, spec.rnd_offset = 1, float(div)
-            return pack.Plan(spec, keep, rows=K, noise_steps=K)
+            # the training rollout leaves the divergence integral out (`if not train`, oc.py:1217)
+            spec.init_cost, spec.rnd_offset = 1, 0.0 if train else float(div)
+            return pack.Plan(spec, keep, rows=K, noise_steps=K, taus=tsc[:-1], ito_w=pack.ito_weights(table, spec.ito_form))
         return self._cached(key, build)
+
+    def __call__(self, ts, x, terminal_unnorm_log_prob, initial_log_prob=None, **kw):
+        """[TRAINING] (loss, metrics) of oc.py:1240-1272 (compute_ito_int = method != 'kl', train=True)."""
+        return self._train(lambda dev: self._plan(ts, dev, False, terminal_unnorm_log_prob, initial_log_prob, True, train=True),
+                           x, **kw)
 
     def simulate(self, ts, x, terminal_unnorm_log_prob, initial_log_prob=None, train: bool = True,
                  compute_ito_int: bool = False, change_sde_ctrl: bool = False, return_traj: bool = False,
                  use_ema: bool = False, noise=None, seed=None, particle_offset: int = 0):
         self._check_plain(change_sde_ctrl)
-        if train:
-            raise NotImplementedError("the training variant (no divergence integral, rnd starting at 0 for kl; "
-                                      "oc.py:1164-1168, 1217) is part of SURVEY.md 8f item 1; eval passes train=False")
-        plan = self._plan(ts, x.device, use_ema, terminal_unnorm_log_prob, initial_log_prob, compute_ito_int)
+        if train and self.method in ["kl", "kl_ito"]:
+            raise NotImplementedError("the kl training rollout starts the log-weight at 0 (oc.py:1164-1165) and is "
+                                      "differentiated through the trajectory: not built (SURVEY.md 8f item 1)")
+        plan = self._plan(ts, x.device, use_ema, terminal_unnorm_log_prob, initial_log_prob, compute_ito_int, train=train)
         return pack.run_rollout(plan, x, noise, self._seed(seed), particle_offset, return_traj)
 
     def eval(self, ts, x, terminal_unnorm_log_prob, initial_log_prob=None, compute_weights: bool = True,

@@ -192,6 +192,19 @@ class Plan:
     keep: list = field(default_factory=list)
     rows: int = 0
     noise_steps: int = 0
+    taus: torch.Tensor | None = None    # [K] host: the time the control is evaluated at in step k (training, train.py)
+    ito_w: torch.Tensor | None = None   # [K] host: the weight of <g, z> in the log-weight of step k
+
+
+def ito_weights(table: torch.Tensor, ito_form: int) -> torch.Tensor:
+    """Per-step weight of sum(g z) in rnd for the LINEAR loops (include/lrds_b200.h, lrds_ito_form)."""
+    if ito_form == N.ITO_SCALED:
+        return table[:, N.STEP_W_ITO].clone()
+    if ito_form == N.ITO_EM:
+        return table[:, N.STEP_SQRT_DT].clone()
+    if ito_form == N.ITO_DDS:
+        return table[:, N.STEP_SIGU] * table[:, N.STEP_W_ITO]
+    return torch.zeros(table.shape[0])
 
 
 def _scalar_rows(ts: torch.Tensor):

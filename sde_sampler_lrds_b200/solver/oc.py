@@ -7,7 +7,9 @@ constructors take the same information as a plain nested ``dict`` with the YAML'
 (``benchmark_utils.default_config``).  What is kept: ``compute_results`` (two rollouts, the
 second one timed as ``eval/sample_time``), ``_compute_results``, ``clipped_target_unnorm_log_prob``,
 ``RDS.change_reference_type`` / ``reference_ctrl``, ``CMCD.update_prior``, ``state_dict`` of the reference parameters.
-What is not: the training loop, checkpoints, wandb, plots (control plane).
+Training: ``compute_loss`` / ``_compute_loss`` / ``step`` (solver/base.py:401-457: Adam, loss / gradient guards, gradient
+clipping, EMA) drive the LV objective of train.py.  What is not: the run loop with its evaluation schedule,
+checkpoints, wandb, plots (control plane).
 Every rollout below is ONE fused CUDA kernel launch (losses/oc.py -> csrc/).
 """
 from __future__ import annotations
@@ -65,9 +67,14 @@ class TrainableDiff(torch.nn.Module):
         self.eval_integrator = EulerIntegrator()
         self.plot_results = False
         self.n_steps = 0
+        self.n_steps_skip = 0
         self.train_steps = cfg.get("train_steps", 0)
+        self.ema_steps = cfg.get("ema_steps", 10)
+        self.max_grad, self.max_loss, self.scale_loss = cfg.get("max_grad"), cfg.get("max_loss"), cfg.get("scale_loss")
+        self.grad_clip = build(cfg.get("grad_clip"))
         self.setup_models()
         self.to(self.device)
+        self.optim = None
 
     # ---- models ---------------------------------------------------------------------------------------------------
     def setup_models(self, langevin_based: bool = False, skip_prior: bool = False):
@@ -107,8 +114,61 @@ class TrainableDiff(torch.nn.Module):
     def _compute_results(self, ts, x, use_ema=True, compute_weights=True, return_traj=True) -> Results:
         raise NotImplementedError
 
+    # ---- training (solver/oc.py:94-121, solver/base.py:289-300, 401-457) -----------------------------------------------
+    def _compute_loss(self, ts, x):
+        raise NotImplementedError("training through this solver's loss is not built (SURVEY.md 8f item 1)")
+
     def compute_loss(self):
-        raise NotImplementedError("training through the fused rollout is the next row of the scope table (SURVEY.md 8f item 1)")
+        """[TRAINING] the variational loss over a fresh batch of prior samples."""
+        x = self.prior.sample((self.train_batch_size,))
+        if self.train_ts is None:
+            self.train_ts = self.train_timesteps(device=x.device)
+        else:
+            self.train_ts = self.train_ts.to(x.device)
+        return self._compute_loss(self.train_ts, x)
+
+    def trainable_parameters(self):
+        return (p for p in self.parameters() if p.requires_grad)
+
+    def setup_optimizer(self):
+        """conf/solver/basic_oc_base.yaml: Adam, lr 3e-4 (``cfg['optim']`` = {'_target_': ..., 'lr': ...} overrides)."""
+        cfg = dict(self.cfg.get("optim") or {"_target_": torch.optim.Adam, "lr": 3e-4})
+        target = cfg.pop("_target_", torch.optim.Adam)
+        self.optim = target(list(self.trainable_parameters()), **cfg)
+
+    def step(self, step_id: int = 0) -> dict:
+        """One stochastic gradient step (solver/base.py:401-457; no lr schedulers: none is configured by default)."""
+        if self.optim is None:
+            self.setup_optimizer()
+        torch.cuda.synchronize(self.device)
+        start_t = time.time()
+        self.optim.zero_grad()
+        loss, metrics = self.compute_loss()
+        if self.scale_loss is not None:
+            loss = self.scale_loss * loss
+        loss.backward()
+        loss_ok = loss.isfinite() if self.max_loss is None else loss.abs() <= self.max_loss
+        grads = [p.grad for p in self.trainable_parameters() if p.grad is not None]
+        if self.max_grad is None:
+            grad_ok = all(g.isfinite().all() for g in grads)
+        else:
+            max_grad = torch.stack([g.abs().max() for g in grads]).max()
+            grad_ok = max_grad <= self.max_grad
+            metrics["train/max_grad"] = max_grad.item()
+        if loss_ok and grad_ok:
+            if self.grad_clip is not None:
+                metrics["train/grad_clip_norm"] = self.grad_clip(self.trainable_parameters()).item()
+            self.optim.step()
+            if self.use_ema and (step_id % self.ema_steps == 0):
+                self.generative_ctrl_ema.update_parameters(self.generative_ctrl)
+        else:
+            self.n_steps_skip += 1
+        torch.cuda.synchronize(self.device)
+        metrics.update({"train/time_per_step": time.time() - start_t, "train/loss": loss.item(),
+                        "train/skipped_steps": self.n_steps_skip,
+                        "train/no_grad": sum(p.grad is None for p in self.trainable_parameters())})
+        self.n_steps += 1
+        return metrics
 
     @torch.no_grad()
     def compute_results(self, use_ema=True) -> Results:
@@ -151,6 +211,9 @@ class Bridge(TrainableDiff):
                                       generative_ctrl_ema=self.generative_ctrl_ema, sde=self.sde,
                                       inference_ctrl=self.inference_ctrl,
                                       filter_samples=getattr(self.target, "filter", None))
+
+    def _compute_loss(self, ts, x):
+        return self.loss(ts, x, self.clipped_target_unnorm_log_prob, initial_log_prob=self.prior.log_prob)
 
     def _compute_results(self, ts, x, use_ema=True, compute_weights=True, return_traj=True) -> Results:
         return self.loss.eval(ts, x, self.clipped_target_unnorm_log_prob, use_ema=use_ema,
@@ -197,6 +260,9 @@ class PIS(TrainableDiff):
                                       generative_ctrl_ema=self.generative_ctrl_ema, sde=self.sde,
                                       filter_samples=getattr(self.target, "filter", None))
 
+    def _compute_loss(self, ts, x):
+        return self.loss(ts, x, self.clipped_target_unnorm_log_prob, self.reference_distr.log_prob)
+
     def _compute_results(self, ts, x, use_ema=True, compute_weights=True, return_traj=True) -> Results:
         return self.loss.eval(ts, x, self.clipped_target_unnorm_log_prob, self.reference_distr.log_prob, use_ema=use_ema,
                               compute_weights=compute_weights, return_traj=return_traj)
@@ -215,6 +281,9 @@ class DDS(TrainableDiff):
         self.loss: BaseOCLoss = build(self.cfg["loss"], generative_ctrl=self.generative_ctrl,
                                       generative_ctrl_ema=self.generative_ctrl_ema, sde=self.sde,
                                       filter_samples=getattr(self.target, "filter", None))
+
+    def _compute_loss(self, ts, x):
+        return self.loss(ts, x, self.clipped_target_unnorm_log_prob, self.reference_distr.log_prob)
 
     def _compute_results(self, ts, x, use_ema=True, compute_weights=True, return_traj=True) -> Results:
         return self.loss.eval(ts, x, self.clipped_target_unnorm_log_prob, self.reference_distr.log_prob, use_ema=use_ema,
@@ -268,6 +337,9 @@ class RDS(TrainableDiff):
 
     def reference_ctrl(self, t: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
         return self.reference_score_t(t, x)
+
+    def _compute_loss(self, ts, x):
+        return self.loss(ts, x, self.clipped_target_unnorm_log_prob, self.reference_distr.log_prob)
 
     def _compute_results(self, ts, x, use_ema=True, compute_weights=True, return_traj=True) -> Results:
         return self.loss.eval(ts, x, self.clipped_target_unnorm_log_prob, self.reference_distr.log_prob, use_ema=use_ema,

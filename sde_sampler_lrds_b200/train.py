@@ -1,0 +1,119 @@
+"""Training objective through the fused rollout: ``loss(ts, x, ...)`` of the linear rollout losses with
+method 'lv' / 'lv_traj' (sde_sampler/losses/oc.py:364-394, 1240-1272, 1399-1431 -> compute_loss 105-131), the first
+version of SURVEY.md 8f item 1.
+
+With these methods the SDE follows the DETACHED control (generative_and_sde_ctrl, oc.py:83-103), so no gradient flows
+along a trajectory: the states x_k are constants and
+
+    d rnd_b / d theta = sum_k  c_k <z_bk, d g(t_k, x_bk) / d theta>          (c_k = the Ito weight of step k)
+
+because the running cost g (sde_ctrl - g / 2) has a vanishing derivative at sde_ctrl = g.  The reference obtains this
+by autograd through K sequential steps (~40-150 eager ops each).  Here
+
+  1. the rollout is ONE fused kernel launch (csrc/), fed with the generator's own increments z (lrds_normals) and
+     returning the trajectory;
+  2. d loss / d rnd comes from the reference's loss formula on the B log-weights;
+  3. the parameter gradient is ONE batched evaluation of the control on all K x B stored states with the cotangent
+     (d loss / d rnd_b) c_k z_bk: a handful of large library GEMMs (cuBLAS through torch autograd) instead of K small ones.
+
+Step 3 is plain PyTorch on the device - plumbing around the kernel, stated as such; a hand-written weight-gradient
+kernel that recomputes the activations from the stored states is the follow-up.  Nothing here
+runs on the CPU or imports the oracle.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+import torch.nn.functional as F
+
+from . import _native as N
+from . import pack
+
+
+def time_embed_rows(m, t: torch.Tensor) -> torch.Tensor:
+    """Differentiable TimeEmbed.forward for a 1-D tensor of times (sde_sampler/models/mlp.py:85-96)."""
+    arg = m.timestep_coeff * t.reshape(-1, 1) + m.timestep_phase
+    e = torch.cat([torch.sin(arg), torch.cos(arg)], dim=1)
+    for layer in m.hidden_layer:
+        e = F.gelu(layer(e))
+    return m.out_layer(e)
+
+
+def _clip(v, bound):
+    return v if bound is None else v.clip(-bound, bound)
+
+
+def control_rows(info: pack.CtrlInfo, taus: torch.Tensor, xs: torch.Tensor, score: torch.Tensor | None) -> torch.Tensor:
+    """g(t_s, x_sb) for times taus [S] and states xs [S, B, d], differentiable in the parameters of the control:
+    FourierMLP.forward (models/mlp.py:135-143) under ClippedCtrl / ScoreCtrl.forward (models/reparam.py:33-43, 112-117).
+    ``score`` = target_score(xs) (a constant: the states carry no gradient)."""
+    base = info.base
+    emb = base.input_embed(xs) + time_embed_rows(base.timestep_embed, taus)[:, None, :]
+    for layer in base.hidden_layer:
+        emb = layer(F.gelu(emb))
+    g = _clip(base.out_layer(F.gelu(emb)), info.clip_model)
+    if info.kind == N.CTRL_CLIPPED:
+        return g
+    sc = info.scale_score * _clip(score, info.clip_score)
+    if info.score_model is not None:
+        sc = sc * _clip(time_embed_rows(info.score_model, taus), info.clip_model)[:, None, :]
+    return g + sc
+
+
+class _InjectGrads(torch.autograd.Function):
+    """loss value whose backward hands the precomputed parameter gradients to autograd."""
+
+    @staticmethod
+    def forward(ctx, value, grads, *params):
+        ctx.grads = grads
+        return value.clone()
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        return (None, None, *[None if g is None else grad_out * g for g in ctx.grads])
+
+
+def normals(seed: int, particle_offset: int, K: int, B: int, d: int, device) -> torch.Tensor:
+    """The increments z [K, B, d] the production-mode rollout would draw in-kernel (lrds_normals, stream 0)."""
+    z = torch.empty(K, B, d, device=device, dtype=torch.float32)
+    with torch.cuda.device(device):
+        N.check(N.lib().lrds_normals(C.c_uint64(seed & (2 ** 64 - 1)), C.c_uint64(particle_offset), 0, K, B, d, N.ptr(z),
+                                     N.stream_ptr(device)))
+    return z
+
+
+def lv_objective(loss_obj, plan: pack.Plan, info: pack.CtrlInfo, x: torch.Tensor, seed: int, noise=None,
+                 particle_offset: int = 0, max_rows: int = 1 << 20):
+    """(loss, metrics) like ``BaseOCLoss.__call__``: ``loss`` is a scalar whose ``backward()`` leaves the LV gradient in
+    the ``.grad`` of the control's parameters."""
+    if info.kind not in (N.CTRL_CLIPPED, N.CTRL_SCORE):
+        raise NotImplementedError("training is built for ClippedCtrl / ScoreCtrl drift models")
+    dev = x.device
+    B, d = x.shape
+    K = plan.noise_steps
+    z = normals(seed, particle_offset, K, B, d, dev) if noise is None else noise.detach().to(dev, torch.float32).contiguous()
+    with torch.no_grad():
+        x_T, rnd, xs = pack.run_rollout(plan, x, z, seed, particle_offset, True)
+    rnd_leaf = rnd.detach().clone().requires_grad_(True)
+    with torch.enable_grad():
+        value, metrics = loss_obj.compute_loss(rnd_leaf, samples=x_T)
+        (w,) = torch.autograd.grad(value, rnd_leaf)  # d loss / d rnd_b, zero for filtered particles
+    params = [p for p in loss_obj.generative_ctrl.parameters() if p.requires_grad]
+    grads: list = [None] * len(params)
+    taus = plan.taus.to(dev)
+    ito_w = plan.ito_w.to(dev)
+    step_rows = max(1, max_rows // B)
+    for k0 in range(0, K, step_rows):
+        k1 = min(K, k0 + step_rows)
+        xs_c = xs[k0:k1]
+        score = None
+        if info.kind == N.CTRL_SCORE:
+            score = info.target.score(xs_c.reshape(-1, d)).reshape(k1 - k0, B, d)
+        cot = (ito_w[k0:k1, None, None] * w[None, :, :]) * z[k0:k1]
+        with torch.enable_grad():
+            surrogate = (cot * control_rows(info, taus[k0:k1], xs_c, score)).sum()
+        for i, g in enumerate(torch.autograd.grad(surrogate, params, allow_unused=True)):
+            if g is not None:
+                grads[i] = g if grads[i] is None else grads[i] + g
+    return _InjectGrads.apply(value.detach(), grads, *params), metrics

@@ -120,6 +120,12 @@ class Built:
         return self.loss.simulate(self.ts, x0.to(self.device), *self.args, return_traj=return_traj,
                                   noise=None if noise is None else noise.to(self.device), **self.kwargs, **extra)
 
+    def train_loss(self, x0, noise=None, **extra):
+        """[TRAINING] ``loss(ts, x, ...)`` -> (loss, metrics); loss.backward() fills the control's parameter gradients."""
+        kw = {"initial_log_prob": self.prior.log_prob} if self.case["problem"]["method"] == "dis" else {}
+        return self.loss(self.ts, x0.to(self.device), *self.args, noise=None if noise is None else noise.to(self.device),
+                         **kw, **extra)
+
     def compute_eubo(self, x0, noise=None, **extra):
         return self.loss.compute_eubo(self.ts, x0.to(self.device).clone(), *self.args,
                                       noise=None if noise is None else noise.to(self.device), **extra)
