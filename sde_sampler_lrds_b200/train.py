@@ -44,10 +44,13 @@ def _clip(v, bound):
     return v if bound is None else v.clip(-bound, bound)
 
 
-def control_rows(info: pack.CtrlInfo, taus: torch.Tensor, xs: torch.Tensor, score: torch.Tensor | None) -> torch.Tensor:
+def control_rows(info: pack.CtrlInfo, taus: torch.Tensor, xs: torch.Tensor, score: torch.Tensor | None,
+                 coef: torch.Tensor | None = None) -> torch.Tensor:
     """g(t_s, x_sb) for times taus [S] and states xs [S, B, d], differentiable in the parameters of the control:
-    FourierMLP.forward (models/mlp.py:135-143) under ClippedCtrl / ScoreCtrl.forward (models/reparam.py:33-43, 112-117).
-    ``score`` = target_score(xs) (a constant: the states carry no gradient)."""
+    FourierMLP.forward (models/mlp.py:135-143) under ClippedCtrl / ScoreCtrl / CancelDriftCtrl / LerpCtrl.forward
+    (models/reparam.py:33-43, 112-117, 131-147, 189-199).  ``score`` = the (for LerpCtrl: interpolated) target score at
+    xs, a constant because the states carry no gradient; ``coef`` [S, 16] = the time-only table columns of the two DIS
+    models (pack.dis_ctrl_rows)."""
     base = info.base
     emb = base.input_embed(xs) + time_embed_rows(base.timestep_embed, taus)[:, None, :]
     for layer in base.hidden_layer:
@@ -58,6 +61,10 @@ def control_rows(info: pack.CtrlInfo, taus: torch.Tensor, xs: torch.Tensor, scor
     sc = info.scale_score * _clip(score, info.clip_score)
     if info.score_model is not None:
         sc = sc * _clip(time_embed_rows(info.score_model, taus), info.clip_model)[:, None, :]
+    if info.kind == N.CTRL_CANCEL_DRIFT:  # ctrl + drift / diff + 0.5 diff score
+        return g + coef[:, N.STEP_CX, None, None] * xs + coef[:, N.STEP_GSCALE, None, None] * sc
+    if info.kind == N.CTRL_LERP:          # ctrl + diff score
+        return g + coef[:, N.STEP_GSCALE, None, None] * sc
     return g + sc
 
 
@@ -87,8 +94,6 @@ def lv_objective(loss_obj, plan: pack.Plan, info: pack.CtrlInfo, x: torch.Tensor
                  particle_offset: int = 0, max_rows: int = 1 << 20):
     """(loss, metrics) like ``BaseOCLoss.__call__``: ``loss`` is a scalar whose ``backward()`` leaves the LV gradient in
     the ``.grad`` of the control's parameters."""
-    if info.kind not in (N.CTRL_CLIPPED, N.CTRL_SCORE):
-        raise NotImplementedError("training is built for ClippedCtrl / ScoreCtrl drift models")
     dev = x.device
     B, d = x.shape
     K = plan.noise_steps
@@ -103,16 +108,22 @@ def lv_objective(loss_obj, plan: pack.Plan, info: pack.CtrlInfo, x: torch.Tensor
     grads: list = [None] * len(params)
     taus = plan.taus.to(dev)
     ito_w = plan.ito_w.to(dev)
+    coef = torch.zeros(K, N.STEP_BIAS1)
+    pack.dis_ctrl_rows(info, plan.taus, coef)
+    coef = coef.to(dev)
     step_rows = max(1, max_rows // B)
     for k0 in range(0, K, step_rows):
         k1 = min(K, k0 + step_rows)
         xs_c = xs[k0:k1]
         score = None
-        if info.kind == N.CTRL_SCORE:
+        if info.kind != N.CTRL_CLIPPED:
             score = info.target.score(xs_c.reshape(-1, d)).reshape(k1 - k0, B, d)
+            if info.kind == N.CTRL_LERP:  # clipped_interpolated_score, models/reparam.py:170-183
+                prior = info.prior.score(xs_c.reshape(-1, d)).reshape(k1 - k0, B, d)
+                score = torch.lerp(prior, score, coef[k0:k1, N.STEP_LERP, None, None])
         cot = (ito_w[k0:k1, None, None] * w[None, :, :]) * z[k0:k1]
         with torch.enable_grad():
-            surrogate = (cot * control_rows(info, taus[k0:k1], xs_c, score)).sum()
+            surrogate = (cot * control_rows(info, taus[k0:k1], xs_c, score, coef[k0:k1])).sum()
         for i, g in enumerate(torch.autograd.grad(surrogate, params, allow_unused=True)):
             if g is not None:
                 grads[i] = g if grads[i] is None else grads[i] + g

@@ -401,7 +401,7 @@ CASES = {
 # cases whose TRAINING objective (method='lv') and parameter gradient are pinned by reference-generated fixtures
 # (tests/golden/grad_<name>.pt, python -m oracle.make_golden --grads)
 GRAD_CASES = ["em_two_modes_score", "ei_many_modes", "ddpm_snr", "ei_phi4_gmm", "pis_many_modes", "dds_many_modes_ito",
-              "dds_phi4_ito", "dis_many_modes_ito", "pis_logreg"]
+              "dds_phi4_ito", "dis_many_modes_ito", "pis_logreg", "dis_many_modes_lerp", "dis_many_modes_langevin"]
 
 
 def initial_state(case: dict, dtype=torch.float32):

@@ -47,6 +47,7 @@ def test_lv_gradient_matches_oracle_and_reference(name, precision, device):
     ("pis_orig", dict(ref_type="default", integrator_type="em", time_type="uniform")),
     ("dds_orig", dict(ref_type="default", integrator_type="em", time_type="uniform")),
     ("dis_orig", dict(ref_type="default", integrator_type="em", time_type="uniform")),
+    ("dis_orig", dict(ref_type="default", integrator_type="em", time_type="uniform", model_type="target_informed_lerp_tempering")),
 ])
 def test_training_steps_through_make_model(solver_type, kw, device):
     """make_model(...).step(): the LV loss is finite, every parameter of the control receives a gradient and moves, and
@@ -56,8 +57,8 @@ def test_training_steps_through_make_model(solver_type, kw, device):
     from tests.test_solver_api_gpu import TRAIN, _gmm_ref, _randomise_last_layers
     d, M = 6, 5
     details = {"sigma": 1.0, **_gmm_ref(d, M)}
-    model = BU.make_model(solver_type=solver_type, loss_type="lv", model_type="target_informed_zero_init",
-                          solver_details=details, target_details=BU.make_target_details("many_modes", dim=d, n_modes=M),
+    kw = dict({"model_type": "target_informed_zero_init"}, **kw)
+    model = BU.make_model(solver_type=solver_type, loss_type="lv", solver_details=details, target_details=BU.make_target_details("many_modes", dim=d, n_modes=M),
                           training_details=dict(TRAIN, train_steps=3), n_steps=24, device=str(device), **kw)
     _randomise_last_layers(model)
     before = {n: p.detach().clone() for n, p in model.generative_ctrl.named_parameters()}
