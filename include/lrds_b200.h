@@ -254,6 +254,19 @@ int lrds_axpy_step(const float* x, const float* s, const float* z, float a, floa
 int lrds_normals(uint64_t seed, uint64_t particle_offset, int32_t stream_id, int32_t K, int32_t B, int32_t d,
                  float* out, void* stream);
 
+/* ---- MALA chains: replaces the loop of mcmc_sample(mcmc_type='mala') (experiments/benchmark_utils.py:268-333) around
+ * mala_step and heuristics_step_size (sde_sampler/additions/mcmc.py:75-134, 54-72) - the sampler that produces the data the
+ * GMM reference is fitted to.  One launch runs n_warmup + n_steps Metropolis-adjusted Langevin steps of C chains
+ * (one thread per chain), with the per-chain step-size heuristic (target acceptance 0.75, factor 1.01, tolerance 0.05)
+ * after every step when `adapt` is set.
+ *   y0 [C][d] initial states        step_size [C] in / out
+ *   noise [n_warmup + n_steps][C][d] standard normals or NULL (in-kernel Philox, stream 0)
+ *   unif  [n_warmup + n_steps][C] uniforms in (0, 1] of the accept test or NULL (Philox, stream 2)
+ *   ys_out [n_steps][C][d] the chains after the warm-up      log_acc_out [n_warmup + n_steps][C] or NULL */
+int lrds_mala(const lrds_distr* target, int32_t d, int32_t C, int32_t n_warmup, int32_t n_steps, int32_t adapt,
+              const float* y0, float* step_size, const float* noise, const float* unif, uint64_t seed, float* ys_out,
+              float* log_acc_out, void* stream);
+
 const char* lrds_last_error(void);
 int lrds_abi_version(void);
 /* number of kernels this library has launched in the calling process (bench.py's gpu_launches claim) */

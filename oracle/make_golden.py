@@ -238,10 +238,57 @@ def run_reference(case, grads=False):
     return {k: (v.detach().clone() if isinstance(v, torch.Tensor) else v) for k, v in out.items()}
 
 
+def run_reference_mala(case):
+    """The loop of mcmc_sample(mcmc_type='mala') (experiments/benchmark_utils.py:268-333; that module imports hydra, which
+    this image lacks, so its driver loop is replayed here) around the reference's OWN mala_step and heuristics_step_size
+    (sde_sampler/additions/mcmc.py), with torch.randn / torch.rand_like replaced by the case's recorded draws."""
+    from sde_sampler.additions.mcmc import heuristics_step_size, mala_step
+    from tests.cases import mala_inputs
+    target = build_reference_target(None, case["target"])
+    y_init, noise, unif = mala_inputs(case)
+
+    def target_log_prob_and_grad(y):  # benchmark_utils.py:274-277
+        y_ = torch.autograd.Variable(y.clone(), requires_grad=True)
+        log_prob_y = target.unnorm_log_prob(y_)
+        return log_prob_y.flatten(), torch.autograd.grad(log_prob_y.sum(), y_)[0].detach()
+    step_size = case["step_size"] * torch.ones((y_init.shape[0], 1))
+    y = torch.autograd.Variable(y_init.clone(), requires_grad=True)
+    target_log_prob_y, target_grad_y = target_log_prob_and_grad(y)
+    ys, accs = [], []
+    k = {"i": 0}
+    orig_randn, orig_rand_like = torch.randn, torch.rand_like
+    torch.randn = lambda shape, **kw: noise[k["i"]].clone()
+    torch.rand_like = lambda t, **kw: unif[k["i"]].clone()
+    try:
+        for step_id in range(case["n_warmup"] + case["n_steps"]):
+            k["i"] = step_id
+            y, target_log_prob_y, target_grad_y, log_acc = mala_step(
+                y=y, target_log_prob_y=target_log_prob_y, target_grad_y=target_grad_y,
+                target_log_prob_and_grad=target_log_prob_and_grad, step_size=step_size)
+            step_size = heuristics_step_size(step_size, log_acc)
+            accs.append(log_acc.detach().clone())
+            if step_id >= case["n_warmup"]:
+                ys.append(y.detach().clone())
+    finally:
+        torch.randn, torch.rand_like = orig_randn, orig_rand_like
+    return {"ys": torch.stack(ys), "step_size": step_size.detach().clone(), "log_acc": torch.stack(accs)}
+
+
 def main(argv):
     from tests.cases import CASES
     import_reference()
     os.makedirs(os.path.join(REPO, "tests", "golden"), exist_ok=True)
+    if argv and argv[0] == "--mala":  # python -m oracle.make_golden --mala [case ...]
+        from tests.cases import MALA_CASES
+        for name in argv[1:] or list(MALA_CASES):
+            out = run_reference_mala(MALA_CASES[name]())
+            out["torch_version"] = str(torch.__version__)
+            path = os.path.join(REPO, "tests", "golden", name + ".pt")
+            torch.save(out, path)
+            acc = torch.exp(out["log_acc"].clamp(max=0)).mean().item()
+            print(f"{name:24s} ys {tuple(out['ys'].shape)} mean acceptance {acc:.3f} step {out['step_size'].min():.3g}.."
+                  f"{out['step_size'].max():.3g} | {os.path.getsize(path)} B")
+        return
     if argv and argv[0] == "--grads":  # python -m oracle.make_golden --grads [case ...]
         from tests.cases import GRAD_CASES
         for name in argv[1:] or GRAD_CASES:

@@ -27,6 +27,7 @@ MASK = np.uint64(0xFFFFFFFF)
 
 STREAM_NOISE = 0
 STREAM_PRIOR = 1
+STREAM_ACCEPT = 2  # the uniforms of the MALA accept test (lrds_mala): u = ((r0 >> 8) + 1) * 2^-24 of counter (chain, step, 0, 2)
 
 
 def philox4x32_10(c0, c1, c2, c3, k0: int, k1: int):
@@ -67,3 +68,11 @@ def normals(seed: int, B: int, K: int, d: int, particle_offset: int = 0, stream:
     z2, z3 = _box_muller(r2, r3)
     z = np.stack([z0, z1, z2, z3], axis=-1).reshape(K, B, nblk * 4)[:, :, :d]
     return np.ascontiguousarray(z.astype(dtype))
+
+
+def uniforms(seed: int, B: int, K: int, stream: int = STREAM_ACCEPT, dtype=np.float32) -> np.ndarray:
+    """u[K, B] in (0, 1]: the first Philox word of counter (b, k, 0, stream), as the MALA kernel draws them."""
+    k0, k1 = seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF
+    kk, bb = np.meshgrid(np.arange(K, dtype=np.uint32), np.arange(B, dtype=np.uint32), indexing="ij")
+    r0, _, _, _ = philox4x32_10(bb, kk, np.zeros_like(bb), np.full_like(bb, stream), k0, k1)
+    return ((r0 >> np.uint32(8)).astype(np.float64) + 1.0).astype(dtype) * dtype(2.0 ** -24)

@@ -786,3 +786,48 @@ def lv_loss_and_grads(problem: dict, x0: torch.Tensor, noise: torch.Tensor, max_
     names = list(ctrl["sd"])
     grads = torch.autograd.grad(loss, [ctrl["sd"][k] for k in names], allow_unused=True)
     return loss.detach(), {k: (g if g is not None else torch.zeros_like(ctrl["sd"][k])) for k, g in zip(names, grads)}, rnd.detach()
+
+
+# --------------------------------------------------------------------------------------
+# MCMC: sde_sampler/additions/mcmc.py, experiments/benchmark_utils.py:268-333
+# --------------------------------------------------------------------------------------
+
+
+def heuristics_step_size(stepsize, log_acc, target_acceptance=0.75, factor=1.01, tol=0.05):
+    """additions/mcmc.py:54-72 (stepsize (C, 1), log_acc (C,))."""
+    up = (log_acc - math.log(target_acceptance) > math.log1p(tol)).view(-1, 1)
+    stepsize = torch.where(up, stepsize * factor, stepsize)
+    down = (math.log(target_acceptance) - log_acc > -math.log1p(-tol)).view(-1, 1)
+    return torch.where(down, stepsize / factor, stepsize)
+
+
+def mala_chains(target: dict, y_init, step_size: float, n_warmup: int, n_steps: int, noise, unif, adapt=True,
+                dtype=torch.float32):
+    """The loop of mcmc_sample(mcmc_type='mala') (experiments/benchmark_utils.py:268-333) around mala_step
+    (additions/mcmc.py:75-134) on recorded draws: noise [S, C, d] for the proposals, unif [S, C] for the accept test.
+    The reference differentiates unnorm_log_prob by autograd; the score restated above is the same function.
+    Returns (ys [n_steps, C, d], step_size (C, 1), log_acc [S, C])."""
+    logp_fn, score_fn = make_target(_cast(target, dtype))
+    y = y_init.to(dtype).clone()
+    h = step_size * torch.ones((y.shape[0], 1), dtype=dtype)
+    logp, grad = logp_fn(y).flatten(), score_fn(y)
+    ys, accs = [], []
+    with torch.no_grad():
+        for k in range(n_warmup + n_steps):
+            mean = y + h * grad
+            var = 2.0 * h
+            y_prop = torch.sqrt(var) * noise[k].to(dtype) + mean
+            logp_p, grad_p = logp_fn(y_prop).flatten(), score_fn(y_prop)
+            joint_prop = logp_p - (-0.5 * torch.sum(torch.square(y_prop - mean), dim=-1)) / var.flatten()
+            joint_orig = logp - (-0.5 * torch.sum(torch.square(y - (y_prop + h * grad_p)), dim=-1)) / var.flatten()
+            log_acc = joint_prop - joint_orig
+            mask = torch.log(unif[k].to(dtype)) < log_acc
+            y = torch.where(mask.view(-1, 1), y_prop, y)
+            grad = torch.where(mask.view(-1, 1), grad_p, grad)
+            logp = torch.where(mask, logp_p, logp)
+            if adapt:
+                h = heuristics_step_size(h, log_acc)
+            accs.append(log_acc)
+            if k >= n_warmup:
+                ys.append(y.clone())
+    return torch.stack(ys), h, torch.stack(accs)

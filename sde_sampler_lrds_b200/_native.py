@@ -75,7 +75,7 @@ class Spec(C.Structure):
 
 EXPORTS = ["lrds_rollout", "lrds_tc_image_bytes", "lrds_gmm_mix_tc_bytes", "lrds_pack_gmm_mix_tc", "lrds_logreg_tc_bytes",
            "lrds_pack_logreg_tc", "lrds_pack_mlp_tc", "lrds_estimator_blocks", "lrds_estimator_partials", "lrds_estimator_merge", "lrds_ctrl_forward",
-           "lrds_distr_eval", "lrds_axpy_step", "lrds_normals", "lrds_last_error", "lrds_abi_version",
+           "lrds_distr_eval", "lrds_axpy_step", "lrds_normals", "lrds_mala", "lrds_last_error", "lrds_abi_version",
            "lrds_launch_count"]
 
 COMPILE_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
@@ -147,6 +147,8 @@ def lib():
                 L.lrds_ctrl_forward.argtypes = [C.POINTER(Spec), C.c_int32, FP, C.c_int32, FP, FP]
                 L.lrds_distr_eval.argtypes = [C.POINTER(Distr), C.c_int32, FP, C.c_int32, FP, FP, FP]
                 L.lrds_axpy_step.argtypes = [FP, FP, FP, C.c_float, C.c_float, C.c_float, FP, C.c_int64, FP]
+                L.lrds_mala.argtypes = [C.POINTER(Distr), C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, FP, FP, FP, FP,
+                                        C.c_uint64, FP, FP, FP]
                 L.lrds_normals.argtypes = [C.c_uint64, C.c_uint64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, FP, FP]
                 if L.lrds_abi_version() != ABI_VERSION:
                     raise RuntimeError("liblrds_b200.so ABI version mismatch; rebuild")

@@ -163,6 +163,28 @@ def _resolve(cfg: dict):
     return cfg
 
 
+def mcmc_sample(device, target, x_init, mcmc_type="mala", step_size=1e-3, n_chains_per_mode=4, dataset_length=50000,
+                n_warmup_steps=512, skip_chain_per_mode=False, target_log_prob_and_grad=None, adapt_step_size=True,
+                shuffle=True, verbose=False, seed=None):
+    """experiments/benchmark_utils.py:268-333 with the chain loop in one kernel launch (additions/mcmc.py).  Returns the
+    [n_mcmc_steps * n_chains, d] dataset on the CPU like the reference."""
+    from .additions.mcmc import mala_chains
+    if mcmc_type != "mala":
+        raise NotImplementedError("only the MALA sampler has a kernel (the shipped experiments use mcmc_type='mala')")
+    if target_log_prob_and_grad is not None:
+        raise NotImplementedError("a custom target_log_prob_and_grad cannot run inside the kernel; pass a Distribution")
+    x_init = x_init.to(device)
+    if skip_chain_per_mode:
+        y_init = x_init.clone()
+    else:
+        y_init = torch.concat([x_init[i].unsqueeze(0).expand((n_chains_per_mode, -1)) for i in range(x_init.shape[0])], dim=0)
+    n_chains = y_init.shape[0]
+    n_mcmc_steps = int(dataset_length / n_chains)
+    ys, _ = mala_chains(target, y_init, step_size, n_warmup_steps, n_mcmc_steps, adapt_step_size=adapt_step_size, seed=seed)
+    ret = ys.cpu().view((-1, *x_init.shape[1:]))
+    return ret[torch.randperm(ret.shape[0])] if shuffle else ret
+
+
 def make_model(solver_type, ref_type, loss_type, integrator_type, model_type, time_type, solver_details, target_details,
                training_details, optim_details=None, n_steps=100, force_base_zero_init=False, use_ema=False,
                force_vp20=False, force_vp_cosine=False, compute_samples_based_metrics=True, force_T_cosine=None,

@@ -312,6 +312,110 @@ __global__ void __launch_bounds__(128) distr_eval_kernel(const lrds_spec s, cons
   }
 }
 
+// ---- MALA chains: the whole loop of mcmc_sample(mcmc_type='mala') (experiments/benchmark_utils.py:268-333) around
+// mala_step and heuristics_step_size (sde_sampler/additions/mcmc.py:75-134, 54-72) in one launch, one thread per chain.
+// Columns: x = proposal, us = current state, tsd = score at the current state, db = score at the proposal.
+struct MalaArgs {
+  const float* y0;      // [C][d]
+  float* step_size;     // [C] in / out
+  const float* noise;   // [S][C][d] standard normals or NULL (Philox stream 0)
+  const float* unif;    // [S][C] uniforms in (0, 1] or NULL (Philox stream 2)
+  uint64_t seed;
+  float* ys;            // [n_steps][C][d] states after the warm-up
+  float* log_acc;       // [S][C] or NULL
+  int n_warmup, n_steps, adapt;
+  float log_target, up_thr, down_thr, factor;  // log(0.75), log1p(tol), -log1p(-tol), 1.01
+};
+
+__global__ void __launch_bounds__(128) mala_kernel(const lrds_spec s, const MalaArgs m) {
+  using namespace lrds;
+  extern __shared__ float smem[];
+  const int NT = blockDim.x, tid = threadIdx.x;
+  const int b_raw = blockIdx.x * NT + tid;
+  const bool live = b_raw < s.B;
+  const int b = live ? b_raw : s.B - 1;
+  const ColLayout L = col_layout(s);
+  const Particle P = make_particle(smem, L, NT, tid);
+  const GmmView tv0 = gmm_at(s.target.gmm, 0);
+  const int d = s.d, dp = s.mlp.d_pad, kind = s.target.kind;
+  const RolloutArgs na{s, nullptr, m.noise, m.seed, 0, nullptr, nullptr, nullptr};
+  // log-density and score at P.x; the score goes to column `out`
+  auto eval = [&](const Col& out) -> float {
+    const float lp = target_pass1<false>(s, kind, tv0, P, true);
+    float xm = 0.f;
+    for (int j0 = 0; j0 < dp; j0 += JC) {
+      float xr[JC], ts[JC];
+      load_chunk(P.x, j0, xr);
+      const float xp = (j0 + JC < dp) ? P.x(j0 + JC) : 0.f;
+      target_score_chunk<false>(s, kind, tv0, P, xr, xm, xp, j0, ts);
+      xm = xr[JC - 1];
+#pragma unroll
+      for (int c = 0; c < JC; ++c) out(j0 + c) = (j0 + c < d) ? ts[c] : 0.f;
+    }
+    return lp;
+  };
+  for (int j = 0; j < dp; ++j) {
+    const float v = (j < d) ? __ldg(m.y0 + (int64_t)b * d + j) : 0.f;
+    P.x(j) = v;
+    P.us(j) = v;
+  }
+  float logp = eval(P.tsd);
+  float h = __ldg(m.step_size + b);
+  const int S = m.n_warmup + m.n_steps;
+  for (int step = 0; step < S; ++step) {
+    // proposal y' = sqrt(2 h) z + (y + h grad)   (mcmc.py:8-14, 98-102)
+    const float var = 2.0f * h, sq = sqrtf(var);
+    float fwd = 0.f;
+    for (int j0 = 0; j0 < dp; j0 += JC) {
+      float z[JC];
+      noise_chunk(na, step, b, j0, z);
+#pragma unroll
+      for (int c = 0; c < JC; ++c) {
+        const int j = j0 + c;
+        const float mean = P.us(j) + h * P.tsd(j);
+        const float yp = (j < d) ? sq * z[c] + mean : 0.f;
+        P.x(j) = yp;
+        const float df = yp - mean;
+        fwd += df * df;
+      }
+    }
+    const float logp_p = eval(P.db);
+    float bwd = 0.f;
+    for (int j = 0; j < d; ++j) {
+      const float df = P.us(j) - (P.x(j) + h * P.db(j));
+      bwd += df * df;
+    }
+    // joint_prop - joint_orig with the unnormalised Gaussian log-densities of mcmc.py:17-31
+    const float log_acc = (logp_p - (-0.5f * fwd) / var) - (logp - (-0.5f * bwd) / var);
+    float u;
+    if (m.unif != nullptr) {
+      u = __ldg(m.unif + (int64_t)step * s.B + b);
+    } else {
+      uint32_t r[4];
+      philox4x32_10((uint32_t)b, (uint32_t)step, 0u, 2u, (uint32_t)m.seed, (uint32_t)(m.seed >> 32), r);
+      u = (float)((r[0] >> 8) + 1u) * 5.9604644775390625e-08f;
+    }
+    if (logf(u) < log_acc) {  // mcmc.py:121-124
+      for (int j = 0; j < dp; ++j) {
+        P.us(j) = P.x(j);
+        P.tsd(j) = P.db(j);
+      }
+      logp = logp_p;
+    }
+    if (m.adapt) {  // heuristics_step_size, mcmc.py:54-72 (both tests read the same log_acc)
+      const float h0 = h;
+      if (log_acc - m.log_target > m.up_thr) h = h0 * m.factor;
+      if (m.log_target - log_acc > m.down_thr) h = h / m.factor;
+    }
+    if (live && m.log_acc != nullptr) m.log_acc[(int64_t)step * s.B + b] = log_acc;
+    if (live && step >= m.n_warmup) {
+      float* out = m.ys + ((int64_t)(step - m.n_warmup) * s.B + b) * d;
+      for (int j = 0; j < d; ++j) out[j] = P.us(j);
+    }
+  }
+  if (live) m.step_size[b] = h;
+}
+
 __global__ void axpy_step_kernel(const float* __restrict__ x, const float* __restrict__ s, const float* __restrict__ z,
                                  float a, float b, float c, float* __restrict__ out, int64_t n) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -545,6 +649,47 @@ int lrds_ctrl_forward(const lrds_spec* spec, int32_t row, const float* x, int32_
 int lrds_distr_eval(const lrds_distr* distr, int32_t d, const float* x, int32_t B, float* logp_out, float* score_out,
                     void* stream) {
   return distr_eval_launch(distr, d, x, B, logp_out, score_out, 0.f, (cudaStream_t)stream);
+}
+
+int lrds_mala(const lrds_distr* target, int32_t d, int32_t C, int32_t n_warmup, int32_t n_steps, int32_t adapt,
+              const float* y0, float* step_size, const float* noise, const float* unif, uint64_t seed, float* ys_out,
+              float* log_acc_out, void* stream) {
+  if (!target || !y0 || !step_size || !ys_out || d < 1 || C < 1 || n_warmup < 0 || n_steps < 1)
+    return fail(LRDS_ERR_INVALID, "mala: bad arguments");
+  lrds_spec s;
+  memset(&s, 0, sizeof(s));
+  s.abi_version = LRDS_ABI_VERSION;
+  s.B = C;
+  s.d = d;
+  s.mlp.d = d;
+  s.mlp.d_pad = ((d + 7) / 8) * 8;
+  s.target = *target;
+  s.ctrl_kind = LRDS_CTRL_CLIPPED;
+  s.kind = LRDS_ROLLOUT_CMCD;  // column layout with the three extra per-chain vectors (current state, two scores)
+  if (target->kind == LRDS_DISTR_GMM) {
+    if (int r = validate_gmm(target->gmm, "target")) return r;
+  } else if (target->kind == LRDS_DISTR_LOGREG) {
+    if (target->logreg.p + 1 != d) return fail(LRDS_ERR_INVALID, "logreg: d must be p + 1");
+  } else if (target->kind != LRDS_DISTR_PHI4) {
+    return fail(LRDS_ERR_UNSUPPORTED, "mala: unknown distribution kind");
+  }
+  const lrds::ColLayout L = lrds::col_layout(s);
+  int nt = 0;
+  size_t smem = 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (int r = launch_cols(mala_kernel, s, L.total, st, &nt, &smem)) return r;
+  if (nt > 32) {  // few chains, long loops: one warp per CTA spreads the chains over the SMs
+    nt = 32;
+    smem = (size_t)L.total * nt * sizeof(float);
+  }
+  const float tol = 0.05f, target_acc = 0.75f;
+  MalaArgs m{y0, step_size, noise, unif, seed, ys_out, log_acc_out, n_warmup, n_steps, adapt,
+             logf(target_acc), log1pf(tol), -log1pf(-tol), 1.01f};
+  mala_kernel<<<(C + nt - 1) / nt, nt, smem, st>>>(s, m);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "mala launch");
+  g_launches.fetch_add(1);
+  return LRDS_OK;
 }
 
 int lrds_axpy_step(const float* x, const float* s, const float* z, float a, float b, float c, float* out, int64_t n,

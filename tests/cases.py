@@ -404,6 +404,37 @@ GRAD_CASES = ["em_two_modes_score", "ei_many_modes", "ddpm_snr", "ei_phi4_gmm", 
               "dds_phi4_ito", "dis_many_modes_ito", "pis_logreg", "dis_many_modes_lerp", "dis_many_modes_langevin"]
 
 
+def case_mala(target="many_modes"):
+    """MALA chains as mcmc_sample starts them (experiments/benchmark_utils.py:268-333): n_chains_per_mode copies of
+    every initial point, per-chain adaptive step size; short runs so that the CPU oracle finishes in seconds."""
+    if target == "many_modes":
+        tgt = many_modes(7, 10)
+        x_init, per_mode, h = tgt["loc"].clone(), 4, 0.15
+    elif target == "phi4":
+        tgt = phi4(24)
+        x_init, per_mode, h = torch.stack([torch.ones(24), -torch.ones(24), torch.zeros(24)]), 6, 4e-3
+    else:
+        tgt = logreg_synthetic(166, 60)
+        x_init, per_mode, h = torch.zeros(1, 61), 20, 2e-3
+    return {"target": tgt, "x_init": x_init, "n_chains_per_mode": per_mode, "step_size": h, "n_warmup": 15, "n_steps": 45,
+            "seed": 300 + len(target)}
+
+
+MALA_CASES = {"mala_many_modes": lambda: case_mala("many_modes"), "mala_phi4": lambda: case_mala("phi4"),
+              "mala_logreg": lambda: case_mala("logreg")}
+
+
+def mala_inputs(case: dict):
+    """(y_init [C, d], noise [S, C, d], unif [S, C]) of a MALA case, from the Philox spec of oracle/philox_ref.py."""
+    from oracle import philox_ref
+    y_init = case["x_init"].repeat_interleave(case["n_chains_per_mode"], dim=0)
+    C, d = y_init.shape
+    S = case["n_warmup"] + case["n_steps"]
+    noise = torch.from_numpy(philox_ref.normals(case["seed"], C, S, d))
+    unif = torch.from_numpy(philox_ref.uniforms(case["seed"], C, S))
+    return y_init, noise, unif
+
+
 def initial_state(case: dict, dtype=torch.float32):
     """x0 for the case: prior samples for a generative rollout (drawn with the Philox stream 1 of
     oracle.philox_ref so that no torch-generator state is involved), target-shaped samples for EUBO."""
