@@ -14,8 +14,6 @@ from oracle import rollout_oracle as O
 from tests.cases import MALA_CASES, mala_inputs
 
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
-# removed once the kernel has been run on a B200 (the pod had no free GPU slot when it was written)
-UNVERIFIED = pytest.mark.skipif(not os.environ.get("LRDS_TEST_MALA_GPU"), reason="lrds_mala not yet run on a GPU")
 
 
 def chains_within(got, want, tol=1e-4):
@@ -36,7 +34,6 @@ def test_oracle_mala_matches_reference_golden(name):
     assert ((h - gold["step_size"]).abs() <= 1e-6 * gold["step_size"]).float().mean() >= 0.9
 
 
-@UNVERIFIED
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", list(MALA_CASES))
 def test_mala_kernel_matches_oracle_and_reference(name, device):
@@ -59,7 +56,6 @@ def test_mala_kernel_matches_oracle_and_reference(name, device):
     assert ((acc[0].cpu() - gold["log_acc"][0]).abs() <= 1e-3 * gold["log_acc"][0].abs().clamp(min=1.0)).all()
 
 
-@UNVERIFIED
 @pytest.mark.gpu
 def test_mala_in_kernel_draws_follow_the_philox_spec(device):
     """Production mode (in-kernel Philox normals and uniforms) equals validation mode fed with oracle/philox_ref.py's
@@ -81,7 +77,6 @@ def test_mala_in_kernel_draws_follow_the_philox_spec(device):
     assert f >= 0.9, (f, worst)
 
 
-@UNVERIFIED
 @pytest.mark.gpu
 def test_mcmc_sample_api(device):
     """mcmc_sample with the reference's signature: dataset of dataset_length rows on the CPU, chains that stay near
