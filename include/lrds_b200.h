@@ -194,7 +194,9 @@ typedef struct {
   int32_t init_cost;   /* LINEAR (simulate only): 0 = rnd starts at 0 and ends with + reference_log_prob(x_T), ref_0 being the
                         * reference (RDS / PIS / DDS: oc.py:245, 290, 1389); 1 = rnd starts at initial_log_prob(x_0) + rnd_offset,
                         * ref_0 being the PRIOR, and ends with the target term alone (DIS: TimeReversalLoss.simulate,
-                        * oc.py:1164-1168, 1230) */
+                        * oc.py:1164-1168, 1230; DiscreteTimeReversalLossEI.simulate, oc.py:925-973).  EUBO_LINEAR with
+                        * init_cost = DiscreteTimeReversalLossEI.compute_eubo (oc.py:980-1036): no reference control, rnd
+                        * starts at -target(x) and ends with + initial_log_prob(x) at the noised state */
   float rnd_offset;    /* init_cost: state-independent part of the log-weight, -sum_k sde.drift_div_int(s_k, t_k, x)
                         * (OU.drift_div_int = d * int_drift_coeff_t, eq/sdes.py:137-141; oc.py:1217-1218, train=False) */
   const float* steps;  /* per-step table, LRDS_STEP_STRIDE floats per row */

@@ -188,6 +188,17 @@ def run_reference(case, grads=False):
                 x, rnd, xs = loss.simulate(ts, x0, target_logp, prior.log_prob,
                                            compute_ito_int=case.get("compute_ito_int", True), return_traj=True)
                 out = {"x_T": x, "rnd": rnd, "xs_mid": xs[len(xs) // 2]}
+        elif method == "dis_ei":  # DiscreteTimeReversalLossEI, oc.py:897-1103 (no config instantiates it; same objects as DIS)
+            sde = build_reference_sde(p["sde"])
+            prior = IsotropicGauss(dim=d, loc=p["ref"]["loc"], scale=p["ref"]["scale"])
+            loss = oc.DiscreteTimeReversalLossEI(sde=sde, **kw)
+            if grads:
+                out = train(loss, prior.log_prob)
+            elif case.get("eubo"):
+                out = {"rnd": loss.compute_eubo(ts, x0.clone(), target_logp, prior.log_prob)}
+            else:
+                x, rnd, xs = loss.simulate(ts, x0, target_logp, initial_log_prob=prior.log_prob, train=False, return_traj=True)
+                out = {"x_T": x, "rnd": rnd, "xs_mid": xs[len(xs) // 2]}
         elif method == "dis":  # solver/oc.py:185-262 (Bridge, inference_ctrl=None), eval = TimeReversalLoss.eval, oc.py:1274-1307
             sde = build_reference_sde(p["sde"])
             prior = IsotropicGauss(dim=d, loc=p["ref"]["loc"], scale=p["ref"]["scale"])

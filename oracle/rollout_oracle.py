@@ -522,6 +522,43 @@ def simulate_dis(ts, x, noise, ctrl, sde, terminal_unnorm_log_prob, initial_log_
     return x, rnd, (torch.stack(xs) if return_traj else None)
 
 
+def simulate_dis_ei(ts, x, noise, ctrl, sde, terminal_unnorm_log_prob, initial_log_prob, return_traj=False, lv=False):
+    """DiscreteTimeReversalLossEI.simulate, losses/oc.py:906-978 (eval: train=False; the lv training form starts at the
+    prior log-density as well, 925-929)."""
+    rnd = initial_log_prob(x)
+    T = ts[-1]
+    xs = [x] if return_traj else None
+    for k, (s, t) in enumerate(zip(ts[:-1], ts[1:])):
+        g = ctrl(T - s, x)
+        u, cost = _running_cost(g, lv)
+        rnd = rnd + (sde.omega(s, t) * cost if lv else 0.5 * sde.omega(s, t) * (g ** 2).sum(dim=-1, keepdim=True))
+        z = noise[k]
+        x = sde.ei_step(x, s, t, u, z)
+        rnd = rnd + torch.sqrt(sde.omega(s, t)) * (g * z).sum(dim=-1, keepdim=True)
+        if return_traj:
+            xs.append(x)
+    rnd = rnd - terminal_unnorm_log_prob(x)
+    return x, rnd, (torch.stack(xs) if return_traj else None)
+
+
+def eubo_dis_ei(ts, x, noise, ctrl, sde, terminal_unnorm_log_prob, initial_log_prob):
+    """DiscreteTimeReversalLossEI.compute_eubo, losses/oc.py:980-1036."""
+    x = x.clone()
+    rnd = -terminal_unnorm_log_prob(x)
+    T = ts[-1]
+    times_s, times_t = ts[:-1].flip((0,)), ts[1:].flip((0,))
+    mean_factors, var_factors = sde.transition_params(T - times_t, T - times_s)
+    std_factors = var_factors.sqrt()
+    for i, (s, t) in enumerate(zip(times_s, times_t)):
+        z = noise[i]
+        x = x * mean_factors[i]
+        x = x + std_factors[i] * z
+        g = ctrl(T - s, x)
+        rnd = rnd - (0.5 * g ** 2).sum(dim=-1, keepdim=True) * sde.omega(s, t)
+        rnd = rnd - (g * z).sum(dim=-1, keepdim=True) * torch.sqrt(sde.omega(s, t))
+    return rnd + initial_log_prob(x)
+
+
 def langevin_drift(t, x, target_score, prior_score, diff, T, clip_score):
     """ControlledLangevinSDE.drift, sde_sampler/eq/sdes.py:101-110."""
     drift = target_score(x) * (t / T) + prior_score(x) * (1.0 - t / T)
@@ -742,6 +779,12 @@ def rollout(problem: dict, x0: torch.Tensor, noise: torch.Tensor, *, eubo: bool 
                 return simulate_em(ts, x0, noise, ctrl, sde, ref_ctrl, target_logp, ref_logp, return_traj, lv=lv)
             return simulate_ei(ts, x0, noise, ctrl, sde, ref_ctrl, target_logp, ref_logp, return_traj,
                                ddpm=(method == "ddpm"), lv=lv)
+        if method == "dis_ei":  # the discrete-time DIS loss; prior as for DIS
+            sde = make_sde(problem["sde"], dtype)
+            _, prior_logp = make_reference(problem["ref"], None)
+            if eubo:
+                return eubo_dis_ei(ts, x0, noise, ctrl, sde, target_logp, prior_logp)
+            return simulate_dis_ei(ts, x0, noise, ctrl, sde, target_logp, prior_logp, return_traj, lv=lv)
         if method == "dis":  # prior = IsotropicGauss (conf/prior/gauss.yaml), scale = sde.scale_diff_coeff (conf/solver/dis.yaml)
             sde = make_sde(problem["sde"], dtype)
             _, prior_logp = make_reference(problem["ref"], None)

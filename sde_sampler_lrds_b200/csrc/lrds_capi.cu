@@ -506,7 +506,8 @@ int lrds_rollout(const lrds_spec* spec, const float* x0, const float* noise, uin
   if (s.K < 1) return fail(LRDS_ERR_INVALID, "K must be >= 1");
   if (int r = validate_gmm(s.ref_0, "ref_0")) return r;
   const bool linear = s.kind == LRDS_ROLLOUT_LINEAR || s.kind == LRDS_ROLLOUT_EUBO_LINEAR;
-  if (s.kind == LRDS_ROLLOUT_EUBO_LINEAR && !s.has_ref_ctrl) return fail(LRDS_ERR_INVALID, "compute_eubo needs a reference control");
+  if (s.kind == LRDS_ROLLOUT_EUBO_LINEAR && !s.has_ref_ctrl && !s.init_cost)
+    return fail(LRDS_ERR_INVALID, "compute_eubo needs a reference control (or init_cost: the discrete-time DIS loss)");
   if (s.ctrl_kind >= LRDS_CTRL_CANCEL_DRIFT && s.kind != LRDS_ROLLOUT_LINEAR)
     return fail(LRDS_ERR_UNSUPPORTED, "CancelDriftCtrl / LerpCtrl are built for the LINEAR simulate loop (DIS) only");
   if (linear && s.has_ref_ctrl)
@@ -515,8 +516,10 @@ int lrds_rollout(const lrds_spec* spec, const float* x0, const float* noise, uin
   if (!linear && s.target.kind == LRDS_DISTR_NONE) return fail(LRDS_ERR_INVALID, "CMCD needs a target");
   cudaStream_t st = (cudaStream_t)stream;
   lrds::RolloutArgs a{s, x0, noise, seed, particle_offset, x_out, rnd_out, traj_out};
-  if (s.init_cost) {  // DIS (oc.py:1164-1168): rnd_out = initial_log_prob(x_0) + rnd_offset; the rollout kernel adds it
-    if (s.kind != LRDS_ROLLOUT_LINEAR) return fail(LRDS_ERR_INVALID, "init_cost is defined for the LINEAR simulate loop only");
+  if (s.init_cost && !linear) return fail(LRDS_ERR_INVALID, "init_cost is defined for the LINEAR loops only");
+  if (s.init_cost && s.kind == LRDS_ROLLOUT_EUBO_LINEAR && (s.has_ref_ctrl || s.update_form != LRDS_UPDATE_AXPY))
+    return fail(LRDS_ERR_UNSUPPORTED, "init_cost compute_eubo is the discrete-time DIS loss: no reference control, axpy update");
+  if (s.init_cost && s.kind == LRDS_ROLLOUT_LINEAR) {  // DIS (oc.py:929, 1164-1168): rnd_out = initial_log_prob(x_0) + rnd_offset
     lrds_distr prior;
     memset(&prior, 0, sizeof(prior));
     prior.kind = LRDS_DISTR_GMM;

@@ -437,8 +437,9 @@ __device__ __forceinline__ void rollout_body(const RolloutArgs& a, float* smem, 
   }
 
   if constexpr (KIND == LRDS_ROLLOUT_EUBO_LINEAR) {
-    {  // rnd = reference_log_prob(x) - terminal_unnorm_log_prob(x)   (oc.py:321, 536)
-      const float lref = gmm_pass1<PIPE>(gmm_at(s.ref_0, 0), d, dp, P.x, P.rr);
+    {  // rnd = reference_log_prob(x) - terminal_unnorm_log_prob(x)   (oc.py:321, 536); init_cost (the discrete-time
+       // DIS loss, oc.py:1000-1033): ref_0 is the prior and enters at the END of the noising rollout instead
+      const float lref = s.init_cost ? 0.f : gmm_pass1<PIPE>(gmm_at(s.ref_0, 0), d, dp, P.x, P.rr);
       const float ltgt = clipf(target_pass1<PIPE>(s, tkind, tv0, P, true), s.clip_target);
       rnd = lref - ltgt;
     }
@@ -458,8 +459,11 @@ __device__ __forceinline__ void rollout_body(const RolloutArgs& a, float* smem, 
         }
       }
       if (score_ctrl) target_pass1<PIPE>(s, tkind, tv0, P, false);
-      const GmmView rv = gmm_at(s.ref_t, k);
-      if (rv.M > 1) gmm_pass1<PIPE>(rv, d, dp, P.x, P.rr);
+      GmmView rv{};
+      if (has_ref) {
+        rv = gmm_at(s.ref_t, k);
+        if (rv.M > 1) gmm_pass1<PIPE>(rv, d, dp, P.x, P.rr);
+      }
       mlp.template hidden<false>(row + LRDS_STEP_BIAS1, P.x);
       float cost = 0.f, gx = 0.f, gz = 0.f, xm = 0.f;
       for (int j0 = 0; j0 < dp; j0 += JC) {
@@ -468,7 +472,12 @@ __device__ __forceinline__ void rollout_body(const RolloutArgs& a, float* smem, 
         const float xp = (need_nbr && j0 + JC < dp) ? P.x(j0 + JC) : 0.f;
         if (score_ctrl) target_score_chunk<PIPE>(s, tkind, tv0, P, xr, xm, xp, j0, ts);
         ctrl_chunk(cc, mlp, j0, ts, gamma, u);
-        gmm_score_chunk<PIPE>(rv, d, dp, xr, P.rr, j0, rs);
+        if (has_ref) {
+          gmm_score_chunk<PIPE>(rv, d, dp, xr, P.rr, j0, rs);
+        } else {
+#pragma unroll
+          for (int c = 0; c < JC; ++c) rs[c] = 0.f;
+        }
 #pragma unroll
         for (int c = 0; c < JC; ++c) {
           const float g = (s.update_form == LRDS_UPDATE_EM) ? u[c] / sig : u[c];
@@ -482,6 +491,7 @@ __device__ __forceinline__ void rollout_body(const RolloutArgs& a, float* smem, 
       if (s.update_form == LRDS_UPDATE_EM) rnd += gx * wx;
       rnd -= gz * wito;
     }
+    if (s.init_cost) rnd += gmm_pass1<PIPE>(gmm_at(s.ref_0, 0), d, dp, P.x, P.rr);  // + initial_log_prob(x), oc.py:1033
   }
 
   if constexpr (KIND == LRDS_ROLLOUT_CMCD || KIND == LRDS_ROLLOUT_EUBO_CMCD) {

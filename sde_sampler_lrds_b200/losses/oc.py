@@ -8,6 +8,7 @@ signatures (sde_sampler/losses/oc.py): ``simulate`` / ``eval`` / ``compute_eubo`
     ControlledLangevinSDELoss     oc.py:654-894   (CMCD)
     ExponentialIntegratorSDELoss  oc.py:1310-1467 (DDS)
     TimeReversalLoss              oc.py:1105-1307 (DIS: inference_ctrl=None)
+    DiscreteTimeReversalLossEI    oc.py:897-1103  (discrete-time DIS with the exponential integrator)
 
 Extra keyword arguments (not in the reference, all optional): ``noise`` = recorded standard normals [K, B, d]
 to consume instead of in-kernel Philox draws (validation mode), ``seed`` / ``particle_offset`` for the
@@ -184,6 +185,7 @@ class EMReferenceSDELoss(BaseOCLoss):
     """RDS loss with the Euler-Maruyama integrator (also PIS when ``reference_ctrl`` is None)."""
 
     _variant = "em"
+    _init_cost = False  # DiscreteTimeReversalLossEI: the second log-density is the PRIOR, taken at the start of the rollout
 
     def __init__(self, *args, reference_ctrl: Callable | None = None, use_rescaling: bool = True, **kwargs):
         super().__init__(*args, **kwargs)
@@ -212,10 +214,10 @@ class EMReferenceSDELoss(BaseOCLoss):
         info = self._ctrl(use_ema)
         ref = _resolve_reference(self.reference_ctrl)
         ref0, _ = pack.resolve_log_prob(reference_log_prob)
-        key = self._key((self._variant, eubo), ts, device, info, (id(ref), id(ref0), id(terminal_unnorm_log_prob)))
+        key = self._key((self._variant, eubo, self._init_cost), ts, device, info, (id(ref), id(ref0), id(terminal_unnorm_log_prob)))
 
         def build():
-            if eubo and ref is None:
+            if eubo and ref is None and not self._init_cost:
                 raise NotImplementedError("compute_eubo needs a reference control (the reference calls it unconditionally)")
             sde = self.sde.host()
             tsc, pairs = pack._scalar_rows(ts)
@@ -232,6 +234,7 @@ class EMReferenceSDELoss(BaseOCLoss):
             spec.update_form = N.UPDATE_EM if em_formulas else N.UPDATE_AXPY
             spec.ito_form = N.ITO_EM if self._variant == "em" else N.ITO_SCALED
             spec.has_ref_ctrl = int(ref is not None)
+            spec.init_cost = int(self._init_cost)
             table = torch.zeros(K, N.STEP_STRIDE)
             if not eubo:
                 taus = T - tsc[:-1]
@@ -319,6 +322,39 @@ class DDPMLikeReferenceSDELoss(EMReferenceSDELoss):
         kwargs.pop("use_rescaling", None)
         super().__init__(*args, reference_ctrl=reference_ctrl, use_rescaling=False, **kwargs)
 
+
+
+class DiscreteTimeReversalLossEI(EIReferenceSDELoss):
+    """Discrete-time DIS loss (Appendix D.4 of the paper; oc.py:897-1103): the exponential-integrator rollout of
+    EIReferenceSDELoss without a reference control, the log-weight starting at the prior log-density
+    (``initial_log_prob(x_0)``) instead of ending with a reference term; ``compute_eubo`` (980-1036) ends with the
+    prior log-density at the noised state."""
+
+    _init_cost = True
+
+    def __init__(self, *args, **kwargs):
+        kwargs.pop("reference_ctrl", None)
+        super().__init__(*args, reference_ctrl=None, **kwargs)
+
+    def __call__(self, ts, x, terminal_unnorm_log_prob, initial_log_prob=None, **kw):
+        return super().__call__(ts, x, terminal_unnorm_log_prob, initial_log_prob, **kw)
+
+    def simulate(self, ts, x, terminal_unnorm_log_prob, initial_log_prob=None, train: bool = True,
+                 change_sde_ctrl: bool = False, return_traj: bool = False, use_ema: bool = False, **kw):
+        if train and self.method in ["kl", "kl_ito"]:
+            raise NotImplementedError("the kl training rollout starts the log-weight at 0 (oc.py:926-927) and is "
+                                      "differentiated through the trajectory: not built (SURVEY.md 8f item 1)")
+        return super().simulate(ts, x, terminal_unnorm_log_prob, initial_log_prob, change_sde_ctrl=change_sde_ctrl,
+                                return_traj=return_traj, use_ema=use_ema, **kw)
+
+    def compute_eubo(self, ts, x, terminal_unnorm_log_prob, initial_log_prob=None, use_ema: bool = False, **kw):
+        return super().compute_eubo(ts, x, terminal_unnorm_log_prob, initial_log_prob, use_ema=use_ema, **kw)
+
+    def eval(self, ts, x, terminal_unnorm_log_prob, initial_log_prob=None, compute_weights: bool = True,
+             return_traj: bool = True, use_ema: bool = True, **kw) -> Results:
+        samples, rnd, xs = self.simulate(ts, x, terminal_unnorm_log_prob, initial_log_prob, train=False,
+                                         return_traj=return_traj, use_ema=use_ema, **kw)
+        return BaseOCLoss.compute_results(rnd, compute_weights=compute_weights, ts=ts, samples=samples, xs=xs)
 
 
 class ExponentialIntegratorSDELoss(BaseOCLoss):

@@ -253,6 +253,21 @@ def case_dis(target="many_modes", compute_ito_int=True, scale=1.0, ctrl_kind="sc
         "B": B, "seed": 120 + len(target), "prior": ("iso", 0.0, scale), "compute_ito_int": compute_ito_int}
 
 
+def case_dis_ei(target="many_modes"):
+    """Discrete-time DIS loss (DiscreteTimeReversalLossEI, losses/oc.py:897-1103): exponential integrator over VP, no
+    reference control, the log-weight starting at the prior log-density."""
+    case = case_dis(target, True)
+    p = case["problem"]
+    p["method"] = "dis_ei"
+    # the time-reversed exponential-integrator step expands x by sqrt(1 + lambda) per step (12x over the horizon) unless the
+    # control holds it: a score factor of the right size (gamma * target score ~ -(x - mu)) keeps the log-weights at
+    # O(10^2), where the absolute 1e-3 bar on log Z is above the float32 resolution
+    d = 10 if target == "many_modes" else 24
+    p["ctrl"] = ctrl(d, "score", seed=34, out_gain=0.3, gamma=0.8 if target == "many_modes" else 0.04)
+    case["seed"] += 40
+    return case
+
+
 def case_ei_phi4_gauss():
     """RDS vp-ref with its default Gaussian reference over the PhiFour lattice (experiments/sample_phi_four_competing.py)."""
     d = 24
@@ -388,6 +403,9 @@ CASES = {
     "dis_many_modes_langevin": lambda: case_dis("many_modes", ctrl_kind="cancel"),
     "dis_phi4_langevin": lambda: case_dis("phi4", False, ctrl_kind="cancel"),
     "dis_logreg_lerp": lambda: case_dis("logreg", ctrl_kind="lerp"),
+    "dis_ei_many_modes": lambda: case_dis_ei("many_modes"),
+    "dis_ei_phi4": lambda: case_dis_ei("phi4"),
+    "eubo_dis_ei_many_modes": lambda: _eubo(case_dis_ei("many_modes"), 207),
     "eubo_em_two_modes": lambda: _eubo(case_em_two_modes("score"), 201),
     "eubo_ei_many_modes": lambda: _eubo(case_ei_many_modes(K=100, B=100), 202),
     "eubo_cmcd_gmm": lambda: _eubo(case_cmcd_gmm(), 203),
@@ -401,7 +419,8 @@ CASES = {
 # cases whose TRAINING objective (method='lv') and parameter gradient are pinned by reference-generated fixtures
 # (tests/golden/grad_<name>.pt, python -m oracle.make_golden --grads)
 GRAD_CASES = ["em_two_modes_score", "ei_many_modes", "ddpm_snr", "ei_phi4_gmm", "pis_many_modes", "dds_many_modes_ito",
-              "dds_phi4_ito", "dis_many_modes_ito", "pis_logreg", "dis_many_modes_lerp", "dis_many_modes_langevin"]
+              "dds_phi4_ito", "dis_many_modes_ito", "pis_logreg", "dis_many_modes_lerp", "dis_many_modes_langevin",
+              "dis_ei_many_modes"]
 
 
 def case_mala(target="many_modes"):

@@ -65,7 +65,7 @@ class Built:
         self.case, self.device = case, device
         self.target = build_target(p["target"], device)
         d = self.target.dim
-        if p["method"] == "dis":  # LerpCtrl interpolates the score of the very prior the rollout starts from
+        if p["method"] in ("dis", "dis_ei"):  # LerpCtrl interpolates the score of the very prior the rollout starts from
             self.prior = IsotropicGauss(dim=d, loc=p["ref"]["loc"], scale=p["ref"]["scale"]).to(device)
         self.ctrl = build_ctrl(p["ctrl"], d, self.target, device, prior=getattr(self, "prior", None))
         self.ts = p["ts"].clone().to(device)
@@ -101,6 +101,11 @@ class Built:
             self.args = (self.target.unnorm_log_prob,)
             self.kwargs = {"initial_log_prob": self.prior.log_prob, "train": False,
                            "compute_ito_int": case.get("compute_ito_int", True)}
+        elif method == "dis_ei":
+            self.sde = build_sde(p["sde"], device)
+            self.loss = oc.DiscreteTimeReversalLossEI(sde=self.sde, **kw)
+            self.args = (self.target.unnorm_log_prob, self.prior.log_prob)
+            self.kwargs = {"train": False}
         elif method == "cmcd":
             pr = p["prior"]
             if pr.get("isotropic"):
