@@ -185,6 +185,31 @@ def mcmc_sample(device, target, x_init, mcmc_type="mala", step_size=1e-3, n_chai
     return ret[torch.randperm(ret.shape[0])] if shuffle else ret
 
 
+def fit_gmm(n_components, dataset, means_init=None, em_type="diag", max_iter=1000):
+    """experiments/benchmark_utils.py:336-365: sklearn's EM over the MCMC data set (host library code in the reference
+    as well), tried over the reference's ladder of ``reg_covar`` values.  Returns (weights, means, variances) as the
+    ``*_ref`` entries of ``solver_details``; only diagonal covariances feed a kernel (full ones: SURVEY.md 8f item 2)."""
+    from sklearn.mixture import GaussianMixture
+    if em_type != "diag":
+        raise NotImplementedError("full-covariance references have no kernel (SURVEY.md 8f item 2)")
+    from .distr.gauss import GMM
+    for reg_covar in [1e-6, 5e-5, 1e-5, 5e-4, 1e-4, 5e-3, 1e-3, 5e-2, 1e-2]:
+        try:
+            dim = dataset.shape[-1]
+            gmm = GaussianMixture(n_components=n_components, covariance_type=em_type,
+                                  means_init=means_init.cpu().numpy() if means_init is not None else None,
+                                  reg_covar=reg_covar, max_iter=max_iter)
+            gmm = gmm.fit(dataset.view((-1, dataset.shape[-1])).numpy())
+            weights = torch.from_numpy(gmm.weights_).float()
+            means = torch.from_numpy(gmm.means_).float()
+            variances = torch.from_numpy(gmm.covariances_).float()
+            GMM(dim=dim, loc=means, scale=variances.sqrt(), mixture_weights=weights)
+            return weights, means, variances
+        except Exception:  # noqa: BLE001  (the reference retries on any failure with the next regularisation)
+            continue
+    raise ValueError("Couldn't fit a GMM on this dataset.")
+
+
 def make_model(solver_type, ref_type, loss_type, integrator_type, model_type, time_type, solver_details, target_details,
                training_details, optim_details=None, n_steps=100, force_base_zero_init=False, use_ema=False,
                force_vp20=False, force_vp_cosine=False, compute_samples_based_metrics=True, force_T_cosine=None,

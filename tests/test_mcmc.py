@@ -93,3 +93,16 @@ def test_mcmc_sample_api(device):
     assert dist.max() < 6.0 * (0.5 * 10) ** 0.5
     with pytest.raises(NotImplementedError):
         BU.mcmc_sample(device, target, case["x_init"], mcmc_type="rwmh")
+    # the reference-fitting workflow of the experiments: MCMC data -> diagonal GMM by EM -> RDS with that reference
+    weights, means, variances = BU.fit_gmm(7, data, means_init=case["x_init"])
+    assert weights.shape == (7,) and means.shape == (7, 10) and variances.shape == (7, 10) and (variances > 0).all()
+    assert torch.cdist(means, case["target"]["loc"]).min(dim=1).values.max() < 1.0
+    details = {"sigma": 1.0, "weights_ref": weights, "means_ref": means, "variances_ref": variances}
+    model = BU.make_model(solver_type="vp-ref", ref_type="gmm", loss_type="lv", integrator_type="ei",
+                          model_type="target_informed_zero_init", time_type="snr", solver_details=details,
+                          target_details=BU.make_target_details("many_modes", dim=10, n_modes=7),
+                          training_details={"train_steps": 2, "train_batch_size": 64, "eval_batch_size": 512},
+                          n_steps=32, device=str(device))
+    res = model.compute_results()
+    # a reference fitted to the target itself with a zero-initialised control is already a good sampler
+    assert res.metrics["eval/elbo"] > -5.0 and abs(res.log_norm_const_preds["log_norm_const_is"]) < 1.0
