@@ -112,7 +112,7 @@ class BaseOCLoss:
             loss = rnd[mask].var() if self.method == "lv" else rnd[mask].mean()
         return loss, {"train/n_filtered_cumulative": self.n_filtered}
 
-    def _train(self, make_plan, x, noise=None, seed=None, particle_offset: int = 0):
+    def _train(self, make_plan, x, noise=None, seed=None, particle_offset: int = 0, group=None):
         """[TRAINING] shared by the ``__call__`` of the linear losses: repeat the initial values, run the fused rollout
         with the detached control driving the SDE, return (loss, metrics) with the LV gradient attached (train.py)."""
         from .. import train
@@ -126,7 +126,7 @@ class BaseOCLoss:
             x = x.repeat(self.traj_per_sample, 1, 1).reshape(-1, x.shape[-1])
         info = self._ctrl(False)
         return train.lv_objective(self, make_plan(x.device), info, x, self._seed(seed), noise=noise,
-                                  particle_offset=particle_offset)
+                                  particle_offset=particle_offset, group=group)
 
     def __call__(self, ts, x, *args, **kwargs):
         raise NotImplementedError("training through this loss is not built (SURVEY.md 8f item 1): the linear losses "

@@ -90,20 +90,49 @@ def normals(seed: int, particle_offset: int, K: int, B: int, d: int, device) -> 
     return z
 
 
+def lv_weights(rnd: torch.Tensor, mask: torch.Tensor, group=None):
+    """(loss, d loss / d rnd) of loss = Var(rnd[mask]) (unbiased) over the GLOBAL batch when the particles are sharded
+    over the ranks of ``group``: three fp64 sums (sum, count, sum of squares) travel through ONE all_reduce - the
+    training-side counterpart of the estimator exchange.  Runs on whatever device ``rnd`` lives on
+    (NCCL on the GPUs, gloo in the CPU tests)."""
+    import torch.distributed as dist
+    r = rnd.detach().double()
+    m = mask.to(r.dtype)
+    stats = torch.stack([(r * m).sum(), m.sum(), (r * r * m).sum()])
+    if group is not None and dist.is_available() and dist.is_initialized():
+        dist.all_reduce(stats, op=dist.ReduceOp.SUM, group=group)
+    s, n, s2 = stats
+    mean = s / n
+    var = (s2 - n * mean * mean) / (n - 1.0)
+    w = 2.0 * (r - mean) / (n - 1.0) * m
+    return var.to(rnd.dtype), w.to(rnd.dtype)
+
+
 def lv_objective(loss_obj, plan: pack.Plan, info: pack.CtrlInfo, x: torch.Tensor, seed: int, noise=None,
-                 particle_offset: int = 0, max_rows: int = 1 << 20):
+                 particle_offset: int = 0, max_rows: int = 1 << 20, group=None):
     """(loss, metrics) like ``BaseOCLoss.__call__``: ``loss`` is a scalar whose ``backward()`` leaves the LV gradient in
-    the ``.grad`` of the control's parameters."""
+    the ``.grad`` of the control's parameters.  With ``group`` (a torch.distributed group; method 'lv') the batch is the
+    union of the ranks' shards (``particle_offset`` = this rank's first global particle index): the variance and its
+    weights are global (lv_weights) and the parameter gradients are summed over the ranks, so every rank returns the
+    loss and gradient of the whole batch."""
     dev = x.device
     B, d = x.shape
     K = plan.noise_steps
     z = normals(seed, particle_offset, K, B, d, dev) if noise is None else noise.detach().to(dev, torch.float32).contiguous()
     with torch.no_grad():
         x_T, rnd, xs = pack.run_rollout(plan, x, z, seed, particle_offset, True)
-    rnd_leaf = rnd.detach().clone().requires_grad_(True)
-    with torch.enable_grad():
-        value, metrics = loss_obj.compute_loss(rnd_leaf, samples=x_T)
-        (w,) = torch.autograd.grad(value, rnd_leaf)  # d loss / d rnd_b, zero for filtered particles
+    if group is not None:
+        if loss_obj.method != "lv":
+            raise NotImplementedError("sharded training is built for method 'lv'")
+        mask = loss_obj.filter(rnd, samples=x_T)
+        loss_obj.n_filtered += (mask.numel() - mask.sum()).item()
+        value, w = lv_weights(rnd, mask, group)
+        metrics = {"train/n_filtered_cumulative": loss_obj.n_filtered}
+    else:
+        rnd_leaf = rnd.detach().clone().requires_grad_(True)
+        with torch.enable_grad():
+            value, metrics = loss_obj.compute_loss(rnd_leaf, samples=x_T)
+            (w,) = torch.autograd.grad(value, rnd_leaf)  # d loss / d rnd_b, zero for filtered particles
     params = [p for p in loss_obj.generative_ctrl.parameters() if p.requires_grad]
     grads: list = [None] * len(params)
     taus = plan.taus.to(dev)
@@ -127,4 +156,9 @@ def lv_objective(loss_obj, plan: pack.Plan, info: pack.CtrlInfo, x: torch.Tensor
         for i, g in enumerate(torch.autograd.grad(surrogate, params, allow_unused=True)):
             if g is not None:
                 grads[i] = g if grads[i] is None else grads[i] + g
+    if group is not None:  # one all_reduce over the flattened gradients
+        import torch.distributed as dist
+        flat = torch.cat([(g if g is not None else torch.zeros_like(p)).reshape(-1) for g, p in zip(grads, params)])
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+        grads = [c.reshape(p.shape) for c, p in zip(flat.split([p.numel() for p in params]), params)]
     return _InjectGrads.apply(value.detach(), grads, *params), metrics

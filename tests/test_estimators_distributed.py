@@ -78,3 +78,44 @@ def test_merge_is_associative_and_ignores_empty_ranks():
     for i in range(8):
         assert math.isclose(float(a[i]), float(whole[i]), rel_tol=1e-12, abs_tol=1e-12)
         assert math.isclose(float(a[i]), float(b[i]), rel_tol=1e-12, abs_tol=1e-12)
+
+
+def _lv_worker(rank, world, port, shards, masks, out):
+    from sde_sampler_lrds_b200.train import lv_weights
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        loss, w = lv_weights(shards[rank], masks[rank], dist.group.WORLD)
+        out[rank] = (loss.item(), w.clone())
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_lv_weights_match_the_single_process_variance_gradient():
+    """Training over sharded particles: loss = Var(rnd[mask]) of the GLOBAL batch and d loss / d rnd from one all_reduce
+    of three fp64 sums equal autograd through the reference's formula (compute_loss, losses/oc.py:105-131) on the whole
+    batch."""
+    g = torch.Generator().manual_seed(8)
+    sizes = (700, 324)
+    rnd = (torch.randn(sum(sizes), 1, generator=g) * 4.0 + 30.0).float()
+    rnd[5] = 2e8  # filtered by max_rnd = 1e8
+    mask = rnd < 1e8
+    leaf = rnd.clone().requires_grad_(True)
+    want_loss = leaf[mask].var()
+    (want_w,) = torch.autograd.grad(want_loss, leaf)
+    ctx = mp.get_context("spawn")
+    with ctx.Manager() as man:
+        out = man.dict()
+        port = _free_port()
+        shards, masks = list(torch.split(rnd, list(sizes))), list(torch.split(mask, list(sizes)))
+        procs = [ctx.Process(target=_lv_worker, args=(r, 2, port, shards, masks, out)) for r in range(2)]
+        for p in procs:
+            p.start()
+        for p in procs:
+            p.join(120)
+            assert p.exitcode == 0
+        got = [out[r] for r in range(2)]
+    assert abs(got[0][0] - want_loss.item()) < 1e-5 * want_loss.item() and got[0][0] == got[1][0]
+    w = torch.cat([got[0][1], got[1][1]])
+    assert (w - want_w).abs().max() < 1e-6 * want_w.abs().max() and w[5] == 0
