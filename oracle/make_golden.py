@@ -220,7 +220,9 @@ def run_reference(case, grads=False):
             kw2 = dict(kw)
             kw2["max_rnd"] = None
             loss = oc.ControlledLangevinSDELoss(sde=sde, **kw2)
-            if case.get("eubo"):
+            if grads:
+                out = train(loss, prior.log_prob)
+            elif case.get("eubo"):
                 rnd = loss.compute_eubo(ts, x0.clone(), target_logp, prior.log_prob)
                 out = {"rnd": rnd}
             else:

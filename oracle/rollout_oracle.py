@@ -567,22 +567,26 @@ def langevin_drift(t, x, target_score, prior_score, diff, T, clip_score):
 
 
 def simulate_cmcd(ts, x, noise, ctrl, drift, diff, terminal_unnorm_log_prob, initial_log_prob,
-                  return_traj=False):
+                  return_traj=False, lv=False):
     """ControlledLangevinSDELoss.simulate, losses/oc.py:666-755 (train=False, use_rescaling=True,
     change_sde_ctrl=False).  (u_t, drift_t) of step k are re-evaluated at step k+1 as (u_s, drift_s)
-    exactly like the reference (no caching here: the oracle keeps the reference's evaluation count)."""
+    exactly like the reference (no caching here: the oracle keeps the reference's evaluation count).  ``lv`` = the
+    training form (change_sde_ctrl=True, train=True with method 'lv': the SDE follows the detached control, 705-706, 739)."""
     rnd = initial_log_prob(x)
     xs = [x] if return_traj else None
     for k, (s, t) in enumerate(zip(ts[:-1], ts[1:])):
         u_s = ctrl(s, x)
+        sde_ctrl = u_s.detach() if lv else u_s
         dt = t - s
         db = dt.sqrt() * noise[k]
         drift_s = drift(s, x)
-        y = x + (drift_s + u_s * diff) * dt + diff * db
+        y = x + (drift_s + sde_ctrl * diff) * dt + diff * db
         drift_t = drift(t, y)
         u_t = ctrl(t, y)
         cost = (drift_s + drift_t) / diff + u_s - u_t
         rnd = rnd + 0.5 * (cost ** 2).sum(dim=-1, keepdim=True) * dt
+        if lv:
+            rnd = rnd + (cost * (sde_ctrl - u_s)).sum(dim=-1, keepdim=True) * dt
         rnd = rnd + (cost * db).sum(dim=-1, keepdim=True)
         x = y
         if return_traj:
@@ -756,8 +760,8 @@ def rollout(problem: dict, x0: torch.Tensor, noise: torch.Tensor, *, eubo: bool 
     dds alpha/sigma, for cmcd diff/T/clip_score/prior).  Returns (x_T, rnd, xs) for the generative
     rollout, or rnd for ``eubo=True`` (x0 = target samples).  ``lv=True`` runs the TRAINING form of the linear
     losses (change_sde_ctrl=True, autograd through the control; see lv_loss_and_grads)."""
-    if lv and (eubo or problem["method"] == "cmcd"):
-        raise ValueError("the lv training form is restated for the linear simulate loops only")
+    if lv and eubo:
+        raise ValueError("the lv training form belongs to the simulate loops")
     problem = _cast(problem, dtype)
     x0, noise = x0.to(dtype), noise.to(dtype)
     ts = problem["ts"]
@@ -807,7 +811,7 @@ def rollout(problem: dict, x0: torch.Tensor, noise: torch.Tensor, *, eubo: bool 
             drift = lambda t, x: langevin_drift(t, x, target_score, prior_score, diff, T, problem.get("clip_score"))  # noqa: E731
             if eubo:
                 return eubo_cmcd(ts, x0, noise, ctrl, drift, diff, target_logp, prior_logp)
-            return simulate_cmcd(ts, x0, noise, ctrl, drift, diff, target_logp, prior_logp, return_traj)
+            return simulate_cmcd(ts, x0, noise, ctrl, drift, diff, target_logp, prior_logp, return_traj, lv=lv)
     raise ValueError(method)
 
 

@@ -14,8 +14,8 @@ Extra keyword arguments (not in the reference, all optional): ``noise`` = record
 to consume instead of in-kernel Philox draws (validation mode), ``seed`` / ``particle_offset`` for the
 counter-based generator (global particle index => results independent of the GPU count).
 Training: ``loss(ts, x, ...)`` with method 'lv' / 'lv_traj' returns a scalar whose ``backward()`` fills the control's
-parameter gradients (train.py: fused rollout + one batched gradient pass); 'kl' (pathwise gradient through the
-trajectory) and the CMCD loss raise.
+parameter gradients (train.py: fused rollout + one batched gradient pass), for every loss class below; 'kl' (pathwise
+gradient through the trajectory) raises.
 """
 from __future__ import annotations
 
@@ -555,8 +555,24 @@ class ControlledLangevinSDELoss(BaseOCLoss):
                 raise NotImplementedError("CMCD needs a (diagonal) Gaussian prior (solver/oc.py:276-277)")
             fill_gmm(spec.ref_0, blk0)
             keep.append(blk0)
-            return pack.Plan(spec, keep, rows=K + 1, noise_steps=K)
+            return pack.Plan(spec, keep, rows=K + 1, noise_steps=K, taus=tsc)
         return self._cached(key, build)
+
+    def __call__(self, ts, x, terminal_unnorm_log_prob, initial_log_prob=None, noise=None, seed=None,
+                 particle_offset: int = 0):
+        """[TRAINING] (loss, metrics) of oc.py:830-860 for method 'lv' / 'lv_traj' (train.cmcd_lv_objective)."""
+        from .. import train
+        if self.method not in ("lv", "lv_traj"):
+            raise NotImplementedError("method 'kl' differentiates through the trajectory: not built (SURVEY.md 8f item 1)")
+        if self.sde_ctrl_noise is not None or self.sde_ctrl_dropout is not None:
+            raise NotImplementedError("sde_ctrl_noise / sde_ctrl_dropout are not set by any shipped config")
+        if self.traj_per_sample != 1:
+            x = x.repeat(self.traj_per_sample, 1, 1).reshape(-1, x.shape[-1])
+        info = self._ctrl(False)
+        if info.kind not in (N.CTRL_CLIPPED, N.CTRL_SCORE):
+            raise NotImplementedError("CMCD trains ClippedCtrl / ScoreCtrl drift models")
+        plan = self._plan(ts, x.device, False, terminal_unnorm_log_prob, initial_log_prob, eubo=False)
+        return train.cmcd_lv_objective(self, plan, info, x, self._seed(seed), noise=noise, particle_offset=particle_offset)
 
     def simulate(self, ts, x, terminal_unnorm_log_prob, initial_log_prob=None, train: bool = True,
                  change_sde_ctrl: bool = False, return_traj: bool = False, use_ema: bool = False, noise=None,

@@ -239,6 +239,9 @@ class CMCD(TrainableDiff):
         self.setup_models(skip_prior=True)
         self.to(self.device)
 
+    def _compute_loss(self, ts, x):
+        return self.loss(ts, x, self.clipped_target_unnorm_log_prob, initial_log_prob=self.prior.log_prob)
+
     def _compute_results(self, ts, x, use_ema=True, compute_weights=True, return_traj=True) -> Results:
         return self.loss.eval(ts, x, self.clipped_target_unnorm_log_prob, use_ema=use_ema,
                               initial_log_prob=self.prior.log_prob, compute_weights=compute_weights,

@@ -162,3 +162,65 @@ def lv_objective(loss_obj, plan: pack.Plan, info: pack.CtrlInfo, x: torch.Tensor
         dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
         grads = [c.reshape(p.shape) for c, p in zip(flat.split([p.numel() for p in params]), params)]
     return _InjectGrads.apply(value.detach(), grads, *params), metrics
+
+
+def _accumulate(grads, params, surrogate):
+    for i, g in enumerate(torch.autograd.grad(surrogate, params, allow_unused=True)):
+        if g is not None:
+            grads[i] = g if grads[i] is None else grads[i] + g
+
+
+def cmcd_lv_objective(loss_obj, plan: pack.Plan, info: pack.CtrlInfo, x: torch.Tensor, seed: int, noise=None,
+                      particle_offset: int = 0, max_rows: int = 1 << 20):
+    """The same for ControlledLangevinSDELoss (oc.py:666-755, 830-860) with method 'lv'.  Every trajectory point
+    (ts[j], xs[j]) enters the log-weight twice - as the start of step j (control u_s) and as the end of step j - 1
+    (control u_t) - through cost_k = (drift_s + drift_t) / sigma + u_s - u_t:
+
+        d rnd_b / d theta = sum_j < [j < K] db_j  -  [j >= 1] (cost_{j-1} dt_{j-1} + db_{j-1}),  d g(ts[j], xs[j]) / d theta >
+
+    (the term cost (sde_ctrl - u_s) dt of oc.py:739 removes the cost dt contribution of the start point).  One batched
+    pass over the K + 1 stored states evaluates the controls and the tempered drifts for the costs, a second one carries
+    the cotangents back."""
+    dev = x.device
+    B, d = x.shape
+    K = plan.noise_steps
+    z = normals(seed, particle_offset, K, B, d, dev) if noise is None else noise.detach().to(dev, torch.float32).contiguous()
+    with torch.no_grad():
+        x_T, rnd, xs = pack.run_rollout(plan, x, z, seed, particle_offset, True)
+    rnd_leaf = rnd.detach().clone().requires_grad_(True)
+    with torch.enable_grad():
+        value, metrics = loss_obj.compute_loss(rnd_leaf, samples=x_T)
+        (w,) = torch.autograd.grad(value, rnd_leaf)
+    params = [p for p in loss_obj.generative_ctrl.parameters() if p.requires_grad]
+    grads: list = [None] * len(params)
+    sde = loss_obj.sde
+    ts = plan.taus.to(dev)                      # [K + 1]
+    dt = (plan.taus[1:] - plan.taus[:-1]).to(dev)
+    sig = sde.diff_coeff.to(dev)
+    frac = (plan.taus / sde.terminal_t.detach().cpu()).to(dev)
+    target, prior = sde.target_score.__self__, sde.prior_score.__self__
+    rows = max(1, max_rows // B)
+    gd, drift, tscore = [], [], []
+    with torch.no_grad():  # pass 1: controls and tempered drifts (eq/sdes.py:101-110) at every stored state
+        for j0 in range(0, K + 1, rows):
+            j1 = min(K + 1, j0 + rows)
+            flat = xs[j0:j1].reshape(-1, d)
+            tsc = target.score(flat).reshape(j1 - j0, B, d)
+            dr = tsc * frac[j0:j1, None, None] + prior.score(flat).reshape(j1 - j0, B, d) * (1.0 - frac[j0:j1, None, None])
+            dr = _clip(dr * (0.5 * sig ** 2), sde.clip_score)
+            gd.append(control_rows(info, ts[j0:j1], xs[j0:j1], tsc if info.kind != N.CTRL_CLIPPED else None))
+            drift.append(dr)
+            tscore.append(tsc)
+        gd, drift, tscore = torch.cat(gd), torch.cat(drift), torch.cat(tscore)
+        db = dt.sqrt()[:, None, None] * z                                   # [K, B, d]
+        cost = (drift[:-1] + drift[1:]) / sig + gd[:-1] - gd[1:]             # [K, B, d]
+        cot = torch.zeros_like(xs)
+        cot[:-1] += db
+        cot[1:] -= cost * dt[:, None, None] + db
+        cot *= w[None, :, :]
+    for j0 in range(0, K + 1, rows):  # pass 2: cotangents through the control
+        j1 = min(K + 1, j0 + rows)
+        with torch.enable_grad():
+            g = control_rows(info, ts[j0:j1], xs[j0:j1], tscore[j0:j1] if info.kind != N.CTRL_CLIPPED else None)
+            _accumulate(grads, params, (cot[j0:j1] * g).sum())
+    return _InjectGrads.apply(value.detach(), grads, *params), metrics

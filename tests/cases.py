@@ -420,7 +420,7 @@ CASES = {
 # (tests/golden/grad_<name>.pt, python -m oracle.make_golden --grads)
 GRAD_CASES = ["em_two_modes_score", "ei_many_modes", "ddpm_snr", "ei_phi4_gmm", "pis_many_modes", "dds_many_modes_ito",
               "dds_phi4_ito", "dis_many_modes_ito", "pis_logreg", "dis_many_modes_lerp", "dis_many_modes_langevin",
-              "dis_ei_many_modes"]
+              "dis_ei_many_modes", "cmcd_gmm", "cmcd_logreg_sonar"]
 
 
 def case_mala(target="many_modes"):
