@@ -147,6 +147,8 @@ def run_reference(case, grads=False):
         return out if clip_t is None else out.clip(-clip_t, clip_t)
 
     kw = dict(generative_ctrl=ctrl, generative_ctrl_ema=ctrl, method="lv", max_rnd=1e8)
+    if case.get("traj_per_sample", 1) != 1:
+        kw.update(method="lv_traj", traj_per_sample=case["traj_per_sample"])
     def train(loss, *args, **kwargs):
         val, _ = loss(ts, x0, target_logp, *args, **kwargs)
         val.backward()
@@ -303,9 +305,9 @@ def main(argv):
                   f"{out['step_size'].max():.3g} | {os.path.getsize(path)} B")
         return
     if argv and argv[0] == "--grads":  # python -m oracle.make_golden --grads [case ...]
-        from tests.cases import GRAD_CASES
+        from tests.cases import GRAD_CASES, grad_case
         for name in argv[1:] or GRAD_CASES:
-            out = run_reference(CASES[name](), grads=True)
+            out = run_reference(grad_case(name), grads=True)
             out["torch_version"] = str(torch.__version__)
             path = os.path.join(REPO, "tests", "golden", "grad_" + name + ".pt")
             torch.save(out, path)

@@ -816,11 +816,14 @@ def rollout(problem: dict, x0: torch.Tensor, noise: torch.Tensor, *, eubo: bool 
 
 
 def lv_loss_and_grads(problem: dict, x0: torch.Tensor, noise: torch.Tensor, max_rnd: float | None = 1e8,
-                      dtype=torch.float32):
+                      dtype=torch.float32, traj_per_sample: int = 1):
     """The training objective ``loss(ts, x, ...)`` of the linear rollout losses with method='lv' and its gradient:
     __call__ (losses/oc.py:364-394, 1240-1272, 1399-1431: change_sde_ctrl=True, compute_ito_int=True) ->
-    BaseOCLoss.compute_loss (105-131: ``rnd[mask].var()`` over the particles that pass ``filter``, 67-81).
-    Returns (loss, {state_dict key: d loss / d parameter}, rnd)."""
+    BaseOCLoss.compute_loss (105-131: ``rnd[mask].var()`` over the particles that pass ``filter``, 67-81; with
+    ``traj_per_sample`` > 1 the 'lv_traj' form: initial values repeated, 383-384, variance over each sample's trajectories,
+    118-124).  Returns (loss, {state_dict key: d loss / d parameter}, rnd)."""
+    if traj_per_sample != 1:
+        x0 = x0.repeat(traj_per_sample, 1, 1).reshape(-1, x0.shape[-1])
     problem = dict(problem)
     ctrl = dict(problem["ctrl"])
     ctrl["sd"] = {k: v.detach().to(dtype).clone().requires_grad_(True) for k, v in ctrl["sd"].items()}
@@ -829,7 +832,10 @@ def lv_loss_and_grads(problem: dict, x0: torch.Tensor, noise: torch.Tensor, max_
     cast["ctrl"] = ctrl
     _, rnd, _ = rollout(cast, x0, noise, compute_ito_int=True, dtype=dtype, lv=True)
     mask = rnd.isfinite() if max_rnd is None else rnd < max_rnd
-    loss = rnd[mask].var()
+    if traj_per_sample != 1:
+        loss = rnd.reshape(traj_per_sample, -1, 1)[:, mask.reshape(traj_per_sample, -1, 1).all(dim=0)].var(dim=0).mean()
+    else:
+        loss = rnd[mask].var()
     names = list(ctrl["sd"])
     grads = torch.autograd.grad(loss, [ctrl["sd"][k] for k in names], allow_unused=True)
     return loss.detach(), {k: (g if g is not None else torch.zeros_like(ctrl["sd"][k])) for k, g in zip(names, grads)}, rnd.detach()

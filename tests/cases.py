@@ -366,6 +366,14 @@ def case_cmcd_gmm():
         "B": 140, "seed": 108, "prior": ("gauss",)}
 
 
+def _lv_traj(case, traj_per_sample=2):
+    """method='lv_traj': every initial value is repeated traj_per_sample times (losses/oc.py:383-384) and the loss is the
+    mean over the samples of the variance over their trajectories (118-124).  ``noise_for`` draws for B * traj particles."""
+    case = dict(case)
+    case["traj_per_sample"] = traj_per_sample
+    return case
+
+
 def _eubo(case, seed):
     case = dict(case)
     case["eubo"] = True
@@ -420,7 +428,7 @@ CASES = {
 # (tests/golden/grad_<name>.pt, python -m oracle.make_golden --grads)
 GRAD_CASES = ["em_two_modes_score", "ei_many_modes", "ddpm_snr", "ei_phi4_gmm", "pis_many_modes", "dds_many_modes_ito",
               "dds_phi4_ito", "dis_many_modes_ito", "pis_logreg", "dis_many_modes_lerp", "dis_many_modes_langevin",
-              "dis_ei_many_modes", "cmcd_gmm", "cmcd_logreg_sonar"]
+              "dis_ei_many_modes", "cmcd_gmm", "cmcd_logreg_sonar", "lvtraj_ei_two_modes_gauss"]
 
 
 def case_mala(target="many_modes"):
@@ -452,6 +460,14 @@ def mala_inputs(case: dict):
     noise = torch.from_numpy(philox_ref.normals(case["seed"], C, S, d))
     unif = torch.from_numpy(philox_ref.uniforms(case["seed"], C, S))
     return y_init, noise, unif
+
+
+# training-only cases (not rollout parity cases: their noise covers B * traj_per_sample particles)
+TRAIN_ONLY_CASES = {"lvtraj_ei_two_modes_gauss": lambda: _lv_traj(case_ei_two_modes_gauss())}
+
+
+def grad_case(name: str) -> dict:
+    return (CASES.get(name) or TRAIN_ONLY_CASES[name])()
 
 
 def initial_state(case: dict, dtype=torch.float32):
@@ -486,4 +502,4 @@ def noise_for(case: dict, dtype=torch.float32):
     p = case["problem"]
     d = p["target"]["loc"].shape[1] if p["target"]["kind"] == "gmm" else p["target"]["dim"]
     K = len(p["ts"]) - 1
-    return torch.from_numpy(philox_ref.normals(case["seed"], case["B"], K, d)).to(dtype)
+    return torch.from_numpy(philox_ref.normals(case["seed"], case["B"] * case.get("traj_per_sample", 1), K, d)).to(dtype)

@@ -71,6 +71,8 @@ class Built:
         self.ts = p["ts"].clone().to(device)
         method = p["method"]
         kw = dict(generative_ctrl=self.ctrl, generative_ctrl_ema=self.ctrl, method="lv", max_rnd=1e8, precision=precision)
+        if case.get("traj_per_sample", 1) != 1:
+            kw.update(method="lv_traj", traj_per_sample=case["traj_per_sample"])
         if method in ("em", "ei", "ddpm"):
             self.sde = build_sde(p["sde"], device)
             ref = p["ref"]

@@ -12,7 +12,7 @@ import pytest
 import torch
 
 from oracle import rollout_oracle as O
-from tests.cases import CASES, GRAD_CASES, initial_state, noise_for
+from tests.cases import GRAD_CASES, grad_case, initial_state, noise_for
 
 pytestmark = pytest.mark.gpu
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
@@ -27,7 +27,7 @@ def worst(got: dict, want: dict):
 @pytest.mark.parametrize("name", GRAD_CASES)
 def test_lv_gradient_matches_oracle_and_reference(name, precision, device):
     from tests.product_builders import Built
-    case = CASES[name]()
+    case = grad_case(name)
     gold = torch.load(os.path.join(GOLDEN, "grad_" + name + ".pt"))
     x0, noise = initial_state(case), noise_for(case)
     built = Built(case, device, precision)
@@ -35,7 +35,8 @@ def test_lv_gradient_matches_oracle_and_reference(name, precision, device):
     assert loss.requires_grad and loss.ndim == 0 and "train/n_filtered_cumulative" in metrics
     loss.backward()
     got = {n: p.grad.detach().cpu() for n, p in built.ctrl.named_parameters() if p.grad is not None}
-    lo, go, _ = O.lv_loss_and_grads(case["problem"], x0, noise, max_rnd=None if case["problem"]["method"] == "cmcd" else 1e8)
+    lo, go, _ = O.lv_loss_and_grads(case["problem"], x0, noise, max_rnd=None if case["problem"]["method"] == "cmcd" else 1e8,
+                                    traj_per_sample=case.get("traj_per_sample", 1))
     tol = 2e-2 if case["problem"]["target"]["kind"] == "logreg" else 1e-3
     for want_loss, want, what in ((lo, go, "oracle"), (gold["loss"], gold["grads"], "reference")):
         assert abs(loss.item() - want_loss.item()) <= max(tol / 10, 1e-4) * max(1.0, abs(want_loss.item())), what
