@@ -152,20 +152,28 @@ class BaseOCLoss:
             return int(seed)
         return (int(torch.initial_seed()) * 0x9E3779B97F4A7C15 + next(self._calls) * 0xD1B54A32D192ED03) & (2 ** 64 - 1)
 
-    def _cached(self, key, build):
-        if key not in self._plans:
+    def _cached(self, key, build, info, device):
+        """Plans are cached by everything that does not depend on the control's parameters (grid, schedule, reference and
+        target blocks: O(K) host work, seconds for a stepped mixture reference); a parameter update (training step, EMA
+        swap) only refreshes the weight images and the TimeEmbed rows of the cached plan (pack.refresh_ctrl)."""
+        skey, vers = key
+        hit = self._plans.get(skey)
+        if hit is None:
             if len(self._plans) >= 16:
                 self._plans.pop(next(iter(self._plans)))
-            self._plans[key] = build()
-        return self._plans[key]
+            hit = self._plans[skey] = [build(), vers]
+        elif hit[1] != vers:
+            pack.refresh_ctrl(hit[0], info, device)
+            hit[1] = vers
+        return hit[0]
 
     def _key(self, tag, ts, device, info, extra=()):
         tsc = ts.detach().to("cpu", torch.float32)
         vers = tuple((p.data_ptr(), p._version) for p in info.base.parameters())
         if info.score_model is not None:
             vers += tuple((p.data_ptr(), p._version) for p in info.score_model.parameters())
-        return (tag, tsc.numpy().tobytes(), str(device), vers, id(info.target), self.precision or pack.default_precision(),
-                info.kind, extra)
+        return (tag, tsc.numpy().tobytes(), str(device), id(info.target), self.precision or pack.default_precision(),
+                info.kind, id(info.sde), id(info.prior), extra), vers
 
 
 def _terminal(spec, keep, device, terminal_unnorm_log_prob, info):
@@ -271,7 +279,7 @@ class EMReferenceSDELoss(BaseOCLoss):
             fill_gmm(spec.ref_0, blk0)
             keep.append(blk0)
             return pack.Plan(spec, keep, rows=K, noise_steps=K, taus=taus, ito_w=pack.ito_weights(table, spec.ito_form))
-        return self._cached(key, build)
+        return self._cached(key, build, info, device)
 
     def __call__(self, ts, x, terminal_unnorm_log_prob, reference_log_prob, **kw):
         """[TRAINING] (loss, metrics) of oc.py:364-394."""
@@ -402,7 +410,7 @@ class ExponentialIntegratorSDELoss(BaseOCLoss):
             fill_gmm(spec.ref_0, blk0)
             keep.append(blk0)
             return pack.Plan(spec, keep, rows=K, noise_steps=K, taus=tsc[:-1], ito_w=pack.ito_weights(table, spec.ito_form))
-        return self._cached(key, build)
+        return self._cached(key, build, info, device)
 
     def __call__(self, ts, x, terminal_unnorm_log_prob, reference_log_prob, **kw):
         """[TRAINING] (loss, metrics) of oc.py:1399-1431 (compute_ito_int = method != 'kl')."""
@@ -480,7 +488,7 @@ class TimeReversalLoss(BaseOCLoss):
             # the training rollout leaves the divergence integral out (`if not train`, oc.py:1217)
             spec.init_cost, spec.rnd_offset = 1, 0.0 if train else float(div)
             return pack.Plan(spec, keep, rows=K, noise_steps=K, taus=tsc[:-1], ito_w=pack.ito_weights(table, spec.ito_form))
-        return self._cached(key, build)
+        return self._cached(key, build, info, device)
 
     def __call__(self, ts, x, terminal_unnorm_log_prob, initial_log_prob=None, **kw):
         """[TRAINING] (loss, metrics) of oc.py:1240-1272 (compute_ito_int = method != 'kl', train=True)."""
@@ -556,7 +564,7 @@ class ControlledLangevinSDELoss(BaseOCLoss):
             fill_gmm(spec.ref_0, blk0)
             keep.append(blk0)
             return pack.Plan(spec, keep, rows=K + 1, noise_steps=K, taus=tsc)
-        return self._cached(key, build)
+        return self._cached(key, build, info, device)
 
     def __call__(self, ts, x, terminal_unnorm_log_prob, initial_log_prob=None, noise=None, seed=None,
                  particle_offset: int = 0):

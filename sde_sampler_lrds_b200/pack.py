@@ -224,7 +224,23 @@ def finish_table(table: torch.Tensor, info: CtrlInfo, taus: torch.Tensor, device
     table[:, N.STEP_BIAS1:N.STEP_BIAS1 + N.CHANNELS] = bias1
     table[:, N.STEP_GAMMA] = gamma
     dis_ctrl_rows(info, taus, table)
-    return table.contiguous().to(device)
+    out = table.contiguous().to(device)
+    out._lrds_ctrl_taus = taus.detach().clone()  # refresh_ctrl re-evaluates the parameter-dependent columns at these times
+    return out
+
+
+def refresh_ctrl(plan: "Plan", info: CtrlInfo, device):
+    """Re-packs what depends on the control's parameters into a cached plan: the weight block / tensor-core image
+    (keep[0], set by fill_ctrl) and the TimeEmbed columns of the device table (bias rows, gamma), in place and ordered
+    on the current stream behind earlier launches that read them."""
+    spec = plan.spec
+    mlp, k = info.base.lrds_mlp(device, spec.precision)
+    spec.mlp = mlp
+    plan.keep[0] = k
+    table = next(t for t in plan.keep if isinstance(t, torch.Tensor) and hasattr(t, "_lrds_ctrl_taus"))
+    bias1, gamma = time_rows(info, table._lrds_ctrl_taus)
+    table[:, N.STEP_BIAS1:N.STEP_BIAS1 + N.CHANNELS] = bias1.to(table.device)
+    table[:, N.STEP_GAMMA] = gamma.to(table.device)
 
 
 def run_rollout(plan: Plan, x0: torch.Tensor, noise: torch.Tensor | None, seed: int, particle_offset: int,

@@ -43,6 +43,28 @@ def test_lv_gradient_matches_oracle_and_reference(name, precision, device):
         assert worst(got, want) < tol, (what, worst(got, want))
 
 
+def test_cached_plan_follows_parameter_updates(device):
+    """A parameter update (an optimiser step) must not rebuild the O(K) host side of a rollout plan - for a stepped
+    mixture reference that is seconds - but the next rollout must run with the new weights and TimeEmbed rows: the
+    cached plan refreshed in place equals a freshly built one, bit for bit."""
+    from tests.cases import CASES
+    from tests.product_builders import Built
+    case = CASES["ei_many_modes"]()
+    x0, noise = initial_state(case), noise_for(case)
+    built = Built(case, device, "f16x3")
+    _, r1, _ = built.simulate(x0, noise)
+    g = torch.Generator().manual_seed(3)
+    with torch.no_grad():
+        for p in built.ctrl.parameters():
+            p.add_(0.02 * torch.randn(p.shape, generator=g).to(device))
+    _, r2, _ = built.simulate(x0, noise)
+    assert len(built.loss._plans) == 1
+    fresh = Built(case, device, "f16x3")
+    fresh.ctrl.load_state_dict(built.ctrl.state_dict())
+    _, r3, _ = fresh.simulate(x0, noise)
+    assert torch.equal(r2, r3) and not torch.equal(r1, r2)
+
+
 @pytest.mark.parametrize("solver_type, kw", [
     ("vp-ref", dict(ref_type="gmm", integrator_type="ei", time_type="snr")),
     ("pis_orig", dict(ref_type="default", integrator_type="em", time_type="uniform")),

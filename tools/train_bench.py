@@ -35,6 +35,8 @@ def main():
         params = list(built.ctrl.parameters())
 
         def step(seed):
+            with torch.no_grad():  # an optimiser step changes the weights: the cached plan refreshes its weight images
+                params[0].add_(0.0)
             for p in params:
                 p.grad = None
             loss, _ = built.train_loss(x0, None, seed=seed)
