@@ -44,8 +44,8 @@ def test_lv_gradient_matches_oracle_and_reference(name, precision, device):
 
 
 def test_cached_plan_follows_parameter_updates(device):
-    """A parameter update (an optimiser step) must not rebuild the O(K) host side of a rollout plan - for a stepped
-    mixture reference that is seconds - but the next rollout must run with the new weights and TimeEmbed rows: the
+    """A parameter update (an optimiser step) must not rebuild the O(K) host side of a rollout plan (tens of
+    milliseconds of scalar schedule formulas) - but the next rollout must run with the new weights and TimeEmbed rows: the
     cached plan refreshed in place equals a freshly built one, bit for bit."""
     from tests.cases import CASES
     from tests.product_builders import Built
