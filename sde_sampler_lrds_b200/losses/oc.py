@@ -33,6 +33,13 @@ from ..estimators import estimator_partials, metrics_from_partials
 from ..utils.common import Results
 
 
+def _fid(fn):
+    """Stable identity of a callable for the plan cache: a bound method is a fresh object at every attribute access
+    (``solver.clipped_target_unnorm_log_prob``), so it is keyed by its owner and name."""
+    owner = getattr(fn, "__self__", None)
+    return (id(owner), getattr(fn, "__name__", "")) if owner is not None else id(fn)
+
+
 def _resolve_reference(ref_ctrl):
     if ref_ctrl is None:
         return None
@@ -222,7 +229,7 @@ class EMReferenceSDELoss(BaseOCLoss):
         info = self._ctrl(use_ema)
         ref = _resolve_reference(self.reference_ctrl)
         ref0, _ = pack.resolve_log_prob(reference_log_prob)
-        key = self._key((self._variant, eubo, self._init_cost), ts, device, info, (id(ref), id(ref0), id(terminal_unnorm_log_prob)))
+        key = self._key((self._variant, eubo, self._init_cost), ts, device, info, (id(ref), id(ref0), _fid(terminal_unnorm_log_prob)))
 
         def build():
             if eubo and ref is None and not self._init_cost:
@@ -377,7 +384,7 @@ class ExponentialIntegratorSDELoss(BaseOCLoss):
         info = self._ctrl(use_ema)
         ref0, _ = pack.resolve_log_prob(reference_log_prob)
         key = self._key(("dds", bool(compute_ito_int), self.alpha, self.sigma), ts, device, info,
-                        (id(ref0), id(terminal_unnorm_log_prob)))
+                        (id(ref0), _fid(terminal_unnorm_log_prob)))
 
         def build():
             tsc, pairs = pack._scalar_rows(ts)
@@ -452,7 +459,7 @@ class TimeReversalLoss(BaseOCLoss):
         info = self._ctrl(use_ema)
         prior, _ = pack.resolve_log_prob(initial_log_prob)
         key = self._key(("dis", bool(compute_ito_int), bool(train)), ts, device, info,
-                        (id(prior), id(terminal_unnorm_log_prob)))
+                        (id(prior), _fid(terminal_unnorm_log_prob)))
 
         def build():
             sde = self.sde.host()
@@ -528,7 +535,7 @@ class ControlledLangevinSDELoss(BaseOCLoss):
             raise NotImplementedError("CMCD needs a ControlledLangevinSDE")
         info = self._ctrl(use_ema)
         prior, _ = pack.resolve_log_prob(initial_log_prob)
-        key = self._key(("cmcd", eubo), ts, device, info, (id(prior), id(terminal_unnorm_log_prob)))
+        key = self._key(("cmcd", eubo), ts, device, info, (id(prior), _fid(terminal_unnorm_log_prob)))
 
         def build():
             sde = self.sde
