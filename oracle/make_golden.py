@@ -115,7 +115,9 @@ def build_reference_ctrl(c, d, target_score):
 
 
 def build_reference_sde(s):
-    from sde_sampler.eq.sdes import VP, PinnedBM, ScaledBM
+    from sde_sampler.eq.sdes import VP, CosineVP, PinnedBM, ScaledBM
+    if s["kind"] == "vpcos":
+        return CosineVP(c=s["c"], scale_diff_coeff=s["scale"], terminal_t=s["T"])
     if s["kind"] == "vp":
         return VP(diff_coeff_sq_min=s["beta_min"], diff_coeff_sq_max=s["beta_max"], scale_diff_coeff=s["scale"],
                   terminal_t=s["T"])

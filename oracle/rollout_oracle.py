@@ -300,6 +300,20 @@ class VP:
         return mean + torch.sqrt(var) * z
 
 
+class CosineVP(VP):
+    """CosineVP, sde_sampler/eq/sdes.py:558-594: VP with beta(t) and alpha(t) of the cosine schedule."""
+
+    def __init__(self, c=0.008, scale=1.0, T=1.0, dtype=torch.float32):
+        super().__init__(0.1, 20.0, scale, T, dtype)
+        self.cc = torch.tensor(c, dtype=dtype)
+
+    def beta(self, t):  # _diff_coeff_sq_t, 577-580
+        return torch.pi * torch.tan(0.5 * torch.pi * ((t / self.T) + self.cc) / (1.0 + self.cc)) / (self.T * (1.0 + self.cc))
+
+    def alpha_(self, t):  # 592-594
+        return -2.0 * torch.log(torch.cos(0.5 * torch.pi * ((t / self.T) + self.cc) / (1.0 + self.cc)))
+
+
 class PinnedBM:
     """PinnedBM, sde_sampler/eq/sdes.py:597-678."""
 
@@ -366,6 +380,8 @@ def make_sde(sde: dict | None, dtype=torch.float32):
     kind = sde["kind"]
     if kind == "vp":
         return VP(sde["beta_min"], sde["beta_max"], sde.get("scale", 1.0), sde.get("T", 1.0), dtype)
+    if kind == "vpcos":
+        return CosineVP(sde.get("c", 0.008), sde.get("scale", 1.0), sde.get("T", 1.0), dtype)
     if kind == "pbm":
         return PinnedBM(sde["diff"], sde["T"], dtype)
     if kind == "bm":

@@ -19,7 +19,7 @@ from .distr.delta import Delta
 from .distr.gauss import IsotropicGauss, ManyModes, TwoModes
 from .distr.logistic_regression import LogisticRegression
 from .distr.phi_four import PhiFour
-from .eq.sdes import VP, ControlledLangevinSDE, PinnedBM, ScaledBM
+from .eq.sdes import VP, ControlledLangevinSDE, CosineVP, PinnedBM, ScaledBM
 from .losses import oc as L
 from .models.mlp import FourierMLP, TimeEmbed
 from .models.reparam import CancelDriftCtrl, ClippedCtrl, LerpCtrl, ScoreCtrl
@@ -106,7 +106,8 @@ def _model_cfg(model_type: str, dim: int) -> dict:
     raise NotImplementedError(f"model_type {model_type!r} has no B200 kernel yet (SURVEY.md 8f item 3)")
 
 
-def default_config(solver_type: str, model_type: str, loss_type: str, target_details: dict, force_vp20=False) -> dict:
+def default_config(solver_type: str, model_type: str, loss_type: str, target_details: dict, force_vp20=False,
+                   force_vp_cosine=False) -> dict:
     """The resolved conf/solver/<solver>.yaml tree (before make_model's patches)."""
     target = _target_cfg(target_details)
     dim = target["dim"]
@@ -120,6 +121,8 @@ def default_config(solver_type: str, model_type: str, loss_type: str, target_det
     if name == "vp_rds":
         sde = {"_target_": VP, "diff_coeff_sq_min": 0.1, "diff_coeff_sq_max": 20.0 if force_vp20 else 10.0,
                "scale_diff_coeff": 1.0, "terminal_t": 1.0}
+        if force_vp_cosine:  # conf/sde/vp_cos.yaml
+            sde = {"_target_": CosineVP, "c": 0.008, "scale_diff_coeff": 1.0, "terminal_t": 1.0}
         base.update(solver=S.RDS, sde=sde, loss=em_loss, prior={"_target_": IsotropicGauss, "dim": dim, "scale": "${sde.scale_diff_coeff}"})
     elif name == "pbm_rds":
         sde = {"_target_": PinnedBM, "diff_coeff": 0.4472135954999579, "terminal_t": 5.0}
@@ -266,11 +269,10 @@ def make_model(solver_type, ref_type, loss_type, integrator_type, model_type, ti
         raise NotImplementedError("the reference wraps this control in RemoveReferenceCtrl(..., sde=None) whose forward "
                                   "dereferences the missing sde (benchmark_utils.py:261-262, models/reparam.py:58-64): "
                                   "there is no reference behaviour to reproduce")
-    if force_vp_cosine:
-        raise NotImplementedError("CosineVP is not on the rollout path built here (SURVEY.md section 2 row 2: secondary)")
 
     # Build the config and apply the reference's patches (162-210)
-    cfg = default_config(solver_type, model_type, loss_type, target_details, force_vp20=force_vp20)
+    cfg = default_config(solver_type, model_type, loss_type, target_details, force_vp20=force_vp20,
+                         force_vp_cosine=force_vp_cosine)
     cfg["device"] = device
     cfg["use_ema"] = use_ema
     cfg["train_steps"] = training_details["train_steps"]
@@ -281,6 +283,8 @@ def make_model(solver_type, ref_type, loss_type, integrator_type, model_type, ti
     if time_type == "snr":
         cfg["train_timesteps"]["start"] = 1e-4
         cfg["train_timesteps"]["end"] = cfg["sde"]["terminal_t"] - 1e-4
+    if force_vp_cosine:  # benchmark_utils.py:191-192
+        cfg["train_timesteps"]["start"] = 1e-3
     if ("ref" in solver_type) and (integrator_type == "ei"):
         cfg["loss"]["_target_"] = L.EIReferenceSDELoss
     if ("ref" in solver_type) and (integrator_type == "ddpm_like"):

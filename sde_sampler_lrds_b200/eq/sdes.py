@@ -1,6 +1,6 @@
 """SDE coefficient algebra and transition kernels with the reference's class and method names
 (sde_sampler/eq/sdes.py: TorchSDE 14-43, ControlledLangevinSDE 78-114, OU 117-351, ConstOU 354-403,
-ScaledBM 406-424, VP 427-555, PinnedBM 597-678).
+ScaledBM 406-424, VP 427-555, CosineVP 558-594, PinnedBM 597-678).
 
 Time-only quantities (schedules, per-step coefficients, marginal parameters) are 0-dim / 1-D float32 torch
 scalars evaluated with the same operation order as the reference, because they fill the per-step table the
@@ -300,6 +300,25 @@ class VP(OU):
         half = self._dalpha(t_k, t_k_p_1) / 2.0
         var = self.scale_diff_coeff ** 2 * lam_rev * (lk1 / lk)
         return torch.sqrt(1.0 + lam), 2.0 * self.scale_diff_coeff ** 2 * torch.sinh(half), torch.sqrt(var)
+
+
+class CosineVP(VP):
+    """Variance-preserving SDE with the cosine schedule (eq/sdes.py:558-594; conf/sde/vp_cos.yaml).  Only the two scalar
+    functions below differ from VP: everything per particle sees the schedule through the per-step table."""
+
+    def __init__(self, c: float = 0.008, scale_diff_coeff: float = 1.0, **kwargs):
+        super().__init__(scale_diff_coeff=scale_diff_coeff, **kwargs)
+        self.register_buffer("c", torch.tensor(c, dtype=torch.float), persistent=False)
+
+    def _diff_coeff_sq_t(self, t):
+        return torch.pi * torch.tan(0.5 * torch.pi * ((t / self.terminal_t) + self.c) / (1.0 + self.c)) \
+            / (self.terminal_t * (1.0 + self.c))
+
+    def int_drift_coeff_t(self, s, t):
+        raise NotImplementedError("int_drift_coeff_t is not yet implemented")  # as in the reference (eq/sdes.py:582-584)
+
+    def alpha_(self, t):
+        return -2.0 * torch.log(torch.cos(0.5 * torch.pi * ((t / self.terminal_t) + self.c) / (1.0 + self.c)))
 
 
 class PinnedBM(OU):

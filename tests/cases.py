@@ -268,6 +268,21 @@ def case_dis_ei(target="many_modes"):
     return case
 
 
+VPCOS = {"kind": "vpcos", "c": 0.008, "scale": 1.0, "T": 1.0}
+
+
+def case_ei_cosine(method="ei"):
+    """RDS vp-ref with the cosine schedule (make_model(force_vp_cosine=True): conf/sde/vp_cos.yaml, grid start 1e-3,
+    experiments/benchmark_utils.py:172-173, 191-192), mixture reference, uniform grid."""
+    d, M = 9, 5
+    tgt = many_modes(M, d)
+    ref = {"kind": "gmm", "means": tgt["loc"] + 0.1, "variances": 1.3 * tgt["scale"] ** 2, "weights": tgt["weights"].clone()}
+    return {
+        "problem": {"method": method, "sde": VPCOS, "ts": uniform_ts(1.0, 300, start=1e-3), "target": tgt,
+                    "ctrl": ctrl(d, "score", seed=35, out_gain=1.0, gamma=0.05), "ref": ref},
+        "B": 110, "seed": 135, "prior": ("iso", 0.0, 1.0)}
+
+
 def case_ei_phi4_gauss():
     """RDS vp-ref with its default Gaussian reference over the PhiFour lattice (experiments/sample_phi_four_competing.py)."""
     d = 24
@@ -414,6 +429,9 @@ CASES = {
     "dis_ei_many_modes": lambda: case_dis_ei("many_modes"),
     "dis_ei_phi4": lambda: case_dis_ei("phi4"),
     "eubo_dis_ei_many_modes": lambda: _eubo(case_dis_ei("many_modes"), 207),
+    "ei_cosine": lambda: case_ei_cosine("ei"),
+    "em_cosine": lambda: case_ei_cosine("em"),
+    "eubo_ei_cosine": lambda: _eubo(case_ei_cosine("ei"), 208),
     "eubo_em_two_modes": lambda: _eubo(case_em_two_modes("score"), 201),
     "eubo_ei_many_modes": lambda: _eubo(case_ei_many_modes(K=100, B=100), 202),
     "eubo_cmcd_gmm": lambda: _eubo(case_cmcd_gmm(), 203),

@@ -7,7 +7,7 @@ import torch
 from sde_sampler_lrds_b200.distr.gauss import GMM, Gauss, IsotropicGauss
 from sde_sampler_lrds_b200.distr.logistic_regression import LogisticRegression
 from sde_sampler_lrds_b200.distr.phi_four import PhiFour
-from sde_sampler_lrds_b200.eq.sdes import VP, ControlledLangevinSDE, MarginalReference, PinnedBM, ScaledBM
+from sde_sampler_lrds_b200.eq.sdes import VP, ControlledLangevinSDE, CosineVP, MarginalReference, PinnedBM, ScaledBM
 from sde_sampler_lrds_b200.losses import oc
 from sde_sampler_lrds_b200.models.mlp import FourierMLP, TimeEmbed
 from sde_sampler_lrds_b200.models.reparam import CancelDriftCtrl, ClippedCtrl, LerpCtrl, ScoreCtrl
@@ -47,7 +47,9 @@ def build_ctrl(c, d, target, device, prior=None):
 
 
 def build_sde(s, device):
-    if s["kind"] == "vp":
+    if s["kind"] == "vpcos":
+        sde = CosineVP(c=s["c"], scale_diff_coeff=s["scale"], terminal_t=s["T"])
+    elif s["kind"] == "vp":
         sde = VP(diff_coeff_sq_min=s["beta_min"], diff_coeff_sq_max=s["beta_max"], scale_diff_coeff=s["scale"],
                  terminal_t=s["T"])
     elif s["kind"] == "pbm":

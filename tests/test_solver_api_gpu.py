@@ -33,6 +33,7 @@ def _randomise_last_layers(model, gain=0.5):
     ("vp-ref", dict(ref_type="gmm", integrator_type="ei", time_type="snr")),
     ("vp-ref", dict(ref_type="gaussian", integrator_type="ddpm_like", time_type="snr")),
     ("vp-ref", dict(ref_type="default", integrator_type="em", time_type="uniform", model_type="base_zero_init")),
+    ("vp-ref", dict(ref_type="gmm", integrator_type="ei", time_type="uniform", force_vp_cosine=True)),
     ("pbm-ref", dict(ref_type="default", integrator_type="ei", time_type="snr")),
     ("pis_orig", dict(ref_type="default", integrator_type="em", time_type="uniform")),
     ("dds_orig", dict(ref_type="default", integrator_type="em", time_type="uniform")),
