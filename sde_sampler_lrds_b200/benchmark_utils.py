@@ -16,7 +16,7 @@ from pathlib import Path
 import torch
 
 from .distr.delta import Delta
-from .distr.gauss import IsotropicGauss, ManyModes, TwoModes
+from .distr.gauss import BracketTwoModes, IsotropicGauss, ManyModes, TwoModes
 from .distr.logistic_regression import LogisticRegression
 from .distr.phi_four import PhiFour
 from .eq.sdes import VP, ControlledLangevinSDE, CosineVP, PinnedBM, ScaledBM
@@ -58,13 +58,16 @@ def _target_cfg(details: dict) -> dict:
     if name == "two_modes":  # conf/target/two_modes.yaml
         cfg = {"_target_": TwoModes, "dim": 5, "a": 1.0, "centered": False, "ill_conditioned": "not",
                "n_reference_samples": 16384}
+    elif name == "bracket_two_modes":  # conf/target/bracket_two_modes.yaml
+        cfg = {"_target_": BracketTwoModes, "dim": 5, "a": 1.0, "n_reference_samples": 16384}
     elif name == "many_modes":  # conf/target/many_modes.yaml
         cfg = {"_target_": ManyModes, "n_modes": 4, "dim": 8, "seed_loc": 42, "mixture_weight_factor": 3.0, "var": 0.5,
                "n_reference_samples": 10000}
     elif name == "phi_four":  # conf/target/phi_four.yaml
         cfg = {"_target_": PhiFour, "dim": 100, "a": 0.1, "b": 0.0, "dim_phys": 1, "beta": 20.0}
-    elif name in ("sonar", "ionosphere"):  # conf/target/{sonar,ionosphere}.yaml
-        prm = {"sonar": (61, -2.5, 0.5, 4.5), "ionosphere": (34, 4.25, 0.25, 5.25)}[name]
+    elif name in ("sonar", "ionosphere", "cancer", "credit"):  # conf/target/{sonar,ionosphere,cancer,credit}.yaml
+        prm = {"sonar": (61, -2.5, 0.5, 4.5), "ionosphere": (34, 4.25, 0.25, 5.25), "cancer": (31, 31.0, 2.0, 3.75),
+               "credit": (25, 3.25, 0.5, 1.25)}[name]
         data_dir = details.get("data_dir") or os.environ.get("LRDS_DATA_DIR")
         cfg = {"_target_": LogisticRegression, "dim": prm[0], "data_type": name, "intercept_mean": prm[1],
                "intercept_scale": prm[2], "weight_scale": prm[3],

@@ -112,6 +112,17 @@ class TwoModes(GMM):
         super().__init__(dim=dim, loc=loc, scale=scale, mixture_weights=weights, **kwargs)
 
 
+class BracketTwoModes(GMM):
+    """p = 2/3 N(-a 1, C_1) + 1/3 N(+a 1, C_2), (C_1)_i = (C_2)_(dim-i) = linspace(var_min, var_max) (gauss.py:522-553)."""
+
+    def __init__(self, dim=2, a=0.75, equilibrated=False, var_min=0.01, var_max=0.2, **kwargs):
+        loc = torch.stack([-a * torch.ones((dim,)), a * torch.ones((dim,))], dim=0)
+        variance_diag = torch.linspace(var_min, var_max, dim)
+        scale = torch.sqrt(torch.stack([variance_diag, torch.flip(variance_diag, dims=(0,))], dim=0))
+        weights = torch.ones((2,)) / 2.0 if equilibrated else torch.FloatTensor([2, 1]) / 2.0
+        super().__init__(dim=dim, loc=loc, scale=scale, mixture_weights=weights, **kwargs)
+
+
 class ManyModes(GMM):
     """n_modes isotropic components at seeded uniform locations, geometric weights (gauss.py:569-594)."""
 

@@ -90,6 +90,17 @@ def test_reference_free_kernel_shapes(which, d, B, device):
     _check(case, device)
 
 
+@pytest.mark.parametrize("n,p,B,precision", [(569, 30, 40, "f16x3"), (1000, 24, 33, "f16x3"), (1000, 24, 33, "fp32")])
+def test_logistic_regression_at_the_cancer_and_credit_shapes(n, p, B, precision, device):
+    """conf/target/cancer.yaml (569 x 30) and credit.yaml (1000 x 24): more data rows than the regression tensor-core
+    kernel holds in tensor memory (N <= 288), so these run the general kernels (residuals per particle in shared memory)."""
+    case = T.case_cmcd_logreg(n, p, K=4, B=B)
+    _check(case, device, need=0.9, precision=precision)
+    pis = T.case_pis_logreg(n, p, K=4, B=B)
+    pis["problem"]["ts"] = T.uniform_ts(5.0, 100)[:5].clone()
+    _check(pis, device, need=0.9, precision=precision)
+
+
 @pytest.mark.parametrize("n,p,B", [(16, 7, 1), (50, 15, 33), (166, 60, 5), (280, 33, 130)])
 def test_logistic_regression_kernel_shapes(n, p, B, device):
     case = T.case_cmcd_logreg(n, p, K=5, B=B)

@@ -83,6 +83,18 @@ def test_make_model_evaluate(solver_type, kw, device):
     assert abs(got.metrics["eval/lv_loss"] - want["eval/lv_loss"]) < 1e-3 * max(1, want["eval/lv_loss"])
 
 
+def test_make_model_over_the_bracket_two_modes_target(device):
+    from sde_sampler_lrds_b200 import benchmark_utils as BU
+    model = BU.make_model(solver_type="vp-ref", ref_type="default", loss_type="lv", integrator_type="ei",
+                          model_type="target_informed_zero_init", time_type="snr", solver_details={"sigma": 1.0},
+                          target_details=BU.make_target_details("bracket_two_modes", dim=6), training_details=TRAIN,
+                          n_steps=24, device=str(device))
+    _randomise_last_layers(model)
+    res = model.compute_results()
+    assert res.samples.shape == (TRAIN["eval_batch_size"], 6) and torch.isfinite(res.weights).all()
+    assert math.isfinite(res.metrics["eval/elbo"]) and math.isfinite(res.log_norm_const_preds["log_norm_const_is"])
+
+
 @pytest.mark.parametrize("name", ["dis_many_modes_lerp", "dis_many_modes_langevin", "dis_logreg_lerp", "dis_many_modes_ito"])
 def test_drift_model_forward_matches_the_oracle(name, device):
     """``generative_ctrl(t, x)`` (lrds_ctrl_forward) of ScoreCtrl / CancelDriftCtrl / LerpCtrl against the oracle's
