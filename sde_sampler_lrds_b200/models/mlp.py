@@ -151,9 +151,10 @@ class FourierMLP(Model):
             hit = self._packed[key] = (m, (keep, image))
         return hit
 
-    def bias_rows(self, taus: torch.Tensor) -> torch.Tensor:
-        """[S][64] host rows input_embed.bias + TimeEmbed(tau) (the reference adds embed_x + embed_t, mlp.py:139)."""
-        return self.timestep_embed.rows(taus, "cpu") + self.input_embed.bias.detach().to("cpu", torch.float32)
+    def bias_rows(self, taus: torch.Tensor, device="cpu") -> torch.Tensor:
+        """[S][64] rows input_embed.bias + TimeEmbed(tau) (the reference adds embed_x + embed_t, mlp.py:139), evaluated
+        on ``device`` (the host when a plan is built; the parameters' device when a training step refreshes it)."""
+        return self.timestep_embed.rows(taus, device) + self.input_embed.bias.detach().to(device, torch.float32)
 
     def forward(self, t: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
         from ..pack import ctrl_forward

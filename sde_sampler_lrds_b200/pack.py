@@ -96,15 +96,15 @@ def resolve_log_prob(fn):
     raise NotImplementedError("log-density callable must be a bound method of a kernel-backed Distribution")
 
 
-def time_rows(info: CtrlInfo, taus: torch.Tensor):
-    """Host rows (bias1[S][64], gamma[S]) of the time-only parts of the control for times ``taus``."""
-    bias1 = info.base.bias_rows(taus)
+def time_rows(info: CtrlInfo, taus: torch.Tensor, device="cpu"):
+    """Rows (bias1[S][64], gamma[S]) of the time-only parts of the control for times ``taus``, evaluated on ``device``."""
+    bias1 = info.base.bias_rows(taus, device)
     if info.kind != N.CTRL_CLIPPED and info.score_model is not None:
-        gamma = info.score_model.rows(taus, "cpu").reshape(-1)
+        gamma = info.score_model.rows(taus, device).reshape(-1)
         if info.clip_model is not None:
             gamma = gamma.clip(-info.clip_model, info.clip_model)
     else:
-        gamma = torch.ones(taus.numel())
+        gamma = torch.ones(taus.numel(), device=device)
     return bias1, gamma
 
 
@@ -232,15 +232,17 @@ def finish_table(table: torch.Tensor, info: CtrlInfo, taus: torch.Tensor, device
 def refresh_ctrl(plan: "Plan", info: CtrlInfo, device):
     """Re-packs what depends on the control's parameters into a cached plan: the weight block / tensor-core image
     (keep[0], set by fill_ctrl) and the TimeEmbed columns of the device table (bias rows, gamma), in place and ordered
-    on the current stream behind earlier launches that read them."""
+    on the current stream behind earlier launches that read them.  The rows are evaluated on the device here (no
+    parameter round trip through the host in a training step); a freshly built plan evaluates them with the same torch
+    ops on the host, which agrees to float32 rounding."""
     spec = plan.spec
     mlp, k = info.base.lrds_mlp(device, spec.precision)
     spec.mlp = mlp
     plan.keep[0] = k
     table = next(t for t in plan.keep if isinstance(t, torch.Tensor) and hasattr(t, "_lrds_ctrl_taus"))
-    bias1, gamma = time_rows(info, table._lrds_ctrl_taus)
-    table[:, N.STEP_BIAS1:N.STEP_BIAS1 + N.CHANNELS] = bias1.to(table.device)
-    table[:, N.STEP_GAMMA] = gamma.to(table.device)
+    bias1, gamma = time_rows(info, table._lrds_ctrl_taus, table.device)
+    table[:, N.STEP_BIAS1:N.STEP_BIAS1 + N.CHANNELS] = bias1
+    table[:, N.STEP_GAMMA] = gamma
 
 
 def run_rollout(plan: Plan, x0: torch.Tensor, noise: torch.Tensor | None, seed: int, particle_offset: int,

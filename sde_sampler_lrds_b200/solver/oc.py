@@ -150,7 +150,7 @@ class TrainableDiff(torch.nn.Module):
         loss_ok = loss.isfinite() if self.max_loss is None else loss.abs() <= self.max_loss
         grads = [p.grad for p in self.trainable_parameters() if p.grad is not None]
         if self.max_grad is None:
-            grad_ok = all(g.isfinite().all() for g in grads)
+            grad_ok = bool(torch.stack([g.isfinite().all() for g in grads]).all())  # one host synchronisation
         else:
             max_grad = torch.stack([g.abs().max() for g in grads]).max()
             grad_ok = max_grad <= self.max_grad

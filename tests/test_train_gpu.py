@@ -46,7 +46,8 @@ def test_lv_gradient_matches_oracle_and_reference(name, precision, device):
 def test_cached_plan_follows_parameter_updates(device):
     """A parameter update (an optimiser step) must not rebuild the O(K) host side of a rollout plan (tens of
     milliseconds of scalar schedule formulas) - but the next rollout must run with the new weights and TimeEmbed rows: the
-    cached plan refreshed in place equals a freshly built one, bit for bit."""
+    cached plan refreshed in place equals a freshly built one (to float32 rounding: the refresh evaluates the TimeEmbed
+    rows on the device, a fresh plan on the host)."""
     from tests.cases import CASES
     from tests.product_builders import Built
     case = CASES["ei_many_modes"]()
@@ -62,7 +63,7 @@ def test_cached_plan_follows_parameter_updates(device):
     fresh = Built(case, device, "f16x3")
     fresh.ctrl.load_state_dict(built.ctrl.state_dict())
     _, r3, _ = fresh.simulate(x0, noise)
-    assert torch.equal(r2, r3) and not torch.equal(r1, r2)
+    assert ((r2 - r3).abs() / r3.abs().clamp(min=1.0)).max() < 1e-5 and ((r1 - r2).abs() / r2.abs().clamp(min=1.0)).max() > 1e-3
 
 
 @pytest.mark.parametrize("solver_type, kw", [
