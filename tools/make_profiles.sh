@@ -1,5 +1,5 @@
 #!/bin/bash
-# Regenerates the tracked profiles/ artefacts of a round from gpurun_out/ (tools/bin/run10.sh):  tools/make_profiles.sh r01
+# Regenerates the tracked profiles/ artefacts of a round from gpurun_out/ (tools/run_round_profiles.sh):  tools/make_profiles.sh r01
 set -e
 R=${1:-r01}
 tools/prof_report.sh gpurun_out/prof_mix_final.ncu-rep lrds_tc_mix_a rollout_mix_kernelILi4ENS_6MixCfgILb0ELi1ELi2ELb0 40 > /tmp/mixsum.md 2>/dev/null
