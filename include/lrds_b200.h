@@ -17,8 +17,9 @@
 extern "C" {
 #endif
 
-#define LRDS_ABI_VERSION 6
+#define LRDS_ABI_VERSION 7
 #define LRDS_CHANNELS 64 /* FourierMLP / TimeEmbed width, conf/model/base/fouriermlp.yaml:4 */
+#define LRDS_MAX_DIM_PAD 1024 /* largest d_pad the operand packers accept */
 
 typedef enum {
   LRDS_OK = 0,
@@ -140,7 +141,15 @@ typedef struct {
                               * chunks c (i < 8: -1/var_{m,8c+i}; i >= 8: mu/var_{m,8c+i-8}), multiplied by the power of two
                               * that puts its largest entry into [2^14, 2^15) and split into fp16 hi | lo parts, each in the
                               * K-major no-swizzle tcgen05 layout [m/8][n][m%8] with m padded to a multiple of 16; then 16
-                              * bytes whose first float is the un-scale.  16-byte aligned. */
+                              * bytes whose first float is the un-scale.  Behind it the LOGIT image of the block: the
+                              * responsibilities r = softmax_m(logc_m - q_m / 2) of a mixture whose modes share their
+                              * variances need only  logit_m = c_m + x . wc_m  (the x^2 term is mode-independent), with
+                              * wc_mj = mu_mj/var_mj - mean_m(mu_mj/var_mj),  c_m = logc_m - sum_j mu_mj^2/var_mj / 2:
+                              * wc as a power-of-two scaled fp16 hi | lo matrix [j/8][m][j%8] (rows m padded to a multiple
+                              * of 16, K = j padded to a multiple of 16), then c_m (fp32, -inf for padded modes), then four
+                              * floats {un-scale, max_m |wc_m|_2, max_m |c_m|, 1.0 if the variances are shared else 0.0}.
+                              * The kernels use it only when that flag is set and a per-particle error bound allows;
+                              * otherwise they evaluate the quadratic forms exactly (sn).  16-byte aligned. */
   int64_t step_stride_mix_tc;/* BYTES between consecutive steps of mix_tc */
 } lrds_gmm;
 
@@ -223,9 +232,10 @@ int lrds_rollout(const lrds_spec* spec, const float* x0, const float* noise, uin
  * every weight update. */
 int64_t lrds_tc_image_bytes(int32_t d, int32_t num_hidden, int32_t precision);
 int64_t lrds_gmm_mix_tc_bytes(int32_t M, int32_t d_pad); /* one block of lrds_gmm.mix_tc */
-/* Builds lrds_gmm.mix_tc from gmm->mu / ivar (M > 1): `steps` consecutive blocks (1 for a static mixture, K for the
- * time-marginal reference, read with step_stride_param) of lrds_gmm_mix_tc_bytes(M, d_pad) bytes each. */
-int lrds_pack_gmm_mix_tc(const lrds_gmm* gmm, int32_t d_pad, int32_t steps, void* image_out, void* stream);
+/* Builds lrds_gmm.mix_tc from gmm->logc / mu / ivar (M > 1): `steps` consecutive blocks (1 for a static mixture, K for
+ * the time-marginal reference, read with step_stride_logc / step_stride_param) of lrds_gmm_mix_tc_bytes(M, d_pad) bytes
+ * each; `d` = the number of real dims (<= d_pad). */
+int lrds_pack_gmm_mix_tc(const lrds_gmm* gmm, int32_t d, int32_t d_pad, int32_t steps, void* image_out, void* stream);
 /* Builds lrds_logreg.x_tc (lrds_logreg_tc_bytes(N, p) bytes) from logreg->X ([N][d_pad]) and logreg->y. */
 int64_t lrds_logreg_tc_bytes(int32_t N, int32_t p);
 int lrds_pack_logreg_tc(const lrds_logreg* logreg, int32_t d_pad, void* image_out, void* stream);

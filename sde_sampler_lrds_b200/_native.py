@@ -15,10 +15,11 @@ import torch
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIB_PATH = os.path.join(CSRC, "liblrds_b200.so")
+# LRDS_B200_LIB: another build of the same library (A/B timing of kernel variants by the tools; same C ABI)
+LIB_PATH = os.environ.get("LRDS_B200_LIB") or os.path.join(CSRC, "liblrds_b200.so")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 
-ABI_VERSION = 6
+ABI_VERSION = 7
 CHANNELS = 64
 STEP_STRIDE = 80
 (STEP_A, STEP_B, STEP_C, STEP_DT, STEP_SQRT_DT, STEP_W_COST, STEP_W_ITO, STEP_GAMMA, STEP_FRAC, STEP_SIGU,
@@ -83,17 +84,20 @@ COMPILE_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo
 LINK_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-Xcompiler", "-fPIC"]
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    """Compiles csrc/*.cu into csrc/liblrds_b200.so for sm_100a (cross-compiles without a GPU)."""
+def build(force: bool = False, verbose: bool = False, extra_flags=(), out: str | None = None) -> str:
+    """Compiles csrc/*.cu into csrc/liblrds_b200.so for sm_100a (cross-compiles without a GPU).
+    ``extra_flags`` / ``out``: instrumented builds of the tools (e.g. -DLRDS_MIX_TIMING) under another file name."""
     srcs = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cu", ".cuh", ".h"))]
     srcs.append(os.path.join(INCLUDE, "lrds_b200.h"))
-    if not force and os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(s) for s in srcs):
-        return LIB_PATH
+    lib_path = out or os.path.join(CSRC, "liblrds_b200.so")
+    if not force and os.path.exists(lib_path) and all(os.path.getmtime(lib_path) >= os.path.getmtime(s) for s in srcs):
+        return lib_path
     units = [f for f in sorted(os.listdir(CSRC)) if f.endswith(".cu")]
     objs, procs = [], []
+    tag = "" if out is None else "." + os.path.basename(out)
     for u in units:  # one nvcc per translation unit, in parallel
-        obj = os.path.join(CSRC, u[:-3] + ".o")
-        cmd = ["nvcc", *COMPILE_FLAGS, "-I", INCLUDE, "-c", "-o", obj, os.path.join(CSRC, u)]
+        obj = os.path.join(CSRC, u[:-3] + tag + ".o")
+        cmd = ["nvcc", *COMPILE_FLAGS, *extra_flags, "-I", INCLUDE, "-c", "-o", obj, os.path.join(CSRC, u)]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         procs.append((u, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
@@ -104,14 +108,14 @@ def build(force: bool = False, verbose: bool = False) -> str:
         log += out
         if p.returncode != 0:
             raise RuntimeError(f"nvcc failed on {u}:\n" + out)
-    res = subprocess.run(["nvcc", *LINK_FLAGS, "-o", LIB_PATH, *objs], capture_output=True, text=True)
+    res = subprocess.run(["nvcc", *LINK_FLAGS, "-o", lib_path, *objs], capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("link failed:\n" + res.stdout + res.stderr)
     for o in objs:  # only the .so travels with the repository snapshot
         os.remove(o)
     if verbose:
         print(log)
-    return LIB_PATH
+    return lib_path
 
 
 _lib = None
@@ -139,7 +143,7 @@ def lib():
                 L.lrds_estimator_partials.argtypes = [FP, C.c_int32, FP, FP, FP]
                 L.lrds_gmm_mix_tc_bytes.restype = C.c_int64
                 L.lrds_gmm_mix_tc_bytes.argtypes = [C.c_int32, C.c_int32]
-                L.lrds_pack_gmm_mix_tc.argtypes = [C.POINTER(Gmm), C.c_int32, C.c_int32, FP, FP]
+                L.lrds_pack_gmm_mix_tc.argtypes = [C.POINTER(Gmm), C.c_int32, C.c_int32, C.c_int32, FP, FP]
                 L.lrds_logreg_tc_bytes.restype = C.c_int64
                 L.lrds_logreg_tc_bytes.argtypes = [C.c_int32, C.c_int32]
                 L.lrds_pack_logreg_tc.argtypes = [C.POINTER(LogReg), C.c_int32, FP, FP]

@@ -193,14 +193,28 @@ __device__ __forceinline__ int pow2_exponent_for(float amax) {  // amax * 2^k in
   return k > 100 ? 100 : (k < -100 ? -100 : k);
 }
 
+__device__ double block_sum_256(double v, double* red) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double r = 0.0;
+  for (int i = 0; i < (int)(blockDim.x >> 5); ++i) r += red[i];
+  return r;
+}
+
 // one block per step
-__global__ void __launch_bounds__(256) pack_gmm_mix_kernel(const lrds_gmm g, int d_pad, uint8_t* __restrict__ out) {
+__global__ void __launch_bounds__(256) pack_gmm_mix_kernel(const lrds_gmm g, int d, int d_pad, uint8_t* __restrict__ out) {
   __shared__ float red[8];
+  __shared__ double redd[8];
+  __shared__ float wbar[LRDS_MAX_DIM_PAD];
+  __shared__ float cm[64], wn[64];
   const int Mp = (g.M + 15) / 16 * 16, N2 = 2 * d_pad;
   const uint32_t part_bytes = (uint32_t)(Mp / 8) * (uint32_t)N2 * 16u;
   const float* mu = g.mu + (int64_t)blockIdx.x * g.step_stride_param;
   const float* iv = g.ivar + (int64_t)blockIdx.x * g.step_stride_param;
-  uint8_t* o = out + (int64_t)blockIdx.x * (2 * (int64_t)part_bytes + 16);
+  const float* logc = g.logc + (int64_t)blockIdx.x * g.step_stride_logc;
+  uint8_t* o = out + (int64_t)blockIdx.x * lrds::gmm_mix_tc_bytes(g.M, d_pad);
   auto value = [&](int m, int n) -> float {
     if (m >= g.M) return 0.f;
     const int c = n >> 4, i = n & 15, j = 8 * c + (i & 7);
@@ -217,6 +231,69 @@ __global__ void __launch_bounds__(256) pack_gmm_mix_kernel(const lrds_gmm g, int
     put_hi_lo(o, part_bytes, (uint32_t)(m >> 3) * (uint32_t)N2 * 16u + (uint32_t)n * 16u + (uint32_t)(m & 7) * 2u, value(m, n) * sc);
   }
   if (threadIdx.x < 4) reinterpret_cast<float*>(o + 2 * part_bytes)[threadIdx.x] = threadIdx.x == 0 ? ldexpf(1.0f, -k) : 0.f;
+
+  // ---- logit image: rows = modes, K = dims; wc_mj = mu_mj / var_mj - mean over the modes
+  uint8_t* ol = o + lrds::gmm_mix_contr_bytes(g.M, d_pad);
+  const uint32_t lpart = lrds::gmm_mix_logit_part_bytes(g.M, d_pad);
+  const int Kin = (d_pad + 15) / 16 * 16;
+  float shared_dev = 0.f;  // largest relative deviation of a mode's 1/var from mode 0's
+  for (int j = threadIdx.x; j < d_pad; j += blockDim.x) {
+    double acc = 0.0;
+    for (int m = 0; m < g.M; ++m) acc += (double)mu[(int64_t)m * d_pad + j] * (double)iv[(int64_t)m * d_pad + j];
+    wbar[j] = j < d ? (float)(acc / g.M) : 0.f;
+    if (j < d)
+      for (int m = 1; m < g.M; ++m)
+        shared_dev = fmaxf(shared_dev, fabsf(iv[(int64_t)m * d_pad + j] - iv[j]) / fabsf(iv[j]));
+  }
+  shared_dev = block_max_256(shared_dev, red);  // (contains the __syncthreads that publishes wbar)
+  auto wc = [&](int m, int j) -> float {
+    if (m >= g.M || j >= d) return 0.f;
+    return (float)((double)mu[(int64_t)m * d_pad + j] * (double)iv[(int64_t)m * d_pad + j] - (double)wbar[j]);
+  };
+  float lmax = 0.f;
+  for (int idx = threadIdx.x; idx < Mp * Kin; idx += blockDim.x) lmax = fmaxf(lmax, fabsf(wc(idx / Kin, idx % Kin)));
+  lmax = block_max_256(lmax, red);
+  const int kl = pow2_exponent_for(lmax);
+  const float scl = ldexpf(1.0f, kl);
+  for (int idx = threadIdx.x; idx < Mp * Kin; idx += blockDim.x) {
+    const int m = idx / Kin, j = idx % Kin;
+    put_hi_lo(ol, lpart, (uint32_t)(j >> 3) * (uint32_t)Mp * 16u + (uint32_t)m * 16u + (uint32_t)(j & 7) * 2u, wc(m, j) * scl);
+  }
+  // c_m = logc_m - sum_j mu^2 / var / 2 and |wc_m|_2, one warp per mode at a time
+  for (int m = threadIdx.x >> 5; m < Mp; m += blockDim.x >> 5) {
+    double q = 0.0, w2 = 0.0;
+    if (m < g.M)
+      for (int j = threadIdx.x & 31; j < d; j += 32) {
+        const double mm = mu[(int64_t)m * d_pad + j], a = iv[(int64_t)m * d_pad + j];
+        q += mm * mm * a;
+        const double w = wc(m, j);
+        w2 += w * w;
+      }
+    for (int off = 16; off > 0; off >>= 1) {
+      q += __shfl_xor_sync(0xffffffffu, q, off);
+      w2 += __shfl_xor_sync(0xffffffffu, w2, off);
+    }
+    if ((threadIdx.x & 31) == 0) {
+      cm[m] = m < g.M ? (float)((double)logc[m] - 0.5 * q) : -INFINITY;
+      wn[m] = (float)sqrt(w2);
+    }
+  }
+  __syncthreads();
+  float* cdst = reinterpret_cast<float*>(ol + 2 * lpart);
+  for (int m = threadIdx.x; m < Mp; m += blockDim.x) cdst[m] = cm[m];
+  if (threadIdx.x == 0) {
+    float wnmax = 0.f, cmax = 0.f;
+    for (int m = 0; m < g.M; ++m) {
+      wnmax = fmaxf(wnmax, wn[m]);
+      if (isfinite(cm[m])) cmax = fmaxf(cmax, fabsf(cm[m]));
+    }
+    float* t2 = cdst + Mp;
+    t2[0] = ldexpf(1.0f, -kl);
+    t2[1] = wnmax;
+    t2[2] = cmax;
+    t2[3] = shared_dev <= 1e-6f ? 1.0f : 0.f;
+  }
+  (void)redd;
 }
 
 __global__ void __launch_bounds__(256) pack_logreg_kernel(const lrds_logreg L, int d_pad, uint8_t* __restrict__ out) {
@@ -565,10 +642,11 @@ int64_t lrds_gmm_mix_tc_bytes(int32_t M, int32_t d_pad) {
   return (int64_t)lrds::gmm_mix_tc_bytes(M, d_pad);
 }
 
-int lrds_pack_gmm_mix_tc(const lrds_gmm* gmm, int32_t d_pad, int32_t steps, void* image_out, void* stream) {
-  if (!gmm || !image_out || !gmm->mu || !gmm->ivar || gmm->M < 2 || d_pad < 8 || d_pad % 8 != 0 || steps < 1)
+int lrds_pack_gmm_mix_tc(const lrds_gmm* gmm, int32_t d, int32_t d_pad, int32_t steps, void* image_out, void* stream) {
+  if (!gmm || !image_out || !gmm->mu || !gmm->ivar || !gmm->logc || gmm->M < 2 || gmm->M > 64 || d < 1 || d > d_pad || d_pad < 8 ||
+      d_pad % 8 != 0 || d_pad > LRDS_MAX_DIM_PAD || steps < 1)
     return fail(LRDS_ERR_INVALID, "pack_gmm_mix_tc: bad arguments");
-  pack_gmm_mix_kernel<<<steps, 256, 0, (cudaStream_t)stream>>>(*gmm, d_pad, static_cast<uint8_t*>(image_out));
+  pack_gmm_mix_kernel<<<steps, 256, 0, (cudaStream_t)stream>>>(*gmm, d, d_pad, static_cast<uint8_t*>(image_out));
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "pack_gmm_mix_tc launch");
   g_launches.fetch_add(1);

@@ -14,13 +14,32 @@
 // GEMM of the network the A region is free: [0,32) holds R = (r_target hi | lo | r_reference hi | lo), 8 packed columns
 // each, [32,64) the 8-dim chunk of the contraction (target a8 b8 | reference a8 b8) while D still holds the network's
 // output.  One chunk is in flight at a time: chunk c+1 is issued as soon as every warp of the tile has read chunk c.
+//
+// Hand-offs.  A tile's tensor-core batches (the network's GEMMs, the logit GEMM, the contraction chunks) are issued by
+// whichever of its warps arrives LAST: every warp stores its operand rows / reads its accumulator rows, increments the
+// tile's shared-memory counter (release / acquire) and goes on; the warp that completes the count issues the batch
+// from warp-uniform registers (elect.sync) and commits it to the tile's mbarrier, on which the tile's warps wait
+// only when they need the result.  The per-step operand buffers are refilled (TMA) by the CTA's last warp to finish a
+// step.  There is no CTA-wide or tile-wide barrier inside the time loop: warps run out of phase.
+//
+// Responsibilities.  r = softmax_m(logc_m - q_m / 2).  For a mixture whose modes share their variances (every
+// ManyModes / TwoModes target of the reference, and the VP time-marginal of a reference built from one) the x^2 term of
+// q_m is mode-independent, so logit_m = c_m + x . wc_m up to a common shift: one more [128 x K] . [K x 16] GEMM per
+// mixture on the x operand the network's first GEMM needs anyway.  Its rounding error grows with |x| |wc| (fp32
+// accumulation of large terms), which only matters when two modes are close to a tie; so every particle checks the
+// bound  kappa (|x|_2 max_m |wc_m|_2 + max_m |c_m|) min(1, 4 (1 - r_max)) <= tau  and a warp with one particle over it
+// (or a mixture with per-mode variances) evaluates the exact quadratic forms on the SIMT pipes instead
+// (gmm_pass1_pair), behind the first two GEMMs of the network.
 #pragma once
 #include "lrds_rollout_tc.cuh"
 
 namespace lrds {
 
 constexpr int MIX_MAX_M = 16;
-constexpr int MIX_MAX_WARPS = 16;  // 3.5 tiles: one wave for 65536 particles on 148 SMs (128 registers: four warps share one 16K-register SM sub-partition)
+constexpr int MIX_MAX_WARPS = 16;   // 3.5 tiles = 14 warps: one wave for 65536 particles on 148 SMs (128 registers)
+constexpr int MIX_TAIL_BYTES = 32;  // the kernel's hand-off counters: tile[4] | step buffer[2]
+constexpr float MIX_LOGIT_KAPPA = 9.5367431640625e-07f;  // 2^-20: error of a 3-pass fp16 logit per unit of |x| |wc| + |c| (tests/test_mix_logit_gpu.py)
+constexpr float MIX_LOGIT_TAU = 2e-5f;                   // accepted logit error where modes tie (= the exact forms' own fp32 error at q ~ 50)
 
 // Compile-time configuration of the kernel: which of the two score contractions run on the tensor core, and the update.
 //   TGT  1: ScoreCtrl over a mixture target (contraction on tcgen05)   2: ScoreCtrl over the PhiFour lattice (stencil)
@@ -174,17 +193,119 @@ __device__ __forceinline__ float gmm_logp_any(const GmmView& g, int d, int dp, c
   return gmm_pass1_pair(g, d, dp, x, r);
 }
 
-// ---- tensor-core side of the contraction (extends the drift-network policy; same tile, mbarrier and phase) --------
+// Optional phase timers (-DLRDS_MIX_TIMING, tools only): lane 0 of every particle warp accumulates the cycles between
+// consecutive marks in shared memory; CTAs 0 and gridDim.x / 2 dump them to g_mix_timing at the end.
+#ifdef LRDS_MIX_TIMING
+static __device__ unsigned long long g_mix_timing[2 * 16 * 16];
+struct MixTm {
+  unsigned long long* w;
+  long long t;
+  __device__ __forceinline__ void start() { t = clock64(); }
+  __device__ __forceinline__ void mark(int i) {
+    const long long n = clock64();
+    if ((threadIdx.x & 31) == 0) w[i] += (unsigned long long)(n - t);
+    t = n;
+  }
+  __device__ __forceinline__ void count(int i, bool hit) {  // warp-steps that evaluated the exact quadratic forms
+    if ((threadIdx.x & 31) == 0 && hit) w[i] += 1ull;
+  }
+};
+#else
+struct MixTm {
+  __device__ __forceinline__ void start() {}
+  __device__ __forceinline__ void mark(int) {}
+  __device__ __forceinline__ void count(int, bool) {}
+};
+#endif
+
+// ---- tensor-core side: operand stores, hand-offs, batches, accumulator reads ------------------------------------------
 template <int PREC>
 struct MixTc : TcMlp<PREC> {
   using Base = TcMlp<PREC>;
   static constexpr uint32_t kRCol = 0, kDCol = 32;
-  uint32_t lbo;  // bytes between the two 16-byte K chunks (modes 0-7 | 8-15) of an image part: 2 d_pad * 16
-  uint32_t part_bytes;
+  uint32_t* cnt;        // the tile's hand-off counter
+  uint32_t next;        // its value that makes this warp the last arriver of its next hand-off
+  uint32_t tile_warps;
+  uint32_t lbo, part_bytes;  // contraction image: bytes between the K chunks (modes 0-7 | 8-15), bytes of one (hi | lo) part
+  uint32_t lg_part;          // logit image: bytes of one (hi | lo) part
+  MixTm tm;
 
-  // r (16 responsibilities) -> fp16 (hi, lo) A operand `which` (0 target, 1 reference)
-  __device__ __forceinline__ void store_r(int which, const float (&r)[MIX_MAX_M]) {
-    uint32_t ph[8], pl[8];
+  // This warp's part of the tile's next batch is in place (A rows stored / accumulator rows read).  The last warp of
+  // the tile to say so issues the batch `f` and commits it to the tile's mbarrier; nobody blocks here.
+  template <class F>
+  __device__ __forceinline__ void arrive_issue(F&& f) {
+    ptx::tmem_wait_st();
+    ptx::tc_fence_before();
+    __syncwarp();
+    uint32_t old = 0;
+    if ((threadIdx.x & 31) == 0) old = ptx::atom_add_acq_rel(cnt, 1u);
+    old = __shfl_sync(0xffffffffu, old, 0);
+    if (old == next) {
+      ptx::tc_fence_after();
+      if (ptx::elect_one()) {
+        f();
+        ptx::mma_commit(this->bar);
+      }
+      __syncwarp();
+    }
+    next += tile_warps;
+  }
+
+  // one layer of the network: D = A . W^T as three passes of fp16 (hi, lo) products, small terms first
+  __device__ __forceinline__ void gemm(uint32_t b_off, int K, int N) const {
+    const uint32_t idesc = ptx::make_idesc_f16(128, N);
+    const uint32_t dcol = this->tm_tile + this->d_col();
+    const int ksteps = K / this->L.kstep;
+    const uint32_t kbytes = 2u * (uint32_t)N * 16u;  // one MMA consumes two 16-byte K chunks
+    uint32_t acc = 0;
+#pragma unroll
+    for (int pass = 0; pass < 3; ++pass) {
+      const int a_part = pass == 0 ? 1 : 0, b_part = pass == 1 ? 1 : 0;
+      const uint32_t abase = this->tm_tile + this->a_col(a_part);
+      const uint32_t bbase = this->img_s + (uint32_t)b_part * this->L.part_bytes + b_off;
+      for (int ks = 0; ks < ksteps; ++ks) {
+        const uint64_t bdesc = ptx::make_smem_desc(bbase + (uint32_t)ks * kbytes, (uint32_t)N * 16u, 128u);
+        ptx::mma_bf16_ts(dcol, abase + ks * 8, bdesc, idesc, acc);
+        acc = 1;
+      }
+    }
+  }
+  // logits of mixture `which` (0 target, 1 reference): accumulator columns [16 which, 16 which + 16) <- x . wc^T
+  __device__ __forceinline__ void logit(int which, uint32_t img) const {
+    const uint32_t idesc = ptx::make_idesc_f16(128, MIX_MAX_M);
+    const uint32_t dcol = this->tm_tile + this->d_col() + (uint32_t)which * MIX_MAX_M;
+    const int ksteps = this->L.Kin / 16;
+    uint32_t acc = 0;
+#pragma unroll
+    for (int pass = 0; pass < 3; ++pass) {
+      const int a_part = pass == 0 ? 1 : 0, b_part = pass == 1 ? 1 : 0;
+      const uint32_t abase = this->tm_tile + this->a_col(a_part);
+      const uint32_t bbase = img + (uint32_t)b_part * lg_part;
+      for (int ks = 0; ks < ksteps; ++ks) {
+        const uint64_t bdesc = ptx::make_smem_desc(bbase + (uint32_t)ks * (2u * MIX_MAX_M * 16u), MIX_MAX_M * 16u, 128u);
+        ptx::mma_bf16_ts(dcol, abase + ks * 8, bdesc, idesc, acc);
+        acc = 1;
+      }
+    }
+  }
+  // chunk c of the contractions -> columns [32, 64) of the tile; images = shared-window addresses of the (hi | lo) blocks
+  template <bool TGT, bool REF>
+  __device__ __forceinline__ void chunk(int c, uint32_t tgt_img, uint32_t ref_img) const {
+    const uint32_t idesc = ptx::make_idesc_f16(128, 16);
+#pragma unroll
+    for (int which = TGT ? 0 : 1; which < (REF ? 2 : 1); ++which) {
+      const uint32_t img = (which ? ref_img : tgt_img) + (uint32_t)c * 256u;  // 16 rows of 16 bytes per chunk
+      const uint32_t dcol = this->tm_tile + kDCol + which * 16;
+      const uint32_t a_hi = this->tm_tile + kRCol + which * 16, a_lo = a_hi + 8;
+      const uint64_t b_hi = ptx::make_smem_desc(img, lbo, 128u), b_lo = ptx::make_smem_desc(img + part_bytes, lbo, 128u);
+      ptx::mma_bf16_ts(dcol, a_lo, b_hi, idesc, 0);
+      ptx::mma_bf16_ts(dcol, a_hi, b_lo, idesc, 1);
+      ptx::mma_bf16_ts(dcol, a_hi, b_hi, idesc, 1);
+    }
+  }
+
+  // r (16 responsibilities) -> packed fp16 (hi [0,8) | lo [8,16)) A-operand words
+  static __device__ __forceinline__ void pack_r(const float (&r)[MIX_MAX_M], uint32_t (&p)[16]) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       u64 hi, lo;
@@ -192,40 +313,79 @@ struct MixTc : TcMlp<PREC> {
       float h0, h1, l0, l1;
       f2::unpack(hi, h0, h1);
       f2::unpack(lo, l0, l1);
-      ph[i] = ptx::pack_f16x2(h0, h1);
-      pl[i] = ptx::pack_f16x2(l0, l1);
+      p[i] = ptx::pack_f16x2(h0, h1);
+      p[8 + i] = ptx::pack_f16x2(l0, l1);
     }
-    ptx::tmem_st8(this->tm_lane + kRCol + which * 16, ph);
-    ptx::tmem_st8(this->tm_lane + kRCol + which * 16 + 8, pl);
   }
-
-  // chunk c of both contractions -> columns [32, 64); images = shared-window addresses of the (hi | lo) blocks
-  // Named-barrier hand-off: every warp of the tile has stored its R rows / read the previous chunk.  (An mbarrier
-  // hand-off, where only the issuing thread waits, measured 4 % slower.)
-  template <bool TGT = true, bool REF = true>
-  __device__ __forceinline__ void issue_chunk(int c, uint32_t tgt_img, uint32_t ref_img) {
-    ptx::tmem_wait_st();
-    ptx::tc_fence_before();
-    ptx::bar_sync(this->bar_id, this->bar_threads);
-    if (this->issuer) {
-      ptx::tc_fence_after();
-      const uint32_t idesc = ptx::make_idesc_f16(128, 16);
-#pragma unroll
-      for (int which = TGT ? 0 : 1; which < (REF ? 2 : 1); ++which) {
-        const uint32_t img = (which ? ref_img : tgt_img) + (uint32_t)c * 256u;  // 16 rows of 16 bytes per chunk
-        const uint32_t dcol = this->tm_tile + kDCol + which * 16;
-        const uint32_t a_hi = this->tm_tile + kRCol + which * 16, a_lo = a_hi + 8;
-        const uint64_t b_hi = ptx::make_smem_desc(img, lbo, 128u), b_lo = ptx::make_smem_desc(img + part_bytes, lbo, 128u);
-        ptx::mma_bf16_ts(dcol, a_lo, b_hi, idesc, 0);
-        ptx::mma_bf16_ts(dcol, a_hi, b_lo, idesc, 1);
-        ptx::mma_bf16_ts(dcol, a_hi, b_hi, idesc, 1);
-      }
-      ptx::mma_commit(this->bar);
-    }
+  // A operand `which` (0 target, 1 reference) of the contraction <- packed responsibilities
+  __device__ __forceinline__ void store_r(int which, const uint32_t (&p)[16]) {
+    ptx::tmem_st16(this->tm_lane + kRCol + which * 16, p);
   }
   __device__ __forceinline__ void load_chunk(uint32_t (&m)[32]) {
     ptx::tmem_ld32(this->tm_lane + kDCol, m);
     ptx::tmem_wait_ld();
+  }
+
+  // Responsibilities from the logit accumulator (16 raw columns `acc` of this particle).  `tail` = the logit image's
+  // c_m | {un-scale, max |wc_m|_2, max |c_m|, shared}.  Returns whether the error bound accepts them for this particle.
+  static __device__ __forceinline__ bool softmax_logits(const uint32_t* acc, const PPtr<true>& tail, float xnorm, uint32_t (&p)[16]) {
+    float r[MIX_MAX_M];
+    const float4 t2 = tail.ld4(MIX_MAX_M / 4);
+#pragma unroll
+    for (int q = 0; q < MIX_MAX_M / 4; ++q) {
+      const float4 c = tail.ld4(q);
+      r[4 * q + 0] = fmaf(__uint_as_float(acc[4 * q + 0]), t2.x, c.x);
+      r[4 * q + 1] = fmaf(__uint_as_float(acc[4 * q + 1]), t2.x, c.y);
+      r[4 * q + 2] = fmaf(__uint_as_float(acc[4 * q + 2]), t2.x, c.z);
+      r[4 * q + 3] = fmaf(__uint_as_float(acc[4 * q + 3]), t2.x, c.w);
+    }
+    float mx = r[0];
+#pragma unroll
+    for (int i = 1; i < MIX_MAX_M; ++i) mx = fmaxf(mx, r[i]);
+    float s = 0.f;
+#pragma unroll
+    for (int mb = 0; mb < MIX_MAX_M / 4; ++mb) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) r[4 * mb + i] = __expf(r[4 * mb + i] - mx);
+      s += (r[4 * mb] + r[4 * mb + 1]) + (r[4 * mb + 2] + r[4 * mb + 3]);
+    }
+    const float inv = 1.0f / s;
+#pragma unroll
+    for (int i = 0; i < MIX_MAX_M; ++i) r[i] *= inv;
+    pack_r(r, p);
+    // 1 - r_max = (s - 1) / s (the largest term of s is exactly 1)
+    const float eps = MIX_LOGIT_KAPPA * fmaf(xnorm, t2.y, t2.z);
+    const float amb = fminf(1.0f, 4.0f * (s - 1.0f) * inv);
+    return eps * amb <= MIX_LOGIT_TAU && xnorm < 3.0e4f;  // (false for NaN; beyond 3e4 the fp16 operands saturate)
+  }
+
+  // The drift network up to the completed output GEMM (A region free afterwards); the A operand x is already stored.
+  // slot0 / slot1 run behind the first / second GEMM of the network (work that needs x but not the network).
+  template <bool BIAS_SH, class S0, class S1>
+  __device__ __forceinline__ void hidden_ws(const float* __restrict__ bias1, S0&& slot0, S1&& slot1) {
+    const TcLayout& L = this->L;
+    arrive_issue([&]() { gemm(L.off_in, L.Kin, C); });
+    tm.mark(1);
+    slot0();
+    tm.mark(2);
+    const float* bh = reinterpret_cast<const float*>(this->img + L.off_bhid);
+    const int nh = L.nh;
+    for (int l = 0; l <= nh; ++l) {
+      if (l == 1) {
+        slot1();
+        tm.mark(5);
+      }
+      this->wait();
+      tm.mark(l == 0 ? 3 : l == 1 ? 6 : 8);
+      if (l == 0) this->template epilogue_f16<!BIAS_SH>(bias1, 0);
+      else this->template epilogue_f16<false>(bh + (l - 1) * C, l);
+      if (l < nh) arrive_issue([&]() { gemm(L.off_hid + (uint32_t)(l * C * C * L.es), C, C); });
+      else arrive_issue([&]() { gemm(L.off_out, C, L.Nout); });
+      tm.mark(l == 0 ? 4 : 7);
+    }
+    if (nh == 0) slot1();
+    this->wait();
+    tm.mark(8);
   }
 };
 
@@ -234,11 +394,12 @@ struct MixTc : TcMlp<PREC> {
 // control and the reference score at the new point enter the cost; x is not integrated by the control.  The step's
 // increments are generated twice (for the update and for the cost) instead of being kept per particle.
 template <int PREC, class CFG>
-__device__ __forceinline__ void rollout_body_mix(const RolloutArgs& a, float* smem, uint8_t* stage, MixTc<PREC>& mlp) {
+__device__ __forceinline__ void rollout_body_mix(const RolloutArgs& a, float* smem, uint8_t* stage, uint32_t* step_cnt, MixTc<PREC>& mlp) {
   constexpr bool EUBO = CFG::kEubo, TMIX = CFG::kTgt == 1, TPHI = CFG::kTgt == 2, RMIX = CFG::kRef == 2, RGAUSS = CFG::kRef == 1, EM = CFG::kEm, DIS = CFG::kDis;
   const lrds_spec& s = a.s;
   const int NT = blockDim.x;
   const int tid = threadIdx.x;
+  const int nwarps = NT >> 5;
   const int b_raw = blockIdx.x * NT + tid;
   const bool live = b_raw < s.B;
   const int b = live ? b_raw : s.B - 1;  // idle lanes shadow the last particle, results are not stored
@@ -253,36 +414,25 @@ __device__ __forceinline__ void rollout_body_mix(const RolloutArgs& a, float* sm
   CtrlConst cc = ctrl_const(s);
   const GmmView tv0 = gmm_at(s.target.gmm, 0);
   const StageLayout SL = stage_layout(s, 2, true);
-  uint64_t* sbar = reinterpret_cast<uint64_t*>(stage);
-  const uint8_t* tmix_g = static_cast<const uint8_t*>(s.target.gmm.mix_tc);
+  uint64_t* sbar = reinterpret_cast<uint64_t*>(stage);  // [i]: step buffer i filled (TMA transaction bytes)
   const uint8_t* rmix_g = static_cast<const uint8_t*>(s.ref_t.mix_tc);
   const uint32_t mix_off_t = SL.tgt_logc_bytes + SL.tgt_param_bytes;                // inside the target area
   const uint32_t mix_off_r = SL.row_bytes + SL.ref_logc_bytes + SL.ref_param_bytes;  // inside a step buffer
-  auto stage_step_mix = [&](uint8_t* dst, int k, uint64_t* bar) {
-    stage_step(dst, s, SL, k, bar);
-    if constexpr (RMIX) ptx::bulk_g2s(dst + mix_off_r, rmix_g + (int64_t)k * s.ref_t.step_stride_mix_tc, SL.ref_mix_bytes, bar);
+  // a block of mix_tc: [contraction hi | lo | 16 B][logit hi | lo][c_m | 16 B]  (gmm_mix_tc_bytes)
+  const int Mt = TMIX ? s.target.gmm.M : s.ref_t.M;  // both are padded to 16 modes: equal block geometry
+  const uint32_t contr_bytes = gmm_mix_contr_bytes(Mt, dp), lg_part = gmm_mix_logit_part_bytes(Mt, dp);
+  const uint32_t lg_tail_off = contr_bytes + 2u * lg_part;
+  auto load_step = [&](int k) {  // table row | reference mixture block | its tensor-core images -> buffer k & 1 (one thread)
+    uint8_t* dst = stage + SL.off_buf + (k & 1) * SL.buf_bytes;
+    ptx::mbar_expect_tx(sbar + (k & 1), SL.buf_bytes);
+    stage_step(dst, s, SL, k, sbar + (k & 1));
+    if constexpr (RMIX) ptx::bulk_g2s(dst + mix_off_r, rmix_g + (int64_t)k * s.ref_t.step_stride_mix_tc, SL.ref_mix_bytes, sbar + (k & 1));
   };
-  // sbar[0..1]: "step buffer filled" (TMA transaction bytes); a CTA barrier per step protects the buffer the prefetch
-  // overwrites (an mbarrier release that lets the tiles drift apart by a step measured the same)
-  if (tid == 0) {
-    ptx::mbar_init(sbar, 1);
-    ptx::mbar_init(sbar + 1, 1);
-    ptx::fence_mbar_init();
-  }
-  __syncthreads();
-  if (tid == 0) {
-    ptx::mbar_expect_tx(sbar, SL.tgt_bytes + SL.buf_bytes);
-    if (SL.tgt_bytes) {  // a mixture target is staged whether or not the control uses its score (terminal cost)
-      stage_gmm(stage + SL.off_tgt, tv0, SL.tgt_logc_bytes, SL.tgt_param_bytes, sbar);
-      ptx::bulk_g2s(stage + SL.off_tgt + mix_off_t, tmix_g, SL.tgt_mix_bytes, sbar);
-    }
-    stage_step_mix(stage + SL.off_buf, 0, sbar);
-  }
   const GmmViewT<true> tv = staged_view(stage + SL.off_tgt, tv0, SL.tgt_logc_bytes, SL.tgt_param_bytes);
   const uint32_t tgt_img = ptx::smem_u32(stage + SL.off_tgt + mix_off_t);
-  const uint32_t tgt_img_bytes = SL.tgt_mix_bytes - 16u, ref_img_bytes = SL.ref_mix_bytes - 16u;
   mlp.lbo = (uint32_t)(2 * dp) * 16u;
-  mlp.part_bytes = (TMIX ? tgt_img_bytes : ref_img_bytes) / 2u;  // mixtures are padded to 16 modes: equal image sizes
+  mlp.part_bytes = (contr_bytes - 16u) / 2u;
+  mlp.lg_part = lg_part;
   // terminal_unnorm_log_prob(x) of whatever the target is (clipped by the caller)
   auto target_logp = [&]() -> float {
     if (s.target.kind == LRDS_DISTR_GMM) {
@@ -298,20 +448,19 @@ __device__ __forceinline__ void rollout_body_mix(const RolloutArgs& a, float* sm
   const u64 p0 = f2::pk(-beta * s.target.phi4.b / coef), p1 = f2::pk(beta / coef), p3 = f2::pk(-beta / coef),
             pn = f2::pk(beta * coef), m2 = f2::pk(-2.0f);
   const int nchunk = dp / JC;
+  const int nq = (d + 3) >> 2;
   float rnd = 0.f;
+  __syncwarp();  // the quadratic forms read the partner lane's coordinates
   if constexpr (EUBO) {  // rnd = reference_log_prob(x) - terminal_unnorm_log_prob(x)   (oc.py:536)
     ptx::mbar_wait(sbar, 0);  // the staged target mixture (the same phase as the first step's buffer)
     const float lref = gmm_logp_any(gmm_at(s.ref_0, 0), d, dp, P.x);
     rnd = lref - clipf(target_logp(), s.clip_target);
   }
 
+  mlp.tm.start();
   for (int k = 0; k < K; ++k) {
-    __syncthreads();  // every warp has finished step k-1, whose buffer the prefetch below overwrites
-    if (tid == 0 && k + 1 < K) {
-      ptx::mbar_expect_tx(sbar + ((k + 1) & 1), SL.buf_bytes);
-      stage_step_mix(stage + SL.off_buf + ((k + 1) & 1) * SL.buf_bytes, k + 1, sbar + ((k + 1) & 1));
-    }
     ptx::mbar_wait(sbar + (k & 1), (uint32_t)(k >> 1) & 1u);
+    mlp.tm.mark(0);
     const uint8_t* buf = stage + SL.off_buf + (k & 1) * SL.buf_bytes;
     const float* row = reinterpret_cast<const float*>(buf);
     const PPtr<true> rowp{ptx::smem_u32(buf)};
@@ -320,8 +469,8 @@ __device__ __forceinline__ void rollout_body_mix(const RolloutArgs& a, float* sm
     const float A = rowp.ld1(LRDS_STEP_A), Bc = rowp.ld1(LRDS_STEP_B), Cc = rowp.ld1(LRDS_STEP_C);
     const float wcost = rowp.ld1(LRDS_STEP_W_COST), wito = rowp.ld1(LRDS_STEP_W_ITO);
     const float gamma = rowp.ld1(LRDS_STEP_GAMMA);
-    const float ust = TMIX ? *reinterpret_cast<const float*>(stage + SL.off_tgt + mix_off_t + tgt_img_bytes) : 1.0f;
-    const float usr = RMIX ? *reinterpret_cast<const float*>(buf + mix_off_r + ref_img_bytes) : 1.0f;
+    const float ust = TMIX ? *reinterpret_cast<const float*>(stage + SL.off_tgt + mix_off_t + contr_bytes - 16u) : 1.0f;
+    const float usr = RMIX ? *reinterpret_cast<const float*>(buf + mix_off_r + contr_bytes - 16u) : 1.0f;
     const GmmView rg = gmm_at(s.ref_t, k);  // single-Gaussian reference: read from global memory (!RMIX)
 
     if constexpr (EUBO) {  // x <- mean x + std z   (oc.py:550-552)
@@ -336,19 +485,76 @@ __device__ __forceinline__ void rollout_body_mix(const RolloutArgs& a, float* sm
                                       f2::fma(std2, f2::pack(z[6], z[7]), f2::mul(xb.y, mean2))});
       }
     }
-    mlp.template hidden<true>(row + LRDS_STEP_BIAS1, P.x);  // ends with the output GEMM complete: A region free
-    {
-      float r[MIX_MAX_M];
-      if constexpr (TMIX) {
-        gmm_pass1_pair(tv, d, dp, P.x, r);
-        mlp.store_r(0, r);
-      }
-      if constexpr (RMIX) {
-        gmm_pass1_pair(rv, d, dp, P.x, r);
-        mlp.store_r(1, r);
+    mlp.store_x(P.x);
+    // Responsibilities of the two mixtures (packed fp16 hi | lo).  Shared-variance mixtures: from the logit GEMM, unless
+    // the error bound of a particle of this warp refuses; otherwise the exact quadratic forms behind the network's GEMMs.
+    // A particle's choice depends on its own bound only (results must not depend on which particles share a warp);
+    // the exact forms are evaluated by the whole warp (the half-warps serve each other) as soon as one lane needs them.
+    uint32_t rt_p[16], rr_p[16];
+    bool need_t = TMIX, need_r = RMIX;   // warp-uniform: some lane needs the exact forms
+    bool ok_t = false, ok_r = false;     // this lane keeps the responsibilities of the logit GEMM
+    if constexpr (TMIX || RMIX) {
+      const PPtr<true> tail_t{tgt_img + lg_tail_off}, tail_r{ref_img + lg_tail_off};
+      const bool lg_t = TMIX && tail_t.ld1(MIX_MAX_M + 3) != 0.f, lg_r = RMIX && tail_r.ld1(MIX_MAX_M + 3) != 0.f;  // CTA-uniform
+      if (lg_t || lg_r) {
+        mlp.arrive_issue([&]() {
+          if (lg_t) mlp.logit(0, tgt_img + contr_bytes);
+          if (lg_r) mlp.logit(1, ref_img + contr_bytes);
+        });
+        u64 n2 = 0;  // |x|^2 while the batch runs
+        for (int c = 0; c < nq; ++c) {
+          const ulonglong2 xv = P.x.ldu(c);
+          n2 = f2::fma(xv.x, xv.x, n2);
+          n2 = f2::fma(xv.y, xv.y, n2);
+        }
+        const float xnorm = sqrtf(f2::hsum1(n2));
+        mlp.wait();
+        uint32_t lg[32];
+        ptx::tmem_ld32(mlp.tm_lane + mlp.d_col(), lg);
+        ptx::tmem_wait_ld();
+        if (lg_t) {
+          ok_t = mlp.softmax_logits(lg, tail_t, xnorm, rt_p);
+          need_t = __any_sync(0xffffffffu, !ok_t);
+        }
+        if (lg_r) {
+          ok_r = mlp.softmax_logits(lg + MIX_MAX_M, tail_r, xnorm, rr_p);
+          need_r = __any_sync(0xffffffffu, !ok_r);
+        }
       }
     }
-    mlp.template issue_chunk<TMIX, RMIX>(0, tgt_img, ref_img);
+    mlp.tm.count(14, need_t);
+    mlp.tm.count(15, need_r);
+    mlp.template hidden_ws<true>(
+        row + LRDS_STEP_BIAS1,
+        [&]() {
+          if constexpr (TMIX) {
+            if (need_t) {
+              float r[MIX_MAX_M];
+              uint32_t p[16];
+              gmm_pass1_pair(tv, d, dp, P.x, r);
+              mlp.pack_r(r, p);
+#pragma unroll
+              for (int i = 0; i < 16; ++i) rt_p[i] = ok_t ? rt_p[i] : p[i];
+            }
+          }
+        },
+        [&]() {
+          if constexpr (RMIX) {
+            if (need_r) {
+              float r[MIX_MAX_M];
+              uint32_t p[16];
+              gmm_pass1_pair(rv, d, dp, P.x, r);
+              mlp.pack_r(r, p);
+#pragma unroll
+              for (int i = 0; i < 16; ++i) rr_p[i] = ok_r ? rr_p[i] : p[i];
+            }
+          }
+        });
+    // the output GEMM is complete: the A region is free for the responsibilities and the contraction chunks
+    if constexpr (TMIX) mlp.store_r(0, rt_p);
+    if constexpr (RMIX) mlp.store_r(1, rr_p);
+    mlp.arrive_issue([&]() { mlp.template chunk<TMIX, RMIX>(0, tgt_img, ref_img); });
+    mlp.tm.mark(9);
     // The integrator update on packed fp32x2 pairs of dims.  The images hold -1/var, so a score is one FFMA2; their
     // power-of-two un-scales are folded into the ScoreCtrl factor / the clip bound (target) and into the FFMA that
     // adds the control (reference).  Padded dims need no masks: their image rows, output weights, biases and noise
@@ -377,8 +583,10 @@ __device__ __forceinline__ void rollout_body_mix(const RolloutArgs& a, float* sm
       const int j0 = c * JC;
       uint32_t m[32];
       mlp.wait();
+      mlp.tm.mark(10);
       mlp.load_chunk(m);
-      if (c + 1 < nchunk) mlp.template issue_chunk<TMIX, RMIX>(c + 1, tgt_img, ref_img);
+      if (c + 1 < nchunk) mlp.arrive_issue([&]() { mlp.template chunk<TMIX, RMIX>(c + 1, tgt_img, ref_img); });
+      mlp.tm.mark(11);
       const ulonglong2 xa = P.x.ldu(2 * c), xb = P.x.ldu(2 * c + 1);
       const u64 X[4] = {xa.x, xa.y, xb.x, xb.y};
       u64 U[4], XN[4];
@@ -455,7 +663,10 @@ __device__ __forceinline__ void rollout_body_mix(const RolloutArgs& a, float* sm
           XN[q] = f2::fma(C2, z2, f2::fma(A2, X[q], f2::mul(B2, rv2)));
         }
       }
-      if constexpr (EUBO) continue;
+      if constexpr (EUBO) {
+        mlp.tm.mark(12);
+        continue;
+      }
       P.x.stu(2 * c, ulonglong2{XN[0], XN[1]});
       P.x.stu(2 * c + 1, ulonglong2{XN[2], XN[3]});
       if (a.traj_out != nullptr && live) {
@@ -464,6 +675,7 @@ __device__ __forceinline__ void rollout_body_mix(const RolloutArgs& a, float* sm
         for (int q = 0; q < 4; ++q) f2::unpack(XN[q], xn[2 * q], xn[2 * q + 1]);
         store_traj(a, k + 1, b, j0, xn);
       }
+      mlp.tm.mark(12);
     }
     if constexpr (EUBO) {
       rnd -= f2::hsum1(su2) * wcost;
@@ -472,7 +684,16 @@ __device__ __forceinline__ void rollout_body_mix(const RolloutArgs& a, float* sm
       rnd += wcost * f2::hsum1(su2);
       rnd += wz * f2::hsum1(sito);
     }
+    // This warp is done with the step's buffer (the last contraction, which reads its image, has completed: wait()
+    // above).  The CTA's last warp to get here refills it with the operands of step k + 2.
+    __syncwarp();
+    if ((tid & 31) == 0) {
+      const uint32_t old = ptx::atom_add_acq_rel(step_cnt + (k & 1), 1u);
+      if (old == (uint32_t)((k >> 1) * nwarps + nwarps - 1) && k + 2 < K) load_step(k + 2);
+    }
+    mlp.tm.mark(13);
   }
+  __syncwarp();  // the partner lane's final coordinates
   if constexpr (!EUBO) {  // terminal cost: rnd += reference_log_prob(x) - terminal_unnorm_log_prob(x)   (oc.py:290, 505, 645)
     // init_cost (DIS): the pre-pass of lrds_rollout left initial_log_prob(x_0) + rnd_offset in rnd_out (oc.py:1164-1168)
     const float lref = s.init_cost ? a.rnd_out[b] : gmm_logp_any(gmm_at(s.ref_0, 0), d, dp, P.x);
@@ -486,32 +707,56 @@ __device__ __forceinline__ void rollout_body_mix(const RolloutArgs& a, float* sm
   }
 }
 
-// shared memory: [weight image | mbarriers + TMEM slot | operand stage | particle columns]
+// shared memory: [weight image | mbarriers + TMEM slot | hand-off counters | operand stage | particle columns]
 template <int PREC, class CFG>
 __global__ void __launch_bounds__(MIX_MAX_WARPS * 32, 1)
 rollout_mix_kernel(const RolloutArgs a, const uint8_t* __restrict__ image, const uint32_t tmem_cols) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
-  const TcLayout TL = tc_layout(a.s.d, a.s.mlp.num_hidden, PREC);
-  const int tid = threadIdx.x, warp = tid >> 5, nwarps = blockDim.x >> 5;
+  constexpr bool TMIX = CFG::kTgt == 1, RMIX = CFG::kRef == 2;
+  const lrds_spec& s = a.s;
+  const TcLayout TL = tc_layout(s.d, s.mlp.num_hidden, PREC);
+  const int tid = threadIdx.x;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // warp-uniform for the compiler as well
+  const int nwarps = blockDim.x >> 5;
   uint8_t* img = smem_raw;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + TL.bytes);  // [0] image, [1 + t] tile t
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + TL.bytes);  // [0] image, [1 + t] MMAs of tile t done
   uint32_t* slot = reinterpret_cast<uint32_t*>(smem_raw + TL.bytes + 48);
-  uint8_t* stage = smem_raw + TL.bytes + TC_TAIL_BYTES;
-  float* cols = reinterpret_cast<float*>(stage + ((stage_layout(a.s, 2, true).total + 15u) & ~15u));
+  uint32_t* cnts = reinterpret_cast<uint32_t*>(smem_raw + TL.bytes + TC_TAIL_BYTES);  // [t] tile hand-offs, [4 + i] step buffer i released
+  uint8_t* stage = smem_raw + TL.bytes + TC_TAIL_BYTES + MIX_TAIL_BYTES;
+  const StageLayout SL = stage_layout(s, 2, true);
+  float* cols = reinterpret_cast<float*>(stage + ((SL.total + 15u) & ~15u));
   if (warp == 0) ptx::tmem_alloc(slot, tmem_cols);
   if (tid == 0) {
+    uint64_t* sbar = reinterpret_cast<uint64_t*>(stage);
     for (int i = 0; i < 5; ++i) ptx::mbar_init(bars + i, 1);
+    ptx::mbar_init(sbar, 1);
+    ptx::mbar_init(sbar + 1, 1);
+    for (int i = 0; i < 6; ++i) cnts[i] = 0u;
     ptx::fence_mbar_init();
   }
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
-  if (tid == 0) {  // drift weights staged once per CTA by the TMA engine
+  if (tid == 0) {  // drift weights staged once per CTA by the TMA engine; the static target mixture and steps 0, 1
     ptx::mbar_expect_tx(bars, TL.bytes);
     ptx::bulk_g2s(img, image, TL.bytes, bars);
+    uint64_t* sbar = reinterpret_cast<uint64_t*>(stage);
+    const uint32_t mix_off_t = SL.tgt_logc_bytes + SL.tgt_param_bytes;
+    const uint32_t mix_off_r = SL.row_bytes + SL.ref_logc_bytes + SL.ref_param_bytes;
+    const uint8_t* rmix_g = static_cast<const uint8_t*>(s.ref_t.mix_tc);
+    for (int k = 0; k < 2 && k < s.K; ++k) {
+      uint8_t* dst = stage + SL.off_buf + k * SL.buf_bytes;
+      ptx::mbar_expect_tx(sbar + k, SL.buf_bytes + (k == 0 ? SL.tgt_bytes : 0u));
+      if (k == 0 && SL.tgt_bytes) {  // a mixture target is staged whether or not the control uses its score (terminal cost)
+        stage_gmm(stage + SL.off_tgt, gmm_at(s.target.gmm, 0), SL.tgt_logc_bytes, SL.tgt_param_bytes, sbar);
+        ptx::bulk_g2s(stage + SL.off_tgt + mix_off_t, static_cast<const uint8_t*>(s.target.gmm.mix_tc), SL.tgt_mix_bytes, sbar);
+      }
+      stage_step(dst, s, SL, k, sbar + k);
+      if constexpr (RMIX) ptx::bulk_g2s(dst + mix_off_r, rmix_g + (int64_t)k * s.ref_t.step_stride_mix_tc, SL.ref_mix_bytes, sbar + k);
+    }
   }
   ptx::mbar_wait(bars, 0);
-  const uint32_t tmem = *slot;
+  const uint32_t tmem = __shfl_sync(0xffffffffu, *slot, 0);
   const int tile = warp >> 2;
   const int tile_warps = min(4, nwarps - 4 * tile);
   MixTc<PREC> mlp;
@@ -522,14 +767,23 @@ rollout_mix_kernel(const RolloutArgs a, const uint8_t* __restrict__ image, const
   mlp.tm_lane = mlp.tm_tile + ((uint32_t)((warp & 3) * 32) << 16);
   mlp.bar = bars + 1 + tile;
   mlp.phase = 0;
-  mlp.bar_id = 1 + tile;
-  mlp.bar_threads = tile_warps * 32;
-  // the tile's LAST warp issues the MMAs: with 14 warps the sub-partitions of warps 0/1 (mod 4) carry four warps and
-  // those of warps 2/3 three, so the issuing work (descriptor arithmetic, ~540 instructions per tile and step) goes
-  // to the lightly loaded ones wherever the tile has four warps
-  mlp.issuer = (tid & 127) == 32 * (tile_warps - 1);
-  mlp.dp = a.s.mlp.d_pad;
-  rollout_body_mix<PREC, CFG>(a, cols, stage, mlp);
+  mlp.cnt = cnts + tile;
+  mlp.tile_warps = (uint32_t)tile_warps;
+  mlp.next = (uint32_t)tile_warps - 1u;
+  mlp.dp = s.mlp.d_pad;
+#ifdef LRDS_MIX_TIMING
+  unsigned long long* tmw = reinterpret_cast<unsigned long long*>(cols + (size_t)col_layout(s, true).total * 32 * nwarps) + warp * 16;
+  if ((tid & 31) < 16) tmw[tid & 31] = 0;
+  __syncwarp();
+  mlp.tm.w = tmw;
+#endif
+  rollout_body_mix<PREC, CFG>(a, cols, stage, cnts + 4, mlp);
+#ifdef LRDS_MIX_TIMING
+  __syncwarp();
+  if ((blockIdx.x == 0 || blockIdx.x == gridDim.x / 2) && (tid & 31) < 16)
+    g_mix_timing[((blockIdx.x ? 1 : 0) * 16 + warp) * 16 + (tid & 31)] = tmw[tid & 31];
+#endif
+  (void)TMIX;
   ptx::tc_fence_before();
   __syncthreads();
   if (warp == 0) ptx::tmem_dealloc(tmem, tmem_cols);
@@ -541,7 +795,10 @@ inline bool plan_rollout_mix(const lrds_spec& s, int smem_cap, int sms, TcPlan* 
   const TcLayout TL = tc_layout(s.d, s.mlp.num_hidden, s.precision);
   if (TL.tile_cols > 512 || TL.parts * TL.a_cols < 64) return false;  // R and the chunk live in 64 columns of the A region
   const ColLayout CL = col_layout(s, true);
-  const size_t fixed = (size_t)TL.bytes + TC_TAIL_BYTES + ((stage_layout(s, 2, true).total + 15u) & ~15u);
+  size_t fixed = (size_t)TL.bytes + TC_TAIL_BYTES + MIX_TAIL_BYTES + ((stage_layout(s, 2, true).total + 15u) & ~15u);
+#ifdef LRDS_MIX_TIMING
+  fixed += 16 * 16 * 8;
+#endif
   const size_t per_warp = (size_t)CL.total * 32 * sizeof(float);
   if (fixed + per_warp > (size_t)smem_cap) return false;
   int wmax = (int)(((size_t)smem_cap - fixed) / per_warp);

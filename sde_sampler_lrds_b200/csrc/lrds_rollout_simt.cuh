@@ -87,8 +87,18 @@ struct StageLayout {
   uint32_t tgt_mix_bytes, ref_mix_bytes;                // tensor-core images of the score contractions (mix_tc)
   uint32_t buf_bytes, off_tgt, off_buf, total;
 };
-__host__ __device__ inline uint32_t gmm_mix_tc_bytes(int M, int d_pad) {
+// A block of lrds_gmm.mix_tc (include/lrds_b200.h):
+//   [contraction image hi | lo][16 B: un-scale]  -  the score contraction (rows n = 16 c + i over 8-dim chunks)
+//   [logit image hi | lo][c_m: Mp floats][16 B: un-scale, Wn, Cmax, shared]  -  the responsibilities' logits of a mixture
+//   whose modes share their variances: logit_m = c_m + x . wc_m (+ a mode-independent term), wc_m = mu_m / var - mean_m
+__host__ __device__ inline uint32_t gmm_mix_contr_bytes(int M, int d_pad) {
   return 2u * (uint32_t)((M + 15) / 16 * 2) * (uint32_t)(2 * d_pad) * 16u + 16u;
+}
+__host__ __device__ inline uint32_t gmm_mix_logit_part_bytes(int M, int d_pad) {  // one (hi | lo) part: Mp rows x Kin halves
+  return (uint32_t)((M + 15) / 16 * 16) * (uint32_t)((d_pad + 15) / 16 * 16) * 2u;
+}
+__host__ __device__ inline uint32_t gmm_mix_tc_bytes(int M, int d_pad) {
+  return gmm_mix_contr_bytes(M, d_pad) + 2u * gmm_mix_logit_part_bytes(M, d_pad) + (uint32_t)((M + 15) / 16 * 16) * 4u + 16u;
 }
 
 // level 1: table row + reference block per step; level 2: also the (static) target mixture

@@ -40,3 +40,9 @@ int launch_mix_f16x3(const RolloutArgs& a, const TcPlan& p, cudaStream_t st, cha
   return LRDS_ERR_UNSUPPORTED;
 }
 }  // namespace lrds
+
+#ifdef LRDS_MIX_TIMING
+extern "C" int lrds_debug_mix_timing(unsigned long long* host_out) {  // tools only: 2 CTAs x 16 warps x 16 phase counters
+  return (int)cudaMemcpyFromSymbol(host_out, lrds::g_mix_timing, sizeof(lrds::g_mix_timing));
+}
+#endif

@@ -46,15 +46,54 @@ def gmm_block(loc: torch.Tensor, var: torch.Tensor, weights: torch.Tensor | None
                      dim=-2)  # [.., m4, nq, 4 modes, 2, 4 dims]
     out = [logc, loc, ivar, sn.reshape(*lead, m4 * nq * 32)]
     if M > 1:
-        out.append(gmm_mix_tc_image(loc[..., :d], var, d + pad))
+        out.append(gmm_mix_tc_image(loc[..., :d], var, d + pad, logc[..., :M], ivar[..., :d]))
     return tuple(t.contiguous().to(device) for t in out)
 
 
-def gmm_mix_tc_image(loc: torch.Tensor, var: torch.Tensor, d_pad: int) -> torch.Tensor:
+def _pow2_scale(amax: torch.Tensor) -> torch.Tensor:
+    """The power of two that puts ``amax`` into [2^14, 2^15) (1 for amax = 0), float64."""
+    k = torch.where(amax > 0, 14 - torch.floor(torch.log2(amax.clamp(min=1e-300))), torch.zeros_like(amax))
+    return torch.pow(torch.tensor(2.0, dtype=torch.float64), k.clamp(-100, 100))
+
+
+def gmm_logit_tc_image(loc: torch.Tensor, logc: torch.Tensor, ivar: torch.Tensor, d_pad: int) -> torch.Tensor:
+    """The logit part of a lrds_gmm.mix_tc block (include/lrds_b200.h): wc = mu / var - mean over the modes as a
+    power-of-two scaled fp16 hi | lo matrix [j/8][m][j%8] (modes padded to a multiple of 16, dims to a multiple of 16),
+    then c_m = logc_m - sum_j mu^2 / var / 2 (fp32, -inf for the padded modes), then four floats
+    {un-scale, max_m |wc_m|_2, max_m |c_m|, variances shared ? 1 : 0}.  ``ivar`` = the fp32 1/var the kernels see."""
+    lead = loc.shape[:-2]
+    M, d = loc.shape[-2:]
+    Mp, Kin = (M + 15) // 16 * 16, (d_pad + 15) // 16 * 16
+    iv = ivar.double()
+    w = loc.double() * iv
+    wc = (w - w.mean(dim=-2, keepdim=True).float().double()).float()   # the mean is held in fp32, as the device packer does
+    c = (logc.double() - 0.5 * (loc.double() ** 2 * iv).sum(dim=-1)).float()
+    F = torch.nn.functional
+    V = F.pad(wc, (0, Kin - d, 0, Mp - M))                             # [.., m, j]
+    scale = _pow2_scale(V.abs().flatten(-2).max(dim=-1).values.double())
+    Vs = (V.double() * scale[..., None, None]).float()
+    hi = Vs.half()
+    lo = (Vs - hi.float()).half()
+    parts = [t.reshape(*lead, Mp, Kin // 8, 8).transpose(-3, -2).contiguous().reshape(*lead, -1).view(torch.uint8)
+             for t in (hi, lo)]
+    cpad = F.pad(c, (0, Mp - M), value=float("-inf"))
+    tail = torch.zeros(*lead, 4, dtype=torch.float32)
+    tail[..., 0] = (1.0 / scale).float()
+    tail[..., 1] = wc.double().pow(2).sum(dim=-1).sqrt().max(dim=-1).values.float()
+    tail[..., 2] = c.abs().max(dim=-1).values
+    dev = ((ivar[..., 1:, :] - ivar[..., :1, :]).abs() / ivar[..., :1, :].abs()).flatten(-2).max(dim=-1).values \
+        if M > 1 else torch.zeros(lead)
+    tail[..., 3] = (dev <= 1e-6).float()
+    return torch.cat(parts + [cpad.contiguous().view(torch.uint8), tail.view(torch.uint8)], dim=-1).contiguous()
+
+
+def gmm_mix_tc_image(loc: torch.Tensor, var: torch.Tensor, d_pad: int, logc: torch.Tensor | None = None,
+                     ivar: torch.Tensor | None = None) -> torch.Tensor:
     """Tensor-core operand of the mixture-score contraction (lrds_gmm.mix_tc, include/lrds_b200.h): per block the
     matrix B[n][m] with rows n = 16 c + i over 8-dim chunks c (i < 8: -1/var_{m, 8c+i}; i >= 8: mu/var_{m, 8c+i-8}),
     scaled by the power of two that puts its largest entry into [2^14, 2^15) and split into fp16 (hi, lo), each part
-    in the K-major no-swizzle tcgen05 layout [m/8][n][m%8], followed by 16 bytes holding the float un-scale."""
+    in the K-major no-swizzle tcgen05 layout [m/8][n][m%8], followed by 16 bytes holding the float un-scale; then the
+    logit image (gmm_logit_tc_image) when ``logc`` is given."""
     lead = loc.shape[:-2]
     M, d = loc.shape[-2:]
     Mp = (M + 15) // 16 * 16
@@ -73,7 +112,10 @@ def gmm_mix_tc_image(loc: torch.Tensor, var: torch.Tensor, d_pad: int) -> torch.
              for t in (hi, lo)]
     tail = torch.zeros(*lead, 4, dtype=torch.float32)
     tail[..., 0] = (1.0 / scale).float()
-    return torch.cat(parts + [tail.view(torch.uint8)], dim=-1).contiguous()
+    blocks = parts + [tail.view(torch.uint8)]
+    if logc is not None:
+        blocks.append(gmm_logit_tc_image(loc, logc, ivar if ivar is not None else (1.0 / var.double()).float(), d_pad))
+    return torch.cat(blocks, dim=-1).contiguous()
 
 
 def fill_gmm(g: N.Gmm, block, stepped: bool = False):

@@ -167,6 +167,21 @@ def case_ei_many_modes(K=200, B=200, d=50, M=16):
         "B": B, "seed": 102, "prior": ("iso", 0.0, 1.0)}
 
 
+def case_ei_close_modes(method="ei"):
+    """Shared-variance mixtures whose modes overlap and sit far from the origin: near-ties of the responsibilities are
+    common and the logits are large, so the mixture kernel's logit GEMM (lrds_rollout_mix.cuh) must hand many particles
+    over to the exact quadratic forms while others keep its result."""
+    d, M = 24, 10
+    g = torch.Generator().manual_seed(5)
+    loc = 8.0 + 1.2 * (torch.rand(M, d, generator=g) - 0.5)
+    tgt = {"kind": "gmm", "loc": loc, "scale": math.sqrt(0.5) * torch.ones(M, d), "weights": torch.logspace(0.0, 1.0, M, base=2.0)}
+    ref = {"kind": "gmm", "means": loc + 0.1, "variances": 0.6 * torch.ones(M, d), "weights": tgt["weights"].clone()}
+    return {
+        "problem": {"method": method, "sde": VP10, "ts": uniform_ts(1.0, 60), "target": tgt,
+                    "ctrl": ctrl(d, "score", seed=33, out_gain=0.5, gamma=0.03), "ref": ref},
+        "B": 130, "seed": 133, "prior": ("iso", 0.0, 1.0)}
+
+
 def case_ei_two_modes_gauss():
     """RDS vp-ref with a Gaussian reference and the EI integrator over a mixture target (cfg 1's solver with cfg 2's
     integrator): target score on the tensor core, reference score one FMA per dim."""
@@ -401,6 +416,9 @@ CASES = {
     "em_two_modes_clipped": lambda: case_em_two_modes("clipped"),
     "ei_many_modes": lambda: case_ei_many_modes(),
     "ddpm_snr": case_ddpm_snr,
+    "ei_close_modes": case_ei_close_modes,
+    "em_close_modes": lambda: case_ei_close_modes("em"),
+    "eubo_ei_close_modes": lambda: _eubo(case_ei_close_modes(), 209),
     "ei_two_modes_gauss": case_ei_two_modes_gauss,
     "ei_phi4_gmm": case_ei_phi4_gmm,
     "ei_many_modes_clipped": case_ei_many_modes_clipped,

@@ -50,12 +50,17 @@ def test_mixture_tensor_core_image_layout():
     torch.manual_seed(0)
     S, M, d, dp = 3, 5, 11, 16
     loc, var = torch.randn(S, M, d) * 7, torch.rand(S, M, d) * 2 + 0.05
-    img = gmm_mix_tc_image(loc, var, dp)
+    w = torch.rand(M) + 0.1
+    logc = -0.5 * d * math.log(2 * math.pi) - 0.5 * torch.log(var).sum(-1) + torch.log(w / w.sum())
+    img = gmm_mix_tc_image(loc, var, dp, logc)
     lib = N.lib()
     lib.lrds_gmm_mix_tc_bytes.restype = C.c_int64
     nbytes = lib.lrds_gmm_mix_tc_bytes(M, dp)
     assert img.shape == (S, nbytes) and img.dtype == torch.uint8 and nbytes % 16 == 0
-    part = (nbytes - 16) // 2
+    Kin, Mp = 16 * ((dp + 15) // 16), 16
+    lpart = Mp * Kin * 2
+    contr = nbytes - (2 * lpart + 4 * Mp + 16)
+    part = (contr - 16) // 2
     for s in range(S):
         unscale = img[s, 2 * part:2 * part + 4].view(torch.float32).item()
         assert unscale > 0 and math.log2(unscale) == round(math.log2(unscale))
@@ -69,3 +74,25 @@ def test_mixture_tensor_core_image_layout():
                 j = 8 * c + i % 8
                 want = 0.0 if (m >= M or j >= d) else (-1.0 / var[s, m, j] if i < 8 else loc[s, m, j] / var[s, m, j]).item()
                 assert abs(Bm[m, n].item() - want) <= 2.0 ** -20 * max(abs(want), 2.0 ** -10), (s, m, n)
+        # the logit image behind it: wc[j/8][m][j%8] hi | lo, c_m, {un-scale, max |wc_m|, max |c_m|, shared}
+        L = img[s, contr:]
+        tail = L[2 * lpart + 4 * Mp:].view(torch.float32)
+        us = tail[0].item()
+        assert us > 0 and math.log2(us) == round(math.log2(us)) and tail[3].item() == 0.0  # per-mode variances: not shared
+        hi = L[:lpart].view(torch.float16).float().reshape(Kin // 8, Mp, 8)
+        lo = L[lpart:2 * lpart].view(torch.float16).float().reshape(Kin // 8, Mp, 8)
+        Wc = ((hi + lo) * us).permute(1, 0, 2).reshape(Mp, Kin)                       # [m][j]
+        wfull = (loc[s].double() / var[s].double())
+        want_w = wfull - wfull.mean(0, keepdim=True)
+        assert (Wc[:M, :d].double() - want_w).abs().max() <= 2.0 ** -19 * want_w.abs().max()
+        assert Wc[M:].abs().max() == 0 and Wc[:, d:].abs().max() == 0
+        cm = L[2 * lpart:2 * lpart + 4 * Mp].view(torch.float32)
+        want_c = logc[s].double() - 0.5 * (loc[s].double() ** 2 / var[s].double()).sum(-1)
+        assert (cm[:M].double() - want_c).abs().max() <= 1e-6 * want_c.abs().max() and torch.isinf(cm[M:]).all()
+        assert abs(tail[1].item() - want_w.pow(2).sum(-1).sqrt().max().item()) <= 1e-5 * tail[1].item()
+        assert abs(tail[2].item() - want_c.abs().max().item()) <= 1e-5 * tail[2].item()
+    # a mixture whose modes share their variances sets the flag
+    var_sh = (torch.rand(1, d) * 2 + 0.05).expand(M, d)
+    logc_sh = -0.5 * torch.log(var_sh).sum(-1) + torch.log(w / w.sum())
+    img2 = gmm_mix_tc_image(loc[0], var_sh, dp, logc_sh)
+    assert img2[-16:].view(torch.float32)[3].item() == 1.0
