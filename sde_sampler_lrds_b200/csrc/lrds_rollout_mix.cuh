@@ -16,10 +16,11 @@
 // output.  One chunk is in flight at a time: chunk c+1 is issued as soon as every warp of the tile has read chunk c.
 //
 // Hand-offs.  A tile's tensor-core batches (the network's GEMMs, the logit GEMM, the contraction chunks) are issued by
-// whichever of its warps arrives LAST: every warp stores its operand rows / reads its accumulator rows, increments the
-// tile's shared-memory counter (release / acquire) and goes on; the warp that completes the count issues the batch
-// from warp-uniform registers (elect.sync) and commits it to the tile's mbarrier, on which the tile's warps wait
-// only when they need the result.  The per-step operand buffers are refilled (TMA) by the CTA's last warp to finish a
+// its last warp: every warp stores its operand rows / reads its accumulator rows, increments the tile's shared-memory
+// counter (release) and goes on; the issuer warp polls the counter (acquire), issues the batch from warp-uniform
+// registers (elect.sync) and commits it to the tile's mbarrier, on which the tile's warps wait only when they need
+// the result.  With 14 warps per SM the last warp of a full tile sits on a sub-partition with three particle warps
+// instead of four, so the issue work stays off the sub-partitions that bound the kernel.  The per-step operand buffers are refilled (TMA) by the CTA's last warp to finish a
 // step.  There is no CTA-wide or tile-wide barrier inside the time loop: warps run out of phase.
 //
 // Responsibilities.  r = softmax_m(logc_m - q_m / 2).  For a mixture whose modes share their variances (every
@@ -223,24 +224,28 @@ template <int PREC>
 struct MixTc : TcMlp<PREC> {
   using Base = TcMlp<PREC>;
   static constexpr uint32_t kRCol = 0, kDCol = 32;
-  uint32_t* cnt;        // the tile's hand-off counter
-  uint32_t next;        // its value that makes this warp the last arriver of its next hand-off
+  uint32_t* cnt;        // the tile's hand-off counter: one increment per warp and hand-off
+  uint32_t target;      // its value once every warp of the tile has arrived for the current hand-off
   uint32_t tile_warps;
+  bool issuer;          // this warp issues the tile's batches (warp-uniform)
   uint32_t lbo, part_bytes;  // contraction image: bytes between the K chunks (modes 0-7 | 8-15), bytes of one (hi | lo) part
   uint32_t lg_part;          // logit image: bytes of one (hi | lo) part
   MixTm tm;
 
-  // This warp's part of the tile's next batch is in place (A rows stored / accumulator rows read).  The last warp of
-  // the tile to say so issues the batch `f` and commits it to the tile's mbarrier; nobody blocks here.
+  // This warp's part of the tile's next batch is in place (A rows stored / accumulator rows read).  Every warp
+  // increments the tile's counter (release, no round trip) and goes on; the tile's issuer warp - its LAST warp, which
+  // sits on one of the two SM sub-partitions that carry three particle warps instead of four and therefore has slack -
+  // polls the counter, issues the batch `f` from warp-uniform registers and commits it to the tile's mbarrier.
   template <class F>
   __device__ __forceinline__ void arrive_issue(F&& f) {
     ptx::tmem_wait_st();
     ptx::tc_fence_before();
     __syncwarp();
-    uint32_t old = 0;
-    if ((threadIdx.x & 31) == 0) old = ptx::atom_add_acq_rel(cnt, 1u);
-    old = __shfl_sync(0xffffffffu, old, 0);
-    if (old == next) {
+    target += tile_warps;
+    if ((threadIdx.x & 31) == 0) ptx::red_add_release(cnt, 1u);
+    if (issuer) {
+      while ((int32_t)(ptx::ld_acquire(cnt) - target) < 0) {
+      }
       ptx::tc_fence_after();
       if (ptx::elect_one()) {
         f();
@@ -248,7 +253,6 @@ struct MixTc : TcMlp<PREC> {
       }
       __syncwarp();
     }
-    next += tile_warps;
   }
 
   // one layer of the network: D = A . W^T as three passes of fp16 (hi, lo) products, small terms first
@@ -769,7 +773,8 @@ rollout_mix_kernel(const RolloutArgs a, const uint8_t* __restrict__ image, const
   mlp.phase = 0;
   mlp.cnt = cnts + tile;
   mlp.tile_warps = (uint32_t)tile_warps;
-  mlp.next = (uint32_t)tile_warps - 1u;
+  mlp.target = 0u;
+  mlp.issuer = (warp & 3) == tile_warps - 1;
   mlp.dp = s.mlp.d_pad;
 #ifdef LRDS_MIX_TIMING
   unsigned long long* tmw = reinterpret_cast<unsigned long long*>(cols + (size_t)col_layout(s, true).total * 32 * nwarps) + warp * 16;

@@ -35,9 +35,37 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity, ui
       : "memory");
   return ok != 0;
 }
+#ifndef LRDS_MBAR_WAIT_MODE
+#define LRDS_MBAR_WAIT_MODE 0
+#endif
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+#if LRDS_MBAR_WAIT_MODE == 0
   while (!mbar_try_wait(bar, parity)) {
   }
+#elif LRDS_MBAR_WAIT_MODE == 1  // try_wait without a suspend-time hint (the hardware's own time limit)
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "LRDS_WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra LRDS_DONE_%=;\n\t"
+      "bra LRDS_WAIT_%=;\n\t"
+      "LRDS_DONE_%=:\n\t}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+#else  // test_wait + a short plain sleep
+  uint32_t ok;
+  for (;;) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (ok) break;
+    asm volatile("nanosleep.u32 %0;" ::"r"((uint32_t)LRDS_MBAR_WAIT_MODE));
+  }
+#endif
 }
 // non-blocking test of the phase with the given parity (the polling loop of a warp that serves several barriers)
 __device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
@@ -66,6 +94,15 @@ __device__ __forceinline__ uint32_t atom_add_acq_rel(uint32_t* p, uint32_t v) {
   uint32_t old;
   asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(smem_u32(p)), "r"(v) : "memory");
   return old;
+}
+// the same without a return value (the arriving warp does not wait for the round trip), and the polling read
+__device__ __forceinline__ void red_add_release(uint32_t* p, uint32_t v) {
+  asm volatile("red.release.cta.shared::cta.add.u32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
+  return v;
 }
 __device__ __forceinline__ void nanosleep(uint32_t ns) { asm volatile("nanosleep.u32 %0;" ::"r"(ns)); }
 
