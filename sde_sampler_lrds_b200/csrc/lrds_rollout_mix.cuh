@@ -227,15 +227,17 @@ struct MixTc : TcMlp<PREC> {
   uint32_t* cnt;        // the tile's hand-off counter: one increment per warp and hand-off
   uint32_t target;      // its value once every warp of the tile has arrived for the current hand-off
   uint32_t tile_warps;
-  bool issuer;          // this warp issues the tile's batches (warp-uniform)
+  uint32_t issue_mask;  // bit (n & 1): this warp issues the tile's hand-offs n with that parity (warp-uniform)
+  uint32_t hand;        // hand-offs so far
   uint32_t lbo, part_bytes;  // contraction image: bytes between the K chunks (modes 0-7 | 8-15), bytes of one (hi | lo) part
   uint32_t lg_part;          // logit image: bytes of one (hi | lo) part
   MixTm tm;
 
   // This warp's part of the tile's next batch is in place (A rows stored / accumulator rows read).  Every warp
-  // increments the tile's counter (release, no round trip) and goes on; the tile's issuer warp - its LAST warp, which
-  // sits on one of the two SM sub-partitions that carry three particle warps instead of four and therefore has slack -
-  // polls the counter, issues the batch `f` from warp-uniform registers and commits it to the tile's mbarrier.
+  // increments the tile's counter (release, no round trip) and goes on; the hand-off's issuer warp - the tile's last
+  // two warps take turns; in a full tile they sit on the two SM sub-partitions that carry three particle warps instead
+  // of four and therefore have slack - polls the counter, issues the batch `f` from warp-uniform registers and
+  // commits it to the tile's mbarrier.
   template <class F>
   __device__ __forceinline__ void arrive_issue(F&& f) {
     ptx::tmem_wait_st();
@@ -243,7 +245,9 @@ struct MixTc : TcMlp<PREC> {
     __syncwarp();
     target += tile_warps;
     if ((threadIdx.x & 31) == 0) ptx::red_add_release(cnt, 1u);
-    if (issuer) {
+    const bool mine = (issue_mask >> (hand & 1u)) & 1u;
+    ++hand;
+    if (mine) {
       while ((int32_t)(ptx::ld_acquire(cnt) - target) < 0) {
       }
       ptx::tc_fence_after();
@@ -774,7 +778,9 @@ rollout_mix_kernel(const RolloutArgs a, const uint8_t* __restrict__ image, const
   mlp.cnt = cnts + tile;
   mlp.tile_warps = (uint32_t)tile_warps;
   mlp.target = 0u;
-  mlp.issuer = (warp & 3) == tile_warps - 1;
+  mlp.hand = 0u;
+  // even hand-offs: the tile's last warp; odd ones: the one before it (the same warp in a one-warp tile)
+  mlp.issue_mask = ((warp & 3) == tile_warps - 1 ? 1u : 0u) | ((warp & 3) == max(tile_warps - 2, 0) ? 2u : 0u);
   mlp.dp = s.mlp.d_pad;
 #ifdef LRDS_MIX_TIMING
   unsigned long long* tmw = reinterpret_cast<unsigned long long*>(cols + (size_t)col_layout(s, true).total * 32 * nwarps) + warp * 16;
