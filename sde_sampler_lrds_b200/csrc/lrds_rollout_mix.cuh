@@ -237,26 +237,31 @@ struct MixTc : TcMlp<PREC> {
   // increments the tile's counter (release, no round trip) and goes on; the hand-off's issuer warp - the tile's last
   // two warps take turns; in a full tile they sit on the two SM sub-partitions that carry three particle warps instead
   // of four and therefore have slack - polls the counter, issues the batch `f` from warp-uniform registers and
-  // commits it to the tile's mbarrier.
+  // commits it to the tile's mbarrier.  A partial last tile (whose warps all sit on the loaded sub-partitions) has
+  // issue_mask = 0: its batches are issued by the CTA's auxiliary warp (mix_aux_issuer).
   template <class F>
   __device__ __forceinline__ void arrive_issue(F&& f) {
     ptx::tmem_wait_st();
     ptx::tc_fence_before();
     __syncwarp();
-    target += tile_warps;
     if ((threadIdx.x & 31) == 0) ptx::red_add_release(cnt, 1u);
     const bool mine = (issue_mask >> (hand & 1u)) & 1u;
     ++hand;
-    if (mine) {
-      while ((int32_t)(ptx::ld_acquire(cnt) - target) < 0) {
-      }
-      ptx::tc_fence_after();
-      if (ptx::elect_one()) {
-        f();
-        ptx::mma_commit(this->bar);
-      }
-      __syncwarp();
+    if (mine) issue_when_ready(f);
+    else target += tile_warps;
+  }
+  // polls the tile's counter until every warp has arrived for the next hand-off, then issues and commits its batch
+  template <class F>
+  __device__ __forceinline__ void issue_when_ready(F&& f) {
+    target += tile_warps;
+    while ((int32_t)(ptx::ld_acquire(cnt) - target) < 0) {
     }
+    ptx::tc_fence_after();
+    if (ptx::elect_one()) {
+      f();
+      ptx::mma_commit(this->bar);
+    }
+    __syncwarp();
   }
 
   // one layer of the network: D = A . W^T as three passes of fp16 (hi, lo) products, small terms first
@@ -402,12 +407,12 @@ struct MixTc : TcMlp<PREC> {
 // control and the reference score at the new point enter the cost; x is not integrated by the control.  The step's
 // increments are generated twice (for the update and for the cost) instead of being kept per particle.
 template <int PREC, class CFG>
-__device__ __forceinline__ void rollout_body_mix(const RolloutArgs& a, float* smem, uint8_t* stage, uint32_t* step_cnt, MixTc<PREC>& mlp) {
+__device__ __forceinline__ void rollout_body_mix(const RolloutArgs& a, float* smem, uint8_t* stage, uint32_t* step_cnt, const int nwarps,
+                                                 MixTc<PREC>& mlp) {
   constexpr bool EUBO = CFG::kEubo, TMIX = CFG::kTgt == 1, TPHI = CFG::kTgt == 2, RMIX = CFG::kRef == 2, RGAUSS = CFG::kRef == 1, EM = CFG::kEm, DIS = CFG::kDis;
   const lrds_spec& s = a.s;
-  const int NT = blockDim.x;
+  const int NT = nwarps * 32;  // particle threads
   const int tid = threadIdx.x;
-  const int nwarps = NT >> 5;
   const int b_raw = blockIdx.x * NT + tid;
   const bool live = b_raw < s.B;
   const int b = live ? b_raw : s.B - 1;  // idle lanes shadow the last particle, results are not stored
@@ -715,17 +720,58 @@ __device__ __forceinline__ void rollout_body_mix(const RolloutArgs& a, float* sm
   }
 }
 
+// The auxiliary warp of a CTA whose last tile is partial: it owns no particles and issues that tile's batches, in the
+// order the tile's warps hand them off (rollout_body_mix), so that the issue work stays off the tile's own warps - both
+// of which share their SM sub-partitions with three other particle warps and would otherwise bound the kernel.
+template <int PREC, class CFG>
+__device__ __forceinline__ void mix_aux_issuer(const RolloutArgs& a, uint8_t* stage, MixTc<PREC>& mlp) {
+  constexpr bool TMIX = CFG::kTgt == 1, RMIX = CFG::kRef == 2;
+  const lrds_spec& s = a.s;
+  const int dp = s.mlp.d_pad, K = s.K, nchunk = dp / JC, nh = mlp.L.nh;
+  const StageLayout SL = stage_layout(s, 2, true);
+  uint64_t* sbar = reinterpret_cast<uint64_t*>(stage);
+  const uint32_t mix_off_t = SL.tgt_logc_bytes + SL.tgt_param_bytes;
+  const uint32_t mix_off_r = SL.row_bytes + SL.ref_logc_bytes + SL.ref_param_bytes;
+  const int Mt = TMIX ? s.target.gmm.M : s.ref_t.M;
+  const uint32_t contr_bytes = gmm_mix_contr_bytes(Mt, dp), lg_part = gmm_mix_logit_part_bytes(Mt, dp);
+  const uint32_t lg_tail_off = contr_bytes + 2u * lg_part;
+  const uint32_t tgt_img = ptx::smem_u32(stage + SL.off_tgt + mix_off_t);
+  mlp.lbo = (uint32_t)(2 * dp) * 16u;
+  mlp.part_bytes = (contr_bytes - 16u) / 2u;
+  mlp.lg_part = lg_part;
+  const TcLayout& L = mlp.L;
+  for (int k = 0; k < K; ++k) {
+    ptx::mbar_wait(sbar + (k & 1), (uint32_t)(k >> 1) & 1u);  // the step's flags and images (read-only use)
+    const uint8_t* buf = stage + SL.off_buf + (k & 1) * SL.buf_bytes;
+    const uint32_t ref_img = ptx::smem_u32(buf + mix_off_r);
+    if constexpr (TMIX || RMIX) {
+      const PPtr<true> tail_t{tgt_img + lg_tail_off}, tail_r{ref_img + lg_tail_off};
+      const bool lg_t = TMIX && tail_t.ld1(MIX_MAX_M + 3) != 0.f, lg_r = RMIX && tail_r.ld1(MIX_MAX_M + 3) != 0.f;
+      if (lg_t || lg_r)
+        mlp.issue_when_ready([&]() {
+          if (lg_t) mlp.logit(0, tgt_img + contr_bytes);
+          if (lg_r) mlp.logit(1, ref_img + contr_bytes);
+        });
+    }
+    mlp.issue_when_ready([&]() { mlp.gemm(L.off_in, L.Kin, C); });
+    for (int l = 0; l < nh; ++l) mlp.issue_when_ready([&]() { mlp.gemm(L.off_hid + (uint32_t)(l * C * C * L.es), C, C); });
+    mlp.issue_when_ready([&]() { mlp.gemm(L.off_out, C, L.Nout); });
+    for (int c = 0; c < nchunk; ++c) mlp.issue_when_ready([&]() { mlp.template chunk<TMIX, RMIX>(c, tgt_img, ref_img); });
+  }
+}
+
 // shared memory: [weight image | mbarriers + TMEM slot | hand-off counters | operand stage | particle columns]
 template <int PREC, class CFG>
 __global__ void __launch_bounds__(MIX_MAX_WARPS * 32, 1)
-rollout_mix_kernel(const RolloutArgs a, const uint8_t* __restrict__ image, const uint32_t tmem_cols) {
+rollout_mix_kernel(const RolloutArgs a, const uint8_t* __restrict__ image, const uint32_t tmem_cols, const int nwarps) {
+  // nwarps = particle warps; blockDim.x / 32 = nwarps + 1 when the last tile is partial (the auxiliary issuer warp)
   extern __shared__ __align__(128) uint8_t smem_raw[];
   constexpr bool TMIX = CFG::kTgt == 1, RMIX = CFG::kRef == 2;
   const lrds_spec& s = a.s;
   const TcLayout TL = tc_layout(s.d, s.mlp.num_hidden, PREC);
   const int tid = threadIdx.x;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // warp-uniform for the compiler as well
-  const int nwarps = blockDim.x >> 5;
+  const bool has_aux = (int)(blockDim.x >> 5) > nwarps;
   uint8_t* img = smem_raw;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + TL.bytes);  // [0] image, [1 + t] MMAs of tile t done
   uint32_t* slot = reinterpret_cast<uint32_t*>(smem_raw + TL.bytes + 48);
@@ -765,7 +811,8 @@ rollout_mix_kernel(const RolloutArgs a, const uint8_t* __restrict__ image, const
   }
   ptx::mbar_wait(bars, 0);
   const uint32_t tmem = __shfl_sync(0xffffffffu, *slot, 0);
-  const int tile = warp >> 2;
+  const bool aux = warp == nwarps;              // the auxiliary issuer serves the partial last tile
+  const int tile = aux ? (nwarps - 1) >> 2 : warp >> 2;
   const int tile_warps = min(4, nwarps - 4 * tile);
   MixTc<PREC> mlp;
   mlp.L = TL;
@@ -779,8 +826,10 @@ rollout_mix_kernel(const RolloutArgs a, const uint8_t* __restrict__ image, const
   mlp.tile_warps = (uint32_t)tile_warps;
   mlp.target = 0u;
   mlp.hand = 0u;
-  // even hand-offs: the tile's last warp; odd ones: the one before it (the same warp in a one-warp tile)
+  // even hand-offs: the tile's last warp; odd ones: the one before it (the same warp in a one-warp tile); none in a
+  // partial tile served by the auxiliary warp
   mlp.issue_mask = ((warp & 3) == tile_warps - 1 ? 1u : 0u) | ((warp & 3) == max(tile_warps - 2, 0) ? 2u : 0u);
+  if (has_aux && tile_warps < 4) mlp.issue_mask = 0u;
   mlp.dp = s.mlp.d_pad;
 #ifdef LRDS_MIX_TIMING
   unsigned long long* tmw = reinterpret_cast<unsigned long long*>(cols + (size_t)col_layout(s, true).total * 32 * nwarps) + warp * 16;
@@ -788,7 +837,8 @@ rollout_mix_kernel(const RolloutArgs a, const uint8_t* __restrict__ image, const
   __syncwarp();
   mlp.tm.w = tmw;
 #endif
-  rollout_body_mix<PREC, CFG>(a, cols, stage, cnts + 4, mlp);
+  if (aux) mix_aux_issuer<PREC, CFG>(a, stage, mlp);
+  else rollout_body_mix<PREC, CFG>(a, cols, stage, cnts + 4, nwarps, mlp);
 #ifdef LRDS_MIX_TIMING
   __syncwarp();
   if ((blockIdx.x == 0 || blockIdx.x == gridDim.x / 2) && (tid & 31) < 16)

@@ -12,7 +12,9 @@ static int launch_mix_cfg(const RolloutArgs& a, const TcPlan& p, cudaStream_t st
   auto kernel = rollout_mix_kernel<LRDS_PRECISION_F16X3, CFG>;
   cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
   if (e == cudaSuccess) {
-    kernel<<<p.grid, p.warps * 32, p.smem, st>>>(a, static_cast<const uint8_t*>(a.s.mlp.tc_image), p.tmem_cols);
+    // a partial last tile gets the auxiliary issuer warp (lrds_rollout_mix.cuh) when the CTA has room for it
+    const int aux = (p.warps % 4 != 0 && p.warps < MIX_MAX_WARPS) ? 1 : 0;
+    kernel<<<p.grid, (p.warps + aux) * 32, p.smem, st>>>(a, static_cast<const uint8_t*>(a.s.mlp.tc_image), p.tmem_cols, p.warps);
     e = cudaGetLastError();
   }
   if (e != cudaSuccess) {

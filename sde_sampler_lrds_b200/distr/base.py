@@ -148,6 +148,12 @@ class Distribution(torch.nn.Module):
         self.expectations = {}
         self._lrds_cache = {}
 
+    def __getstate__(self):
+        # copy.deepcopy / pickling: the packed blocks hold ctypes structs with device pointers; a copy re-packs
+        state = self.__dict__.copy()
+        state["_lrds_cache"] = {}
+        return state
+
     # ---- packing hook: subclasses return (N.Distr, keepalive) for a device ------------------------------
     def _lrds_pack(self, device):
         raise NotImplementedError(f"{type(self).__name__} has no B200 kernel (no fallback is provided).")

@@ -33,7 +33,10 @@ def _axpy_step(x, s, z, a, b, c):
         z = torch.empty_like(xf)
         seed = (int(torch.initial_seed()) & 0xFFFFFFFF) | (next(_noise_calls) << 32)
         flat = xf.reshape(-1, xf.shape[-1])
-        N.check(N.lib().lrds_normals(seed, 0, 0, 1, flat.shape[0], flat.shape[1], N.ptr(z), N.stream_ptr(x.device)))
+        # every rank of a torch.distributed job draws its own increments: the rank offsets the particle index
+        rank = torch.distributed.get_rank() if torch.distributed.is_available() and torch.distributed.is_initialized() else 0
+        with torch.cuda.device(x.device):
+            N.check(N.lib().lrds_normals(seed, (rank & 0xFF) << 24, 0, 1, flat.shape[0], flat.shape[1], N.ptr(z), N.stream_ptr(x.device)))
     zf = z.detach().to(torch.float32).contiguous()
     out = torch.empty_like(xf)
     with torch.cuda.device(x.device):
@@ -51,18 +54,23 @@ class TorchSDE(Module):
     def __init__(self, terminal_t: float = 1.0):
         super().__init__()
         self.register_buffer("terminal_t", torch.tensor(terminal_t, dtype=torch.float), persistent=False)
-        self._host = None
+        object.__setattr__(self, "_host", None)  # plain attribute: the CPU copy must not become a child module
 
     def host(self):
         """CPU copy of the scalar algebra (used to fill per-step tables without device round trips)."""
         if self.terminal_t.device.type == "cpu":
             return self
         if self._host is None:
-            self._host = copy.deepcopy(self).to("cpu")
+            object.__setattr__(self, "_host", copy.deepcopy(self).to("cpu"))
         return self._host
 
+    def __getstate__(self):
+        state = self.__dict__.copy()
+        state["_host"] = None
+        return state
+
     def _apply(self, fn):
-        self._host = None
+        object.__setattr__(self, "_host", None)
         return super()._apply(fn)
 
     @property

@@ -40,6 +40,18 @@ def _fid(fn):
     return (id(owner), getattr(fn, "__name__", "")) if owner is not None else id(fn)
 
 
+def _state(obj):
+    """(identity, tensor versions) of an object a plan was packed from.  The identity is an ``id``: the cache entry keeps
+    a strong reference to the object (``_cached``), so the address cannot be recycled while the entry lives; in-place
+    edits of its parameters / buffers show up in the version counters."""
+    if obj is None:
+        return None
+    if isinstance(obj, torch.nn.Module):
+        return (id(obj),) + tuple((t.data_ptr(), t._version) for t in list(obj.parameters()) + list(obj.buffers()))
+    tensors = tuple(v for v in vars(obj).values() if isinstance(v, torch.Tensor)) if hasattr(obj, "__dict__") else ()
+    return (id(obj),) + tuple((t.data_ptr(), t._version) for t in tensors)
+
+
 def _resolve_reference(ref_ctrl):
     if ref_ctrl is None:
         return None
@@ -76,6 +88,7 @@ class BaseOCLoss:
         self.n_filtered = 0
         self.precision = precision
         self._plans: dict = {}
+        self._grids: dict = {}
         self._calls = itertools.count()
 
     # ---- estimators (oc.py:134-173) ---------------------------------------------------------------------------
@@ -163,24 +176,44 @@ class BaseOCLoss:
         """Plans are cached by everything that does not depend on the control's parameters (grid, schedule, reference and
         target blocks: O(K) host work, ~45 ms at K = 200); a parameter update (training step, EMA
         swap) only refreshes the weight images and the TimeEmbed rows of the cached plan (pack.refresh_ctrl)."""
-        skey, vers = key
+        skey, vers, refs = key
         hit = self._plans.get(skey)
         if hit is None:
             if len(self._plans) >= 16:
                 self._plans.pop(next(iter(self._plans)))
-            hit = self._plans[skey] = [build(), vers]
+            hit = self._plans[skey] = [build(), vers, refs]  # refs: the keyed objects stay alive with the entry
         elif hit[1] != vers:
             pack.refresh_ctrl(hit[0], info, device)
             hit[1] = vers
         return hit[0]
 
-    def _key(self, tag, ts, device, info, extra=()):
-        tsc = ts.detach().to("cpu", torch.float32)
+    def clear_plans(self):
+        """Drops every cached rollout plan (the solvers call this when they swap the reference or the prior)."""
+        self._plans.clear()
+        self._grids.clear()
+
+    def _grid_bytes(self, ts):
+        """The time grid as bytes for the plan key.  A device-resident grid is read back ONCE per (storage, version):
+        ``ts.to('cpu')`` is a stream synchronisation, which must not sit in front of every ``simulate``."""
+        if not ts.is_cuda:
+            return ts.detach().to(torch.float32).numpy().tobytes()
+        gkey = (ts.data_ptr(), ts._version, tuple(ts.shape), ts.dtype)
+        hit = self._grids.get(gkey)
+        if hit is None or hit[1] is not ts:
+            if len(self._grids) >= 16:
+                self._grids.pop(next(iter(self._grids)))
+            hit = self._grids[gkey] = (ts.detach().to("cpu", torch.float32).numpy().tobytes(), ts)  # keeps the storage alive
+        return hit[0]
+
+    def _key(self, tag, ts, device, info, extra=(), objs=()):
+        """(static key, control-parameter versions, keyed objects).  ``objs``: further objects the plan is packed from
+        (references, priors, the owner of the terminal log-density)."""
         vers = tuple((p.data_ptr(), p._version) for p in info.base.parameters())
         if info.score_model is not None:
             vers += tuple((p.data_ptr(), p._version) for p in info.score_model.parameters())
-        return (tag, tsc.numpy().tobytes(), str(device), id(info.target), self.precision or pack.default_precision(),
-                info.kind, id(info.sde), id(info.prior), extra), vers
+        refs = (info.target, info.sde, info.prior) + tuple(objs)
+        return ((tag, self._grid_bytes(ts), str(device), self.precision or pack.default_precision(), info.kind, extra,
+                 tuple(_state(o) for o in refs)), vers, refs)
 
 
 def _terminal(spec, keep, device, terminal_unnorm_log_prob, info):
@@ -229,7 +262,8 @@ class EMReferenceSDELoss(BaseOCLoss):
         info = self._ctrl(use_ema)
         ref = _resolve_reference(self.reference_ctrl)
         ref0, _ = pack.resolve_log_prob(reference_log_prob)
-        key = self._key((self._variant, eubo, self._init_cost), ts, device, info, (id(ref), id(ref0), _fid(terminal_unnorm_log_prob)))
+        key = self._key((self._variant, eubo, self._init_cost), ts, device, info, (_fid(terminal_unnorm_log_prob),),
+                        objs=(ref, ref0, getattr(terminal_unnorm_log_prob, "__self__", terminal_unnorm_log_prob), self.sde))
 
         def build():
             if eubo and ref is None and not self._init_cost:
@@ -384,7 +418,8 @@ class ExponentialIntegratorSDELoss(BaseOCLoss):
         info = self._ctrl(use_ema)
         ref0, _ = pack.resolve_log_prob(reference_log_prob)
         key = self._key(("dds", bool(compute_ito_int), self.alpha, self.sigma), ts, device, info,
-                        (id(ref0), _fid(terminal_unnorm_log_prob)))
+                        (_fid(terminal_unnorm_log_prob),),
+                        objs=(ref0, getattr(terminal_unnorm_log_prob, "__self__", terminal_unnorm_log_prob)))
 
         def build():
             tsc, pairs = pack._scalar_rows(ts)
@@ -459,7 +494,8 @@ class TimeReversalLoss(BaseOCLoss):
         info = self._ctrl(use_ema)
         prior, _ = pack.resolve_log_prob(initial_log_prob)
         key = self._key(("dis", bool(compute_ito_int), bool(train)), ts, device, info,
-                        (id(prior), _fid(terminal_unnorm_log_prob)))
+                        (_fid(terminal_unnorm_log_prob),),
+                        objs=(prior, getattr(terminal_unnorm_log_prob, "__self__", terminal_unnorm_log_prob), self.sde))
 
         def build():
             sde = self.sde.host()
@@ -535,7 +571,8 @@ class ControlledLangevinSDELoss(BaseOCLoss):
             raise NotImplementedError("CMCD needs a ControlledLangevinSDE")
         info = self._ctrl(use_ema)
         prior, _ = pack.resolve_log_prob(initial_log_prob)
-        key = self._key(("cmcd", eubo), ts, device, info, (id(prior), _fid(terminal_unnorm_log_prob)))
+        key = self._key(("cmcd", eubo), ts, device, info, (_fid(terminal_unnorm_log_prob),),
+                        objs=(prior, getattr(terminal_unnorm_log_prob, "__self__", terminal_unnorm_log_prob), self.sde))
 
         def build():
             sde = self.sde

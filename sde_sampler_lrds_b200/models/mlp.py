@@ -98,6 +98,13 @@ class FourierMLP(Model):
         Model.init_linear(self.out_layer, bias_init=last_bias_init, weight_init=last_weight_init)
         self._packed = {}
 
+    def __getstate__(self):
+        # copy.deepcopy (EMA AveragedModel, CMCD.update_prior) / pickling: the packed weight blocks hold ctypes structs
+        # with device pointers; a copy re-packs its own
+        state = self.__dict__.copy()
+        state["_packed"] = {}
+        return state
+
     # ---- packing for the kernels -------------------------------------------------------------------------------
     def _version(self):
         return tuple((p.data_ptr(), p._version) for p in self.parameters())

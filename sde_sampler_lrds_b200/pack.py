@@ -250,12 +250,12 @@ def run_rollout(plan: Plan, x0: torch.Tensor, noise: torch.Tensor | None, seed: 
     """Launches lrds_rollout for ``plan`` on x0's device; returns (x_T, rnd (B,1), xs | None)."""
     if not x0.is_cuda:
         raise N.LrdsError("the rollout runs on CUDA tensors only (no CPU fallback)")
-    spec = plan.spec
     dev = x0.device
     xf = x0.detach().to(torch.float32).contiguous()
     B, d = xf.shape
-    if d != spec.d:
-        raise ValueError(f"x has dimension {d}, the model expects {spec.d}")
+    if d != plan.spec.d:
+        raise ValueError(f"x has dimension {d}, the model expects {plan.spec.d}")
+    spec = N.Spec.from_buffer_copy(plan.spec)  # the cached plan is shared between calls (and threads): never mutated here
     spec.B = B
     if noise is not None:
         noise = noise.detach().to(dev, torch.float32).contiguous()

@@ -99,6 +99,11 @@ class TrainableDiff(torch.nn.Module):
             self.generative_ctrl_ema = torch.optim.swa_utils.AveragedModel(
                 self.generative_ctrl, multi_avg_fn=torch.optim.swa_utils.get_ema_multi_avg_fn(1.0 - alpha),
                 device=self.device)
+            # AveragedModel deep-copies the control, and with it the objects behind its bound target / prior scores and
+            # its SDE; the averaged parameters are the control's own, everything else must stay the solver's objects
+            for name in ("target_score", "prior_score", "sde"):
+                if hasattr(self.generative_ctrl, name):
+                    setattr(self.generative_ctrl_ema.module, name, getattr(self.generative_ctrl, name))
         else:
             self.generative_ctrl_ema = self.generative_ctrl
 
@@ -337,6 +342,8 @@ class RDS(TrainableDiff):
             raise NotImplementedError(f"Reference type {ref_type} is unknown.")
         self.reference_distr = self.reference_score_t.distr_at(torch.tensor(0.0), self.device)
         self.ref_type = ref_type
+        if isinstance(getattr(self, "loss", None), BaseOCLoss):
+            self.loss.clear_plans()  # plans packed from the previous reference must not be served again
 
     def reference_ctrl(self, t: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
         return self.reference_score_t(t, x)

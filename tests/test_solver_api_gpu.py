@@ -83,6 +83,73 @@ def test_make_model_evaluate(solver_type, kw, device):
     assert abs(got.metrics["eval/lv_loss"] - want["eval/lv_loss"]) < 1e-3 * max(1, want["eval/lv_loss"])
 
 
+@pytest.mark.parametrize("solver_type, model_type", [
+    ("vp-ref", "target_informed_zero_init"),
+    ("dis_orig", "target_informed_lerp_tempering"),
+    ("cmcd", "target_informed_zero_init"),
+])
+def test_use_ema_with_target_informed_controls(solver_type, model_type, device):
+    """make_model(use_ema=True): the EMA AveragedModel deep-copies the control (and, through its bound score methods,
+    the target / prior); the copy must keep pointing at the solver's own objects, and objects that have already been
+    packed for the kernels (ctypes blocks in their caches) must survive ``copy.deepcopy``."""
+    import copy
+    from sde_sampler_lrds_b200 import benchmark_utils as BU
+    from sde_sampler_lrds_b200 import pack
+    d, M = 6, 5
+    details = {"sigma": 1.0, **_gmm_ref(d, M), "mean_ref": torch.zeros(d), "var_ref": torch.full((d,), 2.0),
+               "mean": torch.zeros(d), "var": torch.full((d,), 4.0)}
+    model = BU.make_model(solver_type=solver_type, ref_type="gmm" if solver_type == "vp-ref" else "gaussian" if solver_type == "cmcd" else "default",
+                          loss_type="lv", integrator_type="ei" if solver_type == "vp-ref" else "em", model_type=model_type,
+                          time_type="uniform", solver_details=details,
+                          target_details=BU.make_target_details("many_modes", dim=d, n_modes=M), training_details=TRAIN,
+                          n_steps=16, device=str(device), use_ema=True)
+    assert isinstance(model.generative_ctrl_ema, torch.optim.swa_utils.AveragedModel)
+    assert pack.resolve_ctrl(model.generative_ctrl_ema).target is model.target
+    _randomise_last_layers(model)
+    model.generative_ctrl_ema.update_parameters(model.generative_ctrl)
+    res_ema = model.compute_results(use_ema=True)     # evaluates the EMA copy through the kernels (packs target + weights)
+    res_raw = model.compute_results(use_ema=False)
+    for r in (res_ema, res_raw):
+        assert torch.isfinite(r.samples).all() and math.isfinite(r.metrics["eval/elbo"])
+    # a second EMA update + evaluation after the caches are populated, and a deepcopy of a packed control / target
+    model.generative_ctrl_ema.update_parameters(model.generative_ctrl)
+    assert math.isfinite(model.compute_results(use_ema=True).metrics["eval/elbo"])
+    clone = copy.deepcopy(model.generative_ctrl)
+    assert clone.base_model._packed == {} and copy.deepcopy(model.target)._lrds_cache == {}
+    if solver_type == "cmcd":  # update_prior rebuilds the models (deep copies inside) after everything has been packed
+        model.update_prior(torch.zeros(d, device=device), torch.full((d,), 3.0, device=device))
+        assert math.isfinite(model.compute_results(use_ema=True).metrics["eval/elbo"])
+
+
+def test_plan_cache_follows_a_reference_change(device):
+    """RDS.change_reference_type swaps the reference objects of a long-lived loss: the next rollout must be packed
+    from the NEW reference (never a stale plan), and an in-place edit of the reference's parameters must be seen."""
+    from sde_sampler_lrds_b200 import benchmark_utils as BU
+    d, M = 6, 5
+    details = {"sigma": 1.0, **_gmm_ref(d, M), "mean_ref": torch.zeros(d), "var_ref": torch.full((d,), 2.0)}
+    model = BU.make_model(solver_type="vp-ref", ref_type="gmm", loss_type="lv", integrator_type="ei",
+                          model_type="target_informed_zero_init", time_type="uniform", solver_details=details,
+                          target_details=BU.make_target_details("many_modes", dim=d, n_modes=M), training_details=TRAIN,
+                          n_steps=16, device=str(device))
+    _randomise_last_layers(model)
+    model.compute_results()  # sets eval_ts
+    x0 = model.prior.sample((256,))
+
+    def run():
+        return model.loss.simulate(model.eval_ts, x0, model.clipped_target_unnorm_log_prob, model.reference_distr.log_prob, seed=3)[1]
+    a = run()
+    assert torch.equal(a, run())  # cached plan, same result
+    model.change_reference_type(ref_type="gaussian", mean=torch.ones(d), var=torch.full((d,), 1.5))
+    b = run()
+    assert not torch.allclose(a, b)
+    for _ in range(4):  # allocate / free look-alike objects: a recycled address must not resurrect an old plan
+        model.change_reference_type(ref_type="gaussian", mean=torch.ones(d), var=torch.full((d,), 1.5))
+        assert torch.equal(b, run())
+    model.reference_score_t.means.add_(0.5)  # in-place edit of the reference's parameters
+    model.reference_distr = model.reference_score_t.distr_at(torch.tensor(0.0), model.device)
+    assert not torch.allclose(b, run())
+
+
 def test_make_model_over_the_bracket_two_modes_target(device):
     from sde_sampler_lrds_b200 import benchmark_utils as BU
     model = BU.make_model(solver_type="vp-ref", ref_type="default", loss_type="lv", integrator_type="ei",
