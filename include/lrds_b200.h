@@ -213,6 +213,12 @@ typedef struct {
   lrds_distr target;   /* terminal_unnorm_log_prob + ScoreCtrl.target_score */
   lrds_gmm ref_t;      /* time-marginal reference score (has_ref_ctrl), one block per step */
   lrds_gmm ref_0;      /* reference_log_prob at the end of the rollout (LINEAR) / prior = initial_log_prob (CMCD) */
+  uint32_t* status;    /* optional (NULL = not counted): two device counters the rollout ADDS to.  [0] += particle threads
+                        * of an F16X3 launch whose fp16 tensor-core operands saturated at least once (a coordinate beyond
+                        * 65504 or a hidden pre-activation beyond 1023: the results of such a particle are not fp32-grade -
+                        * rerun with TF32X3, which has no magnitude limit); [1] += particles whose final log-weight or
+                        * state is not finite.  The two-threads-per-particle kernels count every thread that saw a
+                        * saturating value, so [0] can reach twice the number of affected particles. */
 } lrds_spec;
 
 /* ---- the rollout: replaces loss.simulate / loss.compute_eubo (losses/oc.py, callers solver/oc.py:305-632,

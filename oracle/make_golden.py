@@ -291,10 +291,44 @@ def run_reference_mala(case):
     return {"ys": torch.stack(ys), "step_size": step_size.detach().clone(), "log_acc": torch.stack(accs)}
 
 
+def run_reference_aux():
+    """Small public interfaces next to the rollout: ``get_timesteps`` grids (utils/common.py:30-82) for every grid kind
+    and SDE family the solvers build, and ``EulerIntegrator.integrate`` (eq/integrator.py:84-129) over a VP SDE with
+    recorded Brownian increments and off-grid output times."""
+    from sde_sampler.utils.common import get_timesteps
+    from sde_sampler.eq.integrator import EulerIntegrator
+    from tests.cases import AUX_SDES, AUX_GRIDS, euler_case
+    out = {"grids": {}}
+    for gname, (sde_name, kw) in AUX_GRIDS.items():
+        sde = build_reference_sde(AUX_SDES[sde_name]) if sde_name else None
+        out["grids"][gname] = get_timesteps(sde=sde, **kw).clone()
+    ec = euler_case()
+    sde = build_reference_sde(ec["sde"])
+    it = iter(ec["noise"])
+
+    def bm(s, t):
+        return next(it) * torch.sqrt(t - s)
+    integ = EulerIntegrator(dt=ec["dt"], rescale_t=None)
+    out["euler_xs"] = integ.integrate(sde, ec["ts"], ec["x0"], bm=bm).clone()
+    out["euler_xs_snr"] = None
+    it = iter(ec["noise"])
+    integ = EulerIntegrator(dt=None, steps=ec["snr_steps"])
+    out["euler_xs_snr"] = integ.integrate(sde, ec["ts_snr"], ec["x0"], bm=bm, snr_adapted=True).clone()
+    return out
+
+
 def main(argv):
     from tests.cases import CASES
     import_reference()
     os.makedirs(os.path.join(REPO, "tests", "golden"), exist_ok=True)
+    if argv and argv[0] == "--aux":  # python -m oracle.make_golden --aux
+        out = run_reference_aux()
+        out["torch_version"] = str(torch.__version__)
+        path = os.path.join(REPO, "tests", "golden", "aux_grids_euler.pt")
+        torch.save(out, path)
+        print(f"aux: {len(out['grids'])} grids, euler {tuple(out['euler_xs'].shape)} / snr {tuple(out['euler_xs_snr'].shape)} | "
+              f"{os.path.getsize(path)} B")
+        return
     if argv and argv[0] == "--mala":  # python -m oracle.make_golden --mala [case ...]
         from tests.cases import MALA_CASES
         for name in argv[1:] or list(MALA_CASES):

@@ -71,7 +71,7 @@ class Spec(C.Structure):
                 ("clip_model", C.c_float), ("clip_score", C.c_float), ("scale_score", C.c_float),
                 ("clip_target", C.c_float), ("cmcd_diff", C.c_float), ("cmcd_clip", C.c_float),
                 ("init_cost", C.c_int32), ("rnd_offset", C.c_float),
-                ("steps", FP), ("mlp", Mlp), ("target", Distr), ("ref_t", Gmm), ("ref_0", Gmm)]
+                ("steps", FP), ("mlp", Mlp), ("target", Distr), ("ref_t", Gmm), ("ref_0", Gmm), ("status", FP)]
 
 
 EXPORTS = ["lrds_rollout", "lrds_tc_image_bytes", "lrds_gmm_mix_tc_bytes", "lrds_pack_gmm_mix_tc", "lrds_logreg_tc_bytes",

@@ -83,6 +83,20 @@ __device__ __forceinline__ float hsum(u64 a, u64 b) {  // (a.x + a.y) + (b.x + b
 }
 }  // namespace f2
 
+// three-input max (FMNMX3 on sm_100) for the saturation trackers of the fp16 tensor-core operands
+__device__ __forceinline__ float max3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+__device__ __forceinline__ float max3abs(float a, float b, float c) {  // max(|a|, |b|, |c|)
+  float d;
+  asm("max.abs.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+constexpr float F16X3_MAX_COORD = 65504.f;  // largest coordinate the fp16 (hi, lo) A operand holds
+constexpr float F16X3_MAX_PREACT = 1023.f;  // hidden activations enter as 64 GELU(v): v beyond this saturates
+
 // GELU with the exact (erf) definition, conf/model/base/fouriermlp.yaml:5-6:  v/2 (1 + erf(v / sqrt 2)).
 // erf(|x|) = 1 - 2^(|x| Q(|x|)) with a degree-6 minimax Q on [0, 4] (saturated beyond): absolute error of erf
 // 7.7e-8, of the GELU 1.6e-7 max(1, |v|) - the same as evaluating the erf formula in fp32 (tools/fit_erf.py).

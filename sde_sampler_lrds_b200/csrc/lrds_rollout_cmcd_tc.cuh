@@ -522,6 +522,7 @@ rollout_cmcd_tc_kernel(const RolloutArgs a, const uint8_t* __restrict__ image, c
   }
   if (live && a.x_out != nullptr)
     for (int j = half; j < d; j += 2) a.x_out[(int64_t)b * d + j] = X(j);
+  report_status(s, live, mlp.saturated(), !half && !isfinite(rnd));
   ptx::tc_fence_before();
   __syncthreads();
   if (warp == 0) ptx::tmem_dealloc(tmem, tmem_cols);

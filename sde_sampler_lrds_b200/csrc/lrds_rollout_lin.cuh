@@ -203,8 +203,14 @@ rollout_lin_kernel(const RolloutArgs a, const uint8_t* __restrict__ image, const
     rnd += lref - clipf(ltgt, s.clip_target);
     if (live) a.rnd_out[b] = rnd;
   }
+  float xsum = 0.f;
   if (live && a.x_out != nullptr)
-    for (int j = half; j < d; j += 2) a.x_out[(int64_t)b * d + j] = X(j);
+    for (int j = half; j < d; j += 2) {
+      const float v = X(j);
+      xsum += v;
+      a.x_out[(int64_t)b * d + j] = v;
+    }
+  report_status(s, live, mlp.saturated(), !isfinite(half ? xsum : rnd + xsum) && !half);  // non-finite: counted once per particle
   ptx::tc_fence_before();
   __syncthreads();
   if (warp == 0) ptx::tmem_dealloc(tmem, tmem_cols);

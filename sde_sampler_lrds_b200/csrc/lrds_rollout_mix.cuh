@@ -713,11 +713,17 @@ __device__ __forceinline__ void rollout_body_mix(const RolloutArgs& a, float* sm
     rnd += lref - clipf(target_logp(), s.clip_target);
   }
 
+  float xsum = 0.f;
   if (live) {
     a.rnd_out[b] = rnd;
     if (a.x_out != nullptr)
-      for (int j = 0; j < d; ++j) a.x_out[(int64_t)b * d + j] = P.x(j);
+      for (int j = 0; j < d; ++j) {
+        const float v = P.x(j);
+        xsum += v;
+        a.x_out[(int64_t)b * d + j] = v;
+      }
   }
+  report_status(s, live, mlp.saturated(), !isfinite(rnd + xsum));
 }
 
 // The auxiliary warp of a CTA whose last tile is partial: it owns no particles and issues that tile's batches, in the

@@ -25,6 +25,14 @@ struct RolloutArgs {
   float* traj_out;
 };
 
+// spec.status (include/lrds_b200.h): [0] += this thread saw a saturating fp16 operand, [1] += non-finite result
+__device__ __forceinline__ void report_status(const lrds_spec& s, bool live, bool saturated, bool nonfinite) {
+  if (s.status != nullptr && live) {
+    if (saturated) atomicAdd(s.status, 1u);
+    if (nonfinite) atomicAdd(s.status + 1, 1u);
+  }
+}
+
 // shared-memory floats per particle for a spec (host + device agree through this one function)
 struct ColLayout {
   int x, act, rt, rr, g, us, tsd, db, total;
@@ -182,6 +190,7 @@ struct SimtMlp {
     mlp_hidden<BIAS_SH>(w, bias1, x, act);
   }
   __device__ __forceinline__ void out_chunk(int j0, float (&out)[JC]) { mlp_out_chunk(w, act, j0, out); }
+  __device__ __forceinline__ bool saturated() const { return false; }  // fp32 FFMA: no operand conversion
 };
 
 // ---- target helpers ---------------------------------------------------------------------------------
@@ -612,11 +621,17 @@ __device__ __forceinline__ void rollout_body(const RolloutArgs& a, float* smem, 
     }
   }
 
+  float xsum = 0.f;
   if (live) {
     a.rnd_out[b] = rnd;
     if (a.x_out != nullptr)
-      for (int j = 0; j < d; ++j) a.x_out[(int64_t)b * d + j] = P.x(j);
+      for (int j = 0; j < d; ++j) {
+        const float v = P.x(j);
+        xsum += v;
+        a.x_out[(int64_t)b * d + j] = v;
+      }
   }
+  report_status(s, live, mlp.saturated(), !isfinite(rnd + xsum));
 }
 
 template <int KIND>

@@ -155,6 +155,8 @@ struct TcMlp {
   int bar_id, bar_threads;
   bool issuer;
   int dp;              // columns of x held by the body (d rounded up to 8, zero padded)
+  float vmax = 0.f, xmax = 0.f;  // F16X3: largest hidden pre-activation / |coordinate| this thread has converted to fp16
+  __device__ __forceinline__ bool saturated() const { return kF16 && (vmax > F16X3_MAX_PREACT || xmax > F16X3_MAX_COORD); }
 
   // (hi, lo) operand bits of an activation.  The 3-pass splits truncate (one LOP3): hi = the top 11 significand bits,
   // lo = v - hi is exact in fp32; the tf32 tensor core drops lo's bits below tf32 itself, the fp16 conversion rounds
@@ -229,6 +231,7 @@ struct TcMlp {
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         u64 hi, lo;
+        xmax = max3abs(xmax, v[2 * i], v[2 * i + 1]);
         f2::split(f2::pack(v[2 * i], v[2 * i + 1]), hi, lo);
         float h0, h1, l0, l1;
         f2::unpack(hi, h0, h1);
@@ -289,6 +292,11 @@ struct TcMlp {
         for (int e = 0; e < 2; ++e) {
           const u64 acc = f2::pack(__uint_as_float(r[4 * i + 2 * e]), __uint_as_float(r[4 * i + 2 * e + 1]));
           const u64 v = f2::fma(acc, us2, e ? f2::pack(b.z, b.w) : f2::pack(b.x, b.y));
+          {
+            float va, vb;
+            f2::unpack(v, va, vb);
+            vmax = max3(vmax, va, vb);
+          }
           const u64 g = gelu_pair(v, 5.0f, TC_ACT_SCALE);  // TC_ACT_SCALE / 2 = 2^5
           u64 hi, lo;
           f2::split(g, hi, lo);

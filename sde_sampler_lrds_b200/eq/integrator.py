@@ -20,10 +20,9 @@ from ..utils.common import get_timesteps
 
 def interpolate(ts: torch.Tensor, s, t, xs: torch.Tensor, xt: torch.Tensor, eps: float = 1e-8) -> torch.Tensor:
     """Linear interpolation of the states at the output times in (s, t]   (integrator.py:66-82)."""
-    mask = ts <= t + eps
-    tsel = ts[mask]
-    coeff = ((tsel - s) / (t - s)).clip(0.0, 1.0)
-    coeff = coeff.view(-1, *[1] * xs.ndim)
+    ind = torch.searchsorted(ts, t + eps, side="right")
+    t_eval = ts[:ind]
+    coeff = ((t_eval - s) / (t - s)).view(-1, *[1] * xs.ndim)  # not clipped: an output time within eps behind t extrapolates, as in the reference
     return torch.lerp(xs.unsqueeze(0), xt.unsqueeze(0), coeff)
 
 

@@ -27,7 +27,7 @@ import torch
 
 from .. import _native as N
 from .. import pack
-from ..distr.base import fill_gmm
+from ..distr.base import Distribution, fill_gmm
 from ..eq.sdes import OU, ControlledLangevinSDE, MarginalReference
 from ..estimators import estimator_partials, metrics_from_partials
 from ..utils.common import Results
@@ -38,6 +38,20 @@ def _fid(fn):
     (``solver.clipped_target_unnorm_log_prob``), so it is keyed by its owner and name."""
     owner = getattr(fn, "__self__", None)
     return (id(owner), getattr(fn, "__name__", "")) if owner is not None else id(fn)
+
+
+def _terminal_target(fn):
+    """The Distribution behind a terminal log-density callable (the object a plan is packed from; NOT the solver that
+    owns ``clipped_target_unnorm_log_prob``, whose parameters change with every training step)."""
+    try:
+        return pack.resolve_log_prob(fn)[0]
+    except NotImplementedError:
+        return None
+
+
+def _fid_clip(fn):
+    owner = getattr(fn, "__self__", None)
+    return getattr(owner, "clip_target", None) if owner is not None and not isinstance(owner, Distribution) else None
 
 
 def _state(obj):
@@ -104,6 +118,9 @@ class BaseOCLoss:
             weights = torch.exp(-rnd.double() - part[0]).div(part[1]).to(rnd.dtype)  # softmax(-rnd, dim=0)
             log_norm_const_preds = {"log_norm_const_is": m["log_norm_const_is"]}
             metrics["eval/lv_loss"] = m["lv_loss"]
+            # ESS of the importance weights, (sum w)^2 / sum w^2 (get_metrics, eval/metrics.py:134-140), from the same partials
+            metrics["eval/effective_sample_size"] = m["effective_sample_size"]
+            metrics["eval/norm_effective_sample_size"] = m["norm_effective_sample_size"]
         else:
             weights, log_norm_const_preds = None, {}
         return Results(samples=samples, weights=weights, log_norm_const_preds=log_norm_const_preds, ts=ts, xs=xs,
@@ -262,8 +279,8 @@ class EMReferenceSDELoss(BaseOCLoss):
         info = self._ctrl(use_ema)
         ref = _resolve_reference(self.reference_ctrl)
         ref0, _ = pack.resolve_log_prob(reference_log_prob)
-        key = self._key((self._variant, eubo, self._init_cost), ts, device, info, (_fid(terminal_unnorm_log_prob),),
-                        objs=(ref, ref0, getattr(terminal_unnorm_log_prob, "__self__", terminal_unnorm_log_prob), self.sde))
+        key = self._key((self._variant, eubo, self._init_cost), ts, device, info, (_fid(terminal_unnorm_log_prob), _fid_clip(terminal_unnorm_log_prob)),
+                        objs=(ref, ref0, _terminal_target(terminal_unnorm_log_prob), self.sde))
 
         def build():
             if eubo and ref is None and not self._init_cost:
@@ -418,8 +435,8 @@ class ExponentialIntegratorSDELoss(BaseOCLoss):
         info = self._ctrl(use_ema)
         ref0, _ = pack.resolve_log_prob(reference_log_prob)
         key = self._key(("dds", bool(compute_ito_int), self.alpha, self.sigma), ts, device, info,
-                        (_fid(terminal_unnorm_log_prob),),
-                        objs=(ref0, getattr(terminal_unnorm_log_prob, "__self__", terminal_unnorm_log_prob)))
+                        (_fid(terminal_unnorm_log_prob), _fid_clip(terminal_unnorm_log_prob)),
+                        objs=(ref0, _terminal_target(terminal_unnorm_log_prob)))
 
         def build():
             tsc, pairs = pack._scalar_rows(ts)
@@ -494,8 +511,8 @@ class TimeReversalLoss(BaseOCLoss):
         info = self._ctrl(use_ema)
         prior, _ = pack.resolve_log_prob(initial_log_prob)
         key = self._key(("dis", bool(compute_ito_int), bool(train)), ts, device, info,
-                        (_fid(terminal_unnorm_log_prob),),
-                        objs=(prior, getattr(terminal_unnorm_log_prob, "__self__", terminal_unnorm_log_prob), self.sde))
+                        (_fid(terminal_unnorm_log_prob), _fid_clip(terminal_unnorm_log_prob)),
+                        objs=(prior, _terminal_target(terminal_unnorm_log_prob), self.sde))
 
         def build():
             sde = self.sde.host()
@@ -571,8 +588,8 @@ class ControlledLangevinSDELoss(BaseOCLoss):
             raise NotImplementedError("CMCD needs a ControlledLangevinSDE")
         info = self._ctrl(use_ema)
         prior, _ = pack.resolve_log_prob(initial_log_prob)
-        key = self._key(("cmcd", eubo), ts, device, info, (_fid(terminal_unnorm_log_prob),),
-                        objs=(prior, getattr(terminal_unnorm_log_prob, "__self__", terminal_unnorm_log_prob), self.sde))
+        key = self._key(("cmcd", eubo), ts, device, info, (_fid(terminal_unnorm_log_prob), _fid_clip(terminal_unnorm_log_prob)),
+                        objs=(prior, _terminal_target(terminal_unnorm_log_prob), self.sde))
 
         def build():
             sde = self.sde

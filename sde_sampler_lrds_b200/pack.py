@@ -245,6 +245,29 @@ def refresh_ctrl(plan: "Plan", info: CtrlInfo, device):
     table[:, N.STEP_GAMMA] = gamma
 
 
+_status: dict = {}
+
+
+def status_counters(device) -> torch.Tensor:
+    """The device's two rollout status counters (lrds_spec.status): [0] particle threads whose fp16 tensor-core operands
+    saturated (f16x3: |coordinate| > 65504 or a hidden pre-activation > 1023), [1] particles with a non-finite result.
+    Every rollout launched from this process ADDS to them; ``read_status`` returns and optionally clears them."""
+    dev = torch.device(device)
+    key = (dev.type, dev.index if dev.index is not None else torch.cuda.current_device())
+    if key not in _status:
+        _status[key] = torch.zeros(2, dtype=torch.int32, device=dev)
+    return _status[key]
+
+
+def read_status(device, reset: bool = True) -> dict:
+    """{'saturated': n, 'nonfinite': n} accumulated by the rollouts on ``device`` since the last reset (synchronises)."""
+    t = status_counters(device)
+    sat, nf = (int(v) for v in t.cpu())
+    if reset:
+        t.zero_()
+    return {"saturated": sat, "nonfinite": nf}
+
+
 def run_rollout(plan: Plan, x0: torch.Tensor, noise: torch.Tensor | None, seed: int, particle_offset: int,
                 return_traj: bool):
     """Launches lrds_rollout for ``plan`` on x0's device; returns (x_T, rnd (B,1), xs | None)."""
@@ -257,6 +280,8 @@ def run_rollout(plan: Plan, x0: torch.Tensor, noise: torch.Tensor | None, seed: 
         raise ValueError(f"x has dimension {d}, the model expects {plan.spec.d}")
     spec = N.Spec.from_buffer_copy(plan.spec)  # the cached plan is shared between calls (and threads): never mutated here
     spec.B = B
+    status = status_counters(dev)
+    spec.status = status.data_ptr()
     if noise is not None:
         noise = noise.detach().to(dev, torch.float32).contiguous()
         if tuple(noise.shape) != (plan.noise_steps, B, d):

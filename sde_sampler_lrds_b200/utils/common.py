@@ -18,10 +18,12 @@ Results = namedtuple(
 
 
 def _bisect(fn, low, high, targets, iters):
-    """Vectorised bisection for a decreasing ``fn`` (reference: binary_search_v, utils/common.py:18-27)."""
+    """Vectorised bisection for a decreasing ``fn`` (reference: binary_search_v, utils/common.py:18-27).  Like the
+    reference, the first midpoint is whatever ``(low + high) / 2`` of the caller's scalars is (a Python float for float
+    bounds: the SDE formulas then see a double-precision scalar, which is visible in the last bit of the grid)."""
     for _ in range(iters):
         mid = (low + high) / 2.0
-        val = fn(mid if isinstance(mid, torch.Tensor) else torch.tensor(mid))
+        val = fn(mid)
         low = torch.where(val > targets, mid, low)
         high = torch.where(val <= targets, mid, high)
     return (low + high) / 2.0
@@ -38,7 +40,10 @@ def get_timesteps(start, end, dt=None, steps=None, rescale_t=None, n_attemps: in
         steps = int(math.ceil((end - start) / dt))
     if sde is not None:
         host = sde.host() if hasattr(sde, "host") else sde
-        snr0, snr1 = host.log_snr(torch.tensor(start)), host.log_snr(torch.tensor(end))
+        if hasattr(sde, "host"):  # the scalar algebra runs on the host copy: tensor-valued bounds follow it
+            start = start.cpu() if torch.is_tensor(start) else start
+            end = end.cpu() if torch.is_tensor(end) else end
+        snr0, snr1 = host.log_snr(start), host.log_snr(end)  # the caller's scalars as they are (utils/common.py:43-48)
         if torch.isnan(snr0):
             raise ValueError("NaN SNR at t_0")
         if torch.isnan(snr1):

@@ -143,6 +143,30 @@ def snr_ts_vp(sde: dict, K: int):
     return torch.concat([torch.FloatTensor([start]), mid, torch.FloatTensor([end])]).sort().values
 
 
+# ---- small public interfaces: time grids and the Euler integrator (goldens: oracle/make_golden.py --aux) ----------
+AUX_SDES = {"vp10": VP10, "vp20": VP20, "vpcos": {"kind": "vpcos", "c": 0.008, "scale": 1.0, "T": 1.0}, "pbm": PBM}
+AUX_GRIDS = {  # name -> (sde or None, get_timesteps keyword arguments)
+    "uniform_steps": (None, dict(start=0.0, end=1.0, steps=37)),
+    "uniform_dt": (None, dict(start=1e-3, end=5.0, dt=0.07)),
+    "cosine_dds": (None, dict(start=0.0, end=6.4, dt=0.05, rescale_t="cosine")),
+    "cosine_steps": (None, dict(start=0.0, end=3.2, steps=41, rescale_t="cosine")),
+    "snr_vp10": ("vp10", dict(start=1e-4, end=1.0 - 1e-4, steps=100)),
+    "snr_vp20": ("vp20", dict(start=1e-4, end=1.0 - 1e-4, steps=200)),
+    "snr_vp20_short": ("vp20", dict(start=1e-4, end=1.0 - 1e-4, steps=17)),
+    "snr_vpcos": ("vpcos", dict(start=1e-3, end=1.0 - 1e-3, steps=64)),
+    "snr_pbm": ("pbm", dict(start=1e-4, end=5.0 - 1e-4, steps=100)),
+}
+
+
+def euler_case():
+    """EulerIntegrator over the uncontrolled VP SDE: 40 Euler steps of dt = 0.025, output times partly off the grid."""
+    g = torch.Generator().manual_seed(77)
+    B, d = 33, 5
+    return {"sde": VP10, "dt": 0.025, "x0": torch.randn(B, d, generator=g), "noise": torch.randn(64, B, d, generator=g),
+            "ts": torch.tensor([0.0, 0.025, 0.06, 0.31, 0.5, 0.777, 1.0]),
+            "snr_steps": 24, "ts_snr": torch.tensor([1e-4, 0.2, 0.5, 0.9, 1.0 - 1e-4])}
+
+
 # ---- cases ---------------------------------------------------------------------------------
 
 

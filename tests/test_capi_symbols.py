@@ -28,7 +28,7 @@ def test_struct_sizes_match_header():
     assert C.sizeof(N.Phi4) == 16
     assert C.sizeof(N.LogReg) == 16 + 24 + 24 + 8
     assert C.sizeof(N.Distr) == 8 + C.sizeof(N.Gmm) + C.sizeof(N.Phi4) + C.sizeof(N.LogReg)
-    assert C.sizeof(N.Spec) == 40 + 24 + 8 + 8 + C.sizeof(N.Mlp) + C.sizeof(N.Distr) + 2 * C.sizeof(N.Gmm)
+    assert C.sizeof(N.Spec) == 40 + 24 + 8 + 8 + C.sizeof(N.Mlp) + C.sizeof(N.Distr) + 2 * C.sizeof(N.Gmm) + 8  # + status
 
 
 def test_invalid_arguments_are_rejected_without_a_gpu():

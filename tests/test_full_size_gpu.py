@@ -25,8 +25,11 @@ def _full_cases():
     return {
         "many_modes_ei": (lambda: T.case_ei_many_modes(K=200, B=65536), "f16x3"),  # the benchmark kernel (bench.py)
         "many_modes_ei_tf32x3": (lambda: T.case_ei_many_modes(K=200, B=65536), "tf32x3"),
+        "phi4_pis_f16x3": (lambda: T.case_pis_phi4(K=256, B=131072), "f16x3"),  # rollout_lin_kernel<F16X3, EM>: the kernel the shape table quotes
+        "phi4_dds_f16x3": (lambda: _dds256(), "f16x3"),                           # rollout_lin_kernel<F16X3, AXPY>
         "phi4_pis": (lambda: T.case_pis_phi4(K=256, B=131072), "tf32x3"),
         "phi4_dds": (lambda: _dds256(), "bf16"),
+        "many_modes_eubo": (lambda: dict(T.case_ei_many_modes(K=200, B=65536), eubo=True), "f16x3"),
         "logreg_cmcd": (lambda: T.case_cmcd_logreg(166, 60, K=100, B=262144), "f16x3"),  # logit / gradient GEMMs on tcgen05
         "logreg_cmcd_fp32": (lambda: T.case_cmcd_logreg(166, 60, K=100, B=32768), "fp32"),
     }
@@ -56,6 +59,9 @@ def test_full_size_rollout_is_tied_to_the_oracle(name, device):
     else:
         x0 = torch.randn(B, d, generator=g) * float(case["prior"][2]) + float(case["prior"][1])
     seed, off = 0xC0FFEE + case["seed"], 7 * B
+    if case.get("eubo"):
+        _full_size_eubo(built, case, x0, seed, off, device)
+        return
     x_full, rnd_full, _ = built.simulate(x0, None, seed=seed, particle_offset=off)
     assert x_full.shape == (B, d) and rnd_full.shape == (B, 1)
     assert torch.isfinite(x_full).all() and torch.isfinite(rnd_full).all()
@@ -76,3 +82,23 @@ def test_full_size_rollout_is_tied_to_the_oracle(name, device):
     er = ((rv.cpu() - ro).abs() / ro.abs().clamp(min=1.0)).reshape(-1)
     assert (ex <= tol).float().mean().item() >= need, f"x_T: worst {ex.max().item():.2e}"
     assert (er <= tol).float().mean().item() >= need, f"rnd: worst {er.max().item():.2e}"
+
+
+def _full_size_eubo(built, case, x0, seed, off, device):
+    """The noising rollout (compute_eubo) at full size: shard independence, production == validation mode on the
+    generator's normals (two draws per step: the increment enters the update and the cost), oracle parity of the slice."""
+    from sde_sampler_lrds_b200 import _native as N
+    p, B = case["problem"], case["B"]
+    d, K = x0.shape[1], len(p["ts"]) - 1
+    rnd_full = built.compute_eubo(x0.clone(), None, seed=seed, particle_offset=off)
+    assert rnd_full.shape == (B, 1) and torch.isfinite(rnd_full).all()
+    lo = B // 2 + 37
+    rs = built.compute_eubo(x0[lo:lo + N_CHECK].clone(), None, seed=seed, particle_offset=off + lo)
+    assert torch.equal(rs, rnd_full[lo:lo + N_CHECK])
+    noise = torch.empty(K, N_CHECK, d, device=device)
+    N.check(N.lib().lrds_normals(C.c_uint64(seed), C.c_uint64(off + lo), 0, K, N_CHECK, d, N.ptr(noise), N.stream_ptr(device)))
+    rv = built.compute_eubo(x0[lo:lo + N_CHECK].clone(), noise)
+    assert torch.equal(rv, rs)
+    ro = O.rollout(p, x0[lo:lo + N_CHECK], noise.cpu(), eubo=True)
+    er = ((rv.cpu() - ro).abs() / ro.abs().clamp(min=1.0)).reshape(-1)
+    assert er.max().item() <= 1e-4, f"rnd: worst {er.max().item():.2e}"

@@ -45,12 +45,15 @@ def test_rollout_matches_oracle_and_golden(name, precision, device):
         # (each disagreeing particle = one flipped (datum, step) mask, an O(0.1) jump of a log-weight of size ~500)
         need = 0.98
     if case.get("eubo"):
-        rnd = built.compute_eubo(x0, noise).cpu()
+        rnd_dev = built.compute_eubo(x0, noise)
+        rnd = rnd_dev.cpu()
         ref = O.rollout(case["problem"], x0, noise, eubo=True)
         m = O.eubo_results(rnd)
+        mp = product_eubo_metrics(rnd_dev)
     else:
-        x, rnd, xs = built.simulate(x0, noise, return_traj=True)
-        x, rnd, xs = x.cpu(), rnd.cpu(), xs.cpu()
+        x, rnd_dev, xs = built.simulate(x0, noise, return_traj=True)
+        x, rnd, xs = x.cpu(), rnd_dev.cpu(), xs.cpu()
+        mp = product_metrics(built, rnd_dev, gold)
         xo, ref, xso = O.rollout(case["problem"], x0, noise, compute_ito_int=case.get("compute_ito_int", True),
                                  return_traj=True)
         m = O.compute_results(rnd)
@@ -64,9 +67,33 @@ def test_rollout_matches_oracle_and_golden(name, precision, device):
         f, worst = frac_within(rnd, want)
         assert f >= need, f"{what}: {f:.4f} of particles within 1e-4 (worst {worst:.2e})"
     if need == 1.0:
-        for k, v in gold["metrics"].items():
-            tol = 1e-3 if "log_norm_const" in k else 1e-3 * max(1.0, abs(v))
-            assert abs(m[k] - v) <= tol, (k, m[k], v)
+        # the oracle's estimators AND the product's (estimator kernel, fp64 partials) on the GPU log-weights against the
+        # reference's own numbers: ELBO / EUBO, log Z (backward and forward), LV, and the effective sample sizes
+        for who, got in (("oracle", m), ("product", mp)):
+            for k, v in gold["metrics"].items():
+                tol = 1e-3 if "log_norm_const" in k else 1e-3 * max(1.0, abs(v))
+                assert abs(got[k] - v) <= tol, (who, k, got[k], v)
+
+
+def product_metrics(built, rnd_dev, gold):
+    """BaseOCLoss.compute_results of the product on the device log-weights; also holds its importance weights to
+    softmax(-rnd) of the reference's log-weights (losses/oc.py:155-158)."""
+    res = type(built.loss).compute_results(rnd_dev, compute_weights=True)
+    w = res.weights.double().cpu()
+    want = torch.softmax(-gold["rnd"].double(), dim=0)
+    assert w.shape == want.shape and abs(w.sum().item() - 1.0) < 1e-5
+    # a weight is exp of a log-weight difference: 1e-4 relative on log-weights of size ~1e2 is ~1e-2 on a weight
+    big = want > 1e-6
+    assert ((w[big] - want[big]).abs() <= 2e-2 * want[big] + 1e-9).all(), ((w - want).abs() / want.clamp(min=1e-12))[big].max().item()
+    return {**res.metrics, **res.log_norm_const_preds}
+
+
+def product_eubo_metrics(rnd_dev):
+    """The forward estimators the product's evaluate_eubo reports (additions/hacking.py) from the estimator kernel."""
+    from sde_sampler_lrds_b200.estimators import estimator_partials, metrics_from_partials
+    m = metrics_from_partials(estimator_partials(rnd_dev))
+    return {"eval/log_norm_const_is_f": m["log_norm_const_is_f"], "eval/eubo": m["eubo"],
+            "eval/effective_sample_size_f": m["effective_sample_size"]}
 
 
 @pytest.mark.parametrize("precision", list(FAST_MODES))
