@@ -239,27 +239,29 @@ struct MixTc : TcMlp<PREC> {
   // of four and therefore have slack - polls the counter, issues the batch `f` from warp-uniform registers and
   // commits it to the tile's mbarrier.  A partial last tile (whose warps all sit on the loaded sub-partitions) has
   // issue_mask = 0: its batches are issued by the CTA's auxiliary warp (mix_aux_issuer).
+  // `done` = the mbarrier the batch commits to (default: the tile's; a batch that completes while the tile already
+  // works on the next one needs its own, or the tile's barrier would run two phases ahead of a waiter)
   template <class F>
-  __device__ __forceinline__ void arrive_issue(F&& f) {
+  __device__ __forceinline__ void arrive_issue(F&& f, uint64_t* done = nullptr) {
     ptx::tmem_wait_st();
     ptx::tc_fence_before();
     __syncwarp();
     if ((threadIdx.x & 31) == 0) ptx::red_add_release(cnt, 1u);
     const bool mine = (issue_mask >> (hand & 1u)) & 1u;
     ++hand;
-    if (mine) issue_when_ready(f);
+    if (mine) issue_when_ready(f, done);
     else target += tile_warps;
   }
   // polls the tile's counter until every warp has arrived for the next hand-off, then issues and commits its batch
   template <class F>
-  __device__ __forceinline__ void issue_when_ready(F&& f) {
+  __device__ __forceinline__ void issue_when_ready(F&& f, uint64_t* done = nullptr) {
     target += tile_warps;
     while ((int32_t)(ptx::ld_acquire(cnt) - target) < 0) {
     }
     ptx::tc_fence_after();
     if (ptx::elect_one()) {
       f();
-      ptx::mma_commit(this->bar);
+      ptx::mma_commit(done ? done : this->bar);
     }
     __syncwarp();
   }
@@ -284,9 +286,9 @@ struct MixTc : TcMlp<PREC> {
     }
   }
   // logits of mixture `which` (0 target, 1 reference): accumulator columns [16 which, 16 which + 16) <- x . wc^T
-  __device__ __forceinline__ void logit(int which, uint32_t img) const {
+  __device__ __forceinline__ void logit(int which, uint32_t img, int col = -1) const {
     const uint32_t idesc = ptx::make_idesc_f16(128, MIX_MAX_M);
-    const uint32_t dcol = this->tm_tile + this->d_col() + (uint32_t)which * MIX_MAX_M;
+    const uint32_t dcol = this->tm_tile + (col < 0 ? this->d_col() : (uint32_t)col) + (uint32_t)which * MIX_MAX_M;
     const int ksteps = this->L.Kin / 16;
     uint32_t acc = 0;
 #pragma unroll
@@ -303,13 +305,13 @@ struct MixTc : TcMlp<PREC> {
   }
   // chunk c of the contractions -> columns [32, 64) of the tile; images = shared-window addresses of the (hi | lo) blocks
   template <bool TGT, bool REF>
-  __device__ __forceinline__ void chunk(int c, uint32_t tgt_img, uint32_t ref_img) const {
+  __device__ __forceinline__ void chunk(int c, uint32_t tgt_img, uint32_t ref_img, uint32_t col = kDCol, uint32_t rcol = kRCol) const {
     const uint32_t idesc = ptx::make_idesc_f16(128, 16);
 #pragma unroll
     for (int which = TGT ? 0 : 1; which < (REF ? 2 : 1); ++which) {
       const uint32_t img = (which ? ref_img : tgt_img) + (uint32_t)c * 256u;  // 16 rows of 16 bytes per chunk
-      const uint32_t dcol = this->tm_tile + kDCol + which * 16;
-      const uint32_t a_hi = this->tm_tile + kRCol + which * 16, a_lo = a_hi + 8;
+      const uint32_t dcol = this->tm_tile + col + which * 16;
+      const uint32_t a_hi = this->tm_tile + rcol + which * 16, a_lo = a_hi + 8;
       const uint64_t b_hi = ptx::make_smem_desc(img, lbo, 128u), b_lo = ptx::make_smem_desc(img + part_bytes, lbo, 128u);
       ptx::mma_bf16_ts(dcol, a_lo, b_hi, idesc, 0);
       ptx::mma_bf16_ts(dcol, a_hi, b_lo, idesc, 1);
@@ -331,8 +333,8 @@ struct MixTc : TcMlp<PREC> {
     }
   }
   // A operand `which` (0 target, 1 reference) of the contraction <- packed responsibilities
-  __device__ __forceinline__ void store_r(int which, const uint32_t (&p)[16]) {
-    ptx::tmem_st16(this->tm_lane + kRCol + which * 16, p);
+  __device__ __forceinline__ void store_r(int which, const uint32_t (&p)[16], uint32_t rcol = kRCol) {
+    ptx::tmem_st16(this->tm_lane + rcol + which * 16, p);
   }
   __device__ __forceinline__ void load_chunk(uint32_t (&m)[32]) {
     ptx::tmem_ld32(this->tm_lane + kDCol, m);

@@ -312,6 +312,41 @@ struct TcMlp {
     }
   }
 
+  // the same for 16 accumulator columns [c0, c0 + 16) (four threads per particle, lrds_rollout_mix_small.cuh)
+  template <bool GLOBAL_BIAS>
+  __device__ __forceinline__ void epilogue_f16_16(const float* __restrict__ bias, int layer, int c0) {
+    const u64 us2 = f2::pk(unscale(layer));
+    uint32_t r[16];
+    ptx::tmem_ld16(tm_lane + d_col() + c0, r);
+    ptx::tmem_wait_ld();
+    const float4* b4 = reinterpret_cast<const float4*>(bias + c0);
+    uint32_t ph[8], pl[8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float4 b = GLOBAL_BIAS ? __ldg(b4 + i) : b4[i];
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const u64 acc = f2::pack(__uint_as_float(r[4 * i + 2 * e]), __uint_as_float(r[4 * i + 2 * e + 1]));
+        const u64 v = f2::fma(acc, us2, e ? f2::pack(b.z, b.w) : f2::pack(b.x, b.y));
+        {
+          float va, vb;
+          f2::unpack(v, va, vb);
+          vmax = max3(vmax, va, vb);
+        }
+        const u64 g = gelu_pair(v, 5.0f, TC_ACT_SCALE);
+        u64 hi, lo;
+        f2::split(g, hi, lo);
+        float h0, h1, l0, l1;
+        f2::unpack(hi, h0, h1);
+        f2::unpack(lo, l0, l1);
+        ph[2 * i + e] = ptx::pack_f16x2(h0, h1);
+        pl[2 * i + e] = ptx::pack_f16x2(l0, l1);
+      }
+    }
+    ptx::tmem_st8(tm_lane + a_col(0) + c0 / 2, ph);
+    ptx::tmem_st8(tm_lane + a_col(1) + c0 / 2, pl);
+  }
+
   // accumulator (64 columns) [* un-scale] + bias -> GELU -> A operand of the next layer
   template <bool GLOBAL_BIAS>
   __device__ __forceinline__ void epilogue(const float* __restrict__ bias, int layer) {

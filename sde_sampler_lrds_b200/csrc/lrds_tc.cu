@@ -2,11 +2,13 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <cstdlib>
 
 #include "lrds_internal.h"
 #include "lrds_rollout_cmcd_tc.cuh"
 #include "lrds_rollout_lin.cuh"
 #include "lrds_rollout_mix.cuh"
+#include "lrds_rollout_mix_small.cuh"
 
 namespace lrds {
 
@@ -18,6 +20,7 @@ extern template int launch_prec<LRDS_PRECISION_TF32>(const RolloutArgs&, const T
 extern template int launch_prec<LRDS_PRECISION_F16X3>(const RolloutArgs&, const TcPlan&, cudaStream_t, char*, size_t);
 
 int launch_mix_f16x3(const RolloutArgs& a, const TcPlan& p, cudaStream_t st, char* err, size_t n);      // lrds_tc_f16x3.cu
+int launch_mix_small_f16x3(const RolloutArgs& a, const TcPlan& p, cudaStream_t st, char* err, size_t n);  // lrds_tc_mix_s.cu
 int launch_cmcd_tc_f16x3(const RolloutArgs& a, const TcPlan& p, cudaStream_t st, char* err, size_t n);  // lrds_tc_f16x3.cu
 int launch_lin_f16x3(const RolloutArgs& a, const TcPlan& p, cudaStream_t st, char* err, size_t n);      // lrds_tc_f16x3.cu
 
@@ -33,6 +36,10 @@ int launch_rollout_tc(const RolloutArgs& a, cudaStream_t st, char* err, size_t n
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   TcPlan p{};
   const char* why = "";
+  // latency-bound batches (LRDS_MIX_SMALL=0: tests and A/B timings run them through the throughput kernel)
+  const char* small_env = getenv("LRDS_MIX_SMALL");
+  if (!(small_env && small_env[0] == '0') && plan_rollout_mix_small(s, cap, sms, &p))
+    return launch_mix_small_f16x3(a, p, st, err, n);
   if (plan_rollout_mix(s, cap, sms, &p)) return launch_mix_f16x3(a, p, st, err, n);
   if (plan_rollout_cmcd_tc(s, cap, &p)) return launch_cmcd_tc_f16x3(a, p, st, err, n);
   if (plan_rollout_lin(s, cap, sms, &p)) return launch_lin_f16x3(a, p, st, err, n);

@@ -48,6 +48,36 @@ def test_mixture_kernel_shapes(M, d, B, K, device):
     _check(dict(case, eubo=True, seed=900 + M), device)
 
 
+@pytest.mark.parametrize("M,d,B,K", [(16, 50, 200, 12), (5, 17, 33, 4), (16, 64, 130, 3), (3, 3, 1, 1), (10, 24, 257, 6)])
+def test_small_batch_and_throughput_kernels_agree(M, d, B, K, device, monkeypatch):
+    """The benchmark configuration has two kernels: four threads per particle for latency-bound batches
+    (lrds_rollout_mix_small.cuh) and one thread per particle for throughput (lrds_rollout_mix.cuh; LRDS_MIX_SMALL=0
+    forces it).  Both against the oracle, and against each other: identical states, log-weights to fp32 rounding, in
+    validation and in production mode."""
+    from tests.product_builders import Built
+    case = T.case_ei_many_modes(K=K, B=B, d=d, M=M)
+    case["problem"]["ts"] = T.uniform_ts(1.0, 100)[:K + 1].clone()
+    x0, noise = initial_state(case), noise_for(case)
+    out = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("LRDS_MIX_SMALL", mode)
+        _check(case, device)
+        built = Built(case, device, "f16x3")
+        out[mode] = [t.cpu() for t in built.simulate(x0, noise, return_traj=True)] + [t.cpu() for t in built.simulate(x0, None, seed=77)[:2]]
+    for i in (0, 2, 3):  # x_T, trajectory (validation mode), x_T (production mode)
+        assert torch.equal(out["1"][i], out["0"][i])
+    for i in (1, 4):     # log-weights
+        assert ((out["1"][i] - out["0"][i]).abs() <= 2e-6 * out["0"][i].abs().clamp(min=1.0)).all()
+
+
+def test_close_modes_through_both_kernels(device, monkeypatch):
+    """The near-tie stress case (logit GEMM hands particles over to the exact quadratic forms) through both kernels."""
+    case = T.case_ei_close_modes()
+    for mode in ("1", "0"):
+        monkeypatch.setenv("LRDS_MIX_SMALL", mode)
+        _check(case, device, need=1.0)
+
+
 @pytest.mark.parametrize("ctrl_kind", ["score", "cancel", "lerp"])
 @pytest.mark.parametrize("M,d,B,K,ito", [(2, 3, 1, 1, True), (5, 17, 33, 4, False), (16, 50, 130, 3, True), (9, 64, 200, 2, True)])
 def test_dis_mixture_kernel_shapes(ctrl_kind, M, d, B, K, ito, device):

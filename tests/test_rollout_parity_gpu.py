@@ -96,6 +96,14 @@ def product_eubo_metrics(rnd_dev):
             "eval/effective_sample_size_f": m["effective_sample_size"]}
 
 
+@pytest.mark.parametrize("name", ["ei_many_modes", "ei_close_modes"])
+def test_throughput_kernel_on_the_benchmark_cases(name, device, monkeypatch):
+    """The parity cases of the benchmark configuration are small batches and run the small-batch kernel above; the same
+    through the throughput kernel (the one bench.py times), against oracle and golden."""
+    monkeypatch.setenv("LRDS_MIX_SMALL", "0")
+    test_rollout_matches_oracle_and_golden(name, "f16x3", device)
+
+
 @pytest.mark.parametrize("precision", list(FAST_MODES))
 @pytest.mark.parametrize("name", list(CASES))
 def test_fast_modes_within_their_stated_tolerance(name, precision, device):

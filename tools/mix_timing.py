@@ -26,7 +26,13 @@ for i in range(3):
     built.simulate(x0, None, seed=i)
 torch.cuda.synchronize()
 buf = (C.c_ulonglong * 512)()
-assert N.lib().lrds_debug_mix_timing(buf) == 0
+SMALL = B <= 128 * 148 and os.environ.get("LRDS_MIX_SMALL", "1") != "0"
+if SMALL:
+    NAMES = ["sync+full", "store_x", "arr LOGIT", "wait LOGIT", "softmax", "arr G_in", "exact Q", "wait GEMMs", "epilogues",
+             "wait out", "R+arr chunks", "wait chunks", "chunk math+tail", "-"]
+    assert N.lib().lrds_debug_mix_small_timing(buf) == 0
+else:
+    assert N.lib().lrds_debug_mix_timing(buf) == 0
 for cta in range(2):
     print(f"CTA {'0' if cta == 0 else 'mid'}: cycles per grid step")
     print("warp " + " ".join(f"{n:>10s}" for n in NAMES) + "      total")

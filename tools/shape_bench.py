@@ -63,6 +63,10 @@ def dis(target, ctrl_kind, B, K=200):
 SHAPES = {
     "cfg1 two_modes d=2 EM K=100 B=2048": lambda: dict(T.case_em_two_modes("score"), B=2048),
     "cfg2 many_modes d=50 M=16 EI K=200 B=65536": lambda: T.case_ei_many_modes(K=200, B=65536),
+    # the reference's real operating points: evaluation batch 8192, training batches 512 .. 2048
+    "small cfg2 many_modes d=50 M=16 EI K=200 B=8192": lambda: T.case_ei_many_modes(K=200, B=8192),
+    "small cfg2 many_modes d=50 M=16 EI K=200 B=2048": lambda: T.case_ei_many_modes(K=200, B=2048),
+    "small cfg2 many_modes d=50 M=16 EI K=200 B=512": lambda: T.case_ei_many_modes(K=200, B=512),
     "cfg3 phi4 d=100 PIS K=256 B=131072": lambda: T.case_pis_phi4(K=256, B=131072),
     "cfg3 phi4 d=100 DDS K=256 B=131072": dds256,
     "cfg4 logreg sonar d=61 CMCD K=100 B=262144": lambda: T.case_cmcd_logreg(166, 60, K=100, B=262144),
