@@ -396,6 +396,10 @@ def other_workloads(dev, precision, flush):
             K = len(p["ts"]) - 1
             gen = torch.Generator().manual_seed(1)
             x0 = (torch.zeros(Bw, d) if case["prior"][0] == "delta" else torch.randn(Bw, d, generator=gen)).to(dev)
+            if case.get("eubo") and p["target"]["kind"] == "gmm":  # compute_eubo starts at TARGET samples (hacking.py:14-19)
+                t = p["target"]
+                idx = torch.multinomial(t["weights"] / t["weights"].sum(), Bw, replacement=True, generator=gen)
+                x0 = (t["loc"][idx] + t["scale"][idx] * torch.randn(Bw, d, generator=gen)).to(dev)
             built = Built(case, dev, precision)
             run = (lambda seed: built.compute_eubo(x0.clone(), None, seed=seed)) if case.get("eubo") else \
                 (lambda seed: built.simulate(x0, None, seed=seed))

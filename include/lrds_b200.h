@@ -144,7 +144,7 @@ typedef struct {
                               * bytes whose first float is the un-scale.  Behind it the LOGIT image of the block: the
                               * responsibilities r = softmax_m(logc_m - q_m / 2) of a mixture whose modes share their
                               * variances need only  logit_m = c_m + x . wc_m  (the x^2 term is mode-independent), with
-                              * wc_mj = mu_mj/var_mj - mean_m(mu_mj/var_mj),  c_m = logc_m - sum_j mu_mj^2/var_mj / 2:
+                              * wc_mj = mu_mj/var_mj - mean_m(mu_mj/var_mj),  c_m = logc_m - sum_j mu_mj^2/var_mj / 2 - max over the modes:
                               * wc as a power-of-two scaled fp16 hi | lo matrix [j/8][m][j%8] (rows m padded to a multiple
                               * of 16, K = j padded to a multiple of 16), then c_m (fp32, -inf for padded modes), then four
                               * floats {un-scale, max_m |wc_m|_2, max_m |c_m|, 1.0 if the variances are shared else 0.0}.

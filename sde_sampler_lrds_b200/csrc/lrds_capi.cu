@@ -208,7 +208,8 @@ __global__ void __launch_bounds__(256) pack_gmm_mix_kernel(const lrds_gmm g, int
   __shared__ float red[8];
   __shared__ double redd[8];
   __shared__ float wbar[LRDS_MAX_DIM_PAD];
-  __shared__ float cm[64], wn[64];
+  __shared__ double cm[64];
+  __shared__ float wn[64];
   const int Mp = (g.M + 15) / 16 * 16, N2 = 2 * d_pad;
   const uint32_t part_bytes = (uint32_t)(Mp / 8) * (uint32_t)N2 * 16u;
   const float* mu = g.mu + (int64_t)blockIdx.x * g.step_stride_param;
@@ -274,18 +275,20 @@ __global__ void __launch_bounds__(256) pack_gmm_mix_kernel(const lrds_gmm g, int
       w2 += __shfl_xor_sync(0xffffffffu, w2, off);
     }
     if ((threadIdx.x & 31) == 0) {
-      cm[m] = m < g.M ? (float)((double)logc[m] - 0.5 * q) : -INFINITY;
+      cm[m] = m < g.M ? (double)logc[m] - 0.5 * q : -INFINITY;
       wn[m] = (float)sqrt(w2);
     }
   }
   __syncthreads();
   float* cdst = reinterpret_cast<float*>(ol + 2 * lpart);
-  for (int m = threadIdx.x; m < Mp; m += blockDim.x) cdst[m] = cm[m];
+  double ctop = -INFINITY;  // softmax-invariant shift: c_m - max_m c_m (the error bound scales with max |c_m|)
+  for (int m = 0; m < g.M; ++m) ctop = fmax(ctop, cm[m]);
+  for (int m = threadIdx.x; m < Mp; m += blockDim.x) cdst[m] = (float)(cm[m] - ctop);
   if (threadIdx.x == 0) {
     float wnmax = 0.f, cmax = 0.f;
     for (int m = 0; m < g.M; ++m) {
       wnmax = fmaxf(wnmax, wn[m]);
-      if (isfinite(cm[m])) cmax = fmaxf(cmax, fabsf(cm[m]));
+      if (isfinite(cm[m])) cmax = fmaxf(cmax, fabsf((float)(cm[m] - ctop)));
     }
     float* t2 = cdst + Mp;
     t2[0] = ldexpf(1.0f, -kl);

@@ -28,7 +28,7 @@
 // q_m is mode-independent, so logit_m = c_m + x . wc_m up to a common shift: one more [128 x K] . [K x 16] GEMM per
 // mixture on the x operand the network's first GEMM needs anyway.  Its rounding error grows with |x| |wc| (fp32
 // accumulation of large terms), which only matters when two modes are close to a tie; so every particle checks the
-// bound  kappa (|x|_2 max_m |wc_m|_2 + max_m |c_m|) min(1, 4 (1 - r_max)) <= tau  and a warp with one particle over it
+// bound  (kappa |x|_2 max_m |wc_m|_2 + kappa_c max_m |c_m|) min(1, 4 (1 - r_max)) <= tau  and a warp with one particle over it
 // (or a mixture with per-mode variances) evaluates the exact quadratic forms on the SIMT pipes instead
 // (gmm_pass1_pair), behind the first two GEMMs of the network.
 #pragma once
@@ -39,7 +39,8 @@ namespace lrds {
 constexpr int MIX_MAX_M = 16;
 constexpr int MIX_MAX_WARPS = 16;   // 3.5 tiles = 14 warps: one wave for 65536 particles on 148 SMs (128 registers)
 constexpr int MIX_TAIL_BYTES = 32;  // the kernel's hand-off counters: tile[4] | step buffer[2]
-constexpr float MIX_LOGIT_KAPPA = 9.5367431640625e-07f;  // 2^-20: error of a 3-pass fp16 logit per unit of |x| |wc| + |c| (tests/test_mix_logit_gpu.py)
+constexpr float MIX_LOGIT_KAPPA = 9.5367431640625e-07f;  // 2^-20: error of a 3-pass fp16 dot product per unit of |x|_2 |wc|_2 (emulated worst case 2^-21.4)
+constexpr float MIX_LOGIT_KAPPA_C = 2.384185791015625e-07f;  // 2^-22: c_m enters by one fp32 rounding of itself and one of the sum
 constexpr float MIX_LOGIT_TAU = 2e-5f;                   // accepted logit error where modes tie (= the exact forms' own fp32 error at q ~ 50)
 
 // Compile-time configuration of the kernel: which of the two score contractions run on the tensor core, and the update.
@@ -369,7 +370,7 @@ struct MixTc : TcMlp<PREC> {
     for (int i = 0; i < MIX_MAX_M; ++i) r[i] *= inv;
     pack_r(r, p);
     // 1 - r_max = (s - 1) / s (the largest term of s is exactly 1)
-    const float eps = MIX_LOGIT_KAPPA * fmaf(xnorm, t2.y, t2.z);
+    const float eps = fmaf(MIX_LOGIT_KAPPA * xnorm, t2.y, MIX_LOGIT_KAPPA_C * t2.z);
     const float amb = fminf(1.0f, 4.0f * (s - 1.0f) * inv);
     return eps * amb <= MIX_LOGIT_TAU && xnorm < 3.0e4f;  // (false for NaN; beyond 3e4 the fp16 operands saturate)
   }

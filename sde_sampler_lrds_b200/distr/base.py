@@ -59,7 +59,7 @@ def _pow2_scale(amax: torch.Tensor) -> torch.Tensor:
 def gmm_logit_tc_image(loc: torch.Tensor, logc: torch.Tensor, ivar: torch.Tensor, d_pad: int) -> torch.Tensor:
     """The logit part of a lrds_gmm.mix_tc block (include/lrds_b200.h): wc = mu / var - mean over the modes as a
     power-of-two scaled fp16 hi | lo matrix [j/8][m][j%8] (modes padded to a multiple of 16, dims to a multiple of 16),
-    then c_m = logc_m - sum_j mu^2 / var / 2 (fp32, -inf for the padded modes), then four floats
+    then c_m = logc_m - sum_j mu^2 / var / 2 minus its maximum over the modes (fp32, -inf for the padded modes), then four floats
     {un-scale, max_m |wc_m|_2, max_m |c_m|, variances shared ? 1 : 0}.  ``ivar`` = the fp32 1/var the kernels see."""
     lead = loc.shape[:-2]
     M, d = loc.shape[-2:]
@@ -67,7 +67,8 @@ def gmm_logit_tc_image(loc: torch.Tensor, logc: torch.Tensor, ivar: torch.Tensor
     iv = ivar.double()
     w = loc.double() * iv
     wc = (w - w.mean(dim=-2, keepdim=True).float().double()).float()   # the mean is held in fp32, as the device packer does
-    c = (logc.double() - 0.5 * (loc.double() ** 2 * iv).sum(dim=-1)).float()
+    c = logc.double() - 0.5 * (loc.double() ** 2 * iv).sum(dim=-1)
+    c = (c - c.max(dim=-1, keepdim=True).values).float()  # softmax-invariant shift: the error bound scales with max |c_m|
     F = torch.nn.functional
     V = F.pad(wc, (0, Kin - d, 0, Mp - M))                             # [.., m, j]
     scale = _pow2_scale(V.abs().flatten(-2).max(dim=-1).values.double())

@@ -88,6 +88,7 @@ def test_mixture_tensor_core_image_layout():
         assert Wc[M:].abs().max() == 0 and Wc[:, d:].abs().max() == 0
         cm = L[2 * lpart:2 * lpart + 4 * Mp].view(torch.float32)
         want_c = logc[s].double() - 0.5 * (loc[s].double() ** 2 / var[s].double()).sum(-1)
+        want_c = want_c - want_c.max()  # shifted by its maximum (softmax-invariant)
         assert (cm[:M].double() - want_c).abs().max() <= 1e-6 * want_c.abs().max() and torch.isinf(cm[M:]).all()
         assert abs(tail[1].item() - want_w.pow(2).sum(-1).sqrt().max().item()) <= 1e-5 * tail[1].item()
         assert abs(tail[2].item() - want_c.abs().max().item()) <= 1e-5 * tail[2].item()

@@ -22,11 +22,15 @@ case = T.case_ei_many_modes(K=K, B=B)
 dev = torch.device("cuda:0")
 x0 = torch.randn(B, 50, generator=torch.Generator().manual_seed(1)).to(dev)
 built = Built(case, dev, "f16x3")
+EUBO = os.environ.get("EUBO", "0") == "1"
 for i in range(3):
-    built.simulate(x0, None, seed=i)
+    if EUBO:
+        built.compute_eubo(x0.clone(), None, seed=i)
+    else:
+        built.simulate(x0, None, seed=i)
 torch.cuda.synchronize()
 buf = (C.c_ulonglong * 512)()
-SMALL = B <= 128 * 148 and os.environ.get("LRDS_MIX_SMALL", "1") != "0"
+SMALL = B <= 128 * 148 and os.environ.get("LRDS_MIX_SMALL", "1") != "0" and not EUBO
 if SMALL:
     NAMES = ["sync+full", "store_x", "arr LOGIT", "wait LOGIT", "softmax", "arr G_in", "exact Q", "wait GEMMs", "epilogues",
              "wait out", "R+arr chunks", "wait chunks", "chunk math+tail", "-"]

@@ -104,6 +104,10 @@ def main():
         K = len(p["ts"]) - 1
         g = torch.Generator().manual_seed(1)
         x0 = (torch.zeros(B, d) if case["prior"][0] == "delta" else torch.randn(B, d, generator=g)).to(dev)
+        if case.get("eubo") and p["target"]["kind"] == "gmm":  # compute_eubo starts at TARGET samples (hacking.py:14-19)
+            t = p["target"]
+            idx = torch.multinomial(t["weights"] / t["weights"].sum(), B, replacement=True, generator=g)
+            x0 = (t["loc"][idx] + t["scale"][idx] * torch.randn(B, d, generator=g)).to(dev)
         for prec in args.precisions.split(","):
             row = {"shape": name, "precision": prec, "B": B, "K": K, "d": d}
             try:
