@@ -200,16 +200,16 @@ __device__ __forceinline__ float gmm_logp_any(const GmmView& g, int d, int dp, c
 #ifdef LRDS_MIX_TIMING
 static __device__ unsigned long long g_mix_timing[2 * 16 * 16];
 struct MixTm {
-  unsigned long long* w;
+  unsigned long long* w = nullptr;  // (kernels that do not collect timings leave it unset)
   long long t;
   __device__ __forceinline__ void start() { t = clock64(); }
   __device__ __forceinline__ void mark(int i) {
     const long long n = clock64();
-    if ((threadIdx.x & 31) == 0) w[i] += (unsigned long long)(n - t);
+    if (w != nullptr && (threadIdx.x & 31) == 0) w[i] += (unsigned long long)(n - t);
     t = n;
   }
   __device__ __forceinline__ void count(int i, bool hit) {  // warp-steps that evaluated the exact quadratic forms
-    if ((threadIdx.x & 31) == 0 && hit) w[i] += 1ull;
+    if (w != nullptr && (threadIdx.x & 31) == 0 && hit) w[i] += 1ull;
   }
 };
 #else

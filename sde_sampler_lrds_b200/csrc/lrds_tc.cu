@@ -7,6 +7,7 @@
 #include "lrds_internal.h"
 #include "lrds_rollout_cmcd_tc.cuh"
 #include "lrds_rollout_lin.cuh"
+#include "lrds_rollout_cmcd_mix.cuh"
 #include "lrds_rollout_mix.cuh"
 #include "lrds_rollout_mix_small.cuh"
 
@@ -21,6 +22,7 @@ extern template int launch_prec<LRDS_PRECISION_F16X3>(const RolloutArgs&, const 
 
 int launch_mix_f16x3(const RolloutArgs& a, const TcPlan& p, cudaStream_t st, char* err, size_t n);      // lrds_tc_f16x3.cu
 int launch_mix_small_f16x3(const RolloutArgs& a, const TcPlan& p, cudaStream_t st, char* err, size_t n);  // lrds_tc_mix_s.cu
+int launch_cmcd_mix_f16x3(const RolloutArgs& a, const TcPlan& p, cudaStream_t st, char* err, size_t n);   // lrds_tc_mix_s.cu
 int launch_cmcd_tc_f16x3(const RolloutArgs& a, const TcPlan& p, cudaStream_t st, char* err, size_t n);  // lrds_tc_f16x3.cu
 int launch_lin_f16x3(const RolloutArgs& a, const TcPlan& p, cudaStream_t st, char* err, size_t n);      // lrds_tc_f16x3.cu
 
@@ -42,6 +44,7 @@ int launch_rollout_tc(const RolloutArgs& a, cudaStream_t st, char* err, size_t n
     return launch_mix_small_f16x3(a, p, st, err, n);
   if (plan_rollout_mix(s, cap, sms, &p)) return launch_mix_f16x3(a, p, st, err, n);
   if (plan_rollout_cmcd_tc(s, cap, &p)) return launch_cmcd_tc_f16x3(a, p, st, err, n);
+  if (plan_rollout_cmcd_mix(s, cap, sms, &p)) return launch_cmcd_mix_f16x3(a, p, st, err, n);
   if (plan_rollout_lin(s, cap, sms, &p)) return launch_lin_f16x3(a, p, st, err, n);
   if (int r = plan_rollout_tc(s, cap, sms, &p, &why)) {
     snprintf(err, n, "tensor-core rollout does not fit (d=%d, precision %d): %s", s.d, s.precision, why);

@@ -420,6 +420,19 @@ def case_cmcd_gmm():
         "B": 140, "seed": 108, "prior": ("gauss",)}
 
 
+def case_cmcd_many_modes(ctrl_kind="score"):
+    """CMCD over a ManyModes target with the target-informed drift model (experiments/sample_many_modes_competing.py:100-115;
+    isotropic Gaussian prior, conf/solver/cmcd.yaml): the CMCD mixture kernel (lrds_rollout_cmcd_mix.cuh), odd number of
+    8-dim chunks, a batch that does not fill its last tile."""
+    d, M = 20, 6
+    return {
+        "problem": {"method": "cmcd", "sde": None, "diff": 1.0, "T": 1.0, "clip_score": 1e5,
+                    "ts": uniform_ts(1.0, 40), "target": many_modes(M, d, var=0.5),
+                    "ctrl": ctrl(d, ctrl_kind, seed=41, out_gain=0.5, gamma=0.02),
+                    "prior": {"loc": torch.zeros(d), "scale": 5.0 * torch.ones(d), "isotropic": True}},
+        "B": 170, "seed": 141, "prior": ("iso", 0.0, 5.0)}
+
+
 def _lv_traj(case, traj_per_sample=2):
     """method='lv_traj': every initial value is repeated traj_per_sample times (losses/oc.py:383-384) and the loss is the
     mean over the samples of the variance over their trajectories (118-124).  ``noise_for`` draws for B * traj particles."""
@@ -458,6 +471,7 @@ CASES = {
     "cmcd_logreg_sonar": lambda: case_cmcd_logreg(166, 60),
     "cmcd_logreg_iono": lambda: case_cmcd_logreg(280, 33, ctrl_kind="clipped"),
     "cmcd_gmm": case_cmcd_gmm,
+    "cmcd_many_modes_score": case_cmcd_many_modes,
     "pis_logreg": lambda: case_pis_logreg(),
     "dds_logreg": lambda: case_dds_logreg(),
     "dis_many_modes_ito": lambda: case_dis("many_modes", True),
