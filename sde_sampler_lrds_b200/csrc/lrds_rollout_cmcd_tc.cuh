@@ -114,11 +114,6 @@ struct CmcdTc : TcMlp<LRDS_PRECISION_F16X3> {
   const uint8_t* ximg;   // the same, generic
   float usx;             // its un-scale
 
-  __device__ __forceinline__ void sync_issue() {
-    ptx::tmem_wait_st();
-    ptx::tc_fence_before();
-    ptx::bar_sync(bar_id, bar_threads);
-  }
   // D[dcol] (+)= A (hi at a_hi, lo at a_lo; 8 packed columns per K step) . B (hi image at b, lo at b + part), 3 passes
   __device__ __forceinline__ void mma_x3(uint32_t dcol, uint32_t a_hi, uint32_t a_lo, uint32_t a_step, uint32_t b, uint32_t b_part,
                                          uint32_t b_step, uint32_t lbo, uint32_t sbo, int ksteps, uint32_t idesc) {
@@ -151,9 +146,8 @@ struct CmcdTc : TcMlp<LRDS_PRECISION_F16X3> {
       }
       store16_half(c0, v);
     }
-    sync_issue();
-    if (issuer) {
-      ptx::tc_fence_after();
+    const bool mine = handoff();
+    if (mine && ptx::elect_one()) {
       const uint32_t a_hi = tm_tile + a_col(0), a_lo = tm_tile + a_col(1);
       mma_x3(tm_tile + d_col(), a_hi, a_lo, 8u, img_s + L.off_in, L.part_bytes, 2u * (uint32_t)C * 16u, (uint32_t)C * 16u, 128u,
              L.Kin / 16, ptx::make_idesc_f16(128, C));
@@ -166,17 +160,18 @@ struct CmcdTc : TcMlp<LRDS_PRECISION_F16X3> {
       }
       ptx::mma_commit(bar);
     }
+    if (mine) __syncwarp();
   }
   // gradient GEMM: A = g (hi | lo per 16 data, in place of the logits), B = the data image read MN-major
   __device__ __forceinline__ void issue_gradient() {
-    sync_issue();
-    if (issuer) {
-      ptx::tc_fence_after();
+    const bool mine = handoff();
+    if (mine && ptx::elect_one()) {
       const uint32_t zc = tm_tile + CL.z_col;
       mma_x3(tm_tile + CL.t_col, zc, zc + 8u, 16u, ximg_s, CL.part_bytes, 256u, 128u, (uint32_t)CL.N16 * 16u, CL.N16 / 16,
              ptx::make_idesc_f16(128, CL.K16) | (1u << 16));
       ptx::mma_commit(bar);
     }
+    if (mine) __syncwarp();
   }
 
   // logits of data [16 t0, 16 t1) -> g = m (y - sigma(z)), m = [eps <= sigma <= 1 - eps] (and >= threshold), as fp16
@@ -286,6 +281,7 @@ rollout_cmcd_tc_kernel(const RolloutArgs a, const uint8_t* __restrict__ image, c
   if (warp == 0) ptx::tmem_alloc(slot, tmem_cols);
   if (tid == 0) {
     for (int i = 0; i < 2; ++i) ptx::mbar_init(bars + i, 1);
+    *reinterpret_cast<uint32_t*>(smem_raw + TL.bytes + 64) = 0u;  // the tile's hand-off counter
     ptx::fence_mbar_init();
   }
   ptx::tc_fence_before();
@@ -308,7 +304,9 @@ rollout_cmcd_tc_kernel(const RolloutArgs a, const uint8_t* __restrict__ image, c
   mlp.phase = 0;
   mlp.bar_id = 1;
   mlp.bar_threads = 2 * NT;
-  mlp.issuer = tid == 0;
+  mlp.issuer = warp == 0;  // (warp-uniform)
+  mlp.hand_cnt = reinterpret_cast<uint32_t*>(smem_raw + TL.bytes + 64);
+  mlp.hand_warps = (uint32_t)(2 * NT / 32);
   mlp.half = half;
   mlp.dp = s.mlp.d_pad;
   mlp.CL = CL;

@@ -39,6 +39,7 @@ rollout_lin_kernel(const RolloutArgs a, const uint8_t* __restrict__ image, const
   if (warp == 0) ptx::tmem_alloc(slot, tmem_cols);
   if (tid == 0) {
     for (int i = 0; i < 5; ++i) ptx::mbar_init(bars + i, 1);
+    for (int i = 0; i < 4; ++i) reinterpret_cast<uint32_t*>(smem_raw + TL.bytes + 64)[i] = 0u;
     ptx::fence_mbar_init();
   }
   ptx::tc_fence_before();
@@ -61,7 +62,9 @@ rollout_lin_kernel(const RolloutArgs a, const uint8_t* __restrict__ image, const
   mlp.phase = 0;
   mlp.bar_id = 1 + tile;
   mlp.bar_threads = 256;  // full tiles only: 4 warps x 2 threads per particle
-  mlp.issuer = half == 0 && (ptid & 127) == 96;
+  mlp.issuer = half == 0 && (pwarp & 3) == 3;  // one warp of the tile (warp-uniform)
+  mlp.hand_cnt = reinterpret_cast<uint32_t*>(smem_raw + TL.bytes + 64) + tile;
+  mlp.hand_warps = 8u;  // 4 warps x 2 threads per particle
   mlp.dp = s.mlp.d_pad;
 
   const int b_raw = blockIdx.x * NT + ptid;

@@ -32,7 +32,7 @@ constexpr int TC_MAX_WARPS = 16;
 __host__ __device__ constexpr int tc_max_warps(int prec) {
   return prec == LRDS_PRECISION_TF32X3 ? 8 : prec == LRDS_PRECISION_F16X3 ? 12 : TC_MAX_WARPS;
 }
-constexpr int TC_TAIL_BYTES = 64;  // mbarriers + TMEM slot after the image
+constexpr int TC_TAIL_BYTES = 96;  // mbarriers (5 x 8 B) + TMEM slot (at 48) + the tiles' hand-off counters (4 x 4 B at 64) after the image
 constexpr float TC_ACT_SCALE = 64.f;  // F16X3: hidden activations enter the tensor core as 64 * GELU(h)
 __host__ __device__ constexpr bool tc_is_x3(int prec) { return prec == LRDS_PRECISION_TF32X3 || prec == LRDS_PRECISION_F16X3; }
 __host__ __device__ constexpr bool tc_is_half(int prec) { return prec == LRDS_PRECISION_BF16 || prec == LRDS_PRECISION_F16X3; }
@@ -152,8 +152,11 @@ struct TcMlp {
   uint32_t tm_lane;    // the same at this warp's first lane (tcgen05.ld / st)
   uint64_t* bar;       // the tile's MMA-completion mbarrier
   uint32_t phase;
-  int bar_id, bar_threads;
-  bool issuer;
+  int bar_id, bar_threads;  // (named barrier of the tile: only the kernels' own barriers use it now)
+  bool issuer;              // this WARP issues the tile's batches (warp-uniform)
+  uint32_t* hand_cnt;       // the tile's hand-off counter: one increment per warp and hand-off
+  uint32_t hand_target = 0; // its value once every warp of the tile has arrived for the current hand-off
+  uint32_t hand_warps;      // warps that take part in a hand-off
   int dp;              // columns of x held by the body (d rounded up to 8, zero padded)
   float vmax = 0.f, xmax = 0.f;  // F16X3: largest hidden pre-activation / |coordinate| this thread has converted to fp16
   __device__ __forceinline__ bool saturated() const { return kF16 && (vmax > F16X3_MAX_PREACT || xmax > F16X3_MAX_COORD); }
@@ -171,14 +174,28 @@ struct TcMlp {
     return reinterpret_cast<const float*>(img + L.off_scale)[8 + layer];
   }
 
-  // every particle thread has stored its A row: make it visible to the tensor core, then one thread issues the
-  // layer's MMAs and commits them to the tile's mbarrier.
-  __device__ __forceinline__ void issue(uint32_t b_off, int K, int N) {
+  // This warp's operand rows are stored / its accumulator rows read: increment the tile's counter (release, no round
+  // trip) and go on; returns true in the tile's issuer warp once every warp of the tile has arrived (it polls the
+  // counter): the caller then issues the batch under elect.sync and commits it to the tile's mbarrier.  Nobody else
+  // blocks here - the warps wait for the batch on the mbarrier when they need its result (the named barrier that
+  // round 1 had in front of every batch cost 6 - 11 % of the warps' time in the two-threads-per-particle kernels).
+  __device__ __forceinline__ bool handoff() {
     ptx::tmem_wait_st();
     ptx::tc_fence_before();
-    ptx::bar_sync(bar_id, bar_threads);
-    if (issuer) {
-      ptx::tc_fence_after();
+    __syncwarp();
+    hand_target += hand_warps;
+    if ((threadIdx.x & 31) == 0) ptx::red_add_release(hand_cnt, 1u);
+    if (!issuer) return false;
+    while ((int32_t)(ptx::ld_acquire(hand_cnt) - hand_target) < 0) {
+    }
+    ptx::tc_fence_after();
+    return true;
+  }
+
+  // one layer's MMAs, issued by the tile's issuer warp and committed to the tile's mbarrier
+  __device__ __forceinline__ void issue(uint32_t b_off, int K, int N) {
+    const bool mine = handoff();
+    if (mine && ptx::elect_one()) {
       const uint32_t idesc = PREC == LRDS_PRECISION_BF16 ? ptx::make_idesc_bf16(128, N)
                              : kF16                      ? ptx::make_idesc_f16(128, N)
                                                          : ptx::make_idesc_tf32(128, N);
@@ -203,6 +220,7 @@ struct TcMlp {
       pass(0, 0);
       ptx::mma_commit(bar);
     }
+    if (mine) __syncwarp();
   }
   __device__ __forceinline__ void wait() {
     ptx::mbar_wait(bar, phase);
@@ -465,6 +483,7 @@ rollout_tc_kernel(const RolloutArgs a, const uint8_t* __restrict__ image, const 
   if (warp == 0) ptx::tmem_alloc(slot, tmem_cols);
   if (tid == 0) {
     for (int i = 0; i < 5; ++i) ptx::mbar_init(bars + i, 1);
+    for (int i = 0; i < 4; ++i) reinterpret_cast<uint32_t*>(smem_raw + TL.bytes + 64)[i] = 0u;
     ptx::fence_mbar_init();
   }
   ptx::tc_fence_before();
@@ -488,7 +507,9 @@ rollout_tc_kernel(const RolloutArgs a, const uint8_t* __restrict__ image, const 
   mlp.phase = 0;
   mlp.bar_id = 1 + tile;
   mlp.bar_threads = tile_warps * 32;
-  mlp.issuer = (tid & 127) == 32 * (tile_warps - 1);  // the tile's last warp: its sub-partition carries the fewest warps
+  mlp.issuer = (warp & 3) == tile_warps - 1;  // the tile's last warp: its sub-partition carries the fewest warps
+  mlp.hand_cnt = reinterpret_cast<uint32_t*>(smem_raw + TL.bytes + 64) + tile;
+  mlp.hand_warps = (uint32_t)tile_warps;
   mlp.dp = a.s.mlp.d_pad;
   rollout_body<KIND, STAGE, TR>(a, cols, stage, mlp);
   ptx::tc_fence_before();
