@@ -3,15 +3,19 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--precision f16x3|tf32x3|fp32|tf32|bf16]
 
-The headline number is measured in the fp32-grade mode f16x3 (drift network AND mixture-score contractions on tcgen05
-tensor cores with the 3-pass fp16 (hi, lo) split of power-of-two scaled operands; parity-tested to the north-star
-tolerance like tf32x3 and the fp32 SIMT anchor).  --fast-mode additionally times the reduced-precision bf16 kernel
-and reports it separately with its tolerance.
+The headline number is measured in the fp32-grade mode f16x3 (drift network, mixture logits AND mixture-score
+contractions on tcgen05 tensor cores with the 3-pass fp16 (hi, lo) split of power-of-two scaled operands; parity-tested to
+the north-star tolerance like tf32x3 and the fp32 SIMT anchor).  --fast-mode additionally times the reduced-precision bf16
+kernel and reports it separately with its tolerance.
 
 A "step" is one complete rollout of the workload's particle batch through all grid times (the quantity the
 reference times as eval/sample_time, solver/oc.py:148-158) followed by the estimator reduction; under
 torchrun every rank integrates its own shard of particles (weak scaling: 65536 per GPU, RNG counter = global
-particle index) and the only exchange is the all_gather of 8 doubles per rank.
+particle index) and the only exchange is the all_gather of 8 doubles per rank, merged on the device.  `value` times the
+step on device-resident inputs; `e2e` times it through sde_sampler_lrds_b200.streaming.HostRolloutStream with pinned HOST
+buffers in and out (the copies of neighbouring steps overlap the kernel); `workloads` times the other BASELINE.json shapes
+on the device in the same run (single-GPU runs); `--impl reference` runs the CPU port of the reference's loop on the same
+config, exactly --warmup + --steps rollouts of a 4096-particle sample.
 
 Workload = BASELINE.json configs[1]: ManyModes d=50 (16 modes), RDS vp-ref (VP beta 0.1..20), diagonal-GMM
 reference, target_informed (ScoreCtrl) drift, EI integrator, 200 steps, batch 65536, synthetic weights.
