@@ -5,6 +5,7 @@
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/bin/tc_probe tools/tc_probe.cu
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include <cmath>
 #include <cstdio>
@@ -155,6 +156,67 @@ __global__ void __launch_bounds__(128) probe_mn_kernel(const float* __restrict__
   if (warp == 0) tmem_dealloc(tmem, TMEM_COLS);
 }
 
+
+// Both operands from shared memory, both MN-major (the weight-gradient GEMM of lrds_ctrl_grad.cuh):
+//   D[m][n] = sum_rows G[row][m] * E[row][n],   rows = the contraction index (128 per call, 16 per MMA)
+// operands stored [groups of 8 features][128 rows][16 bytes]: offset(row, f) = (f / 8) * 2048 + row * 16 + (f % 8) * 2,
+// descriptor start = base + 256 * kstep, LBO = 128 (next 8 rows), SBO = 2048 (next 8 features).  G carries MF <= 128
+// features (the rest of the 128 M rows reads whatever follows), E carries N.
+__global__ void __launch_bounds__(128) probe_ss_kernel(const float* __restrict__ G, const float* __restrict__ E,
+                                                       float* __restrict__ D, int MF, int N, int swap) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  if (warp == 0) tmem_alloc(&tmem_base_s, TMEM_COLS);
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    fence_mbar_init();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+  uint8_t* gs = smem;                 // 16 groups x 2048 (zero where MF ends)
+  uint8_t* es = smem + 16 * 2048;     // N / 8 groups x 2048
+  for (int g = 0; g < 16; ++g) {      // thread = row
+    __half v[8];
+    for (int e = 0; e < 8; ++e) v[e] = __float2half(g * 8 + e < MF ? G[(size_t)tid * MF + g * 8 + e] : 0.f);
+    *reinterpret_cast<uint4*>(gs + g * 2048 + tid * 16) = *reinterpret_cast<const uint4*>(v);
+  }
+  for (int g = 0; g < N / 8; ++g) {
+    __half v[8];
+    for (int e = 0; e < 8; ++e) v[e] = __float2half(E[(size_t)tid * N + g * 8 + e]);
+    *reinterpret_cast<uint4*>(es + g * 2048 + tid * 16) = *reinterpret_cast<const uint4*>(v);
+  }
+  fence_proxy_async();
+  __syncthreads();
+  if (tid == 0) {
+    tc_fence_after();
+    const uint32_t idesc = make_idesc_f16(128, N) | IDESC_A_MN | IDESC_B_MN;
+    const uint32_t lbo = swap ? 2048u : 128u, sbo = swap ? 128u : 2048u;
+    for (int ks = 0; ks < 8; ++ks) {
+      const uint64_t ad = make_smem_desc(smem_u32(gs) + ks * 256u, lbo, sbo);
+      const uint64_t bd = make_smem_desc(smem_u32(es) + ks * 256u, lbo, sbo);
+      mma_f16_ss(tmem + D_COL, ad, bd, idesc, ks > 0);
+    }
+    mma_commit(&bar);
+  }
+  mbar_wait(&bar, 0);
+  tc_fence_after();
+  const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+  for (int c0 = 0; c0 < N; c0 += 8) {
+    uint32_t r[8];
+    tmem_ld8(tmem + lane_base + D_COL + c0, r);
+    tmem_wait_ld();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) D[(size_t)tid * N + c0 + i] = __uint_as_float(r[i]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, TMEM_COLS);
+}
+
 static float round_tf32(float v) {
   uint32_t u;
   memcpy(&u, &v, 4);
@@ -240,8 +302,53 @@ int run_mn_case(int K, int N) {  // image [N][K]; contraction over N
   return worst < 1e-3 ? 0 : 1;
 }
 
+
+static float round_f16(float v) { return __half2float(__float2half(v)); }
+
+int run_ss_case(int MF, int N, int swap) {
+  std::vector<float> G(128 * MF), E(128 * N), D(128 * N, -1.f);
+  srand(MF * 7 + N);
+  for (auto& v : G) v = round_f16((rand() % 2001 - 1000) / 512.f);
+  for (auto& v : E) v = round_f16((rand() % 2001 - 1000) / 1024.f);
+  float *dG, *dE, *dD;
+  cudaMalloc(&dG, G.size() * 4);
+  cudaMalloc(&dE, E.size() * 4);
+  cudaMalloc(&dD, D.size() * 4);
+  cudaMemcpy(dG, G.data(), G.size() * 4, cudaMemcpyHostToDevice);
+  cudaMemcpy(dE, E.data(), E.size() * 4, cudaMemcpyHostToDevice);
+  const size_t smem = 16 * 2048 + (size_t)(N / 8) * 2048;
+  cudaFuncSetAttribute(probe_ss_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  probe_ss_kernel<<<1, 128, smem>>>(dG, dE, dD, MF, N, swap);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) {
+    printf("ss MF=%d N=%d: CUDA error %s\n", MF, N, cudaGetErrorString(e));
+    return 1;
+  }
+  cudaMemcpy(D.data(), dD, D.size() * 4, cudaMemcpyDeviceToHost);
+  double worst = 0;
+  for (int m = 0; m < 128; ++m)
+    for (int n = 0; n < N; ++n) {
+      double ref = 0;
+      if (m < MF)
+        for (int r = 0; r < 128; ++r) ref += (double)G[r * MF + m] * (double)E[r * N + n];
+      worst = fmax(worst, fabs(ref - D[m * N + n]));
+    }
+  printf("f16 SS, A and B MN-major (swap=%d): M feats %3d N %3d: max abs err %.3e  %s\n", swap, MF, N, worst,
+         worst < 1e-3 ? "OK" : "MISMATCH");
+  cudaFree(dG);
+  cudaFree(dE);
+  cudaFree(dD);
+  return worst < 1e-3 ? 0 : 1;
+}
+
 int main() {
-  int bad = 0;
+  int bad_ss = 0;
+  bad_ss += run_ss_case(72, 64, 0);
+  bad_ss += run_ss_case(64, 56, 0);
+  bad_ss += run_ss_case(128, 64, 0);
+  if (bad_ss) run_ss_case(72, 64, 1);
+
+  int bad = bad_ss;
   bad += run_mn_case(64, 176);
   bad += run_mn_case(48, 96);
   bad += run_mn_case(16, 16);
