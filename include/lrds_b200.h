@@ -17,7 +17,7 @@
 extern "C" {
 #endif
 
-#define LRDS_ABI_VERSION 7
+#define LRDS_ABI_VERSION 8
 #define LRDS_CHANNELS 64 /* FourierMLP / TimeEmbed width, conf/model/base/fouriermlp.yaml:4 */
 #define LRDS_MAX_DIM_PAD 1024 /* largest d_pad the operand packers accept */
 
@@ -261,6 +261,29 @@ int lrds_estimator_merge(const double* parts, int32_t n, double* out, void* stre
 /* ---- drop-in pieces of the same arithmetic, for the reference's smaller public interfaces.
  * control u = generative_ctrl(t, x) for the time of table row `row` (models/reparam.py:33-43, 112-117). */
 int lrds_ctrl_forward(const lrds_spec* spec, int32_t row, const float* x, int32_t B, float* u_out, void* stream);
+
+/* Parameter gradient of the drift backbone over S x B stored states: the vector-Jacobian product that autograd takes
+ * through FourierMLP.forward (models/mlp.py:135-143) under the clip of ClippedCtrl (models/reparam.py:33-43) when
+ * loss.backward() runs after BaseOCLoss.compute_loss with method 'lv' / 'lv_traj' (losses/oc.py:105-131; the SDE follows
+ * the detached control there, so the states are constants and the gradient is one batched pass, see train.py).
+ *   x     [S][B][d]  states (e.g. the trajectory lrds_rollout wrote), time row s is shared by the B rows of slice s
+ *   bias1 [S][64]    input_embed.bias + TimeEmbed(t_s)  (the rows of LRDS_STEP_BIAS1)
+ *   cot   [S][B][d]  cotangent of the clipped network output; multiplied by step_w[s] and row_w[b] when given
+ *                    (log-variance loss: cot = z, step_w = the Ito weights, row_w = d loss / d rnd_b)
+ *   clip             bound of the output clip (<= 0: none): rows/columns with |net| > clip receive no gradient
+ *   cot_scale        power of two applied to the cotangents before their fp16 operands are formed and removed from the
+ *                    results: choose it so that max |cot * step_w * row_w| * cot_scale is of order 1 .. 10
+ * Outputs: grads_out = lrds_mlp_grad_floats(d, num_hidden) floats laid out like the weight blocks of lrds_mlp
+ * ([d][64] w_in_t, [nh][64][64] w_hid_t, [nh][64] b_hid, [64][d_pad] w_out_t, [d_pad] b_out) and dbias1_out [S][64] (the
+ * cotangent of bias1: its column sums are the gradient of input_embed.bias, and TimeEmbed's backward takes it from
+ * there).  mlp->tc_image must be the LRDS_PRECISION_F16X3 image.  Built for d <= 64 and num_hidden <= 2 (the
+ * reference's FourierMLP default, num_layers = 4); LRDS_ERR_UNSUPPORTED otherwise.  Sums run in a fixed order
+ * (deterministic).  `scratch` holds lrds_mlp_grad_scratch_floats(d, num_hidden, S, B) floats. */
+int64_t lrds_mlp_grad_floats(int32_t d, int32_t num_hidden);
+int64_t lrds_mlp_grad_scratch_floats(int32_t d, int32_t num_hidden, int32_t S, int32_t B);
+int lrds_mlp_grad(const lrds_mlp* mlp, const float* bias1, const float* x, const float* cot, const float* step_w,
+                  const float* row_w, float clip, float cot_scale, int32_t S, int32_t B, float* grads_out,
+                  float* dbias1_out, float* scratch, void* stream);
 /* Distribution.unnorm_log_prob / score (distr/base.py:128-157); either output may be NULL. */
 int lrds_distr_eval(const lrds_distr* distr, int32_t d, const float* x, int32_t B, float* logp_out,
                     float* score_out, void* stream);

@@ -19,7 +19,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.environ.get("LRDS_B200_LIB") or os.path.join(CSRC, "liblrds_b200.so")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 
-ABI_VERSION = 7
+ABI_VERSION = 8
 CHANNELS = 64
 STEP_STRIDE = 80
 (STEP_A, STEP_B, STEP_C, STEP_DT, STEP_SQRT_DT, STEP_W_COST, STEP_W_ITO, STEP_GAMMA, STEP_FRAC, STEP_SIGU,
@@ -76,7 +76,8 @@ class Spec(C.Structure):
 
 EXPORTS = ["lrds_rollout", "lrds_tc_image_bytes", "lrds_gmm_mix_tc_bytes", "lrds_pack_gmm_mix_tc", "lrds_logreg_tc_bytes",
            "lrds_pack_logreg_tc", "lrds_pack_mlp_tc", "lrds_estimator_blocks", "lrds_estimator_partials", "lrds_estimator_merge", "lrds_ctrl_forward",
-           "lrds_distr_eval", "lrds_axpy_step", "lrds_normals", "lrds_mala", "lrds_last_error", "lrds_abi_version",
+           "lrds_distr_eval", "lrds_axpy_step", "lrds_normals", "lrds_mala", "lrds_mlp_grad", "lrds_mlp_grad_floats",
+           "lrds_mlp_grad_scratch_floats", "lrds_last_error", "lrds_abi_version",
            "lrds_launch_count"]
 
 COMPILE_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
@@ -154,6 +155,12 @@ def lib():
                 L.lrds_mala.argtypes = [C.POINTER(Distr), C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, FP, FP, FP, FP,
                                         C.c_uint64, FP, FP, FP]
                 L.lrds_normals.argtypes = [C.c_uint64, C.c_uint64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, FP, FP]
+                L.lrds_mlp_grad_floats.restype = C.c_int64
+                L.lrds_mlp_grad_floats.argtypes = [C.c_int32, C.c_int32]
+                L.lrds_mlp_grad_scratch_floats.restype = C.c_int64
+                L.lrds_mlp_grad_scratch_floats.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int32]
+                L.lrds_mlp_grad.argtypes = [C.POINTER(Mlp), FP, FP, FP, FP, FP, C.c_float, C.c_float, C.c_int32, C.c_int32,
+                                            FP, FP, FP, FP]
                 if L.lrds_abi_version() != ABI_VERSION:
                     raise RuntimeError("liblrds_b200.so ABI version mismatch; rebuild")
                 _lib = L

@@ -13,12 +13,15 @@ by autograd through K sequential steps (~40-150 eager ops each).  Here
   1. the rollout is ONE fused kernel launch (csrc/), fed with the generator's own increments z (lrds_normals) and
      returning the trajectory;
   2. d loss / d rnd comes from the reference's loss formula on the B log-weights;
-  3. the parameter gradient is ONE batched evaluation of the control on all K x B stored states with the cotangent
-     (d loss / d rnd_b) c_k z_bk: a handful of large library GEMMs (cuBLAS through torch autograd) instead of K small ones.
+  3. the parameter gradient is ONE batched pass over all K x B stored states with the cotangent
+     (d loss / d rnd_b) c_k z_bk: the hand-written weight-gradient kernel lrds_mlp_grad (csrc/lrds_mlp_grad.cu: the
+     activations are recomputed from the stored states on the tensor cores, the weight gradients accumulate in TMEM)
+     for the backbone; what remains for autograd is K rows wide (TimeEmbed under the kernel's bias cotangent, the
+     time-only score factor of ScoreCtrl).  Shapes the kernel is not built for (d > 64, more than 2 hidden layers)
+     and the all-fp32 validation precision ("fp32") take the same pass through torch autograd (large library GEMMs) -
+     stated, not hidden.
 
-Step 3 is plain PyTorch on the device - plumbing around the kernel, stated as such; a hand-written weight-gradient
-kernel that recomputes the activations from the stored states is the follow-up.  Nothing here
-runs on the CPU or imports the oracle.
+Nothing here runs on the CPU or imports the oracle.
 """
 from __future__ import annotations
 
@@ -66,6 +69,100 @@ def control_rows(info: pack.CtrlInfo, taus: torch.Tensor, xs: torch.Tensor, scor
     if info.kind == N.CTRL_LERP:          # ctrl + diff score
         return g + coef[:, N.STEP_GSCALE, None, None] * sc
     return g + sc
+
+
+def mlp_grad_applicable(base) -> bool:
+    """The weight-gradient kernel (lrds_mlp_grad) is built for the FourierMLP shapes d <= 64, at most 2 hidden layers."""
+    return hasattr(base, "lrds_mlp") and N.lib().lrds_mlp_grad_floats(base.dim, len(base.hidden_layer)) > 0
+
+
+def pow2_scale(bound: float, target: float = 4.0) -> float:
+    """Power of two s with bound * s in (target / 2, target] (1 for a zero / non-finite bound)."""
+    import math
+    if not (bound > 0.0) or math.isinf(bound):
+        return 1.0
+    return 2.0 ** math.floor(math.log2(target / bound))
+
+
+def mlp_grad(base, bias1: torch.Tensor, xs: torch.Tensor, cot: torch.Tensor, clip, step_w=None, row_w=None,
+             cot_bound: float | None = None):
+    """Gradient of  sum_{s,b} <cot_sb * step_w_s * row_w_b, clip(FourierMLP(t_s, x_sb))>  in the backbone's parameters,
+    by the hand-written kernel: returns ({parameter: gradient} for input_embed.weight, hidden_layer.*, out_layer.*,
+    dbias1 [S, 64]) where dbias1 is the cotangent of ``bias1`` = input_embed.bias + TimeEmbed(t_s) (the caller carries it
+    through TimeEmbed with autograd: S rows).  ``cot_bound`` >= max |cot * step_w * row_w| sets the fp16 operand scale."""
+    dev = xs.device
+    S, B, d = xs.shape
+    nh = len(base.hidden_layer)
+    mlp, keep = base.lrds_mlp(dev, N.PRECISION_F16X3)
+    xs, cot = xs.contiguous(), cot.contiguous()
+    bias1 = bias1.detach().to(dev, torch.float32).contiguous()
+    if cot_bound is None:
+        cot_bound = float(cot.abs().max()) * (float(step_w.abs().max()) if step_w is not None else 1.0) * \
+            (float(row_w.abs().max()) if row_w is not None else 1.0)
+    L = N.lib()
+    flat = torch.empty(int(L.lrds_mlp_grad_floats(d, nh)), device=dev, dtype=torch.float32)
+    dbias1 = torch.empty(S, N.CHANNELS, device=dev, dtype=torch.float32)
+    scratch = torch.empty(int(L.lrds_mlp_grad_scratch_floats(d, nh, S, B)), device=dev, dtype=torch.float32)
+    sw = None if step_w is None else step_w.detach().to(dev, torch.float32).contiguous()
+    rw = None if row_w is None else row_w.detach().to(dev, torch.float32).reshape(-1).contiguous()
+    with torch.cuda.device(dev):
+        N.check(L.lrds_mlp_grad(C.byref(mlp), N.ptr(bias1), N.ptr(xs), N.ptr(cot), N.ptr(sw), N.ptr(rw),
+                                float(clip) if clip is not None else 0.0, pow2_scale(cot_bound), S, B, N.ptr(flat),
+                                N.ptr(dbias1), N.ptr(scratch), N.stream_ptr(dev)))
+    Cc, dp = N.CHANNELS, mlp.d_pad
+    w_in_t, w_hid_t, b_hid, w_out_t, b_out = flat.split([d * Cc, nh * Cc * Cc, nh * Cc, Cc * dp, dp])
+    grads = {base.input_embed.weight: w_in_t.view(d, Cc).t(),
+             base.out_layer.weight: w_out_t.view(Cc, dp)[:, :d].t(), base.out_layer.bias: b_out[:d]}
+    for i, layer in enumerate(base.hidden_layer):
+        grads[layer.weight] = w_hid_t.view(nh, Cc, Cc)[i].t()
+        grads[layer.bias] = b_hid.view(nh, Cc)[i]
+    return grads, dbias1
+
+
+def control_param_grads(info: pack.CtrlInfo, params, taus, xs, cot, step_w, row_w, coef, score_of, max_rows: int):
+    """Gradients (a list aligned with ``params``) of  sum_{s,b} <cot_sb step_w_s row_w_b, control_rows(...)_sb>  with the
+    backbone's part taken by the weight-gradient kernel (mlp_grad) over all S x B states at once.  What is left for
+    autograd is S rows wide: TimeEmbed + input bias under the kernel's cotangent dbias1, and the time-only factor
+    clip(TimeEmbed_score(t)) of ScoreCtrl / CancelDriftCtrl / LerpCtrl (models/reparam.py:112-117, 131-147, 189-199)
+    under  M[s] = sum_b cot_sb (x) scale_score clip(score(x_sb))  (``score_of(k0, k1)`` -> the constant scores)."""
+    base = info.base
+    S, B, d = xs.shape
+    by_param = {}
+    with torch.enable_grad():
+        bias1 = time_embed_rows(base.timestep_embed, taus) + base.input_embed.bias
+    bound = float(cot.abs().max())
+    if step_w is not None:
+        bound *= float(step_w.abs().max())
+    if row_w is not None:
+        bound *= float(row_w.abs().max())
+    kernel_grads, dbias1 = mlp_grad(base, bias1, xs, cot, info.clip_model, step_w, row_w, cot_bound=bound)
+    by_param.update(kernel_grads)
+    tp = [p for p in [*base.timestep_embed.parameters(), base.input_embed.bias] if p.requires_grad]
+    if tp:
+        for p, g in zip(tp, torch.autograd.grad(bias1, tp, grad_outputs=dbias1, allow_unused=True)):
+            by_param[p] = g
+    sp = [] if info.kind == N.CTRL_CLIPPED or info.score_model is None else \
+        [p for p in info.score_model.parameters() if p.requires_grad]
+    if sp:
+        M = xs.new_empty(S, d)
+        rows = max(1, max_rows // B)
+        with torch.no_grad():
+            for k0 in range(0, S, rows):
+                k1 = min(S, k0 + rows)
+                sc = info.scale_score * _clip(score_of(k0, k1), info.clip_score)
+                if info.kind in (N.CTRL_CANCEL_DRIFT, N.CTRL_LERP):
+                    sc = sc * coef[k0:k1, N.STEP_GSCALE, None, None]
+                c = cot[k0:k1]
+                if step_w is not None:
+                    c = c * step_w[k0:k1, None, None]
+                if row_w is not None:
+                    c = c * row_w.reshape(1, B, 1)
+                M[k0:k1] = (c * sc).sum(1)
+        with torch.enable_grad():
+            gam = _clip(time_embed_rows(info.score_model, taus), info.clip_model)
+            for p, g in zip(sp, torch.autograd.grad((gam * M).sum(), sp, allow_unused=True)):
+                by_param[p] = g
+    return [by_param.get(p) for p in params]
 
 
 class _InjectGrads(torch.autograd.Function):
@@ -141,7 +238,18 @@ def lv_objective(loss_obj, plan: pack.Plan, info: pack.CtrlInfo, x: torch.Tensor
     pack.dis_ctrl_rows(info, plan.taus, coef)
     coef = coef.to(dev)
     step_rows = max(1, max_rows // B)
-    for k0 in range(0, K, step_rows):
+
+    def score_of(k0, k1):  # the constant score factor of the control at the stored states of steps k0 .. k1 - 1
+        flat = xs[k0:k1].reshape(-1, d)
+        score = info.target.score(flat).reshape(k1 - k0, B, d)
+        if info.kind == N.CTRL_LERP:  # clipped_interpolated_score, models/reparam.py:170-183
+            score = torch.lerp(info.prior.score(flat).reshape(k1 - k0, B, d), score, coef[k0:k1, N.STEP_LERP, None, None])
+        return score
+
+    use_kernel = mlp_grad_applicable(info.base) and plan.spec.precision != N.PRECISION_FP32_SIMT
+    if use_kernel:  # the backbone's gradient by lrds_mlp_grad: one launch over all K x B stored states
+        grads = control_param_grads(info, params, taus[:K], xs[:K], z, ito_w[:K], w.reshape(-1), coef, score_of, max_rows)
+    for k0 in range(0, K if not use_kernel else 0, step_rows):
         k1 = min(K, k0 + step_rows)
         xs_c = xs[k0:k1]
         score = None
@@ -218,7 +326,10 @@ def cmcd_lv_objective(loss_obj, plan: pack.Plan, info: pack.CtrlInfo, x: torch.T
         cot[:-1] += db
         cot[1:] -= cost * dt[:, None, None] + db
         cot *= w[None, :, :]
-    for j0 in range(0, K + 1, rows):  # pass 2: cotangents through the control
+    use_kernel = mlp_grad_applicable(info.base) and plan.spec.precision != N.PRECISION_FP32_SIMT
+    if use_kernel:  # pass 2 by lrds_mlp_grad: one launch over the (K + 1) x B stored states
+        grads = control_param_grads(info, params, ts, xs, cot, None, None, None, lambda j0, j1: tscore[j0:j1], max_rows)
+    for j0 in range(0, K + 1 if not use_kernel else 0, rows):  # pass 2 (shapes the kernel is not built for): autograd
         j1 = min(K + 1, j0 + rows)
         with torch.enable_grad():
             g = control_rows(info, ts[j0:j1], xs[j0:j1], tscore[j0:j1] if info.kind != N.CTRL_CLIPPED else None)
