@@ -279,6 +279,13 @@ int lrds_ctrl_forward(const lrds_spec* spec, int32_t row, const float* x, int32_
  * there).  mlp->tc_image must be the LRDS_PRECISION_F16X3 image.  Built for d <= 64 and num_hidden <= 2 (the
  * reference's FourierMLP default, num_layers = 4); LRDS_ERR_UNSUPPORTED otherwise.  Sums run in a fixed order
  * (deterministic).  `scratch` holds lrds_mlp_grad_scratch_floats(d, num_hidden, S, B) floats. */
+/* out[s][j] = sum_b step_w[s] row_w[b] cot[s][b][j] * clip(score(x[s][b]))[j]: the cotangent of the time-only factor
+ * clip(TimeEmbed_score(t)) of ScoreCtrl / CancelDriftCtrl (models/reparam.py:112-117, 131-147) in the same batched
+ * gradient pass (clip <= 0: none; step_w / row_w may be NULL).  Fixed summation order.  `scratch` holds
+ * lrds_score_cot_scratch_floats(distr, d, S, B) floats. */
+int64_t lrds_score_cot_scratch_floats(const lrds_distr* distr, int32_t d, int32_t S, int32_t B);
+int lrds_score_cot_sums(const lrds_distr* distr, int32_t d, const float* x, const float* cot, const float* step_w,
+                        const float* row_w, float clip, int32_t S, int32_t B, float* out, float* scratch, void* stream);
 int64_t lrds_mlp_grad_floats(int32_t d, int32_t num_hidden);
 int64_t lrds_mlp_grad_scratch_floats(int32_t d, int32_t num_hidden, int32_t S, int32_t B);
 int lrds_mlp_grad(const lrds_mlp* mlp, const float* bias1, const float* x, const float* cot, const float* step_w,

@@ -77,7 +77,8 @@ class Spec(C.Structure):
 EXPORTS = ["lrds_rollout", "lrds_tc_image_bytes", "lrds_gmm_mix_tc_bytes", "lrds_pack_gmm_mix_tc", "lrds_logreg_tc_bytes",
            "lrds_pack_logreg_tc", "lrds_pack_mlp_tc", "lrds_estimator_blocks", "lrds_estimator_partials", "lrds_estimator_merge", "lrds_ctrl_forward",
            "lrds_distr_eval", "lrds_axpy_step", "lrds_normals", "lrds_mala", "lrds_mlp_grad", "lrds_mlp_grad_floats",
-           "lrds_mlp_grad_scratch_floats", "lrds_last_error", "lrds_abi_version",
+           "lrds_mlp_grad_scratch_floats", "lrds_score_cot_sums", "lrds_score_cot_scratch_floats",
+           "lrds_last_error", "lrds_abi_version",
            "lrds_launch_count"]
 
 COMPILE_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
@@ -161,6 +162,10 @@ def lib():
                 L.lrds_mlp_grad_scratch_floats.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int32]
                 L.lrds_mlp_grad.argtypes = [C.POINTER(Mlp), FP, FP, FP, FP, FP, C.c_float, C.c_float, C.c_int32, C.c_int32,
                                             FP, FP, FP, FP]
+                L.lrds_score_cot_scratch_floats.restype = C.c_int64
+                L.lrds_score_cot_scratch_floats.argtypes = [C.POINTER(Distr), C.c_int32, C.c_int32, C.c_int32]
+                L.lrds_score_cot_sums.argtypes = [C.POINTER(Distr), C.c_int32, FP, FP, FP, FP, C.c_float, C.c_int32, C.c_int32,
+                                                  FP, FP, FP]
                 if L.lrds_abi_version() != ABI_VERSION:
                     raise RuntimeError("liblrds_b200.so ABI version mismatch; rebuild")
                 _lib = L

@@ -392,6 +392,99 @@ __global__ void __launch_bounds__(128) distr_eval_kernel(const lrds_spec s, cons
   }
 }
 
+// ---- sum_b w_sb cot_sb (x) clip(score(x_sb)) per time slice s: the cotangent of the time-only factor of ScoreCtrl
+// (models/reparam.py:112-117: ctrl = clip(net) + scale * clip(score) * clip(TimeEmbed_score(t))) in the batched gradient
+// pass of train.py.  One thread per stored state; the columns are reduced over the warp, then over the block's warps;
+// every block writes its partial row (part[s][block][dp]) and score_cot_reduce_kernel adds them in a fixed order.
+// bytes of a mixture target staged in shared memory behind the particle columns (0: read from global memory)
+__host__ __device__ inline uint32_t score_cot_stage_bytes(const lrds_spec& s, uint32_t* logc_bytes) {
+  if (s.target.kind != LRDS_DISTR_GMM || s.target.gmm.M < 2) return *logc_bytes = 0u;
+  const int M = s.target.gmm.M;
+  *logc_bytes = (uint32_t)((M + 3) / 4 * 4) * 4u;
+  return *logc_bytes + (uint32_t)((M + 3) / 4) * (uint32_t)s.mlp.d_pad * 32u;
+}
+
+template <bool SH>
+__device__ __forceinline__ void score_cot_body(const lrds_spec& s, const lrds::GmmViewT<SH>& tv, const lrds::Particle& P,
+                                               const float* __restrict__ cot, int64_t row, float w, float clip,
+                                               float (*red)[lrds::JC], float* __restrict__ dst) {
+  using namespace lrds;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nw = blockDim.x >> 5;
+  const int d = s.d, dp = s.mlp.d_pad;
+  target_pass1<SH>(s, s.target.kind, tv, P, false);
+  float xm = 0.f;
+  for (int j0 = 0; j0 < dp; j0 += JC) {
+    float xr[JC], ts[JC];
+    load_chunk(P.x, j0, xr);
+    const float xp = (j0 + JC < dp) ? P.x(j0 + JC) : 0.f;
+    target_score_chunk<SH>(s, s.target.kind, tv, P, xr, xm, xp, j0, ts);
+    xm = xr[JC - 1];
+#pragma unroll
+    for (int c = 0; c < JC; ++c) {
+      float v = ts[c];
+      if (clip > 0.f) v = fminf(fmaxf(v, -clip), clip);
+      v *= (j0 + c < d) ? __ldg(cot + row * d + j0 + c) * w : 0.f;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0) red[warp][c] = v;
+    }
+    __syncthreads();
+    if (tid < JC) {
+      float acc = red[0][tid];
+      for (int i = 1; i < nw; ++i) acc += red[i][tid];
+      dst[j0 + tid] = acc;
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(128) score_cot_kernel(const lrds_spec s, const float* __restrict__ x,
+                                                        const float* __restrict__ cot, const float* __restrict__ step_w,
+                                                        const float* __restrict__ row_w, const float clip,
+                                                        float* __restrict__ part) {
+  using namespace lrds;
+  extern __shared__ __align__(16) float smem[];
+  __shared__ float red[4][JC];
+  const int NT = blockDim.x, tid = threadIdx.x;
+  const int slice = blockIdx.y;
+  const int b_raw = blockIdx.x * NT + tid;
+  const bool live = b_raw < s.B;
+  const int b = live ? b_raw : s.B - 1;
+  const int64_t row = (int64_t)slice * s.B + b;
+  const ColLayout L = col_layout(s);
+  const Particle P = make_particle(smem, L, NT, tid);
+  const GmmView tv0 = gmm_at(s.target.gmm, 0);
+  const int d = s.d, dp = s.mlp.d_pad;
+  for (int j = 0; j < dp; ++j) P.x(j) = (j < d) ? __ldg(x + row * d + j) : 0.f;
+  float w = live ? 1.f : 0.f;
+  if (step_w) w *= __ldg(step_w + slice);
+  if (row_w) w *= __ldg(row_w + b);
+  float* dst = part + ((int64_t)slice * gridDim.x + blockIdx.x) * dp;
+  uint32_t logc_bytes;
+  const uint32_t stage_bytes = score_cot_stage_bytes(s, &logc_bytes);
+  if (stage_bytes) {  // mixture target: its (logc, sn) blocks go to shared memory once per block
+    float4* stg = reinterpret_cast<float4*>(smem + (size_t)L.total * NT);
+    const float4* g_logc = reinterpret_cast<const float4*>(tv0.logc.p);
+    const float4* g_sn = reinterpret_cast<const float4*>(tv0.sn.p);
+    const int n_logc = (int)(logc_bytes / 16u), n_all = (int)(stage_bytes / 16u);
+    for (int i = tid; i < n_all; i += NT) stg[i] = i < n_logc ? __ldg(g_logc + i) : __ldg(g_sn + (i - n_logc));
+    __syncthreads();
+    const GmmViewT<true> tv = staged_view(reinterpret_cast<const uint8_t*>(stg), tv0, logc_bytes, stage_bytes - logc_bytes);
+    score_cot_body<true>(s, tv, P, cot, row, w, clip, red, dst);
+  } else {
+    score_cot_body<false>(s, tv0, P, cot, row, w, clip, red, dst);
+  }
+}
+
+__global__ void score_cot_reduce_kernel(const float* __restrict__ part, int nblk, int dp, int d, float* __restrict__ out) {
+  const int slice = blockIdx.x, j = threadIdx.x;
+  if (j >= d) return;
+  const float* src = part + (int64_t)slice * nblk * dp + j;
+  float acc = 0.f;
+  for (int i = 0; i < nblk; ++i) acc += src[(int64_t)i * dp];
+  out[(int64_t)slice * d + j] = acc;
+}
+
 // ---- MALA chains: the whole loop of mcmc_sample(mcmc_type='mala') (experiments/benchmark_utils.py:268-333) around
 // mala_step and heuristics_step_size (sde_sampler/additions/mcmc.py:75-134, 54-72) in one launch, one thread per chain.
 // Columns: x = proposal, us = current state, tsd = score at the current state, db = score at the proposal.
@@ -570,9 +663,73 @@ int distr_eval_launch(const lrds_distr* distr, int32_t d, const float* x, int32_
   return LRDS_OK;
 }
 
+// spec of a bare distribution evaluation (lrds_distr_eval, lrds_score_cot_sums)
+int distr_spec(const lrds_distr* distr, int32_t d, int32_t B, lrds_spec* out) {
+  lrds_spec& s = *out;
+  memset(&s, 0, sizeof(s));
+  s.abi_version = LRDS_ABI_VERSION;
+  s.B = B;
+  s.d = d;
+  s.mlp.d = d;
+  s.mlp.d_pad = ((d + 7) / 8) * 8;
+  s.target = *distr;
+  s.ctrl_kind = LRDS_CTRL_CLIPPED;
+  if (distr->kind == LRDS_DISTR_GMM) {
+    if (int r = validate_gmm(distr->gmm, "distr")) return r;
+  } else if (distr->kind == LRDS_DISTR_LOGREG) {
+    if (distr->logreg.p + 1 != d) return fail(LRDS_ERR_INVALID, "logreg: d must be p + 1");
+  } else if (distr->kind != LRDS_DISTR_PHI4) {
+    return fail(LRDS_ERR_UNSUPPORTED, "distr: unknown distribution kind");
+  }
+  return LRDS_OK;
+}
+
+int score_cot_threads(const lrds_spec& s) {
+  uint32_t lb;
+  return pick_threads(lrds::col_layout(s).total, max_optin_smem() - (int)score_cot_stage_bytes(s, &lb));
+}
+
 }  // namespace
 
 extern "C" {
+
+int64_t lrds_score_cot_scratch_floats(const lrds_distr* distr, int32_t d, int32_t S, int32_t B) {
+  lrds_spec s;
+  if (!distr || d < 1 || S < 1 || B < 1) return fail(LRDS_ERR_INVALID, "score_cot_sums: bad arguments");
+  if (int r = distr_spec(distr, d, B, &s)) return r;
+  const int nt = score_cot_threads(s);
+  if (nt == 0) return fail(LRDS_ERR_RESOURCES, "score_cot_sums: per-particle state does not fit in shared memory");
+  return (int64_t)S * ((B + nt - 1) / nt) * s.mlp.d_pad;
+}
+
+int lrds_score_cot_sums(const lrds_distr* distr, int32_t d, const float* x, const float* cot, const float* step_w,
+                        const float* row_w, float clip, int32_t S, int32_t B, float* out, float* scratch, void* stream) {
+  if (!distr || !x || !cot || !out || !scratch || d < 1 || S < 1 || B < 1)
+    return fail(LRDS_ERR_INVALID, "score_cot_sums: bad arguments");
+  if (S > 65535) return fail(LRDS_ERR_UNSUPPORTED, "score_cot_sums: at most 65535 time slices per call");
+  lrds_spec s;
+  if (int r = distr_spec(distr, d, B, &s)) return r;
+  const lrds::ColLayout L = lrds::col_layout(s);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nt = score_cot_threads(s);
+  if (nt == 0) return fail(LRDS_ERR_RESOURCES, "score_cot_sums: per-particle state does not fit in shared memory");
+  uint32_t lb;
+  const size_t smem = (size_t)L.total * nt * sizeof(float) + score_cot_stage_bytes(s, &lb);
+  cudaError_t e0 = cudaFuncSetAttribute(score_cot_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e0 != cudaSuccess) return cuda_fail(e0, "cudaFuncSetAttribute");
+  const int nblk = (B + nt - 1) / nt;
+  score_cot_kernel<<<dim3(nblk, S), nt, smem, st>>>(s, x, cot, step_w, row_w, clip, scratch);
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) {
+    score_cot_reduce_kernel<<<S, ((d + 31) / 32) * 32, 0, st>>>(scratch, nblk, s.mlp.d_pad, d, out);
+    e = cudaGetLastError();
+  }
+  if (e != cudaSuccess) return cuda_fail(e, "score_cot_sums launch");
+  g_launches.fetch_add(2);
+  return LRDS_OK;
+}
+
+
 
 const char* lrds_last_error(void) { return g_err; }
 int lrds_abi_version(void) { return LRDS_ABI_VERSION; }

@@ -119,7 +119,29 @@ def mlp_grad(base, bias1: torch.Tensor, xs: torch.Tensor, cot: torch.Tensor, cli
     return grads, dbias1
 
 
-def control_param_grads(info: pack.CtrlInfo, params, taus, xs, cot, step_w, row_w, coef, score_of, max_rows: int):
+def score_cot_sums(distr, xs: torch.Tensor, cot: torch.Tensor, clip, step_w=None, row_w=None) -> torch.Tensor:
+    """M[s, j] = sum_b step_w[s] row_w[b] cot[s, b, j] clip(distr.score(xs[s, b]))[j]  by one fused launch
+    (lrds_score_cot_sums): the scores are evaluated and reduced in the kernel instead of being written out."""
+    dev = xs.device
+    S, B, d = xs.shape
+    block, _keep = distr.lrds_distr(dev)
+    L = N.lib()
+    n = int(L.lrds_score_cot_scratch_floats(C.byref(block), d, S, B))
+    if n < 0:
+        N.check(n)
+    out = torch.empty(S, d, device=dev, dtype=torch.float32)
+    scratch = torch.empty(n, device=dev, dtype=torch.float32)
+    sw = None if step_w is None else step_w.detach().to(dev, torch.float32).contiguous()
+    rw = None if row_w is None else row_w.detach().to(dev, torch.float32).reshape(-1).contiguous()
+    with torch.cuda.device(dev):
+        N.check(L.lrds_score_cot_sums(C.byref(block), d, N.ptr(xs.contiguous()), N.ptr(cot.contiguous()), N.ptr(sw), N.ptr(rw),
+                                      float(clip) if clip is not None else 0.0, S, B, N.ptr(out), N.ptr(scratch),
+                                      N.stream_ptr(dev)))
+    return out
+
+
+def control_param_grads(info: pack.CtrlInfo, params, taus, xs, cot, step_w, row_w, coef, score_of, max_rows: int,
+                        cot_max: float | None = None):
     """Gradients (a list aligned with ``params``) of  sum_{s,b} <cot_sb step_w_s row_w_b, control_rows(...)_sb>  with the
     backbone's part taken by the weight-gradient kernel (mlp_grad) over all S x B states at once.  What is left for
     autograd is S rows wide: TimeEmbed + input bias under the kernel's cotangent dbias1, and the time-only factor
@@ -130,7 +152,7 @@ def control_param_grads(info: pack.CtrlInfo, params, taus, xs, cot, step_w, row_
     by_param = {}
     with torch.enable_grad():
         bias1 = time_embed_rows(base.timestep_embed, taus) + base.input_embed.bias
-    bound = float(cot.abs().max())
+    bound = float(cot.abs().max()) if cot_max is None else cot_max
     if step_w is not None:
         bound *= float(step_w.abs().max())
     if row_w is not None:
@@ -144,20 +166,25 @@ def control_param_grads(info: pack.CtrlInfo, params, taus, xs, cot, step_w, row_
     sp = [] if info.kind == N.CTRL_CLIPPED or info.score_model is None else \
         [p for p in info.score_model.parameters() if p.requires_grad]
     if sp:
-        M = xs.new_empty(S, d)
-        rows = max(1, max_rows // B)
-        with torch.no_grad():
-            for k0 in range(0, S, rows):
-                k1 = min(S, k0 + rows)
-                sc = info.scale_score * _clip(score_of(k0, k1), info.clip_score)
-                if info.kind in (N.CTRL_CANCEL_DRIFT, N.CTRL_LERP):
-                    sc = sc * coef[k0:k1, N.STEP_GSCALE, None, None]
-                c = cot[k0:k1]
-                if step_w is not None:
-                    c = c * step_w[k0:k1, None, None]
-                if row_w is not None:
-                    c = c * row_w.reshape(1, B, 1)
-                M[k0:k1] = (c * sc).sum(1)
+        if info.kind != N.CTRL_LERP and hasattr(info.target, "lrds_distr"):  # scores evaluated and reduced in one kernel
+            M = info.scale_score * score_cot_sums(info.target, xs, cot, info.clip_score, step_w, row_w)
+            if info.kind == N.CTRL_CANCEL_DRIFT:
+                M = M * coef[:S, N.STEP_GSCALE, None]
+        else:  # LerpCtrl clips the INTERPOLATED score (models/reparam.py:170-183): two distributions, elementwise here
+            M = xs.new_empty(S, d)
+            rows = max(1, max_rows // B)
+            with torch.no_grad():
+                for k0 in range(0, S, rows):
+                    k1 = min(S, k0 + rows)
+                    sc = info.scale_score * _clip(score_of(k0, k1), info.clip_score)
+                    if info.kind in (N.CTRL_CANCEL_DRIFT, N.CTRL_LERP):
+                        sc = sc * coef[k0:k1, N.STEP_GSCALE, None, None]
+                    c = cot[k0:k1]
+                    if step_w is not None:
+                        c = c * step_w[k0:k1, None, None]
+                    if row_w is not None:
+                        c = c * row_w.reshape(1, B, 1)
+                    M[k0:k1] = (c * sc).sum(1)
         with torch.enable_grad():
             gam = _clip(time_embed_rows(info.score_model, taus), info.clip_model)
             for p, g in zip(sp, torch.autograd.grad((gam * M).sum(), sp, allow_unused=True)):
@@ -215,9 +242,11 @@ def lv_objective(loss_obj, plan: pack.Plan, info: pack.CtrlInfo, x: torch.Tensor
     dev = x.device
     B, d = x.shape
     K = plan.noise_steps
+    # without recorded increments the rollout draws its own (in-kernel Philox, no read of a [K, B, d] array); lrds_normals
+    # reproduces exactly those for the cotangents below
     z = normals(seed, particle_offset, K, B, d, dev) if noise is None else noise.detach().to(dev, torch.float32).contiguous()
     with torch.no_grad():
-        x_T, rnd, xs = pack.run_rollout(plan, x, z, seed, particle_offset, True)
+        x_T, rnd, xs = pack.run_rollout(plan, x, None if noise is None else z, seed, particle_offset, True)
     if group is not None:
         if loss_obj.method != "lv":
             raise NotImplementedError("sharded training is built for method 'lv'")
@@ -248,7 +277,9 @@ def lv_objective(loss_obj, plan: pack.Plan, info: pack.CtrlInfo, x: torch.Tensor
 
     use_kernel = mlp_grad_applicable(info.base) and plan.spec.precision != N.PRECISION_FP32_SIMT
     if use_kernel:  # the backbone's gradient by lrds_mlp_grad: one launch over all K x B stored states
-        grads = control_param_grads(info, params, taus[:K], xs[:K], z, ito_w[:K], w.reshape(-1), coef, score_of, max_rows)
+        # the generator's normals are bounded: Box-Muller on at most 32-bit uniforms, |z| <= sqrt(2 * 32 * ln 2) < 6.7
+        grads = control_param_grads(info, params, taus[:K], xs[:K], z, ito_w[:K], w.reshape(-1), coef, score_of, max_rows,
+                                    cot_max=7.0 if noise is None else None)
     for k0 in range(0, K if not use_kernel else 0, step_rows):
         k1 = min(K, k0 + step_rows)
         xs_c = xs[k0:k1]

@@ -86,3 +86,27 @@ def test_mlp_grad_unsupported_shapes_raise():
     from sde_sampler_lrds_b200 import _native as N
     assert N.lib().lrds_mlp_grad_floats(65, 2) < 0 and N.lib().lrds_mlp_grad_floats(50, 3) < 0
     assert N.lib().lrds_mlp_grad_floats(50, 2) == 50 * 64 + 2 * 64 * 64 + 2 * 64 + 64 * 56 + 56
+
+
+@pytest.mark.parametrize("name,S,B,clip", [("ei_many_modes", 5, 1000, 3.0), ("ei_many_modes", 3, 77, None),
+                                           ("pis_phi4", 4, 300, 0.5), ("cmcd_logreg_sonar", 2, 200, 10.0)])
+def test_score_cot_sums_matches_elementwise(name, S, B, clip):
+    """lrds_score_cot_sums (scores evaluated and reduced in the kernel) against Distribution.score + torch sums."""
+    from sde_sampler_lrds_b200.train import score_cot_sums
+    from tests.cases import CASES
+    from tests.product_builders import build_target
+    dev = torch.device("cuda:0")
+    target = build_target(CASES[name]()["problem"]["target"], dev)
+    d = target.dim
+    torch.manual_seed(3)
+    xs = torch.randn(S, B, d, device=dev) * 0.7
+    cot = torch.randn(S, B, d, device=dev)
+    step_w = torch.rand(S, device=dev) + 0.5
+    row_w = torch.randn(B, device=dev)
+    got = score_cot_sums(target, xs, cot, clip, step_w, row_w)
+    sc = target.score(xs.reshape(-1, d)).reshape(S, B, d).double()
+    if clip is not None:
+        sc = sc.clip(-clip, clip)
+    want = (sc * cot.double() * step_w.double()[:, None, None] * row_w.double()[None, :, None]).sum(1)
+    assert ((got.double() - want).abs().max() / want.abs().max()) < 1e-5
+    assert torch.equal(got, score_cot_sums(target, xs, cot, clip, step_w, row_w))  # fixed summation order

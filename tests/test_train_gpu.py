@@ -100,3 +100,26 @@ def test_training_steps_through_make_model(solver_type, kw, device):
     with pytest.raises(NotImplementedError):
         model.loss.method = "kl"
         model.compute_loss()
+
+
+@pytest.mark.parametrize("name", ["ei_many_modes", "pis_many_modes", "cmcd_gmm"])
+def test_training_with_generated_noise_equals_recorded_noise(name, device):
+    """Without recorded increments the training rollout draws its noise in the kernel and the gradient pass regenerates
+    it (lrds_normals): loss and gradient must equal the run that is handed those increments as a recorded array."""
+    from sde_sampler_lrds_b200 import train as TR
+    from tests.product_builders import Built
+    case = grad_case(name)
+    x0 = initial_state(case)
+    K, B, d = noise_for(case).shape
+    out = []
+    for recorded in (False, True):
+        built = Built(case, device, "f16x3")
+        z = TR.normals(11, 0, K, B, d, device) if recorded else None
+        loss, _ = built.train_loss(x0, z, seed=11)
+        loss.backward()
+        out.append((loss.item(), {n: p.grad.detach().clone() for n, p in built.ctrl.named_parameters() if p.grad is not None}))
+    (l0, g0), (l1, g1) = out
+    assert abs(l0 - l1) <= 1e-6 * max(1.0, abs(l1))
+    # the two runs may pick different power-of-two scales for the fp16 cotangent operands of lrds_mlp_grad (an analytic
+    # bound on the generator's normals vs. the maximum of the recorded array): equal up to that rounding noise
+    assert worst(g0, g1) < 5e-4
