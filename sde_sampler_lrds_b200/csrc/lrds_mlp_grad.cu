@@ -8,7 +8,7 @@
 //   wanted:   dW_out = sum_r delta_net g_{nh+1}^T,  dW_l = sum_r delta_{l+1} g_l^T,  dW_in = sum_r delta_1 x_r^T,
 //             the bias sums, and  dbias1[s] = sum_b delta_1  (the cotangent of TimeEmbed + input bias)
 //
-// One CTA per SM walks over tiles of 128 rows (thread pair <-> row <-> TMEM lane; the two threads split the columns).
+// One CTA per SM walks over tiles of 128 rows (four threads <-> row <-> TMEM lane; they split the columns in quarters).
 // Per tile the activations are recomputed on the tensor cores exactly like the rollout does (fp16 (hi, lo) 3-pass
 // GEMMs, A operand in TMEM, the rollout's own weight image as B), GELU' is kept in TMEM, the backward-data GEMMs read
 // the SAME weight image as an MN-major B operand (contraction over the image's rows), and the weight gradients are
@@ -29,23 +29,42 @@
 
 namespace lrds {
 
-constexpr int MG_THREADS = 256;
+constexpr int MG_THREADS = 512;  // 16 warps: four threads per row of the tile, 16 columns each
 constexpr uint32_t MG_A_HI = 0, MG_A_LO = 32, MG_D = 64, MG_GP = 128, MG_ACC = 256, MG_TMEM_COLS = 512;
 constexpr uint32_t MG_GROUP = 2048;  // 8 features x 128 rows x fp16: [row][8] with 16 bytes per row
 
 struct MgLayout {
-  uint32_t tail, xbuf, gbuf, gstride, dbuf, bytes;
+  uint32_t tail, xbuf, gbuf, gstride, dbuf, xstage, cstage, bytes;
 };
-__host__ __device__ inline MgLayout mg_layout(const TcLayout& TL) {
+__host__ __device__ inline MgLayout mg_layout(const TcLayout& TL, int d) {
   MgLayout M;
   M.tail = TL.bytes;
   M.xbuf = (TL.bytes + TC_TAIL_BYTES + 127u) & ~127u;
   M.gbuf = M.xbuf + (uint32_t)(TL.Kin / 8) * MG_GROUP;
   M.gstride = 9u * MG_GROUP;  // 8 feature groups + the block of ones
   M.dbuf = M.gbuf + (uint32_t)(TL.nh + 1) * M.gstride;
-  M.bytes = M.dbuf + 8u * MG_GROUP;  // an A operand spans 16 groups from its start: always inside [xbuf, bytes)
+  M.xstage = M.dbuf + 8u * MG_GROUP;  // an A operand spans 16 groups from its start: always inside [xbuf, xstage)
+  const uint32_t stage = (128u * (uint32_t)d * 4u + 127u) & ~127u;  // one tile's rows of x / of the cotangents, as in global memory
+  M.cstage = M.xstage + stage;
+  M.bytes = M.cstage + stage;
   return M;
 }
+
+// Optional phase timers (-DLRDS_MG_TIMING, tools/mlp_grad_timing.py only): threads 0 and 32 of CTA 0 accumulate the cycles
+// between the marks of the tile loop.
+#ifdef LRDS_MG_TIMING
+__device__ unsigned long long g_mg_timing[2 * 24];
+#define MG_MARK(i)                                              \
+  do {                                                          \
+    if (tm_on) {                                                \
+      const long long now_ = clock64();                         \
+      tm_acc[i] += (unsigned long long)(now_ - tm_last);        \
+      tm_last = now_;                                           \
+    }                                                           \
+  } while (0)
+#else
+#define MG_MARK(i) do { } while (0)
+#endif
 
 struct MlpGradArgs {
   lrds_mlp mlp;
@@ -101,9 +120,9 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mlp_grad_kernel(const MlpGradAr
   uint8_t* const smem = smem_raw;
   const int d = a.mlp.d, dp = a.mlp.d_pad, nh = a.mlp.num_hidden;
   const TcLayout TL = tc_layout(d, nh, LRDS_PRECISION_F16X3);
-  const MgLayout ML = mg_layout(TL);
+  const MgLayout ML = mg_layout(TL, d);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, q = warp & 3, h = warp >> 2;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + ML.tail);  // [0] image, [1] MMA batches
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + ML.tail);  // [0] image, [1] MMA batches, [2] x rows, [3] cotangent rows
   uint32_t* slot = reinterpret_cast<uint32_t*>(smem + ML.tail + 48);
   const int64_t t0 = a.tiles * blockIdx.x / gridDim.x, t1 = a.tiles * (blockIdx.x + 1) / gridDim.x;
   float* part = a.part + (int64_t)blockIdx.x * a.P;
@@ -115,6 +134,8 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mlp_grad_kernel(const MlpGradAr
   if (tid == 0) {
     ptx::mbar_init(bars, 1);
     ptx::mbar_init(bars + 1, 1);
+    ptx::mbar_init(bars + 2, 1);
+    ptx::mbar_init(bars + 3, 1);
     ptx::fence_mbar_init();
   }
   for (int l = 0; l <= nh; ++l) {  // the blocks of ones behind the activation buffers
@@ -206,54 +227,94 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mlp_grad_kernel(const MlpGradAr
 
   const float inv_cs = 1.0f / a.cot_scale;
   bool first = true, pending = false;
+#ifdef LRDS_MG_TIMING
+  const bool tm_on = blockIdx.x == 0 && (tid == 0 || tid == 32);
+  unsigned long long tm_acc[24] = {};
+  long long tm_last = clock64();
+#endif
+  // The rows of a tile are contiguous in global memory (128 x d floats): the TMA engine copies them into shared memory one
+  // stage ahead (x of tile t + 1 while tile t runs, its cotangents behind tile t's output stage) and every thread picks
+  // its 16 values from there - per-thread global loads of rows 4 d bytes apart cost 32 wavefronts each.  Tiles that are
+  // ragged (the last of a time slice) or not 16-byte aligned in global memory take the per-thread loads.
+  const uint32_t stage_bytes = 128u * (uint32_t)d * 4u;
+  const float* xs = reinterpret_cast<const float*>(smem + ML.xstage);
+  const float* cs = reinterpret_cast<const float*>(smem + ML.cstage);
+  uint32_t phx = 0, phc = 0;
+  auto tile_row0 = [&](int64_t tile) { return (tile / a.tiles_per_s) * (int64_t)a.B + (tile % a.tiles_per_s) * 128; };
+  auto tile_fast = [&](int64_t tile) -> bool {
+    if ((int)(tile % a.tiles_per_s) * 128 + 128 > a.B) return false;
+    const int64_t e0 = tile_row0(tile) * d;
+    return ((reinterpret_cast<uintptr_t>(a.x + e0) | reinterpret_cast<uintptr_t>(a.cot + e0)) & 15u) == 0;
+  };
+  auto fetch = [&](const float* src, uint32_t stage_off, uint64_t* b, int64_t tile) {  // one thread
+    ptx::mbar_expect_tx(b, stage_bytes);
+    ptx::bulk_g2s(smem + stage_off, src + tile_row0(tile) * d, stage_bytes, b);
+  };
+  auto load16 = [&](const float* __restrict__ src, int64_t r, bool valid, float (&v)[16]) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const int j = 16 * h + i;
+      v[i] = (valid && j < d) ? __ldg(src + r * d + j) : 0.f;
+    }
+  };
+  auto pick16 = [&](const float* stage, float (&v)[16]) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const int j = 16 * h + i;
+      v[i] = j < d ? stage[rloc * d + j] : 0.f;
+    }
+  };
+  if (tid == 0 && tile_fast(t0)) {
+    fetch(a.x, ML.xstage, bars + 2, t0);
+    fetch(a.cot, ML.cstage, bars + 3, t0);
+  }
+  float xv[16], cv[16];
   for (int64_t tile = t0; tile < t1; ++tile) {
     const int s = (int)(tile / a.tiles_per_s);
     const int row = (int)(tile % a.tiles_per_s) * 128 + rloc;
     const bool valid = row < a.B;
     const int64_t r = (int64_t)s * a.B + (valid ? row : 0);
-    // ---- x: 16-dim blocks, block b by the thread with h == (b & 1) ----
-    float xv[2][16];
-#pragma unroll
-    for (int nb = 0; nb < 2; ++nb) {
-      const int b = h + 2 * nb;
-#pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const int j = 16 * b + i;
-        xv[nb][i] = (valid && j < d) ? __ldg(a.x + r * d + j) : 0.f;
-      }
+    const bool fast = tile_fast(tile), next_fast = tile + 1 < t1 && tile_fast(tile + 1);
+    if (fast) {
+      ptx::mbar_wait(bars + 2, phx);
+      phx ^= 1u;
+      pick16(xs, xv);
+    } else {
+      load16(a.x, r, valid, xv);
     }
+    MG_MARK(0);
     if (pending) wait();  // the previous tile's last batch has read its buffers
+    MG_MARK(1);
+    if (h < Kin / 16) {
+      uint32_t ph[8], pl[8], pr[8];
 #pragma unroll
-    for (int nb = 0; nb < 2; ++nb) {
-      const int b = h + 2 * nb;
-      if (b < Kin / 16) {
-        uint32_t ph[8], pl[8], pr[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          split_pack(xv[nb][2 * i], xv[nb][2 * i + 1], ph[i], pl[i]);
-          pr[i] = ptx::pack_f16x2(xv[nb][2 * i], xv[nb][2 * i + 1]);
-        }
-        ptx::tmem_st8(tm_lane + MG_A_HI + 8 * b, ph);
-        ptx::tmem_st8(tm_lane + MG_A_LO + 8 * b, pl);
-        uint8_t* xb = smem + ML.xbuf + (uint32_t)(2 * b) * MG_GROUP + (uint32_t)rloc * 16u;
-        *reinterpret_cast<uint4*>(xb) = make_uint4(pr[0], pr[1], pr[2], pr[3]);
-        *reinterpret_cast<uint4*>(xb + MG_GROUP) = make_uint4(pr[4], pr[5], pr[6], pr[7]);
+      for (int i = 0; i < 8; ++i) {
+        split_pack(xv[2 * i], xv[2 * i + 1], ph[i], pl[i]);
+        pr[i] = ptx::pack_f16x2(xv[2 * i], xv[2 * i + 1]);
       }
+      ptx::tmem_st8(tm_lane + MG_A_HI + 8 * h, ph);
+      ptx::tmem_st8(tm_lane + MG_A_LO + 8 * h, pl);
+      uint8_t* xb = smem + ML.xbuf + (uint32_t)(2 * h) * MG_GROUP + (uint32_t)rloc * 16u;
+      *reinterpret_cast<uint4*>(xb) = make_uint4(pr[0], pr[1], pr[2], pr[3]);
+      *reinterpret_cast<uint4*>(xb + MG_GROUP) = make_uint4(pr[4], pr[5], pr[6], pr[7]);
     }
     hand([&] { mma_fwd(TL.off_in, Kin, C); });
+    if (tid == 0 && next_fast) fetch(a.x, ML.xstage, bars + 2, tile + 1);  // every thread has picked its x values
+    MG_MARK(2);
 
     // ---- forward: bias + GELU, GELU' to TMEM, the activation to TMEM (next GEMM) and shared memory (its weight gradient) ----
     for (int l = 0; l <= nh; ++l) {
       wait();
+      MG_MARK(3 + 2 * l);
       const u64 us2 = f2::pk(sc[8 + l]);
-      uint32_t rr[32];
-      ptx::tmem_ld32(tm_lane + MG_D + 32 * h, rr);
+      uint32_t rr[16];
+      ptx::tmem_ld16(tm_lane + MG_D + 16 * h, rr);
       ptx::tmem_wait_ld();
-      const float4* b4 = l == 0 ? reinterpret_cast<const float4*>(a.bias1 + (int64_t)s * C + 32 * h)
-                                : reinterpret_cast<const float4*>(bhid + (l - 1) * C + 32 * h);
-      uint32_t ph[16], pl[16], pg[16], pp[16];
+      const float4* b4 = l == 0 ? reinterpret_cast<const float4*>(a.bias1 + (int64_t)s * C + 16 * h)
+                                : reinterpret_cast<const float4*>(bhid + (l - 1) * C + 16 * h);
+      uint32_t ph[8], pl[8], pg[8], pp[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
+      for (int i = 0; i < 4; ++i) {
         const float4 bb = l == 0 ? __ldg(b4 + i) : b4[i];
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
@@ -268,48 +329,54 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mlp_grad_kernel(const MlpGradAr
           pp[2 * i + e] = ptx::pack_f16x2(da, db);
         }
       }
-      ptx::tmem_st16(tm_lane + MG_A_HI + 16 * h, ph);
-      ptx::tmem_st16(tm_lane + MG_A_LO + 16 * h, pl);
-      ptx::tmem_st16(tm_lane + MG_GP + 32 * l + 16 * h, pp);
-      uint8_t* gb8 = smem + ML.gbuf + (uint32_t)l * ML.gstride + (uint32_t)(4 * h) * MG_GROUP + (uint32_t)rloc * 16u;
-#pragma unroll
-      for (int g = 0; g < 4; ++g)
-        *reinterpret_cast<uint4*>(gb8 + g * MG_GROUP) = make_uint4(pg[4 * g], pg[4 * g + 1], pg[4 * g + 2], pg[4 * g + 3]);
+      ptx::tmem_st8(tm_lane + MG_A_HI + 8 * h, ph);
+      ptx::tmem_st8(tm_lane + MG_A_LO + 8 * h, pl);
+      ptx::tmem_st8(tm_lane + MG_GP + 32 * l + 8 * h, pp);
+      uint8_t* gb8 = smem + ML.gbuf + (uint32_t)l * ML.gstride + (uint32_t)(2 * h) * MG_GROUP + (uint32_t)rloc * 16u;
+      *reinterpret_cast<uint4*>(gb8) = make_uint4(pg[0], pg[1], pg[2], pg[3]);
+      *reinterpret_cast<uint4*>(gb8 + MG_GROUP) = make_uint4(pg[4], pg[5], pg[6], pg[7]);
       if (l < nh) hand([&] { mma_fwd(TL.off_hid + (uint32_t)(l * C * C * 2), C, C); });
       else hand([&] { mma_fwd(TL.off_out, C, Nout); });
+      MG_MARK(4 + 2 * l);
     }
 
-    // ---- output: clip mask and cotangent -> delta_net ----
+    // ---- output: clip mask and cotangent -> delta_net (16-column block h) ----
     wait();
-    {
+    MG_MARK(9);
+    if (fast) {
+      ptx::mbar_wait(bars + 3, phc);
+      phc ^= 1u;
+      pick16(cs, cv);
+    } else {
+      load16(a.cot, r, valid, cv);
+    }
+    if (h < Nout / 16) {
       const float us = sc[8 + nh + 1];
       float wgt = valid ? a.cot_scale : 0.f;
       if (a.step_w) wgt *= __ldg(a.step_w + s);
       if (a.row_w) wgt *= __ldg(a.row_w + (valid ? row : 0));
-      for (int b = h; b < Nout / 16; b += 2) {
-        uint32_t rr[16];
-        ptx::tmem_ld16(tm_lane + MG_D + 16 * b, rr);
-        ptx::tmem_wait_ld();
-        float dl[16];
+      uint32_t rr[16];
+      ptx::tmem_ld16(tm_lane + MG_D + 16 * h, rr);
+      ptx::tmem_wait_ld();
+      float dl[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const int j = 16 * b + i;
-          const float net = fmaf(__uint_as_float(rr[i]), us, bout[j]);
-          const float c = (j < d) ? __ldg(a.cot + r * d + j) * wgt : 0.f;
-          dl[i] = (a.clip > 0.f && !(fabsf(net) <= a.clip)) ? 0.f : c;
-        }
-        uint32_t ph[8], pl[8], pr[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          split_pack(dl[2 * i], dl[2 * i + 1], ph[i], pl[i]);
-          pr[i] = ptx::pack_f16x2(dl[2 * i], dl[2 * i + 1]);
-        }
-        ptx::tmem_st8(tm_lane + MG_A_HI + 8 * b, ph);
-        ptx::tmem_st8(tm_lane + MG_A_LO + 8 * b, pl);
-        uint8_t* db8 = smem + ML.dbuf + (uint32_t)(2 * b) * MG_GROUP + (uint32_t)rloc * 16u;
-        *reinterpret_cast<uint4*>(db8) = make_uint4(pr[0], pr[1], pr[2], pr[3]);
-        *reinterpret_cast<uint4*>(db8 + MG_GROUP) = make_uint4(pr[4], pr[5], pr[6], pr[7]);
+      for (int i = 0; i < 16; ++i) {
+        const int j = 16 * h + i;
+        const float net = fmaf(__uint_as_float(rr[i]), us, bout[j]);
+        const float c = cv[i] * wgt;
+        dl[i] = (a.clip > 0.f && !(fabsf(net) <= a.clip)) ? 0.f : c;
       }
+      uint32_t ph[8], pl[8], pr[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        split_pack(dl[2 * i], dl[2 * i + 1], ph[i], pl[i]);
+        pr[i] = ptx::pack_f16x2(dl[2 * i], dl[2 * i + 1]);
+      }
+      ptx::tmem_st8(tm_lane + MG_A_HI + 8 * h, ph);
+      ptx::tmem_st8(tm_lane + MG_A_LO + 8 * h, pl);
+      uint8_t* db8 = smem + ML.dbuf + (uint32_t)(2 * h) * MG_GROUP + (uint32_t)rloc * 16u;
+      *reinterpret_cast<uint4*>(db8) = make_uint4(pr[0], pr[1], pr[2], pr[3]);
+      *reinterpret_cast<uint4*>(db8 + MG_GROUP) = make_uint4(pr[4], pr[5], pr[6], pr[7]);
     }
     {
       const uint32_t acc0 = first ? 0u : 1u;
@@ -317,37 +384,39 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mlp_grad_kernel(const MlpGradAr
         mma_wgrad(gbuf_s + (uint32_t)nh * ML.gstride, MG_ACC + 64u * (uint32_t)(nh + 1), Nout, acc0);
         mma_bwd(TL.off_out, Nout);
       });
+      if (tid == 0 && next_fast) fetch(a.cot, ML.cstage, bars + 3, tile + 1);
     }
+    MG_MARK(10);
 
     // ---- backward: delta_l = (delta_{l+1} W) GELU'(v_l), l = nh + 1 .. 1 ----
     for (int l = nh + 1; l >= 1; --l) {
       wait();
+      MG_MARK(11 + 2 * (nh + 1 - l));
       const float ub = 1.0f / sc[l];  // the layer that consumes g_l (hidden layer l, or the output layer) is scaled by sc[l]
-      uint32_t rr[32], gp[16];
-      ptx::tmem_ld32(tm_lane + MG_D + 32 * h, rr);
-      ptx::tmem_ld16(tm_lane + MG_GP + 32 * (l - 1) + 16 * h, gp);
+      uint32_t rr[16], gp[8];
+      ptx::tmem_ld16(tm_lane + MG_D + 16 * h, rr);
+      ptx::tmem_ld8(tm_lane + MG_GP + 32 * (l - 1) + 8 * h, gp);
       ptx::tmem_wait_ld();
-      float dl[32];
+      float dl[16];
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
+      for (int i = 0; i < 8; ++i) {
         const float2 gd = __half22float2(*reinterpret_cast<const __half2*>(&gp[i]));
         dl[2 * i] = __uint_as_float(rr[2 * i]) * ub * gd.x;
         dl[2 * i + 1] = __uint_as_float(rr[2 * i + 1]) * ub * gd.y;
       }
-      uint32_t pr[16];
+      uint32_t pr[8];
       if (l > 1) {
-        uint32_t ph[16], pl[16];
+        uint32_t ph[8], pl[8];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) split_pack(dl[2 * i], dl[2 * i + 1], ph[i], pl[i]);
-        ptx::tmem_st16(tm_lane + MG_A_HI + 16 * h, ph);
-        ptx::tmem_st16(tm_lane + MG_A_LO + 16 * h, pl);
+        for (int i = 0; i < 8; ++i) split_pack(dl[2 * i], dl[2 * i + 1], ph[i], pl[i]);
+        ptx::tmem_st8(tm_lane + MG_A_HI + 8 * h, ph);
+        ptx::tmem_st8(tm_lane + MG_A_LO + 8 * h, pl);
       }
 #pragma unroll
-      for (int i = 0; i < 16; ++i) pr[i] = ptx::pack_f16x2(dl[2 * i], dl[2 * i + 1]);
-      uint8_t* db8 = smem + ML.dbuf + (uint32_t)(4 * h) * MG_GROUP + (uint32_t)rloc * 16u;
-#pragma unroll
-      for (int g = 0; g < 4; ++g)
-        *reinterpret_cast<uint4*>(db8 + g * MG_GROUP) = make_uint4(pr[4 * g], pr[4 * g + 1], pr[4 * g + 2], pr[4 * g + 3]);
+      for (int i = 0; i < 8; ++i) pr[i] = ptx::pack_f16x2(dl[2 * i], dl[2 * i + 1]);
+      uint8_t* db8 = smem + ML.dbuf + (uint32_t)(2 * h) * MG_GROUP + (uint32_t)rloc * 16u;
+      *reinterpret_cast<uint4*>(db8) = make_uint4(pr[0], pr[1], pr[2], pr[3]);
+      *reinterpret_cast<uint4*>(db8 + MG_GROUP) = make_uint4(pr[4], pr[5], pr[6], pr[7]);
       const uint32_t acc0 = first ? 0u : 1u;
       if (l > 1) {
         hand([&] {
@@ -356,26 +425,33 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mlp_grad_kernel(const MlpGradAr
         });
       } else {
         hand([&] { mma_wgrad(xbuf_s, MG_ACC, C, acc0); });
-        // dbias1 contribution of this warp's 32 rows: column sums by a reduce-scatter over the lanes
+        // dbias1 contribution of this warp's 32 rows: column sums of its 16 columns by a reduce-scatter over the lanes
+        // (four halvings leave column (lane >> 1) & 15 in every lane, the last exchange adds the two half sums)
 #pragma unroll
-        for (int stp = 0; stp < 5; ++stp) {
-          const int o = 16 >> stp, n = 16 >> stp;
+        for (int stp = 0; stp < 4; ++stp) {
+          const int o = 16 >> stp, n = 8 >> stp;
           const bool up = (lane & o) != 0;
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
+          for (int i = 0; i < 8; ++i) {
             if (i < n) {
               const float send = up ? dl[i] : dl[i + n], keep = up ? dl[i + n] : dl[i];
               dl[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
             }
           }
         }
-        a.dbias_part[(tile * 4 + q) * C + 32 * h + lane] = dl[0] * inv_cs;
+        dl[0] += __shfl_xor_sync(0xffffffffu, dl[0], 1);
+        if ((lane & 1) == 0) a.dbias_part[(tile * 4 + q) * C + 16 * h + (lane >> 1)] = dl[0] * inv_cs;
       }
+      MG_MARK(12 + 2 * (nh + 1 - l));
     }
     first = false;
     pending = true;
   }
   if (pending) wait();
+#ifdef LRDS_MG_TIMING
+  if (tm_on)
+    for (int i = 0; i < 24; ++i) g_mg_timing[(tid == 0 ? 0 : 24) + i] = tm_acc[i];
+#endif
 
   // ---- the CTA's accumulators -> its slice of `part` (layout of lrds_mlp: w_in_t, w_hid_t, b_hid, w_out_t, b_out) ----
   {
@@ -384,7 +460,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mlp_grad_kernel(const MlpGradAr
     const int o_hid = d * C, o_bhid = o_hid + nh * C * C, o_out = o_bhid + nh * C, o_bout = o_out + C * dp;
     for (int i = 0; i <= nh + 1; ++i) {
       const int ncol = i == nh + 1 ? Nout : C;
-      for (int c0 = 8 * h; c0 < ncol; c0 += 16) {
+      for (int c0 = 8 * h; c0 < ncol; c0 += 32) {
         uint32_t rr[8];
         ptx::tmem_ld8(tm_lane + MG_ACC + 64 * i + c0, rr);
         ptx::tmem_wait_ld();
@@ -476,7 +552,7 @@ int launch_mlp_grad(const lrds_mlp& mlp, const float* bias1, const float* x, con
   a.part = scratch;
   a.dbias_part = scratch + (int64_t)grid * a.P;
   const TcLayout TL = tc_layout(mlp.d, mlp.num_hidden, LRDS_PRECISION_F16X3);
-  const MgLayout ML = mg_layout(TL);
+  const MgLayout ML = mg_layout(TL, mlp.d);
   cudaError_t e = cudaFuncSetAttribute(mlp_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ML.bytes);
   if (e == cudaSuccess) {
     mlp_grad_kernel<<<grid, MG_THREADS, ML.bytes, st>>>(a);
@@ -495,3 +571,9 @@ int launch_mlp_grad(const lrds_mlp& mlp, const float* bias1, const float* x, con
 }
 
 }  // namespace lrds
+
+#ifdef LRDS_MG_TIMING
+extern "C" int lrds_debug_mlp_grad_timing(unsigned long long* host_out) {  // tools only
+  return (int)cudaMemcpyFromSymbol(host_out, lrds::g_mg_timing, sizeof(lrds::g_mg_timing));
+}
+#endif
