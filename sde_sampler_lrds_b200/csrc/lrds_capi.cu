@@ -394,8 +394,8 @@ __global__ void __launch_bounds__(128) distr_eval_kernel(const lrds_spec s, cons
 
 // ---- sum_b w_sb cot_sb (x) clip(score(x_sb)) per time slice s: the cotangent of the time-only factor of ScoreCtrl
 // (models/reparam.py:112-117: ctrl = clip(net) + scale * clip(score) * clip(TimeEmbed_score(t))) in the batched gradient
-// pass of train.py.  One thread per stored state; the columns are reduced over the warp, then over the block's warps;
-// every block writes its partial row (part[s][block][dp]) and score_cot_reduce_kernel adds them in a fixed order.
+// pass of train.py.  One thread per stored state; the products replace the staged cotangents in shared memory and the
+// block's columns are summed from there; every block writes its partial row (part[s][block][dp]) and score_cot_reduce_kernel adds them in a fixed order.
 // bytes of a mixture target staged in shared memory behind the particle columns (0: read from global memory)
 __host__ __device__ inline uint32_t score_cot_stage_bytes(const lrds_spec& s, uint32_t* logc_bytes) {
   if (s.target.kind != LRDS_DISTR_GMM || s.target.gmm.M < 2) return *logc_bytes = 0u;
@@ -406,11 +406,12 @@ __host__ __device__ inline uint32_t score_cot_stage_bytes(const lrds_spec& s, ui
 
 template <bool SH>
 __device__ __forceinline__ void score_cot_body(const lrds_spec& s, const lrds::GmmViewT<SH>& tv, const lrds::Particle& P,
-                                               const float* __restrict__ cot, int64_t row, float w, float clip,
-                                               float (*red)[lrds::JC], float* __restrict__ dst) {
+                                               float* __restrict__ rows, int ld, float w, float clip,
+                                               float* __restrict__ dst) {
   using namespace lrds;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nw = blockDim.x >> 5;
+  const int tid = threadIdx.x, NT = blockDim.x;
   const int d = s.d, dp = s.mlp.d_pad;
+  float* mine = rows + tid * ld;  // this thread's row of the staged cotangents; the products replace them in place
   target_pass1<SH>(s, s.target.kind, tv, P, false);
   float xm = 0.f;
   for (int j0 = 0; j0 < dp; j0 += JC) {
@@ -421,20 +422,23 @@ __device__ __forceinline__ void score_cot_body(const lrds_spec& s, const lrds::G
     xm = xr[JC - 1];
 #pragma unroll
     for (int c = 0; c < JC; ++c) {
-      float v = ts[c];
-      if (clip > 0.f) v = fminf(fmaxf(v, -clip), clip);
-      v *= (j0 + c < d) ? __ldg(cot + row * d + j0 + c) * w : 0.f;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-      if (lane == 0) red[warp][c] = v;
+      if (j0 + c < d) {
+        float v = ts[c];
+        if (clip > 0.f) v = fminf(fmaxf(v, -clip), clip);
+        mine[j0 + c] = v * mine[j0 + c] * w;
+      }
     }
-    __syncthreads();
-    if (tid < JC) {
-      float acc = red[0][tid];
-      for (int i = 1; i < nw; ++i) acc += red[i][tid];
-      dst[j0 + tid] = acc;
+  }
+  __syncthreads();
+  for (int j = tid; j < d; j += NT) {  // column sums over the block's rows, in row order
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;  // four chains (NT is a multiple of 32)
+    for (int p = 0; p < NT; p += 4) {
+      a0 += rows[p * ld + j];
+      a1 += rows[(p + 1) * ld + j];
+      a2 += rows[(p + 2) * ld + j];
+      a3 += rows[(p + 3) * ld + j];
     }
-    __syncthreads();
+    dst[j] = (a0 + a1) + (a2 + a3);
   }
 }
 
@@ -444,24 +448,58 @@ __global__ void __launch_bounds__(128) score_cot_kernel(const lrds_spec s, const
                                                         float* __restrict__ part) {
   using namespace lrds;
   extern __shared__ __align__(16) float smem[];
-  __shared__ float red[4][JC];
   const int NT = blockDim.x, tid = threadIdx.x;
   const int slice = blockIdx.y;
   const int b_raw = blockIdx.x * NT + tid;
   const bool live = b_raw < s.B;
   const int b = live ? b_raw : s.B - 1;
-  const int64_t row = (int64_t)slice * s.B + b;
   const ColLayout L = col_layout(s);
   const Particle P = make_particle(smem, L, NT, tid);
   const GmmView tv0 = gmm_at(s.target.gmm, 0);
   const int d = s.d, dp = s.mlp.d_pad;
-  for (int j = 0; j < dp; ++j) P.x(j) = (j < d) ? __ldg(x + row * d + j) : 0.f;
+  const int warp = tid >> 5, lane = tid & 31, nw = NT >> 5;
+  uint32_t logc_bytes;
+  const uint32_t stage_bytes = score_cot_stage_bytes(s, &logc_bytes);
+  // The block's rows are contiguous in global memory: the warps read them row by row (coalesced) into a padded
+  // row-major staging area and every thread then takes its own row from there (per-thread global reads of rows
+  // 4 d bytes apart cost 32 wavefronts per load).
+  float* rows = smem + (size_t)L.total * NT + stage_bytes / 4u;  // [NT][d + 1]
+  const int ld = d + 1;
+  auto stage_rows = [&](const float* __restrict__ src) {
+    for (int p0 = warp; p0 < NT; p0 += 8 * nw) {  // eight rows in flight per warp
+      float va[8], vb[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int p = p0 + i * nw;
+        const int bp = min(blockIdx.x * NT + (p < NT ? p : 0), s.B - 1);
+        const float* g = src + ((int64_t)slice * s.B + bp) * d;
+        va[i] = lane < d ? __ldg(g + lane) : 0.f;
+        vb[i] = lane + 32 < d ? __ldg(g + lane + 32) : 0.f;
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int p = p0 + i * nw;
+        if (p < NT) {
+          if (lane < d) rows[p * ld + lane] = va[i];
+          if (lane + 32 < d) rows[p * ld + lane + 32] = vb[i];
+        }
+      }
+      for (int j = lane + 64; j < d; j += 32)  // d > 64: the rest of the eight rows
+        for (int i = 0; i < 8; ++i) {
+          const int p = p0 + i * nw;
+          if (p < NT) rows[p * ld + j] = __ldg(src + ((int64_t)slice * s.B + min(blockIdx.x * NT + p, s.B - 1)) * d + j);
+        }
+    }
+  };
+  stage_rows(x);
+  __syncthreads();
+  for (int j = 0; j < dp; ++j) P.x(j) = (j < d) ? rows[tid * ld + j] : 0.f;
+  __syncthreads();
+  stage_rows(cot);
   float w = live ? 1.f : 0.f;
   if (step_w) w *= __ldg(step_w + slice);
   if (row_w) w *= __ldg(row_w + b);
   float* dst = part + ((int64_t)slice * gridDim.x + blockIdx.x) * dp;
-  uint32_t logc_bytes;
-  const uint32_t stage_bytes = score_cot_stage_bytes(s, &logc_bytes);
   if (stage_bytes) {  // mixture target: its (logc, sn) blocks go to shared memory once per block
     float4* stg = reinterpret_cast<float4*>(smem + (size_t)L.total * NT);
     const float4* g_logc = reinterpret_cast<const float4*>(tv0.logc.p);
@@ -470,9 +508,10 @@ __global__ void __launch_bounds__(128) score_cot_kernel(const lrds_spec s, const
     for (int i = tid; i < n_all; i += NT) stg[i] = i < n_logc ? __ldg(g_logc + i) : __ldg(g_sn + (i - n_logc));
     __syncthreads();
     const GmmViewT<true> tv = staged_view(reinterpret_cast<const uint8_t*>(stg), tv0, logc_bytes, stage_bytes - logc_bytes);
-    score_cot_body<true>(s, tv, P, cot, row, w, clip, red, dst);
+    score_cot_body<true>(s, tv, P, rows, ld, w, clip, dst);
   } else {
-    score_cot_body<false>(s, tv0, P, cot, row, w, clip, red, dst);
+    __syncthreads();
+    score_cot_body<false>(s, tv0, P, rows, ld, w, clip, dst);
   }
 }
 
@@ -674,6 +713,7 @@ int distr_spec(const lrds_distr* distr, int32_t d, int32_t B, lrds_spec* out) {
   s.mlp.d_pad = ((d + 7) / 8) * 8;
   s.target = *distr;
   s.ctrl_kind = LRDS_CTRL_CLIPPED;
+  s.precision = LRDS_PRECISION_F16X3;  // column layout without the fp32 network's activation columns (no network here)
   if (distr->kind == LRDS_DISTR_GMM) {
     if (int r = validate_gmm(distr->gmm, "distr")) return r;
   } else if (distr->kind == LRDS_DISTR_LOGREG) {
@@ -684,9 +724,9 @@ int distr_spec(const lrds_distr* distr, int32_t d, int32_t B, lrds_spec* out) {
   return LRDS_OK;
 }
 
-int score_cot_threads(const lrds_spec& s) {
+int score_cot_threads(const lrds_spec& s) {  // the columns + one padded row of the staging area per thread
   uint32_t lb;
-  return pick_threads(lrds::col_layout(s).total, max_optin_smem() - (int)score_cot_stage_bytes(s, &lb));
+  return pick_threads(lrds::col_layout(s).total + s.d + 1, max_optin_smem() - (int)score_cot_stage_bytes(s, &lb));
 }
 
 }  // namespace
@@ -714,7 +754,7 @@ int lrds_score_cot_sums(const lrds_distr* distr, int32_t d, const float* x, cons
   const int nt = score_cot_threads(s);
   if (nt == 0) return fail(LRDS_ERR_RESOURCES, "score_cot_sums: per-particle state does not fit in shared memory");
   uint32_t lb;
-  const size_t smem = (size_t)L.total * nt * sizeof(float) + score_cot_stage_bytes(s, &lb);
+  const size_t smem = (size_t)(L.total + d + 1) * nt * sizeof(float) + score_cot_stage_bytes(s, &lb);
   cudaError_t e0 = cudaFuncSetAttribute(score_cot_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e0 != cudaSuccess) return cuda_fail(e0, "cudaFuncSetAttribute");
   const int nblk = (B + nt - 1) / nt;
