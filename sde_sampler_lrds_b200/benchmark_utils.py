@@ -118,8 +118,9 @@ def default_config(solver_type: str, model_type: str, loss_type: str, target_det
             "use_ema": False, "ema_decay": 0.995, "ema_steps": 10, "clip_target": None, "target": target,
             "train_timesteps": {"_target_": get_timesteps, "_partial_": True, "start": 0.0, "end": None, "steps": 100},
             "generative_ctrl": _model_cfg(model_type, dim)}
+    # every solver YAML pulls the *_lv loss file and make_model only overrides loss.method: max_rnd stays 1e8 for 'kl' too
     em_loss = {"_target_": L.EMReferenceSDELoss, "method": loss_type, "traj_per_sample": 1,
-               "max_rnd": 1e8 if loss_type == "lv" else None, "sde_ctrl_noise": None, "sde_ctrl_dropout": None}
+               "max_rnd": 1e8, "sde_ctrl_noise": None, "sde_ctrl_dropout": None}
     name = solver_types[solver_type]
     if name == "vp_rds":
         sde = {"_target_": VP, "diff_coeff_sq_min": 0.1, "diff_coeff_sq_max": 20.0 if force_vp20 else 10.0,
@@ -136,7 +137,7 @@ def default_config(solver_type: str, model_type: str, loss_type: str, target_det
         base.update(solver=S.PIS, sde=sde, loss=em_loss, prior={"_target_": Delta, "dim": dim})
     elif name == "dds":
         loss = {"_target_": L.ExponentialIntegratorSDELoss, "method": loss_type, "traj_per_sample": 1,
-                "max_rnd": 1e8 if loss_type == "lv" else None, "alpha": 1.0, "sigma": 1.0}
+                "max_rnd": 1e8, "alpha": 1.0, "sigma": 1.0}
         base.update(solver=S.DDS, sde=None, loss=loss, prior={"_target_": IsotropicGauss, "dim": dim, "scale": "${loss.sigma}"})
         base["train_timesteps"].update(rescale_t="cosine", steps=None, end=6.4, dt=0.05)
     elif name == "cmcd":
@@ -147,8 +148,10 @@ def default_config(solver_type: str, model_type: str, loss_type: str, target_det
     elif name == "dis":  # conf/solver/dis.yaml + conf/loss/time_reversal[_lv].yaml
         sde = {"_target_": VP, "diff_coeff_sq_min": 0.1, "diff_coeff_sq_max": 20.0 if force_vp20 else 10.0,
                "scale_diff_coeff": 1.0, "terminal_t": 1.0}
+        if force_vp_cosine:  # conf/sde/vp_cos.yaml (make_model refuses it for DIS; the tree composes all the same)
+            sde = {"_target_": CosineVP, "c": 0.008, "scale_diff_coeff": 1.0, "terminal_t": 1.0}
         loss = {"_target_": L.TimeReversalLoss, "method": loss_type, "traj_per_sample": 1,
-                "max_rnd": 1e8 if loss_type == "lv" else None, "sde_ctrl_noise": None, "sde_ctrl_dropout": None}
+                "max_rnd": 1e8, "sde_ctrl_noise": None, "sde_ctrl_dropout": None}
         base.update(solver=S.Bridge, sde=sde, loss=loss,
                     prior={"_target_": IsotropicGauss, "dim": dim, "scale": "${sde.scale_diff_coeff}"})
     else:

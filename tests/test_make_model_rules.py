@@ -58,3 +58,57 @@ def test_default_config_resolves_the_yaml_defaults():
                                       force_vp20=True))
     assert c["solver"] is S.Bridge and c["loss"]["_target_"] is L.TimeReversalLoss and c["loss"]["max_rnd"] == 1e8
     assert c["sde"]["diff_coeff_sq_max"] == 20.0 and c["prior"]["scale"] == 1.0 and c["train_timesteps"]["end"] == 1.0
+
+
+# ---- default_config against the reference's composed YAML tree ------------------------------------------------------
+# tests/golden/conf_defaults.json = the trees Hydra composes for make_model's overrides (experiments/benchmark_utils.py:
+# 159-171), produced from /root/reference/conf by oracle/make_conf_golden.py.  Keys of the control plane that the product
+# does not carry (optimiser, logging / evaluation cadence, Sinkhorn, ...) are listed, not silently skipped.
+CONTROL_PLANE = ("optim.", "eval_freq", "eval_stddev_steps", "eval_interval", "eval_device", "eval_init",
+                 "ckpt_interval", "log_interval", "max_loss", "max_grad", "scale_loss")
+
+
+def _flatten(node, prefix="", out=None):
+    out = {} if out is None else out
+    for k, v in node.items():
+        if k.startswith("_wants"):  # product-internal wiring flags
+            continue
+        key = prefix + k
+        if isinstance(v, dict):
+            _flatten(v, key + ".", out)
+        else:
+            if k in ("_target_", "solver") and not isinstance(v, str):
+                v = v.__name__
+            out[key if k != "solver" else "solver._target_"] = v
+    return out
+
+
+def _golden():
+    import json
+    import os
+    return json.load(open(os.path.join(os.path.dirname(__file__), "golden", "conf_defaults.json")))
+
+
+SOLVER_KEY = {v: k for k, v in BU.solver_types.items()}
+MODEL_KEY = {"basic": "base_zero_init", "score": "target_informed_zero_init", "langevin_init": "target_informed_langevin_init",
+             "lerp": "target_informed_lerp_tempering"}
+
+
+@pytest.mark.parametrize("key", sorted(_golden()))
+def test_default_config_equals_the_composed_reference_yaml(key):
+    solver, model, method, target, sde = key.split("|")
+    want = {k: v for k, v in _golden()[key].items() if not k.startswith(CONTROL_PLANE)}
+    cfg = BU.default_config(SOLVER_KEY[solver], MODEL_KEY[model], method, {"name": target}, force_vp20=sde == "vp_20",
+                            force_vp_cosine=sde == "vp_cos")
+    BU._resolve(cfg)
+    got = _flatten(cfg)
+    if want.get("target.data_dir") is None:
+        got.pop("target.data_dir", None), want.pop("target.data_dir", None)
+    if cfg.get("sde") is None:
+        got.pop("sde", None)
+    got = {k: v for k, v in got.items() if k not in ("seed", "device")}  # conf/base.yaml, not part of the solver tree
+    missing = sorted(set(want) - set(got))
+    extra = sorted(set(got) - set(want))
+    assert not missing and not extra, (missing, extra)
+    diff = {k: (got[k], want[k]) for k in want if got[k] != want[k] and not (got[k] is None and want[k] is None)}
+    assert not diff, diff

@@ -15,6 +15,8 @@ hdr "logistic-regression CMCD kernel (rollout_cmcd_tc_kernel), sonar shape d = 6
     "ncu --set full ... -k regex:rollout_cmcd_tc_kernel -s 2 -c 1 python tools/shape_bench.py --precisions f16x3 --only 'cfg4 logreg sonar'" gpurun_out/cmcd_tc_summary.md profiles/${R}_cmcd_tc_summary.md
 hdr "MALA kernel (mala_kernel), mcmc_sample defaults over ManyModes d = 50" \
     "ncu --set full ... -k regex:mala_kernel -s 1 -c 1 python tools/mala_bench.py" gpurun_out/mala_summary.md profiles/${R}_mala_summary.md
+hdr "weight-gradient kernel (mlp_grad_kernel: forward recompute, backward-data and weight-gradient GEMMs on tcgen05), 13.1 M rows, d = 50" \
+    "ncu --set full ... -k regex:mlp_grad_kernel -s 1 -c 1 python tools/mlp_grad_bench.py" gpurun_out/mlp_grad_summary.md profiles/${R}_mlp_grad_summary.md
 python - "$R" <<'PY'
 import csv, collections, sys
 R=sys.argv[1]
@@ -37,5 +39,8 @@ cp gpurun_out/bench_final.json profiles/${R}_final_bench.json
 cp gpurun_out/bench_final_reference.json profiles/${R}_final_bench_reference.json
 cp gpurun_out/shapes_final.json profiles/${R}_shapes.json
 cp gpurun_out/mala_final.json profiles/${R}_mala_bench.json
+cp gpurun_out/mlp_grad_bench.json profiles/${R}_mlp_grad_bench.json
+cp gpurun_out/train_bench_final.json profiles/${R}_train_bench.json
+cp gpurun_out/train_phases.json profiles/${R}_train_phases.json
 python tools/sass_evidence.py > profiles/${R}_sass_evidence.txt
 python tools/precision_md.py gpurun_out/precision_final.json ${R} > profiles/${R}_precision.md

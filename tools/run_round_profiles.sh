@@ -16,6 +16,11 @@ $T 400 ncu --set full --clock-control none --import-source on -k regex:rollout_c
 tools/prof_report.sh gpurun_out/prof_cmcd_final.ncu-rep lrds_tc_f16x3 rollout_cmcd_tc_kernelILi4ELi0 30 > gpurun_out/cmcd_tc_summary.md 2>&1; rm -f gpurun_out/prof_cmcd_final.ncu-rep
 $T 400 ncu --set full --clock-control none --import-source on -k regex:mala_kernel -s 1 -c 1 -o gpurun_out/prof_mala_final -f python tools/mala_bench.py > gpurun_out/ncu_mala.log 2>&1; echo "ncu mala rc=$?"
 tools/prof_report.sh gpurun_out/prof_mala_final.ncu-rep lrds_capi mala_kernel 30 > gpurun_out/mala_summary.md 2>&1; rm -f gpurun_out/prof_mala_final.ncu-rep
+$T 400 ncu --set full --clock-control none --import-source on -k regex:mlp_grad_kernel -s 1 -c 1 -o gpurun_out/prof_mlp_grad_final -f python tools/mlp_grad_bench.py > gpurun_out/ncu_mlp_grad.log 2>&1; echo "ncu mlp_grad rc=$?"
+tools/prof_report.sh gpurun_out/prof_mlp_grad_final.ncu-rep lrds_mlp_grad mlp_grad_kernel 30 > gpurun_out/mlp_grad_summary.md 2>&1; rm -f gpurun_out/prof_mlp_grad_final.ncu-rep
+$T 200 python tools/mlp_grad_bench.py --json gpurun_out/mlp_grad_bench.json > gpurun_out/mlp_grad_bench.log 2>&1; echo "mlp_grad bench rc=$?"
+$T 400 python tools/train_bench.py --cpu-batch 512 --json gpurun_out/train_bench_final.json > gpurun_out/train_bench_final.log 2>&1; echo "train bench rc=$?"
+$T 200 python tools/train_phases.py --json gpurun_out/train_phases.json > gpurun_out/train_phases.log 2>&1; echo "train phases rc=$?"
 $T 600 python tools/shape_bench.py --precisions f16x3 --json gpurun_out/shapes_final.json > gpurun_out/shapes_final.log 2>&1; echo "shapes rc=$?"
 $T 600 python tools/precision_report.py --precisions fp32,tf32x3,f16x3,tf32,bf16 --json gpurun_out/precision_final.json > gpurun_out/precision_final.log 2>&1; echo "prec rc=$?"
 $T 120 python tools/mala_bench.py > gpurun_out/mala_final.json 2> gpurun_out/mala_final.err; echo "mala rc=$?"
