@@ -424,6 +424,34 @@ def other_workloads(dev, precision, flush):
             del built, x0
         except Exception as e:  # a shape that fails must not take the headline down with it
             out[key] = {"error": f"{type(e).__name__}: {e}"[:200]}
+    try:  # one LV training objective + gradient of the benchmark problem (rollout + lrds_mlp_grad + lrds_score_cot_sums)
+        from tests import cases as T
+        Bt, Kt = 65536, 200
+        built = Built(T.case_ei_many_modes(K=Kt, B=Bt), dev, precision)
+        x0 = torch.randn(Bt, 50, generator=torch.Generator().manual_seed(1)).to(dev)
+        params = list(built.ctrl.parameters())
+
+        def train_step(seed):
+            for q in params:
+                q.grad = None
+            loss, _ = built.train_loss(x0, None, seed=seed)
+            loss.backward()
+        for w in range(2):
+            train_step(w)
+        torch.cuda.synchronize(dev)
+        evs = [(torch.cuda.Event(True), torch.cuda.Event(True)) for _ in range(3)]
+        for i, (a, b) in enumerate(evs):
+            flush.fill_(i)
+            a.record()
+            train_step(10 + i)
+            b.record()
+        torch.cuda.synchronize(dev)
+        ms = sum(a.elapsed_time(b) for a, b in evs) / len(evs)
+        out["cfg2_lv_training_step"] = {"B": Bt, "K": Kt, "d": 50, "ms": ms, "particle_steps_per_s": Bt * Kt / (ms * 1e-3),
+                                        "what": "loss(ts, x, ...) + loss.backward(): rollout, lrds_mlp_grad, lrds_score_cot_sums"}
+        del built, x0
+    except Exception as e:
+        out["cfg2_lv_training_step"] = {"error": f"{type(e).__name__}: {e}"[:200]}
     return out
 
 

@@ -36,7 +36,9 @@ def _reference(m, taus, xs, cot, clip):
 
 @pytest.mark.parametrize("d,nh,B,S,clip,weighted", [
     (50, 2, 300, 3, None, False), (16, 2, 128, 2, 0.3, True), (61, 1, 1000, 4, 0.5, False), (2, 0, 77, 1, None, True),
-    (50, 2, 4096, 9, 1.0, True), (33, 2, 20000, 40, 0.8, True)])
+    (50, 2, 4096, 9, 1.0, True), (33, 2, 20000, 40, 0.8, True),
+    (50, 2, 1001, 3, 0.9, False),  # odd B: ragged last tiles, and slices that are not 16-byte aligned (no TMA staging)
+    (64, 2, 640, 2, None, False), (7, 1, 129, 5, 0.7, True)])
 def test_mlp_grad_matches_autograd(d, nh, B, S, clip, weighted):
     from sde_sampler_lrds_b200.models.mlp import FourierMLP
     from sde_sampler_lrds_b200.train import mlp_grad, time_embed_rows
