@@ -42,7 +42,13 @@ struct Col4 {
 
 // clip bounds arrive as "<= 0: no clip"; kernels turn that into +inf once so that a clip is two FMNMX
 __device__ __forceinline__ float clip_bound(float c) { return c > 0.f ? c : INFINITY; }
-__device__ __forceinline__ float clipb(float v, float bound) { return fminf(fmaxf(v, -bound), bound); }
+// clip(v, -bound, bound) for bound >= 0 (possibly +inf) as ONE instruction: min(|v|, bound) with v's sign (the bound's
+// sign bit is 0); NaN propagates like torch.clip
+__device__ __forceinline__ float clipb(float v, float bound) {
+  float r;
+  asm("min.NaN.xorsign.abs.f32 %0, %1, %2;" : "=f"(r) : "f"(v), "f"(bound));
+  return r;
+}
 __device__ __forceinline__ float clipf(float v, float c) { return c > 0.f ? fminf(fmaxf(v, -c), c) : v; }
 
 // Packed fp32x2 arithmetic (FFMA2 / FMUL2 on sm_100): one issue slot for two lanes of work.
