@@ -272,7 +272,9 @@ int lrds_ctrl_forward(const lrds_spec* spec, int32_t row, const float* x, int32_
  *                    (log-variance loss: cot = z, step_w = the Ito weights, row_w = d loss / d rnd_b)
  *   clip             bound of the output clip (<= 0: none): rows/columns with |net| > clip receive no gradient
  *   cot_scale        power of two applied to the cotangents before their fp16 operands are formed and removed from the
- *                    results: choose it so that max |cot * step_w * row_w| * cot_scale is of order 1 .. 10
+ *                    results: choose it so that max |cot * step_w * row_w| * cot_scale is of order 1 .. 10;
+ *   cot_scale_dev    optional device copy of that scalar (used instead when non-NULL: a caller whose bound lives on the
+ *                    device, e.g. max |d loss / d rnd|, avoids the host round trip)
  * Outputs: grads_out = lrds_mlp_grad_floats(d, num_hidden) floats laid out like the weight blocks of lrds_mlp
  * ([d][64] w_in_t, [nh][64][64] w_hid_t, [nh][64] b_hid, [64][d_pad] w_out_t, [d_pad] b_out) and dbias1_out [S][64] (the
  * cotangent of bias1: its column sums are the gradient of input_embed.bias, and TimeEmbed's backward takes it from
@@ -289,8 +291,8 @@ int lrds_score_cot_sums(const lrds_distr* distr, int32_t d, const float* x, cons
 int64_t lrds_mlp_grad_floats(int32_t d, int32_t num_hidden);
 int64_t lrds_mlp_grad_scratch_floats(int32_t d, int32_t num_hidden, int32_t S, int32_t B);
 int lrds_mlp_grad(const lrds_mlp* mlp, const float* bias1, const float* x, const float* cot, const float* step_w,
-                  const float* row_w, float clip, float cot_scale, int32_t S, int32_t B, float* grads_out,
-                  float* dbias1_out, float* scratch, void* stream);
+                  const float* row_w, float clip, float cot_scale, const float* cot_scale_dev, int32_t S, int32_t B,
+                  float* grads_out, float* dbias1_out, float* scratch, void* stream);
 /* Distribution.unnorm_log_prob / score (distr/base.py:128-157); either output may be NULL. */
 int lrds_distr_eval(const lrds_distr* distr, int32_t d, const float* x, int32_t B, float* logp_out,
                     float* score_out, void* stream);

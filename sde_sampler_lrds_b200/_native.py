@@ -160,7 +160,7 @@ def lib():
                 L.lrds_mlp_grad_floats.argtypes = [C.c_int32, C.c_int32]
                 L.lrds_mlp_grad_scratch_floats.restype = C.c_int64
                 L.lrds_mlp_grad_scratch_floats.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int32]
-                L.lrds_mlp_grad.argtypes = [C.POINTER(Mlp), FP, FP, FP, FP, FP, C.c_float, C.c_float, C.c_int32, C.c_int32,
+                L.lrds_mlp_grad.argtypes = [C.POINTER(Mlp), FP, FP, FP, FP, FP, C.c_float, C.c_float, FP, C.c_int32, C.c_int32,
                                             FP, FP, FP, FP]
                 L.lrds_score_cot_scratch_floats.restype = C.c_int64
                 L.lrds_score_cot_scratch_floats.argtypes = [C.POINTER(Distr), C.c_int32, C.c_int32, C.c_int32]

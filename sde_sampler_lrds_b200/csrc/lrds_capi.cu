@@ -935,11 +935,12 @@ int64_t lrds_mlp_grad_scratch_floats(int32_t d, int32_t num_hidden, int32_t S, i
   return lrds::mlp_grad_scratch_floats(d, num_hidden, S, B);
 }
 int lrds_mlp_grad(const lrds_mlp* mlp, const float* bias1, const float* x, const float* cot, const float* step_w,
-                  const float* row_w, float clip, float cot_scale, int32_t S, int32_t B, float* grads_out,
-                  float* dbias1_out, float* scratch, void* stream) {
-  if (!mlp || !bias1 || !x || !cot || !grads_out || !dbias1_out || !scratch || S < 1 || B < 1 || !(cot_scale > 0.f))
+                  const float* row_w, float clip, float cot_scale, const float* cot_scale_dev, int32_t S, int32_t B,
+                  float* grads_out, float* dbias1_out, float* scratch, void* stream) {
+  if (!mlp || !bias1 || !x || !cot || !grads_out || !dbias1_out || !scratch || S < 1 || B < 1 ||
+      (!cot_scale_dev && !(cot_scale > 0.f)))
     return fail(LRDS_ERR_INVALID, "mlp_grad: bad arguments");
-  const int r = lrds::launch_mlp_grad(*mlp, bias1, x, cot, step_w, row_w, clip, cot_scale, S, B, grads_out, dbias1_out,
+  const int r = lrds::launch_mlp_grad(*mlp, bias1, x, cot, step_w, row_w, clip, cot_scale, cot_scale_dev, S, B, grads_out, dbias1_out,
                                       scratch, (cudaStream_t)stream, g_err, sizeof(g_err));
   if (r == LRDS_OK) g_launches.fetch_add(2);
   return r;

@@ -17,6 +17,6 @@ bool mlp_grad_applicable(int d, int num_hidden);
 int mlp_grad_params(int d, int num_hidden);
 int64_t mlp_grad_scratch_floats(int d, int num_hidden, int S, int B);
 int launch_mlp_grad(const lrds_mlp& mlp, const float* bias1, const float* x, const float* cot, const float* step_w,
-                    const float* row_w, float clip, float cot_scale, int S, int B, float* grads, float* dbias1,
-                    float* scratch, cudaStream_t st, char* err, size_t n);
+                    const float* row_w, float clip, float cot_scale, const float* cot_scale_dev, int S, int B,
+                    float* grads, float* dbias1, float* scratch, cudaStream_t st, char* err, size_t n);
 }  // namespace lrds

@@ -74,6 +74,7 @@ struct MlpGradArgs {
   const float* step_w;  // [S] or null: cot is multiplied by step_w[s] row_w[b]
   const float* row_w;   // [B] or null
   float clip, cot_scale;
+  const float* cot_scale_dev;  // device copy of cot_scale (replaces it when given: no host round trip to choose it)
   int S, B, tiles_per_s;
   int64_t tiles;
   float* part;        // [grid][P]
@@ -225,7 +226,8 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mlp_grad_kernel(const MlpGradAr
     ptx::tc_fence_after();
   };
 
-  const float inv_cs = 1.0f / a.cot_scale;
+  const float cot_scale = a.cot_scale_dev ? __ldg(a.cot_scale_dev) : a.cot_scale;
+  const float inv_cs = 1.0f / cot_scale;
   bool first = true, pending = false;
 #ifdef LRDS_MG_TIMING
   const bool tm_on = blockIdx.x == 0 && (tid == 0 || tid == 32);
@@ -352,7 +354,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mlp_grad_kernel(const MlpGradAr
     }
     if (h < Nout / 16) {
       const float us = sc[8 + nh + 1];
-      float wgt = valid ? a.cot_scale : 0.f;
+      float wgt = valid ? cot_scale : 0.f;
       if (a.step_w) wgt *= __ldg(a.step_w + s);
       if (a.row_w) wgt *= __ldg(a.row_w + (valid ? row : 0));
       uint32_t rr[16];
@@ -530,8 +532,8 @@ int64_t mlp_grad_scratch_floats(int d, int nh, int S, int B) {
 }
 
 int launch_mlp_grad(const lrds_mlp& mlp, const float* bias1, const float* x, const float* cot, const float* step_w,
-                    const float* row_w, float clip, float cot_scale, int S, int B, float* grads, float* dbias1,
-                    float* scratch, cudaStream_t st, char* err, size_t n) {
+                    const float* row_w, float clip, float cot_scale, const float* cot_scale_dev, int S, int B,
+                    float* grads, float* dbias1, float* scratch, cudaStream_t st, char* err, size_t n) {
   if (!mlp_grad_applicable(mlp.d, mlp.num_hidden)) {
     snprintf(err, n, "mlp_grad: built for d <= 64 and at most 2 hidden layers (got d = %d, %d hidden)", mlp.d, mlp.num_hidden);
     return LRDS_ERR_UNSUPPORTED;
@@ -543,7 +545,7 @@ int launch_mlp_grad(const lrds_mlp& mlp, const float* bias1, const float* x, con
   MlpGradArgs a{};
   a.mlp = mlp;
   a.bias1 = bias1; a.x = x; a.cot = cot; a.step_w = step_w; a.row_w = row_w;
-  a.clip = clip; a.cot_scale = cot_scale;
+  a.clip = clip; a.cot_scale = cot_scale; a.cot_scale_dev = cot_scale_dev;
   a.S = S; a.B = B;
   a.tiles_per_s = (B + 127) / 128;
   a.tiles = (int64_t)S * a.tiles_per_s;

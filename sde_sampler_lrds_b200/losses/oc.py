@@ -142,11 +142,14 @@ class BaseOCLoss:
         if self.method == "lv_traj":
             rnd = rnd.reshape(self.traj_per_sample, -1, 1)
             mask = mask.reshape(self.traj_per_sample, -1, 1).all(dim=0)
-            self.n_filtered += self.traj_per_sample * (mask.numel() - mask.sum()).item()
-            loss = rnd[:, mask].var(dim=0).mean()
+            n_bad = (mask.numel() - mask.sum()).item()  # the one host round trip of the loss formula
+            self.n_filtered += self.traj_per_sample * n_bad
+            loss = (rnd if n_bad == 0 else rnd[:, mask]).var(dim=0).mean()
         else:
-            self.n_filtered += (mask.numel() - mask.sum()).item()
-            loss = rnd[mask].var() if self.method == "lv" else rnd[mask].mean()
+            n_bad = (mask.numel() - mask.sum()).item()
+            self.n_filtered += n_bad
+            kept = rnd if n_bad == 0 else rnd[mask]  # nothing filtered (the usual case): no boolean gather
+            loss = kept.var() if self.method == "lv" else kept.mean()
         return loss, {"train/n_filtered_cumulative": self.n_filtered}
 
     def _train(self, make_plan, x, noise=None, seed=None, particle_offset: int = 0, group=None):

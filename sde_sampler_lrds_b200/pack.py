@@ -194,6 +194,17 @@ class Plan:
     noise_steps: int = 0
     taus: torch.Tensor | None = None    # [K] host: the time the control is evaluated at in step k (training, train.py)
     ito_w: torch.Tensor | None = None   # [K] host: the weight of <g, z> in the log-weight of step k
+    dev_cache: dict = field(default_factory=dict)  # device copies of host-side rows, made once per plan (on_device)
+
+
+def on_device(plan: "Plan", name: str, device, make=None) -> torch.Tensor:
+    """Device copy of a host tensor of the plan (``plan.<name>`` or ``make()``), cached: a pageable host-to-device copy
+    synchronises the stream, which a training step must not do once per step."""
+    key = (name, str(device))
+    if key not in plan.dev_cache:
+        src = getattr(plan, name) if make is None else make()
+        plan.dev_cache[key] = src.to(device)
+    return plan.dev_cache[key]
 
 
 def ito_weights(table: torch.Tensor, ito_form: int) -> torch.Tensor:
@@ -240,7 +251,9 @@ def refresh_ctrl(plan: "Plan", info: CtrlInfo, device):
     spec.mlp = mlp
     plan.keep[0] = k
     table = next(t for t in plan.keep if isinstance(t, torch.Tensor) and hasattr(t, "_lrds_ctrl_taus"))
-    bias1, gamma = time_rows(info, table._lrds_ctrl_taus, table.device)
+    if not hasattr(table, "_lrds_ctrl_taus_dev"):  # one copy per plan: a pageable host-to-device copy drains the stream
+        table._lrds_ctrl_taus_dev = table._lrds_ctrl_taus.to(table.device)
+    bias1, gamma = time_rows(info, table._lrds_ctrl_taus_dev, table.device)
     table[:, N.STEP_BIAS1:N.STEP_BIAS1 + N.CHANNELS] = bias1
     table[:, N.STEP_GAMMA] = gamma
 

@@ -85,11 +85,12 @@ def pow2_scale(bound: float, target: float = 4.0) -> float:
 
 
 def mlp_grad(base, bias1: torch.Tensor, xs: torch.Tensor, cot: torch.Tensor, clip, step_w=None, row_w=None,
-             cot_bound: float | None = None):
+             cot_bound=None):
     """Gradient of  sum_{s,b} <cot_sb * step_w_s * row_w_b, clip(FourierMLP(t_s, x_sb))>  in the backbone's parameters,
     by the hand-written kernel: returns ({parameter: gradient} for input_embed.weight, hidden_layer.*, out_layer.*,
     dbias1 [S, 64]) where dbias1 is the cotangent of ``bias1`` = input_embed.bias + TimeEmbed(t_s) (the caller carries it
-    through TimeEmbed with autograd: S rows).  ``cot_bound`` >= max |cot * step_w * row_w| sets the fp16 operand scale."""
+    through TimeEmbed with autograd: S rows).  ``cot_bound`` >= max |cot * step_w * row_w| sets the fp16 operand scale: a
+    float, or a 0-dim DEVICE tensor (the scale is then formed on the device: no host synchronisation)."""
     dev = xs.device
     S, B, d = xs.shape
     nh = len(base.hidden_layer)
@@ -97,8 +98,18 @@ def mlp_grad(base, bias1: torch.Tensor, xs: torch.Tensor, cot: torch.Tensor, cli
     xs, cot = xs.contiguous(), cot.contiguous()
     bias1 = bias1.detach().to(dev, torch.float32).contiguous()
     if cot_bound is None:
-        cot_bound = float(cot.abs().max()) * (float(step_w.abs().max()) if step_w is not None else 1.0) * \
-            (float(row_w.abs().max()) if row_w is not None else 1.0)
+        cot_bound = cot.abs().max()
+        if step_w is not None:
+            cot_bound = cot_bound * step_w.abs().max().to(dev)
+        if row_w is not None:
+            cot_bound = cot_bound * row_w.abs().max()
+    scale, scale_dev = 1.0, None
+    if torch.is_tensor(cot_bound):  # 2^floor(log2(4 / bound)) on the device; 1 for a zero / non-finite bound
+        bnd = cot_bound.detach().to(dev, torch.float32).reshape(())
+        scale_dev = torch.exp2(torch.floor(torch.log2(4.0 / bnd)))
+        scale_dev = torch.where(torch.isfinite(scale_dev) & (scale_dev > 0), scale_dev, torch.ones_like(scale_dev)).reshape(1)
+    else:
+        scale = pow2_scale(float(cot_bound))
     L = N.lib()
     flat = torch.empty(int(L.lrds_mlp_grad_floats(d, nh)), device=dev, dtype=torch.float32)
     dbias1 = torch.empty(S, N.CHANNELS, device=dev, dtype=torch.float32)
@@ -107,7 +118,7 @@ def mlp_grad(base, bias1: torch.Tensor, xs: torch.Tensor, cot: torch.Tensor, cli
     rw = None if row_w is None else row_w.detach().to(dev, torch.float32).reshape(-1).contiguous()
     with torch.cuda.device(dev):
         N.check(L.lrds_mlp_grad(C.byref(mlp), N.ptr(bias1), N.ptr(xs), N.ptr(cot), N.ptr(sw), N.ptr(rw),
-                                float(clip) if clip is not None else 0.0, pow2_scale(cot_bound), S, B, N.ptr(flat),
+                                float(clip) if clip is not None else 0.0, scale, N.ptr(scale_dev), S, B, N.ptr(flat),
                                 N.ptr(dbias1), N.ptr(scratch), N.stream_ptr(dev)))
     Cc, dp = N.CHANNELS, mlp.d_pad
     w_in_t, w_hid_t, b_hid, w_out_t, b_out = flat.split([d * Cc, nh * Cc * Cc, nh * Cc, Cc * dp, dp])
@@ -152,11 +163,11 @@ def control_param_grads(info: pack.CtrlInfo, params, taus, xs, cot, step_w, row_
     by_param = {}
     with torch.enable_grad():
         bias1 = time_embed_rows(base.timestep_embed, taus) + base.input_embed.bias
-    bound = float(cot.abs().max()) if cot_max is None else cot_max
-    if step_w is not None:
-        bound *= float(step_w.abs().max())
+    bound = cot.abs().max() if cot_max is None else torch.full((), float(cot_max), device=xs.device)  # device scalars:
+    if step_w is not None:                                                                            # no host round trip
+        bound = bound * step_w.abs().max()
     if row_w is not None:
-        bound *= float(row_w.abs().max())
+        bound = bound * row_w.abs().max()
     kernel_grads, dbias1 = mlp_grad(base, bias1, xs, cot, info.clip_model, step_w, row_w, cot_bound=bound)
     by_param.update(kernel_grads)
     tp = [p for p in [*base.timestep_embed.parameters(), base.input_embed.bias] if p.requires_grad]
@@ -261,11 +272,14 @@ def lv_objective(loss_obj, plan: pack.Plan, info: pack.CtrlInfo, x: torch.Tensor
             (w,) = torch.autograd.grad(value, rnd_leaf)  # d loss / d rnd_b, zero for filtered particles
     params = [p for p in loss_obj.generative_ctrl.parameters() if p.requires_grad]
     grads: list = [None] * len(params)
-    taus = plan.taus.to(dev)
-    ito_w = plan.ito_w.to(dev)
-    coef = torch.zeros(K, N.STEP_BIAS1)
-    pack.dis_ctrl_rows(info, plan.taus, coef)
-    coef = coef.to(dev)
+    taus = pack.on_device(plan, "taus", dev)
+    ito_w = pack.on_device(plan, "ito_w", dev)
+
+    def dis_rows():  # time-only table columns of the DIS drift models (they do not depend on the parameters)
+        c = torch.zeros(K, N.STEP_BIAS1)
+        pack.dis_ctrl_rows(info, plan.taus, c)
+        return c
+    coef = pack.on_device(plan, "coef", dev, dis_rows)
     step_rows = max(1, max_rows // B)
 
     def score_of(k0, k1):  # the constant score factor of the control at the stored states of steps k0 .. k1 - 1
@@ -333,10 +347,10 @@ def cmcd_lv_objective(loss_obj, plan: pack.Plan, info: pack.CtrlInfo, x: torch.T
     params = [p for p in loss_obj.generative_ctrl.parameters() if p.requires_grad]
     grads: list = [None] * len(params)
     sde = loss_obj.sde
-    ts = plan.taus.to(dev)                      # [K + 1]
-    dt = (plan.taus[1:] - plan.taus[:-1]).to(dev)
+    ts = pack.on_device(plan, "taus", dev)      # [K + 1]
+    dt = pack.on_device(plan, "dt", dev, lambda: plan.taus[1:] - plan.taus[:-1])
     sig = sde.diff_coeff.to(dev)
-    frac = (plan.taus / sde.terminal_t.detach().cpu()).to(dev)
+    frac = pack.on_device(plan, "frac", dev, lambda: plan.taus / sde.terminal_t.detach().cpu())
     target, prior = sde.target_score.__self__, sde.prior_score.__self__
     rows = max(1, max_rows // B)
     gd, drift, tscore = [], [], []
