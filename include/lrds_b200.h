@@ -312,10 +312,13 @@ int lrds_normals(uint64_t seed, uint64_t particle_offset, int32_t stream_id, int
  *   y0 [C][d] initial states        step_size [C] in / out
  *   noise [n_warmup + n_steps][C][d] standard normals or NULL (in-kernel Philox, stream 0)
  *   unif  [n_warmup + n_steps][C] uniforms in (0, 1] of the accept test or NULL (Philox, stream 2)
- *   ys_out [n_steps][C][d] the chains after the warm-up      log_acc_out [n_warmup + n_steps][C] or NULL */
+ *   ys_out [n_steps][C][d] the chains after the warm-up      log_acc_out [n_warmup + n_steps][C] or NULL
+ *   sampler: LRDS_MCMC_MALA, or LRDS_MCMC_RWMH = the other branch of mcmc_sample: rwmh_step (additions/mcmc.py:258-290),
+ *   proposal y + step_size * z, acceptance on the log-density difference alone (no score is evaluated) */
+typedef enum { LRDS_MCMC_MALA = 0, LRDS_MCMC_RWMH = 1 } lrds_mcmc_sampler;
 int lrds_mala(const lrds_distr* target, int32_t d, int32_t C, int32_t n_warmup, int32_t n_steps, int32_t adapt,
-              const float* y0, float* step_size, const float* noise, const float* unif, uint64_t seed, float* ys_out,
-              float* log_acc_out, void* stream);
+              int32_t sampler, const float* y0, float* step_size, const float* noise, const float* unif, uint64_t seed,
+              float* ys_out, float* log_acc_out, void* stream);
 
 const char* lrds_last_error(void);
 int lrds_abi_version(void);

@@ -291,6 +291,35 @@ def run_reference_mala(case):
     return {"ys": torch.stack(ys), "step_size": step_size.detach().clone(), "log_acc": torch.stack(accs)}
 
 
+def run_reference_rwmh(case):
+    """The same driver loop with mcmc_type='rwmh' (benchmark_utils.py:308-314) around the reference's OWN rwmh_step, whose
+    torch.randn_like / torch.rand draws are replaced by the case's recorded ones."""
+    from sde_sampler.additions.mcmc import heuristics_step_size, rwmh_step
+    from tests.cases import mala_inputs
+    target = build_reference_target(None, case["target"])
+    y_init, noise, unif = mala_inputs(case)
+    step_size = case["step_size"] * torch.ones((y_init.shape[0], 1))
+    y = torch.autograd.Variable(y_init.clone(), requires_grad=True)
+    target_log_prob_y = target.unnorm_log_prob(y).flatten()
+    ys, accs = [], []
+    k = {"i": 0}
+    orig_randn_like, orig_rand = torch.randn_like, torch.rand
+    torch.randn_like = lambda t, **kw: noise[k["i"]].clone()
+    torch.rand = lambda shape, **kw: unif[k["i"]].clone()
+    try:
+        for step_id in range(case["n_warmup"] + case["n_steps"]):
+            k["i"] = step_id
+            y, target_log_prob_y, log_acc = rwmh_step(y=y, target_log_prob_y=target_log_prob_y,
+                                                      target_log_prob=target.unnorm_log_prob, step_size=step_size)
+            step_size = heuristics_step_size(step_size, log_acc)
+            accs.append(log_acc.detach().clone())
+            if step_id >= case["n_warmup"]:
+                ys.append(y.detach().clone())
+    finally:
+        torch.randn_like, torch.rand = orig_randn_like, orig_rand
+    return {"ys": torch.stack(ys), "step_size": step_size.detach().clone(), "log_acc": torch.stack(accs)}
+
+
 def run_reference_aux():
     """Small public interfaces next to the rollout: ``get_timesteps`` grids (utils/common.py:30-82) for every grid kind
     and SDE family the solvers build, and ``EulerIntegrator.integrate`` (eq/integrator.py:84-129) over a VP SDE with
@@ -332,7 +361,8 @@ def main(argv):
     if argv and argv[0] == "--mala":  # python -m oracle.make_golden --mala [case ...]
         from tests.cases import MALA_CASES
         for name in argv[1:] or list(MALA_CASES):
-            out = run_reference_mala(MALA_CASES[name]())
+            case = MALA_CASES[name]()
+            out = run_reference_rwmh(case) if case.get("mcmc_type") == "rwmh" else run_reference_mala(case)
             out["torch_version"] = str(torch.__version__)
             path = os.path.join(REPO, "tests", "golden", name + ".pt")
             torch.save(out, path)

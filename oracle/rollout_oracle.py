@@ -900,3 +900,29 @@ def mala_chains(target: dict, y_init, step_size: float, n_warmup: int, n_steps: 
             if k >= n_warmup:
                 ys.append(y.clone())
     return torch.stack(ys), h, torch.stack(accs)
+
+
+def rwmh_chains(target: dict, y_init, step_size: float, n_warmup: int, n_steps: int, noise, unif, adapt=True,
+                dtype=torch.float32):
+    """The same loop with mcmc_type='rwmh': rwmh_step (additions/mcmc.py:258-290) - proposal y + step_size z, acceptance
+    log u < log p(y') - log p(y) - on recorded draws.  Returns (ys [n_steps, C, d], step_size (C, 1), log_acc [S, C])."""
+    logp_fn, _ = make_target(_cast(target, dtype))
+    y = y_init.to(dtype).clone()
+    h = step_size * torch.ones((y.shape[0], 1), dtype=dtype)
+    logp = logp_fn(y).flatten()
+    ys, accs = [], []
+    with torch.no_grad():
+        for k in range(n_warmup + n_steps):
+            y_prop = y + h * noise[k].to(dtype)
+            logp_p = logp_fn(y_prop).flatten()
+            log_acc = logp_p - logp
+            mask = torch.log(unif[k].to(dtype)) < log_acc
+            y = torch.where(mask.view(-1, 1), y_prop, y)
+            logp = torch.where(mask, logp_p, logp)
+            if adapt:
+                h = heuristics_step_size(h, log_acc)
+            accs.append(log_acc)
+            if k >= n_warmup:
+                ys.append(y.clone())
+    return torch.stack(ys), h, torch.stack(accs)
+

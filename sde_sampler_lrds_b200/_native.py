@@ -31,6 +31,7 @@ UPDATE_AXPY, UPDATE_EM = range(2)
 ITO_NONE, ITO_SCALED, ITO_EM, ITO_DDS = range(4)
 CTRL_CLIPPED, CTRL_SCORE, CTRL_CANCEL_DRIFT, CTRL_LERP = range(4)
 DISTR_NONE, DISTR_GMM, DISTR_PHI4, DISTR_LOGREG = range(4)
+MCMC_MALA, MCMC_RWMH = 0, 1
 PRECISION_FP32_SIMT, PRECISION_TF32X3, PRECISION_BF16, PRECISION_TF32, PRECISION_F16X3 = range(5)
 PRECISIONS = {"fp32": PRECISION_FP32_SIMT, "tf32x3": PRECISION_TF32X3, "bf16": PRECISION_BF16, "tf32": PRECISION_TF32,
               "f16x3": PRECISION_F16X3}
@@ -153,7 +154,7 @@ def lib():
                 L.lrds_ctrl_forward.argtypes = [C.POINTER(Spec), C.c_int32, FP, C.c_int32, FP, FP]
                 L.lrds_distr_eval.argtypes = [C.POINTER(Distr), C.c_int32, FP, C.c_int32, FP, FP, FP]
                 L.lrds_axpy_step.argtypes = [FP, FP, FP, C.c_float, C.c_float, C.c_float, FP, C.c_int64, FP]
-                L.lrds_mala.argtypes = [C.POINTER(Distr), C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, FP, FP, FP, FP,
+                L.lrds_mala.argtypes = [C.POINTER(Distr), C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, FP, FP, FP, FP,
                                         C.c_uint64, FP, FP, FP]
                 L.lrds_normals.argtypes = [C.c_uint64, C.c_uint64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, FP, FP]
                 L.lrds_mlp_grad_floats.restype = C.c_int64

@@ -16,14 +16,17 @@ from ..distr.base import Distribution
 
 def mala_chains(target: Distribution, y_init: torch.Tensor, step_size, n_warmup_steps: int, n_mcmc_steps: int,
                 adapt_step_size: bool = True, noise: torch.Tensor | None = None, unif: torch.Tensor | None = None,
-                seed: int | None = None, return_log_acc: bool = False):
-    """Runs ``n_warmup_steps + n_mcmc_steps`` MALA steps of ``y_init.shape[0]`` chains.
+                seed: int | None = None, return_log_acc: bool = False, mcmc_type: str = "mala"):
+    """Runs ``n_warmup_steps + n_mcmc_steps`` MALA steps of ``y_init.shape[0]`` chains (``mcmc_type='rwmh'``: random-walk
+    Metropolis-Hastings steps, rwmh_step of sde_sampler/additions/mcmc.py:258-290 - the other sampler of mcmc_sample).
 
     Returns (ys [n_mcmc_steps, C, d], step_size [C, 1]) and, with ``return_log_acc``, the log acceptance ratios
     [n_warmup_steps + n_mcmc_steps, C].  ``noise`` [S, C, d] / ``unif`` [S, C] replay recorded draws (validation mode);
     otherwise the kernel draws them with its counter-based generator keyed by ``seed``."""
     if not isinstance(target, Distribution):
         raise NotImplementedError("mala_chains needs a kernel-backed Distribution as target")
+    if mcmc_type not in ("mala", "rwmh"):
+        raise NotImplementedError(f"mcmc_type {mcmc_type!r}: the kernel runs 'mala' and 'rwmh' (the two samplers of mcmc_sample)")
     if not y_init.is_cuda:
         raise N.LrdsError("MALA runs on CUDA tensors only (no CPU fallback)")
     dev = y_init.device
@@ -48,7 +51,7 @@ def mala_chains(target: Distribution, y_init: torch.Tensor, step_size, n_warmup_
     log_acc = torch.empty(S, Cn, device=dev, dtype=torch.float32) if return_log_acc else None
     with torch.cuda.device(dev):
         N.check(N.lib().lrds_mala(C.byref(distr), d, Cn, int(n_warmup_steps), int(n_mcmc_steps), int(bool(adapt_step_size)),
-                                  N.ptr(y0), N.ptr(h), N.ptr(noise), N.ptr(unif), C.c_uint64(seed & (2 ** 64 - 1)),
+                                  N.MCMC_RWMH if mcmc_type == "rwmh" else N.MCMC_MALA, N.ptr(y0), N.ptr(h), N.ptr(noise), N.ptr(unif), C.c_uint64(seed & (2 ** 64 - 1)),
                                   N.ptr(ys), N.ptr(log_acc), N.stream_ptr(dev)))
     del keep
     out = (ys, h.unsqueeze(-1))

@@ -178,8 +178,8 @@ def mcmc_sample(device, target, x_init, mcmc_type="mala", step_size=1e-3, n_chai
     """experiments/benchmark_utils.py:268-333 with the chain loop in one kernel launch (additions/mcmc.py).  Returns the
     [n_mcmc_steps * n_chains, d] dataset on the CPU like the reference."""
     from .additions.mcmc import mala_chains
-    if mcmc_type != "mala":
-        raise NotImplementedError("only the MALA sampler has a kernel (the shipped experiments use mcmc_type='mala')")
+    if mcmc_type not in ("mala", "rwmh"):  # the reference runs rwmh_step for every other value (benchmark_utils.py:308-314)
+        raise NotImplementedError("mcmc_type must be 'mala' or 'rwmh'")
     if target_log_prob_and_grad is not None:
         raise NotImplementedError("a custom target_log_prob_and_grad cannot run inside the kernel; pass a Distribution")
     x_init = x_init.to(device)
@@ -189,7 +189,8 @@ def mcmc_sample(device, target, x_init, mcmc_type="mala", step_size=1e-3, n_chai
         y_init = torch.concat([x_init[i].unsqueeze(0).expand((n_chains_per_mode, -1)) for i in range(x_init.shape[0])], dim=0)
     n_chains = y_init.shape[0]
     n_mcmc_steps = int(dataset_length / n_chains)
-    ys, _ = mala_chains(target, y_init, step_size, n_warmup_steps, n_mcmc_steps, adapt_step_size=adapt_step_size, seed=seed)
+    ys, _ = mala_chains(target, y_init, step_size, n_warmup_steps, n_mcmc_steps, adapt_step_size=adapt_step_size, seed=seed,
+                        mcmc_type=mcmc_type)
     ret = ys.cpu().view((-1, *x_init.shape[1:]))
     return ret[torch.randperm(ret.shape[0])] if shuffle else ret
 

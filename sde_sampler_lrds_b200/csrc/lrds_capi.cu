@@ -535,7 +535,7 @@ struct MalaArgs {
   uint64_t seed;
   float* ys;            // [n_steps][C][d] states after the warm-up
   float* log_acc;       // [S][C] or NULL
-  int n_warmup, n_steps, adapt;
+  int n_warmup, n_steps, adapt, sampler;
   float log_target, up_thr, down_thr, factor;  // log(0.75), log1p(tol), -log1p(-tol), 1.01
 };
 
@@ -571,11 +571,12 @@ __global__ void __launch_bounds__(128) mala_kernel(const lrds_spec s, const Mala
     P.x(j) = v;
     P.us(j) = v;
   }
-  float logp = eval(P.tsd);
+  const bool rwmh = m.sampler == LRDS_MCMC_RWMH;
+  float logp = rwmh ? target_pass1<false>(s, kind, tv0, P, true) : eval(P.tsd);
   float h = __ldg(m.step_size + b);
   const int S = m.n_warmup + m.n_steps;
   for (int step = 0; step < S; ++step) {
-    // proposal y' = sqrt(2 h) z + (y + h grad)   (mcmc.py:8-14, 98-102)
+    // proposal: MALA y' = sqrt(2 h) z + (y + h grad) (mcmc.py:8-14, 98-102);  RWMH y' = y + h z (mcmc.py:275-277)
     const float var = 2.0f * h, sq = sqrtf(var);
     float fwd = 0.f;
     for (int j0 = 0; j0 < dp; j0 += JC) {
@@ -584,21 +585,31 @@ __global__ void __launch_bounds__(128) mala_kernel(const lrds_spec s, const Mala
 #pragma unroll
       for (int c = 0; c < JC; ++c) {
         const int j = j0 + c;
-        const float mean = P.us(j) + h * P.tsd(j);
-        const float yp = (j < d) ? sq * z[c] + mean : 0.f;
-        P.x(j) = yp;
-        const float df = yp - mean;
-        fwd += df * df;
+        if (rwmh) {
+          P.x(j) = (j < d) ? P.us(j) + h * z[c] : 0.f;
+        } else {
+          const float mean = P.us(j) + h * P.tsd(j);
+          const float yp = (j < d) ? sq * z[c] + mean : 0.f;
+          P.x(j) = yp;
+          const float df = yp - mean;
+          fwd += df * df;
+        }
       }
     }
-    const float logp_p = eval(P.db);
-    float bwd = 0.f;
-    for (int j = 0; j < d; ++j) {
-      const float df = P.us(j) - (P.x(j) + h * P.db(j));
-      bwd += df * df;
+    float logp_p, log_acc;
+    if (rwmh) {  // the Metropolis ratio of a symmetric proposal (mcmc.py:279-281); no score
+      logp_p = target_pass1<false>(s, kind, tv0, P, true);
+      log_acc = logp_p - logp;
+    } else {
+      logp_p = eval(P.db);
+      float bwd = 0.f;
+      for (int j = 0; j < d; ++j) {
+        const float df = P.us(j) - (P.x(j) + h * P.db(j));
+        bwd += df * df;
+      }
+      // joint_prop - joint_orig with the unnormalised Gaussian log-densities of mcmc.py:17-31
+      log_acc = (logp_p - (-0.5f * fwd) / var) - (logp - (-0.5f * bwd) / var);
     }
-    // joint_prop - joint_orig with the unnormalised Gaussian log-densities of mcmc.py:17-31
-    const float log_acc = (logp_p - (-0.5f * fwd) / var) - (logp - (-0.5f * bwd) / var);
     float u;
     if (m.unif != nullptr) {
       u = __ldg(m.unif + (int64_t)step * s.B + b);
@@ -952,9 +963,10 @@ int lrds_distr_eval(const lrds_distr* distr, int32_t d, const float* x, int32_t 
 }
 
 int lrds_mala(const lrds_distr* target, int32_t d, int32_t C, int32_t n_warmup, int32_t n_steps, int32_t adapt,
-              const float* y0, float* step_size, const float* noise, const float* unif, uint64_t seed, float* ys_out,
-              float* log_acc_out, void* stream) {
-  if (!target || !y0 || !step_size || !ys_out || d < 1 || C < 1 || n_warmup < 0 || n_steps < 1)
+              int32_t sampler, const float* y0, float* step_size, const float* noise, const float* unif, uint64_t seed,
+              float* ys_out, float* log_acc_out, void* stream) {
+  if (!target || !y0 || !step_size || !ys_out || d < 1 || C < 1 || n_warmup < 0 || n_steps < 1 ||
+      (sampler != LRDS_MCMC_MALA && sampler != LRDS_MCMC_RWMH))
     return fail(LRDS_ERR_INVALID, "mala: bad arguments");
   lrds_spec s;
   memset(&s, 0, sizeof(s));
@@ -983,7 +995,7 @@ int lrds_mala(const lrds_distr* target, int32_t d, int32_t C, int32_t n_warmup, 
     smem = (size_t)L.total * nt * sizeof(float);
   }
   const float tol = 0.05f, target_acc = 0.75f;
-  MalaArgs m{y0, step_size, noise, unif, seed, ys_out, log_acc_out, n_warmup, n_steps, adapt,
+  MalaArgs m{y0, step_size, noise, unif, seed, ys_out, log_acc_out, n_warmup, n_steps, adapt, sampler,
              logf(target_acc), log1pf(tol), -log1pf(-tol), 1.01f};
   mala_kernel<<<(C + nt - 1) / nt, nt, smem, st>>>(s, m);
   cudaError_t e = cudaGetLastError();

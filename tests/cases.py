@@ -521,8 +521,17 @@ def case_mala(target="many_modes"):
             "seed": 300 + len(target)}
 
 
+def case_rwmh(target="many_modes"):
+    """The same chains with mcmc_type='rwmh' (rwmh_step, additions/mcmc.py:258-290); step sizes in the range where the
+    random walk accepts about half of its proposals."""
+    case = case_mala(target)
+    case.update(mcmc_type="rwmh", step_size={"many_modes": 0.25, "phi4": 0.02, "logreg": 0.02}[target], seed=case["seed"] + 50)
+    return case
+
+
 MALA_CASES = {"mala_many_modes": lambda: case_mala("many_modes"), "mala_phi4": lambda: case_mala("phi4"),
-              "mala_logreg": lambda: case_mala("logreg")}
+              "mala_logreg": lambda: case_mala("logreg"), "rwmh_many_modes": lambda: case_rwmh("many_modes"),
+              "rwmh_phi4": lambda: case_rwmh("phi4"), "rwmh_logreg": lambda: case_rwmh("logreg")}
 
 
 def mala_inputs(case: dict):

@@ -1,4 +1,5 @@
-"""MALA chains (lrds_mala; sde_sampler/additions/mcmc.py + the mcmc_sample loop of experiments/benchmark_utils.py).
+"""MALA and random-walk Metropolis chains (lrds_mala; sde_sampler/additions/mcmc.py: mala_step 75-134, rwmh_step 258-290
++ the mcmc_sample loop of experiments/benchmark_utils.py).
 
 CPU: the oracle's restatement against outputs of the reference's own mala_step / heuristics_step_size
 (tests/golden/mala_*.pt, oracle/make_golden.py --mala) on identical draws.  GPU: the one-launch kernel against both.
@@ -16,6 +17,10 @@ from tests.cases import MALA_CASES, mala_inputs
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
 
 
+def oracle_chains(case, *a, **k):
+    return (O.rwmh_chains if case.get("mcmc_type") == "rwmh" else O.mala_chains)(*a, **k)
+
+
 def chains_within(got, want, tol=1e-4):
     """fraction of chains whose whole path ys[:, c, :] agrees within tol relative (denominator max(|want|, 1))."""
     err = ((got - want).abs() / want.abs().clamp(min=1.0)).amax(dim=(0, 2))
@@ -27,7 +32,7 @@ def test_oracle_mala_matches_reference_golden(name):
     case = MALA_CASES[name]()
     gold = torch.load(os.path.join(GOLDEN, name + ".pt"))
     y_init, noise, unif = mala_inputs(case)
-    ys, h, acc = O.mala_chains(case["target"], y_init, case["step_size"], case["n_warmup"], case["n_steps"], noise, unif)
+    ys, h, acc = oracle_chains(case, case["target"], y_init, case["step_size"], case["n_warmup"], case["n_steps"], noise, unif)
     assert ys.shape == gold["ys"].shape
     f, worst = chains_within(ys, gold["ys"])
     assert f >= 0.9, (f, worst)
@@ -44,8 +49,8 @@ def test_mala_kernel_matches_oracle_and_reference(name, device):
     y_init, noise, unif = mala_inputs(case)
     target = build_target(case["target"], device)
     ys, h, acc = mala_chains(target, y_init.to(device), case["step_size"], case["n_warmup"], case["n_steps"],
-                             noise=noise, unif=unif, return_log_acc=True)
-    yo, ho, ao = O.mala_chains(case["target"], y_init, case["step_size"], case["n_warmup"], case["n_steps"], noise, unif)
+                             noise=noise, unif=unif, return_log_acc=True, mcmc_type=case.get("mcmc_type", "mala"))
+    yo, ho, ao = oracle_chains(case, case["target"], y_init, case["step_size"], case["n_warmup"], case["n_steps"], noise, unif)
     assert ys.shape == gold["ys"].shape and h.shape == (y_init.shape[0], 1) and torch.isfinite(ys).all()
     for want, what in ((yo, "oracle"), (gold["ys"], "reference")):
         f, worst = chains_within(ys.cpu(), want)
@@ -91,8 +96,12 @@ def test_mcmc_sample_api(device):
     # every sample sits within a few standard deviations of one of the modes
     dist = torch.cdist(data, case["target"]["loc"]).min(dim=1).values
     assert dist.max() < 6.0 * (0.5 * 10) ** 0.5
+    rw = BU.mcmc_sample(device, target, case["x_init"], mcmc_type="rwmh", step_size=0.2, n_chains_per_mode=4,
+                        dataset_length=1400, n_warmup_steps=64, seed=6)
+    assert rw.shape == (1400, 10) and torch.isfinite(rw).all()
+    assert torch.cdist(rw, case["target"]["loc"]).min(dim=1).values.max() < 6.0 * (0.5 * 10) ** 0.5
     with pytest.raises(NotImplementedError):
-        BU.mcmc_sample(device, target, case["x_init"], mcmc_type="rwmh")
+        BU.mcmc_sample(device, target, case["x_init"], mcmc_type="ula")
     # the reference-fitting workflow of the experiments: MCMC data -> diagonal GMM by EM -> RDS with that reference
     weights, means, variances = BU.fit_gmm(7, data, means_init=case["x_init"])
     assert weights.shape == (7,) and means.shape == (7, 10) and variances.shape == (7, 10) and (variances > 0).all()
