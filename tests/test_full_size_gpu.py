@@ -108,3 +108,55 @@ def _full_size_eubo(built, case, x0, seed, off, device):
     ro = O.rollout(p, x0[lo:lo + N_CHECK], noise.cpu(), eubo=True)
     er = ((rv.cpu() - ro).abs() / ro.abs().clamp(min=1.0)).reshape(-1)
     assert er.max().item() <= 1e-4, f"rnd: worst {er.max().item():.2e}"
+
+
+def test_full_size_training_gradient_is_tied_to_small_batches(device):
+    """The LV gradient of a benchmark-size training step (K = 200, B = 65 536: 13.1 M stored states through lrds_mlp_grad
+    and lrds_score_cot_sums).  The loss is a variance over the batch, so the gradient is not a sum over particles - but
+    the two kernels' outputs ARE sums over rows: with the per-particle weights d loss / d rnd fixed, the full-size pass
+    must equal the sum of the passes over the two halves of the batch (size-independent additivity), and one half is
+    compared with fp32 torch autograd over the same rows (the pass the fixtures of tests/test_train_gpu.py pin at small
+    sizes)."""
+    from sde_sampler_lrds_b200 import train as TR
+    from tests.product_builders import Built
+    K, B, d = 200, 65536, 50
+    case = T.case_ei_many_modes(K=K, B=B)
+    built = Built(case, device, "f16x3")
+    info = built.loss._ctrl(False)
+    base = info.base
+    g = torch.Generator().manual_seed(5)
+    xs = (torch.randn(K, B, d, generator=g) * 3.0).to(device)
+    z = torch.randn(K, B, d, generator=g).to(device)
+    w = (torch.randn(B, generator=g) * 1e-4).to(device)
+    ito = (torch.rand(K, generator=g) * 0.2 + 0.05).to(device)
+    taus = torch.linspace(0.01, 0.99, K, device=device)
+    with torch.no_grad():
+        bias1 = TR.time_embed_rows(base.timestep_embed, taus) + base.input_embed.bias
+    bound = 7.0 * float(ito.max()) * float(w.abs().max())
+    full, db_full = TR.mlp_grad(base, bias1, xs, z, info.clip_model, ito, w, cot_bound=bound)
+    h = B // 2
+    parts = [TR.mlp_grad(base, bias1, xs[:, lo:lo + h].contiguous(), z[:, lo:lo + h].contiguous(), info.clip_model, ito,
+                         w[lo:lo + h], cot_bound=bound) for lo in (0, h)]
+    for p_, gfull in full.items():
+        gsum = parts[0][0][p_] + parts[1][0][p_]
+        assert ((gfull - gsum).abs().max() / gfull.abs().max()) < 1e-5
+    assert ((db_full - (parts[0][1] + parts[1][1])).abs().max() / db_full.abs().max()) < 1e-5
+    m_full = TR.score_cot_sums(info.target, xs, z, info.clip_score, ito, w)
+    m_half = sum(TR.score_cot_sums(info.target, xs[:, lo:lo + h].contiguous(), z[:, lo:lo + h].contiguous(), info.clip_score,
+                                   ito, w[lo:lo + h]) for lo in (0, h))
+    assert ((m_full - m_half).abs().max() / m_full.abs().max()) < 1e-5
+    # one time slice of the full-size pass against fp32 autograd over the same 65 536 rows
+    k = 37
+    params = [p_ for p_ in base.parameters() if p_.requires_grad]
+    with torch.enable_grad():
+        emb = base.input_embed(xs[k]) + TR.time_embed_rows(base.timestep_embed, taus[k:k + 1])
+        for layer in base.hidden_layer:
+            emb = layer(torch.nn.functional.gelu(emb))
+        net = base.out_layer(torch.nn.functional.gelu(emb))
+        if info.clip_model is not None:
+            net = net.clip(-info.clip_model, info.clip_model)
+        ref = dict(zip(params, torch.autograd.grad((z[k] * (ito[k] * w)[:, None] * net).sum(), params, allow_unused=True)))
+    one, _ = TR.mlp_grad(base, bias1[k:k + 1], xs[k:k + 1].contiguous(), z[k:k + 1].contiguous(), info.clip_model, ito[k:k + 1],
+                         w, cot_bound=bound)
+    for p_, gk in one.items():
+        assert ((gk - ref[p_]).norm() / ref[p_].norm()) < 1e-3
