@@ -137,14 +137,15 @@ def test_full_size_training_gradient_is_tied_to_small_batches(device):
     h = B // 2
     parts = [TR.mlp_grad(base, bias1, xs[:, lo:lo + h].contiguous(), z[:, lo:lo + h].contiguous(), info.clip_model, ito,
                          w[lo:lo + h], cot_bound=bound) for lo in (0, h)]
+    # (the sums run over 13.1 M random-sign terms in fp32 and in a different order: rounding ~ 6e-8 sqrt(N) ~ 2e-4 of the result)
     for p_, gfull in full.items():
         gsum = parts[0][0][p_] + parts[1][0][p_]
-        assert ((gfull - gsum).abs().max() / gfull.abs().max()) < 1e-5
-    assert ((db_full - (parts[0][1] + parts[1][1])).abs().max() / db_full.abs().max()) < 1e-5
+        assert ((gfull - gsum).abs().max() / gfull.abs().max()) < 1e-3, float((gfull - gsum).abs().max() / gfull.abs().max())
+    assert ((db_full - (parts[0][1] + parts[1][1])).abs().max() / db_full.abs().max()) < 1e-3
     m_full = TR.score_cot_sums(info.target, xs, z, info.clip_score, ito, w)
     m_half = sum(TR.score_cot_sums(info.target, xs[:, lo:lo + h].contiguous(), z[:, lo:lo + h].contiguous(), info.clip_score,
                                    ito, w[lo:lo + h]) for lo in (0, h))
-    assert ((m_full - m_half).abs().max() / m_full.abs().max()) < 1e-5
+    assert ((m_full - m_half).abs().max() / m_full.abs().max()) < 1e-3
     # one time slice of the full-size pass against fp32 autograd over the same 65 536 rows
     k = 37
     params = [p_ for p_ in base.parameters() if p_.requires_grad]

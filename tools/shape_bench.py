@@ -60,6 +60,18 @@ def dis(target, ctrl_kind, B, K=200):
     return case
 
 
+def fitted_ref(B):
+    """Config 2 with a reference whose components carry their OWN variances and slightly displaced means - what
+    fit_gmm (sklearn EM on MCMC samples, experiments/benchmark_utils.py:336-370) returns: the reference's
+    responsibilities then take the exact quadratic forms (the logit GEMM serves shared-variance mixtures)."""
+    case = T.case_ei_many_modes(K=200, B=B)
+    g = torch.Generator().manual_seed(9)
+    ref = case["problem"]["ref"]
+    ref["variances"] = ref["variances"] * (1.0 + 0.3 * (torch.rand(ref["variances"].shape, generator=g) - 0.5))
+    ref["means"] = ref["means"] + 0.05 * torch.randn(ref["means"].shape, generator=g)
+    return case
+
+
 SHAPES = {
     "cfg1 two_modes d=2 EM K=100 B=2048": lambda: dict(T.case_em_two_modes("score"), B=2048),
     "cfg2 many_modes d=50 M=16 EI K=200 B=65536": lambda: T.case_ei_many_modes(K=200, B=65536),
@@ -67,6 +79,8 @@ SHAPES = {
     "small cfg2 many_modes d=50 M=16 EI K=200 B=8192": lambda: T.case_ei_many_modes(K=200, B=8192),
     "small cfg2 many_modes d=50 M=16 EI K=200 B=2048": lambda: T.case_ei_many_modes(K=200, B=2048),
     "small cfg2 many_modes d=50 M=16 EI K=200 B=512": lambda: T.case_ei_many_modes(K=200, B=512),
+    "fitted-ref cfg2 many_modes d=50 M=16 EI K=200 B=65536 (per-mode reference variances)": lambda: fitted_ref(65536),
+    "fitted-ref cfg2 many_modes d=50 M=16 EI K=200 B=8192 (per-mode reference variances)": lambda: fitted_ref(8192),
     "cfg3 phi4 d=100 PIS K=256 B=131072": lambda: T.case_pis_phi4(K=256, B=131072),
     "cfg3 phi4 d=100 DDS K=256 B=131072": dds256,
     "cfg4 logreg sonar d=61 CMCD K=100 B=262144": lambda: T.case_cmcd_logreg(166, 60, K=100, B=262144),
