@@ -5,7 +5,6 @@ score_gauss 124-126).  Densities and scores are evaluated by the CUDA library.""
 from __future__ import annotations
 
 import ctypes as C
-from numbers import Number
 
 import torch
 

@@ -20,7 +20,6 @@ gradient through the trajectory) raises.
 from __future__ import annotations
 
 import itertools
-import math
 from typing import Callable
 
 import torch
