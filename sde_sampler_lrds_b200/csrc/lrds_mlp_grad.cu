@@ -36,7 +36,7 @@ constexpr uint32_t MG_GROUP = 2048;  // 8 features x 128 rows x fp16: [row][8] w
 struct MgLayout {
   uint32_t tail, xbuf, gbuf, gstride, dbuf, xstage, cstage, bytes;
 };
-__host__ __device__ inline MgLayout mg_layout(const TcLayout& TL, int d) {
+__host__ __device__ inline MgLayout mg_layout(const TcLayout& TL, int d, bool staged) {
   MgLayout M;
   M.tail = TL.bytes;
   M.xbuf = (TL.bytes + TC_TAIL_BYTES + 127u) & ~127u;
@@ -44,7 +44,8 @@ __host__ __device__ inline MgLayout mg_layout(const TcLayout& TL, int d) {
   M.gstride = 9u * MG_GROUP;  // 8 feature groups + the block of ones
   M.dbuf = M.gbuf + (uint32_t)(TL.nh + 1) * M.gstride;
   M.xstage = M.dbuf + 8u * MG_GROUP;  // an A operand spans 16 groups from its start: always inside [xbuf, xstage)
-  const uint32_t stage = (128u * (uint32_t)d * 4u + 127u) & ~127u;  // one tile's rows of x / of the cotangents, as in global memory
+  // one tile's rows of x / of the cotangents, as in global memory (left out when they do not fit: d > 56)
+  const uint32_t stage = staged ? (128u * (uint32_t)d * 4u + 127u) & ~127u : 0u;
   M.cstage = M.xstage + stage;
   M.bytes = M.cstage + stage;
   return M;
@@ -77,6 +78,7 @@ struct MlpGradArgs {
   const float* cot_scale_dev;  // device copy of cot_scale (replaces it when given: no host round trip to choose it)
   int S, B, tiles_per_s;
   int64_t tiles;
+  int staged;         // the tile rows travel through the TMA staging areas
   float* part;        // [grid][P]
   float* dbias_part;  // [tiles * 4][64]
   int P;
@@ -116,12 +118,22 @@ __device__ __forceinline__ void split_pack(float a, float b, uint32_t& hi, uint3
   lo = ptx::pack_f16x2(l0, l1);
 }
 
+// GELU' lies in (-0.13, 1.13): two values per TMEM column as 16-bit fixed point (step 2^-15, absolute error 1.5e-5; an
+// fp16 pair would carry a RELATIVE 2.4e-4, which enters every delta upstream of the layer).  v + 256.25 has the 16 bits
+// round((v + 0.25) 2^15) at the bottom of its significand: one FADD and half a byte permute per value either way.
+__device__ __forceinline__ uint32_t pack_gp(float a, float b) {
+  return __byte_perm(__float_as_uint(a + 256.25f), __float_as_uint(b + 256.25f), 0x5410);
+}
+__device__ __forceinline__ float2 unpack_gp(uint32_t p) {
+  return make_float2(__uint_as_float(0x43800000u | (p & 0xFFFFu)) - 256.25f, __uint_as_float(0x43800000u | (p >> 16)) - 256.25f);
+}
+
 __global__ void __launch_bounds__(MG_THREADS, 1) mlp_grad_kernel(const MlpGradArgs a) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   uint8_t* const smem = smem_raw;
   const int d = a.mlp.d, dp = a.mlp.d_pad, nh = a.mlp.num_hidden;
   const TcLayout TL = tc_layout(d, nh, LRDS_PRECISION_F16X3);
-  const MgLayout ML = mg_layout(TL, d);
+  const MgLayout ML = mg_layout(TL, d, a.staged != 0);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, q = warp & 3, h = warp >> 2;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + ML.tail);  // [0] image, [1] MMA batches, [2] x rows, [3] cotangent rows
   uint32_t* slot = reinterpret_cast<uint32_t*>(smem + ML.tail + 48);
@@ -206,6 +218,16 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mlp_grad_kernel(const MlpGradAr
       ptx::mma_f16_ss(tmem + acc_col, ad, bd, idesc, accumulate | (ks > 0));
     }
   };
+  // this thread's 16 columns of delta as the B operand of the weight-gradient GEMM: one fp16 rounding (a second, (hi, lo)
+  // operand halves the rounding noise of the weight gradients at +22 % kernel time: measured, not kept)
+  auto store_delta = [&](const float (&dl)[16]) {
+    uint32_t pr[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) pr[i] = ptx::pack_f16x2(dl[2 * i], dl[2 * i + 1]);
+    uint8_t* db8 = smem + ML.dbuf + (uint32_t)(2 * h) * MG_GROUP + (uint32_t)rloc * 16u;
+    *reinterpret_cast<uint4*>(db8) = make_uint4(pr[0], pr[1], pr[2], pr[3]);
+    *reinterpret_cast<uint4*>(db8 + MG_GROUP) = make_uint4(pr[4], pr[5], pr[6], pr[7]);
+  };
   auto hand = [&](auto&& issue) {  // operands stored -> the batch is issued and committed to `bar`
     ptx::fence_proxy_async();
     ptx::tmem_wait_st();
@@ -244,7 +266,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mlp_grad_kernel(const MlpGradAr
   uint32_t phx = 0, phc = 0;
   auto tile_row0 = [&](int64_t tile) { return (tile / a.tiles_per_s) * (int64_t)a.B + (tile % a.tiles_per_s) * 128; };
   auto tile_fast = [&](int64_t tile) -> bool {
-    if ((int)(tile % a.tiles_per_s) * 128 + 128 > a.B) return false;
+    if (!a.staged || (int)(tile % a.tiles_per_s) * 128 + 128 > a.B) return false;
     const int64_t e0 = tile_row0(tile) * d;
     return ((reinterpret_cast<uintptr_t>(a.x + e0) | reinterpret_cast<uintptr_t>(a.cot + e0)) & 15u) == 0;
   };
@@ -328,7 +350,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mlp_grad_kernel(const MlpGradAr
           f2::unpack(g, ga, gb);
           split_pack(ga, gb, ph[2 * i + e], pl[2 * i + e]);
           pg[2 * i + e] = ptx::pack_f16x2(ga, gb);
-          pp[2 * i + e] = ptx::pack_f16x2(da, db);
+          pp[2 * i + e] = pack_gp(da, db);
         }
       }
       ptx::tmem_st8(tm_lane + MG_A_HI + 8 * h, ph);
@@ -368,17 +390,12 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mlp_grad_kernel(const MlpGradAr
         const float c = cv[i] * wgt;
         dl[i] = (a.clip > 0.f && !(fabsf(net) <= a.clip)) ? 0.f : c;
       }
-      uint32_t ph[8], pl[8], pr[8];
+      uint32_t ph[8], pl[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        split_pack(dl[2 * i], dl[2 * i + 1], ph[i], pl[i]);
-        pr[i] = ptx::pack_f16x2(dl[2 * i], dl[2 * i + 1]);
-      }
+      for (int i = 0; i < 8; ++i) split_pack(dl[2 * i], dl[2 * i + 1], ph[i], pl[i]);
       ptx::tmem_st8(tm_lane + MG_A_HI + 8 * h, ph);
       ptx::tmem_st8(tm_lane + MG_A_LO + 8 * h, pl);
-      uint8_t* db8 = smem + ML.dbuf + (uint32_t)(2 * h) * MG_GROUP + (uint32_t)rloc * 16u;
-      *reinterpret_cast<uint4*>(db8) = make_uint4(pr[0], pr[1], pr[2], pr[3]);
-      *reinterpret_cast<uint4*>(db8 + MG_GROUP) = make_uint4(pr[4], pr[5], pr[6], pr[7]);
+      store_delta(dl);
     }
     {
       const uint32_t acc0 = first ? 0u : 1u;
@@ -402,11 +419,10 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mlp_grad_kernel(const MlpGradAr
       float dl[16];
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        const float2 gd = __half22float2(*reinterpret_cast<const __half2*>(&gp[i]));
+        const float2 gd = unpack_gp(gp[i]);
         dl[2 * i] = __uint_as_float(rr[2 * i]) * ub * gd.x;
         dl[2 * i + 1] = __uint_as_float(rr[2 * i + 1]) * ub * gd.y;
       }
-      uint32_t pr[8];
       if (l > 1) {
         uint32_t ph[8], pl[8];
 #pragma unroll
@@ -414,11 +430,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mlp_grad_kernel(const MlpGradAr
         ptx::tmem_st8(tm_lane + MG_A_HI + 8 * h, ph);
         ptx::tmem_st8(tm_lane + MG_A_LO + 8 * h, pl);
       }
-#pragma unroll
-      for (int i = 0; i < 8; ++i) pr[i] = ptx::pack_f16x2(dl[2 * i], dl[2 * i + 1]);
-      uint8_t* db8 = smem + ML.dbuf + (uint32_t)(2 * h) * MG_GROUP + (uint32_t)rloc * 16u;
-      *reinterpret_cast<uint4*>(db8) = make_uint4(pr[0], pr[1], pr[2], pr[3]);
-      *reinterpret_cast<uint4*>(db8 + MG_GROUP) = make_uint4(pr[4], pr[5], pr[6], pr[7]);
+      store_delta(dl);
       const uint32_t acc0 = first ? 0u : 1u;
       if (l > 1) {
         hand([&] {
@@ -554,7 +566,11 @@ int launch_mlp_grad(const lrds_mlp& mlp, const float* bias1, const float* x, con
   a.part = scratch;
   a.dbias_part = scratch + (int64_t)grid * a.P;
   const TcLayout TL = tc_layout(mlp.d, mlp.num_hidden, LRDS_PRECISION_F16X3);
-  const MgLayout ML = mg_layout(TL, mlp.d);
+  int dev = 0, cap = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&cap, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  a.staged = mg_layout(TL, mlp.d, true).bytes <= (uint32_t)cap;
+  const MgLayout ML = mg_layout(TL, mlp.d, a.staged != 0);
   cudaError_t e = cudaFuncSetAttribute(mlp_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ML.bytes);
   if (e == cudaSuccess) {
     mlp_grad_kernel<<<grid, MG_THREADS, ML.bytes, st>>>(a);
