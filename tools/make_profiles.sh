@@ -17,6 +17,8 @@ hdr "MALA kernel (mala_kernel), mcmc_sample defaults over ManyModes d = 50" \
     "ncu --set full ... -k regex:mala_kernel -s 1 -c 1 python tools/mala_bench.py" gpurun_out/mala_summary.md profiles/${R}_mala_summary.md
 hdr "weight-gradient kernel (mlp_grad_kernel: forward recompute, backward-data and weight-gradient GEMMs on tcgen05), 13.1 M rows, d = 50" \
     "ncu --set full ... -k regex:mlp_grad_kernel -s 1 -c 1 python tools/mlp_grad_bench.py" gpurun_out/mlp_grad_summary.md profiles/${R}_mlp_grad_summary.md
+hdr "score-cotangent reduction kernel (score_cot_kernel), 13.1 M rows, ManyModes d = 50" \
+    "ncu --set full ... -k regex:score_cot_kernel -s 2 -c 1 python tools/score_cot_bench.py" gpurun_out/score_cot_summary.md profiles/${R}_score_cot_summary.md
 python - "$R" <<'PY'
 import csv, collections, sys
 R=sys.argv[1]

@@ -18,6 +18,8 @@ $T 400 ncu --set full --clock-control none --import-source on -k regex:mala_kern
 tools/prof_report.sh gpurun_out/prof_mala_final.ncu-rep lrds_capi mala_kernel 30 > gpurun_out/mala_summary.md 2>&1; rm -f gpurun_out/prof_mala_final.ncu-rep
 $T 400 ncu --set full --clock-control none --import-source on -k regex:mlp_grad_kernel -s 1 -c 1 -o gpurun_out/prof_mlp_grad_final -f python tools/mlp_grad_bench.py > gpurun_out/ncu_mlp_grad.log 2>&1; echo "ncu mlp_grad rc=$?"
 tools/prof_report.sh gpurun_out/prof_mlp_grad_final.ncu-rep lrds_mlp_grad mlp_grad_kernel 30 > gpurun_out/mlp_grad_summary.md 2>&1; rm -f gpurun_out/prof_mlp_grad_final.ncu-rep
+$T 300 ncu --set full --clock-control none --import-source on -k regex:score_cot_kernel -s 2 -c 1 -o gpurun_out/prof_sc_final -f python tools/score_cot_bench.py > gpurun_out/ncu_sc.log 2>&1; echo "ncu score_cot rc=$?"
+tools/prof_report.sh gpurun_out/prof_sc_final.ncu-rep lrds_capi score_cot_kernel 25 > gpurun_out/score_cot_summary.md 2>&1; rm -f gpurun_out/prof_sc_final.ncu-rep
 $T 200 python tools/mlp_grad_bench.py --json gpurun_out/mlp_grad_bench.json > gpurun_out/mlp_grad_bench.log 2>&1; echo "mlp_grad bench rc=$?"
 $T 400 python tools/train_bench.py --cpu-batch 512 --json gpurun_out/train_bench_final.json > gpurun_out/train_bench_final.log 2>&1; echo "train bench rc=$?"
 $T 200 python tools/train_phases.py --json gpurun_out/train_phases.json > gpurun_out/train_phases.log 2>&1; echo "train phases rc=$?"
