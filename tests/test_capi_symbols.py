@@ -97,3 +97,20 @@ def test_mixture_tensor_core_image_layout():
     logc_sh = -0.5 * torch.log(var_sh).sum(-1) + torch.log(w / w.sum())
     img2 = gmm_mix_tc_image(loc[0], var_sh, dp, logc_sh)
     assert img2[-16:].view(torch.float32)[3].item() == 1.0
+
+
+def test_gradient_kernel_size_queries_without_a_gpu():
+    """lrds_mlp_grad_floats / _scratch_floats are host-only queries: the layout of lrds_mlp's weight blocks, and
+    LRDS_ERR_UNSUPPORTED (-2) for shapes the kernel is not built for (d > 64, more than two hidden layers)."""
+    from sde_sampler_lrds_b200 import _native as N
+    from sde_sampler_lrds_b200.train import pow2_scale
+    L = N.lib()
+    assert L.lrds_mlp_grad_floats(50, 2) == 50 * 64 + 2 * 64 * 64 + 2 * 64 + 64 * 56 + 56
+    assert L.lrds_mlp_grad_floats(2, 0) == 2 * 64 + 64 * 8 + 8
+    assert L.lrds_mlp_grad_floats(65, 2) == -2 and L.lrds_mlp_grad_floats(50, 3) == -2
+    assert L.lrds_mlp_grad_scratch_floats(65, 2, 4, 4) == -2
+    # power-of-two operand scale: bound * scale in (2, 4]
+    for b in (1e-6, 0.3, 4.0, 777.0):
+        s = pow2_scale(b)
+        assert 2.0 < b * s <= 4.0 and s == 2.0 ** round(__import__("math").log2(s))
+    assert pow2_scale(0.0) == 1.0 and pow2_scale(float("inf")) == 1.0
