@@ -9,6 +9,7 @@
 
 #include "lrds_internal.h"
 #include "lrds_rollout_simt.cuh"
+#include "lrds_rollout_mix.cuh"  // gmm_pass1_pair: the quadratic forms of two particles per operand load
 
 namespace {
 
@@ -412,7 +413,18 @@ __device__ __forceinline__ void score_cot_body(const lrds_spec& s, const lrds::G
   const int tid = threadIdx.x, NT = blockDim.x;
   const int d = s.d, dp = s.mlp.d_pad;
   float* mine = rows + tid * ld;  // this thread's row of the staged cotangents; the products replace them in place
-  target_pass1<SH>(s, s.target.kind, tv, P, false);
+  if (SH && s.target.kind == LRDS_DISTR_GMM && s.target.gmm.M <= MIX_MAX_M) {
+    // the responsibilities with every (1/sigma, -mu/sigma) vector serving two particles (lrds_rollout_mix.cuh): this
+    // kernel is bound by the shared-memory data pipe, not by the FMA pipe
+    float r[MIX_MAX_M];
+    gmm_pass1_pair(tv, d, dp, P.x, r);
+    const int M4 = (s.target.gmm.M + 3) / 4;
+#pragma unroll
+    for (int mb = 0; mb < MIX_MAX_M / 4; ++mb)
+      if (mb < M4) P.rt.st4(mb, make_float4(r[4 * mb], r[4 * mb + 1], r[4 * mb + 2], r[4 * mb + 3]));
+  } else {
+    target_pass1<SH>(s, s.target.kind, tv, P, false);
+  }
   float xm = 0.f;
   for (int j0 = 0; j0 < dp; j0 += JC) {
     float xr[JC], ts[JC];
