@@ -45,7 +45,7 @@ rollout_mix_small_kernel(const RolloutArgs a, const uint8_t* __restrict__ image)
   const int ptid = tid & 127;  // particle within the tile = TMEM lane
   constexpr int NT = 128;
   uint8_t* img = smem_raw;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + TL.bytes);  // [0] image, [1] MMAs of the tile done
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + TL.bytes);  // [0] image, [1] MMAs of the tile done, [2] the logits of a step
   uint32_t* slot = reinterpret_cast<uint32_t*>(smem_raw + TL.bytes + 48);
   uint32_t* cnts = reinterpret_cast<uint32_t*>(smem_raw + TL.bytes + TC_TAIL_BYTES);  // [0] hand-offs, [4 + i] step buffer i released
   uint8_t* stage = smem_raw + TL.bytes + TC_TAIL_BYTES + MIX_TAIL_BYTES;
@@ -71,6 +71,7 @@ rollout_mix_small_kernel(const RolloutArgs a, const uint8_t* __restrict__ image)
   if (tid == 0) {
     ptx::mbar_init(bars, 1);
     ptx::mbar_init(bars + 1, 1);
+    ptx::mbar_init(bars + 2, 1);
     ptx::mbar_init(sbar, 1);
     ptx::mbar_init(sbar + 1, 1);
     for (int i = 0; i < 6; ++i) cnts[i] = 0u;
@@ -129,6 +130,7 @@ rollout_mix_small_kernel(const RolloutArgs a, const uint8_t* __restrict__ image)
 #endif
   mlp.tm.start();
 
+  uint32_t lphase = 0;  // parity of the logit barrier (waited for by the threads that own a mixture)
   for (int k = 0; k < K; ++k) {
     __syncthreads();  // the step's x is complete and visible to the four threads of every particle
     ptx::mbar_wait(sbar + (k & 1), (uint32_t)(k >> 1) & 1u);
@@ -161,10 +163,12 @@ rollout_mix_small_kernel(const RolloutArgs a, const uint8_t* __restrict__ image)
     const PPtr<true> tail{(sub == 0 ? tgt_img : ref_img) + lg_tail_off};
     const PPtr<true> tail_t{tgt_img + lg_tail_off}, tail_r{ref_img + lg_tail_off};
     const bool lg_t = tail_t.ld1(MIX_MAX_M + 3) != 0.f, lg_r = tail_r.ld1(MIX_MAX_M + 3) != 0.f;  // CTA-uniform
-    // ONE batch: the logits of both mixtures (own columns) and the network's first GEMM
+    // ONE hand-off: the logits of both mixtures (own columns, committed to their own mbarrier: they complete first and
+    // the softmax of the threads that own them overlaps the MMAs of the network's first GEMM), then that GEMM
     mlp.arrive_issue([&]() {
       if (lg_t) mlp.logit(0, tgt_img + contr_bytes, (int)MIXS_LOGIT_COL);
       if (lg_r) mlp.logit(1, ref_img + contr_bytes, (int)MIXS_LOGIT_COL);
+      ptx::mma_commit(bars + 2);
       mlp.gemm(TL.off_in, TL.Kin, C);
     });
     mlp.tm.mark(2);
@@ -178,7 +182,11 @@ rollout_mix_small_kernel(const RolloutArgs a, const uint8_t* __restrict__ image)
       }
       xnorm = sqrtf(f2::hsum1(n2));
     }
-    mlp.wait();
+    if (sub < 2) {  // warps 0 .. 7: one wait per step and commit, so the parity never runs ahead of a waiter
+      ptx::mbar_wait(bars + 2, lphase);
+      lphase ^= 1u;
+      ptx::tc_fence_after();
+    }
     mlp.tm.mark(3);
     if (sub < 2 && (sub == 0 ? lg_t : lg_r)) {
       uint32_t lg[16];
@@ -206,8 +214,8 @@ rollout_mix_small_kernel(const RolloutArgs a, const uint8_t* __restrict__ image)
       if (l > 0) {
         if (l == 1) noise_chunk(a, k, b, sub * JC, z0);
         else if (l == 2 && two) noise_chunk(a, k, b, (sub + MIXS_TP) * JC, z1);
-        mlp.wait();
       }
+      mlp.wait();  // l == 0: the first GEMM, issued behind the logits
       mlp.tm.mark(7);
       if (l == 0) mlp.template epilogue_f16_16<false>(row + LRDS_STEP_BIAS1, 0, 16 * sub);
       else mlp.template epilogue_f16_16<false>(bh + (l - 1) * C, l, 16 * sub);
