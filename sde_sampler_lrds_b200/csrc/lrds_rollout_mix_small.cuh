@@ -45,7 +45,7 @@ rollout_mix_small_kernel(const RolloutArgs a, const uint8_t* __restrict__ image)
   const int ptid = tid & 127;  // particle within the tile = TMEM lane
   constexpr int NT = 128;
   uint8_t* img = smem_raw;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + TL.bytes);  // [0] image, [1] MMAs of the tile done, [2] the logits of a step
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + TL.bytes);  // [0] image, [1] MMAs of the tile done, [2] the logits of a step, [3] the first contraction chunk of every thread
   uint32_t* slot = reinterpret_cast<uint32_t*>(smem_raw + TL.bytes + 48);
   uint32_t* cnts = reinterpret_cast<uint32_t*>(smem_raw + TL.bytes + TC_TAIL_BYTES);  // [0] hand-offs, [4 + i] step buffer i released
   uint8_t* stage = smem_raw + TL.bytes + TC_TAIL_BYTES + MIX_TAIL_BYTES;
@@ -72,6 +72,7 @@ rollout_mix_small_kernel(const RolloutArgs a, const uint8_t* __restrict__ image)
     ptx::mbar_init(bars, 1);
     ptx::mbar_init(bars + 1, 1);
     ptx::mbar_init(bars + 2, 1);
+    ptx::mbar_init(bars + 3, 1);
     ptx::mbar_init(sbar, 1);
     ptx::mbar_init(sbar + 1, 1);
     for (int i = 0; i < 6; ++i) cnts[i] = 0u;
@@ -131,6 +132,7 @@ rollout_mix_small_kernel(const RolloutArgs a, const uint8_t* __restrict__ image)
   mlp.tm.start();
 
   uint32_t lphase = 0;  // parity of the logit barrier (waited for by the threads that own a mixture)
+  uint32_t cphase = 0;  // parity of the first-chunks barrier
   for (int k = 0; k < K; ++k) {
     __syncthreads();  // the step's x is complete and visible to the four threads of every particle
     ptx::mbar_wait(sbar + (k & 1), (uint32_t)(k >> 1) & 1u);
@@ -228,17 +230,29 @@ rollout_mix_small_kernel(const RolloutArgs a, const uint8_t* __restrict__ image)
     mlp.wait();
     mlp.tm.mark(9);
     if (sub < 2) mlp.store_r(sub, r_p);
-    mlp.arrive_issue([&]() {  // the whole contraction in one batch: chunk c -> columns 128 + 32 c
-      for (int c = 0; c < nchunk; ++c) mlp.template chunk<true, true>(c, tgt_img, ref_img, MIXS_CHUNK_COL + 32u * (uint32_t)c);
+    mlp.arrive_issue([&]() {  // the whole contraction in one hand-off: chunk c -> columns 128 + 32 c; the chunks the
+      // threads take first are committed to their own mbarrier and are consumed while the others are still in the pipe
+      for (int c = 0; c < nchunk; ++c) {
+        if (c == MIXS_TP) ptx::mma_commit(bars + 3);
+        mlp.template chunk<true, true>(c, tgt_img, ref_img, MIXS_CHUNK_COL + 32u * (uint32_t)c);
+      }
+      if (nchunk <= MIXS_TP) ptx::mma_commit(bars + 3);
     });
     const u64 A2 = f2::pk(A), B2 = f2::pk(Bc), C2 = f2::pk(Cc), usr2 = f2::pk(usr);
     const u64 gs2 = f2::pk((cc.scale_score * gamma) * ust);
     const float bts = cc.bound_score / ust;
     u64 su2 = 0, sito = 0;
     mlp.tm.mark(10);
-    mlp.wait();
+    ptx::mbar_wait(bars + 3, cphase);
+    cphase ^= 1u;
+    ptx::tc_fence_after();
     mlp.tm.mark(11);
+    bool waited = false;  // the hand-off's second commit (the tile barrier): once per step in every thread
     for (int c = sub, ci = 0; c < nchunk; c += MIXS_TP, ++ci) {
+      if (ci == 1) {
+        mlp.wait();
+        waited = true;
+      }
       const int j0 = c * JC;
       uint32_t m[32];
       ptx::tmem_ld32(mlp.tm_lane + MIXS_CHUNK_COL + 32u * (uint32_t)c, m);
@@ -281,6 +295,7 @@ rollout_mix_small_kernel(const RolloutArgs a, const uint8_t* __restrict__ image)
         store_traj(a, k + 1, b, j0, xn);
       }
     }
+    if (!waited) mlp.wait();  // threads with a single chunk (or none)
     rnd += wcost * f2::hsum1(su2);
     rnd += wito * f2::hsum1(sito);
     __syncwarp();
